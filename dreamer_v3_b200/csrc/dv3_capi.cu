@@ -1,0 +1,196 @@
+// extern "C" surface of libdv3.so (include/dv3.h).
+#include <cstring>
+#include <new>
+
+#include "dv3_engine.h"
+
+using dv3::Engine;
+
+struct dv3_engine {
+  Engine e;
+};
+
+static std::string g_create_error;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static int check_async(Engine& e) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return e.fail(std::string("CUDA error: ") + cudaGetErrorString(err));
+  return 0;
+}
+
+extern "C" {
+
+int dv3_abi_version(void) { return DV3_ABI_VERSION; }
+
+int dv3_create(const dv3_config* cfg, dv3_engine** out) {
+  if (cfg == nullptr || out == nullptr) { g_create_error = "null argument"; return -1; }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    g_create_error = "no CUDA device: libdv3 has no CPU path";
+    return -2;
+  }
+  dv3_engine* h = new (std::nothrow) dv3_engine();
+  if (!h) { g_create_error = "out of host memory"; return -1; }
+  const int rc = h->e.init(cfg);
+  if (rc != 0) {
+    g_create_error = h->e.err;
+    h->e.destroy();
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+int dv3_destroy(dv3_engine* h) {
+  if (!h) return 0;
+  h->e.destroy();
+  delete h;
+  return 0;
+}
+
+const char* dv3_last_error(const dv3_engine* h) { return h ? h->e.err.c_str() : g_create_error.c_str(); }
+
+void dv3_default_hparams(dv3_hparams* hp) {
+  std::memset(hp, 0, sizeof(*hp));
+  hp->gamma = 0.997f; hp->lambda_ = 0.95f; hp->entropy_scale = 3e-4f; hp->return_normalization_decay = 0.99f;
+  hp->wm_grad_clip = 1000.f; hp->actor_grad_clip = 100.f; hp->critic_grad_clip = 100.f;
+  hp->wm_lr = 1e-4f; hp->wm_eps = 1e-8f; hp->ac_lr = 3e-5f; hp->ac_eps = 1e-5f;
+  hp->critic_ema_decay = 0.98f; hp->train_actor = 1;
+}
+
+int dv3_sync(dv3_engine* h, void* stream) {
+  cudaError_t err = cudaStreamSynchronize(S(stream));
+  if (err != cudaSuccess) return h->e.fail(std::string("cudaStreamSynchronize: ") + cudaGetErrorString(err));
+  return 0;
+}
+
+int dv3_num_tensors(const dv3_engine* h) { return (int)h->e.tensors.size(); }
+
+static void fill_desc(const dv3::TensorEntry& t, dv3_tensor_desc* out) {
+  out->name = t.name.c_str(); out->ptr = t.ptr; out->dtype = t.dtype; out->ndim = (int)t.shape.size();
+  for (int i = 0; i < 6; ++i) out->shape[i] = i < (int)t.shape.size() ? t.shape[i] : 1;
+  out->kind = t.kind; out->group = t.group;
+}
+int dv3_tensor_info(const dv3_engine* h, int index, dv3_tensor_desc* out) {
+  if (index < 0 || index >= (int)h->e.tensors.size()) return -1;
+  fill_desc(h->e.tensors[index], out);
+  return 0;
+}
+int dv3_find_tensor(const dv3_engine* h, const char* name, dv3_tensor_desc* out) {
+  auto it = h->e.index.find(name);
+  if (it == h->e.index.end()) return -1;
+  fill_desc(h->e.tensors[it->second], out);
+  return 0;
+}
+int dv3_write_tensor(dv3_engine* h, const char* name, const void* src, size_t nbytes, int src_is_device, void* stream, int sync) {
+  auto it = h->e.index.find(name);
+  if (it == h->e.index.end()) return h->e.fail(std::string("unknown tensor ") + name);
+  const auto& t = h->e.tensors[it->second];
+  if (nbytes != t.bytes) return h->e.fail(std::string("size mismatch writing ") + name + ": got " + std::to_string(nbytes) + ", expected " + std::to_string(t.bytes));
+  cudaError_t err = cudaMemcpyAsync(t.ptr, src, nbytes, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, S(stream));
+  if (err == cudaSuccess && sync) err = cudaStreamSynchronize(S(stream));
+  if (err != cudaSuccess) return h->e.fail(std::string("copy failed: ") + cudaGetErrorString(err));
+  return 0;
+}
+int dv3_read_tensor(dv3_engine* h, const char* name, void* dst, size_t nbytes, int dst_is_device, void* stream, int sync) {
+  auto it = h->e.index.find(name);
+  if (it == h->e.index.end()) return h->e.fail(std::string("unknown tensor ") + name);
+  const auto& t = h->e.tensors[it->second];
+  if (nbytes != t.bytes) return h->e.fail(std::string("size mismatch reading ") + name);
+  cudaError_t err = cudaMemcpyAsync(dst, t.ptr, nbytes, dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, S(stream));
+  if (err == cudaSuccess && sync) err = cudaStreamSynchronize(S(stream));
+  if (err != cudaSuccess) return h->e.fail(std::string("copy failed: ") + cudaGetErrorString(err));
+  return 0;
+}
+int dv3_group_buffer(const dv3_engine* h, int group, int kind, void** ptr, int64_t* numel) {
+  if (group < 0 || group > 3 || kind < 0 || kind > 3 || (group == 3 && kind != 0)) return -1;
+  const Engine& e = h->e;
+  float* p = kind == 0 ? e.params[group] : kind == 1 ? e.grads[group] : kind == 2 ? e.adam_m[group] : e.adam_v[group];
+  *ptr = p; *numel = e.numel[group];
+  return 0;
+}
+
+int dv3_fill_noise(dv3_engine* h, uint64_t seed, uint64_t step, int which, void* stream) {
+  h->e.fill_noise(seed, step, which, false, S(stream));
+  return check_async(h->e);
+}
+int dv3_initial_state(dv3_engine* h, void* stream) { h->e.initial_state(S(stream)); return check_async(h->e); }
+int dv3_observe_forward(dv3_engine* h, void* stream) { int rc = h->e.observe_forward(S(stream)); return rc ? rc : check_async(h->e); }
+int dv3_wm_loss_backward(dv3_engine* h, void* stream) { int rc = h->e.wm_loss_backward(S(stream)); return rc ? rc : check_async(h->e); }
+int dv3_optimizer_step(dv3_engine* h, int group, float clip, float lr, float eps, float ema_decay, void* stream) {
+  int rc = h->e.optimizer_step(group, clip, lr, eps, ema_decay, S(stream));
+  return rc ? rc : check_async(h->e);
+}
+int dv3_train_world_model_step(dv3_engine* h, const dv3_hparams* hp, void* stream) {
+  int rc = h->e.train_wm(hp, S(stream));
+  return rc ? rc : check_async(h->e);
+}
+int dv3_dream_forward(dv3_engine* h, float gamma, int start_from_observe, void* stream) {
+  int rc = h->e.dream_forward(gamma, start_from_observe, S(stream));
+  return rc ? rc : check_async(h->e);
+}
+int dv3_ac_loss_backward(dv3_engine* h, const dv3_hparams* hp, int phase, void* stream) {
+  int rc = h->e.ac_loss_backward(hp, phase, S(stream));
+  return rc ? rc : check_async(h->e);
+}
+int dv3_critic_init_ema(dv3_engine* h, void* stream) {
+  cudaMemcpyAsync(h->e.params[3], h->e.params[2], (size_t)h->e.numel[2] * 4, cudaMemcpyDeviceToDevice, S(stream));
+  return check_async(h->e);
+}
+int dv3_critic_update_ema(dv3_engine* h, float decay, void* stream) {
+  dv3::ema_update(S(stream), h->e.params[3], h->e.params[2], h->e.numel[2], decay);
+  return check_async(h->e);
+}
+int dv3_train_actor_critic_step(dv3_engine* h, const dv3_hparams* hp, void* stream) {
+  int rc = h->e.train_ac(hp, S(stream));
+  return rc ? rc : check_async(h->e);
+}
+int dv3_train_update(dv3_engine* h, const dv3_hparams* hp, uint64_t noise_seed, int use_graph, void* stream) {
+  int rc = h->e.train_update(hp, noise_seed, use_graph, S(stream));
+  return rc ? rc : check_async(h->e);
+}
+int64_t dv3_kernel_launch_count(const dv3_engine*) { return dv3::g_launches; }
+
+// ---- isolated ops ---------------------------------------------------------------------------------------------
+static int op_done() { return cudaGetLastError() == cudaSuccess ? 0 : -1; }
+int dv3_op_symlog(const float* x, float* y, int64_t n, void* stream) { dv3::symlog_fwd(S(stream), x, y, n); return op_done(); }
+int dv3_op_inverse_symlog(const float* y, float* x, int64_t n, void* stream) { dv3::inverse_symlog_fwd(S(stream), y, x, n); return op_done(); }
+int dv3_op_two_hot(const float* value, int64_t n, int32_t* k, int32_t* kp1, float* w_k, float* w_kp1, float* dense, void* stream) {
+  dv3::two_hot_op(S(stream), value, n, k, kp1, w_k, w_kp1, dense);
+  return op_done();
+}
+int dv3_op_sample_categorical(const float* probs, const float* u, int64_t rows, int K, int32_t* idx, void* stream) {
+  if (K > 32 || K < 1) return -1;
+  dv3::sample_categorical_op(S(stream), probs, u, rows, K, idx);
+  return op_done();
+}
+int dv3_op_value_targets(const float* r, const float* c, const float* v, int H, int64_t N, float gamma, float lambda_, float* targets, void* stream) {
+  dv3::value_targets_raw(S(stream), r, c, v, H, (int)N, gamma, lambda_, targets);
+  return op_done();
+}
+int dv3_op_percentiles(const float* x, int64_t n, float* p5_p95, void* stream) {
+  float* ema = nullptr;
+  if (cudaMalloc((void**)&ema, 8) != cudaSuccess) return -1;
+  const float nanv[2] = {NAN, NAN};
+  cudaMemcpyAsync(ema, nanv, 8, cudaMemcpyHostToDevice, S(stream));
+  dv3::percentile_ema(S(stream), x, n, 0.99f, ema, p5_p95, nullptr);
+  cudaStreamSynchronize(S(stream));
+  cudaFree(ema);
+  return op_done();
+}
+int dv3_op_gemm(const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C, int ldc, int M, int N, int K,
+                const float* bias, float beta, int mode, void* stream) {
+  dv3::GemmArgs g{A, lda, ta, B, ldb, tb, C, ldc, M, N, K, bias, beta};
+  dv3::gemm_dispatch(S(stream), g, mode);
+  return op_done();
+}
+int dv3_op_ln_silu(const float* x, const float* gamma, const float* beta, float* y, int64_t rows, int D, void* stream) {
+  if (D > 1024) return -1;
+  dv3::ln_silu_fwd(S(stream), x, D, gamma, beta, y, D, nullptr, nullptr, 1, rows, D);
+  return op_done();
+}
+
+}  // extern "C"

@@ -1,0 +1,192 @@
+// Internal declarations shared by the kernel translation units and the engine.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define DV3_NB 255            // reward / value buckets
+#define DV3_BUCKET_LO (-20.0f)
+#define DV3_BUCKET_HI (20.0f)
+#define DV3_LN_EPS 1e-3f      // Keras LayerNormalization default
+
+namespace dv3 {
+
+// Number of kernels this library has launched (dv3_kernel_launch_count).
+extern long long g_launches;
+inline void count_launch(int n = 1) { g_launches += n; }
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// C[M,N] (+)= op(A)[M,K] * op(B)[K,N] (+ bias[N])
+//   op(A)(m,k) = ta ? A[k*lda + m] : A[m*lda + k]
+//   op(B)(k,n) = tb ? B[n*ldb + k] : B[k*ldb + n]
+struct GemmArgs {
+  const float* A; int lda; int ta;
+  const float* B; int ldb; int tb;
+  float* C; int ldc;
+  int M, N, K;
+  const float* bias;  // nullable, added once
+  float beta;         // 0 -> overwrite, 1 -> accumulate into C
+};
+
+// ---- gemm (dv3_gemm.cu) ----------------------------------------------------------------------
+void gemm_f32(cudaStream_t s, const GemmArgs& g);
+// mode 0: always fp32 SIMT; mode 1: bf16 tcgen05 tensor cores for large contractions (dv3_gemm_tc.cu)
+void gemm_dispatch(cudaStream_t s, const GemmArgs& g, int mode);
+
+// ---- elementwise / normalisation / recurrent cells (dv3_elem.cu) ---------------------------------
+void symlog_fwd(cudaStream_t s, const float* x, float* y, long long n);
+void inverse_symlog_fwd(cudaStream_t s, const float* y, float* x, long long n);
+void fill_f32(cudaStream_t s, float* p, float v, long long n);
+void zero_2d(cudaStream_t s, float* p, int rows, int cols, int ld);
+void copy_2d(cudaStream_t s, const float* src, int lds, float* dst, int ldd, int rows, int cols);
+void add_2d(cudaStream_t s, const float* src, int lds, float* dst, int ldd, int rows, int cols);  // dst += src
+void tanh_fwd(cudaStream_t s, const float* x, float* y, int n);
+
+// y = silu(LayerNorm(x)); saves mean/rstd per row. Rows addressed as x + r*ldx.
+void ln_silu_fwd(cudaStream_t s, const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy,
+                 float* mean, float* rstd, int sstride, long long rows, int D);
+// dx = d(silu(LN(x)))/dx * dy; dgamma/dbeta accumulated with atomics when non-null.
+void ln_silu_bwd(cudaStream_t s, const float* dy, int lddy, const float* x, int ldx, const float* mean,
+                 const float* rstd, const float* gamma, const float* beta, float* dx, int lddx, float* dgamma,
+                 float* dbeta, int sstride, long long rows, int D);
+
+// Keras GRU (reset_after=True, gates z,r,h). gx/gh hold x*K+b0 and h*U+b1 ([M,3G]); on return gx holds
+// (z, r, c) for the backward pass. h_out may alias nothing.
+void gru_fwd(cudaStream_t s, float* gx, int ldgx, const float* gh, int ldgh, const float* h_prev, int ldhp,
+             float* h_out, int ldho, int M, int G);
+// gates = (z,r,c) as left by gru_fwd, gh as in forward. Produces dgx, dgh ([M,3G]) and dh_prev (=dh*z,
+// overwritten or accumulated).
+void gru_bwd(cudaStream_t s, const float* dh, int lddh, const float* gates, int ldg, const float* gh, int ldgh,
+             const float* h_prev, int ldhp, float* dgx, int lddgx, float* dgh, int lddgh, float* dh_prev, int lddhp,
+             int accumulate_dh_prev, int M, int G);
+
+// RepresentationLayer (components/representation_layer.py:73-113): logits [M, Zc*Zk] -> unimixed probs,
+// optional sample (u [M,Zc] row stride ldu) -> idx [M,Zc] + one-hot z (row stride ldz). mode: 0 = probs only,
+// 1 = sample with u, 2 = argmax (get_initial_state).
+void repr_fwd(cudaStream_t s, const float* logits, int ldl, float* probs, int ldp, const float* u, int ldu,
+              int32_t* idx, int ldi, float* z, int ldz, int M, int Zc, int Zk, int mode);
+// dlogits = J_softmax^T (0.99 * (dz + dprobs)); dz / dprobs nullable.
+void repr_bwd(cudaStream_t s, const float* logits, int ldl, const float* dz, int lddz, const float* dprobs, int lddp,
+              float* dlogits, int lddl, int M, int Zc, int Zk);
+
+// observe-scan helpers
+// Builds the masked recurrent inputs of step t (world_model.py:246-253).
+void scan_mask_inputs(cudaStream_t s, const float* is_first, int ldf, const float* h_prev, int ldhp,
+                      const float* z_prev, int ldzp, const float* h0, const float* z0, const float* actW, int ldaw,
+                      float* h_in, int ldhi, float* z_in, int ldzi, float* x_pre, int ldx, int B, int G, int Z, int D);
+// d_out += (1-f) * d_in (rows): passes gradients to the previous step.
+void scan_mask_grads(cudaStream_t s, const float* is_first, int ldf, const float* d_in, int ldin, float* d_out,
+                     int ldout, int B, int W);
+
+void colsum_acc(cudaStream_t s, const float* x, int ld, long long rows, int cols, float* out);
+void scan_prepare(cudaStream_t s, const float* actions, const float* is_first, float* a_in, float* wf, int B, int T, int A);
+void tanh_bwd_acc(cudaStream_t s, const float* dh0, const float* h0, float* dinit, int n);
+
+// ---- conv helpers (dv3_conv.cu): 4x4 stride-2 "same" ------------------------------------------------
+// cols[(n,oy,ox), (ky,kx,c)] = img[n, 2oy-1+ky, 2ox-1+kx, c] (0 outside); img NHWC [n,H,W,C], out H/2 x W/2
+void im2col_k4s2(cudaStream_t s, const float* img, float* cols, int n, int H, int W, int C);
+// img[n,y,x,c] (+)= sum over the (<=4) patches covering (y,x) of cols[(n,oy,ox),(ky,kx,c)] + bias[c] + add_const
+void col2im_k4s2(cudaStream_t s, const float* cols, float* img, int n, int H, int W, int C, const float* bias,
+                 float add_const);
+
+// ---- losses (dv3_loss.cu) -----------------------------------------------------------------------------
+void two_hot_op(cudaStream_t s, const float* v, long long n, int32_t* k, int32_t* kp1, float* wk, float* wkp1,
+                float* dense);
+// E[bucket] under softmax(logits) per row (reward_predictor_layer.py:84-99)
+void bucket_expectation(cudaStream_t s, const float* logits, int ldl, float* out, long long rows);
+// dlogits = dE * p * (bucket - E)   (backward of bucket_expectation), overwrite
+void bucket_expectation_bwd(cudaStream_t s, const float* logits, int ldl, const float* dE, float* dlogits, int lddl,
+                            long long rows);
+void sample_categorical_op(cudaStream_t s, const float* probs, const float* u, long long rows, int K, int32_t* idx);
+
+struct WmLossArgs {
+  int B, T, Z, Zc, Zk, obs_flat;
+  float inv_count;  // 1 / (world_size * B * T)
+  const float* obs;            // [N, obs_flat] (symlog'ed if enabled)
+  const float* loc;            // [N, obs_flat]
+  const float* rew_logits;     // [N, 255]
+  const float* rewards;        // [N]
+  const float* cont_logit;     // [N]
+  const float* is_terminated;  // [N]
+  const float* post;           // [N, Z]
+  const float* prior;          // [N, Z]
+  // outputs
+  float* L_dec; float* L_rew; float* L_con; float* L_dyn; float* L_rep; float* L_tot;  // [N]
+  float* scalars;              // [8]: means of dec, rew, con, pred, dyn, rep, total
+  float* dloc; float* drew_logits; float* dcont_logit; float* dpost; float* dprior;
+  int32_t* rew_k;              // [N] two-hot lower bucket index of symlog(reward)
+};
+void wm_losses(cudaStream_t s, const WmLossArgs& a);
+
+struct AcArgs {
+  int H, N;                // rows per step
+  int A, discrete;
+  float gamma, lambda_, entropy_scale, decay;
+  float inv_count;         // 1 / (world_size * H * N)
+  const float* rew_E;      // [(H+1)N] symlog-space expected reward
+  const float* cont_logit; // [(H+1)N]
+  const float* v_E;        // [(H+1)N] symlog-space expected value (fast critic)
+  const float* ema_E;      // [(H+1)N]
+  const float* is_terminated;  // [N]
+  float* r; float* c; float* w; float* v;  // [(H+1)N] real-space outputs
+  float* targets;          // [H*N]
+};
+void ac_value_targets(cudaStream_t s, const AcArgs& a);
+void value_targets_raw(cudaStream_t s, const float* r, const float* c, const float* v, int H, int N, float gamma,
+                       float lambda_, float* targets);
+// p5/p95 (tfp nearest) of x[n] via radix select; updates ema[0..1] (NaN = unset) in place; writes raw to out[0..1]
+void percentile_ema(cudaStream_t s, const float* x, long long n, float decay, float* ema, float* raw_out,
+                    uint32_t* scratch);
+
+struct AcLossArgs {
+  AcArgs base;
+  const float* ema;             // [2] pct5, pct95 EMA (device)
+  const float* critic_logits;   // [(H+1)N, 255]
+  float* dcritic_logits;        // [(H+1)N, 255] (rows of step H zeroed)
+  // discrete actor
+  const float* actor_logits;    // [(H+1)N, A] raw (pre-softmax)
+  const int32_t* action_idx;    // [(H+1)N]
+  float* dactor_logits;         // [(H+1)N, A]
+  // box actor
+  const float* actor_mu; const float* actor_s;  // raw outputs [(H+1)N, A]
+  const float* actions;                         // [(H+1)N, A]
+  float* dmu; float* ds;                        // entropy-term gradients (overwritten); BPTT adds to them later
+  float* dR; float* dV;                         // dL_actor/dtargets [H*N], dL_actor/dv [(H+1)N] (Box only)
+  // per-element outputs [H*N]
+  float* L_critic_HB; float* L_val_HB; float* L_reg_HB; float* targets_symlog;
+  float* L_actor_HB; float* logp_HB; float* scaled_HB; float* ent_HB; float* L_reinf_HB; float* L_ent_HB;
+  float* scalars;               // [16]
+};
+void ac_losses(cudaStream_t s, const AcLossArgs& a);
+// Backward of the lambda-return recursion + inverse_symlog for the Box actor: from dR [H*N], dV [(H+1)N] to
+// d rew_E, d v_E (symlog space) [(H+1)N].
+void ac_returns_bwd(cudaStream_t s, const AcArgs& a, const float* dR, const float* dV, float* drew_E, float* dv_E);
+// Box actor sample a = tanh(mu) + std*eps, std = 0.9*sigmoid(s+2)+0.1 (actor_network.py:102-114)
+void box_actor_fwd(cudaStream_t s, const float* mu, const float* sraw, const float* eps, float* a, int lda,
+                   long long rows, int A);
+// dmu += da*(1-tanh^2), ds += da*eps*0.9*sig*(1-sig)
+void box_actor_bwd(cudaStream_t s, const float* mu, const float* sraw, const float* eps, const float* da, int ldda,
+                   float* dmu, float* ds, long long rows, int A);
+// Discrete actor: logits -> unimix probs, sample with u -> idx, one-hot a (row stride lda)
+void disc_actor_fwd(cudaStream_t s, const float* logits, const float* u, float* probs, int32_t* idx, float* a,
+                    int lda, long long rows, int A);
+
+// ---- optimizer (dv3_optim.cu) ---------------------------------------------------------------------------
+// stats[0] = sum of squares (as double bits in 2 floats? no: separate double*), see implementation.
+struct AdamState {
+  double* sumsq;     // device scalar
+  float* stats;      // [4]: global norm, maxabs grad, maxabs clipped grad, scale
+  int* step;         // device step counter (1-based after increment)
+};
+void grad_norm(cudaStream_t s, const float* g, long long n, AdamState st);
+void adam_step(cudaStream_t s, float* w, const float* g, float* m, float* v, long long n, float clip, float lr,
+               float eps, AdamState st, float* ema_w, float ema_decay);
+void ema_update(cudaStream_t s, float* ema, const float* w, long long n, float decay);
+
+// ---- noise (dv3_optim.cu) ----------------------------------------------------------------------------------
+// counter = (element/4, salt + *dev_step) ; dev_step may be null
+void philox_fill(cudaStream_t s, float* out, long long n, uint64_t seed, uint64_t salt, const unsigned long long* dev_step, int normal);
+void bump_counter(cudaStream_t s, unsigned long long* ctr);
+
+}  // namespace dv3

@@ -1,0 +1,80 @@
+// Patch gather/scatter for the 4x4 stride-2 "same" convolutions of CNNAtari / ConvTransposeAtari
+// (components/cnn_atari.py:33-71, components/conv_transpose_atari.py:48-92). The contractions themselves
+// run through the GEMM path:
+//   conv fwd        : Y = im2col(X) * W[16*Cin, Cout]
+//   conv bwd data   : dX = col2im(dY * W^T)            conv bwd weight: dW = im2col(X)^T * dY
+//   convT fwd       : Y = col2im(X * Wt^T) (+bias)     with Wt = Keras kernel [4,4,Cout,Cin] viewed [16*Cout, Cin]
+//   convT bwd data  : dX = im2col(dY) * Wt             convT bwd weight: dWt = im2col(dY)^T * X
+#include "dv3_common.h"
+
+namespace dv3 {
+namespace {
+
+__global__ void im2col_kernel(const float* __restrict__ img, float* __restrict__ cols, int n, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)n * Ho * Wo * 16 * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int kx = (int)(t % 4); t /= 4;
+    const int ky = (int)(t % 4); t /= 4;
+    const int ox = (int)(t % Wo); t /= Wo;
+    const int oy = (int)(t % Ho); t /= Ho;
+    const int b = (int)t;
+    const int y = 2 * oy - 1 + ky, x = 2 * ox - 1 + kx;
+    float v = 0.f;
+    if (y >= 0 && y < H && x >= 0 && x < W) v = img[(((size_t)b * H + y) * W + x) * C + c];
+    cols[i] = v;
+  }
+}
+
+__global__ void col2im_kernel(const float* __restrict__ cols, float* __restrict__ img, int n, int H, int W, int C,
+                              const float* __restrict__ bias, float add_const) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)n * H * W * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int x = (int)(t % W); t /= W;
+    const int y = (int)(t % H); t /= H;
+    const int b = (int)t;
+    float acc = add_const + (bias != nullptr ? bias[c] : 0.f);
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const int ty = y + 1 - ky;
+      if (ty < 0 || (ty & 1)) continue;
+      const int oy = ty >> 1;
+      if (oy >= Ho) continue;
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx) {
+        const int tx = x + 1 - kx;
+        if (tx < 0 || (tx & 1)) continue;
+        const int ox = tx >> 1;
+        if (ox >= Wo) continue;
+        acc += cols[((((size_t)b * Ho + oy) * Wo + ox) * 16 + ky * 4 + kx) * C + c];
+      }
+    }
+    img[i] = acc;
+  }
+}
+
+inline int grid_for(long long n) {
+  long long b = (n + 255) / 256;
+  if (b > 148 * 32) b = 148 * 32;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+void im2col_k4s2(cudaStream_t s, const float* img, float* cols, int n, int H, int W, int C) {
+  im2col_kernel<<<grid_for((long long)n * (H / 2) * (W / 2) * 16 * C), 256, 0, s>>>(img, cols, n, H, W, C);
+  count_launch();
+}
+void col2im_k4s2(cudaStream_t s, const float* cols, float* img, int n, int H, int W, int C, const float* bias,
+                 float add_const) {
+  col2im_kernel<<<grid_for((long long)n * H * W * C), 256, 0, s>>>(cols, img, n, H, W, C, bias, add_const);
+  count_launch();
+}
+
+}  // namespace dv3

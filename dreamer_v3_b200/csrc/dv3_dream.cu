@@ -1,0 +1,201 @@
+// Actor-critic half of the hot path: dream_trajectory (dreamer_model.py:147-303), lambda-returns, critic and
+// actor losses, and their gradients (train_one_step.py:130-252). Dream tensors are time-major [H+1, N, ...]
+// (row = i*N + n) as in the reference. Heads (reward / continue / critic / EMA critic) run once over all
+// (H+1)*N rows after the rollout; the actor has to run inside it because a_i feeds h_{i+1}.
+#include "dv3_engine.h"
+
+namespace dv3 {
+
+void Engine::actor_fwd(long long row_off) {
+  // models/actor_network.py:63-118 on rows [row_off, row_off + N) of the dream
+  const float* x = dr_hz + (size_t)row_off * (G + Z);
+  mlp_fwd(actor_mlp, actor_act, x, G + Z, N, row_off);
+  float* out = actor_logits + (size_t)row_off * A;
+  mm(actor_act.act.back() + (size_t)row_off * D, D, false, actor_out.w, A, false, out, A, N, A, D, actor_out.bias);
+  if (discrete) {
+    disc_actor_fwd(cur, out, in_act_noise + row_off, actor_probs + (size_t)row_off * A, dr_a_idx + row_off,
+                   dr_act + (size_t)row_off * A, A, N, A);
+  } else {
+    mlp_fwd(actor_std_mlp, actor_std_act, x, G + Z, N, row_off);
+    float* sraw = actor_s + (size_t)row_off * A;
+    mm(actor_std_act.act.back() + (size_t)row_off * D, D, false, actor_std_out.w, A, false, sraw, A, N, A, D, actor_std_out.bias);
+    box_actor_fwd(cur, out, sraw, in_act_noise + (size_t)row_off * A, dr_act + (size_t)row_off * A, A, N, A);
+  }
+}
+
+int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
+  cur = s;
+  last_gamma = gamma;
+  const LnLayer& Wx = pre_mlp.layers[0];
+  const LnLayer& Wd = dyn_mlp.layers[0];
+  const int W = G + Z;
+  // start states: row n = b*T + t of the observe pass (run_experiment.py:458-460)
+  if (start_from_observe) {
+    cudaMemcpyAsync(dr_hz, hz, (size_t)N * W * 4, cudaMemcpyDeviceToDevice, s);
+  } else {
+    copy_2d(s, in_dream_h0, G, dr_hz, W, N, G);
+    copy_2d(s, in_dream_z0, Z, dr_hz + G, W, N, Z);
+  }
+  actor_fwd(0);
+  for (int i = 1; i <= H; ++i) {
+    const size_t prev = (size_t)(i - 1) * N, curr = (size_t)i * N, st = (size_t)(i - 1) * N;  // st: per-step buffers
+    const float* hz_p = dr_hz + prev * W;
+    float* hz_c = dr_hz + curr * W;
+    // sequence model on [z_{i-1}, a_{i-1}], h_{i-1}
+    mm(hz_p + G, W, false, Wx.w, D, false, dr_x_pre + st * D, D, N, D, Z);
+    mm(dr_act + prev * A, A, false, Wx.w + (size_t)Z * D, D, false, dr_x_pre + st * D, D, N, D, A, nullptr, 1.f);
+    ln_silu_fwd(s, dr_x_pre + st * D, D, Wx.g, Wx.b, dr_u + st * D, D, dr_x_mean + st, dr_x_rstd + st, 1, N, D);
+    mm(dr_u + st * D, D, false, gru_K, 3 * G, false, dr_gx + st * 3 * G, 3 * G, N, 3 * G, D, gru_b);
+    mm(hz_p, W, false, gru_U, 3 * G, false, dr_gh + st * 3 * G, 3 * G, N, 3 * G, G, gru_b + 3 * G);
+    gru_fwd(s, dr_gx + st * 3 * G, 3 * G, dr_gh + st * 3 * G, 3 * G, hz_p, W, hz_c, W, N, G);
+    // prior z_i ~ dynamics_predictor(h_i), straight-through sample
+    mm(hz_c, W, false, Wd.w, D, false, dr_q_pre + st * D, D, N, D, G);
+    ln_silu_fwd(s, dr_q_pre + st * D, D, Wd.g, Wd.b, dr_q_act + st * D, D, dr_q_mean + st, dr_q_rstd + st, 1, N, D);
+    mm(dr_q_act + st * D, D, false, dyn_repr.w, Z, false, dr_prior_logits + st * Z, Z, N, Z, D, dyn_repr.bias);
+    repr_fwd(s, dr_prior_logits + st * Z, Z, dr_prior_probs + st * Z, Z, in_u_dyn + st * Zc, Zc, dr_z_idx + st * Zc, Zc,
+             hz_c + G, W, N, Zc, Zk, 1);
+    actor_fwd((long long)curr);
+  }
+  // heads on all (H+1)*N rows
+  mlp_fwd(rew_mlp, dr_rew_act, dr_hz, W, R);
+  mm(dr_rew_act.act.back(), D, false, rew_head.w, DV3_NB, false, dr_rew_logits, DV3_NB, R, DV3_NB, D, rew_head.bias);
+  bucket_expectation(s, dr_rew_logits, DV3_NB, dr_rew_E, R);
+  mlp_fwd(cont_mlp, dr_cont_act, dr_hz, W, R);
+  mm(dr_cont_act.act.back(), D, false, cont_out.w, 1, false, dr_cont_logit, 1, R, 1, D, cont_out.bias);
+  mlp_fwd(critic_mlp, critic_act, dr_hz, W, R);
+  mm(critic_act.act.back(), D, false, critic_head.w, DV3_NB, false, critic_logits, DV3_NB, R, DV3_NB, D, critic_head.bias);
+  bucket_expectation(s, critic_logits, DV3_NB, v_E, R);
+  mlp_fwd(ema_mlp, ema_act, dr_hz, W, R);
+  mm(ema_act.act.back(), D, false, ema_head.w, DV3_NB, false, ema_logits, DV3_NB, R, DV3_NB, D, ema_head.bias);
+  bucket_expectation(s, ema_logits, DV3_NB, ema_E, R);
+  // real-space rewards / continues / values, loss weights (dreamer_model.py:219-280) and lambda-returns
+  AcArgs a{};
+  a.H = H; a.N = N; a.A = A; a.discrete = discrete; a.gamma = gamma; a.lambda_ = 0.95f;
+  a.rew_E = dr_rew_E; a.cont_logit = dr_cont_logit; a.v_E = v_E; a.ema_E = ema_E; a.is_terminated = in_is_term;
+  a.r = ac_r; a.c = ac_c; a.w = ac_w; a.v = ac_v; a.targets = ac_targets;
+  ac_value_targets(s, a);
+  return 0;
+}
+
+int Engine::ac_loss_backward(const dv3_hparams* hp, int phase, cudaStream_t s) {
+  cur = s;
+  const int W = G + Z;
+  const long long HN = (long long)H * N;
+  AcArgs a{};
+  a.H = H; a.N = N; a.A = A; a.discrete = discrete;
+  a.gamma = hp->gamma; a.lambda_ = hp->lambda_; a.entropy_scale = hp->entropy_scale; a.decay = hp->return_normalization_decay;
+  a.inv_count = inv_world / (float)HN;
+  a.rew_E = dr_rew_E; a.cont_logit = dr_cont_logit; a.v_E = v_E; a.ema_E = ema_E; a.is_terminated = in_is_term;
+  a.r = ac_r; a.c = ac_c; a.w = ac_w; a.v = ac_v; a.targets = ac_targets;
+  if (phase & 1) {
+    ac_value_targets(s, a);  // dreamer_model.py:219-280 tail + critic_loss.py:92-139
+    if (cfg.world_size == 1) cudaMemcpyAsync(ac_targets_all, ac_targets, (size_t)HN * 4, cudaMemcpyDeviceToDevice, s);
+  }
+  if (!(phase & 2)) return 0;
+
+  // percentile EMAs over the (all-gathered) value targets (actor_loss.py:110-129)
+  percentile_ema(s, ac_targets_all, HN * cfg.world_size, hp->return_normalization_decay, pct_ema, pct_raw, nullptr);
+
+  AcLossArgs l{};
+  l.base = a; l.ema = pct_ema; l.critic_logits = critic_logits; l.dcritic_logits = dcritic_logits;
+  l.actor_logits = actor_logits; l.action_idx = dr_a_idx; l.dactor_logits = dactor_logits;
+  l.actor_mu = actor_logits; l.actor_s = actor_s; l.actions = dr_act; l.dmu = dmu; l.ds = ds; l.dR = dR; l.dV = dV;
+  l.L_critic_HB = L_critic_HB; l.L_val_HB = L_val_HB; l.L_reg_HB = L_reg_HB; l.targets_symlog = targets_symlog;
+  l.L_actor_HB = L_actor_HB; l.logp_HB = logp_HB; l.scaled_HB = scaled_HB; l.ent_HB = ent_HB;
+  l.L_reinf_HB = L_reinf_HB; l.L_ent_HB = L_ent_HB; l.scalars = ac_scalars;
+  ac_losses(s, l);
+
+  // ---- critic: gradient only reaches the fast critic's own weights (train_one_step.py:197-200) ----
+  cudaMemsetAsync(grads[2], 0, (size_t)numel[2] * 4, s);
+  dense_bwd(critic_head, critic_act.act.back(), D, dcritic_logits, DV3_NB, sN_D0, D, 0.f, true, HN);
+  mlp_bwd(critic_mlp, critic_act, dr_hz, W, sN_D0, sN_D1, nullptr, 0, true, HN);
+
+  if (!hp->train_actor) return 0;
+  cudaMemsetAsync(grads[1], 0, (size_t)numel[1] * 4, s);
+  if (!discrete) {
+    // Box actions: the loss is -scaled advantages with gradient (actor_loss.py:57) -> BPTT through rewards,
+    // values and the 15 RSSM steps into the reparameterised action samples.
+    const LnLayer& Wx = pre_mlp.layers[0];
+    const LnLayer& Wd = dyn_mlp.layers[0];
+    ac_returns_bwd(s, a, dR, dV, drew_E, dv_E);
+    cudaMemsetAsync(d_dr_hz, 0, (size_t)R * W * 4, s);
+    bucket_expectation_bwd(s, dr_rew_logits, DV3_NB, drew_E, dr_dlogits255, DV3_NB, R);
+    dense_bwd(rew_head, nullptr, 0, dr_dlogits255, DV3_NB, sN_D0, D, 0.f, false, R);
+    mlp_bwd(rew_mlp, dr_rew_act, dr_hz, W, sN_D0, sN_D1, d_dr_hz, W, false, R);
+    bucket_expectation_bwd(s, critic_logits, DV3_NB, dv_E, dr_dlogits255, DV3_NB, R);
+    dense_bwd(critic_head, nullptr, 0, dr_dlogits255, DV3_NB, sN_D0, D, 0.f, false, R);
+    mlp_bwd(critic_mlp, critic_act, dr_hz, W, sN_D0, sN_D1, d_dr_hz, W, false, R);
+    for (int i = H; i >= 1; --i) {
+      const size_t prev = (size_t)(i - 1) * N, curr = (size_t)i * N, st = (size_t)(i - 1) * N;
+      float* d_c = d_dr_hz + curr * W;
+      float* d_p = d_dr_hz + prev * W;
+      const float* hz_p = dr_hz + prev * W;
+      // z_i = straight-through sample of prior(h_i)
+      repr_bwd(s, dr_prior_logits + st * Z, Z, d_c + G, W, nullptr, 0, sN_Z, Z, N, Zc, Zk);
+      mm(sN_Z, Z, false, dyn_repr.w, Z, true, sN_D0, D, N, D, Z);
+      ln_silu_bwd(s, sN_D0, D, dr_q_pre + st * D, D, dr_q_mean + st, dr_q_rstd + st, Wd.g, Wd.b, sN_D1, D, nullptr, nullptr, 1, N, D);
+      mm(sN_D1, D, false, Wd.w, D, true, d_c, W, N, G, D, nullptr, 1.f);
+      // h_i = GRU(pre([z_{i-1}, a_{i-1}]), h_{i-1})
+      gru_bwd(s, d_c, W, dr_gx + st * 3 * G, 3 * G, dr_gh + st * 3 * G, 3 * G, hz_p, W, sN_3G0, 3 * G, sN_3G1, 3 * G, d_p, W, 1, N, G);
+      mm(sN_3G1, 3 * G, false, gru_U, 3 * G, true, d_p, W, N, G, 3 * G, nullptr, 1.f);
+      mm(sN_3G0, 3 * G, false, gru_K, 3 * G, true, sN_D0, D, N, D, 3 * G);
+      ln_silu_bwd(s, sN_D0, D, dr_x_pre + st * D, D, dr_x_mean + st, dr_x_rstd + st, Wx.g, Wx.b, sN_D1, D, nullptr, nullptr, 1, N, D);
+      mm(sN_D1, D, false, Wx.w, D, true, d_p + G, W, N, Z, D, nullptr, 1.f);
+      mm(sN_D1, D, false, Wx.w + (size_t)Z * D, D, true, sN_A, A, N, A, D);
+      box_actor_bwd(s, actor_logits + prev * A, actor_s + prev * A, in_act_noise + prev * A, sN_A, A, dmu + prev * A, ds + prev * A, N, A);
+    }
+    dense_bwd(actor_std_out, actor_std_act.act.back(), D, ds, A, sN_D0, D, 0.f, true, HN);
+    mlp_bwd(actor_std_mlp, actor_std_act, dr_hz, W, sN_D0, sN_D1, nullptr, 0, true, HN);
+  }
+  // actor MLP: inputs were stop-gradient'ed (dreamer_model.py:179-180), so only weight gradients
+  dense_bwd(actor_out, actor_act.act.back(), D, dactor_logits, A, sN_D0, D, 0.f, true, HN);
+  mlp_bwd(actor_mlp, actor_act, dr_hz, W, sN_D0, sN_D1, nullptr, 0, true, HN);
+  return 0;
+}
+
+int Engine::train_ac(const dv3_hparams* hp, cudaStream_t s) {
+  int rc = dream_forward(hp->gamma, 1, s);
+  if (rc) return rc;
+  rc = ac_loss_backward(hp, 3, s);
+  if (rc) return rc;
+  if (hp->train_actor) {
+    rc = optimizer_step(1, hp->actor_grad_clip, hp->ac_lr, hp->ac_eps, 0.f, s);
+    if (rc) return rc;
+  }
+  return optimizer_step(2, hp->critic_grad_clip, hp->ac_lr, hp->ac_eps, hp->critic_ema_decay, s);
+}
+
+int Engine::train_update(const dv3_hparams* hp, uint64_t seed, int use_graph, cudaStream_t s) {
+  auto body = [&](cudaStream_t st) -> int {
+    if (seed != 0) {
+      bump_counter(st, noise_step);
+      fill_noise(seed, 0, 3, true, st);
+    }
+    int rc = train_wm(hp, st);
+    if (rc) return rc;
+    return train_ac(hp, st);
+  };
+  if (!use_graph) return body(s);
+  if (graph_exec == nullptr || graph_seed != seed) {
+    if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    const long long before = g_launches;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return fail("cudaStreamBeginCapture failed");
+    int rc = body(s);
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    graph_launches = g_launches - before;
+    g_launches = before;
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    graph_seed = seed;
+  }
+  cudaError_t e = cudaGraphLaunch(graph_exec, s);
+  if (e != cudaSuccess) return fail(std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
+  g_launches += graph_launches;
+  return 0;
+}
+
+}  // namespace dv3

@@ -1,0 +1,420 @@
+// Elementwise, LayerNorm+SiLU, GRU cell, categorical representation kernels (fp32).
+#include "dv3_device.cuh"
+
+namespace dv3 {
+namespace {
+
+constexpr int kThreads = 256;
+inline int grid_for(long long n, int per_block = kThreads, int cap = 148 * 16) {
+  long long b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > cap) b = cap;
+  return (int)b;
+}
+
+__global__ void symlog_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = symlog_dev(x[i]);
+}
+__global__ void inv_symlog_kernel(const float* __restrict__ y, float* __restrict__ x, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    x[i] = inv_symlog_dev(y[i]);
+  }
+}
+__global__ void fill_kernel(float* p, float v, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void tanh_kernel(const float* x, float* y, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] = tanhf(x[i]);
+}
+// mode 0: dst = 0; 1: dst = src; 2: dst += src
+template <int MODE>
+__global__ void op_2d_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int rows, int cols) {
+  const long long n = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    float* d = dst + (size_t)r * ldd + c;
+    if (MODE == 0) *d = 0.f;
+    else if (MODE == 1) *d = src[(size_t)r * lds + c];
+    else *d += src[(size_t)r * lds + c];
+  }
+}
+
+// ---- LayerNorm + SiLU: one warp per row ----------------------------------------------------------------
+constexpr int kLnMaxPerLane = 32;  // D <= 1024
+
+__global__ void ln_silu_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ y, int ldy,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int sstride, long long rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const float* xr = x + (size_t)r * ldx;
+    float v[kLnMaxPerLane];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = (c < D) ? xr[c] : 0.f;
+      s += v[i];
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+      const int c = lane + 32 * i;
+      const float d = (c < D) ? (v[i] - mean) : 0.f;
+      q += d * d;
+    }
+    const float var = warp_sum(q) / (float)D;
+    const float rstd = rsqrtf(var + DV3_LN_EPS);
+    float* yr = y + (size_t)r * ldy;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+      const int c = lane + 32 * i;
+      if (c < D) {
+        const float n = (v[i] - mean) * rstd * gamma[c] + beta[c];
+        yr[c] = n * sigmoidf_(n);
+      }
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[r * sstride] = mean;
+      if (rstd_out) rstd_out[r * sstride] = rstd;
+    }
+  }
+}
+
+__global__ void ln_silu_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
+                                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ dx, int lddx, float* __restrict__ dgamma,
+                                   float* __restrict__ dbeta, int sstride, long long rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float ag[kLnMaxPerLane], ab[kLnMaxPerLane];
+#pragma unroll
+  for (int i = 0; i < kLnMaxPerLane; ++i) ag[i] = ab[i] = 0.f;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const float* xr = x + (size_t)r * ldx;
+    const float* dyr = dy + (size_t)r * lddy;
+    const float mean = mean_in[r * sstride], rstd = rstd_in[r * sstride];
+    float xh[kLnMaxPerLane], dxh[kLnMaxPerLane];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+      const int c = lane + 32 * i;
+      if (c < D) {
+        const float xhat = (xr[c] - mean) * rstd;
+        const float gm = gamma[c];
+        const float n = xhat * gm + beta[c];
+        const float sg = sigmoidf_(n);
+        const float dn = dyr[c] * (sg * (1.f + n * (1.f - sg)));
+        ag[i] += dn * xhat;
+        ab[i] += dn;
+        xh[i] = xhat;
+        dxh[i] = dn * gm;
+        s1 += dxh[i];
+        s2 += dxh[i] * xhat;
+      } else {
+        xh[i] = 0.f; dxh[i] = 0.f;
+      }
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+    if (dx != nullptr) {
+      float* dxr = dx + (size_t)r * lddx;
+#pragma unroll
+      for (int i = 0; i < kLnMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        if (c < D) dxr[c] = rstd * (dxh[i] - s1 - xh[i] * s2);
+      }
+    }
+  }
+  if (dgamma != nullptr) {
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+      const int c = lane + 32 * i;
+      if (c < D) {
+        atomicAdd(&dgamma[c], ag[i]);
+        atomicAdd(&dbeta[c], ab[i]);
+      }
+    }
+  }
+}
+
+// ---- GRU cell ---------------------------------------------------------------------------------------
+__global__ void gru_fwd_kernel(float* __restrict__ gx, int ldgx, const float* __restrict__ gh, int ldgh,
+                               const float* __restrict__ h_prev, int ldhp, float* __restrict__ h_out, int ldho,
+                               int M, int G) {
+  const long long n = (long long)M * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / G), j = (int)(i % G);
+    float* gxr = gx + (size_t)r * ldgx;
+    const float* ghr = gh + (size_t)r * ldgh;
+    const float z = sigmoidf_(gxr[j] + ghr[j]);
+    const float rg = sigmoidf_(gxr[G + j] + ghr[G + j]);
+    const float c = tanhf(gxr[2 * G + j] + rg * ghr[2 * G + j]);
+    const float hp = h_prev[(size_t)r * ldhp + j];
+    h_out[(size_t)r * ldho + j] = z * hp + (1.f - z) * c;
+    gxr[j] = z; gxr[G + j] = rg; gxr[2 * G + j] = c;
+  }
+}
+
+__global__ void gru_bwd_kernel(const float* __restrict__ dh, int lddh, const float* __restrict__ gates, int ldg,
+                               const float* __restrict__ gh, int ldgh, const float* __restrict__ h_prev, int ldhp,
+                               float* __restrict__ dgx, int lddgx, float* __restrict__ dgh, int lddgh,
+                               float* __restrict__ dh_prev, int lddhp, int accumulate, int M, int G) {
+  const long long n = (long long)M * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / G), j = (int)(i % G);
+    const float* gr = gates + (size_t)r * ldg;
+    const float z = gr[j], rg = gr[G + j], c = gr[2 * G + j];
+    const float hh = gh[(size_t)r * ldgh + 2 * G + j];
+    const float hp = h_prev[(size_t)r * ldhp + j];
+    const float d = dh[(size_t)r * lddh + j];
+    const float dz = d * (hp - c) * z * (1.f - z);
+    const float dc = d * (1.f - z) * (1.f - c * c);
+    const float dr = dc * hh * rg * (1.f - rg);
+    float* a = dgx + (size_t)r * lddgx;
+    float* b = dgh + (size_t)r * lddgh;
+    a[j] = dz; a[G + j] = dr; a[2 * G + j] = dc;
+    b[j] = dz; b[G + j] = dr; b[2 * G + j] = dc * rg;
+    float* o = dh_prev + (size_t)r * lddhp + j;
+    if (accumulate) *o += d * z; else *o = d * z;
+  }
+}
+
+// ---- categorical representation: one warp per (row, categorical); lane = class -----------------------------
+__global__ void repr_fwd_kernel(const float* __restrict__ logits, int ldl, float* __restrict__ probs, int ldp,
+                                const float* __restrict__ u, int ldu, int32_t* __restrict__ idx, int ldi,
+                                float* __restrict__ z, int ldz, int M, int Zc, int Zk, int mode) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long total = (long long)M * Zc;
+  for (long long w = warp0; w < total; w += nwarps) {
+    const int r = (int)(w / Zc), c = (int)(w % Zc);
+    const bool act = lane < Zk;
+    const float l = act ? logits[(size_t)r * ldl + c * Zk + lane] : -INFINITY;
+    const float mx = warp_max(l);
+    const float e = act ? expf(l - mx) : 0.f;
+    const float s = warp_sum(e);
+    const float p = 0.99f * (e / s) + 0.01f * (1.0f / (float)Zk);
+    if (act && probs != nullptr) probs[(size_t)r * ldp + c * Zk + lane] = p;
+    if (mode == 0) continue;
+    int pick;
+    if (mode == 1) {
+      pick = categorical_pick(p, act, Zk, u[(size_t)r * ldu + c], lane);
+    } else {
+      // argmax, first index on ties
+      const float pm = warp_max(act ? p : -1.f);
+      const unsigned is = __ballot_sync(0xffffffffu, act && (p == pm));
+      pick = __ffs(is) - 1;
+    }
+    if (idx != nullptr && lane == 0) idx[(size_t)r * ldi + c] = pick;
+    if (z != nullptr && act) z[(size_t)r * ldz + c * Zk + lane] = (lane == pick) ? 1.f : 0.f;
+  }
+}
+
+__global__ void repr_bwd_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ dz, int lddz,
+                                const float* __restrict__ dprobs, int lddp, float* __restrict__ dlogits, int lddl,
+                                int M, int Zc, int Zk) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long total = (long long)M * Zc;
+  for (long long w = warp0; w < total; w += nwarps) {
+    const int r = (int)(w / Zc), c = (int)(w % Zc);
+    const bool act = lane < Zk;
+    const int col = c * Zk + lane;
+    const float l = act ? logits[(size_t)r * ldl + col] : -INFINITY;
+    const float mx = warp_max(l);
+    const float e = act ? expf(l - mx) : 0.f;
+    const float s = warp_sum(e);
+    const float p = e / s;
+    float g = 0.f;
+    if (act) {
+      if (dz != nullptr) g += dz[(size_t)r * lddz + col];
+      if (dprobs != nullptr) g += dprobs[(size_t)r * lddp + col];
+      g *= 0.99f;
+    }
+    const float dot = warp_sum(g * p);
+    if (act) dlogits[(size_t)r * lddl + col] = p * (g - dot);
+  }
+}
+
+// ---- observe-scan masking (world_model.py:246-253) -----------------------------------------------------------
+__global__ void scan_mask_inputs_kernel(const float* __restrict__ is_first, int ldf, const float* __restrict__ h_prev,
+                                        int ldhp, const float* __restrict__ z_prev, int ldzp,
+                                        const float* __restrict__ h0, const float* __restrict__ z0,
+                                        const float* __restrict__ actW, int ldaw, float* __restrict__ h_in, int ldhi,
+                                        float* __restrict__ z_in, int ldzi, float* __restrict__ x_pre, int ldx, int B,
+                                        int G, int Z, int D) {
+  const int W = G + Z + D;
+  const long long n = (long long)B * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / W);
+    int j = (int)(i % W);
+    const float f = is_first[(size_t)b * ldf];
+    if (j < G) {
+      const float hp = (h_prev != nullptr) ? h_prev[(size_t)b * ldhp + j] : h0[j];
+      h_in[(size_t)b * ldhi + j] = hp * (1.f - f) + h0[j] * f;
+    } else if (j < G + Z) {
+      j -= G;
+      const float zp = (z_prev != nullptr) ? z_prev[(size_t)b * ldzp + j] : z0[j];
+      z_in[(size_t)b * ldzi + j] = zp * (1.f - f) + z0[j] * f;
+    } else {
+      j -= G + Z;
+      x_pre[(size_t)b * ldx + j] = actW[(size_t)b * ldaw + j];
+    }
+  }
+}
+
+__global__ void scan_mask_grads_kernel(const float* __restrict__ is_first, int ldf, const float* __restrict__ d_in,
+                                       int ldin, float* __restrict__ d_out, int ldout, int B, int W) {
+  const long long n = (long long)B * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / W), j = (int)(i % W);
+    d_out[(size_t)b * ldout + j] += d_in[(size_t)b * ldin + j] * (1.f - is_first[(size_t)b * ldf]);
+  }
+}
+
+
+// out[c] += sum_r x[r*ld + c]
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int ld, long long rows, int cols,
+                                                     float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (c < cols)
+    for (long long r = blockIdx.y * 8 + ty; r < rows; r += (long long)gridDim.y * 8) s += x[(size_t)r * ld + c];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    atomicAdd(&out[c], t);
+  }
+}
+
+// a_in[b,t,:] = (1 - f[b,t]) * actions[b,(t-1) mod T,:]; wf[b,t] = t==0 ? 1 : f[b,t]   (world_model.py:246-253)
+__global__ void scan_prepare_kernel(const float* __restrict__ actions, const float* __restrict__ is_first,
+                                    float* __restrict__ a_in, float* __restrict__ wf, int B, int T, int A) {
+  const long long n = (long long)B * T * (A + 1);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % (A + 1));
+    const long long bt = i / (A + 1);
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    const float f = is_first[bt];
+    if (j < A) a_in[bt * A + j] = (1.f - f) * actions[((size_t)b * T + (t + T - 1) % T) * A + j];
+    else wf[bt] = (t == 0) ? 1.f : f;
+  }
+}
+// dinit[j] += dh0[j] * (1 - h0[j]^2)
+__global__ void tanh_bwd_acc_kernel(const float* __restrict__ dh0, const float* __restrict__ h0, float* __restrict__ dinit, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dinit[i] += dh0[i] * (1.f - h0[i] * h0[i]);
+}
+
+}  // namespace
+
+void symlog_fwd(cudaStream_t s, const float* x, float* y, long long n) {
+  if (n <= 0) return;
+  symlog_kernel<<<grid_for(n), kThreads, 0, s>>>(x, y, n); count_launch();
+}
+void inverse_symlog_fwd(cudaStream_t s, const float* y, float* x, long long n) {
+  if (n <= 0) return;
+  inv_symlog_kernel<<<grid_for(n), kThreads, 0, s>>>(y, x, n); count_launch();
+}
+void fill_f32(cudaStream_t s, float* p, float v, long long n) {
+  if (n <= 0) return;
+  fill_kernel<<<grid_for(n), kThreads, 0, s>>>(p, v, n); count_launch();
+}
+void tanh_fwd(cudaStream_t s, const float* x, float* y, int n) {
+  tanh_kernel<<<grid_for(n), kThreads, 0, s>>>(x, y, n); count_launch();
+}
+void zero_2d(cudaStream_t s, float* p, int rows, int cols, int ld) {
+  if (rows <= 0 || cols <= 0) return;
+  if (ld == cols) { cudaMemsetAsync(p, 0, (size_t)rows * cols * sizeof(float), s); return; }
+  op_2d_kernel<0><<<grid_for((long long)rows * cols), kThreads, 0, s>>>(nullptr, 0, p, ld, rows, cols); count_launch();
+}
+void copy_2d(cudaStream_t s, const float* src, int lds, float* dst, int ldd, int rows, int cols) {
+  if (rows <= 0 || cols <= 0) return;
+  op_2d_kernel<1><<<grid_for((long long)rows * cols), kThreads, 0, s>>>(src, lds, dst, ldd, rows, cols); count_launch();
+}
+void add_2d(cudaStream_t s, const float* src, int lds, float* dst, int ldd, int rows, int cols) {
+  if (rows <= 0 || cols <= 0) return;
+  op_2d_kernel<2><<<grid_for((long long)rows * cols), kThreads, 0, s>>>(src, lds, dst, ldd, rows, cols); count_launch();
+}
+
+void ln_silu_fwd(cudaStream_t s, const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy,
+                 float* mean, float* rstd, int sstride, long long rows, int D) {
+  if (rows <= 0) return;
+  ln_silu_fwd_kernel<<<grid_for(rows, kThreads / 32, 148 * 8), kThreads, 0, s>>>(x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, D);
+  count_launch();
+}
+void ln_silu_bwd(cudaStream_t s, const float* dy, int lddy, const float* x, int ldx, const float* mean,
+                 const float* rstd, const float* gamma, const float* beta, float* dx, int lddx, float* dgamma,
+                 float* dbeta, int sstride, long long rows, int D) {
+  if (rows <= 0) return;
+  ln_silu_bwd_kernel<<<grid_for(rows, kThreads / 32, 148 * 4), kThreads, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, D);
+  count_launch();
+}
+
+void gru_fwd(cudaStream_t s, float* gx, int ldgx, const float* gh, int ldgh, const float* h_prev, int ldhp,
+             float* h_out, int ldho, int M, int G) {
+  gru_fwd_kernel<<<grid_for((long long)M * G), kThreads, 0, s>>>(gx, ldgx, gh, ldgh, h_prev, ldhp, h_out, ldho, M, G);
+  count_launch();
+}
+void gru_bwd(cudaStream_t s, const float* dh, int lddh, const float* gates, int ldg, const float* gh, int ldgh,
+             const float* h_prev, int ldhp, float* dgx, int lddgx, float* dgh, int lddgh, float* dh_prev, int lddhp,
+             int accumulate_dh_prev, int M, int G) {
+  gru_bwd_kernel<<<grid_for((long long)M * G), kThreads, 0, s>>>(dh, lddh, gates, ldg, gh, ldgh, h_prev, ldhp, dgx, lddgx, dgh, lddgh, dh_prev, lddhp, accumulate_dh_prev, M, G);
+  count_launch();
+}
+
+void repr_fwd(cudaStream_t s, const float* logits, int ldl, float* probs, int ldp, const float* u, int ldu,
+              int32_t* idx, int ldi, float* z, int ldz, int M, int Zc, int Zk, int mode) {
+  if (M <= 0) return;
+  repr_fwd_kernel<<<grid_for((long long)M * Zc, kThreads / 32), kThreads, 0, s>>>(logits, ldl, probs, ldp, u, ldu, idx, ldi, z, ldz, M, Zc, Zk, mode);
+  count_launch();
+}
+void repr_bwd(cudaStream_t s, const float* logits, int ldl, const float* dz, int lddz, const float* dprobs, int lddp,
+              float* dlogits, int lddl, int M, int Zc, int Zk) {
+  if (M <= 0) return;
+  repr_bwd_kernel<<<grid_for((long long)M * Zc, kThreads / 32), kThreads, 0, s>>>(logits, ldl, dz, lddz, dprobs, lddp, dlogits, lddl, M, Zc, Zk);
+  count_launch();
+}
+
+void scan_mask_inputs(cudaStream_t s, const float* is_first, int ldf, const float* h_prev, int ldhp,
+                      const float* z_prev, int ldzp, const float* h0, const float* z0, const float* actW, int ldaw,
+                      float* h_in, int ldhi, float* z_in, int ldzi, float* x_pre, int ldx, int B, int G, int Z, int D) {
+  scan_mask_inputs_kernel<<<grid_for((long long)B * (G + Z + D)), kThreads, 0, s>>>(is_first, ldf, h_prev, ldhp, z_prev, ldzp, h0, z0, actW, ldaw, h_in, ldhi, z_in, ldzi, x_pre, ldx, B, G, Z, D);
+  count_launch();
+}
+void scan_mask_grads(cudaStream_t s, const float* is_first, int ldf, const float* d_in, int ldin, float* d_out,
+                     int ldout, int B, int W) {
+  scan_mask_grads_kernel<<<grid_for((long long)B * W), kThreads, 0, s>>>(is_first, ldf, d_in, ldin, d_out, ldout, B, W);
+  count_launch();
+}
+
+}  // namespace dv3
+
+namespace dv3 {
+void colsum_acc(cudaStream_t s, const float* x, int ld, long long rows, int cols, float* out) {
+  if (rows <= 0 || cols <= 0) return;
+  long long gy = (rows + 63) / 64; if (gy > 148 * 2) gy = 148 * 2; if (gy < 1) gy = 1;
+  dim3 grid(cdiv(cols, 32), (unsigned)gy);
+  colsum_kernel<<<grid, 256, 0, s>>>(x, ld, rows, cols, out); count_launch();
+}
+void scan_prepare(cudaStream_t s, const float* actions, const float* is_first, float* a_in, float* wf, int B, int T, int A) {
+  long long n = (long long)B * T * (A + 1);
+  scan_prepare_kernel<<<grid_for(n), kThreads, 0, s>>>(actions, is_first, a_in, wf, B, T, A); count_launch();
+}
+void tanh_bwd_acc(cudaStream_t s, const float* dh0, const float* h0, float* dinit, int n) {
+  tanh_bwd_acc_kernel<<<grid_for(n), kThreads, 0, s>>>(dh0, h0, dinit, n); count_launch();
+}
+}  // namespace dv3

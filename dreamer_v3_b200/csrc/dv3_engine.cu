@@ -1,0 +1,623 @@
+// Engine construction: parameter table (mirrors dreamer_v3_b200/spec.py), memory layout, weight binding,
+// MLP / dense / conv building blocks. The hot-path orchestration lives in dv3_observe.cu and dv3_dream.cu.
+#include "dv3_engine.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace dv3 {
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));   \
+  } while (0)
+
+static long long prod(const std::vector<int64_t>& s) {
+  long long p = 1;
+  for (auto v : s) p *= v;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------ param table
+void Engine::build_param_table() {
+  pinfo.clear();
+  for (int g = 0; g < 4; ++g) numel[g] = 0;
+  auto add = [&](int group, const std::string& name, std::vector<int64_t> shape) {
+    PInfo p{name, group, shape, numel[group]};
+    long long n = prod(shape);
+    numel[group] += (n + 3) / 4 * 4;  // keep every tensor 16-byte aligned inside the flat buffer
+    pinfo.push_back(p);
+  };
+  auto mlp = [&](int group, const std::string& prefix, int in_dim, int L_) {
+    int k = in_dim;
+    for (int l = 0; l < L_; ++l) {
+      const std::string b = prefix + ".mlp" + std::to_string(l);
+      add(group, b + ".w", {k, D});
+      add(group, b + ".g", {D});
+      add(group, b + ".b", {D});
+      k = D;
+    }
+  };
+  auto dense = [&](int group, const std::string& prefix, int in, int out) {
+    add(group, prefix + ".w", {in, out});
+    add(group, prefix + ".bias", {out});
+  };
+  const int m = cfg.cnn_mult;
+  if (image) {
+    int cin = cfg.img_c;
+    for (int l = 0; l < 4; ++l) {
+      const int cout = m << l;
+      const std::string b = "enc.conv" + std::to_string(l);
+      add(0, b + ".w", {4, 4, cin, cout});
+      add(0, b + ".g", {cout});
+      add(0, b + ".b", {cout});
+      cin = cout;
+    }
+  } else {
+    mlp(0, "enc", cfg.obs_dim, L);
+  }
+  mlp(0, "post", E + G, 1);
+  dense(0, "post.repr", D, Z);
+  mlp(0, "dyn", G, 1);
+  dense(0, "dyn.repr", D, Z);
+  add(0, "initial_h", {G});
+  mlp(0, "seq.pre", Z + A, 1);
+  add(0, "seq.gru.kernel", {D, 3 * G});
+  add(0, "seq.gru.recurrent", {G, 3 * G});
+  add(0, "seq.gru.bias", {2, 3 * G});
+  mlp(0, "rew", G + Z, L);
+  dense(0, "rew.head", D, DV3_NB);
+  mlp(0, "cont", G + Z, L);
+  dense(0, "cont.out", D, 1);
+  if (image) {
+    const int c0 = 8 * m;
+    dense(0, "dec.dense", G + Z, 16 * c0);
+    int cin = c0;
+    for (int l = 0; l < 3; ++l) {
+      const int cout = cin / 2;
+      const std::string b = "dec.convT" + std::to_string(l);
+      add(0, b + ".w", {4, 4, cout, cin});
+      add(0, b + ".g", {cout});
+      add(0, b + ".b", {cout});
+      cin = cout;
+    }
+    add(0, "dec.out.w", {4, 4, cfg.img_c, cin});
+    add(0, "dec.out.bias", {cfg.img_c});
+  } else {
+    mlp(0, "dec", G + Z, L);
+    dense(0, "dec.out", D, cfg.obs_dim);
+  }
+  mlp(1, "actor", G + Z, L);
+  dense(1, "actor.out", D, A);
+  if (!discrete) {
+    mlp(1, "actor.std", G + Z, L);
+    dense(1, "actor.std_out", D, A);
+  }
+  mlp(2, "critic", G + Z, L);
+  dense(2, "critic.head", D, DV3_NB);
+  mlp(3, "critic_ema", G + Z, L);
+  dense(3, "critic_ema.head", D, DV3_NB);
+}
+
+float* Engine::P(const std::string& name) const {
+  for (const auto& p : pinfo)
+    if (p.name == name) return params[p.group] + p.off;
+  fprintf(stderr, "dv3: unknown parameter %s\n", name.c_str());
+  abort();
+}
+float* Engine::dP(const std::string& name) const {
+  for (const auto& p : pinfo)
+    if (p.name == name) return p.group < 3 ? grads[p.group] + p.off : nullptr;
+  fprintf(stderr, "dv3: unknown parameter %s\n", name.c_str());
+  abort();
+}
+
+void Engine::bind_mlp(Mlp& mdl, const std::string& prefix, int in_dim, int L_, bool has_grad) {
+  mdl.layers.clear();
+  int k = in_dim;
+  for (int l = 0; l < L_; ++l) {
+    const std::string b = prefix + ".mlp" + std::to_string(l);
+    LnLayer ly;
+    ly.in = k; ly.out = D;
+    ly.w = P(b + ".w"); ly.g = P(b + ".g"); ly.b = P(b + ".b");
+    if (has_grad) { ly.dw = dP(b + ".w"); ly.dg = dP(b + ".g"); ly.db = dP(b + ".b"); }
+    mdl.layers.push_back(ly);
+    k = D;
+  }
+}
+void Engine::bind_dense(DenseLayer& d, const std::string& prefix, int in, int out, bool has_grad) {
+  d.in = in; d.out = out;
+  d.w = P(prefix + ".w"); d.bias = P(prefix + ".bias");
+  if (has_grad) { d.dw = dP(prefix + ".w"); d.dbias = dP(prefix + ".bias"); }
+}
+
+void Engine::bind_params() {
+  const int m = cfg.cnn_mult;
+  if (image) {
+    int cin = cfg.img_c, hin = cfg.img_hw;
+    for (int l = 0; l < 4; ++l) {
+      const std::string b = "enc.conv" + std::to_string(l);
+      ConvLayer& c = enc_conv[l];
+      c.cin = cin; c.cout = m << l; c.hin = hin;
+      c.w = P(b + ".w"); c.g = P(b + ".g"); c.b = P(b + ".b");
+      c.dw = dP(b + ".w"); c.dg = dP(b + ".g"); c.db = dP(b + ".b");
+      cin = c.cout; hin /= 2;
+    }
+    const int c0 = 8 * m;
+    bind_dense(dec_dense, "dec.dense", G + Z, 16 * c0);
+    cin = c0; hin = 4;
+    for (int l = 0; l < 3; ++l) {
+      const std::string b = "dec.convT" + std::to_string(l);
+      ConvLayer& c = dec_convT[l];
+      c.cin = cin; c.cout = cin / 2; c.hin = hin;
+      c.w = P(b + ".w"); c.g = P(b + ".g"); c.b = P(b + ".b");
+      c.dw = dP(b + ".w"); c.dg = dP(b + ".g"); c.db = dP(b + ".b");
+      cin = c.cout; hin *= 2;
+    }
+    dec_out_conv.in = cin; dec_out_conv.out = cfg.img_c;
+    dec_out_conv.w = P("dec.out.w"); dec_out_conv.bias = P("dec.out.bias");
+    dec_out_conv.dw = dP("dec.out.w"); dec_out_conv.dbias = dP("dec.out.bias");
+  } else {
+    bind_mlp(enc_mlp, "enc", cfg.obs_dim, L);
+    bind_mlp(dec_mlp, "dec", G + Z, L);
+    bind_dense(dec_out, "dec.out", D, cfg.obs_dim);
+  }
+  bind_mlp(post_mlp, "post", E + G, 1);
+  bind_dense(post_repr, "post.repr", D, Z);
+  bind_mlp(dyn_mlp, "dyn", G, 1);
+  bind_dense(dyn_repr, "dyn.repr", D, Z);
+  initial_h = P("initial_h"); d_initial_h = dP("initial_h");
+  bind_mlp(pre_mlp, "seq.pre", Z + A, 1);
+  gru_K = P("seq.gru.kernel"); d_gru_K = dP("seq.gru.kernel");
+  gru_U = P("seq.gru.recurrent"); d_gru_U = dP("seq.gru.recurrent");
+  gru_b = P("seq.gru.bias"); d_gru_b = dP("seq.gru.bias");
+  bind_mlp(rew_mlp, "rew", G + Z, L);
+  bind_dense(rew_head, "rew.head", D, DV3_NB);
+  bind_mlp(cont_mlp, "cont", G + Z, L);
+  bind_dense(cont_out, "cont.out", D, 1);
+  bind_mlp(actor_mlp, "actor", G + Z, L);
+  bind_dense(actor_out, "actor.out", D, A);
+  if (!discrete) {
+    bind_mlp(actor_std_mlp, "actor.std", G + Z, L);
+    bind_dense(actor_std_out, "actor.std_out", D, A);
+  }
+  bind_mlp(critic_mlp, "critic", G + Z, L);
+  bind_dense(critic_head, "critic.head", D, DV3_NB);
+  bind_mlp(ema_mlp, "critic_ema", G + Z, L, false);
+  bind_dense(ema_head, "critic_ema.head", D, DV3_NB, false);
+}
+
+// ------------------------------------------------------------------------------------------ memory
+void* Engine::alloc_bytes(const std::string& name, size_t bytes, int dtype, std::vector<int64_t> shape, int kind,
+                          int group) {
+  arena_off = (arena_off + 255) / 256 * 256;
+  void* p = dry ? nullptr : (void*)(arena + arena_off);
+  arena_off += bytes;
+  if (!dry && !name.empty()) {
+    index[name] = (int)tensors.size();
+    tensors.push_back(TensorEntry{name, p, dtype, shape, kind, group, bytes});
+  }
+  return p;
+}
+float* Engine::af(const std::string& name, std::vector<int64_t> shape, int kind) {
+  return (float*)alloc_bytes(name, (size_t)prod(shape) * 4, 0, shape, kind, -1);
+}
+int32_t* Engine::ai(const std::string& name, std::vector<int64_t> shape, int kind) {
+  return (int32_t*)alloc_bytes(name, (size_t)prod(shape) * 4, 1, shape, kind, -1);
+}
+MlpAct Engine::alloc_mlp_act(const std::string& name, long long rows, int L_) {
+  MlpAct a;
+  a.rows = rows;
+  for (int l = 0; l < L_; ++l) {
+    const std::string b = name + ".l" + std::to_string(l);
+    a.pre.push_back(af(b + ".pre", {rows, D}));
+    a.act.push_back(af(b + ".act", {rows, D}));
+    a.mean.push_back(af("", {rows}));
+    a.rstd.push_back(af("", {rows}));
+  }
+  return a;
+}
+
+void Engine::layout() {
+  const long long Nl = N, Rl = R, HN = (long long)H * N;
+  const int m = cfg.cnn_mult;
+  // ---- inputs ----
+  if (image) in_obs = af("in.obs", {B, T, cfg.img_hw, cfg.img_hw, cfg.img_c}, 4);
+  else in_obs = af("in.obs", {B, T, cfg.obs_dim}, 4);
+  in_actions = af("in.actions", {B, T, A}, 4);
+  in_is_first = af("in.is_first", {B, T}, 4);
+  in_rewards = af("in.rewards", {B, T}, 4);
+  in_is_term = af("in.is_terminated", {B, T}, 4);
+  in_u_post = af("in.u_post", {T, B, Zc}, 4);
+  in_u_dyn = af("in.u_dyn", {H, Nl, Zc}, 4);
+  if (discrete) in_act_noise = af("in.act_noise", {H + 1, Nl}, 4);
+  else in_act_noise = af("in.act_noise", {H + 1, Nl, A}, 4);
+  in_dream_h0 = af("in.dream_h0", {Nl, G}, 4);
+  in_dream_z0 = af("in.dream_z0", {Nl, Z}, 4);
+  // ---- observe ----
+  if (cfg.symlog_obs) obs_sym = af("wm.obs_symlog", {Nl, OF});
+  else obs_sym = in_obs;
+  if (image) {
+    for (int l = 0; l < 4; ++l) {
+      const long long rows = Nl * (cfg.img_hw >> (l + 1)) * (cfg.img_hw >> (l + 1));
+      const int cout = m << l;
+      const std::string b = "wm.enc.conv" + std::to_string(l);
+      enc_conv[l].pre = af(b + ".pre", {rows, cout});
+      enc_conv[l].act = af(l == 3 ? "wm.enc_out" : b + ".act", l == 3 ? std::vector<int64_t>{Nl, E} : std::vector<int64_t>{rows, cout});
+      enc_conv[l].mean = af("", {rows});
+      enc_conv[l].rstd = af("", {rows});
+    }
+    enc_out = enc_conv[3].act;
+  } else {
+    enc_act = alloc_mlp_act("wm.enc", Nl, L);
+    enc_out = dry ? nullptr : enc_act.act.back();
+  }
+  a_in = af("wm.a_in", {Nl, A});
+  wf = af("wm.first_weight", {Nl});
+  actW = af("wm.actW", {Nl, D});
+  h0 = af("wm.h0", {G});
+  z0 = af("wm.z0", {Z});
+  q0_pre = af("", {D}); q0_act = af("", {D}); z0_logits = af("", {Z});
+  h_in = af("wm.h_in", {Nl, G});
+  z_in = af("wm.z_in", {Nl, Z});
+  x_pre = af("wm.x_pre", {Nl, D}); x_mean = af("", {Nl}); x_rstd = af("", {Nl});
+  u_act = af("wm.u", {Nl, D});
+  gx = af("wm.gates", {Nl, 3 * G});
+  gh = af("wm.gh", {Nl, 3 * G});
+  hz = af("wm.hz", {Nl, G + Z});
+  p_pre = af("wm.p_pre", {Nl, D}); p_mean = af("", {Nl}); p_rstd = af("", {Nl});
+  p_act = af("wm.p_act", {Nl, D});
+  post_logits = af("wm.post_logits", {Nl, Z});
+  post_probs = af("wm.z_posterior_probs", {Nl, Zc, Zk});
+  z_idx = ai("wm.z_indices", {Nl, Zc});
+  q_pre = af("wm.q_pre", {Nl, D}); q_mean = af("", {Nl}); q_rstd = af("", {Nl});
+  q_act = af("wm.q_act", {Nl, D});
+  prior_logits = af("wm.prior_logits", {Nl, Z});
+  prior_probs = af("wm.z_prior_probs", {Nl, Zc, Zk});
+  rew_act = alloc_mlp_act("wm.rew", Nl, L);
+  cont_act = alloc_mlp_act("wm.cont", Nl, L);
+  rew_logits = af("wm.reward_logits", {Nl, DV3_NB});
+  rew_E = af("wm.rewards", {Nl});
+  cont_logit = af("wm.continue_logits", {Nl});
+  obs_loc = af("wm.obs_loc", {Nl, OF});
+  if (image) {
+    const int c0 = 8 * m;
+    dec_dense_out = af("wm.dec.dense_out", {Nl, 16 * c0});
+    int hin = 4, cin = c0;
+    for (int l = 0; l < 3; ++l) {
+      const long long rows = Nl * (2 * hin) * (2 * hin);
+      const int cout = cin / 2;
+      const std::string b = "wm.dec.convT" + std::to_string(l);
+      dec_convT[l].pre = af(b + ".pre", {rows, cout});
+      dec_convT[l].act = af(b + ".act", {rows, cout});
+      dec_convT[l].mean = af("", {rows});
+      dec_convT[l].rstd = af("", {rows});
+      hin *= 2; cin = cout;
+    }
+    const long long cols_elems = Nl * 4096LL * m > Nl * 1024LL * 16 * cfg.img_c ? Nl * 4096LL * m : Nl * 1024LL * 16 * cfg.img_c;
+    cols = af("", {cols_elems});
+    const long long big = Nl * 1024LL * m > Nl * 128LL * m ? Nl * 1024LL * m : Nl * 128LL * m;
+    conv_d0 = af("", {big}); conv_d1 = af("", {big}); conv_dpre = af("", {big});
+  } else {
+    dec_act = alloc_mlp_act("wm.dec", Nl, L);
+  }
+  // ---- wm losses / grads of activations ----
+  L_dec = af("wm.L_decoder_B_T", {B, T}); L_rew = af("wm.L_reward_B_T", {B, T}); L_con = af("wm.L_continue_B_T", {B, T});
+  L_dyn = af("wm.L_dynamics_B_T", {B, T}); L_rep = af("wm.L_representation_B_T", {B, T}); L_tot = af("wm.L_total_B_T", {B, T});
+  wm_scalars = af("wm.scalars", {8});
+  rew_k = ai("wm.reward_two_hot_k", {Nl});
+  dloc = af("wm.d_obs_loc", {Nl, OF});
+  drew_logits = af("wm.d_reward_logits", {Nl, DV3_NB});
+  dcont_logit = af("wm.d_continue_logits", {Nl});
+  dpost = af("wm.d_post_probs", {Nl, Z});
+  dprior = af("wm.d_prior_probs", {Nl, Z});
+  d_hz = af("wm.d_hz", {Nl, G + Z});
+  dpost_logits = af("wm.d_post_logits", {Nl, Z});
+  dp_pre = af("wm.d_p_pre", {Nl, D});
+  dgx = af("wm.d_gx", {Nl, 3 * G}); dgh = af("wm.d_gh", {Nl, 3 * G});
+  dh_in = af("wm.d_h_in", {Nl, G});
+  dx_pre = af("wm.d_x_pre", {Nl, D});
+  dprior_logits = af("wm.d_prior_logits", {Nl, Z});
+  dq_pre = af("wm.d_q_pre", {Nl, D});
+  d_enc_out = af("wm.d_enc_out", {Nl, E});
+  dh0 = af("wm.d_h0", {G});
+  sB_D0 = af("", {B, D}); sB_D1 = af("", {B, D}); sB_Z = af("", {B, Z});
+  sN_D0 = af("", {Rl, D}); sN_D1 = af("", {Rl, D});
+  // ---- dream ----
+  dr_hz = af("dream.hz", {H + 1, Nl, G + Z});
+  dr_act = af("dream.actions", {H + 1, Nl, A});
+  dr_x_pre = af("", {HN, D}); dr_x_mean = af("", {HN}); dr_x_rstd = af("", {HN});
+  dr_u = af("", {HN, D});
+  dr_gx = af("", {HN, 3 * G}); dr_gh = af("", {HN, 3 * G});
+  dr_q_pre = af("", {HN, D}); dr_q_mean = af("", {HN}); dr_q_rstd = af("", {HN}); dr_q_act = af("", {HN, D});
+  dr_prior_logits = af("", {HN, Z});
+  dr_prior_probs = af("dream.z_prior_probs", {H, Nl, Zc, Zk});
+  dr_z_idx = ai("dream.z_indices", {H, Nl, Zc});
+  dr_a_idx = ai("dream.action_indices", {H + 1, Nl});
+  actor_act = alloc_mlp_act("dream.actor", Rl, L);
+  if (!discrete) actor_std_act = alloc_mlp_act("dream.actor_std", Rl, L);
+  dr_rew_act = alloc_mlp_act("dream.rew", Rl, L);
+  dr_cont_act = alloc_mlp_act("dream.cont", Rl, L);
+  critic_act = alloc_mlp_act("dream.critic", Rl, L);
+  ema_act = alloc_mlp_act("dream.critic_ema", Rl, L);
+  actor_logits = af("dream.actor_out", {H + 1, Nl, A});
+  actor_probs = af("dream.actor_probs", {H + 1, Nl, A});
+  actor_s = af("dream.actor_std_out", {H + 1, Nl, A});
+  dr_rew_logits = af("dream.reward_logits", {Rl, DV3_NB});
+  dr_rew_E = af("dream.rewards_symlog", {H + 1, Nl});
+  dr_cont_logit = af("dream.continue_logits", {H + 1, Nl});
+  critic_logits = af("dream.value_logits", {Rl, DV3_NB});
+  v_E = af("dream.values_symlog", {H + 1, Nl});
+  ema_logits = af("", {Rl, DV3_NB});
+  ema_E = af("dream.values_symlog_ema", {H + 1, Nl});
+  ac_r = af("dream.rewards", {H + 1, Nl}); ac_c = af("dream.continues", {H + 1, Nl});
+  ac_w = af("dream.loss_weights", {H + 1, Nl}); ac_v = af("dream.values", {H + 1, Nl});
+  ac_targets = af("ac.value_targets", {H, Nl});
+  ac_targets_all = af("ac.value_targets_all", {(long long)cfg.world_size, H, Nl});
+  pct_ema = af("ac.pct_ema", {2}, 6);
+  pct_raw = af("ac.pct_raw", {2});
+  ac_scalars = af("ac.scalars", {16});
+  dcritic_logits = af("ac.d_value_logits", {Rl, DV3_NB});
+  dactor_logits = af("ac.d_actor_out", {Rl, A});
+  dmu = dactor_logits;
+  ds = af("ac.d_actor_std_out", {Rl, A});
+  dR = af("ac.d_targets", {H, Nl}); dV = af("ac.d_values", {H + 1, Nl});
+  drew_E = af("", {Rl}); dv_E = af("", {Rl});
+  d_dr_hz = af("ac.d_dream_hz", {Rl, G + Z});
+  dr_dlogits255 = af("", {Rl, DV3_NB});
+  L_critic_HB = af("ac.CRITIC_L_total_H_B", {H, Nl}); L_val_HB = af("ac.CRITIC_L_neg_logp_of_value_targets_H_B", {H, Nl});
+  L_reg_HB = af("ac.CRITIC_L_slow_critic_regularization_H_B", {H, Nl});
+  targets_symlog = af("ac.VALUE_TARGETS_symlog_H_B", {H, Nl});
+  L_actor_HB = af("ac.ACTOR_L_total_H_B", {H, Nl}); logp_HB = af("ac.ACTOR_logp_actions_dreamed_H_B", {H, Nl});
+  scaled_HB = af("ac.ACTOR_scaled_value_targets_H_B", {H, Nl}); ent_HB = af("ac.ACTOR_action_entropy_H_B", {H, Nl});
+  L_reinf_HB = af("ac.ACTOR_L_neglogp_reinforce_term_H_B", {H, Nl}); L_ent_HB = af("ac.ACTOR_L_neg_entropy_term_H_B", {H, Nl});
+  sN_Z = af("", {Nl, Z}); sN_3G0 = af("", {Nl, 3 * G}); sN_3G1 = af("", {Nl, 3 * G}); sN_A = af("", {Nl, A});
+  noise_step = (unsigned long long*)alloc_bytes("noise_step", 8, 1, {2}, 6, -1);
+}
+
+int Engine::init(const dv3_config* c) {
+  cfg = *c;
+  if (cfg.abi_version != DV3_ABI_VERSION) return fail("dv3_config.abi_version mismatch");
+  G = cfg.G; D = cfg.D; L = cfg.L; Zc = cfg.Zc; Zk = cfg.Zk; Z = Zc * Zk; A = cfg.A;
+  B = cfg.B; T = cfg.T; H = cfg.H; N = B * T; R = (H + 1) * N;
+  discrete = cfg.discrete != 0; image = cfg.image_obs != 0;
+  if (cfg.world_size < 1) cfg.world_size = 1;
+  inv_world = 1.0f / (float)cfg.world_size;
+  if (G <= 0 || D <= 0 || L <= 0 || Zc <= 0 || Zk <= 0 || A <= 0 || B <= 0 || T <= 0 || H <= 0) return fail("non-positive dimension in dv3_config");
+  if (Zk > 32) return fail("Zk (classes per categorical) must be <= 32");
+  if (D > 1024) return fail("dense width D must be <= 1024");
+  if (discrete && A > 32) return fail("Discrete action spaces with more than 32 actions are not supported");
+  if (L > 8) return fail("at most 8 MLP layers");
+  if (image) {
+    if (cfg.img_hw != 64) return fail("image observations must be 64x64");
+    if (8 * cfg.cnn_mult > 1024) return fail("cnn multiplier too large");
+    E = 16 * 8 * cfg.cnn_mult;
+    OF = cfg.img_hw * cfg.img_hw * cfg.img_c;
+  } else {
+    E = D;
+    OF = cfg.obs_dim;
+  }
+  if (cfg.compute_mode != 0 && cfg.compute_mode != 1) return fail("compute_mode must be 0 (fp32) or 1 (bf16 tensor cores)");
+  CK(cudaSetDevice(cfg.device));
+  build_param_table();
+  for (int g = 0; g < 4; ++g) {
+    const size_t bytes = (size_t)numel[g] * 4;
+    CK(cudaMalloc((void**)&params[g], bytes)); allocations.push_back(params[g]);
+    CK(cudaMemset(params[g], 0, bytes));
+    if (g < 3) {
+      CK(cudaMalloc((void**)&grads[g], bytes)); allocations.push_back(grads[g]);
+      CK(cudaMalloc((void**)&adam_m[g], bytes)); allocations.push_back(adam_m[g]);
+      CK(cudaMalloc((void**)&adam_v[g], bytes)); allocations.push_back(adam_v[g]);
+      CK(cudaMemset(grads[g], 0, bytes)); CK(cudaMemset(adam_m[g], 0, bytes)); CK(cudaMemset(adam_v[g], 0, bytes));
+      char* st = nullptr;
+      CK(cudaMalloc((void**)&st, 64)); allocations.push_back(st);
+      CK(cudaMemset(st, 0, 64));
+      adam[g].sumsq = (double*)st; adam[g].stats = (float*)(st + 16); adam[g].step = (int*)(st + 32);
+      const char* gn[3] = {"world_model", "actor", "critic"};
+      index[std::string("opt.") + gn[g] + ".stats"] = (int)tensors.size();
+      tensors.push_back(TensorEntry{std::string("opt.") + gn[g] + ".stats", adam[g].stats, 0, {4}, 6, g, 16});
+      index[std::string("opt.") + gn[g] + ".step"] = (int)tensors.size();
+      tensors.push_back(TensorEntry{std::string("opt.") + gn[g] + ".step", adam[g].step, 1, {1}, 6, g, 4});
+    }
+  }
+  for (const auto& p : pinfo) {
+    const size_t bytes = (size_t)prod(p.shape) * 4;
+    index[p.name] = (int)tensors.size();
+    tensors.push_back(TensorEntry{p.name, params[p.group] + p.off, 0, p.shape, 0, p.group, bytes});
+    if (p.group < 3) {
+      index["grad." + p.name] = (int)tensors.size();
+      tensors.push_back(TensorEntry{"grad." + p.name, grads[p.group] + p.off, 0, p.shape, 1, p.group, bytes});
+      index["adam_m." + p.name] = (int)tensors.size();
+      tensors.push_back(TensorEntry{"adam_m." + p.name, adam_m[p.group] + p.off, 0, p.shape, 2, p.group, bytes});
+      index["adam_v." + p.name] = (int)tensors.size();
+      tensors.push_back(TensorEntry{"adam_v." + p.name, adam_v[p.group] + p.off, 0, p.shape, 3, p.group, bytes});
+    }
+  }
+  dry = true; arena_off = 0;
+  layout();
+  arena_size = arena_off + 256;
+  CK(cudaMalloc((void**)&arena, arena_size)); allocations.push_back(arena);
+  CK(cudaMemset(arena, 0, arena_size));
+  dry = false; arena_off = 0;
+  layout();
+  bind_params();
+  // LayerNorm gains default to 1 so that an un-initialised engine is still well defined.
+  for (const auto& p : pinfo) {
+    if (p.name.size() > 2 && p.name.compare(p.name.size() - 2, 2, ".g") == 0)
+      fill_f32(nullptr, params[p.group] + p.off, 1.0f, prod(p.shape));
+  }
+  const float nanv[2] = {NAN, NAN};
+  CK(cudaMemcpy(pct_ema, nanv, 8, cudaMemcpyHostToDevice));
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+void Engine::destroy() {
+  if (graph_exec) cudaGraphExecDestroy(graph_exec);
+  for (void* p : allocations) cudaFree(p);
+  allocations.clear();
+}
+
+// ------------------------------------------------------------------------------------------ building blocks
+void Engine::mm(const float* A_, int lda, bool ta, const float* B_, int ldb, bool tb, float* C, int ldc, int M, int N_,
+                int K, const float* bias, float beta) {
+  GemmArgs g{A_, lda, ta ? 1 : 0, B_, ldb, tb ? 1 : 0, C, ldc, M, N_, K, bias, beta};
+  gemm_dispatch(cur, g, cfg.compute_mode);
+}
+
+void Engine::mlp_fwd(const Mlp& mdl, MlpAct& a, const float* x, int ldx, long long rows, long long row_off) {
+  const float* in = x;
+  int ldin = ldx;
+  for (size_t l = 0; l < mdl.layers.size(); ++l) {
+    const LnLayer& ly = mdl.layers[l];
+    float* pre = a.pre[l] + row_off * ly.out;
+    float* act = a.act[l] + row_off * ly.out;
+    mm(in, ldin, false, ly.w, ly.out, false, pre, ly.out, (int)rows, ly.out, ly.in);
+    ln_silu_fwd(cur, pre, ly.out, ly.g, ly.b, act, ly.out, a.mean[l] + row_off, a.rstd[l] + row_off, 1, rows, ly.out);
+    in = act; ldin = ly.out;
+  }
+}
+
+void Engine::mlp_bwd(const Mlp& mdl, MlpAct& a, const float* x, int ldx, float* dtop, float* scratch, float* dx,
+                     int lddx, bool wgrad, long long rows, long long row_off) {
+  float* dcur = dtop;
+  float* dpre = scratch;
+  for (int l = (int)mdl.layers.size() - 1; l >= 0; --l) {
+    const LnLayer& ly = mdl.layers[l];
+    const float* pre = a.pre[l] + row_off * ly.out;
+    ln_silu_bwd(cur, dcur, ly.out, pre, ly.out, a.mean[l] + row_off, a.rstd[l] + row_off, ly.g, ly.b, dpre, ly.out,
+                wgrad ? ly.dg : nullptr, wgrad ? ly.db : nullptr, 1, rows, ly.out);
+    const float* in = (l == 0) ? x : a.act[l - 1] + row_off * mdl.layers[l - 1].out;
+    const int ldin = (l == 0) ? ldx : mdl.layers[l - 1].out;
+    if (wgrad) mm(in, ldin, true, dpre, ly.out, false, ly.dw, ly.out, ly.in, ly.out, (int)rows, nullptr, 1.f);
+    if (l > 0) mm(dpre, ly.out, false, ly.w, ly.out, true, dcur, ly.in, (int)rows, ly.in, ly.out);
+    else if (dx != nullptr) mm(dpre, ly.out, false, ly.w, ly.out, true, dx, lddx, (int)rows, ly.in, ly.out, nullptr, 1.f);
+  }
+}
+
+void Engine::dense_bwd(const DenseLayer& d, const float* x, int ldx, const float* dy, int lddy, float* dx, int lddx,
+                       float dx_beta, bool wgrad, long long rows) {
+  if (wgrad) {
+    mm(x, ldx, true, dy, lddy, false, d.dw, d.out, d.in, d.out, (int)rows, nullptr, 1.f);
+    if (d.dbias) colsum_acc(cur, dy, lddy, rows, d.out, d.dbias);
+  }
+  if (dx != nullptr) mm(dy, lddy, false, d.w, d.out, true, dx, lddx, (int)rows, d.in, d.out, nullptr, dx_beta);
+}
+
+// ------------------------------------------------------------------------------------------ encoder / decoder
+void Engine::encoder_fwd() {
+  if (!image) {
+    mlp_fwd(enc_mlp, enc_act, obs_sym, OF, N);
+    return;
+  }
+  const float* x = obs_sym;
+  for (int l = 0; l < 4; ++l) {
+    ConvLayer& c = enc_conv[l];
+    const int ho = c.hin / 2;
+    const long long rows = (long long)N * ho * ho;
+    im2col_k4s2(cur, x, cols, N, c.hin, c.hin, c.cin);
+    mm(cols, 16 * c.cin, false, c.w, c.cout, false, c.pre, c.cout, (int)rows, c.cout, 16 * c.cin);
+    ln_silu_fwd(cur, c.pre, c.cout, c.g, c.b, c.act, c.cout, c.mean, c.rstd, 1, rows, c.cout);
+    x = c.act;
+  }
+}
+
+void Engine::encoder_bwd(float* d_enc) {
+  if (!image) {
+    mlp_bwd(enc_mlp, enc_act, obs_sym, OF, d_enc, sN_D1, nullptr, 0, true, N);
+    return;
+  }
+  float* dcur = d_enc;
+  float* bufs[2] = {conv_d0, conv_d1};
+  int flip = 0;
+  for (int l = 3; l >= 0; --l) {
+    ConvLayer& c = enc_conv[l];
+    const int ho = c.hin / 2;
+    const long long rows = (long long)N * ho * ho;
+    ln_silu_bwd(cur, dcur, c.cout, c.pre, c.cout, c.mean, c.rstd, c.g, c.b, conv_dpre, c.cout, c.dg, c.db, 1, rows, c.cout);
+    const float* xin = (l == 0) ? obs_sym : enc_conv[l - 1].act;
+    im2col_k4s2(cur, xin, cols, N, c.hin, c.hin, c.cin);
+    mm(cols, 16 * c.cin, true, conv_dpre, c.cout, false, c.dw, c.cout, 16 * c.cin, c.cout, (int)rows, nullptr, 1.f);
+    if (l > 0) {
+      mm(conv_dpre, c.cout, false, c.w, c.cout, true, cols, 16 * c.cin, (int)rows, 16 * c.cin, c.cout);
+      float* dnext = bufs[flip]; flip ^= 1;
+      col2im_k4s2(cur, cols, dnext, N, c.hin, c.hin, c.cin, nullptr, 0.f);
+      dcur = dnext;
+    }
+  }
+}
+
+void Engine::decoder_fwd() {
+  if (!image) {
+    mlp_fwd(dec_mlp, dec_act, hz, G + Z, N);
+    mm(dec_act.act.back(), D, false, dec_out.w, OF, false, obs_loc, OF, N, OF, D, dec_out.bias);
+    return;
+  }
+  const int c0 = 8 * cfg.cnn_mult;
+  mm(hz, G + Z, false, dec_dense.w, 16 * c0, false, dec_dense_out, 16 * c0, N, 16 * c0, G + Z, dec_dense.bias);
+  const float* x = dec_dense_out;
+  for (int l = 0; l < 3; ++l) {
+    ConvLayer& c = dec_convT[l];
+    const long long rows_in = (long long)N * c.hin * c.hin, rows_out = rows_in * 4;
+    mm(x, c.cin, false, c.w, c.cin, true, cols, 16 * c.cout, (int)rows_in, 16 * c.cout, c.cin);
+    col2im_k4s2(cur, cols, c.pre, N, 2 * c.hin, 2 * c.hin, c.cout, nullptr, 0.f);
+    ln_silu_fwd(cur, c.pre, c.cout, c.g, c.b, c.act, c.cout, c.mean, c.rstd, 1, rows_out, c.cout);
+    x = c.act;
+  }
+  const int mi = dec_out_conv.in, ci = dec_out_conv.out;
+  mm(x, mi, false, dec_out_conv.w, mi, true, cols, 16 * ci, N * 1024, 16 * ci, mi);
+  col2im_k4s2(cur, cols, obs_loc, N, 64, 64, ci, dec_out_conv.bias, 0.5f);  // conv_transpose_atari.py:121
+}
+
+void Engine::decoder_bwd() {
+  if (!image) {
+    dense_bwd(dec_out, dec_act.act.back(), D, dloc, OF, sN_D0, D, 0.f, true, N);
+    mlp_bwd(dec_mlp, dec_act, hz, G + Z, sN_D0, sN_D1, d_hz, G + Z, true, N);
+    return;
+  }
+  const int mi = dec_out_conv.in, ci = dec_out_conv.out;
+  colsum_acc(cur, dloc, ci, (long long)N * 4096, ci, dec_out_conv.dbias);
+  im2col_k4s2(cur, dloc, cols, N, 64, 64, ci);
+  const float* x3 = dec_convT[2].act;
+  mm(cols, 16 * ci, true, x3, mi, false, dec_out_conv.dw, mi, 16 * ci, mi, N * 1024, nullptr, 1.f);
+  float* bufs[2] = {conv_d0, conv_d1};
+  int flip = 0;
+  float* dcur = bufs[flip]; flip ^= 1;
+  mm(cols, 16 * ci, false, dec_out_conv.w, mi, false, dcur, mi, N * 1024, mi, 16 * ci);
+  for (int l = 2; l >= 0; --l) {
+    ConvLayer& c = dec_convT[l];
+    const long long rows_in = (long long)N * c.hin * c.hin, rows_out = rows_in * 4;
+    ln_silu_bwd(cur, dcur, c.cout, c.pre, c.cout, c.mean, c.rstd, c.g, c.b, conv_dpre, c.cout, c.dg, c.db, 1, rows_out, c.cout);
+    im2col_k4s2(cur, conv_dpre, cols, N, 2 * c.hin, 2 * c.hin, c.cout);
+    const float* xin = (l == 0) ? dec_dense_out : dec_convT[l - 1].act;
+    mm(cols, 16 * c.cout, true, xin, c.cin, false, c.dw, c.cin, 16 * c.cout, c.cin, (int)rows_in, nullptr, 1.f);
+    float* dnext = bufs[flip]; flip ^= 1;
+    mm(cols, 16 * c.cout, false, c.w, c.cin, false, dnext, c.cin, (int)rows_in, c.cin, 16 * c.cout);
+    dcur = dnext;
+  }
+  dense_bwd(dec_dense, hz, G + Z, dcur, dec_dense.out, d_hz, G + Z, 1.f, true, N);
+}
+
+int Engine::optimizer_step(int group, float clip, float lr, float eps, float ema_decay, cudaStream_t s) {
+  if (group < 0 || group > 2) return fail("optimizer_step: group must be 0 (world_model), 1 (actor) or 2 (critic)");
+  cur = s;
+  grad_norm(s, grads[group], numel[group], adam[group]);
+  float* ema = (group == 2 && ema_decay > 0.f) ? params[3] : nullptr;
+  adam_step(s, params[group], grads[group], adam_m[group], adam_v[group], numel[group], clip, lr, eps, adam[group], ema, ema_decay);
+  return 0;
+}
+
+int Engine::fill_noise(uint64_t seed, uint64_t step, int which, bool device_step, cudaStream_t s) {
+  const unsigned long long* ds_ = device_step ? noise_step : nullptr;
+  const uint64_t salt = step * 7919ull;
+  if (which & 1) philox_fill(s, in_u_post, (long long)T * B * Zc, seed, salt + 1, ds_, 0);
+  if (which & 2) {
+    philox_fill(s, in_u_dyn, (long long)H * N * Zc, seed, salt + 2, ds_, 0);
+    if (discrete) philox_fill(s, in_act_noise, (long long)(H + 1) * N, seed, salt + 3, ds_, 0);
+    else philox_fill(s, in_act_noise, (long long)(H + 1) * N * A, seed, salt + 3, ds_, 1);
+  }
+  return 0;
+}
+
+}  // namespace dv3

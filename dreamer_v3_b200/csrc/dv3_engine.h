@@ -1,0 +1,162 @@
+// Engine: owns parameters / gradients / Adam slots / activations and orchestrates the hot path.
+#pragma once
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/dv3.h"
+#include "dv3_common.h"
+
+namespace dv3 {
+
+struct TensorEntry {
+  std::string name;
+  void* ptr;
+  int dtype;  // 0 f32, 1 i32
+  std::vector<int64_t> shape;
+  int kind, group;
+  size_t bytes;
+};
+
+// Dense(no bias) + LayerNorm(+SiLU) layer weights (components/mlp.py:43-61)
+struct LnLayer {
+  int in = 0, out = 0;
+  float *w = nullptr, *g = nullptr, *b = nullptr;     // params
+  float *dw = nullptr, *dg = nullptr, *db = nullptr;  // grads (null for the EMA critic)
+};
+struct DenseLayer {
+  int in = 0, out = 0;
+  float *w = nullptr, *bias = nullptr, *dw = nullptr, *dbias = nullptr;
+};
+struct Mlp {
+  std::vector<LnLayer> layers;
+};
+// activations of an MLP instance over `rows` rows (each [rows, D] contiguous)
+struct MlpAct {
+  std::vector<float*> pre, act, mean, rstd;
+  long long rows = 0;
+};
+struct ConvLayer {  // conv / convT (+LN) weights; kernel viewed as a [krows, kcols] row-major matrix
+  int cin = 0, cout = 0, hin = 0;  // hin: input spatial side
+  float *w = nullptr, *g = nullptr, *b = nullptr, *dw = nullptr, *dg = nullptr, *db = nullptr;
+  float *pre = nullptr, *act = nullptr, *mean = nullptr, *rstd = nullptr;  // activations [n*hout*hout, cout]
+};
+
+struct Engine {
+  dv3_config cfg;
+  int G, D, L, Z, Zc, Zk, A, B, T, H, N, R, E, OF;  // OF = flattened obs width, R = (H+1)*N
+  bool discrete, image;
+  float inv_world;
+  std::string err;
+  cudaStream_t cur = nullptr;
+
+  // ---- memory ----
+  std::vector<void*> allocations;
+  std::vector<TensorEntry> tensors;
+  std::unordered_map<std::string, int> index;
+  char* arena = nullptr;
+  size_t arena_off = 0, arena_size = 0;
+  bool dry = true;
+
+  float* params[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* grads[3] = {nullptr, nullptr, nullptr};
+  float* adam_m[3] = {nullptr, nullptr, nullptr};
+  float* adam_v[3] = {nullptr, nullptr, nullptr};
+  long long numel[4] = {0, 0, 0, 0};
+  AdamState adam[3];
+  struct PInfo { std::string name; int group; std::vector<int64_t> shape; long long off; };
+  std::vector<PInfo> pinfo;
+
+  // ---- weights ----
+  Mlp enc_mlp, post_mlp, dyn_mlp, pre_mlp, rew_mlp, cont_mlp, dec_mlp, actor_mlp, actor_std_mlp, critic_mlp, ema_mlp;
+  DenseLayer post_repr, dyn_repr, rew_head, cont_out, dec_out, dec_dense, actor_out, actor_std_out, critic_head, ema_head;
+  ConvLayer enc_conv[4], dec_convT[3];
+  DenseLayer dec_out_conv;  // w = [4,4,img_c,m] viewed [16*img_c, m]; bias [img_c]
+  float *initial_h = nullptr, *d_initial_h = nullptr;
+  float *gru_K = nullptr, *gru_U = nullptr, *gru_b = nullptr, *d_gru_K = nullptr, *d_gru_U = nullptr, *d_gru_b = nullptr;
+
+  // ---- inputs ----
+  float *in_obs, *in_actions, *in_is_first, *in_rewards, *in_is_term, *in_u_post, *in_u_dyn, *in_act_noise;
+  float *in_dream_h0, *in_dream_z0;
+  // ---- observe activations ----
+  float *obs_sym, *enc_out, *a_in, *wf, *actW, *h0, *z0, *q0_pre, *q0_act, *z0_logits;
+  MlpAct enc_act;
+  float *h_in, *z_in, *x_pre, *x_mean, *x_rstd, *u_act, *gx, *gh, *hz;
+  float *p_pre, *p_mean, *p_rstd, *p_act, *post_logits, *post_probs;
+  int32_t* z_idx;
+  float *q_pre, *q_mean, *q_rstd, *q_act, *prior_logits, *prior_probs;
+  MlpAct rew_act, cont_act, dec_act;
+  float *rew_logits, *rew_E, *cont_logit, *obs_loc, *dec_dense_out;
+  // conv scratch
+  float *cols = nullptr, *conv_d0 = nullptr, *conv_d1 = nullptr, *conv_dpre = nullptr;
+  // ---- wm losses / backward ----
+  float *L_dec, *L_rew, *L_con, *L_dyn, *L_rep, *L_tot, *wm_scalars;
+  int32_t* rew_k;
+  float *dloc, *drew_logits, *dcont_logit, *dpost, *dprior;
+  float *d_hz, *dpost_logits, *dp_pre, *dgx, *dgh, *dh_in, *dx_pre, *dprior_logits, *dq_pre, *d_enc_out, *dh0;
+  float *sB_D0, *sB_D1, *sB_Z;     // per-step scratch [B, D], [B, Z]
+  float *sN_D0, *sN_D1;            // [max(N,R) , max(D, ...)] scratch for MLP backward
+  // ---- dream ----
+  float *dr_hz, *dr_act;           // [R, G+Z], [R, A]
+  float *dr_x_pre, *dr_x_mean, *dr_x_rstd, *dr_u, *dr_gx, *dr_gh, *dr_q_pre, *dr_q_mean, *dr_q_rstd, *dr_q_act;
+  float *dr_prior_logits, *dr_prior_probs;
+  int32_t *dr_z_idx, *dr_a_idx;
+  MlpAct actor_act, actor_std_act, dr_rew_act, dr_cont_act, critic_act, ema_act;
+  float *actor_logits, *actor_probs, *actor_s, *dr_rew_logits, *dr_rew_E, *dr_cont_logit, *critic_logits, *v_E,
+      *ema_logits, *ema_E;
+  float *ac_r, *ac_c, *ac_w, *ac_v, *ac_targets, *ac_targets_all, *pct_ema, *pct_raw, *ac_scalars;
+  float *dcritic_logits, *dactor_logits, *dmu, *ds, *dR, *dV, *drew_E, *dv_E, *d_dr_hz, *dr_dlogits255;
+  float *L_critic_HB, *L_val_HB, *L_reg_HB, *targets_symlog, *L_actor_HB, *logp_HB, *scaled_HB, *ent_HB,
+      *L_reinf_HB, *L_ent_HB;
+  float *sN_Z, *sN_3G0, *sN_3G1, *sN_A;  // dream-backward scratch [N, Z], [N, 3G], [N, A]
+  unsigned long long* noise_step = nullptr;
+  float last_gamma = 0.997f;
+
+  // ---- graph ----
+  cudaGraphExec_t graph_exec = nullptr;
+  long long graph_launches = 0;
+  uint64_t graph_seed = 0;
+
+  // ---- methods ----
+  int init(const dv3_config* c);
+  void destroy();
+  void layout();
+  void* alloc_bytes(const std::string& name, size_t bytes, int dtype, std::vector<int64_t> shape, int kind, int group);
+  float* af(const std::string& name, std::vector<int64_t> shape, int kind = 5);
+  int32_t* ai(const std::string& name, std::vector<int64_t> shape, int kind = 5);
+  void build_param_table();
+  void bind_params();
+  float* P(const std::string& name) const;
+  float* dP(const std::string& name) const;
+  void bind_mlp(Mlp& m, const std::string& prefix, int in_dim, int L_, bool has_grad = true);
+  void bind_dense(DenseLayer& d, const std::string& prefix, int in, int out, bool has_grad = true);
+  MlpAct alloc_mlp_act(const std::string& name, long long rows, int L_);
+
+  void mm(const float* A_, int lda, bool ta, const float* B_, int ldb, bool tb, float* C, int ldc, int M, int N_, int K,
+          const float* bias = nullptr, float beta = 0.f);
+  void mlp_fwd(const Mlp& m, MlpAct& a, const float* x, int ldx, long long rows, long long row_off = 0);
+  void mlp_bwd(const Mlp& m, MlpAct& a, const float* x, int ldx, float* dtop, float* scratch, float* dx, int lddx,
+               bool wgrad, long long rows, long long row_off = 0);
+  void dense_bwd(const DenseLayer& d, const float* x, int ldx, const float* dy, int lddy, float* dx, int lddx,
+                 float dx_beta, bool wgrad, long long rows);
+
+  void encoder_fwd();
+  void encoder_bwd(float* d_enc);
+  void decoder_fwd();
+  void decoder_bwd();
+
+  int initial_state(cudaStream_t s);
+  int observe_forward(cudaStream_t s);
+  int wm_loss_backward(cudaStream_t s);
+  int optimizer_step(int group, float clip, float lr, float eps, float ema_decay, cudaStream_t s);
+  int dream_forward(float gamma, int start_from_observe, cudaStream_t s);
+  void actor_fwd(long long row_off);
+  int ac_loss_backward(const dv3_hparams* hp, int phase, cudaStream_t s);
+  int fill_noise(uint64_t seed, uint64_t step, int which, bool device_step, cudaStream_t s);
+  int train_wm(const dv3_hparams* hp, cudaStream_t s);
+  int train_ac(const dv3_hparams* hp, cudaStream_t s);
+  int train_update(const dv3_hparams* hp, uint64_t seed, int use_graph, cudaStream_t s);
+  int fail(const std::string& m) { err = m; return -1; }
+};
+
+}  // namespace dv3

@@ -1,0 +1,201 @@
+// fp32 SIMT GEMM for sm_100a: the exact-precision path (1e-4 parity mode) and the small-M scan steps.
+// C[M,N] (+)= op(A) op(B) (+ bias). Shared-memory tiled, register-blocked, float4 global loads where
+// the operand is 16-byte aligned, split-K with fp32 atomics when the tile grid is smaller than the GPU.
+#include "dv3_common.h"
+
+namespace dv3 {
+
+long long g_launches = 0;
+
+namespace {
+
+constexpr int kNumSMs = 148;
+
+template <int BM, int BN, int BK, int TM, int TN, bool TA, bool TB>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+gemm_f32_kernel(GemmArgs g, int k_per_split, int vecA, int vecB, int use_atomic) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int PAD = 4;
+  __shared__ __align__(16) float As[BK][BM + PAD];
+  __shared__ __align__(16) float Bs[BK][BN + PAD];
+
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(g.K, kbeg + k_per_split);
+  const int tx = tid % (BN / TN);
+  const int ty = tid / (BN / TN);
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    // ---- load A tile into As[k][m] ----
+    if (!TA) {
+      // A[m*lda + k], k contiguous: float4 along k
+      for (int e = tid; e < BM * (BK / 4); e += NT) {
+        const int m = e / (BK / 4), kq = (e % (BK / 4)) * 4;
+        const int gm = m0 + m, gk = k0 + kq;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gm < g.M) {
+          const float* p = g.A + (size_t)gm * g.lda + gk;
+          if (vecA && gk + 3 < kend) {
+            v = *reinterpret_cast<const float4*>(p);
+          } else {
+            if (gk + 0 < kend) v.x = p[0];
+            if (gk + 1 < kend) v.y = p[1];
+            if (gk + 2 < kend) v.z = p[2];
+            if (gk + 3 < kend) v.w = p[3];
+          }
+        }
+        As[kq + 0][m] = v.x; As[kq + 1][m] = v.y; As[kq + 2][m] = v.z; As[kq + 3][m] = v.w;
+      }
+    } else {
+      // A[k*lda + m], m contiguous: float4 along m
+      for (int e = tid; e < BK * (BM / 4); e += NT) {
+        const int k = e / (BM / 4), mq = (e % (BM / 4)) * 4;
+        const int gk = k0 + k, gm = m0 + mq;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gk < kend) {
+          const float* p = g.A + (size_t)gk * g.lda + gm;
+          if (vecA && gm + 3 < g.M) {
+            v = *reinterpret_cast<const float4*>(p);
+          } else {
+            if (gm + 0 < g.M) v.x = p[0];
+            if (gm + 1 < g.M) v.y = p[1];
+            if (gm + 2 < g.M) v.z = p[2];
+            if (gm + 3 < g.M) v.w = p[3];
+          }
+        }
+        *reinterpret_cast<float4*>(&As[k][mq]) = v;
+      }
+    }
+    // ---- load B tile into Bs[k][n] ----
+    if (!TB) {
+      // B[k*ldb + n], n contiguous
+      for (int e = tid; e < BK * (BN / 4); e += NT) {
+        const int k = e / (BN / 4), nq = (e % (BN / 4)) * 4;
+        const int gk = k0 + k, gn = n0 + nq;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gk < kend) {
+          const float* p = g.B + (size_t)gk * g.ldb + gn;
+          if (vecB && gn + 3 < g.N) {
+            v = *reinterpret_cast<const float4*>(p);
+          } else {
+            if (gn + 0 < g.N) v.x = p[0];
+            if (gn + 1 < g.N) v.y = p[1];
+            if (gn + 2 < g.N) v.z = p[2];
+            if (gn + 3 < g.N) v.w = p[3];
+          }
+        }
+        *reinterpret_cast<float4*>(&Bs[k][nq]) = v;
+      }
+    } else {
+      // B[n*ldb + k], k contiguous
+      for (int e = tid; e < BN * (BK / 4); e += NT) {
+        const int n = e / (BK / 4), kq = (e % (BK / 4)) * 4;
+        const int gn = n0 + n, gk = k0 + kq;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gn < g.N) {
+          const float* p = g.B + (size_t)gn * g.ldb + gk;
+          if (vecB && gk + 3 < kend) {
+            v = *reinterpret_cast<const float4*>(p);
+          } else {
+            if (gk + 0 < kend) v.x = p[0];
+            if (gk + 1 < kend) v.y = p[1];
+            if (gk + 2 < kend) v.z = p[2];
+            if (gk + 3 < kend) v.w = p[3];
+          }
+        }
+        Bs[kq + 0][n] = v.x; Bs[kq + 1][n] = v.y; Bs[kq + 2][n] = v.z; Bs[kq + 3][n] = v.w;
+      }
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue ----
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int gm = m0 + ty * TM + i;
+    if (gm >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int gn = n0 + tx * TN + j;
+      if (gn >= g.N) continue;
+      float c = acc[i][j];
+      if (g.bias != nullptr && blockIdx.z == 0) c += g.bias[gn];
+      float* dst = g.C + (size_t)gm * g.ldc + gn;
+      if (use_atomic) atomicAdd(dst, c);
+      else if (g.beta != 0.f) *dst += c;
+      else *dst = c;
+    }
+  }
+}
+
+template <int BM, int BN, int BK, int TM, int TN>
+void launch_tile(cudaStream_t s, const GemmArgs& g) {
+  const int gx = cdiv(g.N, BN), gy = cdiv(g.M, BM);
+  const long long tiles = (long long)gx * gy;
+  int splits = 1;
+  if (tiles < kNumSMs && g.K >= 8 * BK) {
+    splits = (int)min((long long)(2 * kNumSMs / tiles), (long long)(g.K / (4 * BK)));
+    if (splits < 1) splits = 1;
+    if (splits > 64) splits = 64;
+  }
+  int kps = cdiv(cdiv(g.K, splits), BK) * BK;
+  splits = cdiv(g.K, kps);
+  const int use_atomic = splits > 1;
+  if (use_atomic && g.beta == 0.f) zero_2d(s, g.C, g.M, g.N, g.ldc);
+  const bool a16 = ((uintptr_t)g.A % 16 == 0) && (g.lda % 4 == 0);
+  const bool b16 = ((uintptr_t)g.B % 16 == 0) && (g.ldb % 4 == 0);
+  dim3 grid(gx, gy, splits), block((BM / TM) * (BN / TN));
+  const int vA = a16, vB = b16;
+  if (!g.ta && !g.tb) gemm_f32_kernel<BM, BN, BK, TM, TN, false, false><<<grid, block, 0, s>>>(g, kps, vA, vB, use_atomic);
+  else if (!g.ta && g.tb) gemm_f32_kernel<BM, BN, BK, TM, TN, false, true><<<grid, block, 0, s>>>(g, kps, vA, vB, use_atomic);
+  else if (g.ta && !g.tb) gemm_f32_kernel<BM, BN, BK, TM, TN, true, false><<<grid, block, 0, s>>>(g, kps, vA, vB, use_atomic);
+  else gemm_f32_kernel<BM, BN, BK, TM, TN, true, true><<<grid, block, 0, s>>>(g, kps, vA, vB, use_atomic);
+  count_launch();
+}
+
+}  // namespace
+
+void gemm_f32(cudaStream_t s, const GemmArgs& g) {
+  if (g.M <= 0 || g.N <= 0) return;
+  if (g.K <= 0) {
+    if (g.beta == 0.f) zero_2d(s, g.C, g.M, g.N, g.ldc);
+    return;
+  }
+  if (g.M <= 16) {
+    launch_tile<16, 128, 16, 1, 8>(s, g);
+  } else if (g.M <= 64 || g.N <= 64 || (long long)cdiv(g.M, 128) * cdiv(g.N, 128) < kNumSMs) {
+    launch_tile<64, 64, 16, 4, 4>(s, g);
+  } else {
+    launch_tile<128, 128, 16, 8, 8>(s, g);
+  }
+}
+
+
+void gemm_dispatch(cudaStream_t s, const GemmArgs& g, int mode) {
+  (void)mode;
+  gemm_f32(s, g);
+}
+
+}  // namespace dv3

@@ -1,0 +1,155 @@
+// World-model half of the hot path: RSSM observe scan forward (world_model.py:183-326), the world-model
+// losses (world_model_losses.py) and BPTT through the scan (replaces tape.gradient, train_one_step.py:80).
+//
+// Layout: every per-timestep tensor is kept B-major [B, T, width] exactly like the reference's folded
+// "BxT" outputs, so a timestep slice is a strided view (row stride T*width) and nothing is transposed.
+// Work that does not sit on the recurrence is hoisted out of the T loop into N = B*T-row contractions:
+//   forward : encoder part of the posterior MLP, action part of the pre-GRU layer, the whole prior net
+//   backward: every weight gradient (one [N]-row contraction each after the reverse loop)
+#include "dv3_engine.h"
+
+namespace dv3 {
+
+int Engine::initial_state(cudaStream_t s) {
+  cur = s;
+  const LnLayer& Wd = dyn_mlp.layers[0];
+  tanh_fwd(s, initial_h, h0, G);  // world_model.py:128
+  mm(h0, G, false, Wd.w, D, false, q0_pre, D, 1, D, G);
+  ln_silu_fwd(s, q0_pre, D, Wd.g, Wd.b, q0_act, D, nullptr, nullptr, 1, 1, D);
+  mm(q0_act, D, false, dyn_repr.w, Z, false, z0_logits, Z, 1, Z, D, dyn_repr.bias);
+  repr_fwd(s, z0_logits, Z, nullptr, 0, nullptr, 0, nullptr, 0, z0, Z, 1, Zc, Zk, 2);  // mode, not a sample (:130-132)
+  return 0;
+}
+
+int Engine::observe_forward(cudaStream_t s) {
+  cur = s;
+  const LnLayer& Wp = post_mlp.layers[0];
+  const LnLayer& Wx = pre_mlp.layers[0];
+  const LnLayer& Wd = dyn_mlp.layers[0];
+  const int ldhz = T * (G + Z);
+
+  if (cfg.symlog_obs) symlog_fwd(s, in_obs, obs_sym, (long long)N * OF);  // world_model.py:206-207
+  encoder_fwd();
+  scan_prepare(s, in_actions, in_is_first, a_in, wf, B, T, A);
+  mm(enc_out, E, false, Wp.w, D, false, p_pre, D, N, D, E);              // hoisted: enc_t . W_post[:E]
+  mm(a_in, A, false, Wx.w + (size_t)Z * D, D, false, actW, D, N, D, A);  // hoisted: a_{t-1} . W_pre[Z:]
+  initial_state(s);
+
+  for (int t = 0; t < T; ++t) {
+    const float* hz_prev = t > 0 ? hz + (size_t)(t - 1) * (G + Z) : nullptr;
+    scan_mask_inputs(s, in_is_first + t, T, hz_prev, ldhz, hz_prev ? hz_prev + G : nullptr, ldhz, h0, z0,
+                     actW + (size_t)t * D, T * D, h_in + (size_t)t * G, T * G, z_in + (size_t)t * Z, T * Z,
+                     x_pre + (size_t)t * D, T * D, B, G, Z, D);
+    // sequence model (sequence_model.py:56-75)
+    mm(z_in + (size_t)t * Z, T * Z, false, Wx.w, D, false, x_pre + (size_t)t * D, T * D, B, D, Z, nullptr, 1.f);
+    ln_silu_fwd(s, x_pre + (size_t)t * D, T * D, Wx.g, Wx.b, u_act + (size_t)t * D, T * D, x_mean + t, x_rstd + t, T, B, D);
+    mm(u_act + (size_t)t * D, T * D, false, gru_K, 3 * G, false, gx + (size_t)t * 3 * G, T * 3 * G, B, 3 * G, D, gru_b);
+    mm(h_in + (size_t)t * G, T * G, false, gru_U, 3 * G, false, gh + (size_t)t * 3 * G, T * 3 * G, B, 3 * G, G, gru_b + 3 * G);
+    gru_fwd(s, gx + (size_t)t * 3 * G, T * 3 * G, gh + (size_t)t * 3 * G, T * 3 * G, h_in + (size_t)t * G, T * G,
+            hz + (size_t)t * (G + Z), ldhz, B, G);
+    // posterior (world_model.py:259-269)
+    mm(hz + (size_t)t * (G + Z), ldhz, false, Wp.w + (size_t)E * D, D, false, p_pre + (size_t)t * D, T * D, B, D, G, nullptr, 1.f);
+    ln_silu_fwd(s, p_pre + (size_t)t * D, T * D, Wp.g, Wp.b, p_act + (size_t)t * D, T * D, p_mean + t, p_rstd + t, T, B, D);
+    mm(p_act + (size_t)t * D, T * D, false, post_repr.w, Z, false, post_logits + (size_t)t * Z, T * Z, B, Z, D, post_repr.bias);
+    repr_fwd(s, post_logits + (size_t)t * Z, T * Z, post_probs + (size_t)t * Z, T * Z, in_u_post + (size_t)t * B * Zc, Zc,
+             z_idx + (size_t)t * Zc, T * Zc, hz + (size_t)t * (G + Z) + G, ldhz, B, Zc, Zk, 1);
+  }
+  // prior for all timesteps at once (world_model.py:272; its sample is discarded by the reference)
+  mm(hz, G + Z, false, Wd.w, D, false, q_pre, D, N, D, G);
+  ln_silu_fwd(s, q_pre, D, Wd.g, Wd.b, q_act, D, q_mean, q_rstd, 1, N, D);
+  mm(q_act, D, false, dyn_repr.w, Z, false, prior_logits, Z, N, Z, D, dyn_repr.bias);
+  repr_fwd(s, prior_logits, Z, prior_probs, Z, nullptr, 0, nullptr, 0, nullptr, 0, N, Zc, Zk, 0);
+  // heads on the folded B*T rows (world_model.py:299-309)
+  mlp_fwd(rew_mlp, rew_act, hz, G + Z, N);
+  mm(rew_act.act.back(), D, false, rew_head.w, DV3_NB, false, rew_logits, DV3_NB, N, DV3_NB, D, rew_head.bias);
+  bucket_expectation(s, rew_logits, DV3_NB, rew_E, N);
+  mlp_fwd(cont_mlp, cont_act, hz, G + Z, N);
+  mm(cont_act.act.back(), D, false, cont_out.w, 1, false, cont_logit, 1, N, 1, D, cont_out.bias);
+  decoder_fwd();
+  return 0;
+}
+
+int Engine::wm_loss_backward(cudaStream_t s) {
+  cur = s;
+  const LnLayer& Wp = post_mlp.layers[0];
+  const LnLayer& Wx = pre_mlp.layers[0];
+  const LnLayer& Wd = dyn_mlp.layers[0];
+  const int ldhz = T * (G + Z);
+  cudaMemsetAsync(grads[0], 0, (size_t)numel[0] * 4, s);
+
+  WmLossArgs a{};
+  a.B = B; a.T = T; a.Z = Z; a.Zc = Zc; a.Zk = Zk; a.obs_flat = OF;
+  a.inv_count = inv_world / (float)N;
+  a.obs = obs_sym; a.loc = obs_loc; a.rew_logits = rew_logits; a.rewards = in_rewards; a.cont_logit = cont_logit;
+  a.is_terminated = in_is_term; a.post = post_probs; a.prior = prior_probs;
+  a.L_dec = L_dec; a.L_rew = L_rew; a.L_con = L_con; a.L_dyn = L_dyn; a.L_rep = L_rep; a.L_tot = L_tot;
+  a.scalars = wm_scalars; a.dloc = dloc; a.drew_logits = drew_logits; a.dcont_logit = dcont_logit;
+  a.dpost = dpost; a.dprior = dprior; a.rew_k = rew_k;
+  wm_losses(s, a);
+
+  // heads -> d_hz
+  cudaMemsetAsync(d_hz, 0, (size_t)N * (G + Z) * 4, s);
+  decoder_bwd();
+  dense_bwd(rew_head, rew_act.act.back(), D, drew_logits, DV3_NB, sN_D0, D, 0.f, true, N);
+  mlp_bwd(rew_mlp, rew_act, hz, G + Z, sN_D0, sN_D1, d_hz, G + Z, true, N);
+  dense_bwd(cont_out, cont_act.act.back(), D, dcont_logit, 1, sN_D0, D, 0.f, true, N);
+  mlp_bwd(cont_mlp, cont_act, hz, G + Z, sN_D0, sN_D1, d_hz, G + Z, true, N);
+  // prior (dynamics predictor) on all rows: KL gradient w.r.t. prior probs -> d_hz (h part)
+  repr_bwd(s, prior_logits, Z, nullptr, 0, dprior, Z, dprior_logits, Z, N, Zc, Zk);
+  dense_bwd(dyn_repr, q_act, D, dprior_logits, Z, sN_D0, D, 0.f, true, N);
+  ln_silu_bwd(s, sN_D0, D, q_pre, D, q_mean, q_rstd, Wd.g, Wd.b, dq_pre, D, Wd.dg, Wd.db, 1, N, D);
+  mm(hz, G + Z, true, dq_pre, D, false, Wd.dw, D, G, D, N, nullptr, 1.f);
+  mm(dq_pre, D, false, Wd.w, D, true, d_hz, G + Z, N, G, D, nullptr, 1.f);
+
+  // reverse-time scan: only input gradients inside the loop
+  for (int t = T - 1; t >= 0; --t) {
+    float* dhz_t = d_hz + (size_t)t * (G + Z);
+    // posterior representation layer: straight-through dz + KL dprobs -> dlogits
+    repr_bwd(s, post_logits + (size_t)t * Z, T * Z, dhz_t + G, ldhz, dpost + (size_t)t * Z, T * Z,
+             dpost_logits + (size_t)t * Z, T * Z, B, Zc, Zk);
+    mm(dpost_logits + (size_t)t * Z, T * Z, false, post_repr.w, Z, true, sB_D0, D, B, D, Z);
+    ln_silu_bwd(s, sB_D0, D, p_pre + (size_t)t * D, T * D, p_mean + t, p_rstd + t, Wp.g, Wp.b, dp_pre + (size_t)t * D,
+                T * D, Wp.dg, Wp.db, T, B, D);
+    mm(dp_pre + (size_t)t * D, T * D, false, Wp.w + (size_t)E * D, D, true, dhz_t, ldhz, B, G, D, nullptr, 1.f);
+    // GRU
+    gru_bwd(s, dhz_t, ldhz, gx + (size_t)t * 3 * G, T * 3 * G, gh + (size_t)t * 3 * G, T * 3 * G, h_in + (size_t)t * G,
+            T * G, dgx + (size_t)t * 3 * G, T * 3 * G, dgh + (size_t)t * 3 * G, T * 3 * G, dh_in + (size_t)t * G, T * G, 0, B, G);
+    mm(dgh + (size_t)t * 3 * G, T * 3 * G, false, gru_U, 3 * G, true, dh_in + (size_t)t * G, T * G, B, G, 3 * G, nullptr, 1.f);
+    mm(dgx + (size_t)t * 3 * G, T * 3 * G, false, gru_K, 3 * G, true, sB_D0, D, B, D, 3 * G);
+    ln_silu_bwd(s, sB_D0, D, x_pre + (size_t)t * D, T * D, x_mean + t, x_rstd + t, Wx.g, Wx.b, dx_pre + (size_t)t * D,
+                T * D, Wx.dg, Wx.db, T, B, D);
+    if (t > 0) {
+      mm(dx_pre + (size_t)t * D, T * D, false, Wx.w, D, true, sB_Z, Z, B, Z, D);
+      float* dprev = d_hz + (size_t)(t - 1) * (G + Z);
+      scan_mask_grads(s, in_is_first + t, T, dh_in + (size_t)t * G, T * G, dprev, ldhz, B, G);
+      scan_mask_grads(s, in_is_first + t, T, sB_Z, Z, dprev + G, ldhz, B, Z);
+    }
+  }
+  // weight gradients, one N-row contraction each
+  dense_bwd(post_repr, p_act, D, dpost_logits, Z, nullptr, 0, 0.f, true, N);
+  mm(enc_out, E, true, dp_pre, D, false, Wp.dw, D, E, D, N, nullptr, 1.f);
+  mm(hz, G + Z, true, dp_pre, D, false, Wp.dw + (size_t)E * D, D, G, D, N, nullptr, 1.f);
+  mm(u_act, D, true, dgx, 3 * G, false, d_gru_K, 3 * G, D, 3 * G, N, nullptr, 1.f);
+  colsum_acc(s, dgx, 3 * G, N, 3 * G, d_gru_b);
+  mm(h_in, G, true, dgh, 3 * G, false, d_gru_U, 3 * G, G, 3 * G, N, nullptr, 1.f);
+  colsum_acc(s, dgh, 3 * G, N, 3 * G, d_gru_b + 3 * G);
+  mm(z_in, Z, true, dx_pre, D, false, Wx.dw, D, Z, D, N, nullptr, 1.f);
+  mm(a_in, A, true, dx_pre, D, false, Wx.dw + (size_t)Z * D, D, A, D, N, nullptr, 1.f);
+  // learned initial state: every is_first row (and every row at t = 0) starts from tanh(initial_h)
+  mm(wf, 1, true, dh_in, G, false, dh0, G, 1, G, N);
+  tanh_bwd_acc(s, dh0, h0, d_initial_h, G);
+  // encoder
+  mm(dp_pre, D, false, Wp.w, D, true, d_enc_out, E, N, E, D);
+  encoder_bwd(d_enc_out);
+  return 0;
+}
+
+int Engine::train_wm(const dv3_hparams* hp, cudaStream_t s) {
+  int rc = observe_forward(s);
+  if (rc) return rc;
+  rc = wm_loss_backward(s);
+  if (rc) return rc;
+  return optimizer_step(0, hp->wm_grad_clip, hp->wm_lr, hp->wm_eps, 0.f, s);
+}
+
+}  // namespace dv3

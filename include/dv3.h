@@ -1,0 +1,157 @@
+/*
+ * dv3.h -- C ABI of libdv3.so, the B200-native engine for the DreamerV3 training hot path.
+ *
+ * The reference (sven1977/dreamer_v3) has no FFI/plugin interface: its boundary is the Python
+ * API. Each entry point below replaces one reference function; the thin
+ * Python mirror in dreamer_v3_b200/ binds these with ctypes and re-exposes the reference's
+ * WorldModel / DreamerModel / train_*_one_step surface.
+ *
+ * Conventions
+ *   - plain C types only; every call returns 0 on success, <0 on error (dv3_last_error()).
+ *   - all tensors are fp32 row-major unless noted; "rows BxT" are B-major (row = b*T + t),
+ *     dream tensors are time-major (row = i*N + n, N = B*T), as in the reference.
+ *   - the engine owns parameters, gradients, Adam slots, activations and I/O buffers; they are
+ *     looked up by name (dv3_tensor_info) so the caller can wrap them zero-copy (DLPack /
+ *     __cuda_array_interface__) or fill them with dv3_write_tensor / read with dv3_read_tensor.
+ *   - sampling noise is an explicit input ("in.u_post", "in.u_dyn", "in.act_noise"), or is
+ *     generated on the device by dv3_fill_noise (counter-based Philox).
+ *   - every call enqueues on the caller's cudaStream_t (passed as void*); no hidden syncs
+ *     except dv3_read_tensor / dv3_write_tensor with a host pointer and sync=1.
+ *   - a handle is not thread-safe; one handle per device / rank.
+ */
+#ifndef DV3_H_
+#define DV3_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DV3_ABI_VERSION 1
+#define DV3_NUM_BUCKETS 255
+
+typedef struct dv3_engine dv3_engine; /* opaque */
+
+/* Mirrors utils/model_dimensions.py (sizes) + run_experiment.py:131-148 (B, T, H). */
+typedef struct dv3_config {
+  int32_t abi_version;   /* DV3_ABI_VERSION */
+  int32_t G;             /* GRU units            get_gru_units            */
+  int32_t D;             /* dense hidden units   get_dense_hidden_units   */
+  int32_t L;             /* MLP layers           get_num_dense_layers     */
+  int32_t cnn_mult;      /* CNN multiplier       get_cnn_multiplier       */
+  int32_t Zc, Zk;        /* categoricals x classes (Zk <= 32)             */
+  int32_t A;             /* action dim (Discrete.n or prod(Box.shape))    */
+  int32_t discrete;      /* 1 = Discrete, 0 = Box                          */
+  int32_t image_obs;     /* 1 = 64x64xC images (CNNAtari/ConvTransposeAtari), 0 = vector */
+  int32_t obs_dim;       /* vector observation width                       */
+  int32_t img_hw, img_c; /* image side (64) and channels                   */
+  int32_t B, T, H;       /* LOCAL replay batch rows, batch length, dream horizon */
+  int32_t symlog_obs;    /* world_model.py:206-207                         */
+  int32_t compute_mode;  /* 0 = fp32 SIMT everywhere; 1 = bf16 tcgen05 tensor cores for large contractions */
+  int32_t world_size;    /* data-parallel ranks (losses are normalised by world_size*B) */
+  int32_t rank;
+  int32_t device;        /* CUDA device ordinal */
+  int32_t reserved[8];
+} dv3_config;
+
+typedef struct dv3_tensor_desc {
+  const char* name;  /* owned by the engine */
+  void* ptr;         /* device pointer */
+  int32_t dtype;     /* 0 = f32, 1 = i32 */
+  int32_t ndim;
+  int64_t shape[6];
+  int32_t kind;      /* 0 param, 1 grad, 2 adam_m, 3 adam_v, 4 input, 5 output/activation, 6 scalar state */
+  int32_t group;     /* 0 world_model, 1 actor, 2 critic, 3 critic_ema, -1 n/a */
+} dv3_tensor_desc;
+
+/* Hyper-parameters of the two update steps (run_experiment.py:145-148, 245-252; world_model.py:124;
+ * actor_network.py:60; critic_network.py:23,58). dv3_default_hparams fills the reference values. */
+typedef struct dv3_hparams {
+  float gamma, lambda_, entropy_scale, return_normalization_decay;
+  float wm_grad_clip, actor_grad_clip, critic_grad_clip;
+  float wm_lr, wm_eps, ac_lr, ac_eps;
+  float critic_ema_decay;
+  int32_t train_actor;
+  int32_t reserved[7];
+} dv3_hparams;
+
+/* ---- lifetime ----------------------------------------------------------------------------- */
+int dv3_abi_version(void);
+int dv3_create(const dv3_config* cfg, dv3_engine** out); /* replaces WorldModel.__init__ (world_model.py:25-124) + DreamerModel.__init__ (dreamer_model.py:23-67) */
+int dv3_destroy(dv3_engine* e);
+const char* dv3_last_error(const dv3_engine* e); /* e may be NULL: last create() error */
+void dv3_default_hparams(dv3_hparams* hp);
+int dv3_sync(dv3_engine* e, void* stream);
+
+/* ---- tensor table ------------------------------------------------------------------------- */
+int dv3_num_tensors(const dv3_engine* e);
+int dv3_tensor_info(const dv3_engine* e, int index, dv3_tensor_desc* out);
+int dv3_find_tensor(const dv3_engine* e, const char* name, dv3_tensor_desc* out);
+/* copy nbytes between a host (or device) buffer and a named engine tensor; host_is_device=1 for D2D */
+int dv3_write_tensor(dv3_engine* e, const char* name, const void* src, size_t nbytes, int src_is_device, void* stream, int sync);
+int dv3_read_tensor(dv3_engine* e, const char* name, void* dst, size_t nbytes, int dst_is_device, void* stream, int sync);
+/* flat per-group views for the data-parallel all-reduce: kind in {0 param,1 grad,2 m,3 v} */
+int dv3_group_buffer(const dv3_engine* e, int group, int kind, void** ptr, int64_t* numel);
+
+/* ---- noise ------------------------------------------------------------------------------- */
+/* Fills in.u_post / in.u_dyn / in.act_noise on the device (uniform [0,1) or N(0,1) for Box actions). */
+int dv3_fill_noise(dv3_engine* e, uint64_t seed, uint64_t step, int which /*1=u_post,2=dream,3=both*/, void* stream);
+
+/* ---- world model -------------------------------------------------------------------------- */
+/* WorldModel.get_initial_state (world_model.py:127-134): fills out.h0 [G], out.z0 [Zc*Zk]. */
+int dv3_initial_state(dv3_engine* e, void* stream);
+/* WorldModel.forward_train (world_model.py:183-326). Reads in.obs [B,T,...], in.actions [B,T,A],
+ * in.is_first [B,T], in.u_post [T,B,Zc]; fills the wm.* outputs (see DESIGN.md tensor table). */
+int dv3_observe_forward(dv3_engine* e, void* stream);
+/* world_model_prediction_losses + world_model_dynamics_and_representation_loss + the loss
+ * reduction of train_world_model_one_step (world_model_losses.py:15-151, train_one_step.py:48-77),
+ * then BPTT through forward_train into the world_model gradient buffer.
+ * Reads in.rewards [B,T], in.is_terminated [B,T]. */
+int dv3_wm_loss_backward(dv3_engine* e, void* stream);
+/* tf.clip_by_global_norm + Keras Adam (+ critic EMA for group 2) on a group's flat buffers
+ * (train_one_step.py:80-86, 214-250). Call after the gradient all-reduce when world_size > 1. */
+int dv3_optimizer_step(dv3_engine* e, int group, float clip, float lr, float eps, float ema_decay, void* stream);
+/* One call = train_world_model_one_step (train_one_step.py:17-126) for world_size == 1. */
+int dv3_train_world_model_step(dv3_engine* e, const dv3_hparams* hp, void* stream);
+
+/* ---- dreamer / actor / critic --------------------------------------------------------------- */
+/* DreamerModel.dream_trajectory (dreamer_model.py:147-303). start states: start_from_observe=1 uses
+ * wm.hz of the last dv3_observe_forward (as run_experiment.py:458-460 does); otherwise in.dream_h0
+ * [N,G] / in.dream_z0 [N,Zc*Zk]. Reads in.is_terminated, in.u_dyn [H,N,Zc], in.act_noise. */
+int dv3_dream_forward(dv3_engine* e, float gamma, int start_from_observe, void* stream);
+/* compute_value_targets + critic_loss + actor_loss (critic_loss.py:15-139, actor_loss.py:12-138) and
+ * their gradients into the actor / critic gradient buffers (REINFORCE for Discrete, BPTT through the
+ * dream for Box). phase 1 = value targets only (so the caller can all-gather them across ranks for
+ * the percentile), phase 2 = the rest, 3 = both. */
+int dv3_ac_loss_backward(dv3_engine* e, const dv3_hparams* hp, int phase, void* stream);
+/* CriticNetwork.init_ema / update_ema (critic_network.py:84-100). */
+int dv3_critic_init_ema(dv3_engine* e, void* stream);
+int dv3_critic_update_ema(dv3_engine* e, float decay, void* stream);
+/* One call = train_actor_and_critic_one_step (train_one_step.py:130-252) for world_size == 1. */
+int dv3_train_actor_critic_step(dv3_engine* e, const dv3_hparams* hp, void* stream);
+
+/* ---- whole update captured as CUDA graphs ---------------------------------------------------- */
+/* Captures {wm step, ac step} once into a CUDA graph on `stream` and replays it: one launch per
+ * update instead of thousands. noise_seed != 0: noise is regenerated on the device each replay. */
+int dv3_train_update(dv3_engine* e, const dv3_hparams* hp, uint64_t noise_seed, int use_graph, void* stream);
+int64_t dv3_kernel_launch_count(const dv3_engine* e); /* kernels of this library launched (or replayed) so far */
+
+/* ---- isolated ops (parity tests call the same kernels the fused path uses) ---------------------- */
+int dv3_op_symlog(const float* x, float* y, int64_t n, void* stream);                 /* utils/symlog.py:9-12 */
+int dv3_op_inverse_symlog(const float* y, float* x, int64_t n, void* stream);         /* utils/symlog.py:15-28 */
+int dv3_op_two_hot(const float* value, int64_t n, int32_t* k, int32_t* kp1, float* w_k, float* w_kp1,
+                   float* dense_or_null, void* stream);                                   /* utils/two_hot.py:9-78 (255 buckets, [-20,20]) */
+int dv3_op_sample_categorical(const float* probs, const float* u, int64_t rows, int K, int32_t* idx, void* stream);
+int dv3_op_value_targets(const float* r, const float* c, const float* v, int H, int64_t N, float gamma,
+                         float lambda_, float* targets, void* stream);                 /* critic_loss.py:92-139 */
+int dv3_op_percentiles(const float* x, int64_t n, float* p5_p95, void* stream);        /* tfp.stats.percentile nearest */
+int dv3_op_gemm(const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C, int ldc,
+                int M, int N, int K, const float* bias, float beta, int mode, void* stream);
+int dv3_op_ln_silu(const float* x, const float* gamma, const float* beta, float* y, int64_t rows, int D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DV3_H_ */

@@ -1,0 +1,148 @@
+"""Shared helper of the GPU parity tests: runs the oracle (torch CPU, fp64 by default) and the CUDA
+engine on the same seeded inputs / weights / sampling noise and reports per-tensor deviations."""
+import numpy as np
+import torch
+
+from dreamer_v3_b200.engine import Engine
+from dreamer_v3_b200.spec import EngineConfig, init_params
+from oracle.dreamer_oracle import Oracle, make_synthetic_sample
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.size == 0:
+        return 0.0
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12))
+
+
+def to_np(x):
+    if torch.is_tensor(x):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+class ParityRun:
+    """One oracle-vs-engine comparison of a full train update (world model + actor/critic)."""
+
+    def __init__(self, cfg: EngineConfig, seed=0, init_mode="random", oracle_dtype=torch.float64, compute_mode=0,
+                 margin=1e-3, steps=1, sync_grads=True):
+        self.cfg = cfg
+        self.report = {}      # name -> rel err (float tensors)
+        self.exact = {}       # name -> number of mismatching integers
+        self.params0 = init_params(cfg, seed=seed + 1, mode=init_mode)
+        self.sample = make_synthetic_sample(cfg, seed=seed + 2)
+        self.rng = np.random.default_rng(seed + 3)
+        self.oracle = Oracle(cfg, self.params0, dtype=oracle_dtype)
+        self.engine = Engine(cfg, compute_mode=compute_mode)
+        self.engine.load_params(self.params0)
+        self.margin = margin
+        self.sync_grads = sync_grads
+        for _ in range(steps):
+            self.step()
+
+    def cmp(self, name, got, want):
+        self.report[name] = max(self.report.get(name, 0.0), rel_err(to_np(got), to_np(want)))
+
+    def cmp_exact(self, name, got, want):
+        got, want = to_np(got).astype(np.int64), to_np(want).astype(np.int64)
+        assert got.shape == want.shape, (name, got.shape, want.shape)
+        self.exact[name] = self.exact.get(name, 0) + int((got != want).sum())
+
+    def step(self):
+        cfg, o, e = self.cfg, self.oracle, self.engine
+        B, T, N, H, G = cfg.B, cfg.T, cfg.N, cfg.H, cfg.G
+        self.prev_params = o.numpy_params()
+        # ---------------- world model ----------------
+        res = o.train_world_model_one_step(self.sample, rng=self.rng, margin=self.margin)
+        u_post = o.last_noise["u_post"]
+        fwd = res["WORLD_MODEL_forward_train_outs"]
+        e.set_sample(self.sample)
+        e.set_noise(u_post=u_post)
+        e.observe_forward()
+        t = e.tensor
+        self.cmp("wm.enc_out", t("wm.enc_out"), fwd["encoder_out_TB"].transpose(0, 1).reshape(N, -1))
+        self.cmp("wm.h_states", t("wm.hz")[:, :G], fwd["h_states_BxT"])
+        self.cmp_exact("wm.z_indices", t("wm.z_indices"), fwd["z_indices_BxT"])
+        self.cmp("wm.z_states", t("wm.hz")[:, G:], fwd["z_states_BxT"].reshape(N, -1))
+        self.cmp("wm.z_posterior_probs", t("wm.z_posterior_probs"), fwd["z_posterior_probs_BxT"])
+        self.cmp("wm.z_prior_probs", t("wm.z_prior_probs"), fwd["z_prior_probs_BxT"])
+        self.cmp("wm.reward_logits", t("wm.reward_logits"), fwd["reward_logits_BxT"])
+        self.cmp("wm.rewards", t("wm.rewards"), fwd["rewards_BxT"])
+        self.cmp("wm.continue_logits", t("wm.continue_logits"), fwd["continue_distribution_BxT.logits"])
+        self.cmp("wm.obs_loc", t("wm.obs_loc"), fwd["obs_distribution_BxT.loc"])
+        e.wm_loss_backward()
+        for k_e, k_o in (("wm.L_decoder_B_T", "WORLD_MODEL_L_decoder_B_T"), ("wm.L_reward_B_T", "WORLD_MODEL_L_reward_B_T"),
+                         ("wm.L_continue_B_T", "WORLD_MODEL_L_continue_B_T"), ("wm.L_dynamics_B_T", "WORLD_MODEL_L_dynamics_B_T"),
+                         ("wm.L_representation_B_T", "WORLD_MODEL_L_representation_B_T"), ("wm.L_total_B_T", "WORLD_MODEL_L_total_B_T")):
+            self.cmp(k_e, t(k_e), res[k_o])
+        self.cmp("wm.L_total", t("wm.scalars")[6], res["WORLD_MODEL_L_total"])
+        self.cmp_exact("wm.reward_two_hot_k", t("wm.reward_two_hot_k"), res["reward_two_hot_k"])
+        for n, g in res["grads"].items():
+            self.cmp("grad." + n, t("grad." + n), g)
+        before = {n: t(n).detach().cpu().numpy().copy() for n in o.group_names("world_model")}
+        if self.sync_grads:  # keep both trajectories in lock-step; the gradients were compared above
+            for n, g in res["grads"].items():
+                e.write("grad." + n, g.to(torch.float32))
+        e.optimizer_step("world_model", 1000.0, 1e-4, 1e-8)
+        self.cmp("wm.grad_global_norm", t("opt.world_model.stats")[0], res["grad_global_norm"])
+        op = o.numpy_params()
+        for n in o.group_names("world_model"):
+            self.cmp("param." + n, t(n), op[n])
+            if self.sync_grads:
+                self.cmp("adam_delta." + n, to_np(t(n)) - before[n], op[n] - self.prev_params[n])
+        # ---------------- actor / critic ----------------
+        ac = o.train_actor_and_critic_one_step(fwd["h_states_BxT"], fwd["z_states_BxT"], self.sample["is_terminated"],
+                                               H=H, rng=self.rng, margin=self.margin)
+        dream = ac["dream_data"]
+        e.set_noise(u_dyn=o.last_noise["u_dyn"], act_noise=o.last_noise["u_act" if cfg.discrete else "eps_act"])
+        # the oracle dreams from its own (pre-update) h/z; feed exactly those to the engine
+        e.write("in.dream_h0", fwd["h_states_BxT"].to(torch.float32))
+        e.write("in.dream_z0", fwd["z_states_BxT"].reshape(N, -1).to(torch.float32))
+        e.dream_forward(start_from_observe=False)
+        dhz = t("dream.hz")
+        self.cmp("dream.h_states", dhz[..., :G], dream["h_states_t0_to_H_B"])
+        self.cmp_exact("dream.z_indices", t("dream.z_indices"), dream["z_indices_t1_to_H_B"])
+        self.cmp("dream.actions", t("dream.actions"), dream["actions_dreamed_t0_to_H_B"])
+        if cfg.discrete:
+            self.cmp_exact("dream.action_indices", t("dream.action_indices"), dream["actions_ints_dreamed_t0_to_H_B"])
+        self.cmp("dream.rewards", t("dream.rewards"), dream["rewards_dreamed_t0_to_H_B"])
+        self.cmp("dream.continues", t("dream.continues"), dream["continues_dreamed_t0_to_H_B"])
+        self.cmp("dream.values", t("dream.values"), dream["values_dreamed_t0_to_H_B"])
+        self.cmp("dream.value_logits", t("dream.value_logits"), dream["values_symlog_dreamed_logits_t0_to_HxB"])
+        self.cmp("dream.values_symlog_ema", t("dream.values_symlog_ema"), dream["v_symlog_dreamed_ema_t0_to_H_B"])
+        self.cmp("dream.loss_weights", t("dream.loss_weights"), dream["dream_loss_weights_t0_to_H_B"])
+        e.ac_loss_backward(3)
+        self.cmp("ac.value_targets", t("ac.value_targets"), ac["VALUE_TARGETS_H_B"])
+        for k in ("CRITIC_L_total_H_B", "CRITIC_L_neg_logp_of_value_targets_H_B", "CRITIC_L_slow_critic_regularization_H_B",
+                  "VALUE_TARGETS_symlog_H_B", "ACTOR_L_total_H_B", "ACTOR_logp_actions_dreamed_H_B",
+                  "ACTOR_scaled_value_targets_H_B", "ACTOR_action_entropy_H_B", "ACTOR_L_neglogp_reinforce_term_H_B",
+                  "ACTOR_L_neg_entropy_term_H_B"):
+            self.cmp("ac." + k, t("ac." + k), ac[k])
+        self.cmp("ac.CRITIC_L_total", t("ac.scalars")[0], ac["CRITIC_L_total"])
+        self.cmp("ac.ACTOR_L_total", t("ac.scalars")[3], ac["ACTOR_L_total"])
+        self.cmp("ac.pct_ema", t("ac.pct_ema"), np.array([ac["ACTOR_value_targets_pct5_ema"], ac["ACTOR_value_targets_pct95_ema"]]))
+        for n, g in ac["grads"].items():
+            self.cmp("grad." + n, t("grad." + n), g)
+        before = {n: t(n).detach().cpu().numpy().copy() for g_ in ("actor", "critic") for n in o.group_names(g_)}
+        if self.sync_grads:
+            for n, g in ac["grads"].items():
+                e.write("grad." + n, g.to(torch.float32))
+        e.optimizer_step("actor", 100.0, 3e-5, 1e-5)
+        e.optimizer_step("critic", 100.0, 3e-5, 1e-5, 0.98)
+        self.cmp("ac.actor_grad_global_norm", t("opt.actor.stats")[0], ac["actor_grad_global_norm"])
+        self.cmp("ac.critic_grad_global_norm", t("opt.critic.stats")[0], ac["critic_grad_global_norm"])
+        op = o.numpy_params()
+        for grp in ("actor", "critic", "critic_ema"):
+            for n in o.group_names(grp):
+                self.cmp("param." + n, t(n), op[n])
+                if self.sync_grads and grp != "critic_ema":
+                    self.cmp("adam_delta." + n, to_np(t(n)) - before[n], op[n] - self.prev_params[n])
+        torch.cuda.synchronize()
+
+    def worst(self, k=12):
+        return sorted(self.report.items(), key=lambda kv: -kv[1])[:k]
+
+    def close(self):
+        self.engine.close()
