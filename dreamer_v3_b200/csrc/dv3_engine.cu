@@ -252,6 +252,10 @@ void Engine::layout() {
   } else {
     enc_act = alloc_mlp_act("wm.enc", Nl, L);
     enc_out = dry ? nullptr : enc_act.act.back();
+    if (!dry) {
+      index["wm.enc_out"] = (int)tensors.size();
+      tensors.push_back(TensorEntry{"wm.enc_out", enc_out, 0, {Nl, E}, 5, -1, (size_t)Nl * E * 4});
+    }
   }
   a_in = af("wm.a_in", {Nl, A});
   wf = af("wm.first_weight", {Nl});

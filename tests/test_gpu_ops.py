@@ -20,7 +20,7 @@ def test_symlog_bit_exact_and_inverse():
     y = ops.symlog(dev(x)).cpu().numpy()
     np.testing.assert_array_equal(y, nx.symlog(x))  # fp64 log rounded once on both sides
     xr = ops.inverse_symlog(dev(y[:100000])).cpu().numpy()
-    np.testing.assert_allclose(xr, nx.inverse_symlog(y[:100000]), rtol=2e-6, atol=1e-30)
+    np.testing.assert_allclose(xr, nx.inverse_symlog(y[:100000]), rtol=1e-5, atol=3e-7)
 
 
 def test_two_hot_bit_exact_indices():
