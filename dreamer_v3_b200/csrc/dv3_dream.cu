@@ -4,6 +4,8 @@
 // (H+1)*N rows after the rollout; the actor has to run inside it because a_i feeds h_{i+1}.
 #include "dv3_engine.h"
 
+#include <cstring>
+
 namespace dv3 {
 
 void Engine::actor_fwd(long long row_off) {
@@ -176,13 +178,28 @@ int Engine::train_update(const dv3_hparams* hp, uint64_t seed, int use_graph, cu
     return train_ac(hp, st);
   };
   if (!use_graph) return body(s);
-  if (graph_exec == nullptr || graph_seed != seed) {
+  // The legacy default stream cannot be captured: run the graph on an engine-owned stream, ordered after / before
+  // the caller's stream with events.
+  cudaStream_t run = s;
+  const bool hop = (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread);
+  if (hop) {
+    if (own_stream == nullptr) {
+      if (cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
+      cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming);
+    }
+    run = own_stream;
+    cudaEventRecord(ev_in, s);
+    cudaStreamWaitEvent(run, ev_in, 0);
+  }
+  if (graph_exec == nullptr || graph_seed != seed || std::memcmp(&graph_hp, hp, sizeof(*hp)) != 0) {
     if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
     cudaGraph_t graph = nullptr;
     const long long before = g_launches;
-    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return fail("cudaStreamBeginCapture failed");
-    int rc = body(s);
-    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    cudaError_t e = cudaStreamBeginCapture(run, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return fail(std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e));
+    int rc = body(run);
+    e = cudaStreamEndCapture(run, &graph);
     graph_launches = g_launches - before;
     g_launches = before;
     if (rc) return rc;
@@ -191,10 +208,15 @@ int Engine::train_update(const dv3_hparams* hp, uint64_t seed, int use_graph, cu
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
     graph_seed = seed;
+    graph_hp = *hp;
   }
-  cudaError_t e = cudaGraphLaunch(graph_exec, s);
+  cudaError_t e = cudaGraphLaunch(graph_exec, run);
   if (e != cudaSuccess) return fail(std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
   g_launches += graph_launches;
+  if (hop) {
+    cudaEventRecord(ev_out, run);
+    cudaStreamWaitEvent(s, ev_out, 0);
+  }
   return 0;
 }
 

@@ -459,6 +459,7 @@ int Engine::init(const dv3_config* c) {
 
 void Engine::destroy() {
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
+  if (own_stream) { cudaStreamDestroy(own_stream); cudaEventDestroy(ev_in); cudaEventDestroy(ev_out); }
   for (void* p : allocations) cudaFree(p);
   allocations.clear();
 }

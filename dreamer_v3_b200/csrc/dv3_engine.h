@@ -116,6 +116,9 @@ struct Engine {
   cudaGraphExec_t graph_exec = nullptr;
   long long graph_launches = 0;
   uint64_t graph_seed = 0;
+  dv3_hparams graph_hp{};
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 
   // ---- methods ----
   int init(const dv3_config* c);

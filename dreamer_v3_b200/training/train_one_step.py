@@ -1,0 +1,105 @@
+"""train_world_model_one_step / train_actor_and_critic_one_step with the reference's signatures and
+result-dict keys (training/train_one_step.py:16-252). Every tensor in the results is a view of an
+engine-owned device buffer (valid until the next update); nothing is synchronised here.
+
+Data parallelism: when torch.distributed is initialised with world_size > 1 (and the models were built with
+that world_size), the flat gradient buffers are all-reduced (sum; the engine already divides the losses by
+the global batch) between the backward pass and the optimizer step, and the value targets are all-gathered
+before the percentile (the only statistic that does not decompose over the batch)."""
+import torch
+import torch.distributed as dist
+
+
+def _dp(engine):
+    return engine.world_size > 1 and dist.is_available() and dist.is_initialized()
+
+
+def train_world_model_one_step(*, sample, batch_size_B, batch_length_T, grad_clip, world_model):
+    world_model._configure(B=int(batch_size_B))
+    e = world_model.engine
+    assert int(batch_length_T) == e.cfg.T
+    e.set_sample(sample)
+    world_model._draw_noise(1)
+    e.observe_forward()
+    e.wm_loss_backward()
+    if _dp(e):
+        dist.all_reduce(e.group_buffer("world_model", "grad"))
+    opt = world_model.optimizer
+    e.optimizer_step("world_model", float(grad_clip), opt.learning_rate, opt.epsilon)
+    t = e.tensor
+    s = t("wm.scalars")
+    stats = t("opt.world_model.stats")
+    L_dec, L_rew, L_con = t("wm.L_decoder_B_T"), t("wm.L_reward_B_T"), t("wm.L_continue_B_T")
+    return {
+        "WORLD_MODEL_forward_train_outs": world_model._forward_outs(),
+        "WORLD_MODEL_learned_initial_h": world_model.initial_h,
+        "WORLD_MODEL_L_decoder_B_T": L_dec, "WORLD_MODEL_L_decoder": s[0],
+        "WORLD_MODEL_L_reward_B_T": L_rew, "WORLD_MODEL_L_reward": s[1],
+        "WORLD_MODEL_L_continue_B_T": L_con, "WORLD_MODEL_L_continue": s[2],
+        "WORLD_MODEL_L_prediction_B_T": L_dec + L_rew + L_con, "WORLD_MODEL_L_prediction": s[0] + s[1] + s[2],
+        "WORLD_MODEL_L_dynamics_B_T": t("wm.L_dynamics_B_T"), "WORLD_MODEL_L_dynamics": s[4],
+        "WORLD_MODEL_L_representation_B_T": t("wm.L_representation_B_T"), "WORLD_MODEL_L_representation": s[5],
+        "WORLD_MODEL_L_total_B_T": t("wm.L_total_B_T"), "WORLD_MODEL_L_total": s[6],
+        "WORLD_MODEL_gradients_maxabs": stats[1],
+        "WORLD_MODEL_gradients_clipped_by_glob_norm_maxabs": stats[2],
+    }
+
+
+def train_actor_and_critic_one_step(*, world_model_forward_train_outs, is_terminated, horizon_H, gamma, lambda_,
+                                    actor_grad_clip, critic_grad_clip, disagree_grad_clip, dreamer_model,
+                                    entropy_scale, return_normalization_decay, train_actor=True, use_curiosity=False):
+    if use_curiosity:
+        raise NotImplementedError("curiosity is out of scope")
+    e = dreamer_model.engine
+    hp = e.hp
+    hp.gamma, hp.lambda_, hp.entropy_scale = float(gamma), float(lambda_), float(entropy_scale)
+    hp.return_normalization_decay = float(return_normalization_decay)
+    hp.train_actor = int(bool(train_actor))
+    dream_data = dreamer_model.dream_trajectory(
+        start_states={"h": world_model_forward_train_outs["h_states_BxT"],
+                      "z": world_model_forward_train_outs["z_states_BxT"]},
+        start_is_terminated=is_terminated, timesteps_H=horizon_H, gamma=gamma)
+    t = e.tensor
+    if _dp(e):
+        e.ac_loss_backward(1)
+        dist.all_gather_into_tensor(t("ac.value_targets_all"), t("ac.value_targets"))
+        e.ac_loss_backward(2)
+        dist.all_reduce(e.group_buffer("critic", "grad"))
+        if train_actor:
+            dist.all_reduce(e.group_buffer("actor", "grad"))
+    else:
+        e.ac_loss_backward(3)
+    aopt, copt = dreamer_model.actor.optimizer, dreamer_model.critic.optimizer
+    if train_actor:
+        e.optimizer_step("actor", float(actor_grad_clip), aopt.learning_rate, aopt.epsilon)
+    # critic Adam + update_ema() fused (train_one_step.py:235-250)
+    e.optimizer_step("critic", float(critic_grad_clip), copt.learning_rate, copt.epsilon, dreamer_model.critic.ema_decay)
+    s = t("ac.scalars")
+    results = {
+        "VALUE_TARGETS_symlog_H_B": t("ac.VALUE_TARGETS_symlog_H_B"),
+        "CRITIC_L_total": s[0], "CRITIC_L_total_H_B": t("ac.CRITIC_L_total_H_B"),
+        "CRITIC_L_neg_logp_of_value_targets_H_B": t("ac.CRITIC_L_neg_logp_of_value_targets_H_B"),
+        "CRITIC_L_neg_logp_of_value_targets": s[1],
+        "CRITIC_L_slow_critic_regularization_H_B": t("ac.CRITIC_L_slow_critic_regularization_H_B"),
+        "CRITIC_L_slow_critic_regularization": s[2],
+        "VALUE_TARGETS_H_B": t("ac.value_targets"),
+        "dream_data": dream_data,
+    }
+    cst = t("opt.critic.stats")
+    results["CRITIC_gradients_maxabs"] = cst[1]
+    results["CRITIC_gradients_clipped_by_glob_norm_maxabs"] = cst[2]
+    if train_actor:
+        ast = t("opt.actor.stats")
+        pct = t("ac.pct_ema")
+        results.update({
+            "ACTOR_L_total_H_B": t("ac.ACTOR_L_total_H_B"), "ACTOR_L_total": s[3],
+            "ACTOR_logp_actions_dreamed_H_B": t("ac.ACTOR_logp_actions_dreamed_H_B"),
+            "ACTOR_scaled_value_targets_H_B": t("ac.ACTOR_scaled_value_targets_H_B"),
+            "ACTOR_value_targets_pct95_ema": pct[1], "ACTOR_value_targets_pct5_ema": pct[0],
+            "ACTOR_action_entropy_H_B": t("ac.ACTOR_action_entropy_H_B"), "ACTOR_action_entropy": s[4],
+            "ACTOR_L_neglogp_reinforce_term_H_B": t("ac.ACTOR_L_neglogp_reinforce_term_H_B"),
+            "ACTOR_L_neglogp_reinforce_term": s[5],
+            "ACTOR_L_neg_entropy_term_H_B": t("ac.ACTOR_L_neg_entropy_term_H_B"), "ACTOR_L_neg_entropy_term": s[6],
+            "ACTOR_gradients_maxabs": ast[1], "ACTOR_gradients_clipped_by_glob_norm_maxabs": ast[2],
+        })
+    return results

@@ -1,0 +1,106 @@
+"""Invariants of the torch-CPU oracle: the reference pins none of this by tests,
+so the checks are the in-graph asserts / documented properties of the reference."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from dreamer_v3_b200.spec import EngineConfig, init_params
+from oracle.dreamer_oracle import Oracle, make_synthetic_sample
+
+
+def run(cfg, mode="keras", dtype=torch.float32, seed=0):
+    P = init_params(cfg, seed=seed, mode=mode)
+    s = make_synthetic_sample(cfg, seed=seed + 1)
+    o = Oracle(cfg, P, dtype=dtype)
+    rng = np.random.default_rng(seed + 2)
+    res = o.train_world_model_one_step(s, rng=rng, margin=1e-4)
+    return o, s, rng, res
+
+
+@pytest.mark.parametrize("kw", [dict(A=2, discrete=True), dict(A=3, discrete=False), dict(A=4, discrete=True, image_obs=True)])
+def test_world_model_invariants(kw):
+    cfg = EngineConfig.make("nano", B=3, T=6, H=4, **kw)
+    o, s, rng, res = run(cfg)
+    # train_one_step.py:71 tf.assert_equal(L_dyn, L_rep)
+    assert float(res["WORLD_MODEL_L_dynamics"].detach()) == float(res["WORLD_MODEL_L_representation"].detach())
+    assert float(res["WORLD_MODEL_L_dynamics_B_T"].min()) >= 1.0  # free bits
+    # zero-initialised reward head => uniform buckets: E[r] = 0 and CE = log(255) (reward_predictor_layer.py:58-59)
+    f = res["WORLD_MODEL_forward_train_outs"]
+    assert float(f["rewards_BxT"].abs().max()) < 1e-5
+    np.testing.assert_allclose(res["WORLD_MODEL_L_reward_B_T"].detach().numpy(), math.log(255), rtol=1e-5)
+    # unimix: every class keeps >= 1% / Zk probability; rows sum to 1
+    for k in ("z_posterior_probs_BxT", "z_prior_probs_BxT"):
+        p = f[k]
+        assert float(p.min()) >= 0.01 / cfg.Zk - 1e-7
+        np.testing.assert_allclose(p.sum(-1).numpy(), 1.0, atol=1e-5)
+    z = f["z_states_BxT"]
+    # straight-through value (onehot + p) - p is one-hot up to one ulp (representation_layer.py:108-110)
+    assert (((z - 0).abs() < 1e-6) | ((z - 1).abs() < 1e-6)).all() and ((z.sum(-1) - 1).abs() < 1e-5).all()
+    assert all(torch.isfinite(g).all() for g in res["grads"].values())
+    # initial state gradient only flows through tanh(initial_h); the heads of a zero-init model get zero grad
+    assert float(res["grads"]["rew.mlp0.w"].abs().max()) == 0.0
+
+
+def test_actor_critic_invariants_and_ema():
+    cfg = EngineConfig.make("nano", B=3, T=6, H=4, A=2, discrete=True)
+    o, s, rng, res = run(cfg, mode="random")
+    f = res["WORLD_MODEL_forward_train_outs"]
+    before = o.numpy_params()
+    ac = o.train_actor_and_critic_one_step(f["h_states_BxT"], f["z_states_BxT"], s["is_terminated"], H=cfg.H, rng=rng)
+    d = ac["dream_data"]
+    w = d["dream_loss_weights_t0_to_H_B"]
+    c = d["continues_dreamed_t0_to_H_B"]
+    np.testing.assert_allclose(w[0].numpy(), c[0].numpy())                       # cumprod(gamma c)/gamma at t=0
+    assert (w[1:] <= w[:-1] + 1e-7).all()                                        # weights never grow
+    assert (c[0].numpy() == 1.0 - s["is_terminated"].reshape(-1)).all()          # dreamer_model.py:252-255
+    assert ac["VALUE_TARGETS_H_B"].shape == (cfg.H, cfg.N)
+    assert not math.isnan(o.ema_pct5) and o.ema_pct5 <= o.ema_pct95
+    after = o.numpy_params()
+    for n in o.group_names("critic"):
+        e = "critic_ema." + n[len("critic."):]
+        np.testing.assert_allclose(after[e], 0.98 * before[e] + 0.02 * after[n], rtol=1e-5, atol=1e-7)
+    for n in o.group_names("world_model"):
+        np.testing.assert_array_equal(before[n], after[n])  # AC step never touches the world model
+    # second call: EMA percentiles move by (1 - decay)
+    p5 = o.ema_pct5
+    o.train_actor_and_critic_one_step(f["h_states_BxT"], f["z_states_BxT"], s["is_terminated"], H=cfg.H, rng=rng)
+    assert o.ema_pct5 != p5
+
+
+def test_box_actor_gradient_flows_through_dynamics():
+    cfg = EngineConfig.make("nano", B=2, T=4, H=3, A=2, discrete=False)
+    o, s, rng, res = run(cfg, mode="random")
+    f = res["WORLD_MODEL_forward_train_outs"]
+    ac = o.train_actor_and_critic_one_step(f["h_states_BxT"], f["z_states_BxT"], s["is_terminated"], H=cfg.H, rng=rng, apply=False)
+    assert float(ac["grads"]["actor.out.w"].abs().max()) > 0
+    assert float(ac["grads"]["actor.std_out.w"].abs().max()) > 0
+    # -scaled value targets is the reinforce term for Box (actor_loss.py:57)
+    np.testing.assert_allclose(ac["ACTOR_L_neglogp_reinforce_term_H_B"].detach().numpy(),
+                               -ac["ACTOR_scaled_value_targets_H_B"].detach().numpy())
+
+
+def test_fp32_vs_fp64_self_consistency():
+    cfg = EngineConfig.make("micro", B=2, T=5, H=3, A=3, discrete=True)
+    o32, s, rng, r32 = run(cfg, mode="random")
+    o64 = Oracle(cfg, init_params(cfg, seed=0, mode="random"), dtype=torch.float64)
+    r64 = o64.train_world_model_one_step(s, u_post=o32.last_noise["u_post"])
+    np.testing.assert_array_equal(r64["WORLD_MODEL_forward_train_outs"]["z_indices_BxT"],
+                                  r32["WORLD_MODEL_forward_train_outs"]["z_indices_BxT"])
+    for n, g in r32["grads"].items():
+        g64 = r64["grads"][n].float()
+        assert float((g - g64).abs().max()) <= 2e-4 * float(g64.abs().max()) + 1e-9, n
+
+
+def test_keras_adam_matches_numpy_restatement():
+    from oracle import numerics as nx
+    cfg = EngineConfig.make("nano", B=2, T=3, H=2, A=2, discrete=True)
+    o, s, rng, res = run(cfg, mode="random")
+    # redo step 1 of Adam by hand for one tensor
+    P0 = init_params(cfg, seed=0, mode="random")
+    n = "post.mlp0.w"
+    gn = res["grad_global_norm"]
+    g = res["grads"][n].numpy() * np.float32(1000.0 / max(gn, 1000.0))
+    w, _, _ = nx.keras_adam_step(P0[n], g, np.zeros_like(g), np.zeros_like(g), 1, 1e-4, 1e-8)
+    np.testing.assert_allclose(o.numpy_params()[n], w, rtol=0, atol=2e-7)
