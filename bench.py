@@ -234,6 +234,23 @@ def run_ours(args):
 
     # ---- device-resident leg ----
     e.set_sample(pinned)
+    if args.breakdown:
+        e.fill_noise(1, 0, 3)
+        phases = [("observe_forward", e.observe_forward), ("wm_loss_backward", e.wm_loss_backward),
+                  ("wm_optimizer", lambda: e.optimizer_step("world_model", 1000.0, 1e-4, 1e-8)),
+                  ("dream_forward", lambda: e.dream_forward(start_from_observe=True)),
+                  ("ac_loss_backward", lambda: e.ac_loss_backward(3)),
+                  ("ac_optimizers", lambda: (e.optimizer_step("actor", 100.0, 3e-5, 1e-5), e.optimizer_step("critic", 100.0, 3e-5, 1e-5, 0.98)))]
+        out = {}
+        for rep in range(4):
+            for name, fn in phases:
+                torch.cuda.synchronize()
+                l0 = e.kernel_launch_count()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record(); fn(); s1.record(); torch.cuda.synchronize()
+                out[name] = (round(s0.elapsed_time(s1), 3), e.kernel_launch_count() - l0)
+        print(json.dumps({"breakdown_ms_launches": out, "total_ms": round(sum(v[0] for v in out.values()), 3)}), flush=True)
+        return
     for _ in range(args.warmup if args.quick else max(args.warmup, 3)):
         device_step()
     barrier()
@@ -368,6 +385,7 @@ if __name__ == "__main__":
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ref-rows", type=int, default=None)
+    ap.add_argument("--breakdown", action="store_true", help="print per-phase device times (ms) and exit")
     ap.add_argument("--quick", action="store_true", help="profiling aid: only the device-resident leg, no minimum warm-up")
     args = ap.parse_args()
     if args.impl == "reference":

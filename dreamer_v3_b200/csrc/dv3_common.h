@@ -33,6 +33,8 @@ struct GemmArgs {
 void gemm_f32(cudaStream_t s, const GemmArgs& g);
 // mode 0: always fp32 SIMT; mode 1: bf16 tcgen05 tensor cores for large contractions (dv3_gemm_tc.cu)
 void gemm_dispatch(cudaStream_t s, const GemmArgs& g, int mode);
+bool gemm_tc_eligible(const GemmArgs& g);
+void gemm_tc(cudaStream_t s, const GemmArgs& g);  // bf16 tcgen05 / TMEM path
 
 // ---- elementwise / normalisation / recurrent cells (dv3_elem.cu) ---------------------------------
 void symlog_fwd(cudaStream_t s, const float* x, float* y, long long n);

@@ -2,6 +2,10 @@
 // MLP / dense / conv building blocks. The hot-path orchestration lives in dv3_observe.cu and dv3_dream.cu.
 #include "dv3_engine.h"
 
+#include <cstdlib>
+
+#include "dv3_scan.h"
+
 #include <cmath>
 #include <cstring>
 
@@ -263,6 +267,8 @@ void Engine::layout() {
   h0 = af("wm.h0", {G});
   z0 = af("wm.z0", {Z});
   q0_pre = af("", {D}); q0_act = af("", {D}); z0_logits = af("", {Z});
+  z0_idx = ai("wm.z0_indices", {Zc});
+  gx_raw = af("", {B, 3 * G});
   h_in = af("wm.h_in", {Nl, G});
   z_in = af("wm.z_in", {Nl, Z});
   x_pre = af("wm.x_pre", {Nl, D}); x_mean = af("", {Nl}); x_rstd = af("", {Nl});
@@ -450,6 +456,17 @@ int Engine::init(const dv3_config* c) {
   for (const auto& p : pinfo) {
     if (p.name.size() > 2 && p.name.compare(p.name.size() - 2, 2, ".g") == 0)
       fill_f32(nullptr, params[p.group] + p.off, 1.0f, prod(p.shape));
+  }
+  // persistent scan kernels: rows must fit one 16-row tile, classes must tile a 32-column block
+  use_persistent = std::getenv("DV3_NO_PERSISTENT") == nullptr;
+  scan_ctas = 0;
+  if (B <= 16 && (32 % Zk) == 0) {
+    const int max_ctas = scan_fwd_max_ctas(cfg.device);
+    const int tg = (3 * G + 31) / 32, td = (D + 31) / 32, tz = (Z + 31) / 32;
+    int want = tg + td;
+    if (tz > want) want = tz;
+    if (want < 8) want = 8;
+    scan_ctas = want < max_ctas ? want : max_ctas;
   }
   const float nanv[2] = {NAN, NAN};
   CK(cudaMemcpy(pct_ema, nanv, 8, cudaMemcpyHostToDevice));

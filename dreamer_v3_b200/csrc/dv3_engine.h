@@ -79,7 +79,10 @@ struct Engine {
   float *in_obs, *in_actions, *in_is_first, *in_rewards, *in_is_term, *in_u_post, *in_u_dyn, *in_act_noise;
   float *in_dream_h0, *in_dream_z0;
   // ---- observe activations ----
-  float *obs_sym, *enc_out, *a_in, *wf, *actW, *h0, *z0, *q0_pre, *q0_act, *z0_logits;
+  float *obs_sym, *enc_out, *a_in, *wf, *actW, *h0, *z0, *q0_pre, *q0_act, *z0_logits, *gx_raw;
+  int32_t* z0_idx;
+  int scan_ctas = 0;          // > 0: persistent cooperative scan kernels are usable with this many CTAs
+  bool use_persistent = true;
   MlpAct enc_act;
   float *h_in, *z_in, *x_pre, *x_mean, *x_rstd, *u_act, *gx, *gh, *hz;
   float *p_pre, *p_mean, *p_rstd, *p_act, *post_logits, *post_probs;

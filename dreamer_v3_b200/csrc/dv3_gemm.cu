@@ -194,8 +194,9 @@ void gemm_f32(cudaStream_t s, const GemmArgs& g) {
 
 
 void gemm_dispatch(cudaStream_t s, const GemmArgs& g, int mode) {
-  (void)mode;
-  gemm_f32(s, g);
+  if (mode == 1 && g.M > 0 && g.N > 0 && g.K > 0 && gemm_tc_eligible(g)) gemm_tc(s, g);
+  else if (mode == 2 && g.M > 0 && g.N > 0 && g.K > 0) gemm_tc(s, g);  // forced (tests)
+  else gemm_f32(s, g);
 }
 
 }  // namespace dv3

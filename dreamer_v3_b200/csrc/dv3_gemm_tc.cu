@@ -1,0 +1,269 @@
+// bf16 tensor-core GEMM for sm_100a: tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) with the accumulator in
+// TMEM, used for the large contractions of the hot path (dream rollout, heads, CNN patches, weight gradients).
+//
+//   C[M,N] (+)= op(A)[M,K] * op(B)[K,N] (+ bias[N])      same contract as gemm_f32 (fp32 in / fp32 out)
+//
+// The engine keeps fp32 master tensors, so the operands are converted on the way into shared memory: every
+// CTA (128 threads) loads fp32 tiles with coalesced 128-bit loads, rounds to bf16 and writes them in the
+// canonical K-major SWIZZLE_128B UMMA layout (8-row x 128-byte swizzle atoms); operands whose contraction
+// index is not contiguous in memory (B of a forward layer, both operands of a weight gradient) are transposed
+// by that fill. One elected thread issues the MMAs (4 x K=16 per 64-wide k-block) and commits them to an
+// mbarrier; the fill of the next k-block overlaps the tensor-core work of the current one (2-stage ring).
+// Epilogue: tcgen05.ld 32 lanes x 32 columns per warp -> bias / accumulate -> fp32 global stores.
+#include <cuda_bf16.h>
+
+#include "dv3_common.h"
+
+namespace dv3 {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kStages = 2;
+constexpr int kTcThreads = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// byte offset of element (r, k) inside a K-major SWIZZLE_128B tile (k < 64): 1024-byte atoms of 8 rows
+__device__ __forceinline__ uint32_t sw128_chunk_off(int r, int kchunk) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((kchunk ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ---- fills: fp32 global -> bf16 K-major swizzled smem tile of `rows` rows x 64 k ----------------------------
+// source is k-contiguous: src(r, k) = src[r*ld + k]
+__device__ __forceinline__ void fill_direct(unsigned char* tile, const float* __restrict__ src, int ld, int rows,
+                                            int r0, int rmax, int k0, int kmax, bool vec) {
+  for (int task = threadIdx.x; task < rows * 8; task += kTcThreads) {
+    const int r = task >> 3, kc = task & 7;
+    const int gr = r0 + r, gk = k0 + kc * 8;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (gr < rmax && gk < kmax) {
+      const float* p = src + (size_t)gr * ld + gk;
+      if (vec && gk + 7 < kmax) {
+        const float4 a = *reinterpret_cast<const float4*>(p);
+        const float4 b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (gk + i < kmax) v[i] = p[i];
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(tile + sw128_chunk_off(r, kc)) = o;
+  }
+}
+// source is row(mn)-contiguous: src(r, k) = src[k*ld + r]  -> transposed by the fill
+__device__ __forceinline__ void fill_transpose(unsigned char* tile, const float* __restrict__ src, int ld, int rows,
+                                               int r0, int rmax, int k0, int kmax) {
+  for (int task = threadIdx.x; task < rows * 8; task += kTcThreads) {
+    const int r = task % rows, kc = task / rows;  // consecutive threads -> consecutive r: coalesced reads
+    const int gr = r0 + r, gk = k0 + kc * 8;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (gr < rmax && gk + i < kmax) ? src[(size_t)(gk + i) * ld + gr] : 0.f;
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(tile + sw128_chunk_off(r, kc)) = o;
+  }
+}
+
+// ---- descriptors ---------------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: start>>4 | LBO(=1)<<16 | SBO(=1024>>4)<<32 | version 1 | layout 2
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: D = f32 (1<<4), A = B = bf16 (1<<7, 1<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  uint32_t spins = 0;
+  do {
+    if (++spins > (1u << 22)) {  // never hang the GPU on a lost arrival: fail loudly instead
+      printf("dv3 gemm_tc: mbarrier wait timed out (block %d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z);
+      __trap();
+    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+template <int BN>
+struct TcSmem {
+  unsigned char a[kStages][BM * 128];   // 16 KB per stage
+  unsigned char b[kStages][BN * 128];
+  uint64_t bar[kStages];
+  uint32_t tmem_base;
+};
+
+template <int BN, bool TA, bool TB>
+__global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(GemmArgs g, int k_per_split, int vecA, int vecB, int use_atomic) {
+  extern __shared__ unsigned char smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  TcSmem<BN>& sm = *reinterpret_cast<TcSmem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(g.K, kbeg + k_per_split);
+  const int nkb = (kend - kbeg + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&sm.bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {  // one warp allocates BN fp32 accumulator columns of tensor memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+  const uint32_t idesc = make_idesc(BN);
+
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb % kStages;
+    if (kb >= kStages) mbar_wait(&sm.bar[s], (uint32_t)(((kb / kStages) - 1) & 1));  // MMAs that read this stage are done
+    const int k0 = kbeg + kb * BK;
+    if (!TA) fill_direct(sm.a[s], g.A, g.lda, BM, m0, g.M, k0, kend, vecA);
+    else fill_transpose(sm.a[s], g.A, g.lda, BM, m0, g.M, k0, kend);
+    if (TB) fill_direct(sm.b[s], g.B, g.ldb, BN, n0, g.N, k0, kend, vecB);
+    else fill_transpose(sm.b[s], g.B, g.ldb, BN, n0, g.N, k0, kend);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_addr = smem_u32(sm.a[s]), b_addr = smem_u32(sm.b[s]);
+#pragma unroll
+      for (int j = 0; j < BK / 16; ++j) {
+        const uint64_t da = make_smem_desc(a_addr + j * 32);  // +16 bf16 along K inside the 128-byte swizzle row
+        const uint64_t db = make_smem_desc(b_addr + j * 32);
+        const uint32_t accum = (kb > 0 || j > 0) ? 1u : 0u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+            : "memory");
+      }
+      // arrives on the stage's mbarrier once every MMA issued so far has completed
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sm.bar[s])) : "memory");
+    }
+  }
+  // wait for the last commit (it covers all earlier MMAs)
+  {
+    const int last = nkb - 1;
+    mbar_wait(&sm.bar[last % kStages], (uint32_t)((last / kStages) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+
+  // ---- epilogue: warp w owns TMEM lanes (= tile rows) 32w .. 32w+31 ----
+  const int gm = m0 + warp * 32 + lane;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t r[32];
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (gm < g.M) {
+      float* crow = g.C + (size_t)gm * g.ldc;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int gn = n0 + c0 + j;
+        if (gn < g.N) {
+          float v = __uint_as_float(r[j]);
+          if (g.bias != nullptr && blockIdx.z == 0) v += g.bias[gn];
+          if (use_atomic) atomicAdd(crow + gn, v);
+          else if (g.beta != 0.f) crow[gn] += v;
+          else crow[gn] = v;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN));
+}
+
+template <int BN>
+void launch_tc(cudaStream_t s, const GemmArgs& g) {
+  const int gx = cdiv(g.N, BN), gy = cdiv(g.M, BM);
+  const long long tiles = (long long)gx * gy;
+  int splits = 1;
+  if (tiles < 148 && g.K >= 8 * BK) {
+    splits = (int)min((long long)(2 * 148 / tiles), (long long)(g.K / (4 * BK)));
+    if (splits < 1) splits = 1;
+    if (splits > 32) splits = 32;
+  }
+  const int kps = cdiv(cdiv(g.K, splits), BK) * BK;
+  splits = cdiv(g.K, kps);
+  const int use_atomic = splits > 1;
+  if (use_atomic && g.beta == 0.f) zero_2d(s, g.C, g.M, g.N, g.ldc);
+  const int vA = ((uintptr_t)g.A % 16 == 0) && (g.lda % 4 == 0);
+  const int vB = ((uintptr_t)g.B % 16 == 0) && (g.ldb % 4 == 0);
+  const size_t smem = sizeof(TcSmem<BN>) + 1024;
+  dim3 grid(gx, gy, splits), block(kTcThreads);
+#define DV3_TC_LAUNCH(TA_, TB_)                                                                                   \
+  do {                                                                                                            \
+    static bool configured = false;                                                                               \
+    if (!configured) {                                                                                            \
+      cudaFuncSetAttribute(gemm_tc_kernel<BN, TA_, TB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      configured = true;                                                                                          \
+    }                                                                                                             \
+    gemm_tc_kernel<BN, TA_, TB_><<<grid, block, smem, s>>>(g, kps, vA, vB, use_atomic);                           \
+  } while (0)
+  if (!g.ta && !g.tb) DV3_TC_LAUNCH(false, false);
+  else if (!g.ta && g.tb) DV3_TC_LAUNCH(false, true);
+  else if (g.ta && !g.tb) DV3_TC_LAUNCH(true, false);
+  else DV3_TC_LAUNCH(true, true);
+#undef DV3_TC_LAUNCH
+  count_launch();
+}
+
+}  // namespace
+
+// Large contractions go to the tensor cores; small-M scan steps and tiny shapes stay on the exact fp32 path.
+bool gemm_tc_eligible(const GemmArgs& g) {
+  return g.M >= 128 && g.N >= 16 && g.K >= 32 && (long long)g.M * g.N * g.K >= (1LL << 22);
+}
+
+void gemm_tc(cudaStream_t s, const GemmArgs& g) {
+  if (g.N > 128) launch_tc<256>(s, g);
+  else if (g.N > 64) launch_tc<128>(s, g);
+  else launch_tc<64>(s, g);
+}
+
+}  // namespace dv3

@@ -7,6 +7,7 @@
 //   forward : encoder part of the posterior MLP, action part of the pre-GRU layer, the whole prior net
 //   backward: every weight gradient (one [N]-row contraction each after the reverse loop)
 #include "dv3_engine.h"
+#include "dv3_scan.h"
 
 namespace dv3 {
 
@@ -17,7 +18,7 @@ int Engine::initial_state(cudaStream_t s) {
   mm(h0, G, false, Wd.w, D, false, q0_pre, D, 1, D, G);
   ln_silu_fwd(s, q0_pre, D, Wd.g, Wd.b, q0_act, D, nullptr, nullptr, 1, 1, D);
   mm(q0_act, D, false, dyn_repr.w, Z, false, z0_logits, Z, 1, Z, D, dyn_repr.bias);
-  repr_fwd(s, z0_logits, Z, nullptr, 0, nullptr, 0, nullptr, 0, z0, Z, 1, Zc, Zk, 2);  // mode, not a sample (:130-132)
+  repr_fwd(s, z0_logits, Z, nullptr, 0, nullptr, 0, z0_idx, Zc, z0, Z, 1, Zc, Zk, 2);  // mode, not a sample (:130-132)
   return 0;
 }
 
@@ -35,6 +36,18 @@ int Engine::observe_forward(cudaStream_t s) {
   mm(a_in, A, false, Wx.w + (size_t)Z * D, D, false, actW, D, N, D, A);  // hoisted: a_{t-1} . W_pre[Z:]
   initial_state(s);
 
+  if (use_persistent && scan_ctas > 0) {
+    ScanFwdParams sp{};
+    sp.B = B; sp.T = T; sp.G = G; sp.D = D; sp.Z = Z; sp.Zc = Zc; sp.Zk = Zk; sp.E = E;
+    sp.W_pre = Wx.w; sp.pre_g = Wx.g; sp.pre_b = Wx.b; sp.gru_K = gru_K; sp.gru_U = gru_U; sp.gru_b = gru_b;
+    sp.W_post = Wp.w; sp.post_g = Wp.g; sp.post_b = Wp.b; sp.W_zq = post_repr.w; sp.b_zq = post_repr.bias;
+    sp.is_first = in_is_first; sp.actW = actW; sp.u_post = in_u_post; sp.h0 = h0; sp.z0_idx = z0_idx;
+    sp.h_in = h_in; sp.z_in = z_in; sp.x_pre = x_pre; sp.x_mean = x_mean; sp.x_rstd = x_rstd; sp.u_act = u_act;
+    sp.gx_raw = gx_raw; sp.gates = gx; sp.gh = gh; sp.hz = hz; sp.p_pre = p_pre; sp.p_mean = p_mean; sp.p_rstd = p_rstd;
+    sp.p_act = p_act; sp.post_logits = post_logits; sp.post_probs = post_probs; sp.z_idx = z_idx;
+    cudaError_t ce = launch_observe_scan_fwd(s, sp, scan_ctas);
+    if (ce != cudaSuccess) return fail(std::string("observe scan launch: ") + cudaGetErrorString(ce));
+  } else
   for (int t = 0; t < T; ++t) {
     const float* hz_prev = t > 0 ? hz + (size_t)(t - 1) * (G + Z) : nullptr;
     scan_mask_inputs(s, in_is_first + t, T, hz_prev, ldhz, hz_prev ? hz_prev + G : nullptr, ldhz, h0, z0,

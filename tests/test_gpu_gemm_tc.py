@@ -1,0 +1,55 @@
+"""tcgen05 / TMEM bf16 GEMM (csrc/dv3_gemm_tc.cu) against an fp64 product of the bf16-rounded operands
+(isolates layout / descriptor errors from the expected bf16 input rounding), all four transposition modes,
+ragged M/N/K, bias and accumulate epilogues, split-K."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(M, N, K, ta, tb, seed, mode=2):
+    from dreamer_v3_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn((K, M) if ta else (M, K), generator=g)
+    B = torch.randn((N, K) if tb else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    C0 = torch.randn(M, N, generator=g)
+    Ar = A.bfloat16().double()
+    Br = B.bfloat16().double()
+    want = (Ar.T if ta else Ar) @ (Br.T if tb else Br)
+    got = ops.gemm(A.cuda(), B.cuda(), ta, tb, bias=bias.cuda(), mode=mode).cpu().double()
+    tol = 2e-5 * np.sqrt(K) * 8
+    assert float((got - (want + bias.double())).abs().max()) <= tol, (M, N, K, ta, tb, "bias")
+    got = ops.gemm(A.cuda(), B.cuda(), ta, tb, C_=C0.cuda(), beta=1.0, mode=mode).cpu().double()
+    assert float((got - (want + C0.double())).abs().max()) <= tol, (M, N, K, ta, tb, "beta")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 256, 128), (256, 128, 192), (1024, 256, 1280), (1000, 255, 257),
+                                   (130, 24, 70), (4096, 512, 48), (16384, 256, 1281), (1280, 256, 16384), (384, 1024, 640)])
+def test_gemm_tc_matches_bf16_reference(M, N, K):
+    for ta in (False, True):
+        for tb in (False, True):
+            _case(M, N, K, ta, tb, seed=M + 3 * N + 7 * K + int(ta) + 2 * int(tb))
+
+
+def test_gemm_tc_strided_operands():
+    from dreamer_v3_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    big = torch.randn(512, 1400, generator=g).cuda()
+    W = torch.randn(1280, 256, generator=g).cuda()
+    A = big[:, 3:1283]  # unaligned column slice, row stride 1400
+    got = ops.gemm(A, W, mode=2).cpu().double()
+    want = A.cpu().bfloat16().double() @ W.cpu().bfloat16().double()
+    assert float((got - want).abs().max()) < 2e-5 * np.sqrt(1280) * 8
+
+
+def test_gemm_tc_close_to_fp32():
+    """bf16 tolerance statement for the tensor-core mode: |C_tc - C_fp32| <= 2^-8 * sqrt(K) * |A|_rms |B|_rms (3 sigma)."""
+    from dreamer_v3_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    A, B = torch.randn(2048, 1280, generator=g).cuda(), torch.randn(1280, 256, generator=g).cuda()
+    c_tc = ops.gemm(A, B, mode=2)
+    c_32 = ops.gemm(A, B, mode=0)
+    err = float((c_tc - c_32).abs().max())
+    assert err < 3 * 2 ** -8 * np.sqrt(1280) , err
