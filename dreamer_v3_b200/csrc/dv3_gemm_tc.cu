@@ -20,7 +20,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kStages = 2;
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -34,46 +34,78 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// ---- fills: fp32 global -> bf16 K-major swizzled smem tile of `rows` rows x 64 k ----------------------------
-// source is k-contiguous: src(r, k) = src[r*ld + k]
-__device__ __forceinline__ void fill_direct(unsigned char* tile, const float* __restrict__ src, int ld, int rows,
-                                            int r0, int rmax, int k0, int kmax, bool vec) {
-  for (int task = threadIdx.x; task < rows * 8; task += kTcThreads) {
-    const int r = task >> 3, kc = task & 7;
-    const int gr = r0 + r, gk = k0 + kc * 8;
-    float v[8];
+// ---- fills: fp32 global -> registers (all loads of a k-block in flight at once) -> bf16 K-major swizzled smem ----
+// A tile of ROWS rows x 64 k is cut into ROWS*8 tasks of 8 consecutive k; thread t owns tasks t, t+256, ...
+template <int ROWS, bool TRANSPOSE>
+struct Fill {
+  static constexpr int kTasks = ROWS * 8 / kTcThreads;
+  float v[kTasks][8];
+
+  // TRANSPOSE = false: source is k-contiguous, src(r, k) = src[r*ld + k]
+  // TRANSPOSE = true : source is row-contiguous, src(r, k) = src[k*ld + r] (transposed by the fill)
+  __device__ __forceinline__ void load(const float* __restrict__ src, int ld, int r0, int rmax, int k0, int kmax, bool vec) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
-    if (gr < rmax && gk < kmax) {
-      const float* p = src + (size_t)gr * ld + gk;
-      if (vec && gk + 7 < kmax) {
-        const float4 a = *reinterpret_cast<const float4*>(p);
-        const float4 b = *reinterpret_cast<const float4*>(p + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    for (int i = 0; i < kTasks; ++i) {
+      const int task = threadIdx.x + i * kTcThreads;
+      if (!TRANSPOSE) {
+        const int r = task >> 3, kc = task & 7;
+        const int gr = r0 + r, gk = k0 + kc * 8;
+        const float* p = src + (size_t)gr * ld + gk;
+        if (gr < rmax && vec && gk + 7 < kmax) {
+          const float4 a = *reinterpret_cast<const float4*>(p);
+          const float4 b = *reinterpret_cast<const float4*>(p + 4);
+          v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w; v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] = (gr < rmax && gk + j < kmax) ? p[j] : 0.f;
+        }
+      } else if (vec && (kTasks % 4 == 0)) {
+        // quad task q = (4 consecutive rows, 8 k): 8 x LDG.128 along the contiguous row index, transposed in registers.
+        // kTasks is a multiple of 4 here; sub-task i of quad (i / 4) is row (i % 4) of that quad.
+        if ((i & 3) == 0) {
+          const int quad = threadIdx.x + (i >> 2) * kTcThreads;
+          const int r4 = (quad % (ROWS / 4)) * 4, kc = quad / (ROWS / 4);
+          const int gr = r0 + r4, gk = k0 + kc * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gk + j < kmax) {
+              const float* p = src + (size_t)(gk + j) * ld + gr;
+              if (gr + 3 < rmax) t = *reinterpret_cast<const float4*>(p);
+              else {
+                if (gr + 0 < rmax) t.x = p[0];
+                if (gr + 1 < rmax) t.y = p[1];
+                if (gr + 2 < rmax) t.z = p[2];
+              }
+            }
+            v[i + 0][j] = t.x; v[i + 1][j] = t.y; v[i + 2][j] = t.z; v[i + 3][j] = t.w;
+          }
+        }
       } else {
+        const int r = task % ROWS, kc = task / ROWS;  // consecutive threads -> consecutive r: coalesced reads
+        const int gr = r0 + r, gk = k0 + kc * 8;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) if (gk + i < kmax) v[i] = p[i];
+        for (int j = 0; j < 8; ++j) v[i][j] = (gr < rmax && gk + j < kmax) ? src[(size_t)(gk + j) * ld + gr] : 0.f;
       }
     }
-    uint4 o;
-    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-    *reinterpret_cast<uint4*>(tile + sw128_chunk_off(r, kc)) = o;
   }
-}
-// source is row(mn)-contiguous: src(r, k) = src[k*ld + r]  -> transposed by the fill
-__device__ __forceinline__ void fill_transpose(unsigned char* tile, const float* __restrict__ src, int ld, int rows,
-                                               int r0, int rmax, int k0, int kmax) {
-  for (int task = threadIdx.x; task < rows * 8; task += kTcThreads) {
-    const int r = task % rows, kc = task / rows;  // consecutive threads -> consecutive r: coalesced reads
-    const int gr = r0 + r, gk = k0 + kc * 8;
-    float v[8];
+  __device__ __forceinline__ void store(uint32_t tile, bool vec) const {  // tile = shared-space address
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (gr < rmax && gk + i < kmax) ? src[(size_t)(gk + i) * ld + gr] : 0.f;
-    uint4 o;
-    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-    *reinterpret_cast<uint4*>(tile + sw128_chunk_off(r, kc)) = o;
+    for (int i = 0; i < kTasks; ++i) {
+      const int task = threadIdx.x + i * kTcThreads;
+      int r, kc;
+      if (!TRANSPOSE) { r = task >> 3; kc = task & 7; }
+      else if (vec && (kTasks % 4 == 0)) {
+        const int quad = threadIdx.x + (i >> 2) * kTcThreads;
+        r = (quad % (ROWS / 4)) * 4 + (i & 3); kc = quad / (ROWS / 4);
+      } else { r = task % ROWS; kc = task / ROWS; }
+      uint4 o;
+      o.x = pack_bf16(v[i][0], v[i][1]); o.y = pack_bf16(v[i][2], v[i][3]);
+      o.z = pack_bf16(v[i][4], v[i][5]); o.w = pack_bf16(v[i][6], v[i][7]);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + sw128_chunk_off(r, kc)), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+    }
   }
-}
+};
 
 // ---- descriptors ---------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B: start>>4 | LBO(=1)<<16 | SBO(=1024>>4)<<32 | version 1 | layout 2
@@ -146,14 +178,15 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(GemmArgs g, int k_p
   const uint32_t tmem = sm.tmem_base;
   const uint32_t idesc = make_idesc(BN);
 
+  Fill<BM, TA> fa;
+  Fill<BN, !TB> fb;
+  fa.load(g.A, g.lda, m0, g.M, kbeg, kend, vecA);
+  fb.load(g.B, g.ldb, n0, g.N, kbeg, kend, vecB);
   for (int kb = 0; kb < nkb; ++kb) {
     const int s = kb % kStages;
     if (kb >= kStages) mbar_wait(&sm.bar[s], (uint32_t)(((kb / kStages) - 1) & 1));  // MMAs that read this stage are done
-    const int k0 = kbeg + kb * BK;
-    if (!TA) fill_direct(sm.a[s], g.A, g.lda, BM, m0, g.M, k0, kend, vecA);
-    else fill_transpose(sm.a[s], g.A, g.lda, BM, m0, g.M, k0, kend);
-    if (TB) fill_direct(sm.b[s], g.B, g.ldb, BN, n0, g.N, k0, kend, vecB);
-    else fill_transpose(sm.b[s], g.B, g.ldb, BN, n0, g.N, k0, kend);
+    fa.store(smem_u32(sm.a[s]), vecA);
+    fb.store(smem_u32(sm.b[s]), vecB);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
     __syncthreads();
     if (tid == 0) {
@@ -174,6 +207,11 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(GemmArgs g, int k_p
       // arrives on the stage's mbarrier once every MMA issued so far has completed
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sm.bar[s])) : "memory");
     }
+    if (kb + 1 < nkb) {  // next k-block's global loads fly while the tensor core works on this one
+      const int k0 = kbeg + (kb + 1) * BK;
+      fa.load(g.A, g.lda, m0, g.M, k0, kend, vecA);
+      fb.load(g.B, g.ldb, n0, g.N, k0, kend, vecB);
+    }
   }
   // wait for the last commit (it covers all earlier MMAs)
   {
@@ -182,12 +220,16 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(GemmArgs g, int k_p
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
 
-  // ---- epilogue: warp w owns TMEM lanes (= tile rows) 32w .. 32w+31 ----
-  const int gm = m0 + warp * 32 + lane;
+  // ---- epilogue: warp w reads TMEM lanes (= tile rows) 32(w%4) .. +31, column half w/4 ----
+  const int q = warp & 3;                 // TMEM lane quarter this warp may read
+  const int cbeg = (warp >> 2) * (BN / 2), cend = cbeg + BN / 2;
+  // all MMAs have completed, so the operand stages are free: 4 KB per warp to transpose 32x32 blocks so that
+  // the global stores are coalesced along N (XOR swizzle keeps both phases bank-conflict free)
+  const uint32_t epi = smem_u32(sm.a[0]) + warp * 4096;
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
+  for (int c0 = cbeg; c0 < cend; c0 += 32) {
     uint32_t r[32];
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -198,20 +240,26 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(GemmArgs g, int k_p
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (gm < g.M) {
-      float* crow = g.C + (size_t)gm * g.ldc;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int gn = n0 + c0 + j;
-        if (gn < g.N) {
-          float v = __uint_as_float(r[j]);
-          if (g.bias != nullptr && blockIdx.z == 0) v += g.bias[gn];
-          if (use_atomic) atomicAdd(crow + gn, v);
-          else if (g.beta != 0.f) crow[gn] += v;
-          else crow[gn] = v;
-        }
+    for (int j = 0; j < 32; ++j)                                                        // thread = row
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(epi + (uint32_t)((lane * 32 + (j ^ lane)) * 4)), "r"(r[j]) : "memory");
+    __syncwarp();
+    const int gn = n0 + c0 + lane;                                                      // thread = column
+    const float bv = (g.bias != nullptr && blockIdx.z == 0 && gn < g.N) ? g.bias[gn] : 0.f;
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {
+      const int gm = m0 + q * 32 + i;
+      if (gm < g.M && gn < g.N) {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(epi + (uint32_t)((i * 32 + (lane ^ i)) * 4)) : "memory");
+        v += bv;
+        float* dst = g.C + (size_t)gm * g.ldc + gn;
+        if (use_atomic) atomicAdd(dst, v);
+        else if (g.beta != 0.f) *dst += v;
+        else *dst = v;
       }
     }
+    __syncwarp();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -223,8 +271,8 @@ void launch_tc(cudaStream_t s, const GemmArgs& g) {
   const int gx = cdiv(g.N, BN), gy = cdiv(g.M, BM);
   const long long tiles = (long long)gx * gy;
   int splits = 1;
-  if (tiles < 148 && g.K >= 8 * BK) {
-    splits = (int)min((long long)(2 * 148 / tiles), (long long)(g.K / (4 * BK)));
+  if (tiles <= 48 && g.K >= 16 * BK) {
+    splits = (int)min((long long)(148 / tiles), (long long)(g.K / (8 * BK)));
     if (splits < 1) splits = 1;
     if (splits > 32) splits = 32;
   }
@@ -261,8 +309,12 @@ bool gemm_tc_eligible(const GemmArgs& g) {
 }
 
 void gemm_tc(cudaStream_t s, const GemmArgs& g) {
-  if (g.N > 128) launch_tc<256>(s, g);
-  else if (g.N > 64) launch_tc<128>(s, g);
+  // widest N tile that still yields enough CTAs to occupy the GPU (split-K costs an atomic epilogue, so the
+  // tile shape is the first lever for parallelism)
+  const long long mt = cdiv(g.M, BM);
+  if (g.N > 128 && mt * cdiv(g.N, 256) >= 96) launch_tc<256>(s, g);
+  else if (g.N > 64 && mt * cdiv(g.N, 128) >= 64) launch_tc<128>(s, g);
+  else if (g.N > 128 && mt * cdiv(g.N, 64) < 16) launch_tc<256>(s, g);  // tiny grid either way: fewer, fatter CTAs + split-K
   else launch_tc<64>(s, g);
 }
 

@@ -98,16 +98,28 @@ __device__ __forceinline__ void task_gemv(Smem& sm, const float* __restrict__ W,
   __syncthreads();
 }
 
-// LayerNorm statistics of rows x[b*ldx .. +D) for b < B, by the whole CTA -> sm.mean / sm.rstd.
+// LayerNorm statistics of rows x[b*ldx .. +D) for b < B, by the whole CTA -> sm.mean / sm.rstd. Each warp keeps its
+// row in registers (D <= 1024): all loads are issued together, so the cost is one L2 latency, not a chain of them.
 __device__ __forceinline__ void cta_ln_stats(Smem& sm, const float* x, int ldx, int B, int D) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int b = warp; b < B; b += kWarps) {
     const float* xr = x + (size_t)b * ldx;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = (c < D) ? __ldcg(xr + c) : 0.f;
+    }
     float s = 0.f;
-    for (int c = lane; c < D; c += 32) s += __ldcg(xr + c);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += v[i];
     const float mean = warp_sum(s) / (float)D;
     float q = 0.f;
-    for (int c = lane; c < D; c += 32) { const float d = __ldcg(xr + c) - mean; q += d * d; }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float d = (lane + 32 * i < D) ? v[i] - mean : 0.f;
+      q += d * d;
+    }
     const float var = warp_sum(q) / (float)D;
     if (lane == 0) { sm.mean[b] = mean; sm.rstd[b] = rsqrtf(var + DV3_LN_EPS); }
   }
@@ -141,23 +153,36 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
   for (int t = 0; t < T; ++t) {
     // ================= stage A: masked inputs + gather-sum pre-GRU dense =================
     {
+      // indices of the (masked) previous z for every row: one L2 latency, then Zc independent row loads per output
+      int* idx_s = reinterpret_cast<int*>(&sm.red[0][0][0]);
+      for (int e = threadIdx.x; e < B * Zc; e += kThreads) {
+        const int b = e / Zc, c = e % Zc;
+        const size_t bt = (size_t)b * T + t;
+        const bool first = (t == 0) || (p.is_first[bt] != 0.f);
+        idx_s[e] = first ? p.z0_idx[c] : __ldcg(p.z_idx + (bt - 1) * Zc + c);
+      }
+      __syncthreads();
       const int nA = B * D;
       for (int i = gtid; i < nA; i += gthreads) {
         const int b = i / D, d = i % D;
         const size_t bt = (size_t)b * T + t;
-        const bool first = (t == 0) || (p.is_first[bt] != 0.f);
-        const int32_t* idx = first ? p.z0_idx : (p.z_idx + (bt - 1) * Zc);
+        const int* idx = idx_s + b * Zc;
         float s = p.actW[bt * D + d];
-        for (int c = 0; c < Zc; ++c) s += p.W_pre[(size_t)(c * Zk + __ldcg(idx + c)) * D + d];
+        int c = 0;
+        for (; c + 8 <= Zc; c += 8) {
+          float w8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w8[j] = p.W_pre[(size_t)((c + j) * Zk + idx[c + j]) * D + d];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s += w8[j];
+        }
+        for (; c < Zc; ++c) s += p.W_pre[(size_t)(c * Zk + idx[c]) * D + d];
         p.x_pre[bt * D + d] = s;
       }
       const int nZ = B * Z;
       for (int i = gtid; i < nZ; i += gthreads) {
         const int b = i / Z, j = i % Z;
-        const size_t bt = (size_t)b * T + t;
-        const bool first = (t == 0) || (p.is_first[bt] != 0.f);
-        const int32_t* idx = first ? p.z0_idx : (p.z_idx + (bt - 1) * Zc);
-        p.z_in[bt * Z + j] = (__ldcg(idx + j / Zk) == (j % Zk)) ? 1.f : 0.f;
+        p.z_in[((size_t)b * T + t) * Z + j] = (idx_s[b * Zc + j / Zk] == (j % Zk)) ? 1.f : 0.f;
       }
       const int nH = B * G;
       for (int i = gtid; i < nH; i += gthreads) {
@@ -172,16 +197,13 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
     // ================= stage B: gx = SiLU(LN(x_pre)) . K + b0 =================
     {
       const float* xp = p.x_pre + (size_t)t * D;  // row b at stride T*D
-      const bool mine = blk < tasks_gate;
-      if (mine) cta_ln_stats(sm, xp, T * D, B, D);
-      if (blk == 0) {
-        for (int e = threadIdx.x; e < B * D; e += kThreads) {
-          const int b = e / D, k = e % D;
-          const float n = (__ldcg(xp + (size_t)b * T * D + k) - sm.mean[b]) * sm.rstd[b] * p.pre_g[k] + p.pre_b[k];
-          p.u_act[((size_t)b * T + t) * D + k] = n * sigmoidf_(n);
-        }
-        if (threadIdx.x < B) { p.x_mean[(size_t)threadIdx.x * T + t] = sm.mean[threadIdx.x]; p.x_rstd[(size_t)threadIdx.x * T + t] = sm.rstd[threadIdx.x]; }
+      cta_ln_stats(sm, xp, T * D, B, D);
+      for (int e = gtid; e < B * D; e += gthreads) {  // every CTA publishes a slice of u = SiLU(LN(x_pre)) for the backward pass
+        const int b = e / D, k = e % D;
+        const float n = (__ldcg(xp + (size_t)b * T * D + k) - sm.mean[b]) * sm.rstd[b] * p.pre_g[k] + p.pre_b[k];
+        p.u_act[((size_t)b * T + t) * D + k] = n * sigmoidf_(n);
       }
+      if (blk == 0 && threadIdx.x < B) { p.x_mean[(size_t)threadIdx.x * T + t] = sm.mean[threadIdx.x]; p.x_rstd[(size_t)threadIdx.x * T + t] = sm.rstd[threadIdx.x]; }
       for (int task = blk; task < tasks_gate; task += nblk) {
         const int c0 = task * 32;
         task_gemv(sm, p.gru_K, 3 * G, c0, 3 * G, D, B, [&](int b, int k) {
@@ -209,24 +231,22 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
         const float c = tanhf(__ldcg(gxr + 2 * G + k) + r * __ldcg(ghr + 2 * G + k));
         return z * __ldcg(p.h_in + bt * G + k) + (1.f - z) * c;
       };
+      // every CTA publishes a slice of h_t and of the gate activations (z, r, c) for the backward pass
+      for (int e = gtid; e < B * G; e += gthreads) {
+        const int b = e / G, k = e % G;
+        const size_t bt = (size_t)b * T + t;
+        const float* gxr = p.gx_raw + (size_t)b * 3 * G;
+        const float* ghr = p.gh + bt * 3 * G;
+        const float z = sigmoidf_(__ldcg(gxr + k) + __ldcg(ghr + k));
+        const float r = sigmoidf_(__ldcg(gxr + G + k) + __ldcg(ghr + G + k));
+        const float c = tanhf(__ldcg(gxr + 2 * G + k) + r * __ldcg(ghr + 2 * G + k));
+        p.hz[bt * W + k] = z * __ldcg(p.h_in + bt * G + k) + (1.f - z) * c;
+        float* gt = p.gates + bt * 3 * G;
+        gt[k] = z; gt[G + k] = r; gt[2 * G + k] = c;
+      }
       for (int task = blk; task < ntask; task += nblk) {
         if (task < tasks_D) {
           const int c0 = task * 32;
-          if (task == 0) {
-            // the first task also publishes h_t and the gate activations (z, r, c) for the backward pass
-            for (int e = threadIdx.x; e < B * G; e += kThreads) {
-              const int b = e / G, k = e % G;
-              const size_t bt = (size_t)b * T + t;
-              const float* gxr = p.gx_raw + (size_t)b * 3 * G;
-              const float* ghr = p.gh + bt * 3 * G;
-              const float z = sigmoidf_(__ldcg(gxr + k) + __ldcg(ghr + k));
-              const float r = sigmoidf_(__ldcg(gxr + G + k) + __ldcg(ghr + G + k));
-              const float c = tanhf(__ldcg(gxr + 2 * G + k) + r * __ldcg(ghr + 2 * G + k));
-              p.hz[bt * W + k] = z * __ldcg(p.h_in + bt * G + k) + (1.f - z) * c;
-              float* gt = p.gates + bt * 3 * G;
-              gt[k] = z; gt[G + k] = r; gt[2 * G + k] = c;
-            }
-          }
           task_gemv(sm, W_post_h, D, c0, D, G, B, h_of);
           for (int e = threadIdx.x; e < B * 32; e += kThreads) {
             const int b = e >> 5, j = e & 31;
@@ -252,16 +272,13 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
     // ================= stage D: logits = SiLU(LN(p_pre)) . W_zq + b -> unimix probs, sample z_t =================
     {
       const float* pp = p.p_pre + (size_t)t * D;
-      const bool mine = blk < tasks_Z;
-      if (mine) cta_ln_stats(sm, pp, T * D, B, D);
-      if (blk == 0) {
-        for (int e = threadIdx.x; e < B * D; e += kThreads) {
-          const int b = e / D, k = e % D;
-          const float n = (__ldcg(pp + (size_t)b * T * D + k) - sm.mean[b]) * sm.rstd[b] * p.post_g[k] + p.post_b[k];
-          p.p_act[((size_t)b * T + t) * D + k] = n * sigmoidf_(n);
-        }
-        if (threadIdx.x < B) { p.p_mean[(size_t)threadIdx.x * T + t] = sm.mean[threadIdx.x]; p.p_rstd[(size_t)threadIdx.x * T + t] = sm.rstd[threadIdx.x]; }
+      cta_ln_stats(sm, pp, T * D, B, D);
+      for (int e = gtid; e < B * D; e += gthreads) {
+        const int b = e / D, k = e % D;
+        const float n = (__ldcg(pp + (size_t)b * T * D + k) - sm.mean[b]) * sm.rstd[b] * p.post_g[k] + p.post_b[k];
+        p.p_act[((size_t)b * T + t) * D + k] = n * sigmoidf_(n);
       }
+      if (blk == 0 && threadIdx.x < B) { p.p_mean[(size_t)threadIdx.x * T + t] = sm.mean[threadIdx.x]; p.p_rstd[(size_t)threadIdx.x * T + t] = sm.rstd[threadIdx.x]; }
       for (int task = blk; task < tasks_Z; task += nblk) {
         const int c0 = task * 32;
         task_gemv(sm, p.W_zq, Z, c0, Z, D, B, [&](int b, int k) {

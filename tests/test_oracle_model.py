@@ -104,3 +104,22 @@ def test_keras_adam_matches_numpy_restatement():
     g = res["grads"][n].numpy() * np.float32(1000.0 / max(gn, 1000.0))
     w, _, _ = nx.keras_adam_step(P0[n], g, np.zeros_like(g), np.zeros_like(g), 1, 1e-4, 1e-8)
     np.testing.assert_allclose(o.numpy_params()[n], w, rtol=0, atol=2e-7)
+
+
+def test_oracle_reproduces_golden_fixture():
+    """Regression pin: the committed fixture (tests/golden/make_golden.py) is reproduced by the oracle in fp32."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "nano_vec_disc.npz"))
+    cfg = EngineConfig.make("nano", A=2, discrete=True, B=3, T=5, H=4)
+    P = {k[len("param/"):]: g[k] for k in g.files if k.startswith("param/")}
+    sample = {k: g["sample/" + k] for k in ("obs", "actions", "rewards", "is_first", "is_terminated")}
+    o = Oracle(cfg, P, dtype=torch.float32)
+    res = o.train_world_model_one_step(sample, u_post=g["noise/u_post"], apply=False)
+    np.testing.assert_array_equal(res["WORLD_MODEL_forward_train_outs"]["z_indices_BxT"], g["out/z_indices"])
+    np.testing.assert_array_equal(res["reward_two_hot_k"], g["out/reward_two_hot_k"])
+    np.testing.assert_allclose(res["WORLD_MODEL_L_total"].item(), g["out/L_total"], rtol=1e-5)
+    for k in g.files:
+        if k.startswith("grad/"):
+            want = g[k]
+            got = res["grads"][k[len("grad/"):]].numpy()
+            assert np.abs(got - want).max() <= 2e-4 * np.abs(want).max() + 1e-12, k
