@@ -124,8 +124,13 @@ int dv3_optimizer_step(dv3_engine* h, int group, float clip, float lr, float eps
   int rc = h->e.optimizer_step(group, clip, lr, eps, ema_decay, S(stream));
   return rc ? rc : check_async(h->e);
 }
-int dv3_train_world_model_step(dv3_engine* h, const dv3_hparams* hp, void* stream) {
-  int rc = h->e.train_wm(hp, S(stream));
+int dv3_train_world_model_step(dv3_engine* h, const dv3_hparams* hp, uint64_t noise_seed, int use_graph, void* stream) {
+  int rc = 0;
+  if (use_graph) rc = h->e.train_wm_graph(hp, noise_seed, S(stream));
+  else {
+    if (noise_seed != 0) { dv3::bump_counter(S(stream), h->e.noise_step); h->e.fill_noise(noise_seed, 0, 1, true, S(stream)); }
+    rc = h->e.train_wm(hp, S(stream));
+  }
   return rc ? rc : check_async(h->e);
 }
 int dv3_dream_forward(dv3_engine* h, float gamma, int start_from_observe, void* stream) {
@@ -144,8 +149,13 @@ int dv3_critic_update_ema(dv3_engine* h, float decay, void* stream) {
   dv3::ema_update(S(stream), h->e.params[3], h->e.params[2], h->e.numel[2], decay);
   return check_async(h->e);
 }
-int dv3_train_actor_critic_step(dv3_engine* h, const dv3_hparams* hp, void* stream) {
-  int rc = h->e.train_ac(hp, S(stream));
+int dv3_train_actor_critic_step(dv3_engine* h, const dv3_hparams* hp, uint64_t noise_seed, int use_graph, void* stream) {
+  int rc = 0;
+  if (use_graph) rc = h->e.train_ac_graph(hp, noise_seed, S(stream));
+  else {
+    if (noise_seed != 0) h->e.fill_noise(noise_seed, 0, 2, true, S(stream));
+    rc = h->e.train_ac(hp, S(stream));
+  }
   return rc ? rc : check_async(h->e);
 }
 int dv3_train_update(dv3_engine* h, const dv3_hparams* hp, uint64_t noise_seed, int use_graph, void* stream) {

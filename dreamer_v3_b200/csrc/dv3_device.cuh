@@ -15,6 +15,14 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// fast variants for the latency-critical persistent scan kernels (ex2.approx based, rel. error ~1e-6: far inside the
+// 1e-4 parity budget, and nothing integer-valued depends on them)
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = __expf(-2.f * fabsf(x));
+  const float t = __fdividef(1.f - e, 1.f + e);
+  return x < 0.f ? -t : t;
+}
 
 // sign(x) * log(|x| + 1) (utils/symlog.py:9-12): the add is fp32 (as TF does), the log is evaluated in
 // fp64 and rounded once, so two-hot bucket indices derived from it are bit-identical to the oracle's.

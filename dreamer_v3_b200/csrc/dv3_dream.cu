@@ -167,6 +167,63 @@ int Engine::train_ac(const dv3_hparams* hp, cudaStream_t s) {
   return optimizer_step(2, hp->critic_grad_clip, hp->ac_lr, hp->ac_eps, hp->critic_ema_decay, s);
 }
 
+template <class F>
+int Engine::run_graphed(GraphSlot& slot, const dv3_hparams* hp, uint64_t seed, cudaStream_t s, F body) {
+  cudaStream_t run = s;
+  const bool hop = (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread);
+  if (hop) {
+    if (own_stream == nullptr) {
+      if (cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
+      cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming);
+    }
+    run = own_stream;
+    cudaEventRecord(ev_in, s);
+    cudaStreamWaitEvent(run, ev_in, 0);
+  }
+  if (slot.exec == nullptr || slot.seed != seed || std::memcmp(&slot.hp, hp, sizeof(*hp)) != 0) {
+    if (slot.exec) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    const long long before = g_launches;
+    cudaError_t e = cudaStreamBeginCapture(run, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return fail(std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e));
+    int rc = body(run);
+    e = cudaStreamEndCapture(run, &graph);
+    slot.launches = g_launches - before;
+    g_launches = before;
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&slot.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    slot.seed = seed;
+    slot.hp = *hp;
+  }
+  cudaError_t e = cudaGraphLaunch(slot.exec, run);
+  if (e != cudaSuccess) return fail(std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
+  g_launches += slot.launches;
+  if (hop) {
+    cudaEventRecord(ev_out, run);
+    cudaStreamWaitEvent(s, ev_out, 0);
+  }
+  return 0;
+}
+
+// train_world_model_one_step / train_actor_and_critic_one_step as one CUDA-graph replay each. seed != 0: the step's
+// sampling noise is drawn on the device inside the graph.
+int Engine::train_wm_graph(const dv3_hparams* hp, uint64_t seed, cudaStream_t s) {
+  return run_graphed(slot_wm, hp, seed, s, [&](cudaStream_t st) -> int {
+    if (seed != 0) { bump_counter(st, noise_step); fill_noise(seed, 0, 1, true, st); }
+    return train_wm(hp, st);
+  });
+}
+int Engine::train_ac_graph(const dv3_hparams* hp, uint64_t seed, cudaStream_t s) {
+  return run_graphed(slot_ac, hp, seed, s, [&](cudaStream_t st) -> int {
+    if (seed != 0) fill_noise(seed, 0, 2, true, st);
+    return train_ac(hp, st);
+  });
+}
+
 int Engine::train_update(const dv3_hparams* hp, uint64_t seed, int use_graph, cudaStream_t s) {
   auto body = [&](cudaStream_t st) -> int {
     if (seed != 0) {

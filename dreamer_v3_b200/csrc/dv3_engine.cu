@@ -269,6 +269,9 @@ void Engine::layout() {
   q0_pre = af("", {D}); q0_act = af("", {D}); z0_logits = af("", {Z});
   z0_idx = ai("wm.z0_indices", {Zc});
   gx_raw = af("", {B, 3 * G});
+  Wt_zq = af("", {Z, D}); Wt_post_h = af("", {D, G}); Ut = af("", {3 * G, G}); Kt = af("", {3 * G, D}); Wt_pre_z = af("", {D, Z});
+  scan_stamps = (unsigned long long*)alloc_bytes("debug.scan_stamps", (size_t)(T * 8 + 16) * 8, 1, {(long long)(T * 8 + 16) * 2}, 6, -1);
+  dp_act_all = af("", {Nl, D}); du_all = af("", {Nl, D}); dh_tot = af("", {B, G});
   h_in = af("wm.h_in", {Nl, G});
   z_in = af("wm.z_in", {Nl, Z});
   x_pre = af("wm.x_pre", {Nl, D}); x_mean = af("", {Nl}); x_rstd = af("", {Nl});
@@ -467,6 +470,12 @@ int Engine::init(const dv3_config* c) {
     if (tz > want) want = tz;
     if (want < 8) want = 8;
     scan_ctas = want < max_ctas ? want : max_ctas;
+    const int max_b = scan_bwd_max_ctas(cfg.device);
+    const int tgb = (G + 31) / 32;
+    int wb = tgb + td;
+    if (tz > wb) wb = tz;
+    if (wb < 8) wb = 8;
+    scan_bwd_ctas = wb < max_b ? wb : max_b;
   }
   const float nanv[2] = {NAN, NAN};
   CK(cudaMemcpy(pct_ema, nanv, 8, cudaMemcpyHostToDevice));
@@ -476,6 +485,8 @@ int Engine::init(const dv3_config* c) {
 
 void Engine::destroy() {
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
+  if (slot_wm.exec) cudaGraphExecDestroy(slot_wm.exec);
+  if (slot_ac.exec) cudaGraphExecDestroy(slot_ac.exec);
   if (own_stream) { cudaStreamDestroy(own_stream); cudaEventDestroy(ev_in); cudaEventDestroy(ev_out); }
   for (void* p : allocations) cudaFree(p);
   allocations.clear();

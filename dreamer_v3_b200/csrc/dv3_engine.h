@@ -81,6 +81,9 @@ struct Engine {
   // ---- observe activations ----
   float *obs_sym, *enc_out, *a_in, *wf, *actW, *h0, *z0, *q0_pre, *q0_act, *z0_logits, *gx_raw;
   int32_t* z0_idx;
+  float *Wt_zq, *Wt_post_h, *Ut, *Kt, *Wt_pre_z, *dp_act_all, *du_all, *dh_tot;
+  unsigned long long* scan_stamps = nullptr;
+  int scan_bwd_ctas = 0;
   int scan_ctas = 0;          // > 0: persistent cooperative scan kernels are usable with this many CTAs
   bool use_persistent = true;
   MlpAct enc_act;
@@ -116,6 +119,11 @@ struct Engine {
   float last_gamma = 0.997f;
 
   // ---- graph ----
+  struct GraphSlot { cudaGraphExec_t exec = nullptr; long long launches = 0; dv3_hparams hp{}; uint64_t seed = 0; };
+  GraphSlot slot_wm, slot_ac;
+  template <class F> int run_graphed(GraphSlot& slot, const dv3_hparams* hp, uint64_t seed, cudaStream_t s, F body);
+  int train_wm_graph(const dv3_hparams* hp, uint64_t seed, cudaStream_t s);
+  int train_ac_graph(const dv3_hparams* hp, uint64_t seed, cudaStream_t s);
   cudaGraphExec_t graph_exec = nullptr;
   long long graph_launches = 0;
   uint64_t graph_seed = 0;

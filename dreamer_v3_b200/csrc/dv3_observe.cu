@@ -9,6 +9,8 @@
 #include "dv3_engine.h"
 #include "dv3_scan.h"
 
+#include <cstdlib>
+
 namespace dv3 {
 
 int Engine::initial_state(cudaStream_t s) {
@@ -45,6 +47,7 @@ int Engine::observe_forward(cudaStream_t s) {
     sp.h_in = h_in; sp.z_in = z_in; sp.x_pre = x_pre; sp.x_mean = x_mean; sp.x_rstd = x_rstd; sp.u_act = u_act;
     sp.gx_raw = gx_raw; sp.gates = gx; sp.gh = gh; sp.hz = hz; sp.p_pre = p_pre; sp.p_mean = p_mean; sp.p_rstd = p_rstd;
     sp.p_act = p_act; sp.post_logits = post_logits; sp.post_probs = post_probs; sp.z_idx = z_idx;
+    sp.stamps = std::getenv("DV3_SCAN_STAMPS") ? scan_stamps : nullptr;
     cudaError_t ce = launch_observe_scan_fwd(s, sp, scan_ctas);
     if (ce != cudaSuccess) return fail(std::string("observe scan launch: ") + cudaGetErrorString(ce));
   } else
@@ -114,7 +117,27 @@ int Engine::wm_loss_backward(cudaStream_t s) {
   mm(hz, G + Z, true, dq_pre, D, false, Wd.dw, D, G, D, N, nullptr, 1.f);
   mm(dq_pre, D, false, Wd.w, D, true, d_hz, G + Z, N, G, D, nullptr, 1.f);
 
-  // reverse-time scan: only input gradients inside the loop
+  // reverse-time scan: only input gradients on the recurrence
+  if (use_persistent && scan_bwd_ctas > 0) {
+    transpose_f32(s, post_repr.w, Wt_zq, D, Z);
+    transpose_f32(s, Wp.w + (size_t)E * D, Wt_post_h, G, D);
+    transpose_f32(s, gru_U, Ut, G, 3 * G);
+    transpose_f32(s, gru_K, Kt, D, 3 * G);
+    transpose_f32(s, Wx.w, Wt_pre_z, Z, D);
+    ScanBwdParams bp{};
+    bp.B = B; bp.T = T; bp.G = G; bp.D = D; bp.Z = Z; bp.Zc = Zc; bp.Zk = Zk;
+    bp.Wt_zq = Wt_zq; bp.Wt_post_h = Wt_post_h; bp.Ut = Ut; bp.Kt = Kt; bp.Wt_pre_z = Wt_pre_z;
+    bp.post_g = Wp.g; bp.post_b = Wp.b; bp.pre_g = Wx.g; bp.pre_b = Wx.b;
+    bp.is_first = in_is_first; bp.post_logits = post_logits; bp.dpost = dpost; bp.p_pre = p_pre; bp.p_mean = p_mean;
+    bp.p_rstd = p_rstd; bp.gates = gx; bp.gh = gh; bp.h_in = h_in; bp.x_pre = x_pre; bp.x_mean = x_mean; bp.x_rstd = x_rstd;
+    bp.d_hz = d_hz; bp.dlogits = dpost_logits; bp.dp_act = dp_act_all; bp.dp_pre = dp_pre; bp.dh_tot = dh_tot;
+    bp.dgx = dgx; bp.dgh = dgh; bp.dh_in = dh_in; bp.du = du_all; bp.dx_pre = dx_pre;
+    cudaError_t ce = launch_observe_scan_bwd(s, bp, scan_bwd_ctas);
+    if (ce != cudaSuccess) return fail(std::string("observe scan bwd launch: ") + cudaGetErrorString(ce));
+    // LayerNorm gain / offset gradients of the two in-loop layers, one N-row pass each
+    ln_silu_bwd(s, dp_act_all, D, p_pre, D, p_mean, p_rstd, Wp.g, Wp.b, nullptr, 0, Wp.dg, Wp.db, 1, N, D);
+    ln_silu_bwd(s, du_all, D, x_pre, D, x_mean, x_rstd, Wx.g, Wx.b, nullptr, 0, Wx.dg, Wx.db, 1, N, D);
+  } else
   for (int t = T - 1; t >= 0; --t) {
     float* dhz_t = d_hz + (size_t)t * (G + Z);
     // posterior representation layer: straight-through dz + KL dprobs -> dlogits

@@ -11,120 +11,14 @@
 // of a CTA and reduced through shared memory, tasks are dealt round-robin to the CTAs of the grid. Weights are
 // streamed from L2 (they are re-read every step by the same CTAs and stay L2 resident up to size L); activations
 // of the step are staged in shared memory in [k][row] order so one LDS.128 feeds four FMAs.
-#include <cooperative_groups.h>
-
-#include "dv3_device.cuh"
-#include "dv3_scan.h"
+#include "dv3_scan_common.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace dv3 {
 namespace {
 
-constexpr int kWarps = 8;
-constexpr int kThreads = kWarps * 32;
-constexpr int kRows = 16;      // max rows (replay sequences) handled per launch
-constexpr int kKC = 128;       // k-chunk staged per warp
-constexpr int kRedLd = 33;
-constexpr int kInLd = 20;     // row stride of the staged activations (16 rows + pad): conflict-free float4 stores
-
-struct Smem {
-  float in_chunk[kWarps][kKC][kInLd];   // 80 KB
-  float red[kWarps][kRows][kRedLd];     // 16.5 KB
-  float tile[kRows][kRedLd];            // reduced output tile
-  float mean[kRows], rstd[kRows];
-};
-
-// One task: out_tile[b][j] = sum_k in(b,k) * W[k*ldw + c0 + j], j < 32, k < K. `in_fn(b, k)` produces the input
-// on the fly (LayerNorm / GRU gates are applied here by the consumer). Result is left in sm.tile (all threads
-// synchronised on return).
-template <class InFn>
-__device__ __forceinline__ void task_gemv(Smem& sm, const float* __restrict__ W, int ldw, int c0, int ncols, int K,
-                                          int B, InFn in_fn) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ks = (K + kWarps - 1) / kWarps;
-  const int k0 = warp * ks, k1 = min(K, k0 + ks);
-  const bool col_ok = (c0 + lane) < ncols;
-  float acc[kRows];
-#pragma unroll
-  for (int b = 0; b < kRows; ++b) acc[b] = 0.f;
-  for (int kc = k0; kc < k1; kc += kKC) {
-    const int kn = min(kKC, k1 - kc);
-    // stage in[b][kc .. kc+kn) -> in_chunk[warp][kk][b]; lanes run along k (coalesced global reads), each lane
-    // gathers the 16 rows of its k in registers and stores them as four float4
-    for (int kb = 0; kb < kn; kb += 32) {
-      const int kk = kb + lane;
-      float v[kRows];
-#pragma unroll
-      for (int b = 0; b < kRows; ++b) v[b] = (b < B && kk < kn) ? in_fn(b, kc + kk) : 0.f;
-      if (kk < kn) {
-        float4* dst = reinterpret_cast<float4*>(&sm.in_chunk[warp][kk][0]);
-        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-        dst[2] = make_float4(v[8], v[9], v[10], v[11]);
-        dst[3] = make_float4(v[12], v[13], v[14], v[15]);
-      }
-    }
-    __syncwarp();
-    const float* wp = W + (size_t)kc * ldw + c0 + lane;
-    for (int kk0 = 0; kk0 < kn; kk0 += 8) {
-      float wv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) wv[j] = (col_ok && kk0 + j < kn) ? wp[(size_t)(kk0 + j) * ldw] : 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int kk = min(kk0 + j, kn - 1);
-        const float4* iv = reinterpret_cast<const float4*>(&sm.in_chunk[warp][kk][0]);
-        const float4 a0 = iv[0], a1 = iv[1], a2 = iv[2], a3 = iv[3];
-        const float w_ = wv[j];
-        acc[0] = fmaf(a0.x, w_, acc[0]); acc[1] = fmaf(a0.y, w_, acc[1]); acc[2] = fmaf(a0.z, w_, acc[2]); acc[3] = fmaf(a0.w, w_, acc[3]);
-        acc[4] = fmaf(a1.x, w_, acc[4]); acc[5] = fmaf(a1.y, w_, acc[5]); acc[6] = fmaf(a1.z, w_, acc[6]); acc[7] = fmaf(a1.w, w_, acc[7]);
-        acc[8] = fmaf(a2.x, w_, acc[8]); acc[9] = fmaf(a2.y, w_, acc[9]); acc[10] = fmaf(a2.z, w_, acc[10]); acc[11] = fmaf(a2.w, w_, acc[11]);
-        acc[12] = fmaf(a3.x, w_, acc[12]); acc[13] = fmaf(a3.y, w_, acc[13]); acc[14] = fmaf(a3.z, w_, acc[14]); acc[15] = fmaf(a3.w, w_, acc[15]);
-      }
-    }
-    __syncwarp();
-  }
-#pragma unroll
-  for (int b = 0; b < kRows; ++b) sm.red[warp][b][lane] = acc[b];
-  __syncthreads();
-  for (int e = threadIdx.x; e < kRows * 32; e += kThreads) {
-    const int b = e >> 5, j = e & 31;
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) s += sm.red[w][b][j];
-    sm.tile[b][j] = s;
-  }
-  __syncthreads();
-}
-
-// LayerNorm statistics of rows x[b*ldx .. +D) for b < B, by the whole CTA -> sm.mean / sm.rstd. Each warp keeps its
-// row in registers (D <= 1024): all loads are issued together, so the cost is one L2 latency, not a chain of them.
-__device__ __forceinline__ void cta_ln_stats(Smem& sm, const float* x, int ldx, int B, int D) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int b = warp; b < B; b += kWarps) {
-    const float* xr = x + (size_t)b * ldx;
-    float v[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int c = lane + 32 * i;
-      v[i] = (c < D) ? __ldcg(xr + c) : 0.f;
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) s += v[i];
-    const float mean = warp_sum(s) / (float)D;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float d = (lane + 32 * i < D) ? v[i] - mean : 0.f;
-      q += d * d;
-    }
-    const float var = warp_sum(q) / (float)D;
-    if (lane == 0) { sm.mean[b] = mean; sm.rstd[b] = rsqrtf(var + DV3_LN_EPS); }
-  }
-  __syncthreads();
-}
+using namespace scan;
 
 __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -138,6 +32,24 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
   const int tasks_gate = (3 * G + 31) / 32, tasks_D = (D + 31) / 32, tasks_Z = (Z + 31) / 32;
   const float* W_post_h = p.W_post + (size_t)E * D;
 
+  // ---- weights resident in shared memory: when every CTA owns at most one task per stage (XS and smaller), its
+  // three [K x 32] weight tiles are copied once and stay for all T steps ----
+  float* wc_B = reinterpret_cast<float*>(smem_raw + sizeof(Smem));           // stage B tile  [D][32]
+  float* wc_C = wc_B + (size_t)D * 32;                                       // stage C tile  [G][32]
+  float* wc_D = wc_C + (size_t)G * 32;                                       // stage D tile  [D][32]
+  const bool cached = p.cache_weights != 0;
+  if (cached) {
+    if (blk < tasks_gate)
+      for (int e = threadIdx.x; e < D * 32; e += kThreads) { const int k = e >> 5, j = e & 31, c = blk * 32 + j; wc_B[e] = c < 3 * G ? p.gru_K[(size_t)k * 3 * G + c] : 0.f; }
+    if (blk < tasks_D)
+      for (int e = threadIdx.x; e < G * 32; e += kThreads) { const int k = e >> 5, j = e & 31, c = blk * 32 + j; wc_C[e] = c < D ? W_post_h[(size_t)k * D + c] : 0.f; }
+    else if (blk < tasks_D + tasks_gate)
+      for (int e = threadIdx.x; e < G * 32; e += kThreads) { const int k = e >> 5, j = e & 31, c = (blk - tasks_D) * 32 + j; wc_C[e] = c < 3 * G ? p.gru_U[(size_t)k * 3 * G + c] : 0.f; }
+    if (blk < tasks_Z)
+      for (int e = threadIdx.x; e < D * 32; e += kThreads) { const int k = e >> 5, j = e & 31, c = blk * 32 + j; wc_D[e] = c < Z ? p.W_zq[(size_t)k * Z + c] : 0.f; }
+    __syncthreads();
+  }
+
   // ---- prologue: gh(0) = h0 . U + b1 (every row starts from the learned initial state at t = 0) ----
   for (int task = blk; task < tasks_gate; task += nblk) {
     const int c0 = task * 32;
@@ -149,6 +61,14 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
     __syncthreads();
   }
   grid.sync();
+  auto stamp = [&](int i) {
+    if (p.stamps != nullptr && blk == 0 && threadIdx.x == 0) {
+      unsigned long long v;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
+      p.stamps[i] = v;
+    }
+  };
+  stamp(0);
 
   for (int t = 0; t < T; ++t) {
     // ================= stage A: masked inputs + gather-sum pre-GRU dense =================
@@ -192,23 +112,28 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
         p.h_in[bt * G + j] = first ? p.h0[j] : __ldcg(p.hz + (bt - 1) * W + j);
       }
     }
+    stamp(t * 8 + 1);
     grid.sync();
+    stamp(t * 8 + 2);
 
     // ================= stage B: gx = SiLU(LN(x_pre)) . K + b0 =================
     {
       const float* xp = p.x_pre + (size_t)t * D;  // row b at stride T*D
+      if (t == 10) stamp(T * 8 + 1);
       cta_ln_stats(sm, xp, T * D, B, D);
+      if (t == 10) stamp(T * 8 + 2);
       for (int e = gtid; e < B * D; e += gthreads) {  // every CTA publishes a slice of u = SiLU(LN(x_pre)) for the backward pass
         const int b = e / D, k = e % D;
         const float n = (__ldcg(xp + (size_t)b * T * D + k) - sm.mean[b]) * sm.rstd[b] * p.pre_g[k] + p.pre_b[k];
-        p.u_act[((size_t)b * T + t) * D + k] = n * sigmoidf_(n);
+        p.u_act[((size_t)b * T + t) * D + k] = n * sigmoid_fast(n);
       }
       if (blk == 0 && threadIdx.x < B) { p.x_mean[(size_t)threadIdx.x * T + t] = sm.mean[threadIdx.x]; p.x_rstd[(size_t)threadIdx.x * T + t] = sm.rstd[threadIdx.x]; }
+      if (t == 10) stamp(T * 8 + 3);
       for (int task = blk; task < tasks_gate; task += nblk) {
         const int c0 = task * 32;
-        task_gemv(sm, p.gru_K, 3 * G, c0, 3 * G, D, B, [&](int b, int k) {
+        task_gemv(sm, cached ? wc_B : p.gru_K, cached ? 32 : 3 * G, cached ? 0 : c0, cached ? 32 : 3 * G, D, B, [&](int b, int k) {
           const float n = (__ldcg(xp + (size_t)b * T * D + k) - sm.mean[b]) * sm.rstd[b] * p.pre_g[k] + p.pre_b[k];
-          return n * sigmoidf_(n);
+          return n * sigmoid_fast(n);
         });
         for (int e = threadIdx.x; e < B * 32; e += kThreads) {
           const int b = e >> 5, j = e & 31;
@@ -216,8 +141,11 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
         }
         __syncthreads();
       }
+      if (t == 10) stamp(T * 8 + 4);
     }
+    stamp(t * 8 + 3);
     grid.sync();
+    stamp(t * 8 + 4);
 
     // ================= stage C: h = GRU(gx, gh, h_in);  p_pre += h . W_post[E:];  gh(t+1) = h_in(t+1) . U + b1 ==========
     {
@@ -226,9 +154,9 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
         const size_t bt = (size_t)b * T + t;
         const float* gxr = p.gx_raw + (size_t)b * 3 * G;
         const float* ghr = p.gh + bt * 3 * G;
-        const float z = sigmoidf_(__ldcg(gxr + k) + __ldcg(ghr + k));
-        const float r = sigmoidf_(__ldcg(gxr + G + k) + __ldcg(ghr + G + k));
-        const float c = tanhf(__ldcg(gxr + 2 * G + k) + r * __ldcg(ghr + 2 * G + k));
+        const float z = sigmoid_fast(__ldcg(gxr + k) + __ldcg(ghr + k));
+        const float r = sigmoid_fast(__ldcg(gxr + G + k) + __ldcg(ghr + G + k));
+        const float c = tanh_fast(__ldcg(gxr + 2 * G + k) + r * __ldcg(ghr + 2 * G + k));
         return z * __ldcg(p.h_in + bt * G + k) + (1.f - z) * c;
       };
       // every CTA publishes a slice of h_t and of the gate activations (z, r, c) for the backward pass
@@ -237,9 +165,9 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
         const size_t bt = (size_t)b * T + t;
         const float* gxr = p.gx_raw + (size_t)b * 3 * G;
         const float* ghr = p.gh + bt * 3 * G;
-        const float z = sigmoidf_(__ldcg(gxr + k) + __ldcg(ghr + k));
-        const float r = sigmoidf_(__ldcg(gxr + G + k) + __ldcg(ghr + G + k));
-        const float c = tanhf(__ldcg(gxr + 2 * G + k) + r * __ldcg(ghr + 2 * G + k));
+        const float z = sigmoid_fast(__ldcg(gxr + k) + __ldcg(ghr + k));
+        const float r = sigmoid_fast(__ldcg(gxr + G + k) + __ldcg(ghr + G + k));
+        const float c = tanh_fast(__ldcg(gxr + 2 * G + k) + r * __ldcg(ghr + 2 * G + k));
         p.hz[bt * W + k] = z * __ldcg(p.h_in + bt * G + k) + (1.f - z) * c;
         float* gt = p.gates + bt * 3 * G;
         gt[k] = z; gt[G + k] = r; gt[2 * G + k] = c;
@@ -247,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
       for (int task = blk; task < ntask; task += nblk) {
         if (task < tasks_D) {
           const int c0 = task * 32;
-          task_gemv(sm, W_post_h, D, c0, D, G, B, h_of);
+          task_gemv(sm, cached ? wc_C : W_post_h, cached ? 32 : D, cached ? 0 : c0, cached ? 32 : D, G, B, h_of);
           for (int e = threadIdx.x; e < B * 32; e += kThreads) {
             const int b = e >> 5, j = e & 31;
             if (c0 + j < D) { float* q = p.p_pre + ((size_t)b * T + t) * D + c0 + j; *q = __ldcg(q) + sm.tile[b][j]; }
@@ -255,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
           __syncthreads();
         } else {
           const int c0 = (task - tasks_D) * 32;
-          task_gemv(sm, p.gru_U, 3 * G, c0, 3 * G, G, B, [&](int b, int k) {
+          task_gemv(sm, cached ? wc_C : p.gru_U, cached ? 32 : 3 * G, cached ? 0 : c0, cached ? 32 : 3 * G, G, B, [&](int b, int k) {
             const bool first = p.is_first[(size_t)b * T + t + 1] != 0.f;
             return first ? p.h0[k] : h_of(b, k);
           });
@@ -267,7 +195,9 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
         }
       }
     }
+    stamp(t * 8 + 5);
     grid.sync();
+    stamp(t * 8 + 6);
 
     // ================= stage D: logits = SiLU(LN(p_pre)) . W_zq + b -> unimix probs, sample z_t =================
     {
@@ -276,14 +206,14 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
       for (int e = gtid; e < B * D; e += gthreads) {
         const int b = e / D, k = e % D;
         const float n = (__ldcg(pp + (size_t)b * T * D + k) - sm.mean[b]) * sm.rstd[b] * p.post_g[k] + p.post_b[k];
-        p.p_act[((size_t)b * T + t) * D + k] = n * sigmoidf_(n);
+        p.p_act[((size_t)b * T + t) * D + k] = n * sigmoid_fast(n);
       }
       if (blk == 0 && threadIdx.x < B) { p.p_mean[(size_t)threadIdx.x * T + t] = sm.mean[threadIdx.x]; p.p_rstd[(size_t)threadIdx.x * T + t] = sm.rstd[threadIdx.x]; }
       for (int task = blk; task < tasks_Z; task += nblk) {
         const int c0 = task * 32;
-        task_gemv(sm, p.W_zq, Z, c0, Z, D, B, [&](int b, int k) {
+        task_gemv(sm, cached ? wc_D : p.W_zq, cached ? 32 : Z, cached ? 0 : c0, cached ? 32 : Z, D, B, [&](int b, int k) {
           const float n = (__ldcg(pp + (size_t)b * T * D + k) - sm.mean[b]) * sm.rstd[b] * p.post_g[k] + p.post_b[k];
-          return n * sigmoidf_(n);
+          return n * sigmoid_fast(n);
         });
         // bias + publish logits
         for (int e = threadIdx.x; e < B * 32; e += kThreads) {
@@ -316,7 +246,9 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
         __syncthreads();
       }
     }
+    stamp(t * 8 + 7);
     grid.sync();
+    stamp(t * 8 + 8);
   }
 }
 
@@ -333,10 +265,16 @@ int scan_fwd_max_ctas(int device) {
 }
 
 cudaError_t launch_observe_scan_fwd(cudaStream_t s, const ScanFwdParams& p, int ctas) {
-  cudaFuncSetAttribute(observe_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
   ScanFwdParams pp = p;
+  // smem-resident weights need one task per CTA per stage and 3 tiles of [K x 32] fp32 next to the staging buffers
+  const int tg = (3 * p.G + 31) / 32, td = (p.D + 31) / 32, tz = (p.Z + 31) / 32;
+  const size_t cache = ((size_t)2 * p.D + p.G) * 32 * sizeof(float);
+  const bool fits = sizeof(Smem) + cache <= 227 * 1024 && ctas >= tg + td && ctas >= tz;
+  pp.cache_weights = fits ? 1 : 0;
+  const size_t smem = sizeof(Smem) + (fits ? cache : 0);
+  cudaFuncSetAttribute(observe_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   void* args[] = {&pp};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)observe_scan_fwd_kernel, dim3(ctas), dim3(kThreads), args, sizeof(Smem), s);
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)observe_scan_fwd_kernel, dim3(ctas), dim3(kThreads), args, smem, s);
   if (e == cudaSuccess) count_launch();
   return e;
 }

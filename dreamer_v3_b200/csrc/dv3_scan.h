@@ -31,9 +31,40 @@ struct ScanFwdParams {
   float* p_pre;          // [B, T, D], pre-loaded with enc . W_post[:E]
   float* p_mean; float* p_rstd; float* p_act;
   float* post_logits; float* post_probs; int32_t* z_idx;
+  int cache_weights;           // set by the launcher: weight tiles resident in shared memory
+  unsigned long long* stamps;  // optional [T*5+1] globaltimer stamps of CTA 0 (debug / profiling), may be null
+};
+
+struct ScanBwdParams {
+  int B, T, G, D, Z, Zc, Zk;
+  // transposed weight copies (refreshed once per update)
+  const float* Wt_zq;      // [Z, D]
+  const float* Wt_post_h;  // [D, G]
+  const float* Ut;         // [3G, G]
+  const float* Kt;         // [3G, D]
+  const float* Wt_pre_z;   // [D, Z]
+  const float* post_g; const float* post_b; const float* pre_g; const float* pre_b;
+  // saved by the forward pass (B-major [B, T, ...])
+  const float* is_first; const float* post_logits; const float* dpost;
+  const float* p_pre; const float* p_mean; const float* p_rstd;
+  const float* gates; const float* gh; const float* h_in;
+  const float* x_pre; const float* x_mean; const float* x_rstd;
+  // gradients
+  float* d_hz;       // [B, T, G+Z] in: heads + prior contributions; the kernel adds the recurrent ones
+  float* dlogits;    // [B, T, Z]  posterior logits
+  float* dp_act;     // [B, T, D]  grad w.r.t. SiLU(LN(p_pre))
+  float* dp_pre;     // [B, T, D]
+  float* dh_tot;     // [B, G] scratch
+  float* dgx; float* dgh;  // [B, T, 3G]
+  float* dh_in;      // [B, T, G]
+  float* du;         // [B, T, D]  grad w.r.t. SiLU(LN(x_pre))
+  float* dx_pre;     // [B, T, D]
 };
 
 size_t scan_fwd_smem_bytes();
+int scan_bwd_max_ctas(int device);
+cudaError_t launch_observe_scan_bwd(cudaStream_t s, const ScanBwdParams& p, int ctas);
+void transpose_f32(cudaStream_t s, const float* in, float* out, int rows, int cols);
 int scan_fwd_max_ctas(int device);  // 0 when the kernel cannot be made co-resident
 cudaError_t launch_observe_scan_fwd(cudaStream_t s, const ScanFwdParams& p, int ctas);
 

@@ -1,0 +1,119 @@
+// Shared device pieces of the persistent scan kernels (forward: dv3_scan.cu, backward: dv3_scan_bwd.cu).
+#pragma once
+#include <cooperative_groups.h>
+
+#include "dv3_device.cuh"
+#include "dv3_scan.h"
+
+namespace dv3 {
+namespace scan {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kRows = 16;      // max rows (replay sequences) handled per launch
+constexpr int kKC = 128;       // k-chunk staged per warp
+constexpr int kRedLd = 33;
+constexpr int kInLd = 20;     // row stride of the staged activations (16 rows + pad): conflict-free float4 stores
+
+struct Smem {
+  float in_chunk[kWarps][kKC][kInLd];   // 80 KB
+  float red[kWarps][kRows][kRedLd];     // 16.5 KB
+  float tile[kRows][kRedLd];            // reduced output tile
+  float mean[kRows], rstd[kRows];
+  float s1[kRows], s2[kRows];         // LayerNorm-backward row statistics
+};
+
+// One task: out_tile[b][j] = sum_k in(b,k) * W[k*ldw + c0 + j], j < 32, k < K. `in_fn(b, k)` produces the input
+// on the fly (LayerNorm / GRU gates are applied here by the consumer). Result is left in sm.tile (all threads
+// synchronised on return).
+template <class InFn>
+__device__ __forceinline__ void task_gemv(Smem& sm, const float* __restrict__ W, int ldw, int c0, int ncols, int K,
+                                          int B, InFn in_fn) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ks = (K + kWarps - 1) / kWarps;
+  const int k0 = warp * ks, k1 = min(K, k0 + ks);
+  const bool col_ok = (c0 + lane) < ncols;
+  float acc[kRows];
+#pragma unroll
+  for (int b = 0; b < kRows; ++b) acc[b] = 0.f;
+  for (int kc = k0; kc < k1; kc += kKC) {
+    const int kn = min(kKC, k1 - kc);
+    // stage in[b][kc .. kc+kn) -> in_chunk[warp][kk][b]; lanes run along k (coalesced global reads), each lane
+    // gathers the 16 rows of its k in registers and stores them as four float4
+    for (int kb = 0; kb < kn; kb += 32) {
+      const int kk = kb + lane;
+      float v[kRows];
+#pragma unroll
+      for (int b = 0; b < kRows; ++b) v[b] = (b < B && kk < kn) ? in_fn(b, kc + kk) : 0.f;
+      if (kk < kn) {
+        float4* dst = reinterpret_cast<float4*>(&sm.in_chunk[warp][kk][0]);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+        dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+      }
+    }
+    __syncwarp();
+    const float* wp = W + (size_t)kc * ldw + c0 + lane;
+    for (int kk0 = 0; kk0 < kn; kk0 += 8) {
+      float wv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wv[j] = (col_ok && kk0 + j < kn) ? wp[(size_t)(kk0 + j) * ldw] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int kk = min(kk0 + j, kn - 1);
+        const float4* iv = reinterpret_cast<const float4*>(&sm.in_chunk[warp][kk][0]);
+        const float4 a0 = iv[0], a1 = iv[1], a2 = iv[2], a3 = iv[3];
+        const float w_ = wv[j];
+        acc[0] = fmaf(a0.x, w_, acc[0]); acc[1] = fmaf(a0.y, w_, acc[1]); acc[2] = fmaf(a0.z, w_, acc[2]); acc[3] = fmaf(a0.w, w_, acc[3]);
+        acc[4] = fmaf(a1.x, w_, acc[4]); acc[5] = fmaf(a1.y, w_, acc[5]); acc[6] = fmaf(a1.z, w_, acc[6]); acc[7] = fmaf(a1.w, w_, acc[7]);
+        acc[8] = fmaf(a2.x, w_, acc[8]); acc[9] = fmaf(a2.y, w_, acc[9]); acc[10] = fmaf(a2.z, w_, acc[10]); acc[11] = fmaf(a2.w, w_, acc[11]);
+        acc[12] = fmaf(a3.x, w_, acc[12]); acc[13] = fmaf(a3.y, w_, acc[13]); acc[14] = fmaf(a3.z, w_, acc[14]); acc[15] = fmaf(a3.w, w_, acc[15]);
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int b = 0; b < kRows; ++b) sm.red[warp][b][lane] = acc[b];
+  __syncthreads();
+  for (int e = threadIdx.x; e < kRows * 32; e += kThreads) {
+    const int b = e >> 5, j = e & 31;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += sm.red[w][b][j];
+    sm.tile[b][j] = s;
+  }
+  __syncthreads();
+}
+
+// LayerNorm statistics of rows x[b*ldx .. +D) for b < B, by the whole CTA -> sm.mean / sm.rstd. Each warp keeps its
+// row in registers (D <= 1024): all loads are issued together, so the cost is one L2 latency, not a chain of them.
+__device__ __forceinline__ void cta_ln_stats(Smem& sm, const float* x, int ldx, int B, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = warp; b < B; b += kWarps) {
+    const float* xr = x + (size_t)b * ldx;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = (c < D) ? __ldcg(xr + c) : 0.f;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += v[i];
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float d = (lane + 32 * i < D) ? v[i] - mean : 0.f;
+      q += d * d;
+    }
+    const float var = warp_sum(q) / (float)D;
+    if (lane == 0) { sm.mean[b] = mean; sm.rstd[b] = rsqrtf(var + DV3_LN_EPS); }
+  }
+  __syncthreads();
+}
+
+
+}  // namespace scan
+}  // namespace dv3

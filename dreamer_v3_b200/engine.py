@@ -180,13 +180,13 @@ class Engine:
     def critic_update_ema(self, decay=0.98):
         self._check(self.lib.dv3_critic_update_ema(self.h, decay, self._stream()), "dv3_critic_update_ema")
 
-    def train_world_model_step(self):
-        self._check(self.lib.dv3_train_world_model_step(self.h, C.byref(self.hp), self._stream()),
-                    "dv3_train_world_model_step")
+    def train_world_model_step(self, noise_seed=0, use_graph=True):
+        self._check(self.lib.dv3_train_world_model_step(self.h, C.byref(self.hp), int(noise_seed), int(use_graph),
+                                                        self._stream()), "dv3_train_world_model_step")
 
-    def train_actor_critic_step(self):
-        self._check(self.lib.dv3_train_actor_critic_step(self.h, C.byref(self.hp), self._stream()),
-                    "dv3_train_actor_critic_step")
+    def train_actor_critic_step(self, noise_seed=0, use_graph=True):
+        self._check(self.lib.dv3_train_actor_critic_step(self.h, C.byref(self.hp), int(noise_seed), int(use_graph),
+                                                         self._stream()), "dv3_train_actor_critic_step")
 
     def train_update(self, noise_seed=0, use_graph=True):
         self._check(self.lib.dv3_train_update(self.h, C.byref(self.hp), int(noise_seed), int(use_graph), self._stream()),

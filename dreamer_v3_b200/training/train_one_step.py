@@ -19,13 +19,17 @@ def train_world_model_one_step(*, sample, batch_size_B, batch_length_T, grad_cli
     e = world_model.engine
     assert int(batch_length_T) == e.cfg.T
     e.set_sample(sample)
-    world_model._draw_noise(1)
-    e.observe_forward()
-    e.wm_loss_backward()
-    if _dp(e):
-        dist.all_reduce(e.group_buffer("world_model", "grad"))
     opt = world_model.optimizer
-    e.optimizer_step("world_model", float(grad_clip), opt.learning_rate, opt.epsilon)
+    if _dp(e):
+        world_model._draw_noise(1)
+        e.observe_forward()
+        e.wm_loss_backward()
+        dist.all_reduce(e.group_buffer("world_model", "grad"))
+        e.optimizer_step("world_model", float(grad_clip), opt.learning_rate, opt.epsilon)
+    else:
+        # single process: forward + losses + BPTT + clip/Adam replayed as ONE CUDA graph (noise drawn inside it)
+        e.hp.wm_grad_clip, e.hp.wm_lr, e.hp.wm_eps = float(grad_clip), opt.learning_rate, opt.epsilon
+        e.train_world_model_step(noise_seed=0 if world_model._explicit_noise else world_model.noise_seed)
     t = e.tensor
     s = t("wm.scalars")
     stats = t("opt.world_model.stats")
@@ -55,11 +59,24 @@ def train_actor_and_critic_one_step(*, world_model_forward_train_outs, is_termin
     hp.gamma, hp.lambda_, hp.entropy_scale = float(gamma), float(lambda_), float(entropy_scale)
     hp.return_normalization_decay = float(return_normalization_decay)
     hp.train_actor = int(bool(train_actor))
+    t = e.tensor
+    aopt, copt = dreamer_model.actor.optimizer, dreamer_model.critic.optimizer
+    hz = t("wm.hz")
+    h_in = world_model_forward_train_outs["h_states_BxT"]
+    own_states = torch.is_tensor(h_in) and h_in.is_cuda and h_in.data_ptr() == hz.data_ptr()
+    if not _dp(e) and own_states and horizon_H == e.cfg.H:
+        # single process, dreaming from the engine's own last observe pass: the whole actor/critic update (dream, value
+        # targets, losses, gradients, clip/Adam x2, critic EMA) is ONE CUDA-graph replay
+        wm = dreamer_model.world_model
+        e.write("in.is_terminated", torch.as_tensor(is_terminated).reshape(e.cfg.B, e.cfg.T))
+        hp.actor_grad_clip, hp.critic_grad_clip = float(actor_grad_clip), float(critic_grad_clip)
+        hp.ac_lr, hp.ac_eps, hp.critic_ema_decay = aopt.learning_rate, aopt.epsilon, dreamer_model.critic.ema_decay
+        e.train_actor_critic_step(noise_seed=0 if wm._explicit_noise else wm.noise_seed)
+        return _ac_results(e, dreamer_model._dream_outs(), train_actor)
     dream_data = dreamer_model.dream_trajectory(
         start_states={"h": world_model_forward_train_outs["h_states_BxT"],
                       "z": world_model_forward_train_outs["z_states_BxT"]},
         start_is_terminated=is_terminated, timesteps_H=horizon_H, gamma=gamma)
-    t = e.tensor
     if _dp(e):
         e.ac_loss_backward(1)
         dist.all_gather_into_tensor(t("ac.value_targets_all"), t("ac.value_targets"))
@@ -69,11 +86,15 @@ def train_actor_and_critic_one_step(*, world_model_forward_train_outs, is_termin
             dist.all_reduce(e.group_buffer("actor", "grad"))
     else:
         e.ac_loss_backward(3)
-    aopt, copt = dreamer_model.actor.optimizer, dreamer_model.critic.optimizer
     if train_actor:
         e.optimizer_step("actor", float(actor_grad_clip), aopt.learning_rate, aopt.epsilon)
     # critic Adam + update_ema() fused (train_one_step.py:235-250)
     e.optimizer_step("critic", float(critic_grad_clip), copt.learning_rate, copt.epsilon, dreamer_model.critic.ema_decay)
+    return _ac_results(e, dream_data, train_actor)
+
+
+def _ac_results(e, dream_data, train_actor):
+    t = e.tensor
     s = t("ac.scalars")
     results = {
         "VALUE_TARGETS_symlog_H_B": t("ac.VALUE_TARGETS_symlog_H_B"),

@@ -113,8 +113,9 @@ int dv3_wm_loss_backward(dv3_engine* e, void* stream);
 /* tf.clip_by_global_norm + Keras Adam (+ critic EMA for group 2) on a group's flat buffers
  * (train_one_step.py:80-86, 214-250). Call after the gradient all-reduce when world_size > 1. */
 int dv3_optimizer_step(dv3_engine* e, int group, float clip, float lr, float eps, float ema_decay, void* stream);
-/* One call = train_world_model_one_step (train_one_step.py:17-126) for world_size == 1. */
-int dv3_train_world_model_step(dv3_engine* e, const dv3_hparams* hp, void* stream);
+/* One call = train_world_model_one_step (train_one_step.py:17-126) for world_size == 1. noise_seed != 0: in.u_post is
+ * drawn on the device first; use_graph: the call is captured once into a CUDA graph and replayed. */
+int dv3_train_world_model_step(dv3_engine* e, const dv3_hparams* hp, uint64_t noise_seed, int use_graph, void* stream);
 
 /* ---- dreamer / actor / critic --------------------------------------------------------------- */
 /* DreamerModel.dream_trajectory (dreamer_model.py:147-303). start states: start_from_observe=1 uses
@@ -129,8 +130,9 @@ int dv3_ac_loss_backward(dv3_engine* e, const dv3_hparams* hp, int phase, void* 
 /* CriticNetwork.init_ema / update_ema (critic_network.py:84-100). */
 int dv3_critic_init_ema(dv3_engine* e, void* stream);
 int dv3_critic_update_ema(dv3_engine* e, float decay, void* stream);
-/* One call = train_actor_and_critic_one_step (train_one_step.py:130-252) for world_size == 1. */
-int dv3_train_actor_critic_step(dv3_engine* e, const dv3_hparams* hp, void* stream);
+/* One call = train_actor_and_critic_one_step (train_one_step.py:130-252) for world_size == 1 (dreams from the states of
+ * the last observe pass; same noise_seed / use_graph meaning as above). */
+int dv3_train_actor_critic_step(dv3_engine* e, const dv3_hparams* hp, uint64_t noise_seed, int use_graph, void* stream);
 
 /* ---- whole update captured as CUDA graphs ---------------------------------------------------- */
 /* Captures {wm step, ac step} once into a CUDA graph on `stream` and replays it: one launch per

@@ -118,6 +118,7 @@ class ParityRun:
         if cfg.discrete:
             self.cmp_exact("dream.action_indices", t("dream.action_indices"), dream["actions_ints_dreamed_t0_to_H_B"])
         self.cmp("dream.rewards", t("dream.rewards"), dream["rewards_dreamed_t0_to_H_B"])
+        self.cmp_exact("dream.continue_flags", t("dream.continues"), dream["continues_dreamed_t0_to_H_B"])
         self.cmp("dream.continues", t("dream.continues"), dream["continues_dreamed_t0_to_H_B"])
         self.cmp("dream.values", t("dream.values"), dream["values_dreamed_t0_to_H_B"])
         self.cmp("dream.value_logits", t("dream.value_logits"), dream["values_symlog_dreamed_logits_t0_to_HxB"])

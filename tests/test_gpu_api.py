@@ -1,0 +1,88 @@
+"""The reference-facing Python API (WorldModel / DreamerModel / train_*_one_step) on the GPU: result-dict keys of
+training/train_one_step.py:88-126, critic_loss.py:78-89, actor_loss.py:81-96 and values against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+WM_KEYS = {
+    "WORLD_MODEL_forward_train_outs", "WORLD_MODEL_learned_initial_h", "WORLD_MODEL_L_decoder_B_T", "WORLD_MODEL_L_decoder",
+    "WORLD_MODEL_L_reward_B_T", "WORLD_MODEL_L_reward", "WORLD_MODEL_L_continue_B_T", "WORLD_MODEL_L_continue",
+    "WORLD_MODEL_L_prediction_B_T", "WORLD_MODEL_L_prediction", "WORLD_MODEL_L_dynamics_B_T", "WORLD_MODEL_L_dynamics",
+    "WORLD_MODEL_L_representation_B_T", "WORLD_MODEL_L_representation", "WORLD_MODEL_L_total_B_T", "WORLD_MODEL_L_total",
+    "WORLD_MODEL_gradients_maxabs", "WORLD_MODEL_gradients_clipped_by_glob_norm_maxabs"}
+FWD_KEYS = {"sampled_obs_symlog_BxT", "obs_distribution_BxT", "reward_logits_BxT", "rewards_BxT", "continue_distribution_BxT",
+            "continues_BxT", "z_posterior_probs_BxT", "z_prior_probs_BxT", "h_states_BxT", "z_states_BxT"}
+AC_KEYS = {
+    "VALUE_TARGETS_symlog_H_B", "CRITIC_L_total", "CRITIC_L_total_H_B", "CRITIC_L_neg_logp_of_value_targets_H_B",
+    "CRITIC_L_neg_logp_of_value_targets", "CRITIC_L_slow_critic_regularization_H_B", "CRITIC_L_slow_critic_regularization",
+    "VALUE_TARGETS_H_B", "dream_data", "ACTOR_L_total_H_B", "ACTOR_L_total", "ACTOR_logp_actions_dreamed_H_B",
+    "ACTOR_scaled_value_targets_H_B", "ACTOR_value_targets_pct95_ema", "ACTOR_value_targets_pct5_ema",
+    "ACTOR_action_entropy_H_B", "ACTOR_action_entropy", "ACTOR_L_neglogp_reinforce_term_H_B", "ACTOR_L_neglogp_reinforce_term",
+    "ACTOR_L_neg_entropy_term_H_B", "ACTOR_L_neg_entropy_term", "ACTOR_gradients_maxabs",
+    "ACTOR_gradients_clipped_by_glob_norm_maxabs", "CRITIC_gradients_maxabs", "CRITIC_gradients_clipped_by_glob_norm_maxabs"}
+DREAM_KEYS = {"h_states_t0_to_H_B", "z_states_prior_t0_to_H_B", "rewards_dreamed_t0_to_H_B", "continues_dreamed_t0_to_H_B",
+              "actions_dreamed_t0_to_H_B", "actions_dreamed_distributions_t0_to_H_B", "values_dreamed_t0_to_H_B",
+              "values_symlog_dreamed_logits_t0_to_HxB", "v_symlog_dreamed_ema_t0_to_H_B", "dream_loss_weights_t0_to_H_B"}
+
+
+@pytest.mark.parametrize("discrete", [True, False])
+def test_api_matches_oracle_over_three_updates(discrete):
+    from dreamer_v3_b200.models.components import MLP, VectorDecoder
+    from dreamer_v3_b200.models.dreamer_model import DreamerModel
+    from dreamer_v3_b200.models.world_model import WorldModel
+    from dreamer_v3_b200.spec import Box, Discrete
+    from dreamer_v3_b200.training.train_one_step import train_actor_and_critic_one_step, train_world_model_one_step
+    from oracle.dreamer_oracle import Oracle, make_synthetic_sample
+    B, T, H = 4, 8, 5
+    space = Discrete(3) if discrete else Box(-1, 1, (2,))
+    wm = WorldModel(model_dimension="XXS", action_space=space, batch_length_T=T, encoder=MLP(model_dimension="XXS"),
+                    decoder=VectorDecoder(model_dimension="XXS", observation_space=Box(-1, 1, (5,))), symlog_obs=True, seed=3)
+    dm = DreamerModel(model_dimension="XXS", action_space=space, batch_size_B=B, batch_length_T=T, horizon_H=H, world_model=wm)
+    e = dm.engine
+    cfg = e.cfg
+    # break the symmetry of the zero-initialised heads so that every loss term is exercised
+    g = torch.Generator().manual_seed(0)
+    for n in ("rew.head.w", "critic.head.w"):
+        e.tensor(n).copy_(0.02 * torch.randn(e.tensor(n).shape, generator=g))
+    dm.critic.init_ema()
+    oracle = Oracle(cfg, e.get_params(), dtype=torch.float64)
+    sample = make_synthetic_sample(cfg, seed=5)
+    rng = np.random.default_rng(6)
+    assert set(dm.get_initial_state()) == {"h", "z", "a"}
+    for step in range(3):
+        ores = oracle.train_world_model_one_step(sample, rng=rng, margin=1e-3)
+        wm.set_noise(u_post=oracle.last_noise["u_post"])
+        res = train_world_model_one_step(sample=sample, batch_size_B=B, batch_length_T=T, grad_clip=1000.0, world_model=wm)
+        assert set(res) == WM_KEYS and set(res["WORLD_MODEL_forward_train_outs"]) == FWD_KEYS
+        for k in ("WORLD_MODEL_L_total", "WORLD_MODEL_L_decoder", "WORLD_MODEL_L_reward", "WORLD_MODEL_L_continue",
+                  "WORLD_MODEL_L_dynamics", "WORLD_MODEL_L_prediction"):
+            np.testing.assert_allclose(float(res[k]), float(ores[k]), rtol=1e-4)
+        np.testing.assert_allclose(res["WORLD_MODEL_L_total_B_T"].cpu().numpy(), ores["WORLD_MODEL_L_total_B_T"].detach().numpy(), rtol=1e-4)
+        fwd = res["WORLD_MODEL_forward_train_outs"]
+        ofwd = ores["WORLD_MODEL_forward_train_outs"]
+        np.testing.assert_allclose(fwd["h_states_BxT"].cpu().numpy(), ofwd["h_states_BxT"].numpy(), atol=1e-4)
+        np.testing.assert_array_equal(fwd["z_states_BxT"].argmax(-1).cpu().numpy(), ofwd["z_indices_BxT"])
+        np.testing.assert_allclose(fwd["obs_distribution_BxT"].loc.cpu().numpy(), ofwd["obs_distribution_BxT.loc"].numpy(), atol=1e-4)
+        np.testing.assert_allclose(float(res["WORLD_MODEL_gradients_maxabs"]), ores["WORLD_MODEL_gradients_maxabs"], rtol=1e-3)
+        oac = oracle.train_actor_and_critic_one_step(ofwd["h_states_BxT"], ofwd["z_states_BxT"], sample["is_terminated"], H=H,
+                                                     rng=rng, margin=1e-3)
+        wm.set_noise(u_dyn=oracle.last_noise["u_dyn"], act_noise=oracle.last_noise["u_act" if discrete else "eps_act"])
+        ac = train_actor_and_critic_one_step(
+            world_model_forward_train_outs=fwd, is_terminated=torch.as_tensor(sample["is_terminated"]).reshape(-1),
+            horizon_H=H, gamma=0.997, lambda_=0.95, actor_grad_clip=100.0, critic_grad_clip=100.0, disagree_grad_clip=100.0,
+            dreamer_model=dm, entropy_scale=3e-4, return_normalization_decay=0.99)
+        assert set(ac) == AC_KEYS
+        assert DREAM_KEYS <= set(ac["dream_data"])
+        for k in ("CRITIC_L_total", "ACTOR_L_total", "ACTOR_action_entropy", "CRITIC_L_neg_logp_of_value_targets"):
+            np.testing.assert_allclose(float(ac[k]), float(oac[k]), rtol=2e-4, atol=1e-6)
+        np.testing.assert_allclose(ac["VALUE_TARGETS_H_B"].cpu().numpy(), oac["VALUE_TARGETS_H_B"].detach().numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(float(ac["ACTOR_value_targets_pct95_ema"]), oac["ACTOR_value_targets_pct95_ema"], rtol=1e-4, atol=1e-6)
+        d, od = ac["dream_data"], oac["dream_data"]
+        np.testing.assert_allclose(d["rewards_dreamed_t0_to_H_B"].cpu().numpy(), od["rewards_dreamed_t0_to_H_B"].detach().numpy(), atol=1e-4)
+        np.testing.assert_allclose(d["dream_loss_weights_t0_to_H_B"].cpu().numpy(), od["dream_loss_weights_t0_to_H_B"].detach().numpy(), atol=1e-5)
+        dist0 = d["actions_dreamed_distributions_t0_to_H_B"][0]
+        assert dist0.entropy().shape == (cfg.N,)
+    assert dm.critic.optimizer.iterations == 3 and wm.optimizer.iterations == 3
+    e.close()

@@ -20,6 +20,7 @@ CASES = {
     "nano-img-disc": dict(size="nano", A=4, discrete=True, image_obs=True, B=2, T=3, H=3),
     "micro-img-box": dict(size="micro", A=2, discrete=False, image_obs=True, B=2, T=4, H=3),
     "xxs-vec-disc": dict(size="XXS", A=2, discrete=True, B=4, T=8, H=5),
+    "xxs-b8": dict(size="XXS", A=3, discrete=True, B=8, T=16, H=3),
     "xs-cartpole": dict(size="XS", A=2, discrete=True, B=16, T=64, H=15, obs_dim=4),
     "xs-pendulum": dict(size="XS", A=1, discrete=False, B=16, T=64, H=15, obs_dim=3),
 }
@@ -31,6 +32,7 @@ if __name__ == "__main__":
     ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--top", type=int, default=400)
     ap.add_argument("--thresh", type=float, default=1e-4)
+    ap.add_argument("--margin", type=float, default=1e-3)
     args = ap.parse_args()
     for name in args.cases.split(","):
         kw = dict(CASES[name])
@@ -39,7 +41,7 @@ if __name__ == "__main__":
         print(f"===== {name}  {cfg.asdict()}", flush=True)
         t0 = time.time()
         try:
-            run = ParityRun(cfg, steps=args.steps, compute_mode=args.mode)
+            run = ParityRun(cfg, steps=args.steps, compute_mode=args.mode, margin=args.margin)
         except Exception:
             traceback.print_exc()
             continue

@@ -1,0 +1,31 @@
+"""Per-stage timing of the persistent observe-scan forward kernel (CTA 0 globaltimer stamps)."""
+import os
+import sys
+
+os.environ["DV3_SCAN_STAMPS"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from bench import make_cfg, synthetic_sample  # noqa: E402
+from dreamer_v3_b200.engine import Engine  # noqa: E402
+from dreamer_v3_b200.spec import init_params  # noqa: E402
+
+wid = sys.argv[1] if len(sys.argv) > 1 else "c2"
+cfg = make_cfg(wid)
+e = Engine(cfg)
+e.load_params(init_params(cfg, seed=0))
+e.set_sample(synthetic_sample(cfg, 0))
+e.fill_noise(1, 0, 3)
+for _ in range(3):
+    e.observe_forward()
+torch.cuda.synchronize()
+st = e.tensor("debug.scan_stamps").cpu().numpy().astype(np.int64)
+st = (st[0::2] & 0xFFFFFFFF) | (st[1::2] << 32)
+T = cfg.T
+d = np.diff(st[: T * 8 + 1].astype(np.float64)) / 1e3  # us
+d = d.reshape(T, 8)
+names = ["A work", "A sync", "B work", "B sync", "C work", "C sync", "D work", "D sync"]
+ex = st[T * 8 + 1: T * 8 + 5].astype(np.float64)
+print("stage B detail at t=10 (us): ln_stats %.2f publish %.2f task %.2f" % tuple(np.diff(ex) / 1e3))
+print("per-step mean us:", {n: round(float(d[2:, i].mean()), 2) for i, n in enumerate(names)}, "step total", round(float(d[2:].sum(1).mean()), 2))
