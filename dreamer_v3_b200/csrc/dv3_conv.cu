@@ -58,6 +58,56 @@ __global__ void col2im_kernel(const float* __restrict__ cols, float* __restrict_
   }
 }
 
+__global__ void im2col_v4_kernel(const float4* __restrict__ img, float4* __restrict__ cols, int n, int H, int W, int C4) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)n * Ho * Wo * 16 * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    long long t = i / C4;
+    const int kx = (int)(t & 3); t >>= 2;
+    const int ky = (int)(t & 3); t >>= 2;
+    const int ox = (int)(t % Wo); t /= Wo;
+    const int oy = (int)(t % Ho); t /= Ho;
+    const int b = (int)t;
+    const int y = 2 * oy - 1 + ky, x = 2 * ox - 1 + kx;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y >= 0 && y < H && x >= 0 && x < W) v = img[(((size_t)b * H + y) * W + x) * C4 + c];
+    cols[i] = v;
+  }
+}
+
+__global__ void col2im_v4_kernel(const float4* __restrict__ cols, float4* __restrict__ img, int n, int H, int W, int C4,
+                                 const float* __restrict__ bias, float add_const) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)n * H * W * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    long long t = i / C4;
+    const int x = (int)(t % W); t /= W;
+    const int y = (int)(t % H); t /= H;
+    const int b = (int)t;
+    float4 acc = make_float4(add_const, add_const, add_const, add_const);
+    if (bias != nullptr) { acc.x += bias[4 * c]; acc.y += bias[4 * c + 1]; acc.z += bias[4 * c + 2]; acc.w += bias[4 * c + 3]; }
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const int ty = y + 1 - ky;
+      if (ty < 0 || (ty & 1)) continue;
+      const int oy = ty >> 1;
+      if (oy >= Ho) continue;
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx) {
+        const int tx = x + 1 - kx;
+        if (tx < 0 || (tx & 1)) continue;
+        const int ox = tx >> 1;
+        if (ox >= Wo) continue;
+        const float4 v = cols[((((size_t)b * Ho + oy) * Wo + ox) * 16 + ky * 4 + kx) * C4 + c];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    img[i] = acc;
+  }
+}
+
 inline int grid_for(long long n) {
   long long b = (n + 255) / 256;
   if (b > 148 * 32) b = 148 * 32;
@@ -68,12 +118,20 @@ inline int grid_for(long long n) {
 }  // namespace
 
 void im2col_k4s2(cudaStream_t s, const float* img, float* cols, int n, int H, int W, int C) {
-  im2col_kernel<<<grid_for((long long)n * (H / 2) * (W / 2) * 16 * C), 256, 0, s>>>(img, cols, n, H, W, C);
+  if (C % 4 == 0 && ((uintptr_t)img % 16 == 0) && ((uintptr_t)cols % 16 == 0))
+    im2col_v4_kernel<<<grid_for((long long)n * (H / 2) * (W / 2) * 16 * (C / 4)), 256, 0, s>>>(
+        reinterpret_cast<const float4*>(img), reinterpret_cast<float4*>(cols), n, H, W, C / 4);
+  else
+    im2col_kernel<<<grid_for((long long)n * (H / 2) * (W / 2) * 16 * C), 256, 0, s>>>(img, cols, n, H, W, C);
   count_launch();
 }
 void col2im_k4s2(cudaStream_t s, const float* cols, float* img, int n, int H, int W, int C, const float* bias,
                  float add_const) {
-  col2im_kernel<<<grid_for((long long)n * H * W * C), 256, 0, s>>>(cols, img, n, H, W, C, bias, add_const);
+  if (C % 4 == 0 && ((uintptr_t)img % 16 == 0) && ((uintptr_t)cols % 16 == 0))
+    col2im_v4_kernel<<<grid_for((long long)n * H * W * (C / 4)), 256, 0, s>>>(
+        reinterpret_cast<const float4*>(cols), reinterpret_cast<float4*>(img), n, H, W, C / 4, bias, add_const);
+  else
+    col2im_kernel<<<grid_for((long long)n * H * W * C), 256, 0, s>>>(cols, img, n, H, W, C, bias, add_const);
   count_launch();
 }
 

@@ -41,8 +41,9 @@ __global__ void op_2d_kernel(const float* __restrict__ src, int lds, float* __re
 }
 
 // ---- LayerNorm + SiLU: one warp per row ----------------------------------------------------------------
-constexpr int kLnMaxPerLane = 32;  // D <= 1024
-
+// templated on the per-lane element count so that narrow rows (conv channels, D = 24..96) do not pay for 32 predicated
+// iterations: EPL = ceil(D / 32) rounded up to a power of two
+template <int kLnMaxPerLane>
 __global__ void ln_silu_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ y, int ldy,
                                    float* __restrict__ mean_out, float* __restrict__ rstd_out, int sstride, long long rows, int D) {
@@ -85,6 +86,7 @@ __global__ void ln_silu_fwd_kernel(const float* __restrict__ x, int ldx, const f
   }
 }
 
+template <int kLnMaxPerLane>
 __global__ void ln_silu_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
                                    const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -133,13 +135,22 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ dy, int lddy, const
     }
   }
   if (dgamma != nullptr) {
+    // block-level reduction in shared memory first: one global atomic per column per block instead of per warp
+    __shared__ float sdg[32 * kLnMaxPerLane], sdb[32 * kLnMaxPerLane];
+    for (int c = threadIdx.x; c < 32 * kLnMaxPerLane; c += blockDim.x) { sdg[c] = 0.f; sdb[c] = 0.f; }
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < kLnMaxPerLane; ++i) {
       const int c = lane + 32 * i;
       if (c < D) {
-        atomicAdd(&dgamma[c], ag[i]);
-        atomicAdd(&dbeta[c], ab[i]);
+        atomicAdd(&sdg[c], ag[i]);
+        atomicAdd(&sdb[c], ab[i]);
       }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      atomicAdd(&dgamma[c], sdg[c]);
+      atomicAdd(&dbeta[c], sdb[c]);
     }
   }
 }
@@ -353,14 +364,30 @@ void add_2d(cudaStream_t s, const float* src, int lds, float* dst, int ldd, int 
 void ln_silu_fwd(cudaStream_t s, const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy,
                  float* mean, float* rstd, int sstride, long long rows, int D) {
   if (rows <= 0) return;
-  ln_silu_fwd_kernel<<<grid_for(rows, kThreads / 32, 148 * 8), kThreads, 0, s>>>(x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, D);
+  const int grid = grid_for(rows, kThreads / 32, 148 * 8);
+#define DV3_LN_FWD(E_) ln_silu_fwd_kernel<E_><<<grid, kThreads, 0, s>>>(x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, D)
+  if (D <= 32) DV3_LN_FWD(1);
+  else if (D <= 64) DV3_LN_FWD(2);
+  else if (D <= 128) DV3_LN_FWD(4);
+  else if (D <= 256) DV3_LN_FWD(8);
+  else if (D <= 512) DV3_LN_FWD(16);
+  else DV3_LN_FWD(32);
+#undef DV3_LN_FWD
   count_launch();
 }
 void ln_silu_bwd(cudaStream_t s, const float* dy, int lddy, const float* x, int ldx, const float* mean,
                  const float* rstd, const float* gamma, const float* beta, float* dx, int lddx, float* dgamma,
                  float* dbeta, int sstride, long long rows, int D) {
   if (rows <= 0) return;
-  ln_silu_bwd_kernel<<<grid_for(rows, kThreads / 32, 148 * 4), kThreads, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, D);
+  const int grid = grid_for(rows, kThreads / 32, 148 * 4);
+#define DV3_LN_BWD(E_) ln_silu_bwd_kernel<E_><<<grid, kThreads, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, D)
+  if (D <= 32) DV3_LN_BWD(1);
+  else if (D <= 64) DV3_LN_BWD(2);
+  else if (D <= 128) DV3_LN_BWD(4);
+  else if (D <= 256) DV3_LN_BWD(8);
+  else if (D <= 512) DV3_LN_BWD(16);
+  else DV3_LN_BWD(32);
+#undef DV3_LN_BWD
   count_launch();
 }
 

@@ -468,6 +468,8 @@ int Engine::init(const dv3_config* c) {
     const int tg = (3 * G + 31) / 32, td = (D + 31) / 32, tz = (Z + 31) / 32;
     int want = tg + td;
     if (tz > want) want = tz;
+    if ((G + 7) / 8 > want) want = (G + 7) / 8;
+    if (B > want) want = B;
     if (want < 8) want = 8;
     scan_ctas = want < max_ctas ? want : max_ctas;
     const int max_b = scan_bwd_max_ctas(cfg.device);

@@ -305,7 +305,8 @@ void launch_tc(cudaStream_t s, const GemmArgs& g) {
 
 // Large contractions go to the tensor cores; small-M scan steps and tiny shapes stay on the exact fp32 path.
 bool gemm_tc_eligible(const GemmArgs& g) {
-  return g.M >= 128 && g.N >= 16 && g.K >= 32 && (long long)g.M * g.N * g.K >= (1LL << 22);
+  if (g.N < 16 || g.K < 32 || (long long)g.M * g.N * g.K < (1LL << 22)) return false;
+  return g.M >= 128 || (g.M >= 16 && g.K >= 4096);  // skinny outputs only when the contraction is long (weight gradients)
 }
 
 void gemm_tc(cudaStream_t s, const GemmArgs& g) {

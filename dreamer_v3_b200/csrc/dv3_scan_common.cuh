@@ -27,12 +27,22 @@ struct Smem {
 // on the fly (LayerNorm / GRU gates are applied here by the consumer). Result is left in sm.tile (all threads
 // synchronised on return).
 template <class InFn>
+__device__ __forceinline__ void task_gemv_col(Smem& sm, const float* __restrict__ W, int ldw, int col, int K, int B, InFn in_fn);
+
+template <class InFn>
 __device__ __forceinline__ void task_gemv(Smem& sm, const float* __restrict__ W, int ldw, int c0, int ncols, int K,
                                           int B, InFn in_fn) {
+  const int lane = threadIdx.x & 31;
+  task_gemv_col(sm, W, ldw, (c0 + lane) < ncols ? c0 + lane : -1, K, B, in_fn);
+}
+
+// Same, with the output column of each lane given explicitly (col < 0: lane idle): out_tile[b][lane] = sum_k in(b,k) W[k*ldw + col]
+template <class InFn>
+__device__ __forceinline__ void task_gemv_col(Smem& sm, const float* __restrict__ W, int ldw, int col, int K, int B, InFn in_fn) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ks = (K + kWarps - 1) / kWarps;
   const int k0 = warp * ks, k1 = min(K, k0 + ks);
-  const bool col_ok = (c0 + lane) < ncols;
+  const bool col_ok = col >= 0;
   float acc[kRows];
 #pragma unroll
   for (int b = 0; b < kRows; ++b) acc[b] = 0.f;
@@ -54,7 +64,7 @@ __device__ __forceinline__ void task_gemv(Smem& sm, const float* __restrict__ W,
       }
     }
     __syncwarp();
-    const float* wp = W + (size_t)kc * ldw + c0 + lane;
+    const float* wp = W + (size_t)kc * ldw + (col_ok ? col : 0);
     for (int kk0 = 0; kk0 < kn; kk0 += 8) {
       float wv[8];
 #pragma unroll

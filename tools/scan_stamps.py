@@ -25,7 +25,7 @@ st = (st[0::2] & 0xFFFFFFFF) | (st[1::2] << 32)
 T = cfg.T
 d = np.diff(st[: T * 8 + 1].astype(np.float64)) / 1e3  # us
 d = d.reshape(T, 8)
-names = ["A work", "A sync", "B work", "B sync", "C work", "C sync", "D work", "D sync"]
-ex = st[T * 8 + 1: T * 8 + 5].astype(np.float64)
-print("stage B detail at t=10 (us): ln_stats %.2f publish %.2f task %.2f" % tuple(np.diff(ex) / 1e3))
+names = ["A work", "A sync", "B work", "B sync", "C work", "Csync+D0+sync", "D work", "D sync"]
+ex = None
+
 print("per-step mean us:", {n: round(float(d[2:, i].mean()), 2) for i, n in enumerate(names)}, "step total", round(float(d[2:].sum(1).mean()), 2))
