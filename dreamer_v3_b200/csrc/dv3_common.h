@@ -27,6 +27,9 @@ struct GemmArgs {
   int M, N, K;
   const float* bias;  // nullable, added once
   float beta;         // 0 -> overwrite, 1 -> accumulate into C
+  // optional bf16 shadow of op(B), K-major: Bh[n*ldbh + k] (tensor-core path only; refreshed by the engine after
+  // each optimizer step). When set the tensor-core kernel reads it instead of converting B.
+  const void* Bh = nullptr; int ldbh = 0;
 };
 
 // ---- gemm (dv3_gemm.cu) ----------------------------------------------------------------------
@@ -35,6 +38,10 @@ void gemm_f32(cudaStream_t s, const GemmArgs& g);
 void gemm_dispatch(cudaStream_t s, const GemmArgs& g, int mode);
 bool gemm_tc_eligible(const GemmArgs& g);
 void gemm_tc(cudaStream_t s, const GemmArgs& g);  // bf16 tcgen05 / TMEM path
+// bf16 shadows of weight matrices: out_t[c*rows + r] = bf16(in[r*cols + c]) (transposed), out_n = bf16(in) (plain)
+void weight_shadow_bf16(cudaStream_t s, const float* in, void* out_t, void* out_n, int rows, int cols);
+struct ShadowDesc { const float* in; void* out_t; void* out_n; int rows, cols, tile_begin, pad; };
+void weight_shadow_batched(cudaStream_t s, const ShadowDesc* descs_dev, int n, int total_tiles);
 
 // ---- elementwise / normalisation / recurrent cells (dv3_elem.cu) ---------------------------------
 void symlog_fwd(cudaStream_t s, const float* x, float* y, long long n);

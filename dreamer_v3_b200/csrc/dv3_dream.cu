@@ -31,6 +31,7 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
   const LnLayer& Wx = pre_mlp.layers[0];
   const LnLayer& Wd = dyn_mlp.layers[0];
   const int W = G + Z;
+  refresh_shadows(s);  // the world model was just updated (run_experiment.py:426-459), actor / critic at the end of the last step
   // start states: row n = b*T + t of the observe pass (run_experiment.py:458-460)
   if (start_from_observe) {
     cudaMemcpyAsync(dr_hz, hz, (size_t)N * W * 4, cudaMemcpyDeviceToDevice, s);

@@ -455,6 +455,7 @@ int Engine::init(const dv3_config* c) {
   dry = false; arena_off = 0;
   layout();
   bind_params();
+  if (cfg.compute_mode == 1) build_shadows();
   // LayerNorm gains default to 1 so that an un-initialised engine is still well defined.
   for (const auto& p : pinfo) {
     if (p.name.size() > 2 && p.name.compare(p.name.size() - 2, 2, ".g") == 0)
@@ -476,6 +477,7 @@ int Engine::init(const dv3_config* c) {
     const int tgb = (G + 31) / 32;
     int wb = tgb + td;
     if (tz > wb) wb = tz;
+    if (B > wb) wb = B;
     if (wb < 8) wb = 8;
     scan_bwd_ctas = wb < max_b ? wb : max_b;
   }
@@ -494,10 +496,64 @@ void Engine::destroy() {
   allocations.clear();
 }
 
+// ------------------------------------------------------------------------------------------ bf16 weight shadows
+void Engine::build_shadows() {
+  shadow_host.clear();
+  shadow_tiles = 0;
+  size_t bytes = 0;
+  for (const auto& p : pinfo) {
+    if (p.shape.size() < 2) continue;
+    const long long cols = p.shape.back(), rows = prod(p.shape) / cols;
+    if (rows * cols < 4096) continue;  // too small to ever reach the tensor-core path
+    bytes += (size_t)((rows * cols * 2 + 255) / 256 * 256) * 2;
+  }
+  char* base = nullptr;
+  if (bytes == 0 || cudaMalloc((void**)&base, bytes) != cudaSuccess) return;
+  allocations.push_back(base);
+  size_t off = 0;
+  for (const auto& p : pinfo) {
+    if (p.shape.size() < 2) continue;
+    const long long cols = p.shape.back(), rows = prod(p.shape) / cols;
+    if (rows * cols < 4096) continue;
+    const size_t sz = (size_t)(rows * cols * 2 + 255) / 256 * 256;
+    ShadowDesc d{};
+    d.in = params[p.group] + p.off; d.rows = (int)rows; d.cols = (int)cols;
+    d.out_t = base + off; off += sz;
+    d.out_n = base + off; off += sz;
+    d.tile_begin = shadow_tiles;
+    shadow_tiles += ((int)cols + 31) / 32 * (((int)rows + 31) / 32);
+    shadow_host.push_back(d);
+  }
+  if (cudaMalloc((void**)&shadow_dev, shadow_host.size() * sizeof(ShadowDesc)) != cudaSuccess) { shadow_host.clear(); return; }
+  allocations.push_back(shadow_dev);
+  cudaMemcpy(shadow_dev, shadow_host.data(), shadow_host.size() * sizeof(ShadowDesc), cudaMemcpyHostToDevice);
+}
+
+void Engine::refresh_shadows(cudaStream_t s) {
+  if (cfg.compute_mode != 1 || shadow_host.empty()) return;
+  weight_shadow_batched(s, shadow_dev, (int)shadow_host.size(), shadow_tiles);
+}
+
 // ------------------------------------------------------------------------------------------ building blocks
 void Engine::mm(const float* A_, int lda, bool ta, const float* B_, int ldb, bool tb, float* C, int ldc, int M, int N_,
                 int K, const float* bias, float beta) {
   GemmArgs g{A_, lda, ta ? 1 : 0, B_, ldb, tb ? 1 : 0, C, ldc, M, N_, K, bias, beta};
+  if (cfg.compute_mode == 1 && !shadow_host.empty() && gemm_tc_eligible(g)) {
+    // is B a (sub-block of a) weight matrix with a bf16 shadow?
+    for (const ShadowDesc& d : shadow_host) {
+      if (B_ < d.in || B_ >= d.in + (size_t)d.rows * d.cols || ldb != d.cols) continue;
+      const size_t off = (size_t)(B_ - d.in);
+      const int r0 = (int)(off / d.cols), c0 = (int)(off % d.cols);
+      if (!tb) {  // op(B)(k, n) = W[r0 + k][c0 + n] -> transposed shadow T[c0 + n][r0 + k]
+        g.Bh = reinterpret_cast<const unsigned short*>(d.out_t) + (size_t)c0 * d.rows + r0;
+        g.ldbh = d.rows;
+      } else {    // op(B)(k, n) = W[r0 + n][c0 + k] -> plain shadow
+        g.Bh = reinterpret_cast<const unsigned short*>(d.out_n) + off;
+        g.ldbh = d.cols;
+      }
+      break;
+    }
+  }
   gemm_dispatch(cur, g, cfg.compute_mode);
 }
 

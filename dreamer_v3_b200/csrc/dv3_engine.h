@@ -118,6 +118,13 @@ struct Engine {
   unsigned long long* noise_step = nullptr;
   float last_gamma = 0.997f;
 
+  // ---- bf16 weight shadows for the tensor-core path (compute_mode 1) ----
+  std::vector<ShadowDesc> shadow_host;
+  ShadowDesc* shadow_dev = nullptr;
+  int shadow_tiles = 0;
+  void build_shadows();
+  void refresh_shadows(cudaStream_t s);
+
   // ---- graph ----
   struct GraphSlot { cudaGraphExec_t exec = nullptr; long long launches = 0; dv3_hparams hp{}; uint64_t seed = 0; };
   GraphSlot slot_wm, slot_ac;

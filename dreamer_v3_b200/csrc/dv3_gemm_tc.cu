@@ -12,6 +12,8 @@
 // Epilogue: tcgen05.ld 32 lanes x 32 columns per warp -> bias / accumulate -> fp32 global stores.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "dv3_common.h"
 
 namespace dv3 {
@@ -107,6 +109,42 @@ struct Fill {
   }
 };
 
+// B operand already in bf16, K-major (weight shadow): plain 128-bit copies, 8 bf16 per task, no conversion.
+template <int ROWS>
+struct FillBf16 {
+  static constexpr int kTasks = ROWS * 8 / kTcThreads;
+  uint4 v[kTasks];
+  __device__ __forceinline__ void load(const __nv_bfloat16* __restrict__ src, int ld, int r0, int rmax, int k0, int kmax) {
+#pragma unroll
+    for (int i = 0; i < kTasks; ++i) {
+      const int task = threadIdx.x + i * kTcThreads;
+      const int r = task >> 3, kc = task & 7;
+      const int gr = r0 + r, gk = k0 + kc * 8;
+      uint4 t = make_uint4(0u, 0u, 0u, 0u);
+      if (gr < rmax && gk < kmax) {
+        const __nv_bfloat16* p = src + (size_t)gr * ld + gk;
+        if (gk + 7 < kmax) t = *reinterpret_cast<const uint4*>(p);   // ld and k0 are multiples of 8: 16-byte aligned
+        else {
+          unsigned short h[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) h[j] = (gk + j < kmax) ? reinterpret_cast<const unsigned short*>(p)[j] : (unsigned short)0;
+          t.x = h[0] | ((uint32_t)h[1] << 16); t.y = h[2] | ((uint32_t)h[3] << 16);
+          t.z = h[4] | ((uint32_t)h[5] << 16); t.w = h[6] | ((uint32_t)h[7] << 16);
+        }
+      }
+      v[i] = t;
+    }
+  }
+  __device__ __forceinline__ void store(uint32_t tile) const {
+#pragma unroll
+    for (int i = 0; i < kTasks; ++i) {
+      const int task = threadIdx.x + i * kTcThreads;
+      const int r = task >> 3, kc = task & 7;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + sw128_chunk_off(r, kc)), "r"(v[i].x), "r"(v[i].y), "r"(v[i].z), "r"(v[i].w) : "memory");
+    }
+  }
+};
+
 // ---- descriptors ---------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B: start>>4 | LBO(=1)<<16 | SBO(=1024>>4)<<32 | version 1 | layout 2
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -153,8 +191,8 @@ struct TcSmem {
   uint32_t tmem_base;
 };
 
-template <int BN, bool TA, bool TB>
-__global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(GemmArgs g, int k_per_split, int vecA, int vecB, int use_atomic) {
+template <int BN, bool TA, bool TB, bool BH>
+__global__ void __launch_bounds__(kTcThreads, (BN <= 128) ? 2 : 1) gemm_tc_kernel(GemmArgs g, int k_per_split, int vecA, int vecB, int use_atomic) {
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   TcSmem<BN>& sm = *reinterpret_cast<TcSmem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -178,17 +216,8 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(GemmArgs g, int k_p
   const uint32_t tmem = sm.tmem_base;
   const uint32_t idesc = make_idesc(BN);
 
-  Fill<BM, TA> fa;
-  Fill<BN, !TB> fb;
-  fa.load(g.A, g.lda, m0, g.M, kbeg, kend, vecA);
-  fb.load(g.B, g.ldb, n0, g.N, kbeg, kend, vecB);
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb % kStages;
-    if (kb >= kStages) mbar_wait(&sm.bar[s], (uint32_t)(((kb / kStages) - 1) & 1));  // MMAs that read this stage are done
-    fa.store(smem_u32(sm.a[s]), vecA);
-    fb.store(smem_u32(sm.b[s]), vecB);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
-    __syncthreads();
+  // issue the MMAs of one staged k-block (one elected thread) and commit them to the stage's mbarrier
+  auto issue_mma = [&](int kb, int s) {
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t a_addr = smem_u32(sm.a[s]), b_addr = smem_u32(sm.b[s]);
@@ -207,10 +236,58 @@ __global__ void __launch_bounds__(kTcThreads) gemm_tc_kernel(GemmArgs g, int k_p
       // arrives on the stage's mbarrier once every MMA issued so far has completed
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sm.bar[s])) : "memory");
     }
-    if (kb + 1 < nkb) {  // next k-block's global loads fly while the tensor core works on this one
-      const int k0 = kbeg + (kb + 1) * BK;
-      fa.load(g.A, g.lda, m0, g.M, k0, kend, vecA);
-      fb.load(g.B, g.ldb, n0, g.N, k0, kend, vecB);
+  };
+  if constexpr (BH) {
+    // B comes from the bf16 K-major weight shadow: half the bytes and no conversion, which frees enough registers to
+    // keep TWO k-blocks of global loads in flight per thread
+    const __nv_bfloat16* Bh = reinterpret_cast<const __nv_bfloat16*>(g.Bh);
+    Fill<BM, TA> fa[2];
+    FillBf16<BN> fb[2];
+    fa[0].load(g.A, g.lda, m0, g.M, kbeg, kend, vecA);
+    fb[0].load(Bh, g.ldbh, n0, g.N, kbeg, kend);
+    if (nkb > 1) {
+      fa[1].load(g.A, g.lda, m0, g.M, kbeg + BK, kend, vecA);
+      fb[1].load(Bh, g.ldbh, n0, g.N, kbeg + BK, kend);
+    }
+#pragma unroll 1
+    for (int kb2 = 0; kb2 < nkb; kb2 += 2) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int kb = kb2 + u;
+        if (kb < nkb) {
+          const int s = u;  // kStages == 2: stage index == register set index == kb & 1
+          if (kb >= kStages) mbar_wait(&sm.bar[s], (uint32_t)(((kb / kStages) - 1) & 1));
+          fa[u].store(smem_u32(sm.a[s]), vecA);
+          fb[u].store(smem_u32(sm.b[s]));
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncthreads();
+          issue_mma(kb, s);
+          if (kb + 2 < nkb) {
+            const int k0 = kbeg + (kb + 2) * BK;
+            fa[u].load(g.A, g.lda, m0, g.M, k0, kend, vecA);
+            fb[u].load(Bh, g.ldbh, n0, g.N, k0, kend);
+          }
+        }
+      }
+    }
+  } else {
+    Fill<BM, TA> fa;
+    Fill<BN, !TB> fb;
+    fa.load(g.A, g.lda, m0, g.M, kbeg, kend, vecA);
+    fb.load(g.B, g.ldb, n0, g.N, kbeg, kend, vecB);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kStages;
+      if (kb >= kStages) mbar_wait(&sm.bar[s], (uint32_t)(((kb / kStages) - 1) & 1));  // MMAs that read this stage are done
+      fa.store(smem_u32(sm.a[s]), vecA);
+      fb.store(smem_u32(sm.b[s]), vecB);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
+      __syncthreads();
+      issue_mma(kb, s);
+      if (kb + 1 < nkb) {  // next k-block's global loads fly while the tensor core works on this one
+        const int k0 = kbeg + (kb + 1) * BK;
+        fa.load(g.A, g.lda, m0, g.M, k0, kend, vecA);
+        fb.load(g.B, g.ldb, n0, g.N, k0, kend, vecB);
+      }
     }
   }
   // wait for the last commit (it covers all earlier MMAs)
@@ -288,20 +365,94 @@ void launch_tc(cudaStream_t s, const GemmArgs& g) {
   do {                                                                                                            \
     static bool configured = false;                                                                               \
     if (!configured) {                                                                                            \
-      cudaFuncSetAttribute(gemm_tc_kernel<BN, TA_, TB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      cudaFuncSetAttribute(gemm_tc_kernel<BN, TA_, TB_, BH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       configured = true;                                                                                          \
     }                                                                                                             \
-    gemm_tc_kernel<BN, TA_, TB_><<<grid, block, smem, s>>>(g, kps, vA, vB, use_atomic);                           \
+    gemm_tc_kernel<BN, TA_, TB_, BH_><<<grid, block, smem, s>>>(g, kps, vA, vB, use_atomic);                      \
   } while (0)
-  if (!g.ta && !g.tb) DV3_TC_LAUNCH(false, false);
-  else if (!g.ta && g.tb) DV3_TC_LAUNCH(false, true);
-  else if (g.ta && !g.tb) DV3_TC_LAUNCH(true, false);
-  else DV3_TC_LAUNCH(true, true);
+  const bool bh = g.Bh != nullptr && (g.ldbh % 8 == 0) && ((uintptr_t)g.Bh % 16 == 0) && (kps % 8 == 0);
+#define BH_ false
+  if (!bh) {
+    if (!g.ta && !g.tb) DV3_TC_LAUNCH(false, false);
+    else if (!g.ta && g.tb) DV3_TC_LAUNCH(false, true);
+    else if (g.ta && !g.tb) DV3_TC_LAUNCH(true, false);
+    else DV3_TC_LAUNCH(true, true);
+  }
+#undef BH_
+#define BH_ true
+  if (bh) {
+    if (!g.ta) DV3_TC_LAUNCH(false, true);
+    else DV3_TC_LAUNCH(true, true);
+  }
+#undef BH_
 #undef DV3_TC_LAUNCH
   count_launch();
 }
 
 }  // namespace
+
+namespace {
+__global__ void weight_shadow_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out_t,
+                                     __nv_bfloat16* __restrict__ out_n, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = blockIdx.y * 32 + i;
+    const float v = (r < rows && c < cols) ? in[(size_t)r * cols + c] : 0.f;
+    tile[i][threadIdx.x] = v;
+    if (out_n != nullptr && r < rows && c < cols) out_n[(size_t)r * cols + c] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  const int r2 = blockIdx.y * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c2 = blockIdx.x * 32 + i;
+    if (out_t != nullptr && r2 < rows && c2 < cols) out_t[(size_t)c2 * rows + r2] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+}  // namespace
+
+namespace {
+__global__ void weight_shadow_batched_kernel(const ShadowDesc* __restrict__ descs, int n) {
+  __shared__ float tile[32][33];
+  // find the matrix this block belongs to (descs sorted by tile_begin)
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (descs[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const ShadowDesc d = descs[lo];
+  const int local = blockIdx.x - d.tile_begin;
+  const int tiles_x = (d.cols + 31) / 32;
+  const int bx = local % tiles_x, by = local / tiles_x;
+  __nv_bfloat16* out_t = reinterpret_cast<__nv_bfloat16*>(d.out_t);
+  __nv_bfloat16* out_n = reinterpret_cast<__nv_bfloat16*>(d.out_n);
+  const int c = bx * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = by * 32 + i;
+    const float v = (r < d.rows && c < d.cols) ? d.in[(size_t)r * d.cols + c] : 0.f;
+    tile[i][threadIdx.x] = v;
+    if (r < d.rows && c < d.cols) out_n[(size_t)r * d.cols + c] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  const int r2 = by * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c2 = bx * 32 + i;
+    if (r2 < d.rows && c2 < d.cols) out_t[(size_t)c2 * d.rows + r2] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+}  // namespace
+
+void weight_shadow_batched(cudaStream_t s, const ShadowDesc* descs_dev, int n, int total_tiles) {
+  if (n <= 0 || total_tiles <= 0) return;
+  weight_shadow_batched_kernel<<<total_tiles, dim3(32, 8), 0, s>>>(descs_dev, n);
+  count_launch();
+}
+
+void weight_shadow_bf16(cudaStream_t s, const float* in, void* out_t, void* out_n, int rows, int cols) {
+  dim3 grid(cdiv(cols, 32), cdiv(rows, 32)), block(32, 8);
+  weight_shadow_kernel<<<grid, block, 0, s>>>(in, reinterpret_cast<__nv_bfloat16*>(out_t), reinterpret_cast<__nv_bfloat16*>(out_n), rows, cols);
+  count_launch();
+}
 
 // Large contractions go to the tensor cores; small-M scan steps and tiny shapes stay on the exact fp32 path.
 bool gemm_tc_eligible(const GemmArgs& g) {
@@ -310,6 +461,12 @@ bool gemm_tc_eligible(const GemmArgs& g) {
 }
 
 void gemm_tc(cudaStream_t s, const GemmArgs& g) {
+  if (const char* f = std::getenv("DV3_TC_BN")) {  // probing aid
+    const int bn = std::atoi(f);
+    if (bn == 256) return launch_tc<256>(s, g);
+    if (bn == 128) return launch_tc<128>(s, g);
+    if (bn == 64) return launch_tc<64>(s, g);
+  }
   // widest N tile that still yields enough CTAs to occupy the GPU (split-K costs an atomic epilogue, so the
   // tile shape is the first lever for parallelism)
   const long long mt = cdiv(g.M, BM);

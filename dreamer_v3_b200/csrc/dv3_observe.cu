@@ -31,6 +31,7 @@ int Engine::observe_forward(cudaStream_t s) {
   const LnLayer& Wd = dyn_mlp.layers[0];
   const int ldhz = T * (G + Z);
 
+  refresh_shadows(s);
   if (cfg.symlog_obs) symlog_fwd(s, in_obs, obs_sym, (long long)N * OF);  // world_model.py:206-207
   encoder_fwd();
   scan_prepare(s, in_actions, in_is_first, a_in, wf, B, T, A);
@@ -38,7 +39,9 @@ int Engine::observe_forward(cudaStream_t s) {
   mm(a_in, A, false, Wx.w + (size_t)Z * D, D, false, actW, D, N, D, A);  // hoisted: a_{t-1} . W_pre[Z:]
   initial_state(s);
 
-  if (use_persistent && scan_ctas > 0) {
+  // measured on B200: the persistent kernel wins up to size L; at XL (GRU 4096) weight streaming dominates and the
+  // per-op path with split-K GEMMs is faster
+  if (use_persistent && scan_ctas > 0 && G <= 2048) {
     ScanFwdParams sp{};
     sp.B = B; sp.T = T; sp.G = G; sp.D = D; sp.Z = Z; sp.Zc = Zc; sp.Zk = Zk; sp.E = E;
     sp.W_pre = Wx.w; sp.pre_g = Wx.g; sp.pre_b = Wx.b; sp.gru_K = gru_K; sp.gru_U = gru_U; sp.gru_b = gru_b;

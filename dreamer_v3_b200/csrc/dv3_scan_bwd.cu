@@ -1,13 +1,16 @@
 // Reverse-time BPTT through the RSSM observe scan as ONE cooperative launch (replaces the ~700 per-op launches of
 // the reverse loop in Engine::wm_loss_backward). Only input gradients are on the recurrence; every weight gradient
-// is a single N-row contraction after the kernel. Per step t (T-1 .. 0), 4 grid-synchronised stages:
-//   R2  dp_act = dlogits[t] . W_zq^T
-//   R3  dp_pre = LN'SiLU'(dp_act)  (applied by the consumer)      dh_tot = d_hz[t].h + dp_pre . W_post[E:]^T
-//   R4  GRU gate gradients from dh_tot (applied by the consumer)   dh_in  = dh_tot*z + dgh . U^T ;  du = dgx . K^T
-//   R5  dx_pre = LN'SiLU'(du)                                      dz_in  = dx_pre . W_pre[:Z]^T
-//       epilogue: d_hz[t-1] += (1 - is_first[t]) * (dh_in, dz_in), then the straight-through / KL backward of the
-//       posterior categoricals of step t-1 right away (dlogits[t-1]) -- so no separate stage for it.
-// The contractions read TRANSPOSED weight copies (refreshed once per update) so that weight reads stay coalesced.
+// is a single N-row contraction after the kernel. Per step t (T-1 .. 0), 6 short grid-synchronised stages:
+//   R2   dp_act = dlogits[t] . W_zq^T                                       (32-column tasks, K split over 8 warps)
+//   R3a  dp_pre = LN'SiLU'(dp_act)                                          (row owners: one CTA per sequence)
+//   R3   dh_tot = d_hz[t].h + dp_pre . W_post[E:]^T, GRU gate gradients dgx / dgh of the task's 32 units
+//   R4   dh_in  = dh_tot*z + dgh . U^T ;  du = dgx . K^T
+//   R5a  dx_pre = LN'SiLU'(du);  d_hz[t-1].h += (1 - is_first[t]) dh_in     (row owners)
+//   R5   dz_in  = dx_pre . W_pre[:Z]^T;  d_hz[t-1].z += (1 - is_first[t]) dz_in, then the straight-through / KL
+//        backward of the posterior categoricals of step t-1 right away (dlogits[t-1]) -- no separate stage for it.
+// Stage inputs are published to global memory by their producer and staged by plain copies, so no CTA recomputes
+// another CTA's non-linearities. The contractions read TRANSPOSED weight copies (refreshed once per update) so that
+// weight reads stay coalesced.
 #include "dv3_scan_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -21,44 +24,6 @@ using namespace scan;
 __device__ __forceinline__ float silu_grad(float n) {
   const float sg = sigmoidf_(n);
   return sg * (1.f + n * (1.f - sg));
-}
-
-// Row statistics of the LayerNorm backward for rows b < B: s1 = mean(dxhat), s2 = mean(dxhat * xhat), plus mean/rstd
-// copied to smem. dy rows at dy + b*lddy, x rows at x + b*ldx. One warp per row, row cached in registers.
-__device__ __forceinline__ void cta_lnbwd_stats(Smem& sm, const float* dy, int lddy, const float* x, int ldx,
-                                                const float* mean, const float* rstd, int sstride,
-                                                const float* __restrict__ gamma, const float* __restrict__ beta, int B, int D) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int b = warp; b < B; b += kWarps) {
-    const float m = mean[(size_t)b * sstride], r = rstd[(size_t)b * sstride];
-    float xv[32], dv[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int c = lane + 32 * i;
-      xv[i] = (c < D) ? __ldcg(x + (size_t)b * ldx + c) : 0.f;
-      dv[i] = (c < D) ? __ldcg(dy + (size_t)b * lddy + c) : 0.f;
-    }
-    float a1 = 0.f, a2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int c = lane + 32 * i;
-      if (c < D) {
-        const float xh = (xv[i] - m) * r;
-        const float g = gamma[c];
-        const float dxh = dv[i] * silu_grad(xh * g + beta[c]) * g;
-        a1 += dxh; a2 += dxh * xh;
-      }
-    }
-    a1 = warp_sum(a1) / (float)D; a2 = warp_sum(a2) / (float)D;
-    if (lane == 0) { sm.mean[b] = m; sm.rstd[b] = r; sm.s1[b] = a1; sm.s2[b] = a2; }
-  }
-  __syncthreads();
-}
-// dx element of the LayerNorm+SiLU backward given the row statistics in smem
-__device__ __forceinline__ float lnbwd_elem(const Smem& sm, float dy, float x, float g, float bt, int b) {
-  const float xh = (x - sm.mean[b]) * sm.rstd[b];
-  const float dxh = dy * silu_grad(xh * g + bt) * g;
-  return sm.rstd[b] * (dxh - sm.s1[b] - xh * sm.s2[b]);
 }
 
 // Straight-through + KL backward of the posterior categoricals (representation_layer.py:73-113) for the (row, cat)
@@ -78,6 +43,35 @@ __device__ __forceinline__ void repr_bwd_pair(const ScanBwdParams& p, int b, int
   if (act) p.dlogits[bt * Z + col] = pr * (g - dot);
 }
 
+// Row-owner LayerNorm+SiLU backward of one row: dy/x held as up to 4 values per thread (d = tid + 256 i < D).
+__device__ __forceinline__ void row_lnbwd(Smem& sm, const float (&dy)[4], const float (&x)[4], float mean, float rstd,
+                                          const float* __restrict__ gamma, const float* __restrict__ beta, int D, float (&dx)[4]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* red = &sm.red[0][0][0];
+  float xh[4], dxh[4];
+  float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = threadIdx.x + kThreads * i;
+    if (d < D) {
+      xh[i] = (x[i] - mean) * rstd;
+      const float g = gamma[d];
+      dxh[i] = dy[i] * silu_grad(xh[i] * g + beta[d]) * g;
+      a1 += dxh[i]; a2 += dxh[i] * xh[i];
+    } else { xh[i] = 0.f; dxh[i] = 0.f; }
+  }
+  a1 = warp_sum(a1); a2 = warp_sum(a2);
+  if (lane == 0) { red[warp] = a1; red[kWarps + warp] = a2; }
+  __syncthreads();
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) { s1 += red[w]; s2 += red[kWarps + w]; }
+  s1 /= (float)D; s2 /= (float)D;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dx[i] = rstd * (dxh[i] - s1 - xh[i] * s2);
+}
+
 __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -95,7 +89,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
   grid.sync();
 
   for (int t = T - 1; t >= 0; --t) {
-    // ================= R2: dp_act = dlogits[t] . W_zq^T   (Wt_zq [Z, D]) =================
+    // ===== R2: dp_act = dlogits[t] . W_zq^T   (Wt_zq [Z, D]) =====
     for (int task = blk; task < tasks_D; task += nblk) {
       const int c0 = task * 32;
       task_gemv(sm, p.Wt_zq, D, c0, D, Z, B, [&](int b, int k) { return __ldcg(p.dlogits + ((size_t)b * T + t) * Z + k); });
@@ -107,56 +101,57 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
     }
     grid.sync();
 
-    // ================= R3: dp_pre = LN'SiLU'(dp_act);  dh_tot = d_hz[t].h + dp_pre . W_post_h^T  (Wt_post_h [D, G]) ==========
-    {
-      const float* dy = p.dp_act + (size_t)t * D;
-      const float* xx = p.p_pre + (size_t)t * D;
-      cta_lnbwd_stats(sm, dy, T * D, xx, T * D, p.p_mean + t, p.p_rstd + t, T, p.post_g, p.post_b, B, D);
-      for (int e = gtid; e < B * D; e += gthreads) {  // publish dp_pre[t] for the weight gradients
-        const int b = e / D, k = e % D;
-        p.dp_pre[((size_t)b * T + t) * D + k] =
-            lnbwd_elem(sm, __ldcg(dy + (size_t)b * T * D + k), __ldcg(xx + (size_t)b * T * D + k), p.post_g[k], p.post_b[k], b);
+    // ===== R3a (row owners): dp_pre = LN'SiLU'(dp_act) =====
+    for (int b = blk; b < B; b += nblk) {
+      const size_t bt = (size_t)b * T + t;
+      float dy[4], x[4], dx[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = threadIdx.x + kThreads * i;
+        dy[i] = d < D ? __ldcg(p.dp_act + bt * D + d) : 0.f;
+        x[i] = d < D ? p.p_pre[bt * D + d] : 0.f;
       }
-      for (int task = blk; task < tasks_G; task += nblk) {
-        const int c0 = task * 32;
-        task_gemv(sm, p.Wt_post_h, G, c0, G, D, B, [&](int b, int k) {
-          return lnbwd_elem(sm, __ldcg(dy + (size_t)b * T * D + k), __ldcg(xx + (size_t)b * T * D + k), p.post_g[k], p.post_b[k], b);
-        });
-        for (int e = threadIdx.x; e < B * 32; e += kThreads) {
-          const int b = e >> 5, j = e & 31;
-          if (c0 + j < G) p.dh_tot[(size_t)b * G + c0 + j] = sm.tile[b][j] + __ldcg(p.d_hz + ((size_t)b * T + t) * W + c0 + j);
-        }
-        __syncthreads();
+      row_lnbwd(sm, dy, x, p.p_mean[bt], p.p_rstd[bt], p.post_g, p.post_b, D, dx);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = threadIdx.x + kThreads * i;
+        if (d < D) p.dp_pre[bt * D + d] = dx[i];
       }
     }
     grid.sync();
 
-    // ================= R4: GRU backward (gates applied by the consumer) =================
-    {
-      // gate gradient k in [0, 3G) of row b; for_gh selects dgh (third block scaled by r) vs dgx
-      auto dgate = [&](int b, int k, bool for_gh) {
-        const size_t bt = (size_t)b * T + t;
-        const int j = k % G, blk3 = k / G;
-        const float* gt = p.gates + bt * 3 * G;
-        const float z = gt[j], r = gt[G + j], c = gt[2 * G + j];
-        const float d = __ldcg(p.dh_tot + (size_t)b * G + j);
-        const float dc = d * (1.f - z) * (1.f - c * c);
-        if (blk3 == 0) return d * (p.h_in[bt * G + j] - c) * z * (1.f - z);
-        if (blk3 == 1) return dc * p.gh[bt * 3 * G + 2 * G + j] * r * (1.f - r);
-        return for_gh ? dc * r : dc;
-      };
-      for (int e = gtid; e < B * 3 * G; e += gthreads) {  // publish dgx[t], dgh[t] for the weight gradients
-        const int b = e / (3 * G), k = e % (3 * G);
-        const size_t o = ((size_t)b * T + t) * 3 * G + k;
-        const float vx = dgate(b, k, false);
-        p.dgx[o] = vx;
-        p.dgh[o] = (k >= 2 * G) ? vx * p.gates[((size_t)b * T + t) * 3 * G + G + (k - 2 * G)] : vx;
+    // ===== R3: dh_tot = d_hz[t].h + dp_pre . W_post_h^T (Wt_post_h [D, G]); GRU gate gradients for the task's 32 units =====
+    for (int task = blk; task < tasks_G; task += nblk) {
+      const int c0 = task * 32;
+      task_gemv(sm, p.Wt_post_h, G, c0, G, D, B, [&](int b, int k) { return __ldcg(p.dp_pre + ((size_t)b * T + t) * D + k); });
+      for (int e = threadIdx.x; e < B * 32; e += kThreads) {
+        const int b = e >> 5, jj = e & 31, j = c0 + jj;
+        if (j < G) {
+          const size_t bt = (size_t)b * T + t;
+          const float d = sm.tile[b][jj] + __ldcg(p.d_hz + bt * W + j);
+          const float* gt = p.gates + bt * 3 * G;
+          const float z = gt[j], r = gt[G + j], c = gt[2 * G + j];
+          const float dz = d * (p.h_in[bt * G + j] - c) * z * (1.f - z);
+          const float dc = d * (1.f - z) * (1.f - c * c);
+          const float dr = dc * p.gh[bt * 3 * G + 2 * G + j] * r * (1.f - r);
+          p.dh_tot[(size_t)b * G + j] = d;
+          float* gxo = p.dgx + bt * 3 * G;
+          float* gho = p.dgh + bt * 3 * G;
+          gxo[j] = dz; gxo[G + j] = dr; gxo[2 * G + j] = dc;
+          gho[j] = dz; gho[G + j] = dr; gho[2 * G + j] = dc * r;
+        }
       }
+      __syncthreads();
+    }
+    grid.sync();
+
+    // ===== R4: dh_in = dh_tot * z + dgh . U^T (Ut [3G, G]);  du = dgx . K^T (Kt [3G, D]) =====
+    {
       const int ntask = tasks_G + tasks_D;
       for (int task = blk; task < ntask; task += nblk) {
-        if (task < tasks_G) {  // dh_in = dh_tot * z + dgh . U^T   (Ut [3G, G])
+        if (task < tasks_G) {
           const int c0 = task * 32;
-          task_gemv(sm, p.Ut, G, c0, G, 3 * G, B, [&](int b, int k) { return dgate(b, k, true); });
+          task_gemv(sm, p.Ut, G, c0, G, 3 * G, B, [&](int b, int k) { return __ldcg(p.dgh + ((size_t)b * T + t) * 3 * G + k); });
           for (int e = threadIdx.x; e < B * 32; e += kThreads) {
             const int b = e >> 5, j = e & 31;
             if (c0 + j < G) {
@@ -165,9 +160,9 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
             }
           }
           __syncthreads();
-        } else {               // du = dgx . K^T   (Kt [3G, D])
+        } else {
           const int c0 = (task - tasks_G) * 32;
-          task_gemv(sm, p.Kt, D, c0, D, 3 * G, B, [&](int b, int k) { return dgate(b, k, false); });
+          task_gemv(sm, p.Kt, D, c0, D, 3 * G, B, [&](int b, int k) { return __ldcg(p.dgx + ((size_t)b * T + t) * 3 * G + k); });
           for (int e = threadIdx.x; e < B * 32; e += kThreads) {
             const int b = e >> 5, j = e & 31;
             if (c0 + j < D) p.du[((size_t)b * T + t) * D + c0 + j] = sm.tile[b][j];
@@ -178,47 +173,52 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
     }
     grid.sync();
 
-    // ================= R5: dx_pre = LN'SiLU'(du);  dz_in = dx_pre . W_pre[:Z]^T  (Wt_pre_z [D, Z]); pass to step t-1 ==========
-    {
-      const float* dy = p.du + (size_t)t * D;
-      const float* xx = p.x_pre + (size_t)t * D;
-      cta_lnbwd_stats(sm, dy, T * D, xx, T * D, p.x_mean + t, p.x_rstd + t, T, p.pre_g, p.pre_b, B, D);
-      for (int e = gtid; e < B * D; e += gthreads) {
-        const int b = e / D, k = e % D;
-        p.dx_pre[((size_t)b * T + t) * D + k] =
-            lnbwd_elem(sm, __ldcg(dy + (size_t)b * T * D + k), __ldcg(xx + (size_t)b * T * D + k), p.pre_g[k], p.pre_b[k], b);
+    // ===== R5a (row owners): dx_pre = LN'SiLU'(du); h part of the recurrent gradient: d_hz[t-1].h += (1 - f_t) dh_in[t] =====
+    for (int b = blk; b < B; b += nblk) {
+      const size_t bt = (size_t)b * T + t;
+      float dy[4], x[4], dx[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = threadIdx.x + kThreads * i;
+        dy[i] = d < D ? __ldcg(p.du + bt * D + d) : 0.f;
+        x[i] = d < D ? p.x_pre[bt * D + d] : 0.f;
+      }
+      row_lnbwd(sm, dy, x, p.x_mean[bt], p.x_rstd[bt], p.pre_g, p.pre_b, D, dx);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = threadIdx.x + kThreads * i;
+        if (d < D) p.dx_pre[bt * D + d] = dx[i];
       }
       if (t > 0) {
-        // h part of the recurrent gradient: d_hz[t-1].h += (1 - f_t) * dh_in[t]
-        for (int e = gtid; e < B * G; e += gthreads) {
-          const int b = e / G, j = e % G;
-          const size_t bt = (size_t)b * T + t;
-          const float keep = 1.f - p.is_first[bt];
+        const float keep = 1.f - p.is_first[bt];
+        for (int j = threadIdx.x; j < G; j += kThreads) {
           float* dst = p.d_hz + (bt - 1) * W + j;
           *dst = __ldcg(dst) + keep * __ldcg(p.dh_in + bt * G + j);
         }
-        for (int task = blk; task < tasks_Z; task += nblk) {
-          const int c0 = task * 32;
-          task_gemv(sm, p.Wt_pre_z, Z, c0, Z, D, B, [&](int b, int k) {
-            return lnbwd_elem(sm, __ldcg(dy + (size_t)b * T * D + k), __ldcg(xx + (size_t)b * T * D + k), p.pre_g[k], p.pre_b[k], b);
-          });
-          for (int e = threadIdx.x; e < B * 32; e += kThreads) {
-            const int b = e >> 5, j = e & 31;
-            if (c0 + j < Z) {
-              const size_t bt = (size_t)b * T + t;
-              float* dst = p.d_hz + (bt - 1) * W + G + c0 + j;
-              *dst = __ldcg(dst) + (1.f - p.is_first[bt]) * sm.tile[b][j];
-            }
+      }
+    }
+    grid.sync();
+
+    // ===== R5: dz_in = dx_pre . W_pre[:Z]^T (Wt_pre_z [D, Z]); pass to step t-1 and run its posterior repr backward =====
+    if (t > 0) {
+      for (int task = blk; task < tasks_Z; task += nblk) {
+        const int c0 = task * 32;
+        task_gemv(sm, p.Wt_pre_z, Z, c0, Z, D, B, [&](int b, int k) { return __ldcg(p.dx_pre + ((size_t)b * T + t) * D + k); });
+        for (int e = threadIdx.x; e < B * 32; e += kThreads) {
+          const int b = e >> 5, j = e & 31;
+          if (c0 + j < Z) {
+            const size_t bt = (size_t)b * T + t;
+            float* dst = p.d_hz + (bt - 1) * W + G + c0 + j;
+            *dst = __ldcg(dst) + (1.f - p.is_first[bt]) * sm.tile[b][j];
           }
-          __syncthreads();
-          // the categoricals of this 32-column block are final for step t-1: run their repr backward now
-          const int cats = 32 / Zk;
-          for (int pr = warp; pr < B * cats; pr += kWarps) {
-            const int b = pr / cats, cat = c0 / Zk + pr % cats;
-            if (cat < Zc) repr_bwd_pair(p, b, t - 1, cat, lane);
-          }
-          __syncthreads();
         }
+        __syncthreads();
+        const int cats = 32 / Zk;
+        for (int pr = warp; pr < B * cats; pr += kWarps) {
+          const int b = pr / cats, cat = c0 / Zk + pr % cats;
+          if (cat < Zc) repr_bwd_pair(p, b, t - 1, cat, lane);
+        }
+        __syncthreads();
       }
     }
     grid.sync();
