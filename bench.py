@@ -40,6 +40,12 @@ WORKLOADS = {
 GFLOP_PER_UPDATE = {"c1": 150.0, "c2": 235.0, "c3": 827.0, "c4": 2319.0, "L": 3506.0, "c5": 8756.0}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel from the committed ncu --set full
+# capture (profiles/), keyed by (M, K, N, mode); None when no capture exists for the shape
+TRAFFIC_BYTES = {(16384, 1280, 256, 1): 84589568 + 3871232,   # profiles/r01_gemm_tc_ws_ncu.txt
+                 (16384, 1280, 256, 0): None}
+
+
 def make_cfg(wid, B=16, T=64, H=15):
     from dreamer_v3_b200.spec import EngineConfig
     kw = {k: v for k, v in WORKLOADS[wid].items() if k not in ("name", "size")}
@@ -300,6 +306,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.mode == 0 else "bf16", "data": "synthetic",
+        "precision_note": ("fp32 everywhere" if args.mode == 0 else "bf16 operands / fp32 accumulate on tcgen05 for contractions with >= 128 rows; fp32 masters, fp32 B=16 observe scan, losses and optimizer"),
         "config": {"workload": w["name"], "id": wid, "B_per_gpu": B, "T": T, "H": H, "global_batch": B * world,
                    "parallelism": f"dp{world}" if world > 1 else "single",
                    "l2": "256 MiB buffer written between timed steps (L2 flush)",
@@ -330,21 +337,24 @@ def measure_roofline(e, cfg, pk, args):
     A = torch.randn(R, K, device="cuda")
     Bm = torch.randn(K, Nn, device="cuda")
     C = torch.empty(R, Nn, device="cuda")
+    # mode 1: exactly the variant the engine runs for a weight operand (bf16 K-major shadow, built outside the timing)
+    run = ops.gemm_weight_shadow(A, Bm, C_=C) if args.mode == 1 else (lambda: ops.gemm(A, Bm, C_=C, mode=0))
     for _ in range(3):
-        ops.gemm(A, Bm, C_=C, mode=args.mode)
+        run()
     torch.cuda.synchronize()
     reps = 20
     s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(reps):
-        ops.gemm(A, Bm, C_=C, mode=args.mode)
+        run()
     t.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(t) / reps
     flops = 2.0 * R * K * Nn
     ach = flops / (ms * 1e-3) / 1e12
     return {"bound": "tensor", "kernel": f"gemm [{R}x{K}]x[{K}x{Nn}] ({'fp32 SIMT' if args.mode == 0 else 'bf16 tcgen05'})",
-            "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"], "traffic": None,
+            "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"], "traffic": TRAFFIC_BYTES.get((R, K, Nn, args.mode)),
+            "algorithmic_bytes": 4.0 * R * K + (2.0 if args.mode == 1 else 4.0) * K * Nn + 4.0 * R * Nn,
             "peak_source": pk["src"] + " (burst, kernel timed alone)", "ms_per_launch": ms}
 
 
@@ -381,7 +391,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
-    ap.add_argument("--mode", type=int, default=0, help="0 = fp32 SIMT, 1 = bf16 tcgen05 for large contractions")
+    ap.add_argument("--mode", type=int, default=1, help="1 = bf16 tcgen05 tensor cores for contractions with >= 128 rows (fp32 accumulate, fp32 scan / elementwise); 0 = fp32 everywhere")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ref-rows", type=int, default=None)

@@ -197,6 +197,14 @@ int dv3_op_gemm(const float* A, int lda, int ta, const float* B, int ldb, int tb
   dv3::gemm_dispatch(S(stream), g, mode);
   return op_done();
 }
+int dv3_op_gemm_shadow(const float* A, int lda, int ta, const void* Bh, int ldbh, float* C, int ldc, int M, int N, int K,
+                       const float* bias, float beta, void* stream) {
+  dv3::GemmArgs g{A, lda, ta, nullptr, 0, 1, C, ldc, M, N, K, bias, beta};
+  g.Bh = Bh; g.ldbh = ldbh;
+  if ((ldbh % 8) != 0 || ((uintptr_t)Bh % 16) != 0) return -1;
+  dv3::gemm_tc(S(stream), g);
+  return op_done();
+}
 int dv3_op_ln_silu(const float* x, const float* gamma, const float* beta, float* y, int64_t rows, int D, void* stream) {
   if (D > 1024) return -1;
   dv3::ln_silu_fwd(S(stream), x, D, gamma, beta, y, D, nullptr, nullptr, 1, rows, D);

@@ -21,7 +21,9 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int kStages = 2;
+constexpr int kStages = 2;           // fp32-B variant
+// bf16-shadow variant: ring depth = register sets = smem stages; narrow tiles can afford a deeper ring
+__host__ __device__ constexpr int shadow_depth(int bn) { return bn <= 64 ? 4 : (bn <= 128 ? 3 : 2); }
 constexpr int kTcThreads = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -183,19 +185,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
-template <int BN>
+template <int BN, int STAGES>
 struct TcSmem {
-  unsigned char a[kStages][BM * 128];   // 16 KB per stage
-  unsigned char b[kStages][BN * 128];
-  uint64_t bar[kStages];
+  unsigned char a[STAGES][BM * 128];   // 16 KB per stage
+  unsigned char b[STAGES][BN * 128];
+  uint64_t bar[STAGES];
   uint32_t tmem_base;
 };
 
 template <int BN, bool TA, bool TB, bool BH>
-__global__ void __launch_bounds__(kTcThreads, (BN <= 128) ? 2 : 1) gemm_tc_kernel(GemmArgs g, int k_per_split, int vecA, int vecB, int use_atomic) {
+__global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(GemmArgs g, int k_per_split, int vecA, int vecB, int use_atomic) {
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
-  TcSmem<BN>& sm = *reinterpret_cast<TcSmem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int STAGES = BH ? shadow_depth(BN) : kStages;
+  using SmemT = TcSmem<BN, STAGES>;
+  SmemT& sm = *reinterpret_cast<SmemT*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int kbeg = blockIdx.z * k_per_split;
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(kTcThreads, (BN <= 128) ? 2 : 1) gemm_tc_kerne
   const int nkb = (kend - kbeg + BK - 1) / BK;
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&sm.bar[s], 1);
+    for (int s = 0; s < STAGES; ++s) mbar_init(&sm.bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {  // one warp allocates BN fp32 accumulator columns of tensor memory
@@ -241,29 +245,31 @@ __global__ void __launch_bounds__(kTcThreads, (BN <= 128) ? 2 : 1) gemm_tc_kerne
     // B comes from the bf16 K-major weight shadow: half the bytes and no conversion, which frees enough registers to
     // keep TWO k-blocks of global loads in flight per thread
     const __nv_bfloat16* Bh = reinterpret_cast<const __nv_bfloat16*>(g.Bh);
-    Fill<BM, TA> fa[2];
-    FillBf16<BN> fb[2];
-    fa[0].load(g.A, g.lda, m0, g.M, kbeg, kend, vecA);
-    fb[0].load(Bh, g.ldbh, n0, g.N, kbeg, kend);
-    if (nkb > 1) {
-      fa[1].load(g.A, g.lda, m0, g.M, kbeg + BK, kend, vecA);
-      fb[1].load(Bh, g.ldbh, n0, g.N, kbeg + BK, kend);
+    constexpr int DEPTH = STAGES;
+    Fill<BM, TA> fa[DEPTH];
+    FillBf16<BN> fb[DEPTH];
+#pragma unroll
+    for (int u = 0; u < DEPTH; ++u) {
+      if (u < nkb) {
+        fa[u].load(g.A, g.lda, m0, g.M, kbeg + u * BK, kend, vecA);
+        fb[u].load(Bh, g.ldbh, n0, g.N, kbeg + u * BK, kend);
+      }
     }
 #pragma unroll 1
-    for (int kb2 = 0; kb2 < nkb; kb2 += 2) {
+    for (int kb0 = 0; kb0 < nkb; kb0 += DEPTH) {
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int kb = kb2 + u;
+      for (int u = 0; u < DEPTH; ++u) {
+        const int kb = kb0 + u;
         if (kb < nkb) {
-          const int s = u;  // kStages == 2: stage index == register set index == kb & 1
-          if (kb >= kStages) mbar_wait(&sm.bar[s], (uint32_t)(((kb / kStages) - 1) & 1));
+          const int s = u;  // stage index == register set index == kb % DEPTH
+          if (kb >= DEPTH) mbar_wait(&sm.bar[s], (uint32_t)(((kb / DEPTH) - 1) & 1));
           fa[u].store(smem_u32(sm.a[s]), vecA);
           fb[u].store(smem_u32(sm.b[s]));
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncthreads();
           issue_mma(kb, s);
-          if (kb + 2 < nkb) {
-            const int k0 = kbeg + (kb + 2) * BK;
+          if (kb + DEPTH < nkb) {
+            const int k0 = kbeg + (kb + DEPTH) * BK;
             fa[u].load(g.A, g.lda, m0, g.M, k0, kend, vecA);
             fb[u].load(Bh, g.ldbh, n0, g.N, k0, kend);
           }
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(kTcThreads, (BN <= 128) ? 2 : 1) gemm_tc_kerne
   // wait for the last commit (it covers all earlier MMAs)
   {
     const int last = nkb - 1;
-    mbar_wait(&sm.bar[last % kStages], (uint32_t)((last / kStages) & 1));
+    mbar_wait(&sm.bar[last % STAGES], (uint32_t)((last / STAGES) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
 
@@ -343,6 +349,199 @@ __global__ void __launch_bounds__(kTcThreads, (BN <= 128) ? 2 : 1) gemm_tc_kerne
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN));
 }
 
+
+// =====================================================================================================================
+// Warp-specialised variant for a bf16-shadow B operand (weights): two producer groups of 4 warps alternate k-blocks
+// (global loads -> convert -> swizzled st.shared -> proxy fence -> mbarrier arrive), a ninth warp only issues
+// tcgen05.mma and commits completions back to the producers ("stage empty"). There is no CTA-wide barrier in the
+// main loop, so a group's fence only waits for its own loads while the other group's loads stay in flight.
+// =====================================================================================================================
+constexpr int kWsStages = 4;
+constexpr int kWsGroup = 128;                 // threads per producer group
+constexpr int kWsThreads = 2 * kWsGroup + 32;  // + the MMA warp
+
+template <int BN>
+struct WsSmem {
+  unsigned char a[kWsStages][BM * 128];
+  unsigned char b[kWsStages][BN * 128];
+  uint64_t full[kWsStages], empty[kWsStages], done;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, bool TA>
+__global__ void __launch_bounds__(kWsThreads, 1) gemm_tc_ws_kernel(GemmArgs g, int k_per_split, int vecA, int use_atomic) {
+  extern __shared__ unsigned char smem_raw[];
+  using SmemT = WsSmem<BN>;
+  SmemT& sm = *reinterpret_cast<SmemT*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(g.K, kbeg + k_per_split);
+  const int nkb = (kend - kbeg + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < kWsStages; ++s) { mbar_init(&sm.full[s], kWsGroup); mbar_init(&sm.empty[s], 1); }
+    mbar_init(&sm.done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 8) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kWsStages;
+        mbar_wait(&sm.full[s], (uint32_t)((kb / kWsStages) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = smem_u32(sm.a[s]), b_addr = smem_u32(sm.b[s]);
+#pragma unroll
+        for (int j = 0; j < BK / 16; ++j) {
+          const uint64_t da = make_smem_desc(a_addr + j * 32);
+          const uint64_t db = make_smem_desc(b_addr + j * 32);
+          const uint32_t accum = (kb > 0 || j > 0) ? 1u : 0u;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t"
+              "setp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+              ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+              : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sm.empty[s])) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sm.done)) : "memory");
+    }
+  } else {
+    // ---------------- producers: group 0 takes even k-blocks, group 1 odd ones ----------------
+    const int group = warp >> 2, t = tid & (kWsGroup - 1);
+    const __nv_bfloat16* Bh = reinterpret_cast<const __nv_bfloat16*>(g.Bh);
+    constexpr int kTasksA = BM * 8 / kWsGroup;   // 8
+    constexpr int kTasksB = BN * 8 / kWsGroup;   // 4 / 8 / 16
+    for (int kb = group; kb < nkb; kb += 2) {
+      const int s = kb % kWsStages, use = kb / kWsStages;
+      const int k0 = kbeg + kb * BK;
+      // A: fp32 -> registers
+      float va[kTasksA][8];
+#pragma unroll
+      for (int i = 0; i < kTasksA; ++i) {
+        const int task = t + i * kWsGroup;
+        if (!TA) {
+          const int r = task >> 3, kc = task & 7;
+          const int gr = m0 + r, gk = k0 + kc * 8;
+          const float* p = g.A + (size_t)gr * g.lda + gk;
+          if (gr < g.M && vecA && gk + 7 < kend) {
+            const float4 x = *reinterpret_cast<const float4*>(p);
+            const float4 y = *reinterpret_cast<const float4*>(p + 4);
+            va[i][0] = x.x; va[i][1] = x.y; va[i][2] = x.z; va[i][3] = x.w; va[i][4] = y.x; va[i][5] = y.y; va[i][6] = y.z; va[i][7] = y.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) va[i][j] = (gr < g.M && gk + j < kend) ? p[j] : 0.f;
+          }
+        } else {
+          const int r = task % BM, kc = task / BM;
+          const int gr = m0 + r, gk = k0 + kc * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) va[i][j] = (gr < g.M && gk + j < kend) ? g.A[(size_t)(gk + j) * g.lda + gr] : 0.f;
+        }
+      }
+      // B: bf16 shadow -> registers
+      uint4 vb[kTasksB];
+#pragma unroll
+      for (int i = 0; i < kTasksB; ++i) {
+        const int task = t + i * kWsGroup;
+        const int r = task >> 3, kc = task & 7;
+        const int gr = n0 + r, gk = k0 + kc * 8;
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        if (gr < g.N && gk < kend) {
+          const __nv_bfloat16* p = Bh + (size_t)gr * g.ldbh + gk;
+          if (gk + 7 < kend) x = *reinterpret_cast<const uint4*>(p);
+          else {
+            unsigned short h[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = (gk + j < kend) ? reinterpret_cast<const unsigned short*>(p)[j] : (unsigned short)0;
+            x.x = h[0] | ((uint32_t)h[1] << 16); x.y = h[2] | ((uint32_t)h[3] << 16);
+            x.z = h[4] | ((uint32_t)h[5] << 16); x.w = h[6] | ((uint32_t)h[7] << 16);
+          }
+        }
+        vb[i] = x;
+      }
+      if (use > 0) mbar_wait(&sm.empty[s], (uint32_t)((use - 1) & 1));   // the MMAs that read this stage have completed
+      const uint32_t ta_ = smem_u32(sm.a[s]), tb_ = smem_u32(sm.b[s]);
+#pragma unroll
+      for (int i = 0; i < kTasksA; ++i) {
+        const int task = t + i * kWsGroup;
+        const int r = TA ? task % BM : task >> 3, kc = TA ? task / BM : task & 7;
+        const uint32_t x = pack_bf16(va[i][0], va[i][1]), y = pack_bf16(va[i][2], va[i][3]);
+        const uint32_t z = pack_bf16(va[i][4], va[i][5]), w = pack_bf16(va[i][6], va[i][7]);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ta_ + sw128_chunk_off(r, kc)), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+      }
+#pragma unroll
+      for (int i = 0; i < kTasksB; ++i) {
+        const int task = t + i * kWsGroup;
+        const int r = task >> 3, kc = task & 7;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tb_ + sw128_chunk_off(r, kc)), "r"(vb[i].x), "r"(vb[i].y), "r"(vb[i].z), "r"(vb[i].w) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&sm.full[s]);
+    }
+    // ---------------- epilogue (the 8 producer warps) ----------------
+    mbar_wait(&sm.done, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    const int cbeg = (warp >> 2) * (BN / 2), cend = cbeg + BN / 2;
+    const uint32_t epi = smem_u32(sm.a[0]) + warp * 4096;
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(epi + (uint32_t)((lane * 32 + (j ^ lane)) * 4)), "r"(r[j]) : "memory");
+      __syncwarp();
+      const int gn = n0 + c0 + lane;
+      const float bv = (g.bias != nullptr && blockIdx.z == 0 && gn < g.N) ? g.bias[gn] : 0.f;
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+        const int gm = m0 + q * 32 + i;
+        if (gm < g.M && gn < g.N) {
+          float v;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(epi + (uint32_t)((i * 32 + (lane ^ i)) * 4)) : "memory");
+          v += bv;
+          float* dst = g.C + (size_t)gm * g.ldc + gn;
+          if (use_atomic) atomicAdd(dst, v);
+          else if (g.beta != 0.f) *dst += v;
+          else *dst = v;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN));
+}
+
 template <int BN>
 void launch_tc(cudaStream_t s, const GemmArgs& g) {
   const int gx = cdiv(g.N, BN), gy = cdiv(g.M, BM);
@@ -359,7 +558,8 @@ void launch_tc(cudaStream_t s, const GemmArgs& g) {
   if (use_atomic && g.beta == 0.f) zero_2d(s, g.C, g.M, g.N, g.ldc);
   const int vA = ((uintptr_t)g.A % 16 == 0) && (g.lda % 4 == 0);
   const int vB = ((uintptr_t)g.B % 16 == 0) && (g.ldb % 4 == 0);
-  const size_t smem = sizeof(TcSmem<BN>) + 1024;
+  const bool bh = g.Bh != nullptr && (g.ldbh % 8 == 0) && ((uintptr_t)g.Bh % 16 == 0);
+  const size_t smem = (bh ? sizeof(TcSmem<BN, shadow_depth(BN)>) : sizeof(TcSmem<BN, kStages>)) + 1024;
   dim3 grid(gx, gy, splits), block(kTcThreads);
 #define DV3_TC_LAUNCH(TA_, TB_)                                                                                   \
   do {                                                                                                            \
@@ -370,7 +570,6 @@ void launch_tc(cudaStream_t s, const GemmArgs& g) {
     }                                                                                                             \
     gemm_tc_kernel<BN, TA_, TB_, BH_><<<grid, block, smem, s>>>(g, kps, vA, vB, use_atomic);                      \
   } while (0)
-  const bool bh = g.Bh != nullptr && (g.ldbh % 8 == 0) && ((uintptr_t)g.Bh % 16 == 0) && (kps % 8 == 0);
 #define BH_ false
   if (!bh) {
     if (!g.ta && !g.tb) DV3_TC_LAUNCH(false, false);
@@ -381,8 +580,16 @@ void launch_tc(cudaStream_t s, const GemmArgs& g) {
 #undef BH_
 #define BH_ true
   if (bh) {
-    if (!g.ta) DV3_TC_LAUNCH(false, true);
-    else DV3_TC_LAUNCH(true, true);
+    const size_t smem_ws = sizeof(WsSmem<BN>) + 1024;
+    if (!g.ta) {
+      static bool cfgd = false;
+      if (!cfgd) { cudaFuncSetAttribute(gemm_tc_ws_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws); cfgd = true; }
+      gemm_tc_ws_kernel<BN, false><<<grid, dim3(kWsThreads), smem_ws, s>>>(g, kps, vA, use_atomic);
+    } else {
+      static bool cfgd = false;
+      if (!cfgd) { cudaFuncSetAttribute(gemm_tc_ws_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws); cfgd = true; }
+      gemm_tc_ws_kernel<BN, true><<<grid, dim3(kWsThreads), smem_ws, s>>>(g, kps, vA, use_atomic);
+    }
   }
 #undef BH_
 #undef DV3_TC_LAUNCH

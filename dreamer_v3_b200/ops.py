@@ -93,6 +93,25 @@ def gemm(A, B, ta=False, tb=False, bias=None, C_=None, beta=0.0, mode=0):
     return C_
 
 
+def gemm_weight_shadow(A, W, ta=False, bias=None, C_=None, beta=0.0):
+    """C = op(A) W with W [K, N] given in fp32; its bf16 K-major shadow (what the engine keeps per weight matrix and
+    refreshes once per optimizer step) is built here, outside any timing loop the caller runs around `run`."""
+    assert A.dim() == 2 and W.dim() == 2 and A.stride(1) == 1
+    Wh = W.t().contiguous().to(torch.bfloat16)  # [N, K]
+    M, K = (A.shape[1], A.shape[0]) if ta else (A.shape[0], A.shape[1])
+    N = W.shape[1]
+    assert W.shape[0] == K and K % 8 == 0
+    if C_ is None:
+        C_ = torch.zeros((M, N), dtype=torch.float32, device=A.device)
+
+    def run():
+        _ok(_lib.load().dv3_op_gemm_shadow(_p(A), A.stride(0), int(ta), _p(Wh), K, _p(C_), C_.stride(0), M, N, K,
+                                           _p(bias), beta, _s()), "dv3_op_gemm_shadow")
+        return C_
+    run.keepalive = Wh
+    return run
+
+
 def ln_silu(x, gamma, beta):
     x = _f32(x)
     y = torch.empty_like(x)

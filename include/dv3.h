@@ -151,6 +151,9 @@ int dv3_op_value_targets(const float* r, const float* c, const float* v, int H, 
 int dv3_op_percentiles(const float* x, int64_t n, float* p5_p95, void* stream);        /* tfp.stats.percentile nearest */
 int dv3_op_gemm(const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C, int ldc,
                 int M, int N, int K, const float* bias, float beta, int mode, void* stream);
+/* tensor-core GEMM with a pre-converted bf16 K-major B operand (Bh[n*ldbh + k]), as the engine uses for weights */
+int dv3_op_gemm_shadow(const float* A, int lda, int ta, const void* Bh, int ldbh, float* C, int ldc, int M, int N, int K,
+                       const float* bias, float beta, void* stream);
 int dv3_op_ln_silu(const float* x, const float* gamma, const float* beta, float* y, int64_t rows, int D, void* stream);
 
 #ifdef __cplusplus

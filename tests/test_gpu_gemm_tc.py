@@ -53,3 +53,23 @@ def test_gemm_tc_close_to_fp32():
     c_32 = ops.gemm(A, B, mode=0)
     err = float((c_tc - c_32).abs().max())
     assert err < 3 * 2 ** -8 * np.sqrt(1280) , err
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1024, 768, 256), (1000, 255, 264), (16384, 256, 1280), (130, 24, 72),
+                                   (1024, 1024, 256), (4096, 512, 48), (300, 128, 1096)])
+def test_gemm_tc_weight_shadow_variant(M, N, K):
+    """Warp-specialised kernel with the bf16 K-major weight shadow (what the engine uses for every weight operand)."""
+    from dreamer_v3_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    for ta in (False, True):
+        A = torch.randn((K, M) if ta else (M, K), generator=g)
+        W = torch.randn(K, N, generator=g)
+        bias = torch.randn(N, generator=g)
+        C0 = torch.randn(M, N, generator=g)
+        Ar = A.bfloat16().double()
+        want = (Ar.T if ta else Ar) @ W.bfloat16().double()
+        tol = 2e-5 * np.sqrt(K) * 8
+        got = ops.gemm_weight_shadow(A.cuda(), W.cuda(), ta=ta, bias=bias.cuda())().cpu().double()
+        assert float((got - (want + bias.double())).abs().max()) <= tol, (M, N, K, ta)
+        got = ops.gemm_weight_shadow(A.cuda(), W.cuda(), ta=ta, C_=C0.cuda(), beta=1.0)().cpu().double()
+        assert float((got - (want + C0.double())).abs().max()) <= tol, (M, N, K, ta, "beta")
