@@ -133,6 +133,10 @@ int dv3_train_world_model_step(dv3_engine* h, const dv3_hparams* hp, uint64_t no
   }
   return rc ? rc : check_async(h->e);
 }
+int dv3_forward_inference(dv3_engine* h, int rows, uint64_t noise_seed, void* stream) {
+  int rc = h->e.forward_inference(rows, noise_seed, S(stream));
+  return rc ? rc : check_async(h->e);
+}
 int dv3_dream_forward(dv3_engine* h, float gamma, int start_from_observe, void* stream) {
   int rc = h->e.dream_forward(gamma, start_from_observe, S(stream));
   return rc ? rc : check_async(h->e);

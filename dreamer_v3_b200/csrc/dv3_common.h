@@ -91,6 +91,8 @@ void scan_mask_grads(cudaStream_t s, const float* is_first, int ldf, const float
 void colsum_acc(cudaStream_t s, const float* x, int ld, long long rows, int cols, float* out);
 void scan_prepare(cudaStream_t s, const float* actions, const float* is_first, float* a_in, float* wf, int B, int T, int A);
 void tanh_bwd_acc(cudaStream_t s, const float* dh0, const float* h0, float* dinit, int n);
+void infer_mask(cudaStream_t s, const float* f, const float* ph, const float* pz, const float* pa, const float* h0, const float* z0,
+                float* h, float* z, float* a, int rows, int G, int Z, int A);
 
 // ---- conv helpers (dv3_conv.cu): 4x4 stride-2 "same" ------------------------------------------------
 // cols[(n,oy,ox), (ky,kx,c)] = img[n, 2oy-1+ky, 2ox-1+kx, c] (0 outside); img NHWC [n,H,W,C], out H/2 x W/2

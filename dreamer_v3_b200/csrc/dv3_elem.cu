@@ -325,6 +325,21 @@ __global__ void scan_prepare_kernel(const float* __restrict__ actions, const flo
     else wf[bt] = (t == 0) ? 1.f : f;
   }
 }
+// acting-step masking (world_model.py:160-172): h/z fall back to the learned initial state, actions to zero
+__global__ void infer_mask_kernel(const float* __restrict__ f, const float* __restrict__ ph, const float* __restrict__ pz,
+                                  const float* __restrict__ pa, const float* __restrict__ h0, const float* __restrict__ z0,
+                                  float* __restrict__ h, float* __restrict__ z, float* __restrict__ a, int rows, int G, int Z, int A) {
+  const int W = G + Z + A;
+  const long long n = (long long)rows * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / W);
+    int j = (int)(i % W);
+    const float m = f[b];
+    if (j < G) h[(size_t)b * G + j] = ph[(size_t)b * G + j] * (1.f - m) + h0[j] * m;
+    else if (j < G + Z) { j -= G; z[(size_t)b * Z + j] = pz[(size_t)b * Z + j] * (1.f - m) + z0[j] * m; }
+    else { j -= G + Z; a[(size_t)b * A + j] = pa[(size_t)b * A + j] * (1.f - m); }
+  }
+}
 // dinit[j] += dh0[j] * (1 - h0[j]^2)
 __global__ void tanh_bwd_acc_kernel(const float* __restrict__ dh0, const float* __restrict__ h0, float* __restrict__ dinit, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dinit[i] += dh0[i] * (1.f - h0[i] * h0[i]);
@@ -440,6 +455,10 @@ void colsum_acc(cudaStream_t s, const float* x, int ld, long long rows, int cols
 void scan_prepare(cudaStream_t s, const float* actions, const float* is_first, float* a_in, float* wf, int B, int T, int A) {
   long long n = (long long)B * T * (A + 1);
   scan_prepare_kernel<<<grid_for(n), kThreads, 0, s>>>(actions, is_first, a_in, wf, B, T, A); count_launch();
+}
+void infer_mask(cudaStream_t s, const float* f, const float* ph, const float* pz, const float* pa, const float* h0, const float* z0,
+                float* h, float* z, float* a, int rows, int G, int Z, int A) {
+  infer_mask_kernel<<<grid_for((long long)rows * (G + Z + A)), kThreads, 0, s>>>(f, ph, pz, pa, h0, z0, h, z, a, rows, G, Z, A); count_launch();
 }
 void tanh_bwd_acc(cudaStream_t s, const float* dh0, const float* h0, float* dinit, int n) {
   tanh_bwd_acc_kernel<<<grid_for(n), kThreads, 0, s>>>(dh0, h0, dinit, n); count_launch();

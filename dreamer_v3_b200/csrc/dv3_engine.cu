@@ -385,6 +385,26 @@ void Engine::layout() {
   L_actor_HB = af("ac.ACTOR_L_total_H_B", {H, Nl}); logp_HB = af("ac.ACTOR_logp_actions_dreamed_H_B", {H, Nl});
   scaled_HB = af("ac.ACTOR_scaled_value_targets_H_B", {H, Nl}); ent_HB = af("ac.ACTOR_action_entropy_H_B", {H, Nl});
   L_reinf_HB = af("ac.ACTOR_L_neglogp_reinforce_term_H_B", {H, Nl}); L_ent_HB = af("ac.ACTOR_L_neg_entropy_term_H_B", {H, Nl});
+  // ---- acting step ----
+  if (image) inf_obs = af("inf.obs", {B, cfg.img_hw, cfg.img_hw, cfg.img_c}, 4);
+  else inf_obs = af("inf.obs", {B, cfg.obs_dim}, 4);
+  inf_is_first = af("inf.is_first", {B}, 4);
+  inf_prev_h = af("inf.prev_h", {B, G}, 4); inf_prev_z = af("inf.prev_z", {B, Z}, 4); inf_prev_a = af("inf.prev_a", {B, A}, 4);
+  inf_u_z = af("inf.u_z", {B, Zc}, 4);
+  if (discrete) inf_act_noise = af("inf.act_noise", {B}, 4); else inf_act_noise = af("inf.act_noise", {B, A}, 4);
+  inf_h_in = af("", {B, G}); inf_z_in = af("", {B, Z}); inf_a_in = af("", {B, A}); inf_x_pre = af("", {B, D}); inf_u = af("", {B, D});
+  inf_gx = af("", {B, 3 * G}); inf_gh = af("", {B, 3 * G});
+  inf_hz = af("inf.hz", {B, G + Z});
+  inf_obs_sym = af("", {B, OF});
+  if (!image) inf_enc_act = alloc_mlp_act("inf.enc", B, L);
+  inf_enc = af("", {B, E});
+  inf_p_pre = af("", {B, D}); inf_p_act = af("", {B, D}); inf_logits = af("", {B, Z});
+  inf_probs = af("inf.z_probs", {B, Zc, Zk});
+  inf_z_idx = ai("inf.z_indices", {B, Zc});
+  inf_a = af("inf.a", {B, A}); inf_a_idx = ai("inf.action_indices", {B});
+  inf_actor_act = alloc_mlp_act("inf.actor", B, L);
+  if (!discrete) inf_std_act = alloc_mlp_act("inf.actor_std", B, L);
+  inf_actor_out = af("inf.actor_out", {B, A}); inf_actor_probs = af("inf.actor_probs", {B, A}); inf_actor_s = af("inf.actor_std_out", {B, A});
   sN_Z = af("", {Nl, Z}); sN_3G0 = af("", {Nl, 3 * G}); sN_3G1 = af("", {Nl, 3 * G}); sN_A = af("", {Nl, A});
   noise_step = (unsigned long long*)alloc_bytes("noise_step", 8, 1, {2}, 6, -1);
 }

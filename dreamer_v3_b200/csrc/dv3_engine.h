@@ -125,6 +125,15 @@ struct Engine {
   void build_shadows();
   void refresh_shadows(cudaStream_t s);
 
+  // ---- acting step (forward_inference) ----
+  float *inf_obs, *inf_is_first, *inf_prev_h, *inf_prev_z, *inf_prev_a, *inf_u_z, *inf_act_noise;
+  float *inf_h_in, *inf_z_in, *inf_a_in, *inf_x_pre, *inf_u, *inf_gx, *inf_gh, *inf_hz, *inf_obs_sym, *inf_enc, *inf_p_pre, *inf_p_act,
+      *inf_logits, *inf_probs, *inf_a, *inf_actor_out, *inf_actor_probs, *inf_actor_s;
+  int32_t *inf_z_idx, *inf_a_idx;
+  MlpAct inf_enc_act, inf_actor_act, inf_std_act;
+  unsigned long long inf_calls = 0;
+  int forward_inference(int rows, uint64_t noise_seed, cudaStream_t s);
+
   // ---- graph ----
   struct GraphSlot { cudaGraphExec_t exec = nullptr; long long launches = 0; dv3_hparams hp{}; uint64_t seed = 0; };
   GraphSlot slot_wm, slot_ac;

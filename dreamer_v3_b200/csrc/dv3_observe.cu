@@ -183,6 +183,68 @@ int Engine::wm_loss_backward(cudaStream_t s) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------- acting step
+// DreamerModel.forward_inference (dreamer_model.py:113-128): one RSSM step for `rows` parallel envs + actor sample.
+int Engine::forward_inference(int rows, uint64_t noise_seed, cudaStream_t s) {
+  if (rows < 1 || rows > B) return fail("forward_inference: rows must be in [1, B]");
+  cur = s;
+  const LnLayer& Wp = post_mlp.layers[0];
+  const LnLayer& Wx = pre_mlp.layers[0];
+  const int W = G + Z;
+  if (noise_seed != 0) {
+    ++inf_calls;
+    philox_fill(s, inf_u_z, (long long)rows * Zc, noise_seed, 0x1000 + inf_calls * 2, nullptr, 0);
+    philox_fill(s, inf_act_noise, discrete ? rows : (long long)rows * A, noise_seed, 0x1001 + inf_calls * 2, nullptr, discrete ? 0 : 1);
+  }
+  refresh_shadows(s);
+  initial_state(s);
+  // mask previous states with the learned initial state where is_first (world_model.py:160-172); actions are zeroed
+  infer_mask(s, inf_is_first, inf_prev_h, inf_prev_z, inf_prev_a, h0, z0, inf_h_in, inf_z_in, inf_a_in, rows, G, Z, A);
+  // sequence model
+  mm(inf_z_in, Z, false, Wx.w, D, false, inf_x_pre, D, rows, D, Z);
+  mm(inf_a_in, A, false, Wx.w + (size_t)Z * D, D, false, inf_x_pre, D, rows, D, A, nullptr, 1.f);
+  ln_silu_fwd(s, inf_x_pre, D, Wx.g, Wx.b, inf_u, D, nullptr, nullptr, 1, rows, D);
+  mm(inf_u, D, false, gru_K, 3 * G, false, inf_gx, 3 * G, rows, 3 * G, D, gru_b);
+  mm(inf_h_in, G, false, gru_U, 3 * G, false, inf_gh, 3 * G, rows, 3 * G, G, gru_b + 3 * G);
+  gru_fwd(s, inf_gx, 3 * G, inf_gh, 3 * G, inf_h_in, G, inf_hz, W, rows, G);
+  // posterior z from the observation (compute_posterior_z, world_model.py:329-342)
+  const float* x = inf_obs;
+  if (cfg.symlog_obs) { symlog_fwd(s, inf_obs, inf_obs_sym, (long long)rows * OF); x = inf_obs_sym; }
+  const float* enc = nullptr;
+  if (!image) {
+    mlp_fwd(enc_mlp, inf_enc_act, x, OF, rows);
+    enc = inf_enc_act.act.back();
+  } else {
+    const float* cur_in = x;
+    for (int l = 0; l < 4; ++l) {  // same conv stack as the training encoder, on its (larger) activation buffers
+      ConvLayer& c = enc_conv[l];
+      const int ho = c.hin / 2;
+      const long long r = (long long)rows * ho * ho;
+      im2col_k4s2(s, cur_in, cols, rows, c.hin, c.hin, c.cin);
+      mm(cols, 16 * c.cin, false, c.w, c.cout, false, c.pre, c.cout, (int)r, c.cout, 16 * c.cin);
+      ln_silu_fwd(s, c.pre, c.cout, c.g, c.b, c.act, c.cout, c.mean, c.rstd, 1, r, c.cout);
+      cur_in = c.act;
+    }
+    enc = enc_conv[3].act;
+  }
+  mm(enc, E, false, Wp.w, D, false, inf_p_pre, D, rows, D, E);
+  mm(inf_hz, W, false, Wp.w + (size_t)E * D, D, false, inf_p_pre, D, rows, D, G, nullptr, 1.f);
+  ln_silu_fwd(s, inf_p_pre, D, Wp.g, Wp.b, inf_p_act, D, nullptr, nullptr, 1, rows, D);
+  mm(inf_p_act, D, false, post_repr.w, Z, false, inf_logits, Z, rows, Z, D, post_repr.bias);
+  repr_fwd(s, inf_logits, Z, inf_probs, Z, inf_u_z, Zc, inf_z_idx, Zc, inf_hz + G, W, rows, Zc, Zk, 1);
+  // actor (actor_network.py:63-118)
+  mlp_fwd(actor_mlp, inf_actor_act, inf_hz, W, rows);
+  mm(inf_actor_act.act.back(), D, false, actor_out.w, A, false, inf_actor_out, A, rows, A, D, actor_out.bias);
+  if (discrete) {
+    disc_actor_fwd(s, inf_actor_out, inf_act_noise, inf_actor_probs, inf_a_idx, inf_a, A, rows, A);
+  } else {
+    mlp_fwd(actor_std_mlp, inf_std_act, inf_hz, W, rows);
+    mm(inf_std_act.act.back(), D, false, actor_std_out.w, A, false, inf_actor_s, A, rows, A, D, actor_std_out.bias);
+    box_actor_fwd(s, inf_actor_out, inf_actor_s, inf_act_noise, inf_a, A, rows, A);
+  }
+  return 0;
+}
+
 int Engine::train_wm(const dv3_hparams* hp, cudaStream_t s) {
   int rc = observe_forward(s);
   if (rc) return rc;

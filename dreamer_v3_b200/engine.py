@@ -166,6 +166,9 @@ class Engine:
         self._check(self.lib.dv3_optimizer_step(self.h, GROUP_IDS[group], clip, lr, eps, ema_decay, self._stream()),
                     "dv3_optimizer_step")
 
+    def forward_inference(self, rows, noise_seed=0):
+        self._check(self.lib.dv3_forward_inference(self.h, int(rows), int(noise_seed), self._stream()), "dv3_forward_inference")
+
     def dream_forward(self, gamma=None, start_from_observe=True):
         g = self.hp.gamma if gamma is None else float(gamma)
         self._check(self.lib.dv3_dream_forward(self.h, g, int(start_from_observe), self._stream()), "dv3_dream_forward")

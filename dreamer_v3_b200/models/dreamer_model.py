@@ -59,7 +59,13 @@ class DreamerModel:
         return s
 
     def forward_inference(self, previous_states, observations, is_first, training=None):
-        raise NotImplementedError("single-step acting is a 'next' row (SURVEY.md 8f-1), not on the training hot path")
+        """dreamer_model.py:113-128 (called per env step by env_runner_v2.py:274-282): world-model step + actor sample.
+        Returns (actions, {"h", "z", "a"})."""
+        wm = self.world_model
+        cfg = self.engine.cfg
+        rows, hz = wm._run_inference(previous_states, observations, is_first)
+        actions = self.engine.tensor("inf.a")[:rows].clone()
+        return actions, {"h": hz[:, :cfg.G].clone(), "z": hz[:, cfg.G:].unflatten(1, (cfg.Zc, cfg.Zk)).clone(), "a": actions}
 
     def dream_trajectory(self, *, start_states, start_is_terminated, timesteps_H, gamma):
         """dreamer_model.py:147-303. Returns views of engine-owned, time-major buffers."""

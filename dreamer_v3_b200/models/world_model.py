@@ -169,7 +169,49 @@ class WorldModel:
             "z_states_BxT": hz[:, cfg.G:].unflatten(1, (cfg.Zc, cfg.Zk)),
         }
 
+    def _run_inference(self, previous_states, observations, is_first):
+        """One acting step on the engine for rows = observations.shape[0] <= B parallel envs."""
+        e = self.engine
+        cfg = e.cfg
+        rows = int(torch.as_tensor(is_first).reshape(-1).shape[0])
+        if rows > cfg.B:
+            raise ValueError(f"forward_inference supports up to B={cfg.B} rows, got {rows}")
+
+        def put(name, value, width):
+            dst = e.tensor(name).reshape(cfg.B, -1)[:rows]
+            src = value if torch.is_tensor(value) else torch.from_numpy(np.ascontiguousarray(value))
+            dst.copy_(src.reshape(rows, width).to(torch.float32), non_blocking=True)
+
+        put("inf.obs", observations, cfg.obs_flat)
+        put("inf.is_first", is_first, 1)
+        put("inf.prev_h", previous_states["h"], cfg.G)
+        put("inf.prev_z", previous_states["z"], cfg.Z)
+        a = previous_states.get("a")
+        if a is None:
+            a = torch.zeros((rows, cfg.A))
+        put("inf.prev_a", a, cfg.A)
+        if self._explicit_noise:
+            e.forward_inference(rows, 0)
+        else:
+            self._noise_step += 1
+            e.forward_inference(rows, self.noise_seed + 7919 * self._noise_step)
+        hz = e.tensor("inf.hz")[:rows]
+        return rows, hz
+
+    def set_inference_noise(self, u_z, act_noise):
+        """Explicit noise for the acting step (parity runs): u_z [rows, Zc], act_noise [rows] or [rows, A]."""
+        self._explicit_noise = True
+        e = self.engine
+        rows = int(np.asarray(u_z).shape[0])
+        e.tensor("inf.u_z")[:rows].copy_(torch.as_tensor(np.asarray(u_z), dtype=torch.float32))
+        an = torch.as_tensor(np.asarray(act_noise), dtype=torch.float32)
+        e.tensor("inf.act_noise")[:rows].copy_(an.reshape(e.tensor("inf.act_noise")[:rows].shape))
+
     def forward_inference(self, previous_states, observations, is_first, training=None):
-        raise NotImplementedError("single-step acting (world_model.py:141-180) is a 'next' row (SURVEY.md 8f-1), not on the training hot path")
+        """world_model.py:141-180: masks the previous states with the learned initial state where is_first, runs one
+        sequence-model step and draws the posterior z from the observation. Returns {"h": [rows,G], "z": [rows,Zc,Zk]}."""
+        cfg = self.engine.cfg
+        rows, hz = self._run_inference(previous_states, observations, is_first)
+        return {"h": hz[:, :cfg.G].clone(), "z": hz[:, cfg.G:].unflatten(1, (cfg.Zc, cfg.Zk)).clone()}
 
     __call__ = forward_inference

@@ -117,6 +117,12 @@ int dv3_optimizer_step(dv3_engine* e, int group, float clip, float lr, float eps
  * drawn on the device first; use_graph: the call is captured once into a CUDA graph and replayed. */
 int dv3_train_world_model_step(dv3_engine* e, const dv3_hparams* hp, uint64_t noise_seed, int use_graph, void* stream);
 
+/* Acting step, DreamerModel.forward_inference = WorldModel.forward_inference + actor (world_model.py:141-180,
+ * 329-342; dreamer_model.py:113-128; called once per env step by env_runner_v2.py:274-282) for `rows` <= B parallel
+ * envs. Reads inf.obs, inf.is_first, inf.prev_h, inf.prev_z, inf.prev_a, inf.u_z [rows,Zc], inf.act_noise; writes inf.h,
+ * inf.z (one-hot), inf.a (and inf.z_indices, inf.z_probs). noise_seed != 0 draws the noise on the device. */
+int dv3_forward_inference(dv3_engine* e, int rows, uint64_t noise_seed, void* stream);
+
 /* ---- dreamer / actor / critic --------------------------------------------------------------- */
 /* DreamerModel.dream_trajectory (dreamer_model.py:147-303). start states: start_from_observe=1 uses
  * wm.hz of the last dv3_observe_forward (as run_experiment.py:458-460 does); otherwise in.dream_h0

@@ -207,6 +207,25 @@ class Oracle:
         z = F.one_hot(torch.argmax(probs, dim=-1), self.cfg.Zk).to(self.dtype)
         return {"h": h, "z": z.detach()}
 
+    def forward_inference(self, prev_h, prev_z, prev_a, obs, is_first, u_z=None, act_noise=None, rng=None, margin=0.0):
+        """models/world_model.py:141-180 (+ compute_posterior_z :329-342) followed by the actor, i.e.
+        DreamerModel.forward_inference (models/dreamer_model.py:113-128). All inputs are [B, ...] (no time axis)."""
+        cfg, dt = self.cfg, self.dtype
+        prev_h, prev_z, prev_a = _t(prev_h, dt), _t(prev_z, dt).reshape(-1, cfg.Zc, cfg.Zk), _t(prev_a, dt)
+        obs, f = _t(obs, dt), _t(is_first, dt).reshape(-1, 1)
+        init = self.get_initial_state()
+        h_in = prev_h * (1.0 - f) + init["h"] * f
+        z_in = prev_z * (1.0 - f.unsqueeze(-1)) + init["z"] * f.unsqueeze(-1)
+        a_in = prev_a * (1.0 - f)
+        h = self.sequence_model(z_in, a_in, h_in)
+        x = symlog(obs) if cfg.symlog_obs else obs
+        enc = self.encoder(x)
+        p = self.mlp("post", torch.cat([enc, h], dim=-1), 1)
+        z, probs, idx = self.representation("post.repr", p, u_z, "inf_u_z", rng, margin)
+        hz = torch.cat([h, z.reshape(z.shape[0], -1)], -1)
+        a, dist = self.actor(hz.detach(), act_noise, "inf_act_noise", rng, margin)
+        return {"h": h.detach(), "z": z.detach(), "a": a.detach(), "z_idx": idx, "z_probs": probs.detach(), "dist": dist}
+
     def forward_train(self, obs, actions, is_first, u_post=None, rng=None, margin=0.0):
         """models/world_model.py:183-326. obs [B,T,...], actions [B,T,A] (one-hot / float),
         is_first [B,T]; u_post [T,B,Zc] uniforms (or drawn from `rng` and recorded)."""

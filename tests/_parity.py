@@ -27,12 +27,14 @@ class ParityRun:
     """One oracle-vs-engine comparison of a full train update (world model + actor/critic)."""
 
     def __init__(self, cfg: EngineConfig, seed=0, init_mode="random", oracle_dtype=torch.float64, compute_mode=0,
-                 margin=1e-3, steps=1, sync_grads=True):
+                 margin=1e-3, steps=1, sync_grads=True, sample_fn=None):
         self.cfg = cfg
         self.report = {}      # name -> rel err (float tensors)
         self.exact = {}       # name -> number of mismatching integers
         self.params0 = init_params(cfg, seed=seed + 1, mode=init_mode)
         self.sample = make_synthetic_sample(cfg, seed=seed + 2)
+        if sample_fn is not None:
+            sample_fn(self.sample)
         self.rng = np.random.default_rng(seed + 3)
         self.oracle = Oracle(cfg, self.params0, dtype=oracle_dtype)
         self.engine = Engine(cfg, compute_mode=compute_mode)

@@ -86,3 +86,53 @@ def test_api_matches_oracle_over_three_updates(discrete):
         assert dist0.entropy().shape == (cfg.N,)
     assert dm.critic.optimizer.iterations == 3 and wm.optimizer.iterations == 3
     e.close()
+
+
+@pytest.mark.parametrize("kind", ["vec-disc", "vec-box", "img-disc"])
+def test_forward_inference_matches_oracle(kind):
+    """Acting step: DreamerModel.forward_inference over a short closed loop, with is_first resets."""
+    from dreamer_v3_b200.models.components import CNNAtari, ConvTransposeAtari, MLP, VectorDecoder
+    from dreamer_v3_b200.models.dreamer_model import DreamerModel
+    from dreamer_v3_b200.models.world_model import WorldModel
+    from dreamer_v3_b200.spec import Box, Discrete
+    from oracle.dreamer_oracle import Oracle
+    image = kind.startswith("img")
+    discrete = kind.endswith("disc")
+    size = "micro" if image else "XXS"
+    space = Discrete(4) if discrete else Box(-1, 1, (3,))
+    if image:
+        enc, dec = CNNAtari(model_dimension=size), ConvTransposeAtari(model_dimension=size, gray_scaled=False)
+    else:
+        enc, dec = MLP(model_dimension=size), VectorDecoder(model_dimension=size, observation_space=Box(-1, 1, (5,)))
+    wm = WorldModel(model_dimension=size, action_space=space, batch_length_T=4, encoder=enc, decoder=dec,
+                    symlog_obs=not image, seed=1)
+    dm = DreamerModel(model_dimension=size, action_space=space, batch_size_B=4, batch_length_T=4, horizon_H=3, world_model=wm)
+    e = dm.engine
+    cfg = e.cfg
+    g = torch.Generator().manual_seed(0)
+    e.tensor("initial_h").copy_(0.3 * torch.randn(cfg.G, generator=g))   # non-trivial learned initial state
+    oracle = Oracle(cfg, e.get_params(), dtype=torch.float64)
+    rng = np.random.default_rng(1)
+    rows = 3
+    init = dm.get_initial_state()
+    assert init["h"].shape == (1, cfg.G) and init["z"].shape == (1, cfg.Zc, cfg.Zk) and init["a"].shape == (1, cfg.A)
+    oinit = oracle.get_initial_state()
+    np.testing.assert_allclose(init["h"].cpu().numpy(), oinit["h"].detach().numpy(), atol=1e-6)
+    np.testing.assert_array_equal(init["z"].cpu().numpy(), oinit["z"].numpy())
+    states = {k: v.repeat(rows, *([1] * (v.dim() - 1))) for k, v in init.items()}
+    ostates = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in states.items()}
+    for step in range(5):
+        obs = rng.standard_normal((rows,) + ((64, 64, 3) if image else (5,))).astype(np.float32)
+        is_first = np.array([1.0 if step == 0 else 0.0, 1.0 if step == 3 else 0.0, 0.0], np.float32)
+        o = oracle.forward_inference(ostates["h"], ostates["z"], ostates["a"], obs, is_first, rng=rng, margin=1e-3)
+        wm.set_inference_noise(oracle.last_noise.pop("inf_u_z")[0], oracle.last_noise.pop("inf_act_noise")[0])
+        actions, new = dm.forward_inference(states, obs, is_first)
+        np.testing.assert_allclose(new["h"].cpu().numpy(), o["h"].numpy(), atol=1e-4)
+        np.testing.assert_array_equal(new["z"].argmax(-1).cpu().numpy(), o["z_idx"])
+        np.testing.assert_allclose(actions.cpu().numpy(), o["a"].numpy(), atol=1e-4)
+        assert set(new) == {"h", "z", "a"}
+        states = new
+        ostates = {"h": o["h"].numpy(), "z": o["z"].numpy(), "a": o["a"].numpy()}
+    wz = wm.forward_inference(states, obs, is_first)
+    assert set(wz) == {"h", "z"}
+    e.close()
