@@ -11,16 +11,21 @@ namespace dv3 {
 void Engine::actor_fwd(long long row_off) {
   // models/actor_network.py:63-118 on rows [row_off, row_off + N) of the dream
   const float* x = dr_hz + (size_t)row_off * (G + Z);
-  mlp_fwd(actor_mlp, actor_act, x, G + Z, N, row_off);
   float* out = actor_logits + (size_t)row_off * A;
-  mm(actor_act.act.back() + (size_t)row_off * D, D, false, actor_out.w, A, false, out, A, N, A, D, actor_out.bias);
+  auto mean_branch = [&] {
+    mlp_fwd(actor_mlp, actor_act, x, G + Z, N, row_off);
+    mm(actor_act.act.back() + (size_t)row_off * D, D, false, actor_out.w, A, false, out, A, N, A, D, actor_out.bias);
+  };
   if (discrete) {
+    mean_branch();
     disc_actor_fwd(cur, out, in_act_noise + row_off, actor_probs + (size_t)row_off * A, dr_a_idx + row_off,
                    dr_act + (size_t)row_off * A, A, N, A);
   } else {
-    mlp_fwd(actor_std_mlp, actor_std_act, x, G + Z, N, row_off);
     float* sraw = actor_s + (size_t)row_off * A;
-    mm(actor_std_act.act.back() + (size_t)row_off * D, D, false, actor_std_out.w, A, false, sraw, A, N, A, D, actor_std_out.bias);
+    run_branches({mean_branch, [&] {
+                    mlp_fwd(actor_std_mlp, actor_std_act, x, G + Z, N, row_off);
+                    mm(actor_std_act.act.back() + (size_t)row_off * D, D, false, actor_std_out.w, A, false, sraw, A, N, A, D, actor_std_out.bias);
+                  }});
     box_actor_fwd(cur, out, sraw, in_act_noise + (size_t)row_off * A, dr_act + (size_t)row_off * A, A, N, A);
   }
 }
@@ -44,12 +49,14 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
     const size_t prev = (size_t)(i - 1) * N, curr = (size_t)i * N, st = (size_t)(i - 1) * N;  // st: per-step buffers
     const float* hz_p = dr_hz + prev * W;
     float* hz_c = dr_hz + curr * W;
-    // sequence model on [z_{i-1}, a_{i-1}], h_{i-1}
-    mm(hz_p + G, W, false, Wx.w, D, false, dr_x_pre + st * D, D, N, D, Z);
-    mm(dr_act + prev * A, A, false, Wx.w + (size_t)Z * D, D, false, dr_x_pre + st * D, D, N, D, A, nullptr, 1.f);
-    ln_silu_fwd(s, dr_x_pre + st * D, D, Wx.g, Wx.b, dr_u + st * D, D, dr_x_mean + st, dr_x_rstd + st, 1, N, D);
-    mm(dr_u + st * D, D, false, gru_K, 3 * G, false, dr_gx + st * 3 * G, 3 * G, N, 3 * G, D, gru_b);
-    mm(hz_p, W, false, gru_U, 3 * G, false, dr_gh + st * 3 * G, 3 * G, N, 3 * G, G, gru_b + 3 * G);
+    // sequence model on [z_{i-1}, a_{i-1}], h_{i-1}; h_{i-1} . U runs concurrently with the pre-GRU chain
+    run_branches({[&] {
+                    mm(hz_p + G, W, false, Wx.w, D, false, dr_x_pre + st * D, D, N, D, Z);
+                    mm(dr_act + prev * A, A, false, Wx.w + (size_t)Z * D, D, false, dr_x_pre + st * D, D, N, D, A, nullptr, 1.f);
+                    ln_silu_fwd(cur, dr_x_pre + st * D, D, Wx.g, Wx.b, dr_u + st * D, D, dr_x_mean + st, dr_x_rstd + st, 1, N, D);
+                    mm(dr_u + st * D, D, false, gru_K, 3 * G, false, dr_gx + st * 3 * G, 3 * G, N, 3 * G, D, gru_b);
+                  },
+                  [&] { mm(hz_p, W, false, gru_U, 3 * G, false, dr_gh + st * 3 * G, 3 * G, N, 3 * G, G, gru_b + 3 * G); }});
     gru_fwd(s, dr_gx + st * 3 * G, 3 * G, dr_gh + st * 3 * G, 3 * G, hz_p, W, hz_c, W, N, G);
     // prior z_i ~ dynamics_predictor(h_i), straight-through sample
     mm(hz_c, W, false, Wd.w, D, false, dr_q_pre + st * D, D, N, D, G);
@@ -59,18 +66,27 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
              hz_c + G, W, N, Zc, Zk, 1);
     actor_fwd((long long)curr);
   }
-  // heads on all (H+1)*N rows
-  mlp_fwd(rew_mlp, dr_rew_act, dr_hz, W, R);
-  mm(dr_rew_act.act.back(), D, false, rew_head.w, DV3_NB, false, dr_rew_logits, DV3_NB, R, DV3_NB, D, rew_head.bias);
-  bucket_expectation(s, dr_rew_logits, DV3_NB, dr_rew_E, R);
-  mlp_fwd(cont_mlp, dr_cont_act, dr_hz, W, R);
-  mm(dr_cont_act.act.back(), D, false, cont_out.w, 1, false, dr_cont_logit, 1, R, 1, D, cont_out.bias);
-  mlp_fwd(critic_mlp, critic_act, dr_hz, W, R);
-  mm(critic_act.act.back(), D, false, critic_head.w, DV3_NB, false, critic_logits, DV3_NB, R, DV3_NB, D, critic_head.bias);
-  bucket_expectation(s, critic_logits, DV3_NB, v_E, R);
-  mlp_fwd(ema_mlp, ema_act, dr_hz, W, R);
-  mm(ema_act.act.back(), D, false, ema_head.w, DV3_NB, false, ema_logits, DV3_NB, R, DV3_NB, D, ema_head.bias);
-  bucket_expectation(s, ema_logits, DV3_NB, ema_E, R);
+  // heads on all (H+1)*N rows: four independent chains, run concurrently
+  run_branches({
+      [&] {
+        mlp_fwd(critic_mlp, critic_act, dr_hz, W, R);
+        mm(critic_act.act.back(), D, false, critic_head.w, DV3_NB, false, critic_logits, DV3_NB, R, DV3_NB, D, critic_head.bias);
+        bucket_expectation(cur, critic_logits, DV3_NB, v_E, R);
+      },
+      [&] {
+        mlp_fwd(rew_mlp, dr_rew_act, dr_hz, W, R);
+        mm(dr_rew_act.act.back(), D, false, rew_head.w, DV3_NB, false, dr_rew_logits, DV3_NB, R, DV3_NB, D, rew_head.bias);
+        bucket_expectation(cur, dr_rew_logits, DV3_NB, dr_rew_E, R);
+      },
+      [&] {
+        mlp_fwd(cont_mlp, dr_cont_act, dr_hz, W, R);
+        mm(dr_cont_act.act.back(), D, false, cont_out.w, 1, false, dr_cont_logit, 1, R, 1, D, cont_out.bias);
+      },
+      [&] {
+        mlp_fwd(ema_mlp, ema_act, dr_hz, W, R);
+        mm(ema_act.act.back(), D, false, ema_head.w, DV3_NB, false, ema_logits, DV3_NB, R, DV3_NB, D, ema_head.bias);
+        bucket_expectation(cur, ema_logits, DV3_NB, ema_E, R);
+      }});
   // real-space rewards / continues / values, loss weights (dreamer_model.py:219-280) and lambda-returns
   AcArgs a{};
   a.H = H; a.N = N; a.A = A; a.discrete = discrete; a.gamma = gamma; a.lambda_ = 0.95f;
@@ -108,12 +124,28 @@ int Engine::ac_loss_backward(const dv3_hparams* hp, int phase, cudaStream_t s) {
   l.L_reinf_HB = L_reinf_HB; l.L_ent_HB = L_ent_HB; l.scalars = ac_scalars;
   ac_losses(s, l);
 
-  // ---- critic: gradient only reaches the fast critic's own weights (train_one_step.py:197-200) ----
-  cudaMemsetAsync(grads[2], 0, (size_t)numel[2] * 4, s);
-  dense_bwd(critic_head, critic_act.act.back(), D, dcritic_logits, DV3_NB, sN_D0, D, 0.f, true, HN);
-  mlp_bwd(critic_mlp, critic_act, dr_hz, W, sN_D0, sN_D1, nullptr, 0, true, HN);
+  // ---- critic: gradient only reaches the fast critic's own weights (train_one_step.py:197-200). The chain is independent
+  // of everything the actor needs, so it runs on an auxiliary stream next to the whole actor backward. ----
+  auto critic_chain = [&] {
+    cudaMemsetAsync(grads[2], 0, (size_t)numel[2] * 4, cur);
+    dense_bwd(critic_head, critic_act.act.back(), D, dcritic_logits, DV3_NB, sN_D2, D, 0.f, true, HN);
+    mlp_bwd(critic_mlp, critic_act, dr_hz, W, sN_D2, sN_D3, nullptr, 0, true, HN);
+  };
+  if (!hp->train_actor) { critic_chain(); return 0; }
+  side_run(critic_chain);
+  actor_backward(hp, a);
+  side_join();
+  return 0;
+}
 
-  if (!hp->train_actor) return 0;
+// Actor gradients: REINFORCE through the actor MLP (Discrete) or BPTT through rewards / values / the RSSM steps (Box).
+void Engine::actor_backward(const dv3_hparams* hp, const AcArgs& a) {
+  cudaStream_t s = cur;
+  const int W = G + Z;
+  const long long HN = (long long)H * N;
+  {
+    (void)hp;
+  }
   cudaMemsetAsync(grads[1], 0, (size_t)numel[1] * 4, s);
   if (!discrete) {
     // Box actions: the loss is -scaled advantages with gradient (actor_loss.py:57) -> BPTT through rewards,
@@ -140,20 +172,31 @@ int Engine::ac_loss_backward(const dv3_hparams* hp, int phase, cudaStream_t s) {
       mm(sN_D1, D, false, Wd.w, D, true, d_c, W, N, G, D, nullptr, 1.f);
       // h_i = GRU(pre([z_{i-1}, a_{i-1}]), h_{i-1})
       gru_bwd(s, d_c, W, dr_gx + st * 3 * G, 3 * G, dr_gh + st * 3 * G, 3 * G, hz_p, W, sN_3G0, 3 * G, sN_3G1, 3 * G, d_p, W, 1, N, G);
-      mm(sN_3G1, 3 * G, false, gru_U, 3 * G, true, d_p, W, N, G, 3 * G, nullptr, 1.f);
-      mm(sN_3G0, 3 * G, false, gru_K, 3 * G, true, sN_D0, D, N, D, 3 * G);
-      ln_silu_bwd(s, sN_D0, D, dr_x_pre + st * D, D, dr_x_mean + st, dr_x_rstd + st, Wx.g, Wx.b, sN_D1, D, nullptr, nullptr, 1, N, D);
-      mm(sN_D1, D, false, Wx.w, D, true, d_p + G, W, N, Z, D, nullptr, 1.f);
-      mm(sN_D1, D, false, Wx.w + (size_t)Z * D, D, true, sN_A, A, N, A, D);
+      run_branches({[&] {
+                      mm(sN_3G0, 3 * G, false, gru_K, 3 * G, true, sN_D0, D, N, D, 3 * G);
+                      ln_silu_bwd(cur, sN_D0, D, dr_x_pre + st * D, D, dr_x_mean + st, dr_x_rstd + st, Wx.g, Wx.b, sN_D1, D, nullptr, nullptr, 1, N, D);
+                      mm(sN_D1, D, false, Wx.w, D, true, d_p + G, W, N, Z, D, nullptr, 1.f);
+                      mm(sN_D1, D, false, Wx.w + (size_t)Z * D, D, true, sN_A, A, N, A, D);
+                    },
+                    [&] { mm(sN_3G1, 3 * G, false, gru_U, 3 * G, true, d_p, W, N, G, 3 * G, nullptr, 1.f); }});
       box_actor_bwd(s, actor_logits + prev * A, actor_s + prev * A, in_act_noise + prev * A, sN_A, A, dmu + prev * A, ds + prev * A, N, A);
     }
-    dense_bwd(actor_std_out, actor_std_act.act.back(), D, ds, A, sN_D0, D, 0.f, true, HN);
-    mlp_bwd(actor_std_mlp, actor_std_act, dr_hz, W, sN_D0, sN_D1, nullptr, 0, true, HN);
   }
-  // actor MLP: inputs were stop-gradient'ed (dreamer_model.py:179-180), so only weight gradients
-  dense_bwd(actor_out, actor_act.act.back(), D, dactor_logits, A, sN_D0, D, 0.f, true, HN);
-  mlp_bwd(actor_mlp, actor_act, dr_hz, W, sN_D0, sN_D1, nullptr, 0, true, HN);
-  return 0;
+  // actor MLPs: inputs were stop-gradient'ed (dreamer_model.py:179-180), so only weight gradients; the mean and the std
+  // network (Box) are independent chains
+  if (!discrete) {
+    run_branches({[&] {
+                    dense_bwd(actor_out, actor_act.act.back(), D, dactor_logits, A, sN_D0, D, 0.f, true, HN);
+                    mlp_bwd(actor_mlp, actor_act, dr_hz, W, sN_D0, sN_D1, nullptr, 0, true, HN);
+                  },
+                  [&] {
+                    dense_bwd(actor_std_out, actor_std_act.act.back(), D, ds, A, sN_D4, D, 0.f, true, HN);
+                    mlp_bwd(actor_std_mlp, actor_std_act, dr_hz, W, sN_D4, sN_D5, nullptr, 0, true, HN);
+                  }});
+  } else {
+    dense_bwd(actor_out, actor_act.act.back(), D, dactor_logits, A, sN_D0, D, 0.f, true, HN);
+    mlp_bwd(actor_mlp, actor_act, dr_hz, W, sN_D0, sN_D1, nullptr, 0, true, HN);
+  }
 }
 
 int Engine::train_ac(const dv3_hparams* hp, cudaStream_t s) {

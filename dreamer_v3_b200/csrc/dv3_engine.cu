@@ -337,6 +337,7 @@ void Engine::layout() {
   dh0 = af("wm.d_h0", {G});
   sB_D0 = af("", {B, D}); sB_D1 = af("", {B, D}); sB_Z = af("", {B, Z});
   sN_D0 = af("", {Rl, D}); sN_D1 = af("", {Rl, D});
+  sN_D2 = af("", {Rl, D}); sN_D3 = af("", {Rl, D}); sN_D4 = af("", {Rl, D}); sN_D5 = af("", {Rl, D});
   // ---- dream ----
   dr_hz = af("dream.hz", {H + 1, Nl, G + Z});
   dr_act = af("dream.actions", {H + 1, Nl, A});
@@ -483,6 +484,7 @@ int Engine::init(const dv3_config* c) {
   }
   // persistent scan kernels: rows must fit one 16-row tile, classes must tile a 32-column block
   use_persistent = std::getenv("DV3_NO_PERSISTENT") == nullptr;
+  use_branches = std::getenv("DV3_NO_BRANCHES") == nullptr;
   scan_ctas = 0;
   if (B <= 16 && (32 % Zk) == 0) {
     const int max_ctas = scan_fwd_max_ctas(cfg.device);
@@ -511,6 +513,9 @@ void Engine::destroy() {
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
   if (slot_wm.exec) cudaGraphExecDestroy(slot_wm.exec);
   if (slot_ac.exec) cudaGraphExecDestroy(slot_ac.exec);
+  for (int i = 0; i < kAux; ++i) if (aux[i]) { cudaStreamDestroy(aux[i]); cudaEventDestroy(ev_join[i]); }
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (side) { cudaStreamDestroy(side); cudaEventDestroy(ev_side_in); cudaEventDestroy(ev_side_out); }
   if (own_stream) { cudaStreamDestroy(own_stream); cudaEventDestroy(ev_in); cudaEventDestroy(ev_out); }
   for (void* p : allocations) cudaFree(p);
   allocations.clear();
@@ -552,6 +557,58 @@ void Engine::build_shadows() {
 void Engine::refresh_shadows(cudaStream_t s) {
   if (cfg.compute_mode != 1 || shadow_host.empty()) return;
   weight_shadow_batched(s, shadow_dev, (int)shadow_host.size(), shadow_tiles);
+}
+
+// ------------------------------------------------------------------------------------------ fork / join
+void Engine::run_branches(const std::vector<std::function<void()>>& branches) {
+  cudaStream_t main = cur;
+  if (!use_branches || branches.size() <= 1) {
+    for (auto& b : branches) { cur = main; b(); }
+    cur = main;
+    return;
+  }
+  if (aux[0] == nullptr) {
+    for (int i = 0; i < kAux; ++i) {
+      cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+  }
+  cudaEventRecord(ev_fork, main);
+  const int n = (int)branches.size();
+  for (int i = 1; i < n; ++i) {
+    const int a = (i - 1) % kAux;
+    if (i - 1 < kAux) cudaStreamWaitEvent(aux[a], ev_fork, 0);
+    cur = aux[a];
+    branches[i]();
+  }
+  cur = main;
+  branches[0]();
+  for (int a = 0; a < kAux && a < n - 1; ++a) {
+    cudaEventRecord(ev_join[a], aux[a]);
+    cudaStreamWaitEvent(main, ev_join[a], 0);
+  }
+  cur = main;
+}
+
+void Engine::side_run(const std::function<void()>& fn) {
+  if (!use_branches) { fn(); return; }
+  if (side == nullptr) {
+    cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ev_side_in, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_side_out, cudaEventDisableTiming);
+  }
+  cudaStream_t main = cur;
+  cudaEventRecord(ev_side_in, main);
+  cudaStreamWaitEvent(side, ev_side_in, 0);
+  cur = side;
+  fn();
+  cudaEventRecord(ev_side_out, side);
+  cur = main;
+}
+void Engine::side_join() {
+  if (!use_branches || side == nullptr) return;
+  cudaStreamWaitEvent(cur, ev_side_out, 0);
 }
 
 // ------------------------------------------------------------------------------------------ building blocks

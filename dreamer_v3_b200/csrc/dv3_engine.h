@@ -1,5 +1,6 @@
 // Engine: owns parameters / gradients / Adam slots / activations and orchestrates the hot path.
 #pragma once
+#include <functional>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -102,6 +103,7 @@ struct Engine {
   float *d_hz, *dpost_logits, *dp_pre, *dgx, *dgh, *dh_in, *dx_pre, *dprior_logits, *dq_pre, *d_enc_out, *dh0;
   float *sB_D0, *sB_D1, *sB_Z;     // per-step scratch [B, D], [B, Z]
   float *sN_D0, *sN_D1;            // [max(N,R) , max(D, ...)] scratch for MLP backward
+  float *sN_D2, *sN_D3, *sN_D4, *sN_D5;  // second / third scratch pairs for chains that run concurrently
   // ---- dream ----
   float *dr_hz, *dr_act;           // [R, G+Z], [R, A]
   float *dr_x_pre, *dr_x_mean, *dr_x_rstd, *dr_u, *dr_gx, *dr_gh, *dr_q_pre, *dr_q_mean, *dr_q_rstd, *dr_q_act;
@@ -133,6 +135,19 @@ struct Engine {
   MlpAct inf_enc_act, inf_actor_act, inf_std_act;
   unsigned long long inf_calls = 0;
   int forward_inference(int rows, uint64_t noise_seed, cudaStream_t s);
+
+  // ---- fork / join of independent op chains onto auxiliary streams (capturable: events only) ----
+  static constexpr int kAux = 3;
+  cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr, nullptr, nullptr};
+  bool use_branches = true;
+  // runs branches[0] on the current stream and the others concurrently on auxiliary streams, then joins them
+  void run_branches(const std::vector<std::function<void()>>& branches);
+  // a long side chain on its own stream (outside the pool above, so the main chain may still fork internally)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_side_in = nullptr, ev_side_out = nullptr;
+  void side_run(const std::function<void()>& fn);  // forks from cur, runs fn on `side`
+  void side_join();                                // cur waits for the side chain
 
   // ---- graph ----
   struct GraphSlot { cudaGraphExec_t exec = nullptr; long long launches = 0; dv3_hparams hp{}; uint64_t seed = 0; };
@@ -182,6 +197,7 @@ struct Engine {
   int dream_forward(float gamma, int start_from_observe, cudaStream_t s);
   void actor_fwd(long long row_off);
   int ac_loss_backward(const dv3_hparams* hp, int phase, cudaStream_t s);
+  void actor_backward(const dv3_hparams* hp, const AcArgs& a);
   int fill_noise(uint64_t seed, uint64_t step, int which, bool device_step, cudaStream_t s);
   int train_wm(const dv3_hparams* hp, cudaStream_t s);
   int train_ac(const dv3_hparams* hp, cudaStream_t s);

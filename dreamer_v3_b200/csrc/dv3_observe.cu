@@ -73,18 +73,25 @@ int Engine::observe_forward(cudaStream_t s) {
     repr_fwd(s, post_logits + (size_t)t * Z, T * Z, post_probs + (size_t)t * Z, T * Z, in_u_post + (size_t)t * B * Zc, Zc,
              z_idx + (size_t)t * Zc, T * Zc, hz + (size_t)t * (G + Z) + G, ldhz, B, Zc, Zk, 1);
   }
-  // prior for all timesteps at once (world_model.py:272; its sample is discarded by the reference)
-  mm(hz, G + Z, false, Wd.w, D, false, q_pre, D, N, D, G);
-  ln_silu_fwd(s, q_pre, D, Wd.g, Wd.b, q_act, D, q_mean, q_rstd, 1, N, D);
-  mm(q_act, D, false, dyn_repr.w, Z, false, prior_logits, Z, N, Z, D, dyn_repr.bias);
-  repr_fwd(s, prior_logits, Z, prior_probs, Z, nullptr, 0, nullptr, 0, nullptr, 0, N, Zc, Zk, 0);
-  // heads on the folded B*T rows (world_model.py:299-309)
-  mlp_fwd(rew_mlp, rew_act, hz, G + Z, N);
-  mm(rew_act.act.back(), D, false, rew_head.w, DV3_NB, false, rew_logits, DV3_NB, N, DV3_NB, D, rew_head.bias);
-  bucket_expectation(s, rew_logits, DV3_NB, rew_E, N);
-  mlp_fwd(cont_mlp, cont_act, hz, G + Z, N);
-  mm(cont_act.act.back(), D, false, cont_out.w, 1, false, cont_logit, 1, N, 1, D, cont_out.bias);
-  decoder_fwd();
+  // After the scan, four independent chains over the folded B*T rows run concurrently (fork/join on auxiliary streams):
+  // the prior net (world_model.py:272; its sample is discarded by the reference) and the three heads (:299-309).
+  run_branches({
+      [&] { decoder_fwd(); },
+      [&] {
+        mm(hz, G + Z, false, Wd.w, D, false, q_pre, D, N, D, G);
+        ln_silu_fwd(cur, q_pre, D, Wd.g, Wd.b, q_act, D, q_mean, q_rstd, 1, N, D);
+        mm(q_act, D, false, dyn_repr.w, Z, false, prior_logits, Z, N, Z, D, dyn_repr.bias);
+        repr_fwd(cur, prior_logits, Z, prior_probs, Z, nullptr, 0, nullptr, 0, nullptr, 0, N, Zc, Zk, 0);
+      },
+      [&] {
+        mlp_fwd(rew_mlp, rew_act, hz, G + Z, N);
+        mm(rew_act.act.back(), D, false, rew_head.w, DV3_NB, false, rew_logits, DV3_NB, N, DV3_NB, D, rew_head.bias);
+        bucket_expectation(cur, rew_logits, DV3_NB, rew_E, N);
+      },
+      [&] {
+        mlp_fwd(cont_mlp, cont_act, hz, G + Z, N);
+        mm(cont_act.act.back(), D, false, cont_out.w, 1, false, cont_logit, 1, N, 1, D, cont_out.bias);
+      }});
   return 0;
 }
 
@@ -164,19 +171,28 @@ int Engine::wm_loss_backward(cudaStream_t s) {
       scan_mask_grads(s, in_is_first + t, T, sB_Z, Z, dprev + G, ldhz, B, Z);
     }
   }
-  // weight gradients, one N-row contraction each
-  dense_bwd(post_repr, p_act, D, dpost_logits, Z, nullptr, 0, 0.f, true, N);
-  mm(enc_out, E, true, dp_pre, D, false, Wp.dw, D, E, D, N, nullptr, 1.f);
-  mm(hz, G + Z, true, dp_pre, D, false, Wp.dw + (size_t)E * D, D, G, D, N, nullptr, 1.f);
-  mm(u_act, D, true, dgx, 3 * G, false, d_gru_K, 3 * G, D, 3 * G, N, nullptr, 1.f);
-  colsum_acc(s, dgx, 3 * G, N, 3 * G, d_gru_b);
-  mm(h_in, G, true, dgh, 3 * G, false, d_gru_U, 3 * G, G, 3 * G, N, nullptr, 1.f);
-  colsum_acc(s, dgh, 3 * G, N, 3 * G, d_gru_b + 3 * G);
-  mm(z_in, Z, true, dx_pre, D, false, Wx.dw, D, Z, D, N, nullptr, 1.f);
-  mm(a_in, A, true, dx_pre, D, false, Wx.dw + (size_t)Z * D, D, A, D, N, nullptr, 1.f);
-  // learned initial state: every is_first row (and every row at t = 0) starts from tanh(initial_h)
-  mm(wf, 1, true, dh_in, G, false, dh0, G, 1, G, N);
-  tanh_bwd_acc(s, dh0, h0, d_initial_h, G);
+  // weight gradients, one N-row contraction each; they are independent of one another -> four concurrent chains
+  run_branches({
+      [&] {
+        dense_bwd(post_repr, p_act, D, dpost_logits, Z, nullptr, 0, 0.f, true, N);
+        mm(enc_out, E, true, dp_pre, D, false, Wp.dw, D, E, D, N, nullptr, 1.f);
+        mm(hz, G + Z, true, dp_pre, D, false, Wp.dw + (size_t)E * D, D, G, D, N, nullptr, 1.f);
+      },
+      [&] {
+        mm(u_act, D, true, dgx, 3 * G, false, d_gru_K, 3 * G, D, 3 * G, N, nullptr, 1.f);
+        colsum_acc(cur, dgx, 3 * G, N, 3 * G, d_gru_b);
+      },
+      [&] {
+        mm(h_in, G, true, dgh, 3 * G, false, d_gru_U, 3 * G, G, 3 * G, N, nullptr, 1.f);
+        colsum_acc(cur, dgh, 3 * G, N, 3 * G, d_gru_b + 3 * G);
+      },
+      [&] {
+        mm(z_in, Z, true, dx_pre, D, false, Wx.dw, D, Z, D, N, nullptr, 1.f);
+        mm(a_in, A, true, dx_pre, D, false, Wx.dw + (size_t)Z * D, D, A, D, N, nullptr, 1.f);
+        // learned initial state: every is_first row (and every row at t = 0) starts from tanh(initial_h)
+        mm(wf, 1, true, dh_in, G, false, dh0, G, 1, G, N);
+        tanh_bwd_acc(cur, dh0, h0, d_initial_h, G);
+      }});
   // encoder
   mm(dp_pre, D, false, Wp.w, D, true, d_enc_out, E, N, E, D);
   encoder_bwd(d_enc_out);
