@@ -55,6 +55,7 @@ SIGNATURES = {
     "dv3_critic_update_ema": (_I, [_P, _F, _P]),
     "dv3_train_actor_critic_step": (_I, [_P, C.POINTER(Dv3Hparams), _U64, _I, _P]),
     "dv3_train_update": (_I, [_P, C.POINTER(Dv3Hparams), _U64, _I, _P]),
+    "dv3_dp_piece": (_I, [_P, C.POINTER(Dv3Hparams), _I, _U64, _I, _P]),
     "dv3_kernel_launch_count": (_I64, [_P]),
     "dv3_op_symlog": (_I, [_P, _P, _I64, _P]),
     "dv3_op_inverse_symlog": (_I, [_P, _P, _I64, _P]),

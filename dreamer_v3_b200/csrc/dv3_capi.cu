@@ -162,6 +162,10 @@ int dv3_train_actor_critic_step(dv3_engine* h, const dv3_hparams* hp, uint64_t n
   }
   return rc ? rc : check_async(h->e);
 }
+int dv3_dp_piece(dv3_engine* h, const dv3_hparams* hp, int piece, uint64_t noise_seed, int use_graph, void* stream) {
+  int rc = h->e.dp_piece(hp, piece, noise_seed, use_graph, S(stream));
+  return rc ? rc : check_async(h->e);
+}
 int dv3_train_update(dv3_engine* h, const dv3_hparams* hp, uint64_t noise_seed, int use_graph, void* stream) {
   int rc = h->e.train_update(hp, noise_seed, use_graph, S(stream));
   return rc ? rc : check_async(h->e);

@@ -268,6 +268,39 @@ int Engine::train_ac_graph(const dv3_hparams* hp, uint64_t seed, cudaStream_t s)
   });
 }
 
+// Data-parallel update = five graph-replayed pieces with the NCCL collectives of train_one_step.py between them:
+//   0: noise + observe forward + world-model losses / BPTT      -> all-reduce(world_model grads)
+//   1: world-model clip + Adam
+//   2: noise + dream rollout + value targets                    -> all-gather(value targets)
+//   3: percentiles, critic / actor losses and gradients          -> all-reduce(critic grads), all-reduce(actor grads)
+//   4: actor and critic clip + Adam (+ critic EMA)
+int Engine::dp_piece(const dv3_hparams* hp, int piece, uint64_t seed, int use_graph, cudaStream_t s) {
+  if (piece < 0 || piece > 4) return fail("dp_piece: piece must be in [0, 4]");
+  auto body = [&](cudaStream_t st) -> int {
+    int rc = 0;
+    switch (piece) {
+      case 0:
+        if (seed != 0) { bump_counter(st, noise_step); fill_noise(seed, 0, 1, true, st); }
+        rc = observe_forward(st);
+        if (!rc) rc = wm_loss_backward(st);
+        break;
+      case 1: rc = optimizer_step(0, hp->wm_grad_clip, hp->wm_lr, hp->wm_eps, 0.f, st); break;
+      case 2:
+        if (seed != 0) fill_noise(seed, 0, 2, true, st);
+        rc = dream_forward(hp->gamma, 1, st);
+        if (!rc) rc = ac_loss_backward(hp, 1, st);
+        break;
+      case 3: rc = ac_loss_backward(hp, 2, st); break;
+      default:
+        if (hp->train_actor) rc = optimizer_step(1, hp->actor_grad_clip, hp->ac_lr, hp->ac_eps, 0.f, st);
+        if (!rc) rc = optimizer_step(2, hp->critic_grad_clip, hp->ac_lr, hp->ac_eps, hp->critic_ema_decay, st);
+    }
+    return rc;
+  };
+  if (!use_graph) return body(s);
+  return run_graphed(slot_piece[piece], hp, seed, s, body);
+}
+
 int Engine::train_update(const dv3_hparams* hp, uint64_t seed, int use_graph, cudaStream_t s) {
   auto body = [&](cudaStream_t st) -> int {
     if (seed != 0) {

@@ -513,6 +513,7 @@ void Engine::destroy() {
   if (graph_exec) cudaGraphExecDestroy(graph_exec);
   if (slot_wm.exec) cudaGraphExecDestroy(slot_wm.exec);
   if (slot_ac.exec) cudaGraphExecDestroy(slot_ac.exec);
+  for (auto& sl : slot_piece) if (sl.exec) cudaGraphExecDestroy(sl.exec);
   for (int i = 0; i < kAux; ++i) if (aux[i]) { cudaStreamDestroy(aux[i]); cudaEventDestroy(ev_join[i]); }
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (side) { cudaStreamDestroy(side); cudaEventDestroy(ev_side_in); cudaEventDestroy(ev_side_out); }

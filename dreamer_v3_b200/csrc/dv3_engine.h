@@ -151,7 +151,8 @@ struct Engine {
 
   // ---- graph ----
   struct GraphSlot { cudaGraphExec_t exec = nullptr; long long launches = 0; dv3_hparams hp{}; uint64_t seed = 0; };
-  GraphSlot slot_wm, slot_ac;
+  GraphSlot slot_wm, slot_ac, slot_piece[5];
+  int dp_piece(const dv3_hparams* hp, int piece, uint64_t seed, int use_graph, cudaStream_t s);
   template <class F> int run_graphed(GraphSlot& slot, const dv3_hparams* hp, uint64_t seed, cudaStream_t s, F body);
   int train_wm_graph(const dv3_hparams* hp, uint64_t seed, cudaStream_t s);
   int train_ac_graph(const dv3_hparams* hp, uint64_t seed, cudaStream_t s);

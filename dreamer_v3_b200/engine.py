@@ -195,6 +195,10 @@ class Engine:
         self._check(self.lib.dv3_train_update(self.h, C.byref(self.hp), int(noise_seed), int(use_graph), self._stream()),
                     "dv3_train_update")
 
+    def dp_piece(self, piece, noise_seed=0, use_graph=True):
+        self._check(self.lib.dv3_dp_piece(self.h, C.byref(self.hp), int(piece), int(noise_seed), int(use_graph), self._stream()),
+                    "dv3_dp_piece")
+
     def kernel_launch_count(self):
         return int(self.lib.dv3_kernel_launch_count(self.h))
 

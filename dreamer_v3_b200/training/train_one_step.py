@@ -21,11 +21,12 @@ def train_world_model_one_step(*, sample, batch_size_B, batch_length_T, grad_cli
     e.set_sample(sample)
     opt = world_model.optimizer
     if _dp(e):
-        world_model._draw_noise(1)
-        e.observe_forward()
-        e.wm_loss_backward()
+        # data parallel: graph-replayed pieces with the NCCL collectives between them
+        e.hp.wm_grad_clip, e.hp.wm_lr, e.hp.wm_eps = float(grad_clip), opt.learning_rate, opt.epsilon
+        seed = 0 if world_model._explicit_noise else world_model.noise_seed + 104729 * e.rank
+        e.dp_piece(0, seed)
         dist.all_reduce(e.group_buffer("world_model", "grad"))
-        e.optimizer_step("world_model", float(grad_clip), opt.learning_rate, opt.epsilon)
+        e.dp_piece(1)
     else:
         # single process: forward + losses + BPTT + clip/Adam replayed as ONE CUDA graph (noise drawn inside it)
         e.hp.wm_grad_clip, e.hp.wm_lr, e.hp.wm_eps = float(grad_clip), opt.learning_rate, opt.epsilon
@@ -64,6 +65,20 @@ def train_actor_and_critic_one_step(*, world_model_forward_train_outs, is_termin
     hz = t("wm.hz")
     h_in = world_model_forward_train_outs["h_states_BxT"]
     own_states = torch.is_tensor(h_in) and h_in.is_cuda and h_in.data_ptr() == hz.data_ptr()
+    if _dp(e) and own_states and horizon_H == e.cfg.H:
+        wm = dreamer_model.world_model
+        e.write("in.is_terminated", torch.as_tensor(is_terminated).reshape(e.cfg.B, e.cfg.T))
+        hp.actor_grad_clip, hp.critic_grad_clip = float(actor_grad_clip), float(critic_grad_clip)
+        hp.ac_lr, hp.ac_eps, hp.critic_ema_decay = aopt.learning_rate, aopt.epsilon, dreamer_model.critic.ema_decay
+        seed = 0 if wm._explicit_noise else wm.noise_seed + 104729 * e.rank
+        e.dp_piece(2, seed)
+        dist.all_gather_into_tensor(t("ac.value_targets_all").reshape(-1), t("ac.value_targets").reshape(-1))
+        e.dp_piece(3)
+        dist.all_reduce(e.group_buffer("critic", "grad"))
+        if train_actor:
+            dist.all_reduce(e.group_buffer("actor", "grad"))
+        e.dp_piece(4)
+        return _ac_results(e, dreamer_model._dream_outs(), train_actor)
     if not _dp(e) and own_states and horizon_H == e.cfg.H:
         # single process, dreaming from the engine's own last observe pass: the whole actor/critic update (dream, value
         # targets, losses, gradients, clip/Adam x2, critic EMA) is ONE CUDA-graph replay
@@ -79,7 +94,7 @@ def train_actor_and_critic_one_step(*, world_model_forward_train_outs, is_termin
         start_is_terminated=is_terminated, timesteps_H=horizon_H, gamma=gamma)
     if _dp(e):
         e.ac_loss_backward(1)
-        dist.all_gather_into_tensor(t("ac.value_targets_all"), t("ac.value_targets"))
+        dist.all_gather_into_tensor(t("ac.value_targets_all").reshape(-1), t("ac.value_targets").reshape(-1))
         e.ac_loss_backward(2)
         dist.all_reduce(e.group_buffer("critic", "grad"))
         if train_actor:

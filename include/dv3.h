@@ -144,6 +144,10 @@ int dv3_train_actor_critic_step(dv3_engine* e, const dv3_hparams* hp, uint64_t n
 /* Captures {wm step, ac step} once into a CUDA graph on `stream` and replays it: one launch per
  * update instead of thousands. noise_seed != 0: noise is regenerated on the device each replay. */
 int dv3_train_update(dv3_engine* e, const dv3_hparams* hp, uint64_t noise_seed, int use_graph, void* stream);
+/* Data-parallel update (world_size > 1): the same work cut at the collectives into five graph-replayed pieces;
+ * piece 0: observe + WM losses/BPTT [all-reduce WM grads] 1: WM clip+Adam 2: dream + value targets [all-gather targets]
+ * 3: critic/actor losses + gradients [all-reduce critic, actor grads] 4: actor/critic clip+Adam (+EMA). */
+int dv3_dp_piece(dv3_engine* e, const dv3_hparams* hp, int piece, uint64_t noise_seed, int use_graph, void* stream);
 int64_t dv3_kernel_launch_count(const dv3_engine* e); /* kernels of this library launched (or replayed) so far */
 
 /* ---- isolated ops (parity tests call the same kernels the fused path uses) ---------------------- */
