@@ -213,6 +213,18 @@ int dv3_op_gemm_shadow(const float* A, int lda, int ta, const void* Bh, int ldbh
   dv3::gemm_tc(S(stream), g);
   return op_done();
 }
+int dv3_op_to_bf16(const float* src, int lds, void* dst, int ldd, int64_t rows, int cols, void* stream) {
+  dv3::to_bf16(S(stream), src, lds, dst, ldd, rows, cols);
+  return op_done();
+}
+int dv3_op_gemm_bf16(const void* Ah, int ldah, const void* Bh, int ldbh, float* C, int ldc, int M, int N, int K,
+                     const float* bias, float beta, void* stream) {
+  dv3::GemmArgs g{nullptr, 0, 0, nullptr, 0, 1, C, ldc, M, N, K, bias, beta};
+  g.Bh = Bh; g.ldbh = ldbh; g.Ah = Ah; g.ldah = ldah;
+  if (!dv3::gemm_tma_eligible(g)) return -1;
+  if (!dv3::gemm_tma(S(stream), g)) return -2;
+  return op_done();
+}
 int dv3_op_ln_silu(const float* x, const float* gamma, const float* beta, float* y, int64_t rows, int D, void* stream) {
   if (D > 1024) return -1;
   dv3::ln_silu_fwd(S(stream), x, D, gamma, beta, y, D, nullptr, nullptr, 1, rows, D);

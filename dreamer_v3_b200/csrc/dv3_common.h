@@ -30,6 +30,9 @@ struct GemmArgs {
   // optional bf16 shadow of op(B), K-major: Bh[n*ldbh + k] (tensor-core path only; refreshed by the engine after
   // each optimizer step). When set the tensor-core kernel reads it instead of converting B.
   const void* Bh = nullptr; int ldbh = 0;
+  // optional bf16 copy of A (row-major [M, K], written by A's producer kernel). With both Ah and Bh set the
+  // contraction runs on the TMA-fed kernel (dv3_gemm_tma.cu).
+  const void* Ah = nullptr; int ldah = 0;
 };
 
 // ---- gemm (dv3_gemm.cu) ----------------------------------------------------------------------
@@ -38,6 +41,9 @@ void gemm_f32(cudaStream_t s, const GemmArgs& g);
 void gemm_dispatch(cudaStream_t s, const GemmArgs& g, int mode);
 bool gemm_tc_eligible(const GemmArgs& g);
 void gemm_tc(cudaStream_t s, const GemmArgs& g);  // bf16 tcgen05 / TMEM path
+bool gemm_tma_eligible(const GemmArgs& g);
+bool gemm_tma(cudaStream_t s, const GemmArgs& g);  // both operands bf16 K-major in global memory: TMA + tcgen05
+void to_bf16(cudaStream_t s, const float* src, int lds, void* dst, int ldd, long long rows, int cols);
 // bf16 shadows of weight matrices: out_t[c*rows + r] = bf16(in[r*cols + c]) (transposed), out_n = bf16(in) (plain)
 void weight_shadow_bf16(cudaStream_t s, const float* in, void* out_t, void* out_n, int rows, int cols);
 struct ShadowDesc { const float* in; void* out_t; void* out_n; int rows, cols, tile_begin, pad; };
@@ -54,16 +60,16 @@ void tanh_fwd(cudaStream_t s, const float* x, float* y, int n);
 
 // y = silu(LayerNorm(x)); saves mean/rstd per row. Rows addressed as x + r*ldx.
 void ln_silu_fwd(cudaStream_t s, const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy,
-                 float* mean, float* rstd, int sstride, long long rows, int D);
+                 float* mean, float* rstd, int sstride, long long rows, int D, void* y16 = nullptr);  // y16: bf16 twin of y, same ld
 // dx = d(silu(LN(x)))/dx * dy; dgamma/dbeta accumulated with atomics when non-null.
 void ln_silu_bwd(cudaStream_t s, const float* dy, int lddy, const float* x, int ldx, const float* mean,
                  const float* rstd, const float* gamma, const float* beta, float* dx, int lddx, float* dgamma,
-                 float* dbeta, int sstride, long long rows, int D);
+                 float* dbeta, int sstride, long long rows, int D, void* dx16 = nullptr);
 
 // Keras GRU (reset_after=True, gates z,r,h). gx/gh hold x*K+b0 and h*U+b1 ([M,3G]); on return gx holds
 // (z, r, c) for the backward pass. h_out may alias nothing.
 void gru_fwd(cudaStream_t s, float* gx, int ldgx, const float* gh, int ldgh, const float* h_prev, int ldhp,
-             float* h_out, int ldho, int M, int G);
+             float* h_out, int ldho, int M, int G, void* h16 = nullptr);  // h16: bf16 twin of h_out, same ld
 // gates = (z,r,c) as left by gru_fwd, gh as in forward. Produces dgx, dgh ([M,3G]) and dh_prev (=dh*z,
 // overwritten or accumulated).
 void gru_bwd(cudaStream_t s, const float* dh, int lddh, const float* gates, int ldg, const float* gh, int ldgh,
@@ -74,7 +80,7 @@ void gru_bwd(cudaStream_t s, const float* dh, int lddh, const float* gates, int 
 // optional sample (u [M,Zc] row stride ldu) -> idx [M,Zc] + one-hot z (row stride ldz). mode: 0 = probs only,
 // 1 = sample with u, 2 = argmax (get_initial_state).
 void repr_fwd(cudaStream_t s, const float* logits, int ldl, float* probs, int ldp, const float* u, int ldu,
-              int32_t* idx, int ldi, float* z, int ldz, int M, int Zc, int Zk, int mode);
+              int32_t* idx, int ldi, float* z, int ldz, int M, int Zc, int Zk, int mode, void* z16 = nullptr);
 // dlogits = J_softmax^T (0.99 * (dz + dprobs)); dz / dprobs nullable.
 void repr_bwd(cudaStream_t s, const float* logits, int ldl, const float* dz, int lddz, const float* dprobs, int lddp,
               float* dlogits, int lddl, int M, int Zc, int Zk);

@@ -11,9 +11,10 @@ namespace dv3 {
 void Engine::actor_fwd(long long row_off) {
   // models/actor_network.py:63-118 on rows [row_off, row_off + N) of the dream
   const float* x = dr_hz + (size_t)row_off * (G + Z);
+  const void* x16 = dr_hz16 ? (const void*)((const unsigned short*)dr_hz16 + (size_t)row_off * (G + Z)) : nullptr;
   float* out = actor_logits + (size_t)row_off * A;
   auto mean_branch = [&] {
-    mlp_fwd(actor_mlp, actor_act, x, G + Z, N, row_off);
+    mlp_fwd(actor_mlp, actor_act, x, G + Z, N, row_off, x16);
     mm(actor_act.act.back() + (size_t)row_off * D, D, false, actor_out.w, A, false, out, A, N, A, D, actor_out.bias);
   };
   if (discrete) {
@@ -23,7 +24,7 @@ void Engine::actor_fwd(long long row_off) {
   } else {
     float* sraw = actor_s + (size_t)row_off * A;
     run_branches({mean_branch, [&] {
-                    mlp_fwd(actor_std_mlp, actor_std_act, x, G + Z, N, row_off);
+                    mlp_fwd(actor_std_mlp, actor_std_act, x, G + Z, N, row_off, x16);
                     mm(actor_std_act.act.back() + (size_t)row_off * D, D, false, actor_std_out.w, A, false, sraw, A, N, A, D, actor_std_out.bias);
                   }});
     box_actor_fwd(cur, out, sraw, in_act_noise + (size_t)row_off * A, dr_act + (size_t)row_off * A, A, N, A);
@@ -44,6 +45,10 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
     copy_2d(s, in_dream_h0, G, dr_hz, W, N, G);
     copy_2d(s, in_dream_z0, Z, dr_hz + G, W, N, Z);
   }
+  unsigned short* hz16p = reinterpret_cast<unsigned short*>(dr_hz16);   // bf16 twin of dream.hz, written by the producers below
+  auto h16 = [&](size_t row, int col) -> void* { return hz16p ? (void*)(hz16p + row * W + col) : nullptr; };
+  auto t16 = [&](void* base, size_t off) -> void* { return base ? (void*)((unsigned short*)base + off) : nullptr; };
+  if (hz16p) to_bf16(s, dr_hz, W, hz16p, W, N, W);
   actor_fwd(0);
   for (int i = 1; i <= H; ++i) {
     const size_t prev = (size_t)(i - 1) * N, curr = (size_t)i * N, st = (size_t)(i - 1) * N;  // st: per-step buffers
@@ -51,40 +56,40 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
     float* hz_c = dr_hz + curr * W;
     // sequence model on [z_{i-1}, a_{i-1}], h_{i-1}; h_{i-1} . U runs concurrently with the pre-GRU chain
     run_branches({[&] {
-                    mm(hz_p + G, W, false, Wx.w, D, false, dr_x_pre + st * D, D, N, D, Z);
+                    mm(hz_p + G, W, false, Wx.w, D, false, dr_x_pre + st * D, D, N, D, Z, nullptr, 0.f, h16(prev, G));
                     mm(dr_act + prev * A, A, false, Wx.w + (size_t)Z * D, D, false, dr_x_pre + st * D, D, N, D, A, nullptr, 1.f);
-                    ln_silu_fwd(cur, dr_x_pre + st * D, D, Wx.g, Wx.b, dr_u + st * D, D, dr_x_mean + st, dr_x_rstd + st, 1, N, D);
-                    mm(dr_u + st * D, D, false, gru_K, 3 * G, false, dr_gx + st * 3 * G, 3 * G, N, 3 * G, D, gru_b);
+                    ln_silu_fwd(cur, dr_x_pre + st * D, D, Wx.g, Wx.b, dr_u + st * D, D, dr_x_mean + st, dr_x_rstd + st, 1, N, D, t16(dr_u16, st * D));
+                    mm(dr_u + st * D, D, false, gru_K, 3 * G, false, dr_gx + st * 3 * G, 3 * G, N, 3 * G, D, gru_b, 0.f, t16(dr_u16, st * D));
                   },
-                  [&] { mm(hz_p, W, false, gru_U, 3 * G, false, dr_gh + st * 3 * G, 3 * G, N, 3 * G, G, gru_b + 3 * G); }});
-    gru_fwd(s, dr_gx + st * 3 * G, 3 * G, dr_gh + st * 3 * G, 3 * G, hz_p, W, hz_c, W, N, G);
+                  [&] { mm(hz_p, W, false, gru_U, 3 * G, false, dr_gh + st * 3 * G, 3 * G, N, 3 * G, G, gru_b + 3 * G, 0.f, h16(prev, 0)); }});
+    gru_fwd(s, dr_gx + st * 3 * G, 3 * G, dr_gh + st * 3 * G, 3 * G, hz_p, W, hz_c, W, N, G, h16(curr, 0));
     // prior z_i ~ dynamics_predictor(h_i), straight-through sample
-    mm(hz_c, W, false, Wd.w, D, false, dr_q_pre + st * D, D, N, D, G);
-    ln_silu_fwd(s, dr_q_pre + st * D, D, Wd.g, Wd.b, dr_q_act + st * D, D, dr_q_mean + st, dr_q_rstd + st, 1, N, D);
-    mm(dr_q_act + st * D, D, false, dyn_repr.w, Z, false, dr_prior_logits + st * Z, Z, N, Z, D, dyn_repr.bias);
+    mm(hz_c, W, false, Wd.w, D, false, dr_q_pre + st * D, D, N, D, G, nullptr, 0.f, h16(curr, 0));
+    ln_silu_fwd(s, dr_q_pre + st * D, D, Wd.g, Wd.b, dr_q_act + st * D, D, dr_q_mean + st, dr_q_rstd + st, 1, N, D, t16(dr_q_act16, st * D));
+    mm(dr_q_act + st * D, D, false, dyn_repr.w, Z, false, dr_prior_logits + st * Z, Z, N, Z, D, dyn_repr.bias, 0.f, t16(dr_q_act16, st * D));
     repr_fwd(s, dr_prior_logits + st * Z, Z, dr_prior_probs + st * Z, Z, in_u_dyn + st * Zc, Zc, dr_z_idx + st * Zc, Zc,
-             hz_c + G, W, N, Zc, Zk, 1);
+             hz_c + G, W, N, Zc, Zk, 1, h16(curr, G));
     actor_fwd((long long)curr);
   }
   // heads on all (H+1)*N rows: four independent chains, run concurrently
   run_branches({
       [&] {
-        mlp_fwd(critic_mlp, critic_act, dr_hz, W, R);
-        mm(critic_act.act.back(), D, false, critic_head.w, DV3_NB, false, critic_logits, DV3_NB, R, DV3_NB, D, critic_head.bias);
+        mlp_fwd(critic_mlp, critic_act, dr_hz, W, R, 0, dr_hz16);
+        mm(critic_act.act.back(), D, false, critic_head.w, DV3_NB, false, critic_logits, DV3_NB, R, DV3_NB, D, critic_head.bias, 0.f, critic_act.act16.back());
         bucket_expectation(cur, critic_logits, DV3_NB, v_E, R);
       },
       [&] {
-        mlp_fwd(rew_mlp, dr_rew_act, dr_hz, W, R);
-        mm(dr_rew_act.act.back(), D, false, rew_head.w, DV3_NB, false, dr_rew_logits, DV3_NB, R, DV3_NB, D, rew_head.bias);
+        mlp_fwd(rew_mlp, dr_rew_act, dr_hz, W, R, 0, dr_hz16);
+        mm(dr_rew_act.act.back(), D, false, rew_head.w, DV3_NB, false, dr_rew_logits, DV3_NB, R, DV3_NB, D, rew_head.bias, 0.f, dr_rew_act.act16.back());
         bucket_expectation(cur, dr_rew_logits, DV3_NB, dr_rew_E, R);
       },
       [&] {
-        mlp_fwd(cont_mlp, dr_cont_act, dr_hz, W, R);
+        mlp_fwd(cont_mlp, dr_cont_act, dr_hz, W, R, 0, dr_hz16);
         mm(dr_cont_act.act.back(), D, false, cont_out.w, 1, false, dr_cont_logit, 1, R, 1, D, cont_out.bias);
       },
       [&] {
-        mlp_fwd(ema_mlp, ema_act, dr_hz, W, R);
-        mm(ema_act.act.back(), D, false, ema_head.w, DV3_NB, false, ema_logits, DV3_NB, R, DV3_NB, D, ema_head.bias);
+        mlp_fwd(ema_mlp, ema_act, dr_hz, W, R, 0, dr_hz16);
+        mm(ema_act.act.back(), D, false, ema_head.w, DV3_NB, false, ema_logits, DV3_NB, R, DV3_NB, D, ema_head.bias, 0.f, ema_act.act16.back());
         bucket_expectation(cur, ema_logits, DV3_NB, ema_E, R);
       }});
   // real-space rewards / continues / values, loss weights (dreamer_model.py:219-280) and lambda-returns
@@ -168,14 +173,14 @@ void Engine::actor_backward(const dv3_hparams* hp, const AcArgs& a) {
       // z_i = straight-through sample of prior(h_i)
       repr_bwd(s, dr_prior_logits + st * Z, Z, d_c + G, W, nullptr, 0, sN_Z, Z, N, Zc, Zk);
       mm(sN_Z, Z, false, dyn_repr.w, Z, true, sN_D0, D, N, D, Z);
-      ln_silu_bwd(s, sN_D0, D, dr_q_pre + st * D, D, dr_q_mean + st, dr_q_rstd + st, Wd.g, Wd.b, sN_D1, D, nullptr, nullptr, 1, N, D);
-      mm(sN_D1, D, false, Wd.w, D, true, d_c, W, N, G, D, nullptr, 1.f);
+      ln_silu_bwd(s, sN_D0, D, dr_q_pre + st * D, D, dr_q_mean + st, dr_q_rstd + st, Wd.g, Wd.b, sN_D1, D, nullptr, nullptr, 1, N, D, twin_of(sN_D1));
+      mm(sN_D1, D, false, Wd.w, D, true, d_c, W, N, G, D, nullptr, 1.f, twin_of(sN_D1));
       // h_i = GRU(pre([z_{i-1}, a_{i-1}]), h_{i-1})
       gru_bwd(s, d_c, W, dr_gx + st * 3 * G, 3 * G, dr_gh + st * 3 * G, 3 * G, hz_p, W, sN_3G0, 3 * G, sN_3G1, 3 * G, d_p, W, 1, N, G);
       run_branches({[&] {
                       mm(sN_3G0, 3 * G, false, gru_K, 3 * G, true, sN_D0, D, N, D, 3 * G);
-                      ln_silu_bwd(cur, sN_D0, D, dr_x_pre + st * D, D, dr_x_mean + st, dr_x_rstd + st, Wx.g, Wx.b, sN_D1, D, nullptr, nullptr, 1, N, D);
-                      mm(sN_D1, D, false, Wx.w, D, true, d_p + G, W, N, Z, D, nullptr, 1.f);
+                      ln_silu_bwd(cur, sN_D0, D, dr_x_pre + st * D, D, dr_x_mean + st, dr_x_rstd + st, Wx.g, Wx.b, sN_D1, D, nullptr, nullptr, 1, N, D, twin_of(sN_D1));
+                      mm(sN_D1, D, false, Wx.w, D, true, d_p + G, W, N, Z, D, nullptr, 1.f, twin_of(sN_D1));
                       mm(sN_D1, D, false, Wx.w + (size_t)Z * D, D, true, sN_A, A, N, A, D);
                     },
                     [&] { mm(sN_3G1, 3 * G, false, gru_U, 3 * G, true, d_p, W, N, G, 3 * G, nullptr, 1.f); }});

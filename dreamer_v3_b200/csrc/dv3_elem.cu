@@ -1,4 +1,6 @@
 // Elementwise, LayerNorm+SiLU, GRU cell, categorical representation kernels (fp32).
+#include <cuda_bf16.h>
+
 #include "dv3_device.cuh"
 
 namespace dv3 {
@@ -40,13 +42,33 @@ __global__ void op_2d_kernel(const float* __restrict__ src, int lds, float* __re
   }
 }
 
+// fp32 -> bf16 copy of a 2-D block (cols a multiple of 4, 8-byte aligned destination rows)
+__global__ void to_bf16_kernel(const float* __restrict__ src, int lds, __nv_bfloat16* __restrict__ dst, int ldd, long long rows, int cols4) {
+  const long long n = rows * cols4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols4; const int c = (int)(i - r * cols4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(src + r * lds + c);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o; o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(dst + r * ldd + c) = o;
+  }
+}
+__global__ void to_bf16_scalar_kernel(const float* __restrict__ src, int lds, __nv_bfloat16* __restrict__ dst, int ldd, long long rows, int cols) {
+  const long long n = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols; const int c = (int)(i - r * cols);
+    dst[r * ldd + c] = __float2bfloat16_rn(src[r * lds + c]);
+  }
+}
+
 // ---- LayerNorm + SiLU: one warp per row ----------------------------------------------------------------
 // templated on the per-lane element count so that narrow rows (conv channels, D = 24..96) do not pay for 32 predicated
 // iterations: EPL = ceil(D / 32) rounded up to a power of two
 template <int kLnMaxPerLane>
 __global__ void ln_silu_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ y, int ldy,
-                                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int sstride, long long rows, int D) {
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int sstride, long long rows, int D,
+                                   __nv_bfloat16* __restrict__ y16) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -76,7 +98,9 @@ __global__ void ln_silu_fwd_kernel(const float* __restrict__ x, int ldx, const f
       const int c = lane + 32 * i;
       if (c < D) {
         const float n = (v[i] - mean) * rstd * gamma[c] + beta[c];
-        yr[c] = n * sigmoidf_(n);
+        const float o = n * sigmoidf_(n);
+        yr[c] = o;
+        if (y16 != nullptr) y16[(size_t)r * ldy + c] = __float2bfloat16_rn(o);  // bf16 twin for the TMA-fed GEMM
       }
     }
     if (lane == 0) {
@@ -91,7 +115,8 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ dy, int lddy, const
                                    const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ dx, int lddx, float* __restrict__ dgamma,
-                                   float* __restrict__ dbeta, int sstride, long long rows, int D) {
+                                   float* __restrict__ dbeta, int sstride, long long rows, int D,
+                                   __nv_bfloat16* __restrict__ dx16) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -130,7 +155,11 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ dy, int lddy, const
 #pragma unroll
       for (int i = 0; i < kLnMaxPerLane; ++i) {
         const int c = lane + 32 * i;
-        if (c < D) dxr[c] = rstd * (dxh[i] - s1 - xh[i] * s2);
+        if (c < D) {
+          const float o = rstd * (dxh[i] - s1 - xh[i] * s2);
+          dxr[c] = o;
+          if (dx16 != nullptr) dx16[(size_t)r * lddx + c] = __float2bfloat16_rn(o);
+        }
       }
     }
   }
@@ -158,7 +187,7 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ dy, int lddy, const
 // ---- GRU cell ---------------------------------------------------------------------------------------
 __global__ void gru_fwd_kernel(float* __restrict__ gx, int ldgx, const float* __restrict__ gh, int ldgh,
                                const float* __restrict__ h_prev, int ldhp, float* __restrict__ h_out, int ldho,
-                               int M, int G) {
+                               int M, int G, __nv_bfloat16* __restrict__ h16) {
   const long long n = (long long)M * G;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / G), j = (int)(i % G);
@@ -168,7 +197,9 @@ __global__ void gru_fwd_kernel(float* __restrict__ gx, int ldgx, const float* __
     const float rg = sigmoidf_(gxr[G + j] + ghr[G + j]);
     const float c = tanhf(gxr[2 * G + j] + rg * ghr[2 * G + j]);
     const float hp = h_prev[(size_t)r * ldhp + j];
-    h_out[(size_t)r * ldho + j] = z * hp + (1.f - z) * c;
+    const float hn = z * hp + (1.f - z) * c;
+    h_out[(size_t)r * ldho + j] = hn;
+    if (h16 != nullptr) h16[(size_t)r * ldho + j] = __float2bfloat16_rn(hn);
     gxr[j] = z; gxr[G + j] = rg; gxr[2 * G + j] = c;
   }
 }
@@ -200,7 +231,8 @@ __global__ void gru_bwd_kernel(const float* __restrict__ dh, int lddh, const flo
 // ---- categorical representation: one warp per (row, categorical); lane = class -----------------------------
 __global__ void repr_fwd_kernel(const float* __restrict__ logits, int ldl, float* __restrict__ probs, int ldp,
                                 const float* __restrict__ u, int ldu, int32_t* __restrict__ idx, int ldi,
-                                float* __restrict__ z, int ldz, int M, int Zc, int Zk, int mode) {
+                                float* __restrict__ z, int ldz, int M, int Zc, int Zk, int mode,
+                                __nv_bfloat16* __restrict__ z16) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -226,6 +258,7 @@ __global__ void repr_fwd_kernel(const float* __restrict__ logits, int ldl, float
     }
     if (idx != nullptr && lane == 0) idx[(size_t)r * ldi + c] = pick;
     if (z != nullptr && act) z[(size_t)r * ldz + c * Zk + lane] = (lane == pick) ? 1.f : 0.f;
+    if (z16 != nullptr && act) z16[(size_t)r * ldz + c * Zk + lane] = __float2bfloat16_rn((lane == pick) ? 1.f : 0.f);
   }
 }
 
@@ -367,6 +400,15 @@ void zero_2d(cudaStream_t s, float* p, int rows, int cols, int ld) {
   if (ld == cols) { cudaMemsetAsync(p, 0, (size_t)rows * cols * sizeof(float), s); return; }
   op_2d_kernel<0><<<grid_for((long long)rows * cols), kThreads, 0, s>>>(nullptr, 0, p, ld, rows, cols); count_launch();
 }
+void to_bf16(cudaStream_t s, const float* src, int lds, void* dst, int ldd, long long rows, int cols) {
+  if (rows <= 0 || cols <= 0) return;
+  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
+  if (cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 8 == 0)
+    to_bf16_kernel<<<grid_for(rows * (cols / 4)), kThreads, 0, s>>>(src, lds, d, ldd, rows, cols / 4);
+  else
+    to_bf16_scalar_kernel<<<grid_for(rows * cols), kThreads, 0, s>>>(src, lds, d, ldd, rows, cols);
+  count_launch();
+}
 void copy_2d(cudaStream_t s, const float* src, int lds, float* dst, int ldd, int rows, int cols) {
   if (rows <= 0 || cols <= 0) return;
   op_2d_kernel<1><<<grid_for((long long)rows * cols), kThreads, 0, s>>>(src, lds, dst, ldd, rows, cols); count_launch();
@@ -377,10 +419,11 @@ void add_2d(cudaStream_t s, const float* src, int lds, float* dst, int ldd, int 
 }
 
 void ln_silu_fwd(cudaStream_t s, const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy,
-                 float* mean, float* rstd, int sstride, long long rows, int D) {
+                 float* mean, float* rstd, int sstride, long long rows, int D, void* y16_) {
   if (rows <= 0) return;
   const int grid = grid_for(rows, kThreads / 32, 148 * 8);
-#define DV3_LN_FWD(E_) ln_silu_fwd_kernel<E_><<<grid, kThreads, 0, s>>>(x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, D)
+  __nv_bfloat16* y16 = reinterpret_cast<__nv_bfloat16*>(y16_);
+#define DV3_LN_FWD(E_) ln_silu_fwd_kernel<E_><<<grid, kThreads, 0, s>>>(x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, D, y16)
   if (D <= 32) DV3_LN_FWD(1);
   else if (D <= 64) DV3_LN_FWD(2);
   else if (D <= 128) DV3_LN_FWD(4);
@@ -392,10 +435,11 @@ void ln_silu_fwd(cudaStream_t s, const float* x, int ldx, const float* gamma, co
 }
 void ln_silu_bwd(cudaStream_t s, const float* dy, int lddy, const float* x, int ldx, const float* mean,
                  const float* rstd, const float* gamma, const float* beta, float* dx, int lddx, float* dgamma,
-                 float* dbeta, int sstride, long long rows, int D) {
+                 float* dbeta, int sstride, long long rows, int D, void* dx16_) {
   if (rows <= 0) return;
   const int grid = grid_for(rows, kThreads / 32, 148 * 4);
-#define DV3_LN_BWD(E_) ln_silu_bwd_kernel<E_><<<grid, kThreads, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, D)
+  __nv_bfloat16* dx16 = reinterpret_cast<__nv_bfloat16*>(dx16_);
+#define DV3_LN_BWD(E_) ln_silu_bwd_kernel<E_><<<grid, kThreads, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, D, dx16)
   if (D <= 32) DV3_LN_BWD(1);
   else if (D <= 64) DV3_LN_BWD(2);
   else if (D <= 128) DV3_LN_BWD(4);
@@ -407,8 +451,9 @@ void ln_silu_bwd(cudaStream_t s, const float* dy, int lddy, const float* x, int 
 }
 
 void gru_fwd(cudaStream_t s, float* gx, int ldgx, const float* gh, int ldgh, const float* h_prev, int ldhp,
-             float* h_out, int ldho, int M, int G) {
-  gru_fwd_kernel<<<grid_for((long long)M * G), kThreads, 0, s>>>(gx, ldgx, gh, ldgh, h_prev, ldhp, h_out, ldho, M, G);
+             float* h_out, int ldho, int M, int G, void* h16) {
+  gru_fwd_kernel<<<grid_for((long long)M * G), kThreads, 0, s>>>(gx, ldgx, gh, ldgh, h_prev, ldhp, h_out, ldho, M, G,
+                                                                 reinterpret_cast<__nv_bfloat16*>(h16));
   count_launch();
 }
 void gru_bwd(cudaStream_t s, const float* dh, int lddh, const float* gates, int ldg, const float* gh, int ldgh,
@@ -419,9 +464,10 @@ void gru_bwd(cudaStream_t s, const float* dh, int lddh, const float* gates, int 
 }
 
 void repr_fwd(cudaStream_t s, const float* logits, int ldl, float* probs, int ldp, const float* u, int ldu,
-              int32_t* idx, int ldi, float* z, int ldz, int M, int Zc, int Zk, int mode) {
+              int32_t* idx, int ldi, float* z, int ldz, int M, int Zc, int Zk, int mode, void* z16) {
   if (M <= 0) return;
-  repr_fwd_kernel<<<grid_for((long long)M * Zc, kThreads / 32), kThreads, 0, s>>>(logits, ldl, probs, ldp, u, ldu, idx, ldi, z, ldz, M, Zc, Zk, mode);
+  repr_fwd_kernel<<<grid_for((long long)M * Zc, kThreads / 32), kThreads, 0, s>>>(logits, ldl, probs, ldp, u, ldu, idx, ldi, z, ldz, M, Zc, Zk, mode,
+                                                                                  reinterpret_cast<__nv_bfloat16*>(z16));
   count_launch();
 }
 void repr_bwd(cudaStream_t s, const float* logits, int ldl, const float* dz, int lddz, const float* dprobs, int lddp,

@@ -210,6 +210,15 @@ float* Engine::af(const std::string& name, std::vector<int64_t> shape, int kind)
 int32_t* Engine::ai(const std::string& name, std::vector<int64_t> shape, int kind) {
   return (int32_t*)alloc_bytes(name, (size_t)prod(shape) * 4, 1, shape, kind, -1);
 }
+void* Engine::twin_alloc(const float* base, size_t elems) {
+  if (cfg.compute_mode != 1) return nullptr;
+  void* p = alloc_bytes("", elems * 2, 0, {}, 5, -1);
+  if (!dry && base != nullptr) twins[base] = p;
+  return p;
+}
+static inline void* bf16_off(void* p, size_t elems) { return p == nullptr ? nullptr : (void*)((unsigned short*)p + elems); }
+static inline const void* bf16_off(const void* p, size_t elems) { return p == nullptr ? nullptr : (const void*)((const unsigned short*)p + elems); }
+
 MlpAct Engine::alloc_mlp_act(const std::string& name, long long rows, int L_) {
   MlpAct a;
   a.rows = rows;
@@ -217,6 +226,7 @@ MlpAct Engine::alloc_mlp_act(const std::string& name, long long rows, int L_) {
     const std::string b = name + ".l" + std::to_string(l);
     a.pre.push_back(af(b + ".pre", {rows, D}));
     a.act.push_back(af(b + ".act", {rows, D}));
+    a.act16.push_back(rows >= 128 ? twin_alloc(a.act.back(), (size_t)rows * D) : nullptr);
     a.mean.push_back(af("", {rows}));
     a.rstd.push_back(af("", {rows}));
   }
@@ -279,6 +289,7 @@ void Engine::layout() {
   gx = af("wm.gates", {Nl, 3 * G});
   gh = af("wm.gh", {Nl, 3 * G});
   hz = af("wm.hz", {Nl, G + Z});
+  if (Nl >= 128) hz16 = twin_alloc(hz, (size_t)Nl * (G + Z));
   p_pre = af("wm.p_pre", {Nl, D}); p_mean = af("", {Nl}); p_rstd = af("", {Nl});
   p_act = af("wm.p_act", {Nl, D});
   post_logits = af("wm.post_logits", {Nl, Z});
@@ -338,13 +349,17 @@ void Engine::layout() {
   sB_D0 = af("", {B, D}); sB_D1 = af("", {B, D}); sB_Z = af("", {B, Z});
   sN_D0 = af("", {Rl, D}); sN_D1 = af("", {Rl, D});
   sN_D2 = af("", {Rl, D}); sN_D3 = af("", {Rl, D}); sN_D4 = af("", {Rl, D}); sN_D5 = af("", {Rl, D});
+  for (float* sc : {sN_D0, sN_D1, sN_D2, sN_D3, sN_D4, sN_D5}) twin_alloc(sc, (size_t)Rl * D);
   // ---- dream ----
   dr_hz = af("dream.hz", {H + 1, Nl, G + Z});
+  if (Nl >= 128) dr_hz16 = twin_alloc(dr_hz, (size_t)Rl * (G + Z));
   dr_act = af("dream.actions", {H + 1, Nl, A});
   dr_x_pre = af("", {HN, D}); dr_x_mean = af("", {HN}); dr_x_rstd = af("", {HN});
   dr_u = af("", {HN, D});
+  if (Nl >= 128) dr_u16 = twin_alloc(dr_u, (size_t)HN * D);
   dr_gx = af("", {HN, 3 * G}); dr_gh = af("", {HN, 3 * G});
   dr_q_pre = af("", {HN, D}); dr_q_mean = af("", {HN}); dr_q_rstd = af("", {HN}); dr_q_act = af("", {HN, D});
+  if (Nl >= 128) dr_q_act16 = twin_alloc(dr_q_act, (size_t)HN * D);
   dr_prior_logits = af("", {HN, Z});
   dr_prior_probs = af("dream.z_prior_probs", {H, Nl, Zc, Zk});
   dr_z_idx = ai("dream.z_indices", {H, Nl, Zc});
@@ -614,8 +629,9 @@ void Engine::side_join() {
 
 // ------------------------------------------------------------------------------------------ building blocks
 void Engine::mm(const float* A_, int lda, bool ta, const float* B_, int ldb, bool tb, float* C, int ldc, int M, int N_,
-                int K, const float* bias, float beta) {
+                int K, const float* bias, float beta, const void* A16) {
   GemmArgs g{A_, lda, ta ? 1 : 0, B_, ldb, tb ? 1 : 0, C, ldc, M, N_, K, bias, beta};
+  if (A16 != nullptr && !ta && cfg.compute_mode == 1) { g.Ah = A16; g.ldah = lda; }
   if (cfg.compute_mode == 1 && !shadow_host.empty() && gemm_tc_eligible(g)) {
     // is B a (sub-block of a) weight matrix with a bf16 shadow?
     for (const ShadowDesc& d : shadow_host) {
@@ -635,16 +651,19 @@ void Engine::mm(const float* A_, int lda, bool ta, const float* B_, int ldb, boo
   gemm_dispatch(cur, g, cfg.compute_mode);
 }
 
-void Engine::mlp_fwd(const Mlp& mdl, MlpAct& a, const float* x, int ldx, long long rows, long long row_off) {
+void Engine::mlp_fwd(const Mlp& mdl, MlpAct& a, const float* x, int ldx, long long rows, long long row_off,
+                     const void* x16) {
   const float* in = x;
+  const void* in16 = x16;
   int ldin = ldx;
   for (size_t l = 0; l < mdl.layers.size(); ++l) {
     const LnLayer& ly = mdl.layers[l];
     float* pre = a.pre[l] + row_off * ly.out;
     float* act = a.act[l] + row_off * ly.out;
-    mm(in, ldin, false, ly.w, ly.out, false, pre, ly.out, (int)rows, ly.out, ly.in);
-    ln_silu_fwd(cur, pre, ly.out, ly.g, ly.b, act, ly.out, a.mean[l] + row_off, a.rstd[l] + row_off, 1, rows, ly.out);
-    in = act; ldin = ly.out;
+    void* act16 = rows >= 128 ? bf16_off(a.act16[l], (size_t)row_off * ly.out) : nullptr;
+    mm(in, ldin, false, ly.w, ly.out, false, pre, ly.out, (int)rows, ly.out, ly.in, nullptr, 0.f, in16);
+    ln_silu_fwd(cur, pre, ly.out, ly.g, ly.b, act, ly.out, a.mean[l] + row_off, a.rstd[l] + row_off, 1, rows, ly.out, act16);
+    in = act; in16 = act16; ldin = ly.out;
   }
 }
 
@@ -652,16 +671,18 @@ void Engine::mlp_bwd(const Mlp& mdl, MlpAct& a, const float* x, int ldx, float* 
                      int lddx, bool wgrad, long long rows, long long row_off) {
   float* dcur = dtop;
   float* dpre = scratch;
+  void* dpre16 = rows >= 128 ? twin_of(scratch) : nullptr;  // written by the LN backward launch, read by the dX contraction
   for (int l = (int)mdl.layers.size() - 1; l >= 0; --l) {
     const LnLayer& ly = mdl.layers[l];
     const float* pre = a.pre[l] + row_off * ly.out;
+    const bool need_dx = l > 0 || dx != nullptr;
     ln_silu_bwd(cur, dcur, ly.out, pre, ly.out, a.mean[l] + row_off, a.rstd[l] + row_off, ly.g, ly.b, dpre, ly.out,
-                wgrad ? ly.dg : nullptr, wgrad ? ly.db : nullptr, 1, rows, ly.out);
+                wgrad ? ly.dg : nullptr, wgrad ? ly.db : nullptr, 1, rows, ly.out, need_dx ? dpre16 : nullptr);
     const float* in = (l == 0) ? x : a.act[l - 1] + row_off * mdl.layers[l - 1].out;
     const int ldin = (l == 0) ? ldx : mdl.layers[l - 1].out;
     if (wgrad) mm(in, ldin, true, dpre, ly.out, false, ly.dw, ly.out, ly.in, ly.out, (int)rows, nullptr, 1.f);
-    if (l > 0) mm(dpre, ly.out, false, ly.w, ly.out, true, dcur, ly.in, (int)rows, ly.in, ly.out);
-    else if (dx != nullptr) mm(dpre, ly.out, false, ly.w, ly.out, true, dx, lddx, (int)rows, ly.in, ly.out, nullptr, 1.f);
+    if (l > 0) mm(dpre, ly.out, false, ly.w, ly.out, true, dcur, ly.in, (int)rows, ly.in, ly.out, nullptr, 0.f, dpre16);
+    else if (dx != nullptr) mm(dpre, ly.out, false, ly.w, ly.out, true, dx, lddx, (int)rows, ly.in, ly.out, nullptr, 1.f, dpre16);
   }
 }
 

@@ -35,6 +35,7 @@ struct Mlp {
 // activations of an MLP instance over `rows` rows (each [rows, D] contiguous)
 struct MlpAct {
   std::vector<float*> pre, act, mean, rstd;
+  std::vector<void*> act16;  // bf16 twins of act (tensor-core mode, rows >= 128), written by the same LN+SiLU launch
   long long rows = 0;
 };
 struct ConvLayer {  // conv / convT (+LN) weights; kernel viewed as a [krows, kcols] row-major matrix
@@ -178,9 +179,16 @@ struct Engine {
   void bind_dense(DenseLayer& d, const std::string& prefix, int in, int out, bool has_grad = true);
   MlpAct alloc_mlp_act(const std::string& name, long long rows, int L_);
 
+  // A16: bf16 twin of A (same element layout), valid only when the kernel that produced A wrote it in the same launch
   void mm(const float* A_, int lda, bool ta, const float* B_, int ldb, bool tb, float* C, int ldc, int M, int N_, int K,
-          const float* bias = nullptr, float beta = 0.f);
-  void mlp_fwd(const Mlp& m, MlpAct& a, const float* x, int ldx, long long rows, long long row_off = 0);
+          const float* bias = nullptr, float beta = 0.f, const void* A16 = nullptr);
+  void mlp_fwd(const Mlp& m, MlpAct& a, const float* x, int ldx, long long rows, long long row_off = 0,
+               const void* x16 = nullptr);
+  // ---- bf16 twins of activation buffers that feed large contractions (tensor-core mode only) ----
+  std::unordered_map<const float*, void*> twins;
+  void* twin_alloc(const float* base, size_t elems);
+  void* twin_of(const float* base) const { auto it = twins.find(base); return it == twins.end() ? nullptr : it->second; }
+  void *hz16 = nullptr, *dr_hz16 = nullptr, *dr_u16 = nullptr, *dr_q_act16 = nullptr;
   void mlp_bwd(const Mlp& m, MlpAct& a, const float* x, int ldx, float* dtop, float* scratch, float* dx, int lddx,
                bool wgrad, long long rows, long long row_off = 0);
   void dense_bwd(const DenseLayer& d, const float* x, int ldx, const float* dy, int lddy, float* dx, int lddx,

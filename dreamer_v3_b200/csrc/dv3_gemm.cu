@@ -194,6 +194,7 @@ void gemm_f32(cudaStream_t s, const GemmArgs& g) {
 
 
 void gemm_dispatch(cudaStream_t s, const GemmArgs& g, int mode) {
+  if (mode >= 1 && g.M > 0 && g.N > 0 && g.K > 0 && gemm_tma_eligible(g) && (mode == 2 || gemm_tc_eligible(g)) && gemm_tma(s, g)) return;
   if (mode == 1 && g.M > 0 && g.N > 0 && g.K > 0 && gemm_tc_eligible(g)) gemm_tc(s, g);
   else if (mode == 2 && g.M > 0 && g.N > 0 && g.K > 0) gemm_tc(s, g);  // forced (tests)
   else gemm_f32(s, g);

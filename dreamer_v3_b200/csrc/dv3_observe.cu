@@ -75,21 +75,22 @@ int Engine::observe_forward(cudaStream_t s) {
   }
   // After the scan, four independent chains over the folded B*T rows run concurrently (fork/join on auxiliary streams):
   // the prior net (world_model.py:272; its sample is discarded by the reference) and the three heads (:299-309).
+  if (hz16 != nullptr) to_bf16(s, hz, G + Z, hz16, G + Z, N, G + Z);  // bf16 twin of [h, z] for the N-row head contractions
   run_branches({
       [&] { decoder_fwd(); },
       [&] {
-        mm(hz, G + Z, false, Wd.w, D, false, q_pre, D, N, D, G);
+        mm(hz, G + Z, false, Wd.w, D, false, q_pre, D, N, D, G, nullptr, 0.f, hz16);
         ln_silu_fwd(cur, q_pre, D, Wd.g, Wd.b, q_act, D, q_mean, q_rstd, 1, N, D);
         mm(q_act, D, false, dyn_repr.w, Z, false, prior_logits, Z, N, Z, D, dyn_repr.bias);
         repr_fwd(cur, prior_logits, Z, prior_probs, Z, nullptr, 0, nullptr, 0, nullptr, 0, N, Zc, Zk, 0);
       },
       [&] {
-        mlp_fwd(rew_mlp, rew_act, hz, G + Z, N);
-        mm(rew_act.act.back(), D, false, rew_head.w, DV3_NB, false, rew_logits, DV3_NB, N, DV3_NB, D, rew_head.bias);
+        mlp_fwd(rew_mlp, rew_act, hz, G + Z, N, 0, hz16);
+        mm(rew_act.act.back(), D, false, rew_head.w, DV3_NB, false, rew_logits, DV3_NB, N, DV3_NB, D, rew_head.bias, 0.f, rew_act.act16.back());
         bucket_expectation(cur, rew_logits, DV3_NB, rew_E, N);
       },
       [&] {
-        mlp_fwd(cont_mlp, cont_act, hz, G + Z, N);
+        mlp_fwd(cont_mlp, cont_act, hz, G + Z, N, 0, hz16);
         mm(cont_act.act.back(), D, false, cont_out.w, 1, false, cont_logit, 1, N, 1, D, cont_out.bias);
       }});
   return 0;

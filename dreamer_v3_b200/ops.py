@@ -112,6 +112,33 @@ def gemm_weight_shadow(A, W, ta=False, bias=None, C_=None, beta=0.0):
     return run
 
 
+def to_bf16(x):
+    """bf16 copy of a 2-D fp32 CUDA tensor, made by the library's conversion kernel."""
+    x = _f32(x)
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _ok(_lib.load().dv3_op_to_bf16(_p(x), x.stride(0), _p(out), out.stride(0), x.shape[0], x.shape[1], _s()), "dv3_op_to_bf16")
+    return out
+
+
+def gemm_bf16(A16, W, bias=None, C_=None, beta=0.0):
+    """C = A16 W with A16 [M, K] bf16 (as written by the producer kernels in tensor-core mode) and W [K, N] fp32 whose
+    bf16 K-major shadow is built here; `run` launches the TMA-fed tcgen05 kernel only."""
+    assert A16.dtype == torch.bfloat16 and A16.dim() == 2 and A16.stride(1) == 1
+    Wh = W.t().contiguous().to(torch.bfloat16)  # [N, K]
+    M, K = A16.shape
+    N = W.shape[1]
+    assert W.shape[0] == K and K % 8 == 0
+    if C_ is None:
+        C_ = torch.zeros((M, N), dtype=torch.float32, device=A16.device)
+
+    def run():
+        _ok(_lib.load().dv3_op_gemm_bf16(_p(A16), A16.stride(0), _p(Wh), K, _p(C_), C_.stride(0), M, N, K, _p(bias), beta,
+                                         _s()), "dv3_op_gemm_bf16")
+        return C_
+    run.keepalive = Wh
+    return run
+
+
 def ln_silu(x, gamma, beta):
     x = _f32(x)
     y = torch.empty_like(x)

@@ -73,3 +73,24 @@ def test_gemm_tc_weight_shadow_variant(M, N, K):
         assert float((got - (want + bias.double())).abs().max()) <= tol, (M, N, K, ta)
         got = ops.gemm_weight_shadow(A.cuda(), W.cuda(), ta=ta, C_=C0.cuda(), beta=1.0)().cpu().double()
         assert float((got - (want + C0.double())).abs().max()) <= tol, (M, N, K, ta, "beta")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (1024, 768, 256), (1000, 252, 264), (16384, 256, 1280), (130, 24, 72),
+                                   (1024, 1024, 256), (4096, 512, 48), (300, 128, 1096), (20000, 1024, 512), (1024, 256, 4096)])
+def test_gemm_tma_variant(M, N, K):
+    """TMA-fed persistent kernel (csrc/dv3_gemm_tma.cu): both operands bf16 K-major in global memory. Ragged M/N/K,
+    bias + accumulate epilogues, split-K, several tiles per CTA (double-buffered TMEM accumulator)."""
+    from dreamer_v3_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(K, N, generator=g)
+    bias = torch.randn(N, generator=g)
+    C0 = torch.randn(M, N, generator=g)
+    A16 = ops.to_bf16(A.cuda())
+    assert torch.equal(A16.cpu(), A.bfloat16())
+    want = A.bfloat16().double() @ W.bfloat16().double()
+    tol = 2e-5 * np.sqrt(K) * 8
+    got = ops.gemm_bf16(A16, W.cuda(), bias=bias.cuda())().cpu().double()
+    assert float((got - (want + bias.double())).abs().max()) <= tol, (M, N, K)
+    got = ops.gemm_bf16(A16, W.cuda(), C_=C0.cuda(), beta=1.0)().cpu().double()
+    assert float((got - (want + C0.double())).abs().max()) <= tol, (M, N, K, "beta")

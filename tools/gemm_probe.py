@@ -12,15 +12,30 @@ ta, tb = (int(sys.argv[5]), int(sys.argv[6])) if len(sys.argv) > 6 else (0, 0)
 A = torch.randn((K, M) if ta else (M, K), device="cuda")
 B = torch.randn((N, K) if tb else (K, N), device="cuda")
 C = torch.empty(M, N, device="cuda")
-run = (lambda: ops.gemm(A, B, bool(ta), bool(tb), C_=C, mode=mode)) if mode != 3 else ops.gemm_weight_shadow(A, B, bool(ta), C_=C)
+if mode == 4:   # TMA-fed kernel: A in bf16 (as the producer kernels write it), B as bf16 shadow
+    run = ops.gemm_bf16(ops.to_bf16(A), B, C_=C)
+elif mode == 3:
+    run = ops.gemm_weight_shadow(A, B, bool(ta), C_=C)
+else:
+    run = lambda: ops.gemm(A, B, bool(ta), bool(tb), C_=C, mode=mode)  # noqa: E731
 for _ in range(3):
     run()
 torch.cuda.synchronize()
-s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-s.record()
-for _ in range(10):
+# back-to-back replays of a captured graph: launch overhead of the Python / ctypes call is not in the number
+REPS = 20
+st = torch.cuda.Stream()
+with torch.cuda.stream(st):
     run()
-t.record()
-torch.cuda.synchronize()
-ms = s.elapsed_time(t) / 10
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr, stream=st):
+        for _ in range(REPS):
+            run()
+    gr.replay()
+    torch.cuda.synchronize()
+    s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    gr.replay()
+    t.record()
+    torch.cuda.synchronize()
+ms = s.elapsed_time(t) / REPS
 print(f"gemm {M}x{N}x{K} mode {mode} ta={ta} tb={tb}: {ms * 1e3:.1f} us, {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
