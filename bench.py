@@ -42,7 +42,7 @@ GFLOP_PER_UPDATE = {"c1": 150.0, "c2": 235.0, "c3": 827.0, "c4": 2319.0, "L": 35
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel from the committed ncu --set full
 # capture (profiles/), keyed by (M, K, N, mode); None when no capture exists for the shape
-TRAFFIC_BYTES = {(16384, 1280, 256, 1): 84589568 + 3871232,   # profiles/r01_gemm_tc_ws_ncu.txt
+TRAFFIC_BYTES = {(16384, 1280, 256, 1): None,   # filled from profiles/r01_gemm_tma_ncu.txt
                  (16384, 1280, 256, 0): None}
 
 
@@ -329,33 +329,46 @@ def run_ours(args):
 
 
 def measure_roofline(e, cfg, pk, args):
-    """Dominant kernel of the update = the GEMM behind the dream-rollout / head contractions ((H+1)*N rows).
-    Timed live with CUDA events on the launching stream, same kernel and shape as inside the step:
-    the first-layer head GEMM [R, G+Z] x [G+Z, D] (run 4x forward + backward per update)."""
+    """Dominant kernel class of the update = the contractions over the (H+1)*N dream rows (heads forward / backward).
+    Timed live with CUDA events on the launching stream, same kernel and shape as inside the step: the first-layer head
+    GEMM [R, G+Z] x [G+Z, D]. In tensor-core mode that is the TMA-fed tcgen05 kernel on the bf16 twin of [h, z] (written by
+    the producer kernels) and the bf16 weight shadow. The launches rotate over operand sets larger than L2 together, and
+    are replayed from a CUDA graph so that the Python launch overhead is not in the per-launch time."""
     from dreamer_v3_b200 import ops
     R, K, Nn = (cfg.H + 1) * cfg.N, cfg.G + cfg.Z, cfg.D
-    A = torch.randn(R, K, device="cuda")
     Bm = torch.randn(K, Nn, device="cuda")
-    C = torch.empty(R, Nn, device="cuda")
-    # mode 1: exactly the variant the engine runs for a weight operand (bf16 K-major shadow, built outside the timing)
-    run = ops.gemm_weight_shadow(A, Bm, C_=C) if args.mode == 1 else (lambda: ops.gemm(A, Bm, C_=C, mode=0))
-    for _ in range(3):
-        run()
-    torch.cuda.synchronize()
-    reps = 20
-    s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(reps):
-        run()
-    t.record()
-    torch.cuda.synchronize()
+    a_bytes = R * K * (2 if args.mode == 1 else 4)
+    nset = max(2, int(np.ceil(160e6 / (a_bytes + 4.0 * R * Nn))))       # > 126 MB L2 across the rotation
+    runs = []
+    for _ in range(nset):
+        A = torch.randn(R, K, device="cuda")
+        C = torch.empty(R, Nn, device="cuda")
+        runs.append(ops.gemm_bf16(ops.to_bf16(A), Bm, C_=C) if args.mode == 1 else (lambda A=A, C=C: ops.gemm(A, Bm, C_=C, mode=0)))
+        del A
+    reps = 5 * nset
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for r in runs:
+            r()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=st):
+            for i in range(reps):
+                runs[i % nset]()
+        gr.replay()
+        torch.cuda.synchronize()
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        gr.replay()
+        t.record()
+        torch.cuda.synchronize()
     ms = s.elapsed_time(t) / reps
     flops = 2.0 * R * K * Nn
     ach = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": f"gemm [{R}x{K}]x[{K}x{Nn}] ({'fp32 SIMT' if args.mode == 0 else 'bf16 tcgen05'})",
+    return {"bound": "tensor", "kernel": f"gemm [{R}x{K}]x[{K}x{Nn}] ({'fp32 SIMT' if args.mode == 0 else 'bf16 tcgen05, TMA-fed (gemm_tma_kernel)'})",
             "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"], "traffic": TRAFFIC_BYTES.get((R, K, Nn, args.mode)),
-            "algorithmic_bytes": 4.0 * R * K + (2.0 if args.mode == 1 else 4.0) * K * Nn + 4.0 * R * Nn,
-            "peak_source": pk["src"] + " (burst, kernel timed alone)", "ms_per_launch": ms}
+            "algorithmic_bytes": float(a_bytes) + (2.0 if args.mode == 1 else 4.0) * K * Nn + 4.0 * R * Nn,
+            "peak_source": pk["src"] + " (burst, kernel timed alone)", "ms_per_launch": ms,
+            "l2": f"{nset} operand sets rotated ({nset * (a_bytes + 4 * R * Nn) / 1e6:.0f} MB > L2)", "launches_timed": reps}
 
 
 def cpu_baseline(wid):

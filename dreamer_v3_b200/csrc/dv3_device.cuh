@@ -17,9 +17,14 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 // fast variants for the latency-critical persistent scan kernels (ex2.approx based, rel. error ~1e-6: far inside the
 // 1e-4 parity budget, and nothing integer-valued depends on them)
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float ex2_ftz(float x) {   // single MUFU.EX2, no denormal fix-up branches
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + ex2_ftz(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_fast(float x) {
-  const float e = __expf(-2.f * fabsf(x));
+  const float e = ex2_ftz(-2.8853900817779268f * fabsf(x));
   const float t = __fdividef(1.f - e, 1.f + e);
   return x < 0.f ? -t : t;
 }

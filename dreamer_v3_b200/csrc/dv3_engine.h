@@ -85,6 +85,7 @@ struct Engine {
   int32_t* z0_idx;
   float *Wt_zq, *Wt_post_h, *Ut, *Kt, *Wt_pre_z, *dp_act_all, *du_all, *dh_tot;
   unsigned long long* scan_stamps = nullptr;
+  unsigned int* scan_bar = nullptr;   // [2] grid-barrier counters of the persistent scan kernels (fwd, bwd)
   int scan_bwd_ctas = 0;
   int scan_ctas = 0;          // > 0: persistent cooperative scan kernels are usable with this many CTAs
   bool use_persistent = true;

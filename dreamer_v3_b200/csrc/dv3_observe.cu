@@ -51,6 +51,7 @@ int Engine::observe_forward(cudaStream_t s) {
     sp.gx_raw = gx_raw; sp.gates = gx; sp.gh = gh; sp.hz = hz; sp.p_pre = p_pre; sp.p_mean = p_mean; sp.p_rstd = p_rstd;
     sp.p_act = p_act; sp.post_logits = post_logits; sp.post_probs = post_probs; sp.z_idx = z_idx;
     sp.stamps = std::getenv("DV3_SCAN_STAMPS") ? scan_stamps : nullptr;
+    sp.bar = scan_bar;
     cudaError_t ce = launch_observe_scan_fwd(s, sp, scan_ctas);
     if (ce != cudaSuccess) return fail(std::string("observe scan launch: ") + cudaGetErrorString(ce));
   } else
@@ -142,7 +143,7 @@ int Engine::wm_loss_backward(cudaStream_t s) {
     bp.is_first = in_is_first; bp.post_logits = post_logits; bp.dpost = dpost; bp.p_pre = p_pre; bp.p_mean = p_mean;
     bp.p_rstd = p_rstd; bp.gates = gx; bp.gh = gh; bp.h_in = h_in; bp.x_pre = x_pre; bp.x_mean = x_mean; bp.x_rstd = x_rstd;
     bp.d_hz = d_hz; bp.dlogits = dpost_logits; bp.dp_act = dp_act_all; bp.dp_pre = dp_pre; bp.dh_tot = dh_tot;
-    bp.dgx = dgx; bp.dgh = dgh; bp.dh_in = dh_in; bp.du = du_all; bp.dx_pre = dx_pre;
+    bp.dgx = dgx; bp.dgh = dgh; bp.dh_in = dh_in; bp.du = du_all; bp.dx_pre = dx_pre; bp.bar = scan_bar + 32;
     cudaError_t ce = launch_observe_scan_bwd(s, bp, scan_bwd_ctas);
     if (ce != cudaSuccess) return fail(std::string("observe scan bwd launch: ") + cudaGetErrorString(ce));
     // LayerNorm gain / offset gradients of the two in-loop layers, one N-row pass each

@@ -1,7 +1,7 @@
 // Persistent RSSM observe-scan kernels (world_model.py:244-273 and its BPTT): ONE cooperative launch walks all T
 // timesteps; the grid synchronises between the dependent stages of a step instead of returning to the host.
 //
-// Forward, per step t (4 grid syncs):
+// Forward, per step t (4 grid barriers):
 //   A  x_pre = actW[t] + sum_c W_pre[c*Zk + idx_in[c]]        one-hot z -> row gather, no 1024-deep contraction
 //      (+ materialise the masked inputs h_in / z_in of world_model.py:246-250 for the backward pass)
 //   B  gx    = SiLU(LN(x_pre)) . K + b0                        LayerNorm applied on the fly by the consumer
@@ -12,8 +12,6 @@
 // streamed from L2 (they are re-read every step by the same CTAs and stay L2 resident up to size L); activations
 // of the step are staged in shared memory in [k][row] order so one LDS.128 feeds four FMAs.
 #include "dv3_scan_common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace dv3 {
 namespace {
@@ -51,7 +49,7 @@ __device__ __forceinline__ void row_stats(Smem& sm, const float (&x)[4], int D, 
 __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-  cg::grid_group grid = cg::this_grid();
+  unsigned int bar_target = 0;
   const int B = p.B, T = p.T, G = p.G, D = p.D, Z = p.Z, Zc = p.Zc, Zk = p.Zk, E = p.E;
   const int W = G + Z;
   const int nblk = gridDim.x, blk = blockIdx.x;
@@ -97,7 +95,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
     }
     __syncthreads();
   }
-  grid.sync();
+  grid_bar(p.bar, bar_target);
   auto stamp = [&](int i) {
     if (p.stamps != nullptr && blk == 0 && threadIdx.x == 0) {
       unsigned long long v;
@@ -106,6 +104,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
     }
   };
   stamp(0);
+  if (p.stamps != nullptr) g_ln_dbg = p.stamps + T * 8 + 4;
 
   for (int t = 0; t < T; ++t) {
     // ===== stage A (row owners): x_pre = actW + gather-sum of W_pre rows, LayerNorm + SiLU -> u; masked inputs =====
@@ -154,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
       }
     }
     stamp(t * 8 + 1);
-    grid.sync();
+    grid_bar(p.bar, bar_target);
     stamp(t * 8 + 2);
 
     // ===== stage B: gx = u . K + b0 for 8 units x 3 gates per task, then the GRU cell -> h_t =====
@@ -178,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
       __syncthreads();
     }
     stamp(t * 8 + 3);
-    grid.sync();
+    grid_bar(p.bar, bar_target);
     stamp(t * 8 + 4);
 
     // ===== stage C: p_pre += h . W_post[E:];  gh(t+1) = h_in(t+1) . U + b1 =====
@@ -212,38 +211,26 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
       }
     }
     stamp(t * 8 + 5);
-    grid.sync();
+    grid_bar(p.bar, bar_target);
 
-    // ===== stage D0 (row owners): p_act = SiLU(LN(p_pre)) =====
-    for (int b = blk; b < B; b += nblk) {
-      const size_t bt = (size_t)b * T + t;
-      float x[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int d = threadIdx.x + kThreads * i;
-        x[i] = d < D ? __ldcg(p.p_pre + bt * D + d) : 0.f;
-      }
-      float mean, rstd;
-      row_stats(sm, x, D, mean, rstd);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int d = threadIdx.x + kThreads * i;
-        if (d < D) {
-          const float n = (x[i] - mean) * rstd * p.post_g[d] + p.post_b[d];
-          p.p_act[bt * D + d] = n * sigmoid_fast(n);
-        }
-      }
-      if (threadIdx.x == 0) { p.p_mean[bt] = mean; p.p_rstd[bt] = rstd; }
-    }
-    grid.sync();
     stamp(t * 8 + 6);
 
-    // ===== stage D: logits = p_act . W_zq + b -> unimix probs, sample z_t =====
+    // ===== stage D: p_act = SiLU(LN(p_pre)) by every task CTA itself (one warp per row, staged straight into shared
+    // memory; the first CTA also writes p_act / mean / rstd out for the backward pass), logits = p_act . W_zq + b
+    // -> unimix probs, sample z_t =====
     for (int task = blk; task < tasks_Z; task += nblk) {
       const int c0 = task * 32;
-      auto pa_of = [&](int b, int k) { return __ldcg(p.p_act + ((size_t)b * T + t) * D + k); };
-      if (cached) task_gemv(sm, wc_D, 32, 0, 32, D, B, pa_of);
-      else task_gemv(sm, p.W_zq, Z, c0, Z, D, B, pa_of);
+      float* in_s = &sm.in_chunk[0][0][0];
+      const bool writer = task == 0;
+      cta_ln_silu_stage(in_s, p.p_pre + (size_t)t * D, (size_t)T * D, p.post_g, p.post_b, B, D,
+                        writer ? p.p_act + (size_t)t * D : nullptr, (size_t)T * D, p.p_mean + t, p.p_rstd + t, (size_t)T);
+      stamp(t * 8 + 7);
+      float acc[kRows];
+#pragma unroll
+      for (int b = 0; b < kRows; ++b) acc[b] = 0.f;
+      if (cached) gemv_acc<32>(acc, in_s, wc_D, 32, lane, D);
+      else gemv_acc<32>(acc, in_s, p.W_zq, Z, (c0 + lane) < Z ? c0 + lane : -1, D);
+      gemv_finish<32>(sm, acc);
       for (int e = threadIdx.x; e < B * 32; e += kThreads) {
         const int b = e >> 5, j = e & 31;
         if (c0 + j < Z) {
@@ -273,8 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
       }
       __syncthreads();
     }
-    stamp(t * 8 + 7);
-    grid.sync();
+    grid_bar(p.bar, bar_target);
     stamp(t * 8 + 8);
   }
 }
@@ -300,6 +286,7 @@ cudaError_t launch_observe_scan_fwd(cudaStream_t s, const ScanFwdParams& p, int 
   pp.cache_weights = fits ? 1 : 0;
   const size_t smem = sizeof(Smem) + (fits ? cache : 0);
   cudaFuncSetAttribute(observe_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaMemsetAsync(pp.bar, 0, sizeof(unsigned int), s);
   void* args[] = {&pp};
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)observe_scan_fwd_kernel, dim3(ctas), dim3(kThreads), args, smem, s);
   if (e == cudaSuccess) count_launch();

@@ -32,6 +32,7 @@ struct ScanFwdParams {
   float* p_mean; float* p_rstd; float* p_act;
   float* post_logits; float* post_probs; int32_t* z_idx;
   int cache_weights;           // set by the launcher: weight tiles resident in shared memory
+  unsigned int* bar;           // grid-barrier counter (zeroed by the launcher)
   unsigned long long* stamps;  // optional [T*5+1] globaltimer stamps of CTA 0 (debug / profiling), may be null
 };
 
@@ -59,6 +60,7 @@ struct ScanBwdParams {
   float* dh_in;      // [B, T, G]
   float* du;         // [B, T, D]  grad w.r.t. SiLU(LN(x_pre))
   float* dx_pre;     // [B, T, D]
+  unsigned int* bar; // grid-barrier counter (zeroed by the launcher)
 };
 
 size_t scan_fwd_smem_bytes();

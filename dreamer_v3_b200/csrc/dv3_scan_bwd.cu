@@ -1,19 +1,17 @@
 // Reverse-time BPTT through the RSSM observe scan as ONE cooperative launch (replaces the ~700 per-op launches of
 // the reverse loop in Engine::wm_loss_backward). Only input gradients are on the recurrence; every weight gradient
-// is a single N-row contraction after the kernel. Per step t (T-1 .. 0), 6 short grid-synchronised stages:
-//   R2   dp_act = dlogits[t] . W_zq^T                                       (32-column tasks, K split over 8 warps)
-//   R3a  dp_pre = LN'SiLU'(dp_act)                                          (row owners: one CTA per sequence)
-//   R3   dh_tot = d_hz[t].h + dp_pre . W_post[E:]^T, GRU gate gradients dgx / dgh of the task's 32 units
-//   R4   dh_in  = dh_tot*z + dgh . U^T ;  du = dgx . K^T
-//   R5a  dx_pre = LN'SiLU'(du);  d_hz[t-1].h += (1 - is_first[t]) dh_in     (row owners)
-//   R5   dz_in  = dx_pre . W_pre[:Z]^T;  d_hz[t-1].z += (1 - is_first[t]) dz_in, then the straight-through / KL
-//        backward of the posterior categoricals of step t-1 right away (dlogits[t-1]) -- no separate stage for it.
-// Stage inputs are published to global memory by their producer and staged by plain copies, so no CTA recomputes
-// another CTA's non-linearities. The contractions read TRANSPOSED weight copies (refreshed once per update) so that
-// weight reads stay coalesced.
+// is a single N-row contraction after the kernel. Per step t (T-1 .. 0), 4 stages separated by grid barriers:
+//   S1  dp_act = dlogits[t] . W_zq^T                                 (narrow column tasks: the K = Z contraction is the
+//                                                                      longest of the step, so it is spread over many CTAs)
+//   S2  dp_pre = LN'SiLU'(dp_act) recomputed by every task CTA (one warp per row, staged in shared memory);
+//       dh_tot = d_hz[t].h + dp_pre . W_post[E:]^T, GRU gate gradients dgx / dgh of the task's units
+//   S3  dh_in  = dh_tot*z + dgh . U^T  (and d_hz[t-1].h += (1 - is_first[t]) dh_in);  du = dgx . K^T
+//   S4  dx_pre = LN'SiLU'(du) recomputed per task CTA; dz_in = dx_pre . W_pre[:Z]^T; d_hz[t-1].z += (1 - is_first[t]) dz_in,
+//       then the straight-through / KL backward of the posterior categoricals of step t-1 right away (dlogits[t-1]).
+// The LayerNorm backward needs whole-row statistics; instead of a separate row-owner stage (one more barrier) every
+// consumer CTA redoes it for the 16 rows from data it has to stage anyway. The contractions read TRANSPOSED weight
+// copies (refreshed once per update) so that weight reads stay coalesced.
 #include "dv3_scan_common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace dv3 {
 namespace {
@@ -22,7 +20,7 @@ using namespace scan;
 
 // d(SiLU(LN(x)))/dx helpers: n = xhat*g + b ; dn = dy * silu'(n)
 __device__ __forceinline__ float silu_grad(float n) {
-  const float sg = sigmoidf_(n);
+  const float sg = sigmoid_fast(n);
   return sg * (1.f + n * (1.f - sg));
 }
 
@@ -43,87 +41,157 @@ __device__ __forceinline__ void repr_bwd_pair(const ScanBwdParams& p, int b, int
   if (act) p.dlogits[bt * Z + col] = pr * (g - dot);
 }
 
-// Row-owner LayerNorm+SiLU backward of one row: dy/x held as up to 4 values per thread (d = tid + 256 i < D).
-__device__ __forceinline__ void row_lnbwd(Smem& sm, const float (&dy)[4], const float (&x)[4], float mean, float rstd,
-                                          const float* __restrict__ gamma, const float* __restrict__ beta, int D, float (&dx)[4]) {
+// LayerNorm+SiLU backward of rows b < B by the whole CTA (one warp per row, NR rows per warp at once): dy row b at
+// dy + b*ld (read through L2), x likewise; the result is staged as in_s[d][b] for the contraction that follows and
+// optionally written out. All global loads are issued before the first reduction (the grid barrier invalidates L1).
+template <int EPL, int NR>
+__device__ __forceinline__ void cta_lnbwd_stage_t(float* in_s, const float* dy, const float* x, size_t ld, const float* mean,
+                                                  const float* rstd, size_t lds, const float* __restrict__ gamma,
+                                                  const float* __restrict__ beta, int B, int D, float* out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* red = &sm.red[0][0][0];
-  float xh[4], dxh[4];
-  float a1 = 0.f, a2 = 0.f;
+  for (int bb = warp; bb < kRows; bb += kWarps * NR) {
+    float xh[NR][EPL], dxh[NR][EPL], g[EPL], be[EPL], mu[NR], rs[NR];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int d = threadIdx.x + kThreads * i;
-    if (d < D) {
-      xh[i] = (x[i] - mean) * rstd;
-      const float g = gamma[d];
-      dxh[i] = dy[i] * silu_grad(xh[i] * g + beta[d]) * g;
-      a1 += dxh[i]; a2 += dxh[i] * xh[i];
-    } else { xh[i] = 0.f; dxh[i] = 0.f; }
+    for (int r = 0; r < NR; ++r) {
+      const int b = bb + r * kWarps;
+      mu[r] = b < B ? mean[(size_t)b * lds] : 0.f;
+      rs[r] = b < B ? rstd[(size_t)b * lds] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int c = lane + 32 * i;
+      const bool ok = c < D;
+      g[i] = ok ? gamma[c] : 0.f;
+      be[i] = ok ? beta[c] : 0.f;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const int b = bb + r * kWarps;
+        xh[r][i] = (ok && b < B) ? x[(size_t)b * ld + c] : 0.f;
+        dxh[r][i] = (ok && b < B) ? __ldcg(dy + (size_t)b * ld + c) : 0.f;
+      }
+    }
+    asm volatile("" ::: "memory");   // keep every load of the pass ahead of the reductions
+    float s1[NR], s2[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        const float xhat = (xh[r][i] - mu[r]) * rs[r];
+        const float d = dxh[r][i] * silu_grad(xhat * g[i] + be[i]) * g[i];   // 0 beyond D (g = 0) and beyond B (dy = 0)
+        xh[r][i] = xhat; dxh[r][i] = d;
+        a1 += d; a2 += d * xhat;
+      }
+      s1[r] = a1; s2[r] = a2;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        s1[r] += __shfl_xor_sync(0xffffffffu, s1[r], o);
+        s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int b = bb + r * kWarps;
+      if (b >= kRows) continue;
+      const float m1 = s1[r] / (float)D, m2 = s2[r] / (float)D;
+#pragma unroll
+      const bool row_ok = b < B, wr = out != nullptr && row_ok;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        const int c = lane + 32 * i;
+        const float o = row_ok ? rs[r] * (dxh[r][i] - m1 - xh[r][i] * m2) : 0.f;
+        if (c < D) in_s[(size_t)c * kInLd + b] = o;
+        if (wr && c < D) out[(size_t)b * ld + c] = o;
+      }
+    }
   }
-  a1 = warp_sum(a1); a2 = warp_sum(a2);
-  if (lane == 0) { red[warp] = a1; red[kWarps + warp] = a2; }
   __syncthreads();
-  float s1 = 0.f, s2 = 0.f;
+}
+__device__ __forceinline__ void cta_lnbwd_stage(float* in_s, const float* dy, const float* x, size_t ld, const float* mean,
+                                                const float* rstd, size_t lds, const float* __restrict__ gamma,
+                                                const float* __restrict__ beta, int B, int D, float* out) {
+  if (D <= 256) cta_lnbwd_stage_t<8, 2>(in_s, dy, x, ld, mean, rstd, lds, gamma, beta, B, D, out);
+  else if (D <= 512) cta_lnbwd_stage_t<16, 2>(in_s, dy, x, ld, mean, rstd, lds, gamma, beta, B, D, out);
+  else cta_lnbwd_stage_t<32, 1>(in_s, dy, x, ld, mean, rstd, lds, gamma, beta, B, D, out);
+}
+
+// columns per task of a contraction with `ncols` outputs: the narrowest of 32 / 16 / 8 that still gives every CTA work
+__device__ __forceinline__ int pick_cw(int ncols, int nblk) {
+  if ((ncols + 31) / 32 * 2 > nblk) return 32;
+  if ((ncols + 15) / 16 * 2 > nblk) return 16;
+  return 8;
+}
+
+// out_tile = in(b, 0..K) . Wt[:, c0 .. c0+CW): K staged in chunks of kStageK
+template <int CW, class InFn>
+__device__ __forceinline__ void task_contract(Smem& sm, const float* __restrict__ Wt, int ldw, int c0, int ncols, int K, int B, InFn in_fn) {
+  const int lane = threadIdx.x & 31;
+  float* in_s = &sm.in_chunk[0][0][0];
+  const int c = c0 + (lane % CW);
+  float acc[kRows];
 #pragma unroll
-  for (int w = 0; w < kWarps; ++w) { s1 += red[w]; s2 += red[kWarps + w]; }
-  s1 /= (float)D; s2 /= (float)D;
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) dx[i] = rstd * (dxh[i] - s1 - xh[i] * s2);
+  for (int b = 0; b < kRows; ++b) acc[b] = 0.f;
+  for (int kc = 0; kc < K; kc += kStageK) {
+    const int kn = min(kStageK, K - kc);
+    stage_rows(in_s, kn, B, [&](int b, int k) { return in_fn(b, kc + k); });
+    gemv_acc<CW>(acc, in_s, Wt + (size_t)kc * ldw, ldw, c < ncols ? c : -1, kn);
+    __syncthreads();
+  }
+  gemv_finish<CW>(sm, acc);
+}
+template <class InFn>
+__device__ __forceinline__ void task_contract_cw(Smem& sm, int cw, const float* __restrict__ Wt, int ldw, int c0, int ncols, int K, int B, InFn in_fn) {
+  if (cw == 32) task_contract<32>(sm, Wt, ldw, c0, ncols, K, B, in_fn);
+  else if (cw == 16) task_contract<16>(sm, Wt, ldw, c0, ncols, K, B, in_fn);
+  else task_contract<8>(sm, Wt, ldw, c0, ncols, K, B, in_fn);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-  cg::grid_group grid = cg::this_grid();
+  unsigned int bar_target = 0;
   const int B = p.B, T = p.T, G = p.G, D = p.D, Z = p.Z, Zc = p.Zc, Zk = p.Zk;
   const int W = G + Z;
   const int nblk = gridDim.x, blk = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gtid = blk * kThreads + threadIdx.x, gthreads = nblk * kThreads;
   const int gwarp = gtid >> 5, gwarps = gthreads >> 5;
-  const int tasks_G = (G + 31) / 32, tasks_D = (D + 31) / 32, tasks_Z = (Z + 31) / 32;
+  const int tasks_G = (G + 31) / 32, tasks_Z = (Z + 31) / 32;
+  const int cw1 = pick_cw(D, nblk), ntask1 = (D + cw1 - 1) / cw1;                 // S1: D output columns
+  const int cw3 = pick_cw(G + D, nblk), nt3g = (G + cw3 - 1) / cw3, nt3d = (D + cw3 - 1) / cw3;   // S3: G + D output columns
+  float* in_s = &sm.in_chunk[0][0][0];
 
   // prologue: dlogits of the last step (no recurrent contribution yet)
   for (int pr = gwarp; pr < B * Zc; pr += gwarps) repr_bwd_pair(p, pr / Zc, T - 1, pr % Zc, lane);
-  grid.sync();
+  grid_bar(p.bar, bar_target);
 
   for (int t = T - 1; t >= 0; --t) {
-    // ===== R2: dp_act = dlogits[t] . W_zq^T   (Wt_zq [Z, D]) =====
-    for (int task = blk; task < tasks_D; task += nblk) {
-      const int c0 = task * 32;
-      task_gemv(sm, p.Wt_zq, D, c0, D, Z, B, [&](int b, int k) { return __ldcg(p.dlogits + ((size_t)b * T + t) * Z + k); });
-      for (int e = threadIdx.x; e < B * 32; e += kThreads) {
-        const int b = e >> 5, j = e & 31;
+    // ===== S1: dp_act = dlogits[t] . W_zq^T   (Wt_zq [Z, D]) =====
+    for (int task = blk; task < ntask1; task += nblk) {
+      const int c0 = task * cw1;
+      task_contract_cw(sm, cw1, p.Wt_zq, D, c0, D, Z, B, [&](int b, int k) { return __ldcg(p.dlogits + ((size_t)b * T + t) * Z + k); });
+      for (int e = threadIdx.x; e < B * cw1; e += kThreads) {
+        const int b = e / cw1, j = e % cw1;
         if (c0 + j < D) p.dp_act[((size_t)b * T + t) * D + c0 + j] = sm.tile[b][j];
       }
       __syncthreads();
     }
-    grid.sync();
+    grid_bar(p.bar, bar_target);
 
-    // ===== R3a (row owners): dp_pre = LN'SiLU'(dp_act) =====
-    for (int b = blk; b < B; b += nblk) {
-      const size_t bt = (size_t)b * T + t;
-      float dy[4], x[4], dx[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int d = threadIdx.x + kThreads * i;
-        dy[i] = d < D ? __ldcg(p.dp_act + bt * D + d) : 0.f;
-        x[i] = d < D ? p.p_pre[bt * D + d] : 0.f;
-      }
-      row_lnbwd(sm, dy, x, p.p_mean[bt], p.p_rstd[bt], p.post_g, p.post_b, D, dx);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int d = threadIdx.x + kThreads * i;
-        if (d < D) p.dp_pre[bt * D + d] = dx[i];
-      }
-    }
-    grid.sync();
-
-    // ===== R3: dh_tot = d_hz[t].h + dp_pre . W_post_h^T (Wt_post_h [D, G]); GRU gate gradients for the task's 32 units =====
+    // ===== S2: dp_pre = LN'SiLU'(dp_act) (per task CTA); dh_tot = d_hz[t].h + dp_pre . W_post_h^T (Wt_post_h [D, G]);
+    //       GRU gate gradients for the task's 32 units =====
     for (int task = blk; task < tasks_G; task += nblk) {
       const int c0 = task * 32;
-      task_gemv(sm, p.Wt_post_h, G, c0, G, D, B, [&](int b, int k) { return __ldcg(p.dp_pre + ((size_t)b * T + t) * D + k); });
+      cta_lnbwd_stage(in_s, p.dp_act + (size_t)t * D, p.p_pre + (size_t)t * D, (size_t)T * D, p.p_mean + t, p.p_rstd + t, (size_t)T,
+                      p.post_g, p.post_b, B, D, task == 0 ? p.dp_pre + (size_t)t * D : nullptr);
+      float acc[kRows];
+#pragma unroll
+      for (int b = 0; b < kRows; ++b) acc[b] = 0.f;
+      gemv_acc<32>(acc, in_s, p.Wt_post_h, G, (c0 + lane) < G ? c0 + lane : -1, D);
+      gemv_finish<32>(sm, acc);
       for (int e = threadIdx.x; e < B * 32; e += kThreads) {
         const int b = e >> 5, jj = e & 31, j = c0 + jj;
         if (j < G) {
@@ -143,85 +211,67 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
       }
       __syncthreads();
     }
-    grid.sync();
+    grid_bar(p.bar, bar_target);
 
-    // ===== R4: dh_in = dh_tot * z + dgh . U^T (Ut [3G, G]);  du = dgx . K^T (Kt [3G, D]) =====
-    {
-      const int ntask = tasks_G + tasks_D;
-      for (int task = blk; task < ntask; task += nblk) {
-        if (task < tasks_G) {
-          const int c0 = task * 32;
-          task_gemv(sm, p.Ut, G, c0, G, 3 * G, B, [&](int b, int k) { return __ldcg(p.dgh + ((size_t)b * T + t) * 3 * G + k); });
-          for (int e = threadIdx.x; e < B * 32; e += kThreads) {
-            const int b = e >> 5, j = e & 31;
-            if (c0 + j < G) {
-              const size_t bt = (size_t)b * T + t;
-              p.dh_in[bt * G + c0 + j] = sm.tile[b][j] + __ldcg(p.dh_tot + (size_t)b * G + c0 + j) * p.gates[bt * 3 * G + c0 + j];
+    // ===== S3: dh_in = dh_tot * z + dgh . U^T (Ut [3G, G]), passed on to d_hz[t-1].h;  du = dgx . K^T (Kt [3G, D]) =====
+    for (int task = blk; task < nt3g + nt3d; task += nblk) {
+      if (task < nt3g) {
+        const int c0 = task * cw3;
+        task_contract_cw(sm, cw3, p.Ut, G, c0, G, 3 * G, B, [&](int b, int k) { return __ldcg(p.dgh + ((size_t)b * T + t) * 3 * G + k); });
+        for (int e = threadIdx.x; e < B * cw3; e += kThreads) {
+          const int b = e / cw3, j = c0 + e % cw3;
+          if (j < G) {
+            const size_t bt = (size_t)b * T + t;
+            const float v = sm.tile[b][e % cw3] + __ldcg(p.dh_tot + (size_t)b * G + j) * p.gates[bt * 3 * G + j];
+            p.dh_in[bt * G + j] = v;
+            if (t > 0) {
+              float* dst = p.d_hz + (bt - 1) * W + j;
+              *dst = __ldcg(dst) + (1.f - p.is_first[bt]) * v;
             }
           }
-          __syncthreads();
-        } else {
-          const int c0 = (task - tasks_G) * 32;
-          task_gemv(sm, p.Kt, D, c0, D, 3 * G, B, [&](int b, int k) { return __ldcg(p.dgx + ((size_t)b * T + t) * 3 * G + k); });
-          for (int e = threadIdx.x; e < B * 32; e += kThreads) {
-            const int b = e >> 5, j = e & 31;
-            if (c0 + j < D) p.du[((size_t)b * T + t) * D + c0 + j] = sm.tile[b][j];
-          }
-          __syncthreads();
-        }
-      }
-    }
-    grid.sync();
-
-    // ===== R5a (row owners): dx_pre = LN'SiLU'(du); h part of the recurrent gradient: d_hz[t-1].h += (1 - f_t) dh_in[t] =====
-    for (int b = blk; b < B; b += nblk) {
-      const size_t bt = (size_t)b * T + t;
-      float dy[4], x[4], dx[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int d = threadIdx.x + kThreads * i;
-        dy[i] = d < D ? __ldcg(p.du + bt * D + d) : 0.f;
-        x[i] = d < D ? p.x_pre[bt * D + d] : 0.f;
-      }
-      row_lnbwd(sm, dy, x, p.x_mean[bt], p.x_rstd[bt], p.pre_g, p.pre_b, D, dx);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int d = threadIdx.x + kThreads * i;
-        if (d < D) p.dx_pre[bt * D + d] = dx[i];
-      }
-      if (t > 0) {
-        const float keep = 1.f - p.is_first[bt];
-        for (int j = threadIdx.x; j < G; j += kThreads) {
-          float* dst = p.d_hz + (bt - 1) * W + j;
-          *dst = __ldcg(dst) + keep * __ldcg(p.dh_in + bt * G + j);
-        }
-      }
-    }
-    grid.sync();
-
-    // ===== R5: dz_in = dx_pre . W_pre[:Z]^T (Wt_pre_z [D, Z]); pass to step t-1 and run its posterior repr backward =====
-    if (t > 0) {
-      for (int task = blk; task < tasks_Z; task += nblk) {
-        const int c0 = task * 32;
-        task_gemv(sm, p.Wt_pre_z, Z, c0, Z, D, B, [&](int b, int k) { return __ldcg(p.dx_pre + ((size_t)b * T + t) * D + k); });
-        for (int e = threadIdx.x; e < B * 32; e += kThreads) {
-          const int b = e >> 5, j = e & 31;
-          if (c0 + j < Z) {
-            const size_t bt = (size_t)b * T + t;
-            float* dst = p.d_hz + (bt - 1) * W + G + c0 + j;
-            *dst = __ldcg(dst) + (1.f - p.is_first[bt]) * sm.tile[b][j];
-          }
         }
         __syncthreads();
-        const int cats = 32 / Zk;
-        for (int pr = warp; pr < B * cats; pr += kWarps) {
-          const int b = pr / cats, cat = c0 / Zk + pr % cats;
-          if (cat < Zc) repr_bwd_pair(p, b, t - 1, cat, lane);
+      } else {
+        const int c0 = (task - nt3g) * cw3;
+        task_contract_cw(sm, cw3, p.Kt, D, c0, D, 3 * G, B, [&](int b, int k) { return __ldcg(p.dgx + ((size_t)b * T + t) * 3 * G + k); });
+        for (int e = threadIdx.x; e < B * cw3; e += kThreads) {
+          const int b = e / cw3, j = c0 + e % cw3;
+          if (j < D) p.du[((size_t)b * T + t) * D + j] = sm.tile[b][e % cw3];
         }
         __syncthreads();
       }
     }
-    grid.sync();
+    grid_bar(p.bar, bar_target);
+
+    // ===== S4: dx_pre = LN'SiLU'(du) (per task CTA); dz_in = dx_pre . W_pre[:Z]^T (Wt_pre_z [D, Z]); pass to step t-1 and
+    //       run its posterior repr backward. At t = 0 only dx_pre is needed (weight gradients). =====
+    for (int task = blk; task < (t > 0 ? tasks_Z : 1); task += nblk) {
+      const int c0 = task * 32;
+      cta_lnbwd_stage(in_s, p.du + (size_t)t * D, p.x_pre + (size_t)t * D, (size_t)T * D, p.x_mean + t, p.x_rstd + t, (size_t)T,
+                      p.pre_g, p.pre_b, B, D, task == 0 ? p.dx_pre + (size_t)t * D : nullptr);
+      if (t == 0) break;
+      float acc[kRows];
+#pragma unroll
+      for (int b = 0; b < kRows; ++b) acc[b] = 0.f;
+      gemv_acc<32>(acc, in_s, p.Wt_pre_z, Z, (c0 + lane) < Z ? c0 + lane : -1, D);
+      gemv_finish<32>(sm, acc);
+      for (int e = threadIdx.x; e < B * 32; e += kThreads) {
+        const int b = e >> 5, j = e & 31;
+        if (c0 + j < Z) {
+          const size_t bt = (size_t)b * T + t;
+          float* dst = p.d_hz + (bt - 1) * W + G + c0 + j;
+          *dst = __ldcg(dst) + (1.f - p.is_first[bt]) * sm.tile[b][j];
+        }
+      }
+      __syncthreads();
+      const int cats = 32 / Zk;
+      for (int pr = warp; pr < B * cats; pr += kWarps) {
+        const int b = pr / cats, cat = c0 / Zk + pr % cats;
+        if (cat < Zc) repr_bwd_pair(p, b, t - 1, cat, lane);
+      }
+      __syncthreads();
+    }
+    if (t > 0) grid_bar(p.bar, bar_target);
   }
 }
 
@@ -260,6 +310,7 @@ int scan_bwd_max_ctas(int device) {
 cudaError_t launch_observe_scan_bwd(cudaStream_t s, const ScanBwdParams& p, int ctas) {
   cudaFuncSetAttribute(observe_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
   ScanBwdParams pp = p;
+  cudaMemsetAsync(pp.bar, 0, sizeof(unsigned int), s);
   void* args[] = {&pp};
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)observe_scan_bwd_kernel, dim3(ctas), dim3(kThreads), args, sizeof(Smem), s);
   if (e == cudaSuccess) count_launch();

@@ -125,5 +125,178 @@ __device__ __forceinline__ void cta_ln_stats(Smem& sm, const float* x, int ldx, 
 }
 
 
+
+// ---- grid-wide barrier for the cooperative (co-resident) scan kernels --------------------------------------------
+// One monotonically increasing counter in global memory (zeroed by the host before the launch): every CTA adds 1 and
+// spins until the count reaches its next multiple of gridDim.x. Cheaper than cooperative_groups' grid.sync() (one
+// fence + one atomic + an acquire-load spin by a single thread per CTA). Data exchanged across the barrier is read
+// with __ldcg (L2), never through L1.
+__device__ __forceinline__ void grid_bar(unsigned int* ctr, unsigned int& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned int v, spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (++spins > (1u << 24)) { printf("dv3 scan: grid barrier timed out (block %d)\n", blockIdx.x); __trap(); }
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+// ---- contraction on activations already staged CTA-wide as in_s[k][kInLd] (k < K <= kStageK) -----------------------
+// CW output columns per task (lane % CW), the 32 / CW lane groups and the 8 warps split K. Accumulates into acc[16].
+constexpr int kStageK = kWarps * kKC;   // k lines that fit the staging buffer (in_chunk viewed as [kStageK][kInLd])
+
+template <int CW>
+__device__ __forceinline__ void gemv_acc(float (&acc)[kRows], const float* in_s, const float* __restrict__ W, int ldw, int col, int K) {
+  constexpr int NPH = 32 / CW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ks = (K + kWarps - 1) / kWarps;
+  const int k0 = warp * ks + lane / CW, k1 = min(K, (warp + 1) * ks);
+  const bool col_ok = col >= 0;
+  const float* wp = W + (col_ok ? col : 0);
+  for (int kk0 = k0; kk0 < k1; kk0 += 8 * NPH) {
+    float wv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int k = kk0 + j * NPH; wv[j] = (col_ok && k < k1) ? wp[(size_t)k * ldw] : 0.f; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = min(kk0 + j * NPH, k1 - 1);
+      const float4* iv = reinterpret_cast<const float4*>(in_s + (size_t)k * kInLd);
+      const float4 a0 = iv[0], a1 = iv[1], a2 = iv[2], a3 = iv[3];
+      const float w_ = wv[j];
+      acc[0] = fmaf(a0.x, w_, acc[0]); acc[1] = fmaf(a0.y, w_, acc[1]); acc[2] = fmaf(a0.z, w_, acc[2]); acc[3] = fmaf(a0.w, w_, acc[3]);
+      acc[4] = fmaf(a1.x, w_, acc[4]); acc[5] = fmaf(a1.y, w_, acc[5]); acc[6] = fmaf(a1.z, w_, acc[6]); acc[7] = fmaf(a1.w, w_, acc[7]);
+      acc[8] = fmaf(a2.x, w_, acc[8]); acc[9] = fmaf(a2.y, w_, acc[9]); acc[10] = fmaf(a2.z, w_, acc[10]); acc[11] = fmaf(a2.w, w_, acc[11]);
+      acc[12] = fmaf(a3.x, w_, acc[12]); acc[13] = fmaf(a3.y, w_, acc[13]); acc[14] = fmaf(a3.z, w_, acc[14]); acc[15] = fmaf(a3.w, w_, acc[15]);
+    }
+  }
+}
+// Reduces the lane groups and the 8 warps: sm.tile[b][j], j < CW (all threads synchronised on return).
+template <int CW>
+__device__ __forceinline__ void gemv_finish(Smem& sm, float (&acc)[kRows]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int off = 16; off >= CW; off >>= 1) {
+#pragma unroll
+    for (int b = 0; b < kRows; ++b) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], off);
+  }
+  if (lane < CW) {
+#pragma unroll
+    for (int b = 0; b < kRows; ++b) sm.red[warp][b][lane] = acc[b];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < kRows * CW; e += kThreads) {
+    const int b = e / CW, j = e % CW;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += sm.red[w][b][j];
+    sm.tile[b][j] = s;
+  }
+  __syncthreads();
+}
+// CTA-wide staging of in(b, k), k < K <= kStageK, into in_s[k][b] (rows >= B zero); lanes run along k (coalesced reads)
+template <class InFn>
+__device__ __forceinline__ void stage_rows(float* in_s, int K, int B, InFn in_fn) {
+  for (int k = threadIdx.x; k < K; k += kThreads) {
+    float v[kRows];
+#pragma unroll
+    for (int b = 0; b < kRows; ++b) v[b] = (b < B) ? in_fn(b, k) : 0.f;
+    float4* dst = reinterpret_cast<float4*>(in_s + (size_t)k * kInLd);
+    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+    dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+  }
+  __syncthreads();
+}
+
+// Forward LayerNorm + SiLU of rows b < B (x row b at x + b*ldx, read through L2), one warp per row, result staged as
+// in_s[d][b] for the contraction that follows; optionally also written out (act / mean / rstd, row b at + b*ldo / b*lds).
+// Every global load of the pass (NR rows per warp at once, gain and offset) is issued before the first reduction: the
+// grid barrier invalidates L1, so each dependent load would cost a full L2 round trip.
+__device__ unsigned long long* g_ln_dbg = nullptr;   // debug: per-phase globaltimer stamps of the LN pass (CTA 0, thread 0)
+#define DV3_LN_DBG(i_) do { if (g_ln_dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long v_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v_)); g_ln_dbg[i_] = v_; } } while (0)
+template <int EPL, int NR>
+__device__ __forceinline__ void cta_ln_silu_stage_t(float* in_s, const float* x, size_t ldx, const float* __restrict__ gamma,
+                                                    const float* __restrict__ beta, int B, int D, float* act_out, size_t ldo,
+                                                    float* mean_out, float* rstd_out, size_t lds) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int bb = warp; bb < kRows; bb += kWarps * NR) {
+    float v[NR][EPL], g[EPL], be[EPL];
+    DV3_LN_DBG(0);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int c = lane + 32 * i;
+      const bool ok = c < D;
+      g[i] = ok ? gamma[c] : 0.f;
+      be[i] = ok ? beta[c] : 0.f;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const int b = bb + r * kWarps;
+        v[r][i] = (ok && b < B) ? __ldcg(x + (size_t)b * ldx + c) : 0.f;
+      }
+    }
+    asm volatile("" ::: "memory");   // keep every load of the pass ahead of the reductions
+    float mean[NR], rstd[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) s += v[r][i];
+      mean[r] = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+    }
+    DV3_LN_DBG(1);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      mean[r] /= (float)D;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) { const float d = (lane + 32 * i < D) ? v[r][i] - mean[r] : 0.f; q += d * d; }
+      rstd[r] = q;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+    }
+    DV3_LN_DBG(2);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int b = bb + r * kWarps;
+      if (b >= kRows) continue;
+      rstd[r] = rsqrtf(rstd[r] / (float)D + DV3_LN_EPS);
+      const bool row_ok = b < B, wr = act_out != nullptr && row_ok;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {   // branch-free: columns beyond D have g = be = 0 -> o = 0, only the stores are predicated
+        const int c = lane + 32 * i;
+        const float n = (v[r][i] - mean[r]) * rstd[r] * g[i] + be[i];
+        const float o = row_ok ? n * sigmoid_fast(n) : 0.f;
+        if (c < D) in_s[(size_t)c * kInLd + b] = o;
+        if (wr && c < D) act_out[(size_t)b * ldo + c] = o;
+      }
+      if (act_out != nullptr && lane == 0 && b < B) { mean_out[(size_t)b * lds] = mean[r]; rstd_out[(size_t)b * lds] = rstd[r]; }
+    }
+    DV3_LN_DBG(3);
+  }
+  __syncthreads();
+  DV3_LN_DBG(4);
+}
+__device__ __forceinline__ void cta_ln_silu_stage(float* in_s, const float* x, size_t ldx, const float* __restrict__ gamma,
+                                                  const float* __restrict__ beta, int B, int D, float* act_out, size_t ldo,
+                                                  float* mean_out, float* rstd_out, size_t lds) {
+  if (D <= 256) cta_ln_silu_stage_t<8, 2>(in_s, x, ldx, gamma, beta, B, D, act_out, ldo, mean_out, rstd_out, lds);
+  else if (D <= 512) cta_ln_silu_stage_t<16, 2>(in_s, x, ldx, gamma, beta, B, D, act_out, ldo, mean_out, rstd_out, lds);
+  else cta_ln_silu_stage_t<32, 2>(in_s, x, ldx, gamma, beta, B, D, act_out, ldo, mean_out, rstd_out, lds);
+}
+
 }  // namespace scan
 }  // namespace dv3

@@ -29,3 +29,6 @@ names = ["A work", "A sync", "B work", "B sync", "C work", "Csync+D0+sync", "D w
 ex = None
 
 print("per-step mean us:", {n: round(float(d[2:, i].mean()), 2) for i, n in enumerate(names)}, "step total", round(float(d[2:].sum(1).mean()), 2))
+
+dbg = st[T * 8 + 4: T * 8 + 9].astype(np.float64)
+print("LN pass phases of the last step (us): loads+sum", (dbg[1] - dbg[0]) / 1e3, "var", (dbg[2] - dbg[1]) / 1e3, "write", (dbg[3] - dbg[2]) / 1e3, "sync", (dbg[4] - dbg[3]) / 1e3)
