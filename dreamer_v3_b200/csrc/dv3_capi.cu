@@ -64,6 +64,7 @@ void dv3_default_hparams(dv3_hparams* hp) {
 int dv3_sync(dv3_engine* h, void* stream) {
   cudaError_t err = cudaStreamSynchronize(S(stream));
   if (err != cudaSuccess) return h->e.fail(std::string("cudaStreamSynchronize: ") + cudaGetErrorString(err));
+  h->e.phase_dump();
   return 0;
 }
 

@@ -74,7 +74,7 @@ void gru_fwd(cudaStream_t s, float* gx, int ldgx, const float* gh, int ldgh, con
 // overwritten or accumulated).
 void gru_bwd(cudaStream_t s, const float* dh, int lddh, const float* gates, int ldg, const float* gh, int ldgh,
              const float* h_prev, int ldhp, float* dgx, int lddgx, float* dgh, int lddgh, float* dh_prev, int lddhp,
-             int accumulate_dh_prev, int M, int G);
+             int accumulate_dh_prev, int M, int G, void* dgx16 = nullptr, void* dgh16 = nullptr);  // bf16 twins, same ld
 
 // RepresentationLayer (components/representation_layer.py:73-113): logits [M, Zc*Zk] -> unimixed probs,
 // optional sample (u [M,Zc] row stride ldu) -> idx [M,Zc] + one-hot z (row stride ldz). mode: 0 = probs only,
@@ -83,7 +83,7 @@ void repr_fwd(cudaStream_t s, const float* logits, int ldl, float* probs, int ld
               int32_t* idx, int ldi, float* z, int ldz, int M, int Zc, int Zk, int mode, void* z16 = nullptr);
 // dlogits = J_softmax^T (0.99 * (dz + dprobs)); dz / dprobs nullable.
 void repr_bwd(cudaStream_t s, const float* logits, int ldl, const float* dz, int lddz, const float* dprobs, int lddp,
-              float* dlogits, int lddl, int M, int Zc, int Zk);
+              float* dlogits, int lddl, int M, int Zc, int Zk, void* dl16 = nullptr);
 
 // observe-scan helpers
 // Builds the masked recurrent inputs of step t (world_model.py:246-253).

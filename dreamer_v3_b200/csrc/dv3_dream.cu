@@ -49,7 +49,9 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
   auto h16 = [&](size_t row, int col) -> void* { return hz16p ? (void*)(hz16p + row * W + col) : nullptr; };
   auto t16 = [&](void* base, size_t off) -> void* { return base ? (void*)((unsigned short*)base + off) : nullptr; };
   if (hz16p) to_bf16(s, dr_hz, W, hz16p, W, N, W);
+  phase_mark("dream.begin");
   actor_fwd(0);
+  phase_mark("dream.actor");
   for (int i = 1; i <= H; ++i) {
     const size_t prev = (size_t)(i - 1) * N, curr = (size_t)i * N, st = (size_t)(i - 1) * N;  // st: per-step buffers
     const float* hz_p = dr_hz + prev * W;
@@ -62,14 +64,18 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
                     mm(dr_u + st * D, D, false, gru_K, 3 * G, false, dr_gx + st * 3 * G, 3 * G, N, 3 * G, D, gru_b, 0.f, t16(dr_u16, st * D));
                   },
                   [&] { mm(hz_p, W, false, gru_U, 3 * G, false, dr_gh + st * 3 * G, 3 * G, N, 3 * G, G, gru_b + 3 * G, 0.f, h16(prev, 0)); }});
+    phase_mark("dream.pre+gx|gh");
     gru_fwd(s, dr_gx + st * 3 * G, 3 * G, dr_gh + st * 3 * G, 3 * G, hz_p, W, hz_c, W, N, G, h16(curr, 0));
+    phase_mark("dream.gru");
     // prior z_i ~ dynamics_predictor(h_i), straight-through sample
     mm(hz_c, W, false, Wd.w, D, false, dr_q_pre + st * D, D, N, D, G, nullptr, 0.f, h16(curr, 0));
     ln_silu_fwd(s, dr_q_pre + st * D, D, Wd.g, Wd.b, dr_q_act + st * D, D, dr_q_mean + st, dr_q_rstd + st, 1, N, D, t16(dr_q_act16, st * D));
     mm(dr_q_act + st * D, D, false, dyn_repr.w, Z, false, dr_prior_logits + st * Z, Z, N, Z, D, dyn_repr.bias, 0.f, t16(dr_q_act16, st * D));
     repr_fwd(s, dr_prior_logits + st * Z, Z, dr_prior_probs + st * Z, Z, in_u_dyn + st * Zc, Zc, dr_z_idx + st * Zc, Zc,
              hz_c + G, W, N, Zc, Zk, 1, h16(curr, G));
+    phase_mark("dream.prior");
     actor_fwd((long long)curr);
+    phase_mark("dream.actor");
   }
   // heads on all (H+1)*N rows: four independent chains, run concurrently
   run_branches({
@@ -92,12 +98,14 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
         mm(ema_act.act.back(), D, false, ema_head.w, DV3_NB, false, ema_logits, DV3_NB, R, DV3_NB, D, ema_head.bias, 0.f, ema_act.act16.back());
         bucket_expectation(cur, ema_logits, DV3_NB, ema_E, R);
       }});
+  phase_mark("dream.heads");
   // real-space rewards / continues / values, loss weights (dreamer_model.py:219-280) and lambda-returns
   AcArgs a{};
   a.H = H; a.N = N; a.A = A; a.discrete = discrete; a.gamma = gamma; a.lambda_ = 0.95f;
   a.rew_E = dr_rew_E; a.cont_logit = dr_cont_logit; a.v_E = v_E; a.ema_E = ema_E; a.is_terminated = in_is_term;
   a.r = ac_r; a.c = ac_c; a.w = ac_w; a.v = ac_v; a.targets = ac_targets;
   ac_value_targets(s, a);
+  phase_mark("dream.targets");
   return 0;
 }
 
@@ -127,7 +135,9 @@ int Engine::ac_loss_backward(const dv3_hparams* hp, int phase, cudaStream_t s) {
   l.L_critic_HB = L_critic_HB; l.L_val_HB = L_val_HB; l.L_reg_HB = L_reg_HB; l.targets_symlog = targets_symlog;
   l.L_actor_HB = L_actor_HB; l.logp_HB = logp_HB; l.scaled_HB = scaled_HB; l.ent_HB = ent_HB;
   l.L_reinf_HB = L_reinf_HB; l.L_ent_HB = L_ent_HB; l.scalars = ac_scalars;
+  phase_mark("ac.begin");
   ac_losses(s, l);
+  phase_mark("ac.losses");
 
   // ---- critic: gradient only reaches the fast critic's own weights (train_one_step.py:197-200). The chain is independent
   // of everything the actor needs, so it runs on an auxiliary stream next to the whole actor backward. ----
@@ -139,7 +149,9 @@ int Engine::ac_loss_backward(const dv3_hparams* hp, int phase, cudaStream_t s) {
   if (!hp->train_actor) { critic_chain(); return 0; }
   side_run(critic_chain);
   actor_backward(hp, a);
+  phase_mark("ac.actor_mlps_bwd");
   side_join();
+  phase_mark("ac.join_critic");
   return 0;
 }
 
@@ -165,26 +177,29 @@ void Engine::actor_backward(const dv3_hparams* hp, const AcArgs& a) {
     bucket_expectation_bwd(s, critic_logits, DV3_NB, dv_E, dr_dlogits255, DV3_NB, R);
     dense_bwd(critic_head, nullptr, 0, dr_dlogits255, DV3_NB, sN_D0, D, 0.f, false, R);
     mlp_bwd(critic_mlp, critic_act, dr_hz, W, sN_D0, sN_D1, d_dr_hz, W, false, R);
+    phase_mark("ac.heads_dx");
     for (int i = H; i >= 1; --i) {
       const size_t prev = (size_t)(i - 1) * N, curr = (size_t)i * N, st = (size_t)(i - 1) * N;
       float* d_c = d_dr_hz + curr * W;
       float* d_p = d_dr_hz + prev * W;
       const float* hz_p = dr_hz + prev * W;
       // z_i = straight-through sample of prior(h_i)
-      repr_bwd(s, dr_prior_logits + st * Z, Z, d_c + G, W, nullptr, 0, sN_Z, Z, N, Zc, Zk);
-      mm(sN_Z, Z, false, dyn_repr.w, Z, true, sN_D0, D, N, D, Z);
+      repr_bwd(s, dr_prior_logits + st * Z, Z, d_c + G, W, nullptr, 0, sN_Z, Z, N, Zc, Zk, twin_of(sN_Z));
+      mm(sN_Z, Z, false, dyn_repr.w, Z, true, sN_D0, D, N, D, Z, nullptr, 0.f, twin_of(sN_Z));
       ln_silu_bwd(s, sN_D0, D, dr_q_pre + st * D, D, dr_q_mean + st, dr_q_rstd + st, Wd.g, Wd.b, sN_D1, D, nullptr, nullptr, 1, N, D, twin_of(sN_D1));
       mm(sN_D1, D, false, Wd.w, D, true, d_c, W, N, G, D, nullptr, 1.f, twin_of(sN_D1));
       // h_i = GRU(pre([z_{i-1}, a_{i-1}]), h_{i-1})
-      gru_bwd(s, d_c, W, dr_gx + st * 3 * G, 3 * G, dr_gh + st * 3 * G, 3 * G, hz_p, W, sN_3G0, 3 * G, sN_3G1, 3 * G, d_p, W, 1, N, G);
+      gru_bwd(s, d_c, W, dr_gx + st * 3 * G, 3 * G, dr_gh + st * 3 * G, 3 * G, hz_p, W, sN_3G0, 3 * G, sN_3G1, 3 * G, d_p, W, 1, N, G,
+              twin_of(sN_3G0), twin_of(sN_3G1));
       run_branches({[&] {
-                      mm(sN_3G0, 3 * G, false, gru_K, 3 * G, true, sN_D0, D, N, D, 3 * G);
+                      mm(sN_3G0, 3 * G, false, gru_K, 3 * G, true, sN_D0, D, N, D, 3 * G, nullptr, 0.f, twin_of(sN_3G0));
                       ln_silu_bwd(cur, sN_D0, D, dr_x_pre + st * D, D, dr_x_mean + st, dr_x_rstd + st, Wx.g, Wx.b, sN_D1, D, nullptr, nullptr, 1, N, D, twin_of(sN_D1));
                       mm(sN_D1, D, false, Wx.w, D, true, d_p + G, W, N, Z, D, nullptr, 1.f, twin_of(sN_D1));
                       mm(sN_D1, D, false, Wx.w + (size_t)Z * D, D, true, sN_A, A, N, A, D);
                     },
-                    [&] { mm(sN_3G1, 3 * G, false, gru_U, 3 * G, true, d_p, W, N, G, 3 * G, nullptr, 1.f); }});
+                    [&] { mm(sN_3G1, 3 * G, false, gru_U, 3 * G, true, d_p, W, N, G, 3 * G, nullptr, 1.f, twin_of(sN_3G1)); }});
       box_actor_bwd(s, actor_logits + prev * A, actor_s + prev * A, in_act_noise + prev * A, sN_A, A, dmu + prev * A, ds + prev * A, N, A);
+      phase_mark("ac.bptt_step");
     }
   }
   // actor MLPs: inputs were stop-gradient'ed (dreamer_model.py:179-180), so only weight gradients; the mean and the std

@@ -207,7 +207,8 @@ __global__ void gru_fwd_kernel(float* __restrict__ gx, int ldgx, const float* __
 __global__ void gru_bwd_kernel(const float* __restrict__ dh, int lddh, const float* __restrict__ gates, int ldg,
                                const float* __restrict__ gh, int ldgh, const float* __restrict__ h_prev, int ldhp,
                                float* __restrict__ dgx, int lddgx, float* __restrict__ dgh, int lddgh,
-                               float* __restrict__ dh_prev, int lddhp, int accumulate, int M, int G) {
+                               float* __restrict__ dh_prev, int lddhp, int accumulate, int M, int G,
+                               __nv_bfloat16* __restrict__ dgx16, __nv_bfloat16* __restrict__ dgh16) {
   const long long n = (long long)M * G;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / G), j = (int)(i % G);
@@ -223,6 +224,13 @@ __global__ void gru_bwd_kernel(const float* __restrict__ dh, int lddh, const flo
     float* b = dgh + (size_t)r * lddgh;
     a[j] = dz; a[G + j] = dr; a[2 * G + j] = dc;
     b[j] = dz; b[G + j] = dr; b[2 * G + j] = dc * rg;
+    if (dgx16 != nullptr) {   // bf16 twins for the two input-gradient contractions that follow
+      __nv_bfloat16* a16 = dgx16 + (size_t)r * lddgx;
+      __nv_bfloat16* b16 = dgh16 + (size_t)r * lddgh;
+      const __nv_bfloat16 hz_ = __float2bfloat16_rn(dz), hr = __float2bfloat16_rn(dr);
+      a16[j] = hz_; a16[G + j] = hr; a16[2 * G + j] = __float2bfloat16_rn(dc);
+      b16[j] = hz_; b16[G + j] = hr; b16[2 * G + j] = __float2bfloat16_rn(dc * rg);
+    }
     float* o = dh_prev + (size_t)r * lddhp + j;
     if (accumulate) *o += d * z; else *o = d * z;
   }
@@ -264,7 +272,7 @@ __global__ void repr_fwd_kernel(const float* __restrict__ logits, int ldl, float
 
 __global__ void repr_bwd_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ dz, int lddz,
                                 const float* __restrict__ dprobs, int lddp, float* __restrict__ dlogits, int lddl,
-                                int M, int Zc, int Zk) {
+                                int M, int Zc, int Zk, __nv_bfloat16* __restrict__ dl16) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -285,7 +293,11 @@ __global__ void repr_bwd_kernel(const float* __restrict__ logits, int ldl, const
       g *= 0.99f;
     }
     const float dot = warp_sum(g * p);
-    if (act) dlogits[(size_t)r * lddl + col] = p * (g - dot);
+    if (act) {
+      const float o = p * (g - dot);
+      dlogits[(size_t)r * lddl + col] = o;
+      if (dl16 != nullptr) dl16[(size_t)r * lddl + col] = __float2bfloat16_rn(o);
+    }
   }
 }
 
@@ -458,8 +470,9 @@ void gru_fwd(cudaStream_t s, float* gx, int ldgx, const float* gh, int ldgh, con
 }
 void gru_bwd(cudaStream_t s, const float* dh, int lddh, const float* gates, int ldg, const float* gh, int ldgh,
              const float* h_prev, int ldhp, float* dgx, int lddgx, float* dgh, int lddgh, float* dh_prev, int lddhp,
-             int accumulate_dh_prev, int M, int G) {
-  gru_bwd_kernel<<<grid_for((long long)M * G), kThreads, 0, s>>>(dh, lddh, gates, ldg, gh, ldgh, h_prev, ldhp, dgx, lddgx, dgh, lddgh, dh_prev, lddhp, accumulate_dh_prev, M, G);
+             int accumulate_dh_prev, int M, int G, void* dgx16, void* dgh16) {
+  gru_bwd_kernel<<<grid_for((long long)M * G), kThreads, 0, s>>>(dh, lddh, gates, ldg, gh, ldgh, h_prev, ldhp, dgx, lddgx, dgh, lddgh, dh_prev, lddhp, accumulate_dh_prev, M, G,
+                                                                 reinterpret_cast<__nv_bfloat16*>(dgx16), reinterpret_cast<__nv_bfloat16*>(dgh16));
   count_launch();
 }
 
@@ -471,9 +484,9 @@ void repr_fwd(cudaStream_t s, const float* logits, int ldl, float* probs, int ld
   count_launch();
 }
 void repr_bwd(cudaStream_t s, const float* logits, int ldl, const float* dz, int lddz, const float* dprobs, int lddp,
-              float* dlogits, int lddl, int M, int Zc, int Zk) {
+              float* dlogits, int lddl, int M, int Zc, int Zk, void* dl16) {
   if (M <= 0) return;
-  repr_bwd_kernel<<<grid_for((long long)M * Zc, kThreads / 32), kThreads, 0, s>>>(logits, ldl, dz, lddz, dprobs, lddp, dlogits, lddl, M, Zc, Zk);
+  repr_bwd_kernel<<<grid_for((long long)M * Zc, kThreads / 32), kThreads, 0, s>>>(logits, ldl, dz, lddz, dprobs, lddp, dlogits, lddl, M, Zc, Zk, reinterpret_cast<__nv_bfloat16*>(dl16));
   count_launch();
 }
 

@@ -2,6 +2,8 @@
 // MLP / dense / conv building blocks. The hot-path orchestration lives in dv3_observe.cu and dv3_dream.cu.
 #include "dv3_engine.h"
 
+#include <map>
+
 #include <cstdlib>
 
 #include "dv3_scan.h"
@@ -210,6 +212,33 @@ float* Engine::af(const std::string& name, std::vector<int64_t> shape, int kind)
 int32_t* Engine::ai(const std::string& name, std::vector<int64_t> shape, int kind) {
   return (int32_t*)alloc_bytes(name, (size_t)prod(shape) * 4, 1, shape, kind, -1);
 }
+void Engine::phase_mark(const char* label) {
+  if (!phase_times) return;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(cur, &st);
+  if (st != cudaStreamCaptureStatusNone) return;
+  cudaEvent_t ev;
+  cudaEventCreate(&ev);
+  cudaEventRecord(ev, cur);
+  phase_marks.emplace_back(label, ev);
+}
+void Engine::phase_dump() {
+  if (phase_marks.empty()) return;
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<double, int>> acc;
+  std::vector<std::string> order;
+  for (size_t i = 1; i < phase_marks.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, phase_marks[i - 1].second, phase_marks[i].second);
+    auto& a = acc[phase_marks[i].first];
+    if (a.second == 0) order.push_back(phase_marks[i].first);
+    a.first += ms; a.second += 1;
+  }
+  for (const auto& k : order) fprintf(stderr, "[dv3 phase] %-28s %8.3f ms  (n=%d)\n", k.c_str(), acc[k].first, acc[k].second);
+  for (auto& m : phase_marks) cudaEventDestroy(m.second);
+  phase_marks.clear();
+}
+
 void* Engine::twin_alloc(const float* base, size_t elems) {
   if (cfg.compute_mode != 1) return nullptr;
   void* p = alloc_bytes("", elems * 2, 0, {}, 5, -1);
@@ -423,12 +452,14 @@ void Engine::layout() {
   if (!discrete) inf_std_act = alloc_mlp_act("inf.actor_std", B, L);
   inf_actor_out = af("inf.actor_out", {B, A}); inf_actor_probs = af("inf.actor_probs", {B, A}); inf_actor_s = af("inf.actor_std_out", {B, A});
   sN_Z = af("", {Nl, Z}); sN_3G0 = af("", {Nl, 3 * G}); sN_3G1 = af("", {Nl, 3 * G}); sN_A = af("", {Nl, A});
+  if (Nl >= 128) { twin_alloc(sN_Z, (size_t)Nl * Z); twin_alloc(sN_3G0, (size_t)Nl * 3 * G); twin_alloc(sN_3G1, (size_t)Nl * 3 * G); }
   noise_step = (unsigned long long*)alloc_bytes("noise_step", 8, 1, {2}, 6, -1);
 }
 
 int Engine::init(const dv3_config* c) {
   cfg = *c;
   if (cfg.abi_version != DV3_ABI_VERSION) return fail("dv3_config.abi_version mismatch");
+  phase_times = std::getenv("DV3_PHASE_TIMES") != nullptr;
   G = cfg.G; D = cfg.D; L = cfg.L; Zc = cfg.Zc; Zk = cfg.Zk; Z = Zc * Zk; A = cfg.A;
   B = cfg.B; T = cfg.T; H = cfg.H; N = B * T; R = (H + 1) * N;
   discrete = cfg.discrete != 0; image = cfg.image_obs != 0;

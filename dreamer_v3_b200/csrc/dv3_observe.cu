@@ -38,6 +38,7 @@ int Engine::observe_forward(cudaStream_t s) {
   mm(enc_out, E, false, Wp.w, D, false, p_pre, D, N, D, E);              // hoisted: enc_t . W_post[:E]
   mm(a_in, A, false, Wx.w + (size_t)Z * D, D, false, actW, D, N, D, A);  // hoisted: a_{t-1} . W_pre[Z:]
   initial_state(s);
+  phase_mark("obs.enc+prep");
 
   // measured on B200: the persistent kernel wins up to size L; at XL (GRU 4096) weight streaming dominates and the
   // per-op path with split-K GEMMs is faster
@@ -76,6 +77,7 @@ int Engine::observe_forward(cudaStream_t s) {
   }
   // After the scan, four independent chains over the folded B*T rows run concurrently (fork/join on auxiliary streams):
   // the prior net (world_model.py:272; its sample is discarded by the reference) and the three heads (:299-309).
+  phase_mark("obs.scan");
   if (hz16 != nullptr) to_bf16(s, hz, G + Z, hz16, G + Z, N, G + Z);  // bf16 twin of [h, z] for the N-row head contractions
   run_branches({
       [&] { decoder_fwd(); },
@@ -94,6 +96,7 @@ int Engine::observe_forward(cudaStream_t s) {
         mlp_fwd(cont_mlp, cont_act, hz, G + Z, N, 0, hz16);
         mm(cont_act.act.back(), D, false, cont_out.w, 1, false, cont_logit, 1, N, 1, D, cont_out.bias);
       }});
+  phase_mark("obs.heads");
   return 0;
 }
 
@@ -113,7 +116,9 @@ int Engine::wm_loss_backward(cudaStream_t s) {
   a.L_dec = L_dec; a.L_rew = L_rew; a.L_con = L_con; a.L_dyn = L_dyn; a.L_rep = L_rep; a.L_tot = L_tot;
   a.scalars = wm_scalars; a.dloc = dloc; a.drew_logits = drew_logits; a.dcont_logit = dcont_logit;
   a.dpost = dpost; a.dprior = dprior; a.rew_k = rew_k;
+  phase_mark("wmb.begin");
   wm_losses(s, a);
+  phase_mark("wmb.losses");
 
   // heads -> d_hz
   cudaMemsetAsync(d_hz, 0, (size_t)N * (G + Z) * 4, s);
@@ -129,6 +134,7 @@ int Engine::wm_loss_backward(cudaStream_t s) {
   mm(hz, G + Z, true, dq_pre, D, false, Wd.dw, D, G, D, N, nullptr, 1.f);
   mm(dq_pre, D, false, Wd.w, D, true, d_hz, G + Z, N, G, D, nullptr, 1.f);
 
+  phase_mark("wmb.heads_bwd");
   // reverse-time scan: only input gradients on the recurrence
   if (use_persistent && scan_bwd_ctas > 0) {
     transpose_f32(s, post_repr.w, Wt_zq, D, Z);
@@ -173,6 +179,7 @@ int Engine::wm_loss_backward(cudaStream_t s) {
       scan_mask_grads(s, in_is_first + t, T, sB_Z, Z, dprev + G, ldhz, B, Z);
     }
   }
+  phase_mark("wmb.scan_bwd");
   // weight gradients, one N-row contraction each; they are independent of one another -> four concurrent chains
   run_branches({
       [&] {
@@ -195,9 +202,11 @@ int Engine::wm_loss_backward(cudaStream_t s) {
         mm(wf, 1, true, dh_in, G, false, dh0, G, 1, G, N);
         tanh_bwd_acc(cur, dh0, h0, d_initial_h, G);
       }});
+  phase_mark("wmb.wgrads");
   // encoder
   mm(dp_pre, D, false, Wp.w, D, true, d_enc_out, E, N, E, D);
   encoder_bwd(d_enc_out);
+  phase_mark("wmb.encoder_bwd");
   return 0;
 }
 

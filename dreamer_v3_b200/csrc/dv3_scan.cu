@@ -11,6 +11,8 @@
 // of a CTA and reduced through shared memory, tasks are dealt round-robin to the CTAs of the grid. Weights are
 // streamed from L2 (they are re-read every step by the same CTAs and stay L2 resident up to size L); activations
 // of the step are staged in shared memory in [k][row] order so one LDS.128 feeds four FMAs.
+#include <cstdlib>
+
 #include "dv3_scan_common.cuh"
 
 namespace dv3 {
@@ -285,6 +287,13 @@ cudaError_t launch_observe_scan_fwd(cudaStream_t s, const ScanFwdParams& p, int 
   const bool fits = p.D <= 4 * kThreads && sizeof(Smem) + cache <= 227 * 1024 && ctas >= tg + td && ctas >= tz && ctas >= tu;
   pp.cache_weights = fits ? 1 : 0;
   const size_t smem = sizeof(Smem) + (fits ? cache : 0);
+  // CTAs beyond the widest stage only lengthen the grid barrier (every arrival is an atomic on one address)
+  int need = tg + td;
+  if (tz > need) need = tz;
+  if (tu > need) need = tu;
+  if (p.B > need) need = p.B;
+  if (const char* f = std::getenv("DV3_SCAN_CTAS")) need = std::atoi(f);
+  if (need < ctas && need > 0) ctas = need;
   cudaFuncSetAttribute(observe_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaMemsetAsync(pp.bar, 0, sizeof(unsigned int), s);
   void* args[] = {&pp};

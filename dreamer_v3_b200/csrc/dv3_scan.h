@@ -61,6 +61,7 @@ struct ScanBwdParams {
   float* du;         // [B, T, D]  grad w.r.t. SiLU(LN(x_pre))
   float* dx_pre;     // [B, T, D]
   unsigned int* bar; // grid-barrier counter (zeroed by the launcher)
+  int cache_weights; // set by the launcher: every CTA keeps its weight slice of each stage in shared memory
 };
 
 size_t scan_fwd_smem_bytes();

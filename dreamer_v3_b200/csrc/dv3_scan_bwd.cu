@@ -11,6 +11,8 @@
 // The LayerNorm backward needs whole-row statistics; instead of a separate row-owner stage (one more barrier) every
 // consumer CTA redoes it for the 16 rows from data it has to stage anyway. The contractions read TRANSPOSED weight
 // copies (refreshed once per update) so that weight reads stay coalesced.
+#include <cstdlib>
+
 #include "dv3_scan_common.cuh"
 
 namespace dv3 {
@@ -126,8 +128,9 @@ __device__ __forceinline__ int pick_cw(int ncols, int nblk) {
 }
 
 // out_tile = in(b, 0..K) . Wt[:, c0 .. c0+CW): K staged in chunks of kStageK
+// wc != nullptr: this CTA's slice [K][CW] of Wt is resident in shared memory
 template <int CW, class InFn>
-__device__ __forceinline__ void task_contract(Smem& sm, const float* __restrict__ Wt, int ldw, int c0, int ncols, int K, int B, InFn in_fn) {
+__device__ __forceinline__ void task_contract(Smem& sm, const float* __restrict__ Wt, int ldw, const float* wc, int c0, int ncols, int K, int B, InFn in_fn) {
   const int lane = threadIdx.x & 31;
   float* in_s = &sm.in_chunk[0][0][0];
   const int c = c0 + (lane % CW);
@@ -137,16 +140,24 @@ __device__ __forceinline__ void task_contract(Smem& sm, const float* __restrict_
   for (int kc = 0; kc < K; kc += kStageK) {
     const int kn = min(kStageK, K - kc);
     stage_rows(in_s, kn, B, [&](int b, int k) { return in_fn(b, kc + k); });
-    gemv_acc<CW>(acc, in_s, Wt + (size_t)kc * ldw, ldw, c < ncols ? c : -1, kn);
+    if (wc != nullptr) gemv_acc<CW>(acc, in_s, wc + (size_t)kc * CW, CW, c < ncols ? (lane % CW) : -1, kn);
+    else gemv_acc<CW>(acc, in_s, Wt + (size_t)kc * ldw, ldw, c < ncols ? c : -1, kn);
     __syncthreads();
   }
   gemv_finish<CW>(sm, acc);
 }
 template <class InFn>
-__device__ __forceinline__ void task_contract_cw(Smem& sm, int cw, const float* __restrict__ Wt, int ldw, int c0, int ncols, int K, int B, InFn in_fn) {
-  if (cw == 32) task_contract<32>(sm, Wt, ldw, c0, ncols, K, B, in_fn);
-  else if (cw == 16) task_contract<16>(sm, Wt, ldw, c0, ncols, K, B, in_fn);
-  else task_contract<8>(sm, Wt, ldw, c0, ncols, K, B, in_fn);
+__device__ __forceinline__ void task_contract_cw(Smem& sm, int cw, const float* __restrict__ Wt, int ldw, const float* wc, int c0, int ncols, int K, int B, InFn in_fn) {
+  if (cw == 32) task_contract<32>(sm, Wt, ldw, wc, c0, ncols, K, B, in_fn);
+  else if (cw == 16) task_contract<16>(sm, Wt, ldw, wc, c0, ncols, K, B, in_fn);
+  else task_contract<8>(sm, Wt, ldw, wc, c0, ncols, K, B, in_fn);
+}
+// copies columns [c0, c0 + cw) of Wt [K, ldw] into wc [K][cw] (zero beyond ncols)
+__device__ __forceinline__ void cache_slice(float* wc, const float* __restrict__ Wt, int ldw, int c0, int cw, int ncols, int K) {
+  for (int e = threadIdx.x; e < K * cw; e += kThreads) {
+    const int k = e / cw, j = e % cw;
+    wc[e] = (c0 + j < ncols) ? Wt[(size_t)k * ldw + c0 + j] : 0.f;
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdParams p) {
@@ -164,6 +175,21 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
   const int cw3 = pick_cw(G + D, nblk), nt3g = (G + cw3 - 1) / cw3, nt3d = (D + cw3 - 1) / cw3;   // S3: G + D output columns
   float* in_s = &sm.in_chunk[0][0][0];
 
+  // ---- weight slices resident in shared memory for all T steps (launcher: one task per CTA per stage and they fit) ----
+  const bool cached = p.cache_weights != 0;
+  float* wc1 = reinterpret_cast<float*>(smem_raw + sizeof(Smem));   // [Z][cw1]
+  float* wc2 = wc1 + (size_t)Z * cw1;                               // [D][32]
+  float* wc3 = wc2 + (size_t)D * 32;                                // [3G][cw3]
+  float* wc4 = wc3 + (size_t)3 * G * cw3;                           // [D][32]
+  if (cached) {
+    if (blk < ntask1) cache_slice(wc1, p.Wt_zq, D, blk * cw1, cw1, D, Z);
+    if (blk < tasks_G) cache_slice(wc2, p.Wt_post_h, G, blk * 32, 32, G, D);
+    if (blk < nt3g) cache_slice(wc3, p.Ut, G, blk * cw3, cw3, G, 3 * G);
+    else if (blk < nt3g + nt3d) cache_slice(wc3, p.Kt, D, (blk - nt3g) * cw3, cw3, D, 3 * G);
+    if (blk < tasks_Z) cache_slice(wc4, p.Wt_pre_z, Z, blk * 32, 32, Z, D);
+    __syncthreads();
+  }
+
   // prologue: dlogits of the last step (no recurrent contribution yet)
   for (int pr = gwarp; pr < B * Zc; pr += gwarps) repr_bwd_pair(p, pr / Zc, T - 1, pr % Zc, lane);
   grid_bar(p.bar, bar_target);
@@ -172,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
     // ===== S1: dp_act = dlogits[t] . W_zq^T   (Wt_zq [Z, D]) =====
     for (int task = blk; task < ntask1; task += nblk) {
       const int c0 = task * cw1;
-      task_contract_cw(sm, cw1, p.Wt_zq, D, c0, D, Z, B, [&](int b, int k) { return __ldcg(p.dlogits + ((size_t)b * T + t) * Z + k); });
+      task_contract_cw(sm, cw1, p.Wt_zq, D, cached ? wc1 : nullptr, c0, D, Z, B, [&](int b, int k) { return __ldcg(p.dlogits + ((size_t)b * T + t) * Z + k); });
       for (int e = threadIdx.x; e < B * cw1; e += kThreads) {
         const int b = e / cw1, j = e % cw1;
         if (c0 + j < D) p.dp_act[((size_t)b * T + t) * D + c0 + j] = sm.tile[b][j];
@@ -190,7 +216,8 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
       float acc[kRows];
 #pragma unroll
       for (int b = 0; b < kRows; ++b) acc[b] = 0.f;
-      gemv_acc<32>(acc, in_s, p.Wt_post_h, G, (c0 + lane) < G ? c0 + lane : -1, D);
+      if (cached) gemv_acc<32>(acc, in_s, wc2, 32, (c0 + lane) < G ? lane : -1, D);
+      else gemv_acc<32>(acc, in_s, p.Wt_post_h, G, (c0 + lane) < G ? c0 + lane : -1, D);
       gemv_finish<32>(sm, acc);
       for (int e = threadIdx.x; e < B * 32; e += kThreads) {
         const int b = e >> 5, jj = e & 31, j = c0 + jj;
@@ -217,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
     for (int task = blk; task < nt3g + nt3d; task += nblk) {
       if (task < nt3g) {
         const int c0 = task * cw3;
-        task_contract_cw(sm, cw3, p.Ut, G, c0, G, 3 * G, B, [&](int b, int k) { return __ldcg(p.dgh + ((size_t)b * T + t) * 3 * G + k); });
+        task_contract_cw(sm, cw3, p.Ut, G, cached ? wc3 : nullptr, c0, G, 3 * G, B, [&](int b, int k) { return __ldcg(p.dgh + ((size_t)b * T + t) * 3 * G + k); });
         for (int e = threadIdx.x; e < B * cw3; e += kThreads) {
           const int b = e / cw3, j = c0 + e % cw3;
           if (j < G) {
@@ -233,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
         __syncthreads();
       } else {
         const int c0 = (task - nt3g) * cw3;
-        task_contract_cw(sm, cw3, p.Kt, D, c0, D, 3 * G, B, [&](int b, int k) { return __ldcg(p.dgx + ((size_t)b * T + t) * 3 * G + k); });
+        task_contract_cw(sm, cw3, p.Kt, D, cached ? wc3 : nullptr, c0, D, 3 * G, B, [&](int b, int k) { return __ldcg(p.dgx + ((size_t)b * T + t) * 3 * G + k); });
         for (int e = threadIdx.x; e < B * cw3; e += kThreads) {
           const int b = e / cw3, j = c0 + e % cw3;
           if (j < D) p.du[((size_t)b * T + t) * D + j] = sm.tile[b][e % cw3];
@@ -253,7 +280,8 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
       float acc[kRows];
 #pragma unroll
       for (int b = 0; b < kRows; ++b) acc[b] = 0.f;
-      gemv_acc<32>(acc, in_s, p.Wt_pre_z, Z, (c0 + lane) < Z ? c0 + lane : -1, D);
+      if (cached) gemv_acc<32>(acc, in_s, wc4, 32, (c0 + lane) < Z ? lane : -1, D);
+      else gemv_acc<32>(acc, in_s, p.Wt_pre_z, Z, (c0 + lane) < Z ? c0 + lane : -1, D);
       gemv_finish<32>(sm, acc);
       for (int e = threadIdx.x; e < B * 32; e += kThreads) {
         const int b = e >> 5, j = e & 31;
@@ -308,11 +336,21 @@ int scan_bwd_max_ctas(int device) {
 }
 
 cudaError_t launch_observe_scan_bwd(cudaStream_t s, const ScanBwdParams& p, int ctas) {
-  cudaFuncSetAttribute(observe_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
   ScanBwdParams pp = p;
+  if (const char* f = std::getenv("DV3_SCAN_BWD_CTAS")) { const int n = std::atoi(f); if (n > 0 && n < ctas) ctas = n; }
+  // same task-width choice as the kernel (pick_cw), to size the shared-memory weight cache
+  auto cw_of = [&](int ncols) { return ((ncols + 31) / 32 * 2 > ctas) ? 32 : (((ncols + 15) / 16 * 2 > ctas) ? 16 : 8); };
+  const int cw1 = cw_of(p.D), cw3 = cw_of(p.G + p.D);
+  const int nt1 = (p.D + cw1 - 1) / cw1, nt3 = (p.G + cw3 - 1) / cw3 + (p.D + cw3 - 1) / cw3;
+  const size_t cache = ((size_t)p.Z * cw1 + (size_t)p.D * 32 * 2 + (size_t)3 * p.G * cw3) * sizeof(float);
+  const bool fits = sizeof(Smem) + cache <= 227 * 1024 && nt1 <= ctas && nt3 <= ctas && (p.G + 31) / 32 <= ctas && (p.Z + 31) / 32 <= ctas &&
+                    std::getenv("DV3_SCAN_NO_CACHE") == nullptr;
+  pp.cache_weights = fits ? 1 : 0;
+  const size_t smem = sizeof(Smem) + (fits ? cache : 0);
+  cudaFuncSetAttribute(observe_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaMemsetAsync(pp.bar, 0, sizeof(unsigned int), s);
   void* args[] = {&pp};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)observe_scan_bwd_kernel, dim3(ctas), dim3(kThreads), args, sizeof(Smem), s);
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)observe_scan_bwd_kernel, dim3(ctas), dim3(kThreads), args, smem, s);
   if (e == cudaSuccess) count_launch();
   return e;
 }

@@ -198,20 +198,37 @@ __device__ __forceinline__ void gemv_finish(Smem& sm, float (&acc)[kRows]) {
   }
   __syncthreads();
 }
-// CTA-wide staging of in(b, k), k < K <= kStageK, into in_s[k][b] (rows >= B zero); lanes run along k (coalesced reads)
-template <class InFn>
-__device__ __forceinline__ void stage_rows(float* in_s, int K, int B, InFn in_fn) {
-  for (int k = threadIdx.x; k < K; k += kThreads) {
-    float v[kRows];
+// CTA-wide staging of in(b, k), k < K <= kStageK, into in_s[k][b] (rows >= B zero); lanes run along k (coalesced reads).
+// All loads of the pass are issued before the first shared-memory store: one L2 round trip instead of K / 256.
+template <int NIT, class InFn>
+__device__ __forceinline__ void stage_rows_t(float* in_s, int K, int B, InFn in_fn) {
+  float v[NIT][kRows];
 #pragma unroll
-    for (int b = 0; b < kRows; ++b) v[b] = (b < B) ? in_fn(b, k) : 0.f;
-    float4* dst = reinterpret_cast<float4*>(in_s + (size_t)k * kInLd);
-    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-    dst[2] = make_float4(v[8], v[9], v[10], v[11]);
-    dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+  for (int it = 0; it < NIT; ++it) {
+    const int k = threadIdx.x + it * kThreads;
+#pragma unroll
+    for (int b = 0; b < kRows; ++b) v[it][b] = (b < B && k < K) ? in_fn(b, k) : 0.f;
+  }
+  asm volatile("" ::: "memory");
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int k = threadIdx.x + it * kThreads;
+    if (k < K) {
+      float4* dst = reinterpret_cast<float4*>(in_s + (size_t)k * kInLd);
+      dst[0] = make_float4(v[it][0], v[it][1], v[it][2], v[it][3]);
+      dst[1] = make_float4(v[it][4], v[it][5], v[it][6], v[it][7]);
+      dst[2] = make_float4(v[it][8], v[it][9], v[it][10], v[it][11]);
+      dst[3] = make_float4(v[it][12], v[it][13], v[it][14], v[it][15]);
+    }
   }
   __syncthreads();
+}
+template <class InFn>
+__device__ __forceinline__ void stage_rows(float* in_s, int K, int B, InFn in_fn) {
+  if (K <= kThreads) stage_rows_t<1>(in_s, K, B, in_fn);
+  else if (K <= 2 * kThreads) stage_rows_t<2>(in_s, K, B, in_fn);
+  else if (K <= 3 * kThreads) stage_rows_t<3>(in_s, K, B, in_fn);
+  else stage_rows_t<4>(in_s, K, B, in_fn);
 }
 
 // Forward LayerNorm + SiLU of rows b < B (x row b at x + b*ldx, read through L2), one warp per row, result staged as
