@@ -363,12 +363,22 @@ def measure_roofline(e, cfg, pk, args):
         torch.cuda.synchronize()
     ms = s.elapsed_time(t) / reps
     flops = 2.0 * R * K * Nn
-    ach = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": f"gemm [{R}x{K}]x[{K}x{Nn}] ({'fp32 SIMT' if args.mode == 0 else 'bf16 tcgen05, TMA-fed (gemm_tma_kernel)'})",
-            "achieved": ach, "peak": pk["tf"], "unit": "TFLOP/s", "frac": ach / pk["tf"], "traffic": TRAFFIC_BYTES.get((R, K, Nn, args.mode)),
-            "algorithmic_bytes": float(a_bytes) + (2.0 if args.mode == 1 else 4.0) * K * Nn + 4.0 * R * Nn,
-            "peak_source": pk["src"] + " (burst, kernel timed alone)", "ms_per_launch": ms,
-            "l2": f"{nset} operand sets rotated ({nset * (a_bytes + 4 * R * Nn) / 1e6:.0f} MB > L2)", "launches_timed": reps}
+    alg_bytes = float(a_bytes) + (2.0 if args.mode == 1 else 4.0) * K * Nn + 4.0 * R * Nn
+    tf = flops / (ms * 1e-3) / 1e12
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    # the roofline that binds this shape: with bf16 operands the head contraction has ~180 flop/B, below the ridge
+    # (measured 1634.5 TF / 6.49 TB/s = 252 flop/B), so it is HBM-bound; the fp32 SIMT variant is far below both
+    hbm_bound = (alg_bytes / (pk["hbm"] * 1e9)) > (flops / (pk["tf"] * 1e12))
+    out = {"kernel": f"gemm [{R}x{K}]x[{K}x{Nn}] ({'fp32 SIMT' if args.mode == 0 else 'bf16 tcgen05, TMA-fed (gemm_tma_kernel)'})",
+           "traffic": TRAFFIC_BYTES.get((R, K, Nn, args.mode)), "algorithmic_bytes": alg_bytes, "algorithmic_flops": flops,
+           "peak_source": pk["src"] + " (burst, kernel timed alone)", "ms_per_launch": ms,
+           "l2": f"{nset} operand sets rotated ({nset * (a_bytes + 4 * R * Nn) / 1e6:.0f} MB > L2)", "launches_timed": reps,
+           "tensor_tflops": tf, "tensor_frac": tf / pk["tf"], "hbm_gbs": gbs, "hbm_frac": gbs / pk["hbm"]}
+    if hbm_bound:
+        out.update({"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"]})
+    else:
+        out.update({"bound": "tensor", "achieved": tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": tf / pk["tf"]})
+    return out
 
 
 def cpu_baseline(wid):

@@ -202,6 +202,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const uint32_t as = acc_it & 1;
       mbar_wait(&sm.acc_full[as], (acc_it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // Last work item of this CTA: every MMA has completed and the producer has nothing left to load, so the B ring
+      // is free -- each 32-column block gets its own staging block there and no store ever waits for an earlier one.
+      const bool last_item = w + (int)gridDim.x >= nwork;
+      const uint32_t ring = smem_u32(sm.b[0]) + (uint32_t)ew * (BN / 32) * 4096;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32, ++blk) {
         if (n0 + c0 >= g.N) break;
@@ -217,13 +221,16 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
               "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr));
         // the staging block about to be reused must have been read by the TMA unit before it is overwritten
-        if (lane == 0) {
-          if (SmemT::EB == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        const uint32_t blk_base = last_item ? ring + (uint32_t)(c0 / 32) * 4096 : epi0 + (blk & (SmemT::EB - 1)) * 4096;
+        if (!last_item) {
+          if (lane == 0) {
+            if (SmemT::EB == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          __syncwarp();
         }
-        __syncwarp();
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const uint32_t buf = epi0 + (blk & (SmemT::EB - 1)) * 4096 + lane * 128;
+        const uint32_t buf = blk_base + lane * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
@@ -238,7 +245,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          const uint32_t src = epi0 + (blk & (SmemT::EB - 1)) * 4096;
+          const uint32_t src = blk_base;
           if (reduce)
             asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
                          ::"l"(&mapC), "r"(n0 + c0), "r"(m0 + q * 32), "r"(src) : "memory");
