@@ -226,6 +226,14 @@ int dv3_op_gemm_bf16(const void* Ah, int ldah, const void* Bh, int ldbh, float* 
   if (!dv3::gemm_tma(S(stream), g)) return -2;
   return op_done();
 }
+int dv3_op_gemm_bf16_wgrad(const void* Xh, int ldx, const void* dYh, int ldy, float* C, int ldc, int M, int N, int K, float beta,
+                           void* stream) {
+  dv3::GemmArgs g{nullptr, 0, 1, nullptr, 0, 0, C, ldc, M, N, K, nullptr, beta};
+  g.Ah = Xh; g.ldah = ldx; g.Bmn = dYh; g.ldbmn = ldy;
+  if (!dv3::gemm_tma_eligible(g)) return -1;
+  if (!dv3::gemm_tma(S(stream), g)) return -2;
+  return op_done();
+}
 int dv3_op_ln_silu(const float* x, const float* gamma, const float* beta, float* y, int64_t rows, int D, void* stream) {
   if (D > 1024) return -1;
   dv3::ln_silu_fwd(S(stream), x, D, gamma, beta, y, D, nullptr, nullptr, 1, rows, D);

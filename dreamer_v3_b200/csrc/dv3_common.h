@@ -33,6 +33,10 @@ struct GemmArgs {
   // optional bf16 copy of A (row-major [M, K], written by A's producer kernel). With both Ah and Bh set the
   // contraction runs on the TMA-fed kernel (dv3_gemm_tma.cu).
   const void* Ah = nullptr; int ldah = 0;
+  // optional bf16 copy of B exactly as given with tb = 0 ([K, N] row-major). Together with ta = 1 and Ah (A as given,
+  // [K, M] row-major) this is the weight-gradient case X^T dY: both operands "MN-major", fed to the tensor core by TMA
+  // without any transposition.
+  const void* Bmn = nullptr; int ldbmn = 0;
 };
 
 // ---- gemm (dv3_gemm.cu) ----------------------------------------------------------------------

@@ -144,7 +144,7 @@ int Engine::ac_loss_backward(const dv3_hparams* hp, int phase, cudaStream_t s) {
   auto critic_chain = [&] {
     cudaMemsetAsync(grads[2], 0, (size_t)numel[2] * 4, cur);
     dense_bwd(critic_head, critic_act.act.back(), D, dcritic_logits, DV3_NB, sN_D2, D, 0.f, true, HN);
-    mlp_bwd(critic_mlp, critic_act, dr_hz, W, sN_D2, sN_D3, nullptr, 0, true, HN);
+    mlp_bwd(critic_mlp, critic_act, dr_hz, W, sN_D2, sN_D3, nullptr, 0, true, HN, 0, dr_hz16);
   };
   if (!hp->train_actor) { critic_chain(); return 0; }
   side_run(critic_chain);
@@ -207,15 +207,15 @@ void Engine::actor_backward(const dv3_hparams* hp, const AcArgs& a) {
   if (!discrete) {
     run_branches({[&] {
                     dense_bwd(actor_out, actor_act.act.back(), D, dactor_logits, A, sN_D0, D, 0.f, true, HN);
-                    mlp_bwd(actor_mlp, actor_act, dr_hz, W, sN_D0, sN_D1, nullptr, 0, true, HN);
+                    mlp_bwd(actor_mlp, actor_act, dr_hz, W, sN_D0, sN_D1, nullptr, 0, true, HN, 0, dr_hz16);
                   },
                   [&] {
                     dense_bwd(actor_std_out, actor_std_act.act.back(), D, ds, A, sN_D4, D, 0.f, true, HN);
-                    mlp_bwd(actor_std_mlp, actor_std_act, dr_hz, W, sN_D4, sN_D5, nullptr, 0, true, HN);
+                    mlp_bwd(actor_std_mlp, actor_std_act, dr_hz, W, sN_D4, sN_D5, nullptr, 0, true, HN, 0, dr_hz16);
                   }});
   } else {
     dense_bwd(actor_out, actor_act.act.back(), D, dactor_logits, A, sN_D0, D, 0.f, true, HN);
-    mlp_bwd(actor_mlp, actor_act, dr_hz, W, sN_D0, sN_D1, nullptr, 0, true, HN);
+    mlp_bwd(actor_mlp, actor_act, dr_hz, W, sN_D0, sN_D1, nullptr, 0, true, HN, 0, dr_hz16);
   }
 }
 

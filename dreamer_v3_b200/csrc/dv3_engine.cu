@@ -661,9 +661,10 @@ void Engine::side_join() {
 
 // ------------------------------------------------------------------------------------------ building blocks
 void Engine::mm(const float* A_, int lda, bool ta, const float* B_, int ldb, bool tb, float* C, int ldc, int M, int N_,
-                int K, const float* bias, float beta, const void* A16) {
+                int K, const float* bias, float beta, const void* A16, const void* B16) {
   GemmArgs g{A_, lda, ta ? 1 : 0, B_, ldb, tb ? 1 : 0, C, ldc, M, N_, K, bias, beta};
-  if (A16 != nullptr && !ta && cfg.compute_mode == 1) { g.Ah = A16; g.ldah = lda; }
+  if (A16 != nullptr && cfg.compute_mode == 1 && (!ta || (B16 != nullptr && !tb))) { g.Ah = A16; g.ldah = lda; }
+  if (B16 != nullptr && ta && !tb && cfg.compute_mode == 1) { g.Bmn = B16; g.ldbmn = ldb; }
   if (cfg.compute_mode == 1 && !shadow_host.empty() && gemm_tc_eligible(g)) {
     // is B a (sub-block of a) weight matrix with a bf16 shadow?
     for (const ShadowDesc& d : shadow_host) {
@@ -700,7 +701,7 @@ void Engine::mlp_fwd(const Mlp& mdl, MlpAct& a, const float* x, int ldx, long lo
 }
 
 void Engine::mlp_bwd(const Mlp& mdl, MlpAct& a, const float* x, int ldx, float* dtop, float* scratch, float* dx,
-                     int lddx, bool wgrad, long long rows, long long row_off) {
+                     int lddx, bool wgrad, long long rows, long long row_off, const void* x16) {
   float* dcur = dtop;
   float* dpre = scratch;
   void* dpre16 = rows >= 128 ? twin_of(scratch) : nullptr;  // written by the LN backward launch, read by the dX contraction
@@ -709,10 +710,12 @@ void Engine::mlp_bwd(const Mlp& mdl, MlpAct& a, const float* x, int ldx, float* 
     const float* pre = a.pre[l] + row_off * ly.out;
     const bool need_dx = l > 0 || dx != nullptr;
     ln_silu_bwd(cur, dcur, ly.out, pre, ly.out, a.mean[l] + row_off, a.rstd[l] + row_off, ly.g, ly.b, dpre, ly.out,
-                wgrad ? ly.dg : nullptr, wgrad ? ly.db : nullptr, 1, rows, ly.out, need_dx ? dpre16 : nullptr);
+                wgrad ? ly.dg : nullptr, wgrad ? ly.db : nullptr, 1, rows, ly.out, (need_dx || wgrad) ? dpre16 : nullptr);
     const float* in = (l == 0) ? x : a.act[l - 1] + row_off * mdl.layers[l - 1].out;
     const int ldin = (l == 0) ? ldx : mdl.layers[l - 1].out;
-    if (wgrad) mm(in, ldin, true, dpre, ly.out, false, ly.dw, ly.out, ly.in, ly.out, (int)rows, nullptr, 1.f);
+    const void* in16 = (l == 0) ? x16 : (rows >= 128 ? bf16_off((const void*)a.act16[l - 1], (size_t)row_off * mdl.layers[l - 1].out) : nullptr);
+    // weight gradient X^T dY: both operands have bf16 twins written by their producers -> TMA-fed MN-major contraction
+    if (wgrad) mm(in, ldin, true, dpre, ly.out, false, ly.dw, ly.out, ly.in, ly.out, (int)rows, nullptr, 1.f, dpre16 ? in16 : nullptr, dpre16);
     if (l > 0) mm(dpre, ly.out, false, ly.w, ly.out, true, dcur, ly.in, (int)rows, ly.in, ly.out, nullptr, 0.f, dpre16);
     else if (dx != nullptr) mm(dpre, ly.out, false, ly.w, ly.out, true, dx, lddx, (int)rows, ly.in, ly.out, nullptr, 1.f, dpre16);
   }

@@ -188,7 +188,7 @@ struct Engine {
 
   // A16: bf16 twin of A (same element layout), valid only when the kernel that produced A wrote it in the same launch
   void mm(const float* A_, int lda, bool ta, const float* B_, int ldb, bool tb, float* C, int ldc, int M, int N_, int K,
-          const float* bias = nullptr, float beta = 0.f, const void* A16 = nullptr);
+          const float* bias = nullptr, float beta = 0.f, const void* A16 = nullptr, const void* B16 = nullptr);
   void mlp_fwd(const Mlp& m, MlpAct& a, const float* x, int ldx, long long rows, long long row_off = 0,
                const void* x16 = nullptr);
   // ---- bf16 twins of activation buffers that feed large contractions (tensor-core mode only) ----
@@ -197,7 +197,7 @@ struct Engine {
   void* twin_of(const float* base) const { auto it = twins.find(base); return it == twins.end() ? nullptr : it->second; }
   void *hz16 = nullptr, *dr_hz16 = nullptr, *dr_u16 = nullptr, *dr_q_act16 = nullptr;
   void mlp_bwd(const Mlp& m, MlpAct& a, const float* x, int ldx, float* dtop, float* scratch, float* dx, int lddx,
-               bool wgrad, long long rows, long long row_off = 0);
+               bool wgrad, long long rows, long long row_off = 0, const void* x16 = nullptr);
   void dense_bwd(const DenseLayer& d, const float* x, int ldx, const float* dy, int lddy, float* dx, int lddx,
                  float dx_beta, bool wgrad, long long rows);
 

@@ -43,8 +43,19 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {  // K-major
   d |= (uint64_t)2 << 61;
   return d;
 }
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// MN-major, SWIZZLE_128B: 64 MN elements (128 B) x 8 k per swizzle atom; k-groups 1024 B apart (SBO), the next 64 MN
+// elements 8192 B apart (LBO) -- exactly how two [64 k x 64 mn] TMA boxes land back to back
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int n, bool mn_major = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -99,7 +110,7 @@ struct TmaGemmArgs {
   int tiles_n, tiles, splits, k_per_split, use_atomic;
 };
 
-template <int BN>
+template <int BN, bool MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                 const __grid_constant__ CUtensorMap mapC, TmaGemmArgs g) {
@@ -140,15 +151,22 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           const int s = it % S;
           mbar_wait(&sm.empty[s], ((it / S) & 1) ^ 1);
           mbar_expect_tx(&sm.full[s], kBytes);
-          tma_load_2d(smem_u32(sm.a[s]), &mapA, k0, m0, &sm.full[s]);
-          tma_load_2d(smem_u32(sm.b[s]), &mapB, k0, n0, &sm.full[s]);
+          if (!MN) {
+            tma_load_2d(smem_u32(sm.a[s]), &mapA, k0, m0, &sm.full[s]);
+            tma_load_2d(smem_u32(sm.b[s]), &mapB, k0, n0, &sm.full[s]);
+          } else {   // operands stored [k][mn]: boxes of 64 mn x 64 k, 8 KB each
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d(smem_u32(sm.a[s]) + i * 8192, &mapA, m0 + 64 * i, k0, &sm.full[s]);
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(smem_u32(sm.b[s]) + i * 8192, &mapB, n0 + 64 * i, k0, &sm.full[s]);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BN);
+      const uint32_t idesc = make_idesc(BN, MN);
       uint32_t it = 0, acc_it = 0;
       for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++acc_it) {
         const int split = w % g.splits;
@@ -165,8 +183,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           const uint32_t a_addr = smem_u32(sm.a[s]), b_addr = smem_u32(sm.b[s]);
 #pragma unroll
           for (int j = 0; j < BK / 16; ++j) {
-            const uint64_t da = make_smem_desc(a_addr + j * 32);
-            const uint64_t db = make_smem_desc(b_addr + j * 32);
+            const uint64_t da = MN ? make_smem_desc_mn(a_addr + j * 2048) : make_smem_desc(a_addr + j * 32);
+            const uint64_t db = MN ? make_smem_desc_mn(b_addr + j * 2048) : make_smem_desc(b_addr + j * 32);
             const uint32_t accum = (first && j == 0) ? 0u : 1u;
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
@@ -290,11 +308,16 @@ bool make_map_c(CUtensorMap* map, float* ptr, int M, int N, int ldc) {
   return r == CUDA_SUCCESS;
 }
 
-template <int BN>
+template <int BN, bool MN>
 bool launch_tma(cudaStream_t s, const GemmArgs& g) {
   CUtensorMap mapA, mapB, mapC;
-  if (!make_map(&mapA, g.Ah, g.M, g.K, g.ldah, BM)) return false;
-  if (!make_map(&mapB, g.Bh, g.N, g.K, g.ldbh, BN)) return false;
+  if (!MN) {
+    if (!make_map(&mapA, g.Ah, g.M, g.K, g.ldah, BM)) return false;
+    if (!make_map(&mapB, g.Bh, g.N, g.K, g.ldbh, BN)) return false;
+  } else {   // [K rows, M (or N) contiguous]: boxes of 64 k x 64 mn
+    if (!make_map(&mapA, g.Ah, g.K, g.M, g.ldah, 64)) return false;
+    if (!make_map(&mapB, g.Bmn, g.K, g.N, g.ldbmn, 64)) return false;
+  }
   if (!make_map_c(&mapC, g.C, g.M, g.N, g.ldc)) return false;
   TmaGemmArgs a;
   a.C = g.C; a.ldc = g.ldc; a.M = g.M; a.N = g.N; a.K = g.K; a.bias = g.bias; a.beta = g.beta;
@@ -313,11 +336,11 @@ bool launch_tma(cudaStream_t s, const GemmArgs& g) {
   static_assert(sizeof(TmaSmem<BN>) + 1024 <= 227 * 1024, "TmaSmem exceeds the 227 KB dynamic shared memory limit");
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(gemm_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(gemm_tma_kernel<BN, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
   const int grid = min(a.tiles * a.splits, 148);
-  gemm_tma_kernel<BN><<<grid, kThreads, smem, s>>>(mapA, mapB, mapC, a);
+  gemm_tma_kernel<BN, MN><<<grid, kThreads, smem, s>>>(mapA, mapB, mapC, a);
   count_launch();
   return true;
 }
@@ -325,22 +348,31 @@ bool launch_tma(cudaStream_t s, const GemmArgs& g) {
 }  // namespace
 
 bool gemm_tma_eligible(const GemmArgs& g) {
+  if ((g.ldc % 4 != 0) || ((uintptr_t)g.C % 16 != 0) || g.N < 16 || g.K < 32) return false;
+  if (g.ta && !g.tb)   // weight gradient X^T dY: both operands bf16 copies as stored ([K, M] and [K, N] row-major)
+    return g.Ah != nullptr && g.Bmn != nullptr && (g.ldah % 8 == 0) && (g.ldbmn % 8 == 0) && ((uintptr_t)g.Ah % 16 == 0) &&
+           ((uintptr_t)g.Bmn % 16 == 0) && g.M >= 64 && g.K >= 512;
   return g.Ah != nullptr && g.Bh != nullptr && !g.ta && (g.ldah % 8 == 0) && (g.ldbh % 8 == 0) &&
-         ((uintptr_t)g.Ah % 16 == 0) && ((uintptr_t)g.Bh % 16 == 0) && (g.ldc % 4 == 0) && ((uintptr_t)g.C % 16 == 0) && g.M >= 128 && g.N >= 16 && g.K >= 32;
+         ((uintptr_t)g.Ah % 16 == 0) && ((uintptr_t)g.Bh % 16 == 0) && g.M >= 128;
+}
+
+template <bool MN>
+static bool gemm_tma_sel(cudaStream_t s, const GemmArgs& g) {
+  if (const char* f = std::getenv("DV3_TC_BN")) {  // probing aid
+    const int bn = std::atoi(f);
+    if (bn == 256) return launch_tma<256, MN>(s, g);
+    if (bn == 128) return launch_tma<128, MN>(s, g);
+    if (bn == 64) return launch_tma<64, MN>(s, g);
+  }
+  const long long mt = cdiv(g.M, BM);
+  if (g.N > 128 && mt * cdiv(g.N, 256) >= 96) return launch_tma<256, MN>(s, g);
+  if (g.N > 64 && mt * cdiv(g.N, 128) >= 64) return launch_tma<128, MN>(s, g);
+  if (g.N > 128 && mt * cdiv(g.N, 64) < 16) return launch_tma<256, MN>(s, g);
+  return launch_tma<64, MN>(s, g);
 }
 
 bool gemm_tma(cudaStream_t s, const GemmArgs& g) {
-  if (const char* f = std::getenv("DV3_TC_BN")) {  // probing aid
-    const int bn = std::atoi(f);
-    if (bn == 256) return launch_tma<256>(s, g);
-    if (bn == 128) return launch_tma<128>(s, g);
-    if (bn == 64) return launch_tma<64>(s, g);
-  }
-  const long long mt = cdiv(g.M, BM);
-  if (g.N > 128 && mt * cdiv(g.N, 256) >= 96) return launch_tma<256>(s, g);
-  if (g.N > 64 && mt * cdiv(g.N, 128) >= 64) return launch_tma<128>(s, g);
-  if (g.N > 128 && mt * cdiv(g.N, 64) < 16) return launch_tma<256>(s, g);
-  return launch_tma<64>(s, g);
+  return (g.ta && !g.tb) ? gemm_tma_sel<true>(s, g) : gemm_tma_sel<false>(s, g);
 }
 
 }  // namespace dv3

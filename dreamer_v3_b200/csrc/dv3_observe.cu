@@ -124,9 +124,9 @@ int Engine::wm_loss_backward(cudaStream_t s) {
   cudaMemsetAsync(d_hz, 0, (size_t)N * (G + Z) * 4, s);
   decoder_bwd();
   dense_bwd(rew_head, rew_act.act.back(), D, drew_logits, DV3_NB, sN_D0, D, 0.f, true, N);
-  mlp_bwd(rew_mlp, rew_act, hz, G + Z, sN_D0, sN_D1, d_hz, G + Z, true, N);
+  mlp_bwd(rew_mlp, rew_act, hz, G + Z, sN_D0, sN_D1, d_hz, G + Z, true, N, 0, hz16);
   dense_bwd(cont_out, cont_act.act.back(), D, dcont_logit, 1, sN_D0, D, 0.f, true, N);
-  mlp_bwd(cont_mlp, cont_act, hz, G + Z, sN_D0, sN_D1, d_hz, G + Z, true, N);
+  mlp_bwd(cont_mlp, cont_act, hz, G + Z, sN_D0, sN_D1, d_hz, G + Z, true, N, 0, hz16);
   // prior (dynamics predictor) on all rows: KL gradient w.r.t. prior probs -> d_hz (h part)
   repr_bwd(s, prior_logits, Z, nullptr, 0, dprior, Z, dprior_logits, Z, N, Zc, Zk);
   dense_bwd(dyn_repr, q_act, D, dprior_logits, Z, sN_D0, D, 0.f, true, N);

@@ -139,6 +139,19 @@ def gemm_bf16(A16, W, bias=None, C_=None, beta=0.0):
     return run
 
 
+def gemm_bf16_wgrad(X16, dY16, C_=None, beta=0.0):
+    """C [M, N] (+)= X16^T dY16 with X16 [K, M], dY16 [K, N] bf16 row-major: the weight-gradient contraction on the
+    operands as stored (TMA boxes of 64 k x 64 mn, MN-major UMMA descriptors)."""
+    assert X16.dtype == torch.bfloat16 and dY16.dtype == torch.bfloat16 and X16.shape[0] == dY16.shape[0]
+    K, M = X16.shape
+    N = dY16.shape[1]
+    if C_ is None:
+        C_ = torch.zeros((M, N), dtype=torch.float32, device=X16.device)
+    _ok(_lib.load().dv3_op_gemm_bf16_wgrad(_p(X16), X16.stride(0), _p(dY16), dY16.stride(0), _p(C_), C_.stride(0), M, N, K,
+                                           beta, _s()), "dv3_op_gemm_bf16_wgrad")
+    return C_
+
+
 def ln_silu(x, gamma, beta):
     x = _f32(x)
     y = torch.empty_like(x)

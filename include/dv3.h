@@ -169,6 +169,9 @@ int dv3_op_gemm_shadow(const float* A, int lda, int ta, const void* Bh, int ldbh
 int dv3_op_to_bf16(const float* src, int lds, void* dst, int ldd, int64_t rows, int cols, void* stream);
 int dv3_op_gemm_bf16(const void* Ah, int ldah, const void* Bh, int ldbh, float* C, int ldc, int M, int N, int K,
                      const float* bias, float beta, void* stream);
+/* weight-gradient contraction C[M,N] (+)= Xh[K,M]^T * dYh[K,N] on bf16 copies as stored (both operands MN-major) */
+int dv3_op_gemm_bf16_wgrad(const void* Xh, int ldx, const void* dYh, int ldy, float* C, int ldc, int M, int N, int K, float beta,
+                           void* stream);
 int dv3_op_ln_silu(const float* x, const float* gamma, const float* beta, float* y, int64_t rows, int D, void* stream);
 
 #ifdef __cplusplus

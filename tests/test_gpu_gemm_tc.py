@@ -94,3 +94,21 @@ def test_gemm_tma_variant(M, N, K):
     assert float((got - (want + bias.double())).abs().max()) <= tol, (M, N, K)
     got = ops.gemm_bf16(A16, W.cuda(), C_=C0.cuda(), beta=1.0)().cpu().double()
     assert float((got - (want + C0.double())).abs().max()) <= tol, (M, N, K, "beta")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 512), (1280, 256, 15360), (256, 256, 16384), (1000, 248, 1000), (64, 768, 1024),
+                                   (1280, 256, 1024), (520, 72, 4104)])
+def test_gemm_tma_wgrad_variant(M, N, K):
+    """Weight-gradient contraction X^T dY on bf16 operands as stored: MN-major UMMA descriptors, 64x64 TMA boxes,
+    split-K with TMA reduce-add, accumulate epilogue. Ragged M / N / K."""
+    from dreamer_v3_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    X = torch.randn(K, M, generator=g)
+    dY = torch.randn(K, N, generator=g)
+    C0 = torch.randn(M, N, generator=g)
+    want = X.bfloat16().double().T @ dY.bfloat16().double()
+    tol = 2e-5 * np.sqrt(K) * 8
+    got = ops.gemm_bf16_wgrad(ops.to_bf16(X.cuda()), ops.to_bf16(dY.cuda())).cpu().double()
+    assert float((got - want).abs().max()) <= tol, (M, N, K)
+    got = ops.gemm_bf16_wgrad(ops.to_bf16(X.cuda()), ops.to_bf16(dY.cuda()), C_=C0.cuda(), beta=1.0).cpu().double()
+    assert float((got - (want + C0.double())).abs().max()) <= tol, (M, N, K, "beta")

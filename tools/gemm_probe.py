@@ -12,7 +12,10 @@ ta, tb = (int(sys.argv[5]), int(sys.argv[6])) if len(sys.argv) > 6 else (0, 0)
 A = torch.randn((K, M) if ta else (M, K), device="cuda")
 B = torch.randn((N, K) if tb else (K, N), device="cuda")
 C = torch.empty(M, N, device="cuda")
-if mode == 4:   # TMA-fed kernel: A in bf16 (as the producer kernels write it), B as bf16 shadow
+if mode == 5:   # weight-gradient contraction X^T dY on bf16 operands as stored: A [K, M], B [K, N]
+    A16, B16 = ops.to_bf16(torch.randn(K, M, device="cuda")), ops.to_bf16(torch.randn(K, N, device="cuda"))
+    run = lambda: ops.gemm_bf16_wgrad(A16, B16, C_=C)  # noqa: E731
+elif mode == 4:   # TMA-fed kernel: A in bf16 (as the producer kernels write it), B as bf16 shadow
     run = ops.gemm_bf16(ops.to_bf16(A), B, C_=C)
 elif mode == 3:
     run = ops.gemm_weight_shadow(A, B, bool(ta), C_=C)
