@@ -50,21 +50,20 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
   auto t16 = [&](void* base, size_t off) -> void* { return base ? (void*)((unsigned short*)base + off) : nullptr; };
   if (hz16p) to_bf16(s, dr_hz, W, hz16p, W, N, W);
   phase_mark("dream.begin");
-  actor_fwd(0);
-  phase_mark("dream.actor");
   for (int i = 1; i <= H; ++i) {
     const size_t prev = (size_t)(i - 1) * N, curr = (size_t)i * N, st = (size_t)(i - 1) * N;  // st: per-step buffers
     const float* hz_p = dr_hz + prev * W;
     float* hz_c = dr_hz + curr * W;
-    // sequence model on [z_{i-1}, a_{i-1}], h_{i-1}; h_{i-1} . U runs concurrently with the pre-GRU chain
-    run_branches({[&] {
-                    mm(hz_p + G, W, false, Wx.w, D, false, dr_x_pre + st * D, D, N, D, Z, nullptr, 0.f, h16(prev, G));
-                    mm(dr_act + prev * A, A, false, Wx.w + (size_t)Z * D, D, false, dr_x_pre + st * D, D, N, D, A, nullptr, 1.f);
-                    ln_silu_fwd(cur, dr_x_pre + st * D, D, Wx.g, Wx.b, dr_u + st * D, D, dr_x_mean + st, dr_x_rstd + st, 1, N, D, t16(dr_u16, st * D));
-                    mm(dr_u + st * D, D, false, gru_K, 3 * G, false, dr_gx + st * 3 * G, 3 * G, N, 3 * G, D, gru_b, 0.f, t16(dr_u16, st * D));
-                  },
+    // Everything that only needs [h, z]_{i-1} runs concurrently: the actor (its action a_{i-1} enters the sequence model
+    // through the small a-part of the pre-GRU layer only), the z-part of that layer, and h_{i-1} . U.
+    run_branches({[&] { actor_fwd((long long)prev); },
+                  [&] { mm(hz_p + G, W, false, Wx.w, D, false, dr_x_pre + st * D, D, N, D, Z, nullptr, 0.f, h16(prev, G)); },
                   [&] { mm(hz_p, W, false, gru_U, 3 * G, false, dr_gh + st * 3 * G, 3 * G, N, 3 * G, G, gru_b + 3 * G, 0.f, h16(prev, 0)); }});
-    phase_mark("dream.pre+gx|gh");
+    phase_mark("dream.actor|z|gh");
+    mm(dr_act + prev * A, A, false, Wx.w + (size_t)Z * D, D, false, dr_x_pre + st * D, D, N, D, A, nullptr, 1.f);
+    ln_silu_fwd(s, dr_x_pre + st * D, D, Wx.g, Wx.b, dr_u + st * D, D, dr_x_mean + st, dr_x_rstd + st, 1, N, D, t16(dr_u16, st * D));
+    mm(dr_u + st * D, D, false, gru_K, 3 * G, false, dr_gx + st * 3 * G, 3 * G, N, 3 * G, D, gru_b, 0.f, t16(dr_u16, st * D));
+    phase_mark("dream.pre+gx");
     gru_fwd(s, dr_gx + st * 3 * G, 3 * G, dr_gh + st * 3 * G, 3 * G, hz_p, W, hz_c, W, N, G, h16(curr, 0));
     phase_mark("dream.gru");
     // prior z_i ~ dynamics_predictor(h_i), straight-through sample
@@ -74,10 +73,9 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
     repr_fwd(s, dr_prior_logits + st * Z, Z, dr_prior_probs + st * Z, Z, in_u_dyn + st * Zc, Zc, dr_z_idx + st * Zc, Zc,
              hz_c + G, W, N, Zc, Zk, 1, h16(curr, G));
     phase_mark("dream.prior");
-    actor_fwd((long long)curr);
-    phase_mark("dream.actor");
   }
-  // heads on all (H+1)*N rows: four independent chains, run concurrently
+  // heads on all (H+1)*N rows: four independent chains, run concurrently (together with the actor of the last dreamed state,
+  // whose action is never fed back)
   run_branches({
       [&] {
         mlp_fwd(critic_mlp, critic_act, dr_hz, W, R, 0, dr_hz16);
@@ -97,7 +95,8 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
         mlp_fwd(ema_mlp, ema_act, dr_hz, W, R, 0, dr_hz16);
         mm(ema_act.act.back(), D, false, ema_head.w, DV3_NB, false, ema_logits, DV3_NB, R, DV3_NB, D, ema_head.bias, 0.f, ema_act.act16.back());
         bucket_expectation(cur, ema_logits, DV3_NB, ema_E, R);
-      }});
+      },
+      [&] { actor_fwd((long long)H * N); }});
   phase_mark("dream.heads");
   // real-space rewards / continues / values, loss weights (dreamer_model.py:219-280) and lambda-returns
   AcArgs a{};
@@ -193,14 +192,19 @@ void Engine::actor_backward(const dv3_hparams* hp, const AcArgs& a) {
               twin_of(sN_3G0), twin_of(sN_3G1));
       run_branches({[&] {
                       mm(sN_3G0, 3 * G, false, gru_K, 3 * G, true, sN_D0, D, N, D, 3 * G, nullptr, 0.f, twin_of(sN_3G0));
-                      ln_silu_bwd(cur, sN_D0, D, dr_x_pre + st * D, D, dr_x_mean + st, dr_x_rstd + st, Wx.g, Wx.b, sN_D1, D, nullptr, nullptr, 1, N, D, twin_of(sN_D1));
-                      mm(sN_D1, D, false, Wx.w, D, true, d_p + G, W, N, Z, D, nullptr, 1.f, twin_of(sN_D1));
-                      mm(sN_D1, D, false, Wx.w + (size_t)Z * D, D, true, sN_A, A, N, A, D);
+                      float* dxp = dr_dx_pre + st * D;   // kept per step: the action gradients are formed for all steps at once below
+                      void* dxp16 = twin_of(dr_dx_pre) ? (void*)((unsigned short*)twin_of(dr_dx_pre) + st * D) : nullptr;
+                      ln_silu_bwd(cur, sN_D0, D, dr_x_pre + st * D, D, dr_x_mean + st, dr_x_rstd + st, Wx.g, Wx.b, dxp, D, nullptr, nullptr, 1, N, D, dxp16);
+                      mm(dxp, D, false, Wx.w, D, true, d_p + G, W, N, Z, D, nullptr, 1.f, dxp16);
                     },
                     [&] { mm(sN_3G1, 3 * G, false, gru_U, 3 * G, true, d_p, W, N, G, 3 * G, nullptr, 1.f, twin_of(sN_3G1)); }});
-      box_actor_bwd(s, actor_logits + prev * A, actor_s + prev * A, in_act_noise + prev * A, sN_A, A, dmu + prev * A, ds + prev * A, N, A);
       phase_mark("ac.bptt_step");
     }
+    // a_{i-1} enters step i only through the a-part of the pre-GRU layer and the actor inputs are stop-gradient'ed, so the
+    // action gradients of all H steps are one contraction + one reparameterisation backward after the loop
+    mm(dr_dx_pre, D, false, Wx.w + (size_t)Z * D, D, true, dr_dact, A, (int)HN, A, D);
+    box_actor_bwd(s, actor_logits, actor_s, in_act_noise, dr_dact, A, dmu, ds, HN, A);
+    phase_mark("ac.action_grads");
   }
   // actor MLPs: inputs were stop-gradient'ed (dreamer_model.py:179-180), so only weight gradients; the mean and the std
   // network (Box) are independent chains

@@ -452,6 +452,10 @@ void Engine::layout() {
   if (!discrete) inf_std_act = alloc_mlp_act("inf.actor_std", B, L);
   inf_actor_out = af("inf.actor_out", {B, A}); inf_actor_probs = af("inf.actor_probs", {B, A}); inf_actor_s = af("inf.actor_std_out", {B, A});
   sN_Z = af("", {Nl, Z}); sN_3G0 = af("", {Nl, 3 * G}); sN_3G1 = af("", {Nl, 3 * G}); sN_A = af("", {Nl, A});
+  if (!discrete) {
+    dr_dx_pre = af("", {HN, D}); dr_dact = af("", {HN, A});
+    if (Nl >= 128) twin_alloc(dr_dx_pre, (size_t)HN * D);
+  }
   if (Nl >= 128) { twin_alloc(sN_Z, (size_t)Nl * Z); twin_alloc(sN_3G0, (size_t)Nl * 3 * G); twin_alloc(sN_3G1, (size_t)Nl * 3 * G); }
   noise_step = (unsigned long long*)alloc_bytes("noise_step", 8, 1, {2}, 6, -1);
 }
@@ -561,8 +565,10 @@ void Engine::destroy() {
   if (slot_wm.exec) cudaGraphExecDestroy(slot_wm.exec);
   if (slot_ac.exec) cudaGraphExecDestroy(slot_ac.exec);
   for (auto& sl : slot_piece) if (sl.exec) cudaGraphExecDestroy(sl.exec);
-  for (int i = 0; i < kAux; ++i) if (aux[i]) { cudaStreamDestroy(aux[i]); cudaEventDestroy(ev_join[i]); }
-  if (ev_fork) cudaEventDestroy(ev_fork);
+  for (int d = 0; d < kDepth; ++d) {
+    for (int i = 0; i < kAux; ++i) if (aux[d][i]) { cudaStreamDestroy(aux[d][i]); cudaEventDestroy(ev_join[d][i]); }
+    if (ev_fork[d]) cudaEventDestroy(ev_fork[d]);
+  }
   if (side) { cudaStreamDestroy(side); cudaEventDestroy(ev_side_in); cudaEventDestroy(ev_side_out); }
   if (own_stream) { cudaStreamDestroy(own_stream); cudaEventDestroy(ev_in); cudaEventDestroy(ev_out); }
   for (void* p : allocations) cudaFree(p);
@@ -610,32 +616,35 @@ void Engine::refresh_shadows(cudaStream_t s) {
 // ------------------------------------------------------------------------------------------ fork / join
 void Engine::run_branches(const std::vector<std::function<void()>>& branches) {
   cudaStream_t main = cur;
-  if (!use_branches || branches.size() <= 1) {
+  if (!use_branches || branches.size() <= 1 || branch_depth >= kDepth) {
     for (auto& b : branches) { cur = main; b(); }
     cur = main;
     return;
   }
-  if (aux[0] == nullptr) {
+  const int d = branch_depth;
+  if (aux[d][0] == nullptr) {
     for (int i = 0; i < kAux; ++i) {
-      cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking);
-      cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming);
+      cudaStreamCreateWithFlags(&aux[d][i], cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&ev_join[d][i], cudaEventDisableTiming);
     }
-    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_fork[d], cudaEventDisableTiming);
   }
-  cudaEventRecord(ev_fork, main);
+  ++branch_depth;
+  cudaEventRecord(ev_fork[d], main);
   const int n = (int)branches.size();
   for (int i = 1; i < n; ++i) {
     const int a = (i - 1) % kAux;
-    if (i - 1 < kAux) cudaStreamWaitEvent(aux[a], ev_fork, 0);
-    cur = aux[a];
+    if (i - 1 < kAux) cudaStreamWaitEvent(aux[d][a], ev_fork[d], 0);
+    cur = aux[d][a];
     branches[i]();
   }
   cur = main;
   branches[0]();
   for (int a = 0; a < kAux && a < n - 1; ++a) {
-    cudaEventRecord(ev_join[a], aux[a]);
-    cudaStreamWaitEvent(main, ev_join[a], 0);
+    cudaEventRecord(ev_join[d][a], aux[d][a]);
+    cudaStreamWaitEvent(main, ev_join[d][a], 0);
   }
+  --branch_depth;
   cur = main;
 }
 

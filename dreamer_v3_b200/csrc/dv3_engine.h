@@ -119,6 +119,7 @@ struct Engine {
   float *L_critic_HB, *L_val_HB, *L_reg_HB, *targets_symlog, *L_actor_HB, *logp_HB, *scaled_HB, *ent_HB,
       *L_reinf_HB, *L_ent_HB;
   float *sN_Z, *sN_3G0, *sN_3G1, *sN_A;  // dream-backward scratch [N, Z], [N, 3G], [N, A]
+  float *dr_dx_pre = nullptr, *dr_dact = nullptr;  // Box BPTT: per-step grads w.r.t. the pre-GRU pre-activation [H*N, D] and the actions [H*N, A]
   unsigned long long* noise_step = nullptr;
   float last_gamma = 0.997f;
 
@@ -140,8 +141,10 @@ struct Engine {
 
   // ---- fork / join of independent op chains onto auxiliary streams (capturable: events only) ----
   static constexpr int kAux = 3;
-  cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr, nullptr, nullptr};
+  static constexpr int kDepth = 2;   // run_branches may nest once (a branch that forks again uses its own stream set)
+  cudaStream_t aux[kDepth][kAux] = {};
+  cudaEvent_t ev_fork[kDepth] = {}, ev_join[kDepth][kAux] = {};
+  int branch_depth = 0;
   bool use_branches = true;
   // runs branches[0] on the current stream and the others concurrently on auxiliary streams, then joins them
   void run_branches(const std::vector<std::function<void()>>& branches);
