@@ -106,7 +106,6 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
     }
   };
   stamp(0);
-  if (p.stamps != nullptr) g_ln_dbg = p.stamps + T * 8 + 4;
 
   for (int t = 0; t < T; ++t) {
     // ===== stage A (row owners): x_pre = actW + gather-sum of W_pre rows, LayerNorm + SiLU -> u; masked inputs =====
@@ -226,7 +225,6 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
       const bool writer = task == 0;
       cta_ln_silu_stage(in_s, p.p_pre + (size_t)t * D, (size_t)T * D, p.post_g, p.post_b, B, D,
                         writer ? p.p_act + (size_t)t * D : nullptr, (size_t)T * D, p.p_mean + t, p.p_rstd + t, (size_t)T);
-      stamp(t * 8 + 7);
       float acc[kRows];
 #pragma unroll
       for (int b = 0; b < kRows; ++b) acc[b] = 0.f;
@@ -262,6 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
       }
       __syncthreads();
     }
+    stamp(t * 8 + 7);
     grid_bar(p.bar, bar_target);
     stamp(t * 8 + 8);
   }

@@ -70,5 +70,8 @@ cudaError_t launch_observe_scan_bwd(cudaStream_t s, const ScanBwdParams& p, int 
 void transpose_f32(cudaStream_t s, const float* in, float* out, int rows, int cols);
 int scan_fwd_max_ctas(int device);  // 0 when the kernel cannot be made co-resident
 cudaError_t launch_observe_scan_fwd(cudaStream_t s, const ScanFwdParams& p, int ctas);
+// single 16-CTA cluster version (dv3_scan_cluster.cu): weights resident in the cluster's shared memory, DSMEM exchange
+bool scan_cluster_supported(const ScanFwdParams& p);
+cudaError_t launch_observe_scan_cluster(cudaStream_t s, const ScanFwdParams& p);
 
 }  // namespace dv3

@@ -1,0 +1,423 @@
+// RSSM observe scan (world_model.py:244-273) on ONE 16-CTA thread-block cluster, for model sizes whose recurrent
+// weights fit the cluster's shared memory (XS: GRU 256, dense 256, 32x32 latents).
+//
+// The grid-wide version (dv3_scan.cu) spends most of a step waiting: every stage boundary is a grid barrier plus a
+// chain of L2 round trips (publish, fence, atomic, poll, reload). Here the 16 CTAs of a cluster own 1/16 of every layer's
+// output columns, keep exactly those weight columns resident in shared memory for all T steps, and hand activations to
+// each other through distributed shared memory: a producer writes its [16 columns x 16 rows] block straight into the
+// staging buffer of every peer and a hardware cluster barrier separates the stages. Nothing on the recurrence touches
+// L2 except the one-hot row gather of the pre-GRU layer; everything the backward pass needs is written to global
+// memory on the side (fire and forget).
+//
+// Per step t, 4 stages (cluster barrier after each):
+//   A  x_pre[:, my 16 cols] = actW + sum_c W_pre[c*32 + idx_in[c], my cols]              -> all peers' buf0
+//   B  u = SiLU(LN(x_pre)) in place (every CTA, one warp per row); gx = u . K[:, my 16 units x 3 gates];
+//      GRU cell with gh (own units, kept locally from stage C of the previous step)        -> h[:, my units] to all peers' buf1
+//   C  p_pre[:, my 16 cols] += h . W_post[E:][:, my cols] (weights in registers)          -> all peers' buf0
+//      gh(t+1)[:, my units] = h . U[:, my gate cols] + b (kept locally; rows that restart at t+1 use h0 . U + b)
+//   D  p_act = SiLU(LN(p_pre)) in place; logits[:, my 64 cols] = p_act . W_zq + b; softmax, 1% unimix, fp64 inverse-CDF
+//      sample of my 2 categoricals                                                          -> idx to all peers
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
+#include "dv3_scan_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace dv3 {
+namespace {
+
+using namespace scan;
+
+constexpr int kC = 16;        // CTAs per cluster
+constexpr int kU = 16;        // GRU units / dense columns owned per CTA (G = D = 16 * 16)
+constexpr int kZC = 64;       // posterior logit columns owned per CTA (2 categoricals of 32 classes)
+constexpr int kG = kC * kU;   // 256
+constexpr int kLd = kInLd;    // 20: row stride of the [k][row] staging buffers
+
+struct CSmem {
+  float wK[kG][3 * kU];       // K[:, gate*G + my units]            48 KB
+  float wU[kG][3 * kU];       // U[:, gate*G + my units]            48 KB
+  float wZ[kG][kZC];          // W_zq[:, my 64 columns]             64 KB
+  float buf0[kG][kLd];        // x_pre -> u, then p_pre -> p_act    20 KB   [k][row]
+  float buf1[kG][kLd];        // h; cross-warp scratch in stage D   20 KB
+  float red[4 * kRows * (3 * kU + 1)];   // k-slice partial sums of a 48-column pass ([4][16][49]); also the 16-column p_pre pass
+  float gh[kRows][3 * kU];    // gh(t) of my units (z, r, c gate blocks of 16)
+  float gh0[3 * kU];          // h0 . U + b for my units
+  float hown[kRows][kU];      // h_{t-1} of my units
+  float xch[kU][kRows];       // this CTA's [16 columns][16 rows] block, staged for the vectorised DSMEM broadcast
+  int idx[kRows][32];         // z_{t-1} class indices of every row (all 32 categoricals)
+  int idx0[32];               // mode of the prior at the initial state (rows that restart)
+  float h0[kG];               // learned initial state
+  float lnp[4][kG];           // LayerNorm gain / offset of the pre-GRU and the posterior layer
+};
+static_assert(sizeof(CSmem) <= 227 * 1024, "cluster scan shared memory");
+
+// Register-tiled contraction of the 16 staged rows with NC = 16 * CPL resident weight columns, K = 256:
+// warp -> (k-slice of 64, column half), lane -> (4 rows, CPL columns): one LDS.128 of activations and CPL weights feed
+// 4 * CPL FMAs, so the pass is bound by the FMA pipe, not by shared-memory wavefronts. Leaves the four k-slice partial sums
+// in red[ks][row][col] (row stride NC + 1); the consumer adds them.
+template <int CPL>
+__device__ __forceinline__ void tile_pass(const float* in_s, const float* W, float* red) {
+  constexpr int NC = 16 * CPL;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ks = warp & 3, half = warp >> 2, rg = lane & 3, cg = lane >> 2;
+  const int c0 = half * (NC / 2) + cg * CPL;
+  float acc[4][CPL];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) acc[r][c] = 0.f;
+  const float* ap = in_s + (size_t)(64 * ks) * kLd + 4 * rg;
+  const float* wp = W + (size_t)(64 * ks) * NC + c0;
+#pragma unroll 8
+  for (int k = 0; k < 64; ++k) {
+    const float4 a = *reinterpret_cast<const float4*>(ap + k * kLd);
+    float w[CPL];
+    if (CPL == 4) {
+      const float4 w4 = *reinterpret_cast<const float4*>(wp + k * NC);
+      w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[CPL - 1] = w4.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) w[c] = wp[k * NC + c];
+    }
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      acc[0][c] = fmaf(a.x, w[c], acc[0][c]); acc[1][c] = fmaf(a.y, w[c], acc[1][c]);
+      acc[2][c] = fmaf(a.z, w[c], acc[2][c]); acc[3][c] = fmaf(a.w, w[c], acc[3][c]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) red[(ks * kRows + 4 * rg + r) * (NC + 1) + c0 + c] = acc[r][c];
+  __syncthreads();
+}
+template <int NC>
+__device__ __forceinline__ float red_sum(const float* red, int b, int col) {
+  return red[(0 * kRows + b) * (NC + 1) + col] + red[(1 * kRows + b) * (NC + 1) + col] + red[(2 * kRows + b) * (NC + 1) + col] +
+         red[(3 * kRows + b) * (NC + 1) + col];
+}
+
+// Broadcasts this CTA's block (value `v` of thread (row b, column j)) into rows [u0, u0 + 16) of every peer's [k][row] buffer:
+// staged through shared memory so that each remote store carries 4 rows (16 bytes) instead of 4 bytes.
+__device__ __forceinline__ void broadcast_block(cg::cluster_group& cl, CSmem& sm, float* buf_local, int u0, float v) {
+  const int b = threadIdx.x >> 4, j = threadIdx.x & 15;
+  sm.xch[j][b] = v;
+  __syncthreads();
+  const unsigned peer = threadIdx.x >> 4;
+  float* dst = cl.map_shared_rank(buf_local, peer);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int chunk = (threadIdx.x & 15) + 16 * i, col = chunk >> 2, rg = chunk & 3;
+    const float4 q = *reinterpret_cast<const float4*>(&sm.xch[col][4 * rg]);
+    *reinterpret_cast<float4*>(dst + (size_t)(u0 + col) * kLd + 4 * rg) = q;
+  }
+}
+
+// In-place LayerNorm + SiLU of the 16 rows staged as buf[k][row]; one warp per row (2 rows per warp, both in flight).
+// Row b's result is also written to global memory by CTA `rank == b` (spreads the side traffic over the cluster).
+__device__ __forceinline__ void ln_silu_inplace(float* buf, const float* gamma, const float* beta, int B,
+                                                unsigned rank, float* act_out, float* mean_out, float* rstd_out, size_t row_stride,
+                                                size_t stat_stride) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int EPL = kG / 32;
+  float v[2][EPL], g[EPL], be[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    const int c = lane + 32 * i;
+    g[i] = gamma[c]; be[i] = beta[c];
+    v[0][i] = buf[c * kLd + warp];
+    v[1][i] = buf[c * kLd + warp + kWarps];
+  }
+  float mean[2], rstd[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) s += v[r][i];
+    mean[r] = s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mean[0] += __shfl_xor_sync(0xffffffffu, mean[0], o);
+    mean[1] += __shfl_xor_sync(0xffffffffu, mean[1], o);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    mean[r] /= (float)kG;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) { const float d = v[r][i] - mean[r]; q += d * d; }
+    rstd[r] = q;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    rstd[0] += __shfl_xor_sync(0xffffffffu, rstd[0], o);
+    rstd[1] += __shfl_xor_sync(0xffffffffu, rstd[1], o);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int b = warp + r * kWarps;
+    rstd[r] = rsqrtf(rstd[r] / (float)kG + DV3_LN_EPS);
+    const bool wr = (unsigned)b == rank && b < B;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int c = lane + 32 * i;
+      const float n = (v[r][i] - mean[r]) * rstd[r] * g[i] + be[i];
+      const float o = b < B ? n * sigmoid_fast(n) : 0.f;
+      buf[c * kLd + b] = o;
+      if (wr) act_out[(size_t)b * row_stride + c] = o;
+    }
+    if (wr && lane == 0) { mean_out[(size_t)b * stat_stride] = mean[r]; rstd_out[(size_t)b * stat_stride] = rstd[r]; }
+  }
+  __syncthreads();
+}
+
+__global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observe_scan_cluster_kernel(ScanFwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CSmem& sm = *reinterpret_cast<CSmem*>(smem_raw);
+  cg::cluster_group cl = cg::this_cluster();
+  const unsigned rank = cl.block_rank();
+  const int B = p.B, T = p.T, G = kG, D = kG, Z = p.Z, Zc = p.Zc, Zk = p.Zk, E = p.E;
+  const int W = G + Z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int u0 = rank * kU;        // my GRU units / dense columns
+  const int z0c = rank * kZC;      // my posterior logit columns
+  const float* W_post_h = p.W_post + (size_t)E * D;
+
+  // ---- resident weights ----
+  for (int e = tid; e < kG * 3 * kU; e += kThreads) {
+    const int k = e / (3 * kU), j = e % (3 * kU), col = (j / kU) * G + u0 + (j % kU);
+    sm.wK[k][j] = p.gru_K[(size_t)k * 3 * G + col];
+    sm.wU[k][j] = p.gru_U[(size_t)k * 3 * G + col];
+  }
+  for (int e = tid; e < kG * kZC; e += kThreads) { const int k = e / kZC, j = e % kZC; sm.wZ[k][j] = p.W_zq[(size_t)k * Z + z0c + j]; }
+  // W_post[E:][:, my 16 columns] in registers: thread (warp, lane) owns column lane % 16 and the k's of its gemv_acc<16> slice
+  float wP[16];
+  {
+    const int k0 = warp * (kG / kWarps) + lane / 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) wP[i] = W_post_h[(size_t)(k0 + 2 * i) * D + u0 + (lane & 15)];
+  }
+  for (int e = tid; e < kRows * 32; e += kThreads) sm.idx[e / 32][e % 32] = p.z0_idx[e % 32];
+  if (tid < 32) sm.idx0[tid] = p.z0_idx[tid];
+  for (int e = tid; e < kG; e += kThreads) {
+    sm.h0[e] = p.h0[e];
+    sm.lnp[0][e] = p.pre_g[e]; sm.lnp[1][e] = p.pre_b[e]; sm.lnp[2][e] = p.post_g[e]; sm.lnp[3][e] = p.post_b[e];
+  }
+  for (int e = tid; e < kRows * kU; e += kThreads) sm.hown[e / kU][e % kU] = p.h0[u0 + (e % kU)];
+  // every row starts from the learned initial state: buf1 <- h0 for all rows, gh(0) = gh0 = h0 . U + b1
+  for (int e = tid; e < kG * kRows; e += kThreads) sm.buf1[e / kRows][e % kRows] = p.h0[e / kRows];
+  __syncthreads();
+  tile_pass<3>(&sm.buf1[0][0], &sm.wU[0][0], sm.red);
+  if (tid < 3 * kU) sm.gh0[tid] = red_sum<48>(sm.red, 0, tid) + p.gru_b[3 * G + (tid / kU) * G + u0 + (tid % kU)];
+  __syncthreads();
+  for (int e = tid; e < kRows * 3 * kU; e += kThreads) sm.gh[e / (3 * kU)][e % (3 * kU)] = sm.gh0[e % (3 * kU)];
+  cl.sync();
+
+  const int b = tid >> 4, j = tid & 15;   // (row, owned column) of this thread in the 16 x 16 epilogues
+  const bool row_ok = b < B;
+  // per-thread constants and the first step's streamed inputs (later steps are prefetched one step ahead, so that the
+  // only global load a stage ever waits for is the row gather of stage A)
+  float gb[6];
+#pragma unroll
+  for (int g2 = 0; g2 < 3; ++g2) { gb[g2] = p.gru_b[g2 * G + u0 + j]; gb[3 + g2] = p.gru_b[3 * G + g2 * G + u0 + j]; }
+  const float bz0 = p.b_zq[z0c + lane], bz1 = p.b_zq[z0c + 32 + lane];
+  auto stamp = [&](int i) {
+    if (p.stamps != nullptr && rank == 0 && tid == 0) {
+      unsigned long long v;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
+      p.stamps[i] = v;
+    }
+  };
+  stamp(0);
+  bool first = row_ok;
+  float actw = row_ok ? p.actW[((size_t)b * T) * D + u0 + j] : 0.f;
+
+  for (int t = 0; t < T; ++t) {
+    const size_t bt = (size_t)b * T + t;
+    // streamed inputs of this step, consumed in stages C / D
+    const float pp_in = row_ok ? p.p_pre[bt * D + u0 + j] : 0.f;
+    float up[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int pr = warp + q * kWarps, r = pr >> 1, cat = z0c / 32 + (pr & 1);
+      up[q] = r < B ? p.u_post[((size_t)t * B + r) * Zc + cat] : 0.f;
+    }
+    bool first_n = false;
+    float actw_n = 0.f;
+    if (t + 1 < T && row_ok) { first_n = p.is_first[bt + 1] != 0.f; actw_n = p.actW[(bt + 1) * D + u0 + j]; }
+
+    // ===== stage A: pre-GRU layer, my 16 columns: one-hot z -> 32 row gathers per output =====
+    {
+      float x = 0.f;
+      if (row_ok) {
+        x = actw;
+        float w8[8];
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 8) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int cls = first ? sm.idx0[c0 + c] : sm.idx[b][c0 + c];
+            w8[c] = p.W_pre[(size_t)((c0 + c) * Zk + cls) * D + u0 + j];
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) x += w8[c];
+        }
+        p.x_pre[bt * D + u0 + j] = x;
+        // masked recurrent inputs kept for the backward pass (world_model.py:246-250): my units / my 2 categoricals
+        p.h_in[bt * G + u0 + j] = first ? sm.h0[u0 + j] : sm.hown[b][j];
+      }
+      broadcast_block(cl, sm, &sm.buf0[0][0], u0, x);
+      if (row_ok) {
+        for (int q = j; q < kZC; q += 16) {
+          const int cat = (z0c + q) / Zk, cls = (z0c + q) % Zk;
+          const int pick = first ? sm.idx0[cat] : sm.idx[b][cat];
+          p.z_in[bt * Z + z0c + q] = (pick == cls) ? 1.f : 0.f;
+        }
+      }
+    }
+    stamp(t * 8 + 1);
+    cl.sync();
+    stamp(t * 8 + 2);
+
+    // ===== stage B: u = SiLU(LN(x_pre)); gx for my units; GRU cell =====
+    ln_silu_inplace(&sm.buf0[0][0], sm.lnp[0], sm.lnp[1], B, rank, p.u_act + (size_t)t * D, p.x_mean + t, p.x_rstd + t, (size_t)T * D, (size_t)T);
+    tile_pass<3>(&sm.buf0[0][0], &sm.wK[0][0], sm.red);
+    {
+      const int u = u0 + j;
+      float hn = 0.f;
+      if (row_ok) {
+        const float hp = first ? sm.h0[u] : sm.hown[b][j];
+        const float ghz = sm.gh[b][j], ghr = sm.gh[b][kU + j], ghc = sm.gh[b][2 * kU + j];
+        const float z = sigmoid_fast(red_sum<48>(sm.red, b, j) + gb[0] + ghz);
+        const float r = sigmoid_fast(red_sum<48>(sm.red, b, kU + j) + gb[1] + ghr);
+        const float c = tanh_fast(red_sum<48>(sm.red, b, 2 * kU + j) + gb[2] + r * ghc);
+        hn = z * hp + (1.f - z) * c;
+        p.hz[bt * W + u] = hn;
+        float* gt = p.gates + bt * 3 * G;
+        gt[u] = z; gt[G + u] = r; gt[2 * G + u] = c;
+        float* gho = p.gh + bt * 3 * G;
+        gho[u] = ghz; gho[G + u] = ghr; gho[2 * G + u] = ghc;
+      }
+      __syncthreads();   // every thread has read hown / gh of this step
+        sm.hown[b][j] = hn;
+      broadcast_block(cl, sm, &sm.buf1[0][0], u0, hn);
+    }
+    stamp(t * 8 + 3);
+    cl.sync();
+    stamp(t * 8 + 4);
+
+    // ===== stage C: p_pre (my 16 columns, weights in registers); gh(t+1) for my units =====
+    {
+      float acc[kRows];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
+      const float* in_s = &sm.buf1[0][0];
+      const int k0 = warp * (kG / kWarps) + lane / 16;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4* iv = reinterpret_cast<const float4*>(in_s + (size_t)(k0 + 2 * i) * kLd);
+        const float4 a0 = iv[0], a1 = iv[1], a2 = iv[2], a3 = iv[3];
+        const float w_ = wP[i];
+        acc[0] = fmaf(a0.x, w_, acc[0]); acc[1] = fmaf(a0.y, w_, acc[1]); acc[2] = fmaf(a0.z, w_, acc[2]); acc[3] = fmaf(a0.w, w_, acc[3]);
+        acc[4] = fmaf(a1.x, w_, acc[4]); acc[5] = fmaf(a1.y, w_, acc[5]); acc[6] = fmaf(a1.z, w_, acc[6]); acc[7] = fmaf(a1.w, w_, acc[7]);
+        acc[8] = fmaf(a2.x, w_, acc[8]); acc[9] = fmaf(a2.y, w_, acc[9]); acc[10] = fmaf(a2.z, w_, acc[10]); acc[11] = fmaf(a2.w, w_, acc[11]);
+        acc[12] = fmaf(a3.x, w_, acc[12]); acc[13] = fmaf(a3.y, w_, acc[13]); acc[14] = fmaf(a3.z, w_, acc[14]); acc[15] = fmaf(a3.w, w_, acc[15]);
+      }
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 16);
+      if (lane < 16) {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) sm.red[(warp * kRows + r) * 17 + lane] = acc[r];
+      }
+      __syncthreads();
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s += sm.red[(w * kRows + b) * 17 + j];
+      float pv = 0.f;
+      if (row_ok) {
+        pv = pp_in + s;     // p_pre was pre-loaded with enc . W_post[:E]
+        p.p_pre[bt * D + u0 + j] = pv;
+      }
+      broadcast_block(cl, sm, &sm.buf0[0][0], u0, pv);
+      __syncthreads();
+    }
+    if (t + 1 < T) {
+      tile_pass<3>(&sm.buf1[0][0], &sm.wU[0][0], sm.red);
+#pragma unroll
+      for (int gate = 0; gate < 3; ++gate) {
+        const int q = gate * kU + j;
+        sm.gh[b][q] = first_n ? sm.gh0[q] : red_sum<48>(sm.red, b, q) + gb[3 + gate];
+      }
+    }
+    stamp(t * 8 + 5);
+    cl.sync();
+    stamp(t * 8 + 6);
+
+    // ===== stage D: p_act = SiLU(LN(p_pre)); logits for my 64 columns; sample my 2 categoricals =====
+    ln_silu_inplace(&sm.buf0[0][0], sm.lnp[2], sm.lnp[3], B, rank, p.p_act + (size_t)t * D, p.p_mean + t, p.p_rstd + t, (size_t)T * D, (size_t)T);
+    {
+      float* red64 = &sm.buf1[0][0];   // h is dead until stage B of the next step: [4][16][65] k-slice partial sums
+      tile_pass<4>(&sm.buf0[0][0], &sm.wZ[0][0], red64);
+      float lg[4];   // logits of this thread: rows (tid >> 5) + 8 i' ... laid out so that a warp owns one (row, categorical) pair
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int pr = warp + q4 * kWarps, r = pr >> 1, cl_ = pr & 1;
+        const float v = red_sum<64>(red64, r, cl_ * 32 + lane) + (cl_ == 0 ? bz0 : bz1);
+        lg[q4] = v;
+        if (r < B) p.post_logits[((size_t)r * T + t) * Z + z0c + cl_ * 32 + lane] = v;
+      }
+      // 2 categoricals x 16 rows = 32 (row, categorical) pairs, one warp each (4 per warp)
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int pr = warp + q4 * kWarps;
+        const int r = pr >> 1, cl_ = pr & 1;
+        const int cat = z0c / Zk + cl_;
+        if (r >= B) continue;
+        const float l = lg[q4];
+        const float mx = warp_max(l);
+        const float ex = expf(l - mx);
+        const float s = warp_sum(ex);
+        const float pu = 0.99f * (ex / s) + 0.01f * (1.0f / 32.f);
+        const size_t rt = (size_t)r * T + t;
+        p.post_probs[rt * Z + cat * 32 + lane] = pu;
+        const int pick = categorical_pick(pu, true, 32, up[q4], lane);
+        if (lane == 0) p.z_idx[rt * Zc + cat] = pick;
+        p.hz[rt * W + G + cat * 32 + lane] = (lane == pick) ? 1.f : 0.f;
+        if (lane < kC) cl.map_shared_rank(&sm.idx[0][0], lane)[r * 32 + cat] = pick;
+      }
+    }
+    first = first_n;
+    actw = actw_n;
+    stamp(t * 8 + 7);
+    cl.sync();
+    stamp(t * 8 + 8);
+  }
+}
+
+}  // namespace
+
+// The cluster version needs the XS layer sizes (everything resident in 16 SMs' shared memory).
+bool scan_cluster_supported(const ScanFwdParams& p) {
+  return p.G == kG && p.D == kG && p.Z == kC * kZC && p.Zk == 32 && p.Zc == 32 && p.B <= kRows && std::getenv("DV3_NO_CLUSTER_SCAN") == nullptr;
+}
+
+cudaError_t launch_observe_scan_cluster(cudaStream_t s, const ScanFwdParams& p) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(observe_scan_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(observe_scan_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CSmem));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  observe_scan_cluster_kernel<<<dim3(kC), dim3(kThreads), sizeof(CSmem), s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) count_launch();
+  return e;
+}
+
+}  // namespace dv3

@@ -235,8 +235,6 @@ __device__ __forceinline__ void stage_rows(float* in_s, int K, int B, InFn in_fn
 // in_s[d][b] for the contraction that follows; optionally also written out (act / mean / rstd, row b at + b*ldo / b*lds).
 // Every global load of the pass (NR rows per warp at once, gain and offset) is issued before the first reduction: the
 // grid barrier invalidates L1, so each dependent load would cost a full L2 round trip.
-__device__ unsigned long long* g_ln_dbg = nullptr;   // debug: per-phase globaltimer stamps of the LN pass (CTA 0, thread 0)
-#define DV3_LN_DBG(i_) do { if (g_ln_dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long v_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v_)); g_ln_dbg[i_] = v_; } } while (0)
 template <int EPL, int NR>
 __device__ __forceinline__ void cta_ln_silu_stage_t(float* in_s, const float* x, size_t ldx, const float* __restrict__ gamma,
                                                     const float* __restrict__ beta, int B, int D, float* act_out, size_t ldo,
@@ -244,7 +242,6 @@ __device__ __forceinline__ void cta_ln_silu_stage_t(float* in_s, const float* x,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int bb = warp; bb < kRows; bb += kWarps * NR) {
     float v[NR][EPL], g[EPL], be[EPL];
-    DV3_LN_DBG(0);
 #pragma unroll
     for (int i = 0; i < EPL; ++i) {
       const int c = lane + 32 * i;
@@ -271,7 +268,6 @@ __device__ __forceinline__ void cta_ln_silu_stage_t(float* in_s, const float* x,
 #pragma unroll
       for (int r = 0; r < NR; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
     }
-    DV3_LN_DBG(1);
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       mean[r] /= (float)D;
@@ -285,7 +281,6 @@ __device__ __forceinline__ void cta_ln_silu_stage_t(float* in_s, const float* x,
 #pragma unroll
       for (int r = 0; r < NR; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
     }
-    DV3_LN_DBG(2);
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       const int b = bb + r * kWarps;
@@ -302,10 +297,8 @@ __device__ __forceinline__ void cta_ln_silu_stage_t(float* in_s, const float* x,
       }
       if (act_out != nullptr && lane == 0 && b < B) { mean_out[(size_t)b * lds] = mean[r]; rstd_out[(size_t)b * lds] = rstd[r]; }
     }
-    DV3_LN_DBG(3);
   }
   __syncthreads();
-  DV3_LN_DBG(4);
 }
 __device__ __forceinline__ void cta_ln_silu_stage(float* in_s, const float* x, size_t ldx, const float* __restrict__ gamma,
                                                   const float* __restrict__ beta, int B, int D, float* act_out, size_t ldo,

@@ -25,10 +25,8 @@ st = (st[0::2] & 0xFFFFFFFF) | (st[1::2] << 32)
 T = cfg.T
 d = np.diff(st[: T * 8 + 1].astype(np.float64)) / 1e3  # us
 d = d.reshape(T, 8)
-names = ["A work", "A sync", "B work", "B sync", "C work", "Csync+D0+sync", "D work", "D sync"]
+names = ["A work", "A sync", "B work", "B sync", "C work", "C sync", "D work", "D sync"]
 ex = None
 
 print("per-step mean us:", {n: round(float(d[2:, i].mean()), 2) for i, n in enumerate(names)}, "step total", round(float(d[2:].sum(1).mean()), 2))
 
-dbg = st[T * 8 + 4: T * 8 + 9].astype(np.float64)
-print("LN pass phases of the last step (us): loads+sum", (dbg[1] - dbg[0]) / 1e3, "var", (dbg[2] - dbg[1]) / 1e3, "write", (dbg[3] - dbg[2]) / 1e3, "sync", (dbg[4] - dbg[3]) / 1e3)
