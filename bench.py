@@ -42,7 +42,7 @@ GFLOP_PER_UPDATE = {"c1": 150.0, "c2": 235.0, "c3": 827.0, "c4": 2319.0, "L": 35
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel from the committed ncu --set full
 # capture (profiles/), keyed by (M, K, N, mode); None when no capture exists for the shape
-TRAFFIC_BYTES = {(16384, 1280, 256, 1): None,   # filled from profiles/r01_gemm_tma_ncu.txt
+TRAFFIC_BYTES = {(16384, 1280, 256, 1): 42616320 + 142080,   # profiles/r01_gemm_tma_ncu.txt (the fp32 C tile stays in L2 past kernel end)
                  (16384, 1280, 256, 0): None}
 
 
