@@ -1,5 +1,6 @@
 // Internal declarations shared by the kernel translation units and the engine.
 #pragma once
+#include <utility>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -38,6 +39,23 @@ struct GemmArgs {
   // without any transposition.
   const void* Bmn = nullptr; int ldbmn = 0;
 };
+
+// ---- programmatic dependent launch ----------------------------------------------------------------
+// Kernels launched through launch_pdl may start (and run their prologue) while the previous kernel of the stream is
+// still running; they call pdl_wait() (dv3_device.cuh) before their first access to global memory, which blocks until
+// the previous grid has completed and its writes are visible. Inside a captured graph this becomes a programmatic edge.
+// Opt-in with DV3_PDL=1 (no measurable gain inside the replayed graphs on B200); otherwise plain stream order.
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---- gemm (dv3_gemm.cu) ----------------------------------------------------------------------
 void gemm_f32(cudaStream_t s, const GemmArgs& g);

@@ -14,6 +14,10 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// programmatic dependent launch (see launch_pdl in dv3_common.h): let the next kernel of the stream start its prologue now,
+// and do not touch global memory before the previous kernel has completed
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 // fast variants for the latency-critical persistent scan kernels (ex2.approx based, rel. error ~1e-6: far inside the
 // 1e-4 parity budget, and nothing integer-valued depends on them)

@@ -32,6 +32,8 @@ __global__ void tanh_kernel(const float* x, float* y, int n) {
 // mode 0: dst = 0; 1: dst = src; 2: dst += src
 template <int MODE>
 __global__ void op_2d_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int rows, int cols) {
+  pdl_trigger();
+  pdl_wait();
   const long long n = (long long)rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i % cols);
@@ -44,6 +46,8 @@ __global__ void op_2d_kernel(const float* __restrict__ src, int lds, float* __re
 
 // fp32 -> bf16 copy of a 2-D block (cols a multiple of 4, 8-byte aligned destination rows)
 __global__ void to_bf16_kernel(const float* __restrict__ src, int lds, __nv_bfloat16* __restrict__ dst, int ldd, long long rows, int cols4) {
+  pdl_trigger();
+  pdl_wait();
   const long long n = rows * cols4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cols4; const int c = (int)(i - r * cols4) * 4;
@@ -54,6 +58,8 @@ __global__ void to_bf16_kernel(const float* __restrict__ src, int lds, __nv_bflo
   }
 }
 __global__ void to_bf16_scalar_kernel(const float* __restrict__ src, int lds, __nv_bfloat16* __restrict__ dst, int ldd, long long rows, int cols) {
+  pdl_trigger();
+  pdl_wait();
   const long long n = rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cols; const int c = (int)(i - r * cols);
@@ -69,6 +75,8 @@ __global__ void ln_silu_fwd_kernel(const float* __restrict__ x, int ldx, const f
                                    const float* __restrict__ beta, float* __restrict__ y, int ldy,
                                    float* __restrict__ mean_out, float* __restrict__ rstd_out, int sstride, long long rows, int D,
                                    __nv_bfloat16* __restrict__ y16) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -117,6 +125,8 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ dy, int lddy, const
                                    float* __restrict__ dx, int lddx, float* __restrict__ dgamma,
                                    float* __restrict__ dbeta, int sstride, long long rows, int D,
                                    __nv_bfloat16* __restrict__ dx16) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -188,6 +198,8 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ dy, int lddy, const
 __global__ void gru_fwd_kernel(float* __restrict__ gx, int ldgx, const float* __restrict__ gh, int ldgh,
                                const float* __restrict__ h_prev, int ldhp, float* __restrict__ h_out, int ldho,
                                int M, int G, __nv_bfloat16* __restrict__ h16) {
+  pdl_trigger();
+  pdl_wait();
   const long long n = (long long)M * G;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / G), j = (int)(i % G);
@@ -209,6 +221,8 @@ __global__ void gru_bwd_kernel(const float* __restrict__ dh, int lddh, const flo
                                float* __restrict__ dgx, int lddgx, float* __restrict__ dgh, int lddgh,
                                float* __restrict__ dh_prev, int lddhp, int accumulate, int M, int G,
                                __nv_bfloat16* __restrict__ dgx16, __nv_bfloat16* __restrict__ dgh16) {
+  pdl_trigger();
+  pdl_wait();
   const long long n = (long long)M * G;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / G), j = (int)(i % G);
@@ -241,6 +255,8 @@ __global__ void repr_fwd_kernel(const float* __restrict__ logits, int ldl, float
                                 const float* __restrict__ u, int ldu, int32_t* __restrict__ idx, int ldi,
                                 float* __restrict__ z, int ldz, int M, int Zc, int Zk, int mode,
                                 __nv_bfloat16* __restrict__ z16) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -273,6 +289,8 @@ __global__ void repr_fwd_kernel(const float* __restrict__ logits, int ldl, float
 __global__ void repr_bwd_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ dz, int lddz,
                                 const float* __restrict__ dprobs, int lddp, float* __restrict__ dlogits, int lddl,
                                 int M, int Zc, int Zk, __nv_bfloat16* __restrict__ dl16) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -341,6 +359,8 @@ __global__ void scan_mask_grads_kernel(const float* __restrict__ is_first, int l
 // out[c] += sum_r x[r*ld + c]
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int ld, long long rows, int cols,
                                                      float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -410,24 +430,24 @@ void tanh_fwd(cudaStream_t s, const float* x, float* y, int n) {
 void zero_2d(cudaStream_t s, float* p, int rows, int cols, int ld) {
   if (rows <= 0 || cols <= 0) return;
   if (ld == cols) { cudaMemsetAsync(p, 0, (size_t)rows * cols * sizeof(float), s); return; }
-  op_2d_kernel<0><<<grid_for((long long)rows * cols), kThreads, 0, s>>>(nullptr, 0, p, ld, rows, cols); count_launch();
+  launch_pdl(op_2d_kernel<0>, dim3(grid_for((long long)rows * cols)), dim3(kThreads), 0, s, nullptr, 0, p, ld, rows, cols); count_launch();
 }
 void to_bf16(cudaStream_t s, const float* src, int lds, void* dst, int ldd, long long rows, int cols) {
   if (rows <= 0 || cols <= 0) return;
   __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
   if (cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 8 == 0)
-    to_bf16_kernel<<<grid_for(rows * (cols / 4)), kThreads, 0, s>>>(src, lds, d, ldd, rows, cols / 4);
+    launch_pdl(to_bf16_kernel, dim3(grid_for(rows * (cols / 4))), dim3(kThreads), 0, s, src, lds, d, ldd, rows, cols / 4);
   else
-    to_bf16_scalar_kernel<<<grid_for(rows * cols), kThreads, 0, s>>>(src, lds, d, ldd, rows, cols);
+    launch_pdl(to_bf16_scalar_kernel, dim3(grid_for(rows * cols)), dim3(kThreads), 0, s, src, lds, d, ldd, rows, cols);
   count_launch();
 }
 void copy_2d(cudaStream_t s, const float* src, int lds, float* dst, int ldd, int rows, int cols) {
   if (rows <= 0 || cols <= 0) return;
-  op_2d_kernel<1><<<grid_for((long long)rows * cols), kThreads, 0, s>>>(src, lds, dst, ldd, rows, cols); count_launch();
+  launch_pdl(op_2d_kernel<1>, dim3(grid_for((long long)rows * cols)), dim3(kThreads), 0, s, src, lds, dst, ldd, rows, cols); count_launch();
 }
 void add_2d(cudaStream_t s, const float* src, int lds, float* dst, int ldd, int rows, int cols) {
   if (rows <= 0 || cols <= 0) return;
-  op_2d_kernel<2><<<grid_for((long long)rows * cols), kThreads, 0, s>>>(src, lds, dst, ldd, rows, cols); count_launch();
+  launch_pdl(op_2d_kernel<2>, dim3(grid_for((long long)rows * cols)), dim3(kThreads), 0, s, src, lds, dst, ldd, rows, cols); count_launch();
 }
 
 void ln_silu_fwd(cudaStream_t s, const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy,
@@ -435,7 +455,7 @@ void ln_silu_fwd(cudaStream_t s, const float* x, int ldx, const float* gamma, co
   if (rows <= 0) return;
   const int grid = grid_for(rows, kThreads / 32, 148 * 8);
   __nv_bfloat16* y16 = reinterpret_cast<__nv_bfloat16*>(y16_);
-#define DV3_LN_FWD(E_) ln_silu_fwd_kernel<E_><<<grid, kThreads, 0, s>>>(x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, D, y16)
+#define DV3_LN_FWD(E_) launch_pdl(ln_silu_fwd_kernel<E_>, dim3(grid), dim3(kThreads), 0, s, x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, D, y16)
   if (D <= 32) DV3_LN_FWD(1);
   else if (D <= 64) DV3_LN_FWD(2);
   else if (D <= 128) DV3_LN_FWD(4);
@@ -451,7 +471,7 @@ void ln_silu_bwd(cudaStream_t s, const float* dy, int lddy, const float* x, int 
   if (rows <= 0) return;
   const int grid = grid_for(rows, kThreads / 32, 148 * 4);
   __nv_bfloat16* dx16 = reinterpret_cast<__nv_bfloat16*>(dx16_);
-#define DV3_LN_BWD(E_) ln_silu_bwd_kernel<E_><<<grid, kThreads, 0, s>>>(dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, D, dx16)
+#define DV3_LN_BWD(E_) launch_pdl(ln_silu_bwd_kernel<E_>, dim3(grid), dim3(kThreads), 0, s, dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, D, dx16)
   if (D <= 32) DV3_LN_BWD(1);
   else if (D <= 64) DV3_LN_BWD(2);
   else if (D <= 128) DV3_LN_BWD(4);
@@ -464,14 +484,14 @@ void ln_silu_bwd(cudaStream_t s, const float* dy, int lddy, const float* x, int 
 
 void gru_fwd(cudaStream_t s, float* gx, int ldgx, const float* gh, int ldgh, const float* h_prev, int ldhp,
              float* h_out, int ldho, int M, int G, void* h16) {
-  gru_fwd_kernel<<<grid_for((long long)M * G), kThreads, 0, s>>>(gx, ldgx, gh, ldgh, h_prev, ldhp, h_out, ldho, M, G,
+  launch_pdl(gru_fwd_kernel, dim3(grid_for((long long)M * G)), dim3(kThreads), 0, s, gx, ldgx, gh, ldgh, h_prev, ldhp, h_out, ldho, M, G,
                                                                  reinterpret_cast<__nv_bfloat16*>(h16));
   count_launch();
 }
 void gru_bwd(cudaStream_t s, const float* dh, int lddh, const float* gates, int ldg, const float* gh, int ldgh,
              const float* h_prev, int ldhp, float* dgx, int lddgx, float* dgh, int lddgh, float* dh_prev, int lddhp,
              int accumulate_dh_prev, int M, int G, void* dgx16, void* dgh16) {
-  gru_bwd_kernel<<<grid_for((long long)M * G), kThreads, 0, s>>>(dh, lddh, gates, ldg, gh, ldgh, h_prev, ldhp, dgx, lddgx, dgh, lddgh, dh_prev, lddhp, accumulate_dh_prev, M, G,
+  launch_pdl(gru_bwd_kernel, dim3(grid_for((long long)M * G)), dim3(kThreads), 0, s, dh, lddh, gates, ldg, gh, ldgh, h_prev, ldhp, dgx, lddgx, dgh, lddgh, dh_prev, lddhp, accumulate_dh_prev, M, G,
                                                                  reinterpret_cast<__nv_bfloat16*>(dgx16), reinterpret_cast<__nv_bfloat16*>(dgh16));
   count_launch();
 }
@@ -479,14 +499,14 @@ void gru_bwd(cudaStream_t s, const float* dh, int lddh, const float* gates, int 
 void repr_fwd(cudaStream_t s, const float* logits, int ldl, float* probs, int ldp, const float* u, int ldu,
               int32_t* idx, int ldi, float* z, int ldz, int M, int Zc, int Zk, int mode, void* z16) {
   if (M <= 0) return;
-  repr_fwd_kernel<<<grid_for((long long)M * Zc, kThreads / 32), kThreads, 0, s>>>(logits, ldl, probs, ldp, u, ldu, idx, ldi, z, ldz, M, Zc, Zk, mode,
+  launch_pdl(repr_fwd_kernel, dim3(grid_for((long long)M * Zc, kThreads / 32)), dim3(kThreads), 0, s, logits, ldl, probs, ldp, u, ldu, idx, ldi, z, ldz, M, Zc, Zk, mode,
                                                                                   reinterpret_cast<__nv_bfloat16*>(z16));
   count_launch();
 }
 void repr_bwd(cudaStream_t s, const float* logits, int ldl, const float* dz, int lddz, const float* dprobs, int lddp,
               float* dlogits, int lddl, int M, int Zc, int Zk, void* dl16) {
   if (M <= 0) return;
-  repr_bwd_kernel<<<grid_for((long long)M * Zc, kThreads / 32), kThreads, 0, s>>>(logits, ldl, dz, lddz, dprobs, lddp, dlogits, lddl, M, Zc, Zk, reinterpret_cast<__nv_bfloat16*>(dl16));
+  launch_pdl(repr_bwd_kernel, dim3(grid_for((long long)M * Zc, kThreads / 32)), dim3(kThreads), 0, s, logits, ldl, dz, lddz, dprobs, lddp, dlogits, lddl, M, Zc, Zk, reinterpret_cast<__nv_bfloat16*>(dl16));
   count_launch();
 }
 
@@ -509,7 +529,7 @@ void colsum_acc(cudaStream_t s, const float* x, int ld, long long rows, int cols
   if (rows <= 0 || cols <= 0) return;
   long long gy = (rows + 63) / 64; if (gy > 148 * 2) gy = 148 * 2; if (gy < 1) gy = 1;
   dim3 grid(cdiv(cols, 32), (unsigned)gy);
-  colsum_kernel<<<grid, 256, 0, s>>>(x, ld, rows, cols, out); count_launch();
+  launch_pdl(colsum_kernel, dim3(grid), dim3(256), 0, s, x, ld, rows, cols, out); count_launch();
 }
 void scan_prepare(cudaStream_t s, const float* actions, const float* is_first, float* a_in, float* wf, int B, int T, int A) {
   long long n = (long long)B * T * (A + 1);

@@ -1,7 +1,10 @@
 // fp32 SIMT GEMM for sm_100a: the exact-precision path (1e-4 parity mode) and the small-M scan steps.
 // C[M,N] (+)= op(A) op(B) (+ bias). Shared-memory tiled, register-blocked, float4 global loads where
 // the operand is 16-byte aligned, split-K with fp32 atomics when the tile grid is smaller than the GPU.
+#include <cstdlib>
+
 #include "dv3_common.h"
+#include "dv3_device.cuh"
 
 namespace dv3 {
 
@@ -18,6 +21,8 @@ gemm_f32_kernel(GemmArgs g, int k_per_split, int vecA, int vecB, int use_atomic)
   constexpr int PAD = 4;
   __shared__ __align__(16) float As[BK][BM + PAD];
   __shared__ __align__(16) float Bs[BK][BN + PAD];
+  pdl_trigger();
+  pdl_wait();
 
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * BM;
@@ -168,10 +173,10 @@ void launch_tile(cudaStream_t s, const GemmArgs& g) {
   const bool b16 = ((uintptr_t)g.B % 16 == 0) && (g.ldb % 4 == 0);
   dim3 grid(gx, gy, splits), block((BM / TM) * (BN / TN));
   const int vA = a16, vB = b16;
-  if (!g.ta && !g.tb) gemm_f32_kernel<BM, BN, BK, TM, TN, false, false><<<grid, block, 0, s>>>(g, kps, vA, vB, use_atomic);
-  else if (!g.ta && g.tb) gemm_f32_kernel<BM, BN, BK, TM, TN, false, true><<<grid, block, 0, s>>>(g, kps, vA, vB, use_atomic);
-  else if (g.ta && !g.tb) gemm_f32_kernel<BM, BN, BK, TM, TN, true, false><<<grid, block, 0, s>>>(g, kps, vA, vB, use_atomic);
-  else gemm_f32_kernel<BM, BN, BK, TM, TN, true, true><<<grid, block, 0, s>>>(g, kps, vA, vB, use_atomic);
+  if (!g.ta && !g.tb) launch_pdl(gemm_f32_kernel<BM, BN, BK, TM, TN, false, false>, grid, block, 0, s, g, kps, vA, vB, use_atomic);
+  else if (!g.ta && g.tb) launch_pdl(gemm_f32_kernel<BM, BN, BK, TM, TN, false, true>, grid, block, 0, s, g, kps, vA, vB, use_atomic);
+  else if (g.ta && !g.tb) launch_pdl(gemm_f32_kernel<BM, BN, BK, TM, TN, true, false>, grid, block, 0, s, g, kps, vA, vB, use_atomic);
+  else launch_pdl(gemm_f32_kernel<BM, BN, BK, TM, TN, true, true>, grid, block, 0, s, g, kps, vA, vB, use_atomic);
   count_launch();
 }
 
@@ -192,6 +197,12 @@ void gemm_f32(cudaStream_t s, const GemmArgs& g) {
   }
 }
 
+
+bool pdl_enabled() {
+  // measured on B200 inside the replayed graphs: no gain (6.739 vs 6.740 ms per update), so it is opt-in
+  static const bool on = std::getenv("DV3_PDL") != nullptr;
+  return on;
+}
 
 void gemm_dispatch(cudaStream_t s, const GemmArgs& g, int mode) {
   if (mode >= 1 && g.M > 0 && g.N > 0 && g.K > 0 && gemm_tma_eligible(g) && (mode == 2 || gemm_tc_eligible(g)) && gemm_tma(s, g)) return;

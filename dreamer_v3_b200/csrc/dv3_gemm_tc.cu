@@ -218,6 +218,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(GemmArgs g, int 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = sm.tmem_base;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // programmatic dependent launch: prologue above overlaps
+  asm volatile("griddepcontrol.wait;" ::: "memory");                 // the previous kernel's tail; its results are visible from here
   const uint32_t idesc = make_idesc(BN);
 
   // issue the MMAs of one staged k-block (one elected thread) and commit them to the stage's mbarrier
@@ -396,6 +398,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) gemm_tc_ws_kernel(GemmArgs g, i
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = sm.tmem_base;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // programmatic dependent launch: prologue above overlaps
+  asm volatile("griddepcontrol.wait;" ::: "memory");                 // the previous kernel's tail; its results are visible from here
 
   if (warp == 8) {
     // ---------------- MMA issuer ----------------
@@ -568,7 +572,7 @@ void launch_tc(cudaStream_t s, const GemmArgs& g) {
       cudaFuncSetAttribute(gemm_tc_kernel<BN, TA_, TB_, BH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       configured = true;                                                                                          \
     }                                                                                                             \
-    gemm_tc_kernel<BN, TA_, TB_, BH_><<<grid, block, smem, s>>>(g, kps, vA, vB, use_atomic);                      \
+    launch_pdl(gemm_tc_kernel<BN, TA_, TB_, BH_>, grid, block, smem, s, g, kps, vA, vB, use_atomic);               \
   } while (0)
 #define BH_ false
   if (!bh) {
@@ -584,11 +588,11 @@ void launch_tc(cudaStream_t s, const GemmArgs& g) {
     if (!g.ta) {
       static bool cfgd = false;
       if (!cfgd) { cudaFuncSetAttribute(gemm_tc_ws_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws); cfgd = true; }
-      gemm_tc_ws_kernel<BN, false><<<grid, dim3(kWsThreads), smem_ws, s>>>(g, kps, vA, use_atomic);
+      launch_pdl(gemm_tc_ws_kernel<BN, false>, grid, dim3(kWsThreads), smem_ws, s, g, kps, vA, use_atomic);
     } else {
       static bool cfgd = false;
       if (!cfgd) { cudaFuncSetAttribute(gemm_tc_ws_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws); cfgd = true; }
-      gemm_tc_ws_kernel<BN, true><<<grid, dim3(kWsThreads), smem_ws, s>>>(g, kps, vA, use_atomic);
+      launch_pdl(gemm_tc_ws_kernel<BN, true>, grid, dim3(kWsThreads), smem_ws, s, g, kps, vA, use_atomic);
     }
   }
 #undef BH_

@@ -137,6 +137,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = sm.tmem_base;
+  // programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the
+  // tail of the previous kernel; nothing below may run before its results are visible
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -340,7 +344,7 @@ bool launch_tma(cudaStream_t s, const GemmArgs& g) {
     configured = true;
   }
   const int grid = min(a.tiles * a.splits, 148);
-  gemm_tma_kernel<BN, MN><<<grid, kThreads, smem, s>>>(mapA, mapB, mapC, a);
+  launch_pdl(gemm_tma_kernel<BN, MN>, dim3(grid), dim3(kThreads), smem, s, mapA, mapB, mapC, a);
   count_launch();
   return true;
 }

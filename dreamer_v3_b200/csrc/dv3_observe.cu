@@ -150,6 +150,7 @@ int Engine::wm_loss_backward(cudaStream_t s) {
     bp.p_rstd = p_rstd; bp.gates = gx; bp.gh = gh; bp.h_in = h_in; bp.x_pre = x_pre; bp.x_mean = x_mean; bp.x_rstd = x_rstd;
     bp.d_hz = d_hz; bp.dlogits = dpost_logits; bp.dp_act = dp_act_all; bp.dp_pre = dp_pre; bp.dh_tot = dh_tot;
     bp.dgx = dgx; bp.dgh = dgh; bp.dh_in = dh_in; bp.du = du_all; bp.dx_pre = dx_pre; bp.bar = scan_bar + 32;
+    bp.stamps = std::getenv("DV3_SCAN_STAMPS") ? scan_stamps : nullptr;
     cudaError_t ce = launch_observe_scan_bwd(s, bp, scan_bwd_ctas);
     if (ce != cudaSuccess) return fail(std::string("observe scan bwd launch: ") + cudaGetErrorString(ce));
     // LayerNorm gain / offset gradients of the two in-loop layers, one N-row pass each

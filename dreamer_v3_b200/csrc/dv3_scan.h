@@ -62,6 +62,7 @@ struct ScanBwdParams {
   float* dx_pre;     // [B, T, D]
   unsigned int* bar; // grid-barrier counter (zeroed by the launcher)
   int cache_weights; // set by the launcher: every CTA keeps its weight slice of each stage in shared memory
+  unsigned long long* stamps;  // optional [T*8+1] globaltimer stamps of CTA 0 (profiling), may be null
 };
 
 size_t scan_fwd_smem_bytes();

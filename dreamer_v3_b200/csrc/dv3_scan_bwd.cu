@@ -194,7 +194,16 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
   for (int pr = gwarp; pr < B * Zc; pr += gwarps) repr_bwd_pair(p, pr / Zc, T - 1, pr % Zc, lane);
   grid_bar(p.bar, bar_target);
 
+  auto stamp = [&](int i) {
+    if (p.stamps != nullptr && blk == 0 && threadIdx.x == 0) {
+      unsigned long long v;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
+      p.stamps[i] = v;
+    }
+  };
+  stamp(0);
   for (int t = T - 1; t >= 0; --t) {
+    const int si = (T - 1 - t) * 8;
     // ===== S1: dp_act = dlogits[t] . W_zq^T   (Wt_zq [Z, D]) =====
     for (int task = blk; task < ntask1; task += nblk) {
       const int c0 = task * cw1;
@@ -205,12 +214,29 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
       }
       __syncthreads();
     }
+    stamp(si + 1);
     grid_bar(p.bar, bar_target);
+    stamp(si + 2);
 
     // ===== S2: dp_pre = LN'SiLU'(dp_act) (per task CTA); dh_tot = d_hz[t].h + dp_pre . W_post_h^T (Wt_post_h [D, G]);
     //       GRU gate gradients for the task's 32 units =====
     for (int task = blk; task < tasks_G; task += nblk) {
       const int c0 = task * 32;
+      // operands of the epilogue do not depend on the contraction: issue their loads now, one L2 round trip earlier
+      float e_d[2], e_z[2], e_r[2], e_c[2], e_h[2], e_g[2];
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int e = threadIdx.x + it * kThreads, b = e >> 5, j = c0 + (e & 31);
+        const bool ok = b < B && j < G;
+        const size_t bt = (size_t)(ok ? b : 0) * T + t;
+        const int jj = ok ? j : 0;
+        e_d[it] = ok ? __ldcg(p.d_hz + bt * W + jj) : 0.f;
+        e_z[it] = ok ? p.gates[bt * 3 * G + jj] : 0.f;
+        e_r[it] = ok ? p.gates[bt * 3 * G + G + jj] : 0.f;
+        e_c[it] = ok ? p.gates[bt * 3 * G + 2 * G + jj] : 0.f;
+        e_h[it] = ok ? p.h_in[bt * G + jj] : 0.f;
+        e_g[it] = ok ? p.gh[bt * 3 * G + 2 * G + jj] : 0.f;
+      }
       cta_lnbwd_stage(in_s, p.dp_act + (size_t)t * D, p.p_pre + (size_t)t * D, (size_t)T * D, p.p_mean + t, p.p_rstd + t, (size_t)T,
                       p.post_g, p.post_b, B, D, task == 0 ? p.dp_pre + (size_t)t * D : nullptr);
       float acc[kRows];
@@ -219,16 +245,17 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
       if (cached) gemv_acc<32>(acc, in_s, wc2, 32, (c0 + lane) < G ? lane : -1, D);
       else gemv_acc<32>(acc, in_s, p.Wt_post_h, G, (c0 + lane) < G ? c0 + lane : -1, D);
       gemv_finish<32>(sm, acc);
-      for (int e = threadIdx.x; e < B * 32; e += kThreads) {
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int e = threadIdx.x + it * kThreads;
         const int b = e >> 5, jj = e & 31, j = c0 + jj;
-        if (j < G) {
+        if (b < B && j < G) {
           const size_t bt = (size_t)b * T + t;
-          const float d = sm.tile[b][jj] + __ldcg(p.d_hz + bt * W + j);
-          const float* gt = p.gates + bt * 3 * G;
-          const float z = gt[j], r = gt[G + j], c = gt[2 * G + j];
-          const float dz = d * (p.h_in[bt * G + j] - c) * z * (1.f - z);
+          const float d = sm.tile[b][jj] + e_d[it];
+          const float z = e_z[it], r = e_r[it], c = e_c[it];
+          const float dz = d * (e_h[it] - c) * z * (1.f - z);
           const float dc = d * (1.f - z) * (1.f - c * c);
-          const float dr = dc * p.gh[bt * 3 * G + 2 * G + j] * r * (1.f - r);
+          const float dr = dc * e_g[it] * r * (1.f - r);
           p.dh_tot[(size_t)b * G + j] = d;
           float* gxo = p.dgx + bt * 3 * G;
           float* gho = p.dgh + bt * 3 * G;
@@ -238,7 +265,9 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
       }
       __syncthreads();
     }
+    stamp(si + 3);
     grid_bar(p.bar, bar_target);
+    stamp(si + 4);
 
     // ===== S3: dh_in = dh_tot * z + dgh . U^T (Ut [3G, G]), passed on to d_hz[t-1].h;  du = dgx . K^T (Kt [3G, D]) =====
     for (int task = blk; task < nt3g + nt3d; task += nblk) {
@@ -268,12 +297,33 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
         __syncthreads();
       }
     }
+    stamp(si + 5);
     grid_bar(p.bar, bar_target);
+    stamp(si + 6);
 
     // ===== S4: dx_pre = LN'SiLU'(du) (per task CTA); dz_in = dx_pre . W_pre[:Z]^T (Wt_pre_z [D, Z]); pass to step t-1 and
     //       run its posterior repr backward. At t = 0 only dx_pre is needed (weight gradients). =====
     for (int task = blk; task < (t > 0 ? tasks_Z : 1); task += nblk) {
       const int c0 = task * 32;
+      // epilogue / categorical-backward operands (independent of the contraction): loads issued up front
+      float e_old[2], e_keep[2], r_l[2], r_dp[2];
+      const int cats = 32 / Zk;
+      if (t > 0) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int e = threadIdx.x + it * kThreads, b = e >> 5, j = e & 31;
+          const bool ok = b < B && c0 + j < Z;
+          const size_t bt = (size_t)(ok ? b : 0) * T + t;
+          e_old[it] = ok ? __ldcg(p.d_hz + (bt - 1) * W + G + c0 + (ok ? j : 0)) : 0.f;
+          e_keep[it] = ok ? 1.f - p.is_first[bt] : 0.f;
+          const int pr = warp + it * kWarps, rb = pr / cats, cat = c0 / Zk + pr % cats;
+          const bool rok = pr < B * cats && cat < Zc && lane < Zk;
+          const size_t rbt = (size_t)(rok ? rb : 0) * T + (t - 1);
+          const int col = rok ? cat * Zk + lane : 0;
+          r_l[it] = rok ? p.post_logits[rbt * Z + col] : -INFINITY;
+          r_dp[it] = rok ? p.dpost[rbt * Z + col] : 0.f;
+        }
+      }
       cta_lnbwd_stage(in_s, p.du + (size_t)t * D, p.x_pre + (size_t)t * D, (size_t)T * D, p.x_mean + t, p.x_rstd + t, (size_t)T,
                       p.pre_g, p.pre_b, B, D, task == 0 ? p.dx_pre + (size_t)t * D : nullptr);
       if (t == 0) break;
@@ -283,23 +333,47 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
       if (cached) gemv_acc<32>(acc, in_s, wc4, 32, (c0 + lane) < Z ? lane : -1, D);
       else gemv_acc<32>(acc, in_s, p.Wt_pre_z, Z, (c0 + lane) < Z ? c0 + lane : -1, D);
       gemv_finish<32>(sm, acc);
-      for (int e = threadIdx.x; e < B * 32; e += kThreads) {
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int e = threadIdx.x + it * kThreads;
         const int b = e >> 5, j = e & 31;
-        if (c0 + j < Z) {
+        if (b < B && c0 + j < Z) {
           const size_t bt = (size_t)b * T + t;
-          float* dst = p.d_hz + (bt - 1) * W + G + c0 + j;
-          *dst = __ldcg(dst) + (1.f - p.is_first[bt]) * sm.tile[b][j];
+          const float v = e_old[it] + e_keep[it] * sm.tile[b][j];
+          p.d_hz[(bt - 1) * W + G + c0 + j] = v;
+          sm.tile[b][j] = v;      // the categorical backward below takes the updated gradient from here, not from L2
         }
       }
       __syncthreads();
-      const int cats = 32 / Zk;
-      for (int pr = warp; pr < B * cats; pr += kWarps) {
+      // straight-through / KL backward of the step t-1 categoricals of this 32-column block (B * cats <= 16 pairs, 2 per warp)
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int pr = warp + it * kWarps;
+        if (pr < B * cats) {
+          const int b = pr / cats, cl_ = pr % cats, cat = c0 / Zk + cl_;
+          if (cat < Zc) {
+            const bool act = lane < Zk;
+            const int col = cat * Zk + lane;
+            const float l = r_l[it];
+            const float mx = warp_max(l);
+            const float ex = act ? expf(l - mx) : 0.f;
+            const float sden = warp_sum(ex);
+            const float prb = ex / sden;
+            const float g = act ? 0.99f * (sm.tile[b][cl_ * Zk + lane] + r_dp[it]) : 0.f;
+            const float dot = warp_sum(g * prb);
+            if (act) p.dlogits[((size_t)b * T + (t - 1)) * Z + col] = prb * (g - dot);
+          }
+        }
+      }
+      for (int pr = warp + 2 * kWarps; pr < B * cats; pr += kWarps) {   // narrow categoricals (Zk < 32): more than 16 pairs per block
         const int b = pr / cats, cat = c0 / Zk + pr % cats;
         if (cat < Zc) repr_bwd_pair(p, b, t - 1, cat, lane);
       }
       __syncthreads();
     }
+    stamp(si + 7);
     if (t > 0) grid_bar(p.bar, bar_target);
+    stamp(si + 8);
   }
 }
 

@@ -30,3 +30,13 @@ ex = None
 
 print("per-step mean us:", {n: round(float(d[2:, i].mean()), 2) for i, n in enumerate(names)}, "step total", round(float(d[2:].sum(1).mean()), 2))
 
+
+# backward scan (same stamp buffer, written by the next kernel)
+e.wm_loss_backward()
+torch.cuda.synchronize()
+st = e.tensor("debug.scan_stamps").cpu().numpy().astype(np.int64)
+st = (st[0::2] & 0xFFFFFFFF) | (st[1::2] << 32)
+d = np.diff(st[: T * 8 + 1].astype(np.float64)) / 1e3
+d = d.reshape(T, 8)
+names = ["S1 work", "S1 sync", "S2 work", "S2 sync", "S3 work", "S3 sync", "S4 work", "S4 sync"]
+print("backward per-step mean us:", {n: round(float(d[2:-1, i].mean()), 2) for i, n in enumerate(names)}, "step total", round(float(d[2:-1].sum(1).mean()), 2))
