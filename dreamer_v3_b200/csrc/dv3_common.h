@@ -124,7 +124,7 @@ void infer_mask(cudaStream_t s, const float* f, const float* ph, const float* pz
 
 // ---- conv helpers (dv3_conv.cu): 4x4 stride-2 "same" ------------------------------------------------
 // cols[(n,oy,ox), (ky,kx,c)] = img[n, 2oy-1+ky, 2ox-1+kx, c] (0 outside); img NHWC [n,H,W,C], out H/2 x W/2
-void im2col_k4s2(cudaStream_t s, const float* img, float* cols, int n, int H, int W, int C);
+void im2col_k4s2(cudaStream_t s, const float* img, float* cols, int n, int H, int W, int C, void* cols16 = nullptr);  // cols16: bf16 twin
 // img[n,y,x,c] (+)= sum over the (<=4) patches covering (y,x) of cols[(n,oy,ox),(ky,kx,c)] + bias[c] + add_const
 void col2im_k4s2(cudaStream_t s, const float* cols, float* img, int n, int H, int W, int C, const float* bias,
                  float add_const);

@@ -5,12 +5,15 @@
 //   conv bwd data   : dX = col2im(dY * W^T)            conv bwd weight: dW = im2col(X)^T * dY
 //   convT fwd       : Y = col2im(X * Wt^T) (+bias)     with Wt = Keras kernel [4,4,Cout,Cin] viewed [16*Cout, Cin]
 //   convT bwd data  : dX = im2col(dY) * Wt             convT bwd weight: dWt = im2col(dY)^T * X
+#include <cuda_bf16.h>
+
 #include "dv3_common.h"
 
 namespace dv3 {
 namespace {
 
-__global__ void im2col_kernel(const float* __restrict__ img, float* __restrict__ cols, int n, int H, int W, int C) {
+__global__ void im2col_kernel(const float* __restrict__ img, float* __restrict__ cols, int n, int H, int W, int C,
+                              __nv_bfloat16* __restrict__ cols16) {
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)n * Ho * Wo * 16 * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -25,6 +28,7 @@ __global__ void im2col_kernel(const float* __restrict__ img, float* __restrict__
     float v = 0.f;
     if (y >= 0 && y < H && x >= 0 && x < W) v = img[(((size_t)b * H + y) * W + x) * C + c];
     cols[i] = v;
+    if (cols16 != nullptr) cols16[i] = __float2bfloat16_rn(v);
   }
 }
 
@@ -58,7 +62,8 @@ __global__ void col2im_kernel(const float* __restrict__ cols, float* __restrict_
   }
 }
 
-__global__ void im2col_v4_kernel(const float4* __restrict__ img, float4* __restrict__ cols, int n, int H, int W, int C4) {
+__global__ void im2col_v4_kernel(const float4* __restrict__ img, float4* __restrict__ cols, int n, int H, int W, int C4,
+                                 uint2* __restrict__ cols16) {
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)n * Ho * Wo * 16 * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -73,6 +78,11 @@ __global__ void im2col_v4_kernel(const float4* __restrict__ img, float4* __restr
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (y >= 0 && y < H && x >= 0 && x < W) v = img[(((size_t)b * H + y) * W + x) * C4 + c];
     cols[i] = v;
+    if (cols16 != nullptr) {   // bf16 twin of the patch matrix for the TMA-fed contraction
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 o; o.x = *reinterpret_cast<uint32_t*>(&lo); o.y = *reinterpret_cast<uint32_t*>(&hi);
+      cols16[i] = o;
+    }
   }
 }
 
@@ -117,12 +127,13 @@ inline int grid_for(long long n) {
 
 }  // namespace
 
-void im2col_k4s2(cudaStream_t s, const float* img, float* cols, int n, int H, int W, int C) {
-  if (C % 4 == 0 && ((uintptr_t)img % 16 == 0) && ((uintptr_t)cols % 16 == 0))
+void im2col_k4s2(cudaStream_t s, const float* img, float* cols, int n, int H, int W, int C, void* cols16) {
+  if (C % 4 == 0 && ((uintptr_t)img % 16 == 0) && ((uintptr_t)cols % 16 == 0) && ((uintptr_t)cols16 % 8 == 0))
     im2col_v4_kernel<<<grid_for((long long)n * (H / 2) * (W / 2) * 16 * (C / 4)), 256, 0, s>>>(
-        reinterpret_cast<const float4*>(img), reinterpret_cast<float4*>(cols), n, H, W, C / 4);
+        reinterpret_cast<const float4*>(img), reinterpret_cast<float4*>(cols), n, H, W, C / 4, reinterpret_cast<uint2*>(cols16));
   else
-    im2col_kernel<<<grid_for((long long)n * (H / 2) * (W / 2) * 16 * C), 256, 0, s>>>(img, cols, n, H, W, C);
+    im2col_kernel<<<grid_for((long long)n * (H / 2) * (W / 2) * 16 * C), 256, 0, s>>>(img, cols, n, H, W, C,
+                                                                                       reinterpret_cast<__nv_bfloat16*>(cols16));
   count_launch();
 }
 void col2im_k4s2(cudaStream_t s, const float* cols, float* img, int n, int H, int W, int C, const float* bias,

@@ -288,6 +288,7 @@ void Engine::layout() {
       const std::string b = "wm.enc.conv" + std::to_string(l);
       enc_conv[l].pre = af(b + ".pre", {rows, cout});
       enc_conv[l].act = af(l == 3 ? "wm.enc_out" : b + ".act", l == 3 ? std::vector<int64_t>{Nl, E} : std::vector<int64_t>{rows, cout});
+      enc_conv[l].act16 = twin_alloc(enc_conv[l].act, (size_t)rows * cout);
       enc_conv[l].mean = af("", {rows});
       enc_conv[l].rstd = af("", {rows});
     }
@@ -338,6 +339,7 @@ void Engine::layout() {
   if (image) {
     const int c0 = 8 * m;
     dec_dense_out = af("wm.dec.dense_out", {Nl, 16 * c0});
+    dec_dense_out16 = twin_alloc(dec_dense_out, (size_t)Nl * 16 * c0);
     int hin = 4, cin = c0;
     for (int l = 0; l < 3; ++l) {
       const long long rows = Nl * (2 * hin) * (2 * hin);
@@ -345,14 +347,17 @@ void Engine::layout() {
       const std::string b = "wm.dec.convT" + std::to_string(l);
       dec_convT[l].pre = af(b + ".pre", {rows, cout});
       dec_convT[l].act = af(b + ".act", {rows, cout});
+      dec_convT[l].act16 = twin_alloc(dec_convT[l].act, (size_t)rows * cout);
       dec_convT[l].mean = af("", {rows});
       dec_convT[l].rstd = af("", {rows});
       hin *= 2; cin = cout;
     }
     const long long cols_elems = Nl * 4096LL * m > Nl * 1024LL * 16 * cfg.img_c ? Nl * 4096LL * m : Nl * 1024LL * 16 * cfg.img_c;
     cols = af("", {cols_elems});
+    cols16 = twin_alloc(cols, (size_t)cols_elems);
     const long long big = Nl * 1024LL * m > Nl * 128LL * m ? Nl * 1024LL * m : Nl * 128LL * m;
     conv_d0 = af("", {big}); conv_d1 = af("", {big}); conv_dpre = af("", {big});
+    conv_dpre16 = twin_alloc(conv_dpre, (size_t)big);
   } else {
     dec_act = alloc_mlp_act("wm.dec", Nl, L);
   }
@@ -750,9 +755,9 @@ void Engine::encoder_fwd() {
     ConvLayer& c = enc_conv[l];
     const int ho = c.hin / 2;
     const long long rows = (long long)N * ho * ho;
-    im2col_k4s2(cur, x, cols, N, c.hin, c.hin, c.cin);
-    mm(cols, 16 * c.cin, false, c.w, c.cout, false, c.pre, c.cout, (int)rows, c.cout, 16 * c.cin);
-    ln_silu_fwd(cur, c.pre, c.cout, c.g, c.b, c.act, c.cout, c.mean, c.rstd, 1, rows, c.cout);
+    im2col_k4s2(cur, x, cols, N, c.hin, c.hin, c.cin, cols16);
+    mm(cols, 16 * c.cin, false, c.w, c.cout, false, c.pre, c.cout, (int)rows, c.cout, 16 * c.cin, nullptr, 0.f, cols16);
+    ln_silu_fwd(cur, c.pre, c.cout, c.g, c.b, c.act, c.cout, c.mean, c.rstd, 1, rows, c.cout, c.act16);
     x = c.act;
   }
 }
@@ -769,12 +774,12 @@ void Engine::encoder_bwd(float* d_enc) {
     ConvLayer& c = enc_conv[l];
     const int ho = c.hin / 2;
     const long long rows = (long long)N * ho * ho;
-    ln_silu_bwd(cur, dcur, c.cout, c.pre, c.cout, c.mean, c.rstd, c.g, c.b, conv_dpre, c.cout, c.dg, c.db, 1, rows, c.cout);
+    ln_silu_bwd(cur, dcur, c.cout, c.pre, c.cout, c.mean, c.rstd, c.g, c.b, conv_dpre, c.cout, c.dg, c.db, 1, rows, c.cout, conv_dpre16);
     const float* xin = (l == 0) ? obs_sym : enc_conv[l - 1].act;
-    im2col_k4s2(cur, xin, cols, N, c.hin, c.hin, c.cin);
-    mm(cols, 16 * c.cin, true, conv_dpre, c.cout, false, c.dw, c.cout, 16 * c.cin, c.cout, (int)rows, nullptr, 1.f);
+    im2col_k4s2(cur, xin, cols, N, c.hin, c.hin, c.cin, cols16);
+    mm(cols, 16 * c.cin, true, conv_dpre, c.cout, false, c.dw, c.cout, 16 * c.cin, c.cout, (int)rows, nullptr, 1.f, cols16, conv_dpre16);
     if (l > 0) {
-      mm(conv_dpre, c.cout, false, c.w, c.cout, true, cols, 16 * c.cin, (int)rows, 16 * c.cin, c.cout);
+      mm(conv_dpre, c.cout, false, c.w, c.cout, true, cols, 16 * c.cin, (int)rows, 16 * c.cin, c.cout, nullptr, 0.f, conv_dpre16);
       float* dnext = bufs[flip]; flip ^= 1;
       col2im_k4s2(cur, cols, dnext, N, c.hin, c.hin, c.cin, nullptr, 0.f);
       dcur = dnext;
@@ -790,17 +795,19 @@ void Engine::decoder_fwd() {
   }
   const int c0 = 8 * cfg.cnn_mult;
   mm(hz, G + Z, false, dec_dense.w, 16 * c0, false, dec_dense_out, 16 * c0, N, 16 * c0, G + Z, dec_dense.bias);
+  if (dec_dense_out16 != nullptr) to_bf16(cur, dec_dense_out, 16 * c0, dec_dense_out16, 16 * c0, N, 16 * c0);
   const float* x = dec_dense_out;
+  const void* x16 = dec_dense_out16;
   for (int l = 0; l < 3; ++l) {
     ConvLayer& c = dec_convT[l];
     const long long rows_in = (long long)N * c.hin * c.hin, rows_out = rows_in * 4;
-    mm(x, c.cin, false, c.w, c.cin, true, cols, 16 * c.cout, (int)rows_in, 16 * c.cout, c.cin);
+    mm(x, c.cin, false, c.w, c.cin, true, cols, 16 * c.cout, (int)rows_in, 16 * c.cout, c.cin, nullptr, 0.f, x16);
     col2im_k4s2(cur, cols, c.pre, N, 2 * c.hin, 2 * c.hin, c.cout, nullptr, 0.f);
-    ln_silu_fwd(cur, c.pre, c.cout, c.g, c.b, c.act, c.cout, c.mean, c.rstd, 1, rows_out, c.cout);
-    x = c.act;
+    ln_silu_fwd(cur, c.pre, c.cout, c.g, c.b, c.act, c.cout, c.mean, c.rstd, 1, rows_out, c.cout, c.act16);
+    x = c.act; x16 = c.act16;
   }
   const int mi = dec_out_conv.in, ci = dec_out_conv.out;
-  mm(x, mi, false, dec_out_conv.w, mi, true, cols, 16 * ci, N * 1024, 16 * ci, mi);
+  mm(x, mi, false, dec_out_conv.w, mi, true, cols, 16 * ci, N * 1024, 16 * ci, mi, nullptr, 0.f, x16);
   col2im_k4s2(cur, cols, obs_loc, N, 64, 64, ci, dec_out_conv.bias, 0.5f);  // conv_transpose_atari.py:121
 }
 
@@ -812,22 +819,23 @@ void Engine::decoder_bwd() {
   }
   const int mi = dec_out_conv.in, ci = dec_out_conv.out;
   colsum_acc(cur, dloc, ci, (long long)N * 4096, ci, dec_out_conv.dbias);
-  im2col_k4s2(cur, dloc, cols, N, 64, 64, ci);
+  im2col_k4s2(cur, dloc, cols, N, 64, 64, ci, cols16);
   const float* x3 = dec_convT[2].act;
-  mm(cols, 16 * ci, true, x3, mi, false, dec_out_conv.dw, mi, 16 * ci, mi, N * 1024, nullptr, 1.f);
+  mm(cols, 16 * ci, true, x3, mi, false, dec_out_conv.dw, mi, 16 * ci, mi, N * 1024, nullptr, 1.f, cols16, dec_convT[2].act16);
   float* bufs[2] = {conv_d0, conv_d1};
   int flip = 0;
   float* dcur = bufs[flip]; flip ^= 1;
-  mm(cols, 16 * ci, false, dec_out_conv.w, mi, false, dcur, mi, N * 1024, mi, 16 * ci);
+  mm(cols, 16 * ci, false, dec_out_conv.w, mi, false, dcur, mi, N * 1024, mi, 16 * ci, nullptr, 0.f, cols16);
   for (int l = 2; l >= 0; --l) {
     ConvLayer& c = dec_convT[l];
     const long long rows_in = (long long)N * c.hin * c.hin, rows_out = rows_in * 4;
     ln_silu_bwd(cur, dcur, c.cout, c.pre, c.cout, c.mean, c.rstd, c.g, c.b, conv_dpre, c.cout, c.dg, c.db, 1, rows_out, c.cout);
-    im2col_k4s2(cur, conv_dpre, cols, N, 2 * c.hin, 2 * c.hin, c.cout);
+    im2col_k4s2(cur, conv_dpre, cols, N, 2 * c.hin, 2 * c.hin, c.cout, cols16);
     const float* xin = (l == 0) ? dec_dense_out : dec_convT[l - 1].act;
-    mm(cols, 16 * c.cout, true, xin, c.cin, false, c.dw, c.cin, 16 * c.cout, c.cin, (int)rows_in, nullptr, 1.f);
+    const void* xin16 = (l == 0) ? dec_dense_out16 : dec_convT[l - 1].act16;
+    mm(cols, 16 * c.cout, true, xin, c.cin, false, c.dw, c.cin, 16 * c.cout, c.cin, (int)rows_in, nullptr, 1.f, cols16, xin16);
     float* dnext = bufs[flip]; flip ^= 1;
-    mm(cols, 16 * c.cout, false, c.w, c.cin, false, dnext, c.cin, (int)rows_in, c.cin, 16 * c.cout);
+    mm(cols, 16 * c.cout, false, c.w, c.cin, false, dnext, c.cin, (int)rows_in, c.cin, 16 * c.cout, nullptr, 0.f, cols16);
     dcur = dnext;
   }
   dense_bwd(dec_dense, hz, G + Z, dcur, dec_dense.out, d_hz, G + Z, 1.f, true, N);

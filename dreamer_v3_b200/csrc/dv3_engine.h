@@ -42,6 +42,7 @@ struct ConvLayer {  // conv / convT (+LN) weights; kernel viewed as a [krows, kc
   int cin = 0, cout = 0, hin = 0;  // hin: input spatial side
   float *w = nullptr, *g = nullptr, *b = nullptr, *dw = nullptr, *dg = nullptr, *db = nullptr;
   float *pre = nullptr, *act = nullptr, *mean = nullptr, *rstd = nullptr;  // activations [n*hout*hout, cout]
+  void* act16 = nullptr;  // bf16 twin of act (tensor-core mode)
 };
 
 struct Engine {
@@ -98,6 +99,7 @@ struct Engine {
   float *rew_logits, *rew_E, *cont_logit, *obs_loc, *dec_dense_out;
   // conv scratch
   float *cols = nullptr, *conv_d0 = nullptr, *conv_d1 = nullptr, *conv_dpre = nullptr;
+  void *cols16 = nullptr, *conv_dpre16 = nullptr, *dec_dense_out16 = nullptr;  // bf16 twins (tensor-core mode)
   // ---- wm losses / backward ----
   float *L_dec, *L_rew, *L_con, *L_dyn, *L_rep, *L_tot, *wm_scalars;
   int32_t* rew_k;
