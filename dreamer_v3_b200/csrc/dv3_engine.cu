@@ -377,6 +377,11 @@ void Engine::layout() {
   dgx = af("wm.d_gx", {Nl, 3 * G}); dgh = af("wm.d_gh", {Nl, 3 * G});
   dh_in = af("wm.d_h_in", {Nl, G});
   dx_pre = af("wm.d_x_pre", {Nl, D});
+  if (Nl >= 512) {   // bf16 twins of the scan's saved activations / gradients: operands of the N-row weight-gradient contractions
+    twin_alloc(h_in, (size_t)Nl * G); twin_alloc(z_in, (size_t)Nl * Z); twin_alloc(u_act, (size_t)Nl * D); twin_alloc(p_act, (size_t)Nl * D);
+    twin_alloc(dpost_logits, (size_t)Nl * Z); twin_alloc(dp_pre, (size_t)Nl * D); twin_alloc(dgx, (size_t)Nl * 3 * G);
+    twin_alloc(dgh, (size_t)Nl * 3 * G); twin_alloc(dx_pre, (size_t)Nl * D);
+  }
   dprior_logits = af("wm.d_prior_logits", {Nl, Z});
   dq_pre = af("wm.d_q_pre", {Nl, D});
   d_enc_out = af("wm.d_enc_out", {Nl, E});

@@ -181,23 +181,37 @@ int Engine::wm_loss_backward(cudaStream_t s) {
     }
   }
   phase_mark("wmb.scan_bwd");
-  // weight gradients, one N-row contraction each; they are independent of one another -> four concurrent chains
+  // weight gradients, one N-row contraction each; they are independent of one another -> four concurrent chains.
+  // In tensor-core mode both operands of each get a bf16 copy first (the scan kernels write fp32 only), so the
+  // contractions run on the TMA-fed MN-major path.
+  auto tw = [&](const float* src, int cols_) -> const void* {
+    void* t = twin_of(src);
+    if (t != nullptr) to_bf16(cur, src, cols_, t, cols_, N, cols_);
+    return t;
+  };
+  const void* enc16 = image ? (const void*)enc_conv[3].act16 : (enc_act.act16.empty() ? nullptr : (const void*)enc_act.act16.back());
   run_branches({
       [&] {
-        dense_bwd(post_repr, p_act, D, dpost_logits, Z, nullptr, 0, 0.f, true, N);
-        mm(enc_out, E, true, dp_pre, D, false, Wp.dw, D, E, D, N, nullptr, 1.f);
-        mm(hz, G + Z, true, dp_pre, D, false, Wp.dw + (size_t)E * D, D, G, D, N, nullptr, 1.f);
+        const void* dpl16 = tw(dpost_logits, Z);
+        const void* dpp16 = tw(dp_pre, D);
+        mm(p_act, D, true, dpost_logits, Z, false, post_repr.dw, Z, D, Z, N, nullptr, 1.f, dpl16 ? tw(p_act, D) : nullptr, dpl16);
+        if (post_repr.dbias) colsum_acc(cur, dpost_logits, Z, N, Z, post_repr.dbias);
+        mm(enc_out, E, true, dp_pre, D, false, Wp.dw, D, E, D, N, nullptr, 1.f, dpp16 ? enc16 : nullptr, dpp16);
+        mm(hz, G + Z, true, dp_pre, D, false, Wp.dw + (size_t)E * D, D, G, D, N, nullptr, 1.f, dpp16 ? hz16 : nullptr, dpp16);
       },
       [&] {
-        mm(u_act, D, true, dgx, 3 * G, false, d_gru_K, 3 * G, D, 3 * G, N, nullptr, 1.f);
+        const void* dgx16 = tw(dgx, 3 * G);
+        mm(u_act, D, true, dgx, 3 * G, false, d_gru_K, 3 * G, D, 3 * G, N, nullptr, 1.f, dgx16 ? tw(u_act, D) : nullptr, dgx16);
         colsum_acc(cur, dgx, 3 * G, N, 3 * G, d_gru_b);
       },
       [&] {
-        mm(h_in, G, true, dgh, 3 * G, false, d_gru_U, 3 * G, G, 3 * G, N, nullptr, 1.f);
+        const void* dgh16 = tw(dgh, 3 * G);
+        mm(h_in, G, true, dgh, 3 * G, false, d_gru_U, 3 * G, G, 3 * G, N, nullptr, 1.f, dgh16 ? tw(h_in, G) : nullptr, dgh16);
         colsum_acc(cur, dgh, 3 * G, N, 3 * G, d_gru_b + 3 * G);
       },
       [&] {
-        mm(z_in, Z, true, dx_pre, D, false, Wx.dw, D, Z, D, N, nullptr, 1.f);
+        const void* dxp16 = tw(dx_pre, D);
+        mm(z_in, Z, true, dx_pre, D, false, Wx.dw, D, Z, D, N, nullptr, 1.f, dxp16 ? tw(z_in, Z) : nullptr, dxp16);
         mm(a_in, A, true, dx_pre, D, false, Wx.dw + (size_t)Z * D, D, A, D, N, nullptr, 1.f);
         // learned initial state: every is_first row (and every row at t = 0) starts from tanh(initial_h)
         mm(wf, 1, true, dh_in, G, false, dh0, G, 1, G, N);
