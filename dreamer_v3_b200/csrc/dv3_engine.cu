@@ -308,7 +308,6 @@ void Engine::layout() {
   z0 = af("wm.z0", {Z});
   q0_pre = af("", {D}); q0_act = af("", {D}); z0_logits = af("", {Z});
   z0_idx = ai("wm.z0_indices", {Zc});
-  gx_raw = af("", {B, 3 * G});
   Wt_zq = af("", {Z, D}); Wt_post_h = af("", {D, G}); Ut = af("", {3 * G, G}); Kt = af("", {3 * G, D}); Wt_pre_z = af("", {D, Z});
   scan_bar = (unsigned int*)alloc_bytes("", 256, 1, {}, 6, -1);
   scan_stamps = (unsigned long long*)alloc_bytes("debug.scan_stamps", (size_t)(T * 8 + 16) * 8, 1, {(long long)(T * 8 + 16) * 2}, 6, -1);

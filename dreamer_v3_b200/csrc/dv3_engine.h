@@ -82,7 +82,7 @@ struct Engine {
   float *in_obs, *in_actions, *in_is_first, *in_rewards, *in_is_term, *in_u_post, *in_u_dyn, *in_act_noise;
   float *in_dream_h0, *in_dream_z0;
   // ---- observe activations ----
-  float *obs_sym, *enc_out, *a_in, *wf, *actW, *h0, *z0, *q0_pre, *q0_act, *z0_logits, *gx_raw;
+  float *obs_sym, *enc_out, *a_in, *wf, *actW, *h0, *z0, *q0_pre, *q0_act, *z0_logits;
   int32_t* z0_idx;
   float *Wt_zq, *Wt_post_h, *Ut, *Kt, *Wt_pre_z, *dp_act_all, *du_all, *dh_tot;
   unsigned long long* scan_stamps = nullptr;

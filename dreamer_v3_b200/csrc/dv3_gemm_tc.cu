@@ -1,10 +1,11 @@
-// bf16 tensor-core GEMM for sm_100a: tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) with the accumulator in
-// TMEM, used for the large contractions of the hot path (dream rollout, heads, CNN patches, weight gradients).
+// bf16 tensor-core GEMM for sm_100a on fp32 operands: tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) with the accumulator in
+// TMEM. This is the fallback of the tensor-core mode for contractions whose operands have no bf16 copy in global memory
+// (255-wide logits and their gradients, a few small wgrads); everything else runs on the TMA-fed kernel in dv3_gemm_tma.cu.
 //
 //   C[M,N] (+)= op(A)[M,K] * op(B)[K,N] (+ bias[N])      same contract as gemm_f32 (fp32 in / fp32 out)
 //
 // The engine keeps fp32 master tensors, so the operands are converted on the way into shared memory: every
-// CTA (128 threads) loads fp32 tiles with coalesced 128-bit loads, rounds to bf16 and writes them in the
+// CTA (256 threads) loads fp32 tiles with coalesced 128-bit loads, rounds to bf16 and writes them in the
 // canonical K-major SWIZZLE_128B UMMA layout (8-row x 128-byte swizzle atoms); operands whose contraction
 // index is not contiguous in memory (B of a forward layer, both operands of a weight gradient) are transposed
 // by that fill. One elected thread issues the MMAs (4 x K=16 per 64-wide k-block) and commits them to an
@@ -21,9 +22,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;           // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int kStages = 2;           // fp32-B variant
-// bf16-shadow variant: ring depth = register sets = smem stages; narrow tiles can afford a deeper ring
-__host__ __device__ constexpr int shadow_depth(int bn) { return bn <= 64 ? 4 : (bn <= 128 ? 3 : 2); }
+constexpr int kStages = 2;
 constexpr int kTcThreads = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -111,42 +110,6 @@ struct Fill {
   }
 };
 
-// B operand already in bf16, K-major (weight shadow): plain 128-bit copies, 8 bf16 per task, no conversion.
-template <int ROWS>
-struct FillBf16 {
-  static constexpr int kTasks = ROWS * 8 / kTcThreads;
-  uint4 v[kTasks];
-  __device__ __forceinline__ void load(const __nv_bfloat16* __restrict__ src, int ld, int r0, int rmax, int k0, int kmax) {
-#pragma unroll
-    for (int i = 0; i < kTasks; ++i) {
-      const int task = threadIdx.x + i * kTcThreads;
-      const int r = task >> 3, kc = task & 7;
-      const int gr = r0 + r, gk = k0 + kc * 8;
-      uint4 t = make_uint4(0u, 0u, 0u, 0u);
-      if (gr < rmax && gk < kmax) {
-        const __nv_bfloat16* p = src + (size_t)gr * ld + gk;
-        if (gk + 7 < kmax) t = *reinterpret_cast<const uint4*>(p);   // ld and k0 are multiples of 8: 16-byte aligned
-        else {
-          unsigned short h[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) h[j] = (gk + j < kmax) ? reinterpret_cast<const unsigned short*>(p)[j] : (unsigned short)0;
-          t.x = h[0] | ((uint32_t)h[1] << 16); t.y = h[2] | ((uint32_t)h[3] << 16);
-          t.z = h[4] | ((uint32_t)h[5] << 16); t.w = h[6] | ((uint32_t)h[7] << 16);
-        }
-      }
-      v[i] = t;
-    }
-  }
-  __device__ __forceinline__ void store(uint32_t tile) const {
-#pragma unroll
-    for (int i = 0; i < kTasks; ++i) {
-      const int task = threadIdx.x + i * kTcThreads;
-      const int r = task >> 3, kc = task & 7;
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + sw128_chunk_off(r, kc)), "r"(v[i].x), "r"(v[i].y), "r"(v[i].z), "r"(v[i].w) : "memory");
-    }
-  }
-};
-
 // ---- descriptors ---------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B: start>>4 | LBO(=1)<<16 | SBO(=1024>>4)<<32 | version 1 | layout 2
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -193,11 +156,11 @@ struct TcSmem {
   uint32_t tmem_base;
 };
 
-template <int BN, bool TA, bool TB, bool BH>
+template <int BN, bool TA, bool TB>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(GemmArgs g, int k_per_split, int vecA, int vecB, int use_atomic) {
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
-  constexpr int STAGES = BH ? shadow_depth(BN) : kStages;
+  constexpr int STAGES = kStages;
   using SmemT = TcSmem<BN, STAGES>;
   SmemT& sm = *reinterpret_cast<SmemT*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -243,42 +206,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(GemmArgs g, int 
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sm.bar[s])) : "memory");
     }
   };
-  if constexpr (BH) {
-    // B comes from the bf16 K-major weight shadow: half the bytes and no conversion, which frees enough registers to
-    // keep TWO k-blocks of global loads in flight per thread
-    const __nv_bfloat16* Bh = reinterpret_cast<const __nv_bfloat16*>(g.Bh);
-    constexpr int DEPTH = STAGES;
-    Fill<BM, TA> fa[DEPTH];
-    FillBf16<BN> fb[DEPTH];
-#pragma unroll
-    for (int u = 0; u < DEPTH; ++u) {
-      if (u < nkb) {
-        fa[u].load(g.A, g.lda, m0, g.M, kbeg + u * BK, kend, vecA);
-        fb[u].load(Bh, g.ldbh, n0, g.N, kbeg + u * BK, kend);
-      }
-    }
-#pragma unroll 1
-    for (int kb0 = 0; kb0 < nkb; kb0 += DEPTH) {
-#pragma unroll
-      for (int u = 0; u < DEPTH; ++u) {
-        const int kb = kb0 + u;
-        if (kb < nkb) {
-          const int s = u;  // stage index == register set index == kb % DEPTH
-          if (kb >= DEPTH) mbar_wait(&sm.bar[s], (uint32_t)(((kb / DEPTH) - 1) & 1));
-          fa[u].store(smem_u32(sm.a[s]), vecA);
-          fb[u].store(smem_u32(sm.b[s]));
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncthreads();
-          issue_mma(kb, s);
-          if (kb + DEPTH < nkb) {
-            const int k0 = kbeg + (kb + DEPTH) * BK;
-            fa[u].load(g.A, g.lda, m0, g.M, k0, kend, vecA);
-            fb[u].load(Bh, g.ldbh, n0, g.N, k0, kend);
-          }
-        }
-      }
-    }
-  } else {
+  {
     Fill<BM, TA> fa;
     Fill<BN, !TB> fb;
     fa.load(g.A, g.lda, m0, g.M, kbeg, kend, vecA);
@@ -563,26 +491,23 @@ void launch_tc(cudaStream_t s, const GemmArgs& g) {
   const int vA = ((uintptr_t)g.A % 16 == 0) && (g.lda % 4 == 0);
   const int vB = ((uintptr_t)g.B % 16 == 0) && (g.ldb % 4 == 0);
   const bool bh = g.Bh != nullptr && (g.ldbh % 8 == 0) && ((uintptr_t)g.Bh % 16 == 0);
-  const size_t smem = (bh ? sizeof(TcSmem<BN, shadow_depth(BN)>) : sizeof(TcSmem<BN, kStages>)) + 1024;
+  const size_t smem = sizeof(TcSmem<BN, kStages>) + 1024;
   dim3 grid(gx, gy, splits), block(kTcThreads);
 #define DV3_TC_LAUNCH(TA_, TB_)                                                                                   \
   do {                                                                                                            \
     static bool configured = false;                                                                               \
     if (!configured) {                                                                                            \
-      cudaFuncSetAttribute(gemm_tc_kernel<BN, TA_, TB_, BH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      cudaFuncSetAttribute(gemm_tc_kernel<BN, TA_, TB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
       configured = true;                                                                                          \
     }                                                                                                             \
-    launch_pdl(gemm_tc_kernel<BN, TA_, TB_, BH_>, grid, block, smem, s, g, kps, vA, vB, use_atomic);               \
+    launch_pdl(gemm_tc_kernel<BN, TA_, TB_>, grid, block, smem, s, g, kps, vA, vB, use_atomic);                    \
   } while (0)
-#define BH_ false
   if (!bh) {
     if (!g.ta && !g.tb) DV3_TC_LAUNCH(false, false);
     else if (!g.ta && g.tb) DV3_TC_LAUNCH(false, true);
     else if (g.ta && !g.tb) DV3_TC_LAUNCH(true, false);
     else DV3_TC_LAUNCH(true, true);
   }
-#undef BH_
-#define BH_ true
   if (bh) {
     const size_t smem_ws = sizeof(WsSmem<BN>) + 1024;
     if (!g.ta) {
@@ -595,7 +520,6 @@ void launch_tc(cudaStream_t s, const GemmArgs& g) {
       launch_pdl(gemm_tc_ws_kernel<BN, true>, grid, dim3(kWsThreads), smem_ws, s, g, kps, vA, use_atomic);
     }
   }
-#undef BH_
 #undef DV3_TC_LAUNCH
   count_launch();
 }

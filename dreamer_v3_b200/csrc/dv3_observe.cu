@@ -49,7 +49,7 @@ int Engine::observe_forward(cudaStream_t s) {
     sp.W_post = Wp.w; sp.post_g = Wp.g; sp.post_b = Wp.b; sp.W_zq = post_repr.w; sp.b_zq = post_repr.bias;
     sp.is_first = in_is_first; sp.actW = actW; sp.u_post = in_u_post; sp.h0 = h0; sp.z0_idx = z0_idx;
     sp.h_in = h_in; sp.z_in = z_in; sp.x_pre = x_pre; sp.x_mean = x_mean; sp.x_rstd = x_rstd; sp.u_act = u_act;
-    sp.gx_raw = gx_raw; sp.gates = gx; sp.gh = gh; sp.hz = hz; sp.p_pre = p_pre; sp.p_mean = p_mean; sp.p_rstd = p_rstd;
+    sp.gates = gx; sp.gh = gh; sp.hz = hz; sp.p_pre = p_pre; sp.p_mean = p_mean; sp.p_rstd = p_rstd;
     sp.p_act = p_act; sp.post_logits = post_logits; sp.post_probs = post_probs; sp.z_idx = z_idx;
     sp.stamps = std::getenv("DV3_SCAN_STAMPS") ? scan_stamps : nullptr;
     sp.bar = scan_bar;

@@ -56,7 +56,6 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_fwd_kernel(ScanFwdPa
   const int W = G + Z;
   const int nblk = gridDim.x, blk = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gtid = blk * kThreads + threadIdx.x, gthreads = nblk * kThreads;
   const int tasks_unit = (G + 7) / 8;                 // stage B: 8 GRU units x 3 gates = 24 columns per task
   const int tasks_gate = (3 * G + 31) / 32, tasks_D = (D + 31) / 32, tasks_Z = (Z + 31) / 32;
   const float* W_post_h = p.W_post + (size_t)E * D;

@@ -24,7 +24,6 @@ struct ScanFwdParams {
   const int32_t* z0_idx; // [Zc]
   // state / saved activations (all [B, T, ...] B-major)
   float* h_in; float* z_in; float* x_pre; float* x_mean; float* x_rstd; float* u_act;
-  float* gx_raw;         // [B, 3G] scratch
   float* gates;          // [B, T, 3G] (z, r, c)
   float* gh;             // [B, T, 3G]
   float* hz;             // [B, T, G + Z]

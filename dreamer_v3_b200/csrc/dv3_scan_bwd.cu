@@ -99,7 +99,6 @@ __device__ __forceinline__ void cta_lnbwd_stage_t(float* in_s, const float* dy, 
       const int b = bb + r * kWarps;
       if (b >= kRows) continue;
       const float m1 = s1[r] / (float)D, m2 = s2[r] / (float)D;
-#pragma unroll
       const bool row_ok = b < B, wr = out != nullptr && row_ok;
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {

@@ -1,7 +1,5 @@
 // Shared device pieces of the persistent scan kernels (forward: dv3_scan.cu, backward: dv3_scan_bwd.cu).
 #pragma once
-#include <cooperative_groups.h>
-
 #include "dv3_device.cuh"
 #include "dv3_scan.h"
 
@@ -19,8 +17,6 @@ struct Smem {
   float in_chunk[kWarps][kKC][kInLd];   // 80 KB
   float red[kWarps][kRows][kRedLd];     // 16.5 KB
   float tile[kRows][kRedLd];            // reduced output tile
-  float mean[kRows], rstd[kRows];
-  float s1[kRows], s2[kRows];         // LayerNorm-backward row statistics
 };
 
 // One task: out_tile[b][j] = sum_k in(b,k) * W[k*ldw + c0 + j], j < 32, k < K. `in_fn(b, k)` produces the input
@@ -95,36 +91,6 @@ __device__ __forceinline__ void task_gemv_col(Smem& sm, const float* __restrict_
   }
   __syncthreads();
 }
-
-// LayerNorm statistics of rows x[b*ldx .. +D) for b < B, by the whole CTA -> sm.mean / sm.rstd. Each warp keeps its
-// row in registers (D <= 1024): all loads are issued together, so the cost is one L2 latency, not a chain of them.
-__device__ __forceinline__ void cta_ln_stats(Smem& sm, const float* x, int ldx, int B, int D) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int b = warp; b < B; b += kWarps) {
-    const float* xr = x + (size_t)b * ldx;
-    float v[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int c = lane + 32 * i;
-      v[i] = (c < D) ? __ldcg(xr + c) : 0.f;
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) s += v[i];
-    const float mean = warp_sum(s) / (float)D;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float d = (lane + 32 * i < D) ? v[i] - mean : 0.f;
-      q += d * d;
-    }
-    const float var = warp_sum(q) / (float)D;
-    if (lane == 0) { sm.mean[b] = mean; sm.rstd[b] = rsqrtf(var + DV3_LN_EPS); }
-  }
-  __syncthreads();
-}
-
-
 
 // ---- grid-wide barrier for the cooperative (co-resident) scan kernels --------------------------------------------
 // One monotonically increasing counter in global memory (zeroed by the host before the launch): every CTA adds 1 and
