@@ -180,6 +180,82 @@ void launch_tile(cudaStream_t s, const GemmArgs& g) {
   count_launch();
 }
 
+// ---- degenerate shapes of the hot path ---------------------------------------------------------------------------
+// Heads with a handful of outputs (actor mean / std / logits, continue logit: N <= 32) and rank-few updates (the action
+// part of the pre-GRU layer, input gradients of those heads: K <= 32) are latency-bound launches in a tiled GEMM
+// (10 us per node in the replayed graph for [1024 x 256] x [256 x 1]); these two kernels do them in one pass.
+
+// C[M, N] (+)= A[M, K] * op(B)[K, N] (+ bias), N <= 32: one warp per row, lanes stride K, N shuffle reductions
+template <bool TB>
+__global__ void __launch_bounds__(256) gemm_skinny_n_kernel(GemmArgs g) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp0; r < g.M; r += nwarps) {
+    const float* a = g.A + (size_t)r * g.lda;
+    float acc[32];
+#pragma unroll
+    for (int n = 0; n < 32; ++n) acc[n] = 0.f;
+    for (int k = lane; k < g.K; k += 32) {
+      const float av = a[k];
+#pragma unroll
+      for (int n = 0; n < 32; ++n)
+        if (n < g.N) acc[n] = fmaf(av, TB ? g.B[(size_t)n * g.ldb + k] : g.B[(size_t)k * g.ldb + n], acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+      if (n < g.N) {
+        float v = acc[n];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) {
+          if (g.bias != nullptr) v += g.bias[n];
+          float* dst = g.C + (size_t)r * g.ldc + n;
+          *dst = (g.beta != 0.f) ? *dst + v : v;
+        }
+      }
+    }
+  }
+}
+
+// C[M, N] (+)= A[M, K] * op(B)[K, N] (+ bias), K <= 32: one thread per output element
+template <bool TB>
+__global__ void __launch_bounds__(256) gemm_skinny_k_kernel(GemmArgs g) {
+  pdl_trigger();
+  pdl_wait();
+  const long long total = (long long)g.M * g.N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / g.N;
+    const int c = (int)(i - r * g.N);
+    const float* a = g.A + (size_t)r * g.lda;
+    float v = g.bias != nullptr ? g.bias[c] : 0.f;
+    for (int k = 0; k < g.K; ++k) v = fmaf(a[k], TB ? g.B[(size_t)c * g.ldb + k] : g.B[(size_t)k * g.ldb + c], v);
+    float* dst = g.C + (size_t)r * g.ldc + c;
+    *dst = (g.beta != 0.f) ? *dst + v : v;
+  }
+}
+
+bool gemm_skinny(cudaStream_t s, const GemmArgs& g) {
+  if (g.ta || g.M < 64) return false;
+  if (g.N <= 32 && g.K >= 32) {
+    const int grid = (int)min((long long)148 * 8, ((long long)g.M + 7) / 8);
+    if (g.tb) launch_pdl(gemm_skinny_n_kernel<true>, dim3(grid), dim3(256), 0, s, g);
+    else launch_pdl(gemm_skinny_n_kernel<false>, dim3(grid), dim3(256), 0, s, g);
+    count_launch();
+    return true;
+  }
+  if (g.K <= 32 && g.N >= 32) {
+    const int grid = (int)min((long long)148 * 16, ((long long)g.M * g.N + 255) / 256);
+    if (g.tb) launch_pdl(gemm_skinny_k_kernel<true>, dim3(grid), dim3(256), 0, s, g);
+    else launch_pdl(gemm_skinny_k_kernel<false>, dim3(grid), dim3(256), 0, s, g);
+    count_launch();
+    return true;
+  }
+  return false;
+}
+
 }  // namespace
 
 void gemm_f32(cudaStream_t s, const GemmArgs& g) {
@@ -188,6 +264,7 @@ void gemm_f32(cudaStream_t s, const GemmArgs& g) {
     if (g.beta == 0.f) zero_2d(s, g.C, g.M, g.N, g.ldc);
     return;
   }
+  if (gemm_skinny(s, g)) return;
   if (g.M <= 16) {
     launch_tile<16, 128, 16, 1, 8>(s, g);
   } else if (g.M <= 64 || g.N <= 64 || (long long)cdiv(g.M, 128) * cdiv(g.N, 128) < kNumSMs) {
@@ -205,6 +282,10 @@ bool pdl_enabled() {
 }
 
 void gemm_dispatch(cudaStream_t s, const GemmArgs& g, int mode) {
+  if (g.M > 0 && g.N > 0 && g.K > 0 && !g.ta && g.M >= 64 && ((g.N <= 32 && g.K >= 32) || (g.K <= 32 && g.N >= 32)) && mode != 2) {
+    gemm_f32(s, g);   // degenerate shapes: skinny kernels, exact fp32 in every mode
+    return;
+  }
   if (mode >= 1 && g.M > 0 && g.N > 0 && g.K > 0 && gemm_tma_eligible(g) && (mode == 2 || gemm_tc_eligible(g)) && gemm_tma(s, g)) return;
   if (mode == 1 && g.M > 0 && g.N > 0 && g.K > 0 && gemm_tc_eligible(g)) gemm_tc(s, g);
   else if (mode == 2 && g.M > 0 && g.N > 0 && g.K > 0) gemm_tc(s, g);  // forced (tests)

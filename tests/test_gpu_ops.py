@@ -76,7 +76,9 @@ def test_value_targets_and_percentiles():
 
 
 @pytest.mark.parametrize("M,N,K", [(16, 768, 256), (16, 1024, 1280), (1024, 256, 1280), (1024, 255, 256), (1, 256, 1024),
-                                   (1024, 1, 256), (333, 77, 45), (4096, 512, 48), (128, 128, 16), (257, 129, 1031)])
+                                   (1024, 1, 256), (333, 77, 45), (4096, 512, 48), (128, 128, 16), (257, 129, 1031),
+                                   # degenerate shapes of the heads: few outputs (skinny-N kernel) / rank-few updates (skinny-K)
+                                   (1000, 18, 256), (16384, 1, 256), (1024, 256, 1), (1024, 1024, 6), (300, 32, 1280), (64, 40, 32)])
 def test_gemm_f32_all_transposes(M, N, K):
     from dreamer_v3_b200 import ops
     rng = np.random.default_rng(M * 7 + N * 3 + K)
