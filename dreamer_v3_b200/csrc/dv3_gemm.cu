@@ -185,34 +185,67 @@ void launch_tile(cudaStream_t s, const GemmArgs& g) {
 // part of the pre-GRU layer, input gradients of those heads: K <= 32) are latency-bound launches in a tiled GEMM
 // (10 us per node in the replayed graph for [1024 x 256] x [256 x 1]); these two kernels do them in one pass.
 
-// C[M, N] (+)= A[M, K] * op(B)[K, N] (+ bias), N <= 32: one warp per row, lanes stride K, N shuffle reductions
-template <bool TB>
-__global__ void __launch_bounds__(256) gemm_skinny_n_kernel(GemmArgs g) {
+// C[M, N] (+)= A[M, K] * op(B)[K, N] (+ bias), N <= NMAX <= 32: one warp per row, lanes stride K (128-bit loads when the
+// row is aligned), N shuffle reductions; two rows per warp in flight
+template <bool TB, int NMAX>
+__global__ void __launch_bounds__(256) gemm_skinny_n_kernel(GemmArgs g, int vec) {
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long r = warp0; r < g.M; r += nwarps) {
-    const float* a = g.A + (size_t)r * g.lda;
-    float acc[32];
+  for (long long r0 = warp0 * 2; r0 < g.M; r0 += nwarps * 2) {
+    float acc[2][NMAX];
 #pragma unroll
-    for (int n = 0; n < 32; ++n) acc[n] = 0.f;
-    for (int k = lane; k < g.K; k += 32) {
-      const float av = a[k];
+    for (int q = 0; q < 2; ++q)
 #pragma unroll
-      for (int n = 0; n < 32; ++n)
-        if (n < g.N) acc[n] = fmaf(av, TB ? g.B[(size_t)n * g.ldb + k] : g.B[(size_t)k * g.ldb + n], acc[n]);
+      for (int n = 0; n < NMAX; ++n) acc[q][n] = 0.f;
+    const bool two = r0 + 1 < g.M;
+    const float* a0 = g.A + (size_t)r0 * g.lda;
+    const float* a1 = g.A + (size_t)(two ? r0 + 1 : r0) * g.lda;
+    if (vec) {
+      for (int k = 4 * lane; k < g.K; k += 128) {
+        const float4 x0 = *reinterpret_cast<const float4*>(a0 + k);
+        const float4 x1 = *reinterpret_cast<const float4*>(a1 + k);
+        const float xs0[4] = {x0.x, x0.y, x0.z, x0.w}, xs1[4] = {x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int n = 0; n < NMAX; ++n) {
+            if (n < g.N) {
+              const float w = TB ? g.B[(size_t)n * g.ldb + k + j] : g.B[(size_t)(k + j) * g.ldb + n];
+              acc[0][n] = fmaf(xs0[j], w, acc[0][n]);
+              acc[1][n] = fmaf(xs1[j], w, acc[1][n]);
+            }
+          }
+        }
+      }
+    } else {
+      for (int k = lane; k < g.K; k += 32) {
+        const float x0 = a0[k], x1 = a1[k];
+#pragma unroll
+        for (int n = 0; n < NMAX; ++n) {
+          if (n < g.N) {
+            const float w = TB ? g.B[(size_t)n * g.ldb + k] : g.B[(size_t)k * g.ldb + n];
+            acc[0][n] = fmaf(x0, w, acc[0][n]);
+            acc[1][n] = fmaf(x1, w, acc[1][n]);
+          }
+        }
+      }
     }
 #pragma unroll
-    for (int n = 0; n < 32; ++n) {
+    for (int n = 0; n < NMAX; ++n) {
       if (n < g.N) {
-        float v = acc[n];
+        float v0 = acc[0][n], v1 = acc[1][n];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) {
+        for (int o = 16; o > 0; o >>= 1) {
+          v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+          v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        }
+        if (lane < 2 && (lane == 0 || two)) {
+          float v = lane == 0 ? v0 : v1;
           if (g.bias != nullptr) v += g.bias[n];
-          float* dst = g.C + (size_t)r * g.ldc + n;
+          float* dst = g.C + (size_t)(r0 + lane) * g.ldc + n;
           *dst = (g.beta != 0.f) ? *dst + v : v;
         }
       }
@@ -240,9 +273,13 @@ __global__ void __launch_bounds__(256) gemm_skinny_k_kernel(GemmArgs g) {
 bool gemm_skinny(cudaStream_t s, const GemmArgs& g) {
   if (g.ta || g.M < 64) return false;
   if (g.N <= 32 && g.K >= 32) {
-    const int grid = (int)min((long long)148 * 8, ((long long)g.M + 7) / 8);
-    if (g.tb) launch_pdl(gemm_skinny_n_kernel<true>, dim3(grid), dim3(256), 0, s, g);
-    else launch_pdl(gemm_skinny_n_kernel<false>, dim3(grid), dim3(256), 0, s, g);
+    const int grid = (int)min((long long)148 * 8, ((long long)g.M + 15) / 16);
+    const int vec = ((uintptr_t)g.A % 16 == 0) && (g.lda % 4 == 0) && (g.K % 4 == 0);
+#define DV3_SKINNY_N(TB_, NM_) launch_pdl(gemm_skinny_n_kernel<TB_, NM_>, dim3(grid), dim3(256), 0, s, g, vec)
+    if (g.N == 1) { if (g.tb) DV3_SKINNY_N(true, 1); else DV3_SKINNY_N(false, 1); }
+    else if (g.N <= 8) { if (g.tb) DV3_SKINNY_N(true, 8); else DV3_SKINNY_N(false, 8); }
+    else { if (g.tb) DV3_SKINNY_N(true, 32); else DV3_SKINNY_N(false, 32); }
+#undef DV3_SKINNY_N
     count_launch();
     return true;
   }
