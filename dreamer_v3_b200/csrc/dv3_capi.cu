@@ -214,6 +214,12 @@ int dv3_op_gemm_shadow(const float* A, int lda, int ta, const void* Bh, int ldbh
   dv3::gemm_tc(S(stream), g);
   return op_done();
 }
+int dv3_op_ln_silu_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                       float* dx, float* dgamma, float* dbeta, int64_t rows, int D, void* stream) {
+  if (D > 1024) return -1;
+  dv3::ln_silu_bwd(S(stream), dy, D, x, D, mean, rstd, gamma, beta, dx, D, dgamma, dbeta, 1, rows, D);
+  return op_done();
+}
 int dv3_op_to_bf16(const float* src, int lds, void* dst, int ldd, int64_t rows, int cols, void* stream) {
   dv3::to_bf16(S(stream), src, lds, dst, ldd, rows, cols);
   return op_done();

@@ -194,6 +194,143 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ dy, int lddy, const
   }
 }
 
+// ---- vectorised LayerNorm + SiLU (D a multiple of 128, 16-byte aligned rows): lane owns V chunks of 4 consecutive columns,
+// chunk i at column 4 * (lane + 32 i); all loads of a row are 128-bit and issued together ----
+__device__ __forceinline__ void store_bf16x4(__nv_bfloat16* p, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 o; o.x = *reinterpret_cast<uint32_t*>(&lo); o.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = o;
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) ln_silu_fwd_v4_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float* __restrict__ y, int ldy,
+                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out, int sstride,
+                                                             long long rows, __nv_bfloat16* __restrict__ y16) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int D = V * 128;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float4 g[V], be[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    g[i] = *reinterpret_cast<const float4*>(gamma + 4 * (lane + 32 * i));
+    be[i] = *reinterpret_cast<const float4*>(beta + 4 * (lane + 32 * i));
+  }
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const float* xr = x + (size_t)r * ldx;
+    float4 v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i] = *reinterpret_cast<const float4*>(xr + 4 * (lane + 32 * i));
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + DV3_LN_EPS);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c0 = 4 * (lane + 32 * i);
+      float4 o;
+      float n;
+      n = (v[i].x - mean) * rstd * g[i].x + be[i].x; o.x = n * sigmoidf_(n);
+      n = (v[i].y - mean) * rstd * g[i].y + be[i].y; o.y = n * sigmoidf_(n);
+      n = (v[i].z - mean) * rstd * g[i].z + be[i].z; o.z = n * sigmoidf_(n);
+      n = (v[i].w - mean) * rstd * g[i].w + be[i].w; o.w = n * sigmoidf_(n);
+      *reinterpret_cast<float4*>(y + (size_t)r * ldy + c0) = o;
+      if (y16 != nullptr) store_bf16x4(y16 + (size_t)r * ldy + c0, o.x, o.y, o.z, o.w);
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[r * sstride] = mean;
+      if (rstd_out) rstd_out[r * sstride] = rstd;
+    }
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) ln_silu_bwd_v4_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
+                                                             const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             float* __restrict__ dx, int lddx, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbeta, int sstride, long long rows,
+                                                             __nv_bfloat16* __restrict__ dx16) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int D = V * 128;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float4 g[V], be[V], ag[V], ab[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    g[i] = *reinterpret_cast<const float4*>(gamma + 4 * (lane + 32 * i));
+    be[i] = *reinterpret_cast<const float4*>(beta + 4 * (lane + 32 * i));
+    ag[i] = make_float4(0.f, 0.f, 0.f, 0.f); ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const float mean = mean_in[r * sstride], rstd = rstd_in[r * sstride];
+    float4 xh[V], dh[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      xh[i] = *reinterpret_cast<const float4*>(x + (size_t)r * ldx + 4 * (lane + 32 * i));
+      dh[i] = *reinterpret_cast<const float4*>(dy + (size_t)r * lddy + 4 * (lane + 32 * i));
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+#define DV3_LNB(c_)                                                              \
+      {                                                                          \
+        const float xhat = (xh[i].c_ - mean) * rstd;                             \
+        const float n = xhat * g[i].c_ + be[i].c_;                               \
+        const float sg = sigmoidf_(n);                                           \
+        const float dn = dh[i].c_ * (sg * (1.f + n * (1.f - sg)));               \
+        ag[i].c_ += dn * xhat; ab[i].c_ += dn;                                   \
+        xh[i].c_ = xhat; dh[i].c_ = dn * g[i].c_;                                \
+        s1 += dh[i].c_; s2 += dh[i].c_ * xhat;                                   \
+      }
+      DV3_LNB(x) DV3_LNB(y) DV3_LNB(z) DV3_LNB(w)
+#undef DV3_LNB
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+    if (dx != nullptr) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c0 = 4 * (lane + 32 * i);
+        float4 o;
+        o.x = rstd * (dh[i].x - s1 - xh[i].x * s2); o.y = rstd * (dh[i].y - s1 - xh[i].y * s2);
+        o.z = rstd * (dh[i].z - s1 - xh[i].z * s2); o.w = rstd * (dh[i].w - s1 - xh[i].w * s2);
+        *reinterpret_cast<float4*>(dx + (size_t)r * lddx + c0) = o;
+        if (dx16 != nullptr) store_bf16x4(dx16 + (size_t)r * lddx + c0, o.x, o.y, o.z, o.w);
+      }
+    }
+  }
+  if (dgamma != nullptr) {
+    __shared__ float sdg[D], sdb[D];
+    for (int c = threadIdx.x; c < D; c += blockDim.x) { sdg[c] = 0.f; sdb[c] = 0.f; }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c0 = 4 * (lane + 32 * i);
+      atomicAdd(&sdg[c0], ag[i].x); atomicAdd(&sdg[c0 + 1], ag[i].y); atomicAdd(&sdg[c0 + 2], ag[i].z); atomicAdd(&sdg[c0 + 3], ag[i].w);
+      atomicAdd(&sdb[c0], ab[i].x); atomicAdd(&sdb[c0 + 1], ab[i].y); atomicAdd(&sdb[c0 + 2], ab[i].z); atomicAdd(&sdb[c0 + 3], ab[i].w);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      atomicAdd(&dgamma[c], sdg[c]);
+      atomicAdd(&dbeta[c], sdb[c]);
+    }
+  }
+}
+
 // ---- GRU cell ---------------------------------------------------------------------------------------
 __global__ void gru_fwd_kernel(float* __restrict__ gx, int ldgx, const float* __restrict__ gh, int ldgh,
                                const float* __restrict__ h_prev, int ldhp, float* __restrict__ h_out, int ldho,
@@ -455,6 +592,14 @@ void ln_silu_fwd(cudaStream_t s, const float* x, int ldx, const float* gamma, co
   if (rows <= 0) return;
   const int grid = grid_for(rows, kThreads / 32, 148 * 8);
   __nv_bfloat16* y16 = reinterpret_cast<__nv_bfloat16*>(y16_);
+  if ((D == 256 || D == 512 || D == 1024) && ldx % 4 == 0 && ldy % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0 &&
+      (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0 && (uintptr_t)y16_ % 8 == 0) {
+#define DV3_LN_FWD4(V_) launch_pdl(ln_silu_fwd_v4_kernel<V_>, dim3(grid), dim3(kThreads), 0, s, x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, y16)
+    if (D == 256) DV3_LN_FWD4(2); else if (D == 512) DV3_LN_FWD4(4); else DV3_LN_FWD4(8);
+#undef DV3_LN_FWD4
+    count_launch();
+    return;
+  }
 #define DV3_LN_FWD(E_) launch_pdl(ln_silu_fwd_kernel<E_>, dim3(grid), dim3(kThreads), 0, s, x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, D, y16)
   if (D <= 32) DV3_LN_FWD(1);
   else if (D <= 64) DV3_LN_FWD(2);
@@ -471,6 +616,15 @@ void ln_silu_bwd(cudaStream_t s, const float* dy, int lddy, const float* x, int 
   if (rows <= 0) return;
   const int grid = grid_for(rows, kThreads / 32, 148 * 4);
   __nv_bfloat16* dx16 = reinterpret_cast<__nv_bfloat16*>(dx16_);
+  if ((D == 256 || D == 512 || D == 1024) && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)dy % 16 == 0 &&
+      (uintptr_t)dx % 16 == 0 && (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0 && (uintptr_t)dx16_ % 8 == 0) {
+    const int grid4 = grid_for(rows, kThreads / 32, 148 * 8);
+#define DV3_LN_BWD4(V_) launch_pdl(ln_silu_bwd_v4_kernel<V_>, dim3(grid4), dim3(kThreads), 0, s, dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, dx16)
+    if (D == 256) DV3_LN_BWD4(2); else if (D == 512) DV3_LN_BWD4(4); else DV3_LN_BWD4(8);
+#undef DV3_LN_BWD4
+    count_launch();
+    return;
+  }
 #define DV3_LN_BWD(E_) launch_pdl(ln_silu_bwd_kernel<E_>, dim3(grid), dim3(kThreads), 0, s, dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, D, dx16)
   if (D <= 32) DV3_LN_BWD(1);
   else if (D <= 64) DV3_LN_BWD(2);

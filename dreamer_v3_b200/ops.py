@@ -112,6 +112,20 @@ def gemm_weight_shadow(A, W, ta=False, bias=None, C_=None, beta=0.0):
     return run
 
 
+def ln_silu_bwd(dy, x, gamma, beta, dgamma=None, dbeta=None):
+    """dx of y = silu(LayerNorm(x)) (row statistics recomputed here with torch for the probe); accumulates dgamma / dbeta."""
+    x = _f32(x)
+    mean = x.mean(1).contiguous()
+    rstd = torch.rsqrt(x.var(1, unbiased=False) + 1e-3).contiguous()
+    dx = torch.empty_like(x)
+
+    def run():
+        _ok(_lib.load().dv3_op_ln_silu_bwd(_p(_f32(dy)), _p(x), _p(mean), _p(rstd), _p(_f32(gamma)), _p(_f32(beta)), _p(dx), _p(dgamma),
+                                           _p(dbeta), x.shape[0], x.shape[1], _s()), "dv3_op_ln_silu_bwd")
+        return dx
+    return run
+
+
 def to_bf16(x):
     """bf16 copy of a 2-D fp32 CUDA tensor, made by the library's conversion kernel."""
     x = _f32(x)

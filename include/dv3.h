@@ -164,6 +164,9 @@ int dv3_op_gemm(const float* A, int lda, int ta, const float* B, int ldb, int tb
 /* tensor-core GEMM with a pre-converted bf16 K-major B operand (Bh[n*ldbh + k]), as the engine uses for weights */
 int dv3_op_gemm_shadow(const float* A, int lda, int ta, const void* Bh, int ldbh, float* C, int ldc, int M, int N, int K,
                        const float* bias, float beta, void* stream);
+/* backward of y = silu(LayerNorm(x)) given the saved row statistics; dgamma / dbeta are accumulated (nullable) */
+int dv3_op_ln_silu_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                       float* dx, float* dgamma, float* dbeta, int64_t rows, int D, void* stream);
 /* fp32 -> bf16 copy of a 2-D block, and the TMA-fed tensor-core GEMM on two bf16 K-major operands
  * (C[M,N] = Ah[M,K] * Bh[N,K]^T): the contraction the engine runs when the producer of A wrote a bf16 copy */
 int dv3_op_to_bf16(const float* src, int lds, void* dst, int ldd, int64_t rows, int cols, void* stream);

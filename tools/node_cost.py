@@ -40,3 +40,9 @@ A2 = torch.randn(N, 1, device="cuda"); W2 = torch.randn(1, 256, device="cuda"); 
 print(f"gemm_f32 1024x256x1 (action part)     : {time_chain(lambda: ops.gemm(A2, W2, C_=C2, beta=1.0, mode=0)):.2f} us / node")
 A3 = torch.randn(16384, 256, device="cuda"); C3 = torch.empty(16384, 1, device="cuda")
 print(f"gemm_f32 16384x1x256 (continue head)  : {time_chain(lambda: ops.gemm(A3, W1, C_=C3, mode=0)):.2f} us / node")
+for rows in (1024, 16384):
+    xx = torch.randn(rows, 256, device="cuda"); dy = torch.randn(rows, 256, device="cuda")
+    dg, db = torch.zeros(256, device="cuda"), torch.zeros(256, device="cuda")
+    print(f"ln_silu_bwd {rows}x256 (dx only)        : {time_chain(ops.ln_silu_bwd(dy, xx, gam, bet)):.2f} us / node")
+    print(f"ln_silu_bwd {rows}x256 (+dgamma, dbeta) : {time_chain(ops.ln_silu_bwd(dy, xx, gam, bet, dg, db)):.2f} us / node")
+    print(f"ln_silu     {rows}x256                  : {time_chain(lambda: ops.ln_silu(xx, gam, bet)):.2f} us / node")
