@@ -280,7 +280,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&sm.acc_empty[as]);
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may go away once it has been read; kernel end covers the writes
     __syncwarp();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

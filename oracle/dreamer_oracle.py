@@ -55,6 +55,9 @@ class Oracle:
         self.ema_pct95 = float("nan")
         self.buckets = torch.linspace(-20.0, 20.0, NUM_BUCKETS, dtype=dtype)
         self.last_noise = {}
+        # float type of the symlog -> two-hot target arithmetic: float32 like the reference (the bucket-index
+        # contract); np.float64 only to compare against the float64 reference fixtures at 1e-9
+        self.th_float = np.float32
 
     # ------------------------------------------------------------------ groups
     def group_names(self, group):
@@ -283,8 +286,8 @@ class Oracle:
         dt = self.dtype
         obs = fwd["sampled_obs_symlog_BxT"].reshape(B * T, -1)
         L_dec = ((fwd["obs_distribution_BxT.loc"] - obs) ** 2).sum(-1).reshape(B, T)  # :36
-        r_sym = nx.symlog(np.asarray(rewards, dtype=np.float32).reshape(-1))  # :45-47
-        th = _t(nx.two_hot(r_sym), dt)  # :49
+        r_sym = nx.symlog(np.asarray(rewards, dtype=np.float32).reshape(-1), self.th_float)  # :45-47
+        th = _t(nx.two_hot(r_sym, ft=self.th_float), dt)  # :49
         logp = fwd["reward_logits_BxT"] - torch.logsumexp(fwd["reward_logits_BxT"], -1, keepdim=True)
         L_rew = -(logp * th).sum(-1).reshape(B, T)  # :57-59
         cont = 1.0 - _t(is_terminated, dt).reshape(-1)
@@ -312,7 +315,7 @@ class Oracle:
             "WORLD_MODEL_L_dynamics_B_T": L_dyn, "WORLD_MODEL_L_dynamics": L_dyn.mean(),
             "WORLD_MODEL_L_representation_B_T": L_rep, "WORLD_MODEL_L_representation": L_rep.mean(),
             "WORLD_MODEL_L_total_B_T": L_tot_BT, "WORLD_MODEL_L_total": L_tot_BT.mean(),
-            "reward_two_hot_k": nx.two_hot_indices(r_sym)[0],
+            "reward_two_hot_k": nx.two_hot_indices(r_sym, ft=self.th_float)[0],
         }
 
     # ------------------------------------------------------------------ optimizer
@@ -430,13 +433,13 @@ class Oracle:
         Hp1, N = dream["rewards_dreamed_t0_to_H_B"].shape
         H = Hp1 - 1
         vt = value_targets.detach()
-        vt_sym = nx.symlog(vt.to(torch.float32).numpy().reshape(-1))
-        th = _t(nx.two_hot(vt_sym), dt).reshape(H, N, NUM_BUCKETS)
+        vt_sym = nx.symlog(vt.numpy().astype(self.th_float).reshape(-1), self.th_float)
+        th = _t(nx.two_hot(vt_sym, ft=self.th_float), dt).reshape(H, N, NUM_BUCKETS)
         logits = dream["values_symlog_dreamed_logits_t0_to_HxB"].reshape(Hp1, N, NUM_BUCKETS)[:-1]
         logp = logits - torch.logsumexp(logits, -1, keepdim=True)
         L_val = -(logp * th).sum(-1)
         ema = dream["v_symlog_dreamed_ema_t0_to_H_B"].detach()[:-1]
-        th_ema = _t(nx.two_hot(ema.to(torch.float32).numpy().reshape(-1)), dt).reshape(H, N, NUM_BUCKETS)
+        th_ema = _t(nx.two_hot(ema.numpy().astype(self.th_float).reshape(-1), ft=self.th_float), dt).reshape(H, N, NUM_BUCKETS)
         L_reg = -(logp * th_ema).sum(-1)
         L_HB = (L_val + L_reg) * dream["dream_loss_weights_t0_to_H_B"].detach()[:-1]  # :73
         return {

@@ -14,16 +14,17 @@ import numpy as np
 F32 = np.float32
 
 
-def symlog(x):
+def symlog(x, ft=F32):
     """`sign(x) * log(|x| + 1)` in float32 (reference utils/symlog.py:9-12).
 
     `|x| + 1` is a float32 add as in TF; the logarithm is taken in float64 and rounded
     once to float32 (i.e. the correctly rounded float32 log), which is the contract the
     CUDA path implements as well so that two-hot bucket indices are bit-exact.
+    `ft=np.float64` runs the same formula in double (only for comparing against the float64 reference fixtures).
     """
-    x = np.asarray(x).astype(F32)
-    t = (np.abs(x) + F32(1.0)).astype(F32)
-    return (np.sign(x) * np.log(t.astype(np.float64)).astype(F32)).astype(F32)
+    x = np.asarray(x).astype(ft)
+    t = (np.abs(x) + ft(1.0)).astype(ft)
+    return (np.sign(x) * np.log(t.astype(np.float64)).astype(ft)).astype(ft)
 
 
 def inverse_symlog(y):
@@ -32,28 +33,28 @@ def inverse_symlog(y):
     return (np.sign(y) * (np.exp(np.abs(y)) - F32(1.0))).astype(F32)
 
 
-def two_hot_indices(value, num_buckets=255, lower_bound=-20.0, upper_bound=20.0):
+def two_hot_indices(value, num_buckets=255, lower_bound=-20.0, upper_bound=20.0, ft=F32):
     """(k, kp1, w_k, w_kp1) exactly as reference utils/two_hot.py:39-66 computes them,
     in float32 arithmetic (python-float constants are cast to float32 at use, as TF does)."""
-    v = np.clip(np.asarray(value).astype(F32), F32(lower_bound), F32(upper_bound))
-    delta = F32((upper_bound - lower_bound) / (num_buckets - 1))  # two_hot.py:44
-    idx = ((F32(-lower_bound) + v).astype(F32) / delta).astype(F32)  # two_hot.py:46
+    v = np.clip(np.asarray(value).astype(ft), ft(lower_bound), ft(upper_bound))
+    delta = ft((upper_bound - lower_bound) / (num_buckets - 1))  # two_hot.py:44
+    idx = ((ft(-lower_bound) + v).astype(ft) / delta).astype(ft)  # two_hot.py:46
     k = np.floor(idx)
     kp1 = np.ceil(idx)
-    kp1 = np.where(k == kp1, kp1 + F32(1.0), kp1)  # two_hot.py:53
-    kp1 = np.where(kp1 == F32(num_buckets), kp1 - F32(2.0), kp1)  # two_hot.py:58
-    values_k = (F32(lower_bound) + (k * delta).astype(F32)).astype(F32)
-    values_kp1 = (F32(lower_bound) + (kp1 * delta).astype(F32)).astype(F32)
-    w_k = ((v - values_kp1).astype(F32) / (values_k - values_kp1).astype(F32)).astype(F32)
-    w_kp1 = (F32(1.0) - w_k).astype(F32)
+    kp1 = np.where(k == kp1, kp1 + ft(1.0), kp1)  # two_hot.py:53
+    kp1 = np.where(kp1 == ft(num_buckets), kp1 - ft(2.0), kp1)  # two_hot.py:58
+    values_k = (ft(lower_bound) + (k * delta).astype(ft)).astype(ft)
+    values_kp1 = (ft(lower_bound) + (kp1 * delta).astype(ft)).astype(ft)
+    w_k = ((v - values_kp1).astype(ft) / (values_k - values_kp1).astype(ft)).astype(ft)
+    w_kp1 = (ft(1.0) - w_k).astype(ft)
     return k.astype(np.int32), kp1.astype(np.int32), w_k, w_kp1
 
 
-def two_hot(value, num_buckets=255, lower_bound=-20.0, upper_bound=20.0):
+def two_hot(value, num_buckets=255, lower_bound=-20.0, upper_bound=20.0, ft=F32):
     """Dense two-hot encoding [n, num_buckets] (reference utils/two_hot.py:9-78)."""
-    value = np.asarray(value).astype(F32).reshape(-1)
-    k, kp1, w_k, w_kp1 = two_hot_indices(value, num_buckets, lower_bound, upper_bound)
-    out = np.zeros((value.shape[0], num_buckets), dtype=F32)
+    value = np.asarray(value).astype(ft).reshape(-1)
+    k, kp1, w_k, w_kp1 = two_hot_indices(value, num_buckets, lower_bound, upper_bound, ft)
+    out = np.zeros((value.shape[0], num_buckets), dtype=ft)
     rows = np.arange(value.shape[0])
     # tf.scatter_nd adds duplicates; k != kp1 always holds after the fix-ups above.
     np.add.at(out, (rows, k), w_k)

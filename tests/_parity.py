@@ -23,20 +23,95 @@ def to_np(x):
     return np.asarray(x)
 
 
+class FixtureOracle:
+    """Replays a `tests/golden/ref_*.npz` fixture (outputs of the reference's own code, see
+    tests/golden/make_reference_golden.py) through the result-dict layout of `Oracle`, so that `ParityRun.step`
+    compares the CUDA engine against reference-generated vectors with the same code that compares it against the
+    live oracle."""
+
+    def __init__(self, cfg, z):
+        self.cfg, self.z, self.step_no = cfg, z, 0
+        grp = lambda pre: {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}  # noqa: E731
+        self._grp = grp
+        self.params0 = {k: v.astype(np.float32) for k, v in grp("param0/").items()}
+        self.sample = grp("sample/")
+        self.params = dict(self.params0)
+        self.last_noise = {}
+
+    group_names = Oracle.group_names
+
+    @property
+    def P(self):
+        return self.params
+
+    def numpy_params(self):
+        return {k: np.asarray(v, dtype=np.float32) for k, v in self.params.items()}
+
+    def train_world_model_one_step(self, sample, rng=None, margin=0.0):
+        import oracle.numerics as nx
+        cfg = self.cfg
+        self.step_no += 1
+        g = self.g = self._grp(f"s{self.step_no}/")
+        T = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))  # noqa: E731
+        self.last_noise = {"u_post": g["noise/u_post"], "u_dyn": g["noise/u_dyn"],
+                           ("u_act" if cfg.discrete else "eps_act"): g["noise/act"]}
+        zi = g["wm/z_indices_BxT"]
+        fwd = {
+            "h_states_BxT": T(g["wm/h_states_BxT"]), "z_indices_BxT": zi,
+            "z_states_BxT": T(np.eye(cfg.Zk)[zi]),
+            "z_posterior_probs_BxT": T(g["wm/z_posterior_probs_BxT"]), "z_prior_probs_BxT": T(g["wm/z_prior_probs_BxT"]),
+            "reward_logits_BxT": T(g["wm/reward_logits_BxT"]), "rewards_BxT": T(g["wm/rewards_BxT"]),
+            "continue_distribution_BxT.logits": T(g["wm/continue_logits"]),
+            "obs_distribution_BxT.loc": T(g["wm/obs_loc"]),
+        }
+        res = {k[3:]: T(v) for k, v in g.items() if k.startswith("wm/WORLD_MODEL_")}
+        res["WORLD_MODEL_forward_train_outs"] = fwd
+        # integer bucket index of the symlog'd replay rewards (two_hot.py:46-49; float32 arithmetic)
+        res["reward_two_hot_k"] = nx.two_hot_indices(nx.symlog(self.sample["rewards"].reshape(-1)))[0]
+        names = self.group_names("world_model")
+        res["grads"] = {n: T(g["grad/" + n]) for n in names}
+        res["grad_global_norm"] = float(np.sqrt(sum((g["grad/" + n].astype(np.float64) ** 2).sum() for n in names)))
+        for n in names:
+            self.params[n] = g["param/" + n]
+        return res
+
+    def train_actor_and_critic_one_step(self, h, z, is_terminated, H=15, rng=None, margin=0.0):
+        cfg, g = self.cfg, self.g
+        T = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))  # noqa: E731
+        dream = {k[6:]: T(v) for k, v in g.items() if k.startswith("dream/") and "indices" not in k and "ints" not in k}
+        dream["z_indices_t1_to_H_B"] = g["dream/z_indices_t1_to_H_B"]
+        if cfg.discrete:
+            dream["actions_ints_dreamed_t0_to_H_B"] = g["dream/actions_ints_dreamed_t0_to_H_B"]
+        ac = {k[3:]: T(v) for k, v in g.items() if k.startswith("ac/")}
+        ac["dream_data"] = dream
+        names = self.group_names("actor") + self.group_names("critic")
+        ac["grads"] = {n: T(g["grad/" + n]) for n in names}
+        for grp in ("actor", "critic"):
+            ac[grp + "_grad_global_norm"] = float(np.sqrt(sum(
+                (g["grad/" + n].astype(np.float64) ** 2).sum() for n in self.group_names(grp))))
+        for n in names + self.group_names("critic_ema"):
+            self.params[n] = g["param/" + n]
+        return ac
+
+
 class ParityRun:
     """One oracle-vs-engine comparison of a full train update (world model + actor/critic)."""
 
     def __init__(self, cfg: EngineConfig, seed=0, init_mode="random", oracle_dtype=torch.float64, compute_mode=0,
-                 margin=1e-3, steps=1, sync_grads=True, sample_fn=None):
+                 margin=1e-3, steps=1, sync_grads=True, sample_fn=None, fixture=None):
         self.cfg = cfg
         self.report = {}      # name -> rel err (float tensors)
         self.exact = {}       # name -> number of mismatching integers
-        self.params0 = init_params(cfg, seed=seed + 1, mode=init_mode)
-        self.sample = make_synthetic_sample(cfg, seed=seed + 2)
-        if sample_fn is not None:
-            sample_fn(self.sample)
+        if fixture is not None:  # replay of reference-generated golden vectors instead of a live oracle
+            self.oracle = FixtureOracle(cfg, fixture)
+            self.params0, self.sample = self.oracle.params0, self.oracle.sample
+        else:
+            self.params0 = init_params(cfg, seed=seed + 1, mode=init_mode)
+            self.sample = make_synthetic_sample(cfg, seed=seed + 2)
+            if sample_fn is not None:
+                sample_fn(self.sample)
+            self.oracle = Oracle(cfg, self.params0, dtype=oracle_dtype)
         self.rng = np.random.default_rng(seed + 3)
-        self.oracle = Oracle(cfg, self.params0, dtype=oracle_dtype)
         self.engine = Engine(cfg, compute_mode=compute_mode)
         self.engine.load_params(self.params0)
         self.margin = margin
@@ -74,7 +149,8 @@ class ParityRun:
         e.set_noise(u_post=u_post)
         e.observe_forward()
         t = e.tensor
-        self.cmp("wm.enc_out", t("wm.enc_out"), fwd["encoder_out_TB"].transpose(0, 1).reshape(N, -1))
+        if "encoder_out_TB" in fwd:  # not part of forward_train's result dict (absent from reference fixtures)
+            self.cmp("wm.enc_out", t("wm.enc_out"), fwd["encoder_out_TB"].transpose(0, 1).reshape(N, -1))
         self.cmp("wm.h_states", t("wm.hz")[:, :G], fwd["h_states_BxT"])
         self.cmp_exact("wm.z_indices", t("wm.z_indices"), fwd["z_indices_BxT"])
         self.cmp("wm.z_states", t("wm.hz")[:, G:], fwd["z_states_BxT"].reshape(N, -1))
