@@ -6,12 +6,19 @@ Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl
 legs may import this module; `dreamer_v3_b200` (the product) never does and fails loudly
 when its CUDA library is missing.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path
-(only `utils/two_hot.py:23-37`, which pins `oracle/numerics.py:two_hot`), and TensorFlow /
-Keras / tfp (versions not pinned by the reference; ~TF 2.10-2.12, tfp 0.18-0.20 inferred)
-cannot be installed in this image, so the reference itself cannot be run to generate
-vectors. Every function below therefore follows the cited reference lines plus the
-documented defaults of the Keras/tfp layers they call.
+PARITY PIN: the reference ships no tests or fixtures for this path, and TensorFlow / Keras / tfp
+(versions not pinned by the reference; ~TF 2.10-2.12, tfp 0.18-0.20 inferred) cannot be installed in
+this image.  The reference's OWN Python files are therefore executed, unmodified, over a TF-API shim
+(tests/golden/tfshim/, PyTorch-CPU backed) by tests/golden/make_reference_golden.py, which calls
+`train_world_model_one_step` / `train_actor_and_critic_one_step` as run_experiment.py does and commits
+the outputs (tests/golden/ref_*.npz).  tests/test_reference_golden.py holds this oracle to those
+vectors: 1e-9 relative in float64, every sampled index exact, over two consecutive updates
+(forward tensors, losses, dream, lambda-returns, every gradient, Adam / EMA results).
+That pins the reference's COMPOSITION (masking, wrap-around action index, concatenation orders,
+stop-gradients, loss weighting, clipping, optimizer / EMA order).  Still UNPINNED: TensorFlow's own
+arithmetic of the primitives (Dense, LayerNormalization eps, GRU gate order / reset_after, conv
+padding, tfp formulas, Keras Adam), which shim and oracle both restate from the documented defaults
+(SURVEY.md appendix A); `utils/two_hot.py:23-37` additionally pins `oracle/numerics.py:two_hot`.
 
 Deliberate, documented deviations (they make results reproducible, not different):
   * sampling noise is an explicit input (uniforms for categoricals, normals for Box actions)

@@ -5,9 +5,10 @@ Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl
 legs may import this module. The product path (`dreamer_v3_b200`) never does.
 
 Parity pin: `two_hot` is pinned by the reference's own docstring known-answer vectors
-(`utils/two_hot.py:23-37`, checked in tests/test_oracle_numerics.py). Everything else here is
-**parity unpinned** by reference tests (the reference has none and TensorFlow is not
-installable in this image); it follows the cited source lines.
+(`utils/two_hot.py:23-37`, checked in tests/test_oracle_numerics.py). symlog / two_hot /
+lambda-returns / percentile are additionally held to the outputs of the reference's own code run
+over the TF-API shim (tests/golden/ref_*.npz, tests/test_reference_golden.py); TensorFlow's own
+arithmetic of the primitives stays unpinned (TensorFlow is not installable in this image).
 """
 import numpy as np
 
