@@ -142,6 +142,13 @@ int dv3_dream_forward(dv3_engine* h, float gamma, int start_from_observe, void* 
   int rc = h->e.dream_forward(gamma, start_from_observe, S(stream));
   return rc ? rc : check_async(h->e);
 }
+int dv3_dream_forward_actions(dv3_engine* h, float gamma, int start_from_observe, int action_mode, void* stream) {
+  if (action_mode < 0 || action_mode > 2) return h->e.fail("dream_forward_actions: action_mode must be 0, 1 or 2");
+  h->e.dream_action_mode = action_mode;
+  int rc = h->e.dream_forward(gamma, start_from_observe, S(stream));
+  h->e.dream_action_mode = 0;
+  return rc ? rc : check_async(h->e);
+}
 int dv3_ac_loss_backward(dv3_engine* h, const dv3_hparams* hp, int phase, void* stream) {
   int rc = h->e.ac_loss_backward(hp, phase, S(stream));
   return rc ? rc : check_async(h->e);

@@ -31,6 +31,16 @@ void Engine::actor_fwd(long long row_off) {
   }
 }
 
+// Action of dream step i: the actor's sample, or the caller's (dream_trajectory_with_burn_in, dreamer_model.py:306-413:
+// a_0 = the last burn-in action; with use_sampled_actions / use_random_actions every action is given).
+void Engine::dream_action(int i) {
+  const long long off = (long long)i * N;
+  if (dream_action_mode == 2 || (dream_action_mode == 1 && i == 0))
+    cudaMemcpyAsync(dr_act + (size_t)off * A, in_dream_actions + (size_t)off * A, (size_t)N * A * 4, cudaMemcpyDeviceToDevice, cur);
+  else
+    actor_fwd(off);
+}
+
 int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
   cur = s;
   last_gamma = gamma;
@@ -56,7 +66,7 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
     float* hz_c = dr_hz + curr * W;
     // Everything that only needs [h, z]_{i-1} runs concurrently: the actor (its action a_{i-1} enters the sequence model
     // through the small a-part of the pre-GRU layer only), the z-part of that layer, and h_{i-1} . U.
-    run_branches({[&] { actor_fwd((long long)prev); },
+    run_branches({[&] { dream_action(i - 1); },
                   [&] { mm(hz_p + G, W, false, Wx.w, D, false, dr_x_pre + st * D, D, N, D, Z, nullptr, 0.f, h16(prev, G)); },
                   [&] { mm(hz_p, W, false, gru_U, 3 * G, false, dr_gh + st * 3 * G, 3 * G, N, 3 * G, G, gru_b + 3 * G, 0.f, h16(prev, 0)); }});
     phase_mark("dream.actor|z|gh");
@@ -96,7 +106,7 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
         mm(ema_act.act.back(), D, false, ema_head.w, DV3_NB, false, ema_logits, DV3_NB, R, DV3_NB, D, ema_head.bias, 0.f, ema_act.act16.back());
         bucket_expectation(cur, ema_logits, DV3_NB, ema_E, R);
       },
-      [&] { actor_fwd((long long)H * N); }});
+      [&] { dream_action(H); }});
   phase_mark("dream.heads");
   // real-space rewards / continues / values, loss weights (dreamer_model.py:219-280) and lambda-returns
   AcArgs a{};

@@ -278,6 +278,7 @@ void Engine::layout() {
   else in_act_noise = af("in.act_noise", {H + 1, Nl, A}, 4);
   in_dream_h0 = af("in.dream_h0", {Nl, G}, 4);
   in_dream_z0 = af("in.dream_z0", {Nl, Z}, 4);
+  in_dream_actions = af("in.dream_actions", {H + 1, Nl, A}, 4);  // given actions of dream_trajectory_with_burn_in
   // ---- observe ----
   if (cfg.symlog_obs) obs_sym = af("wm.obs_symlog", {Nl, OF});
   else obs_sym = in_obs;

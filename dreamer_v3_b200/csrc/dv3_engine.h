@@ -80,7 +80,8 @@ struct Engine {
 
   // ---- inputs ----
   float *in_obs, *in_actions, *in_is_first, *in_rewards, *in_is_term, *in_u_post, *in_u_dyn, *in_act_noise;
-  float *in_dream_h0, *in_dream_z0;
+  float *in_dream_h0, *in_dream_z0, *in_dream_actions;
+  int dream_action_mode = 0;  // 0: actor everywhere, 1: a_0 given (in.dream_actions[0]), 2: every action given
   // ---- observe activations ----
   float *obs_sym, *enc_out, *a_in, *wf, *actW, *h0, *z0, *q0_pre, *q0_act, *z0_logits;
   int32_t* z0_idx;
@@ -140,6 +141,7 @@ struct Engine {
   MlpAct inf_enc_act, inf_actor_act, inf_std_act;
   unsigned long long inf_calls = 0;
   int forward_inference(int rows, uint64_t noise_seed, cudaStream_t s);
+  void dream_action(int i);
 
   // ---- fork / join of independent op chains onto auxiliary streams (capturable: events only) ----
   static constexpr int kAux = 3;

@@ -173,6 +173,12 @@ class Engine:
         g = self.hp.gamma if gamma is None else float(gamma)
         self._check(self.lib.dv3_dream_forward(self.h, g, int(start_from_observe), self._stream()), "dv3_dream_forward")
 
+    def dream_forward_actions(self, action_mode, gamma=None, start_from_observe=False):
+        """Prior rollout with given actions (include/dv3.h: dv3_dream_forward_actions)."""
+        g = float(self.hp.gamma if gamma is None else gamma)
+        self._check(self.lib.dv3_dream_forward_actions(self.h, g, int(start_from_observe), int(action_mode), self._stream()),
+                    "dv3_dream_forward_actions")
+
     def ac_loss_backward(self, phase=3):
         self._check(self.lib.dv3_ac_loss_backward(self.h, C.byref(self.hp), int(phase), self._stream()),
                     "dv3_ac_loss_backward")

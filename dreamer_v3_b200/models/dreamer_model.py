@@ -112,5 +112,54 @@ class DreamerModel:
             ret["actions_ints_dreamed_t0_to_H_B"] = e.tensor("dream.action_indices")
         return ret
 
-    def dream_trajectory_with_burn_in(self, **kwargs):
-        raise NotImplementedError("evaluation-only path (dreamer_model.py:306-413), 'next' row 8f-3")
+    def dream_trajectory_with_burn_in(self, *, start_states, timesteps_burn_in, timesteps_H, observations, actions,
+                                      use_sampled_actions_in_dream=False, use_random_actions_in_dream=False,
+                                      random_actions=None):
+        """dreamer_model.py:306-413 (evaluation path, run_experiment.py:629-644): `timesteps_burn_in` posterior steps on
+        the given observations / actions (one `forward_inference` kernel sequence each), then `timesteps_H` prior steps
+        with the actor's, the given, or random actions (`dv3_dream_forward_actions`). Rows = observations.shape[0] <= B.
+        `random_actions` [H, rows] ints makes use_random_actions_in_dream reproducible."""
+        assert not (use_sampled_actions_in_dream and use_random_actions_in_dream)
+        e = self.engine
+        cfg = e.cfg
+        assert timesteps_H == cfg.H, f"engine was built for horizon {cfg.H}"
+        dev = e.device
+        observations = torch.as_tensor(observations)
+        actions = torch.as_tensor(actions).to(dev, torch.float32)
+        rows = int(observations.shape[0])
+        states = dict(start_states)
+        for i in range(timesteps_burn_in):
+            first = torch.full((rows,), 1.0 if i == 0 else 0.0)
+            states = self.world_model.forward_inference(states, observations[:, i], first)
+            states["a"] = actions[:, i]
+        given = e.tensor("in.dream_actions")
+        given.zero_()
+        given[0, :rows] = states["a"]
+        if use_sampled_actions_in_dream:
+            given[1:, :rows] = actions[:, timesteps_burn_in:timesteps_burn_in + timesteps_H].transpose(0, 1)
+        elif use_random_actions_in_dream:
+            if random_actions is None:
+                random_actions = torch.randint(0, cfg.A, (timesteps_H, rows))
+            given[1:, :rows] = torch.nn.functional.one_hot(torch.as_tensor(random_actions).long(), cfg.A).to(dev, torch.float32)
+        h0, z0 = e.tensor("in.dream_h0"), e.tensor("in.dream_z0")
+        h0.zero_(); z0.zero_()
+        h0[:rows] = torch.as_tensor(states["h"]).to(dev).reshape(rows, cfg.G)
+        z0[:rows] = torch.as_tensor(states["z"]).to(dev).reshape(rows, cfg.Z)
+        self.world_model._draw_noise(2)
+        e.dream_forward_actions(2 if (use_sampled_actions_in_dream or use_random_actions_in_dream) else 1,
+                                start_from_observe=False)
+        dhz = e.tensor("dream.hz")[:, :rows]
+        a_t0_to_H = e.tensor("dream.actions")[:, :rows]
+        ret = {
+            "h_states_t0_to_H_B": dhz[..., :cfg.G],
+            "z_states_prior_t0_to_H_B": dhz[..., cfg.G:].unflatten(2, (cfg.Zc, cfg.Zk)),
+            # inverse_symlog(reward_predictor) / continue_predictor mode on every dreamed state incl. t0 (:374-392)
+            "rewards_dreamed_t0_to_H_B": e.tensor("dream.rewards")[:, :rows],
+            "continues_dreamed_t0_to_H_B": (e.tensor("dream.continue_logits")[:, :rows] > 0).to(torch.float32),
+        }
+        key = ("actions_sampled_t0_to_H_B" if use_sampled_actions_in_dream
+               else "actions_random_t0_to_H_B" if use_random_actions_in_dream else "actions_dreamed_t0_to_H_B")
+        ret[key] = a_t0_to_H
+        if cfg.discrete:
+            ret[key.replace("actions_", "actions_ints_", 1)] = torch.argmax(a_t0_to_H, dim=-1)
+        return ret

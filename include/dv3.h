@@ -128,6 +128,12 @@ int dv3_forward_inference(dv3_engine* e, int rows, uint64_t noise_seed, void* st
  * wm.hz of the last dv3_observe_forward (as run_experiment.py:458-460 does); otherwise in.dream_h0
  * [N,G] / in.dream_z0 [N,Zc*Zk]. Reads in.is_terminated, in.u_dyn [H,N,Zc], in.act_noise. */
 int dv3_dream_forward(dv3_engine* e, float gamma, int start_from_observe, void* stream);
+/* The prior rollout of DreamerModel.dream_trajectory_with_burn_in (dreamer_model.py:337-372; evaluation path,
+ * run_experiment.py:629-644) on the same kernels: action_mode 1 = a_0 is in.dream_actions[0] (the last burn-in action)
+ * and the actor samples a_1..a_H; 2 = every action is read from in.dream_actions [H+1,N,A] (use_sampled_actions_in_dream /
+ * use_random_actions_in_dream); 0 = dv3_dream_forward. Rows are independent: a caller with fewer than N start states
+ * fills the first rows and ignores the rest. The burn-in steps themselves are dv3_forward_inference calls. */
+int dv3_dream_forward_actions(dv3_engine* e, float gamma, int start_from_observe, int action_mode, void* stream);
 /* compute_value_targets + critic_loss + actor_loss (critic_loss.py:15-139, actor_loss.py:12-138) and
  * their gradients into the actor / critic gradient buffers (REINFORCE for Discrete, BPTT through the
  * dream for Box). phase 1 = value targets only (so the caller can all-gather them across ranks for

@@ -424,6 +424,46 @@ class Oracle:
             out["actions_ints_dreamed_t0_to_H_B"] = torch.argmax(a_HB, -1)
         return out
 
+    def dream_trajectory_with_burn_in(self, start_states, timesteps_burn_in, timesteps_H, observations, actions,
+                                      u_burn, u_dyn, act_noise=None, use_sampled_actions_in_dream=False):
+        """models/dreamer_model.py:306-413 (evaluation path, run_experiment.py:629-644). start_states {"h","z","a"}
+        [B,...]; observations [B, >=burn_in, ...]; actions [B, burn_in (+H), A]; u_burn [burn_in, B, Zc] uniforms of the
+        posterior draws, u_dyn [H, B, Zc] of the prior draws, act_noise [H, B(, A)] for the actor samples a_1..a_H
+        (unused with use_sampled_actions_in_dream)."""
+        cfg, dt = self.cfg, self.dtype
+        B = np.asarray(observations).shape[0]
+        actions = _t(actions, dt)
+        h, z, a = _t(start_states["h"], dt), _t(start_states["z"], dt), _t(start_states["a"], dt)
+        dummy = np.full((B,) if cfg.discrete else (B, cfg.A), 0.5, np.float32)  # the actor's sample is not used in burn-in
+        for i in range(timesteps_burn_in):
+            first = np.full((B,), 1.0 if i == 0 else 0.0, np.float32)  # :326-330
+            st = self.forward_inference(h, z, a, np.asarray(observations)[:, i], first, u_z=u_burn[i], act_noise=dummy)
+            h, z, a = st["h"], st["z"], actions[:, i]  # :331
+        hs, zs, acts, zidx = [h], [z], [a], []
+        for j in range(timesteps_H):
+            h = self.sequence_model(z, a, h)  # :338-342
+            z, _, idx = self.representation("dyn.repr", self.mlp("dyn", h, 1), u_dyn[j], "burn_u_dyn")  # :344
+            if use_sampled_actions_in_dream:
+                a = actions[:, timesteps_burn_in + j]  # :347-348
+            else:
+                hz = torch.cat([h, z.reshape(B, -1)], -1)
+                a, _ = self.actor(hz.detach(), act_noise[j], "burn_act")  # :354
+            hs.append(h); zs.append(z); acts.append(a); zidx.append(idx)
+        h_HB, z_HB, a_HB = torch.stack(hs, 0), torch.stack(zs, 0), torch.stack(acts, 0)
+        hz = torch.cat([h_HB.reshape(-1, cfg.G), z_HB.reshape(-1, cfg.Z)], -1)
+        r_sym, _ = self.reward_predictor(hz)
+        c, _ = self.continue_predictor(hz)
+        key = "actions_sampled_t0_to_H_B" if use_sampled_actions_in_dream else "actions_dreamed_t0_to_H_B"
+        out = {
+            "h_states_t0_to_H_B": h_HB.detach(), "z_states_prior_t0_to_H_B": z_HB.detach(),
+            "rewards_dreamed_t0_to_H_B": inverse_symlog(r_sym).reshape(-1, B).detach(),  # :383
+            "continues_dreamed_t0_to_H_B": c.reshape(-1, B).detach(),
+            key: a_HB.detach(), "z_indices_t1_to_H_B": np.stack(zidx, 0),
+        }
+        if cfg.discrete:
+            out[key.replace("actions_", "actions_ints_", 1)] = torch.argmax(a_HB, -1)
+        return out
+
     @staticmethod
     def compute_value_targets(r, c, v, gamma, lambda_):
         """losses/critic_loss.py:92-139 (differentiable restatement)."""

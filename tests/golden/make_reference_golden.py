@@ -249,6 +249,28 @@ def run_case(name, kw, seed, dtype):
                 for var, g in zip(model.trainable_variables, gl):
                     out[pre + "grad/" + by_id[id(var)]] = npf(g)
             out.update({pre + "param/" + n: npf(v) for n, v in vm.items()})
+        # ---- dream_trajectory_with_burn_in (dreamer_model.py:306-413), called as run_experiment.py:629-644 does
+        # (given actions) and in its default mode (actor's actions), on the twice-updated weights ----
+        burn = cfg.T - H  # burn_in_T + horizon_H <= batch_length_T (run_experiment.py:141-144)
+        start = {k: tf.repeat(v, cfg.B, axis=0) for k, v in dm.get_initial_state().items()}
+        for mode, sampled in (("given", True), ("actor", False)):
+            tfp.DRAW_LOG.clear()
+            bd = dm.dream_trajectory_with_burn_in(
+                start_states=dict(start), timesteps_burn_in=burn, timesteps_H=H,
+                observations=sample["obs"][:, :burn], actions=sample["actions"][:, :burn + H] if sampled
+                else sample["actions"][:, :burn], use_sampled_actions_in_dream=sampled, use_random_actions_in_dream=False)
+            log = list(tfp.DRAW_LOG)
+            pre = f"burn_{mode}/"
+            # per burn-in step: initial-state draw (discarded) + posterior draw; per dream step: prior draw (+ actor draw)
+            per = 1 if sampled else 2
+            assert len(log) == 2 * burn + per * H, (len(log), burn, H)
+            out[pre + "noise/u_burn"] = np.stack([log[2 * i + 1][1] for i in range(burn)], 0)            # [burn,B,Zc]
+            out[pre + "noise/u_dyn"] = np.stack([log[2 * burn + per * j][1] for j in range(H)], 0)        # [H,B,Zc]
+            if not sampled:
+                out[pre + "noise/act"] = np.stack([log[2 * burn + 2 * j + 1][1] for j in range(H)], 0)    # [H,B(,A)]
+            for k, v in bd.items():
+                out[pre + k] = v.numpy().astype(np.int32) if "ints" in k else npf(v)
+            out[pre + "z_indices_t1_to_H_B"] = bd["z_states_prior_t0_to_H_B"].numpy()[1:].argmax(-1).astype(np.int32)
     finally:
         tf.clip_by_global_norm = real_clip
     return out

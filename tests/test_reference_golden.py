@@ -149,3 +149,92 @@ def test_cuda_engine_matches_reference_code(case):
         assert len(run.report) > 100
     finally:
         run.close()
+
+
+def _burn_inputs(z, cfg, mode):
+    g = group(z, f"burn_{mode}/")
+    sample = group(z, "sample/")
+    burn = cfg.T - cfg.H
+    acts = sample["actions"][:, :burn + cfg.H] if mode == "given" else sample["actions"][:, :burn]
+    return g, sample, burn, acts
+
+
+BURN_FLOAT_KEYS = ("h_states_t0_to_H_B", "rewards_dreamed_t0_to_H_B")
+
+
+@pytest.mark.parametrize("mode", ("given", "actor"))
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_burn_in_dream_matches_reference_code(case, mode):
+    """dream_trajectory_with_burn_in (dreamer_model.py:306-413) on the twice-updated weights of the fixture."""
+    z, cfg = load(case, "f64")
+    g, sample, burn, acts = _burn_inputs(z, cfg, mode)
+    o = Oracle(cfg, group(z, "s2/param/"), dtype=torch.float64)
+    init = o.get_initial_state()
+    start = {"h": init["h"].detach().repeat(cfg.B, 1), "z": init["z"].repeat(cfg.B, 1, 1),
+             "a": torch.zeros(cfg.B, cfg.A, dtype=torch.float64)}
+    out = o.dream_trajectory_with_burn_in(start, burn, cfg.H, sample["obs"][:, :burn], acts, g["noise/u_burn"],
+                                          g["noise/u_dyn"], g.get("noise/act"), use_sampled_actions_in_dream=(mode == "given"))
+    akey = "actions_sampled_t0_to_H_B" if mode == "given" else "actions_dreamed_t0_to_H_B"
+    assert (out["z_indices_t1_to_H_B"] != g["z_indices_t1_to_H_B"]).sum() == 0
+    assert (tnp(out["continues_dreamed_t0_to_H_B"]) != g["continues_dreamed_t0_to_H_B"]).sum() == 0
+    if cfg.discrete:
+        ik = akey.replace("actions_", "actions_ints_", 1)
+        assert (tnp(out[ik]) != g[ik]).sum() == 0
+    for k in BURN_FLOAT_KEYS + (akey,):
+        assert rel(tnp(out[k]), g[k]) <= 1e-9, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ("given", "actor"))
+@pytest.mark.parametrize("case", CASES)
+def test_cuda_burn_in_dream_matches_reference_code(case, mode):
+    """DreamerModel.dream_trajectory_with_burn_in of the drop-in API (forward_inference steps + the given-action
+    prior rollout kernels) against the float32 vectors of the reference's own code, fed its noise."""
+    from dreamer_v3_b200.models.components import CNNAtari, ConvTransposeAtari, MLP, VectorDecoder
+    from dreamer_v3_b200.models.dreamer_model import DreamerModel
+    from dreamer_v3_b200.models.world_model import WorldModel
+    from dreamer_v3_b200.spec import Box, Discrete
+    z, cfg = load(case, "f32")
+    g, sample, burn, acts = _burn_inputs(z, cfg, mode)
+    space = Discrete(cfg.A) if cfg.discrete else Box(-1.0, 1.0, (cfg.A,))
+    if cfg.image_obs:
+        enc, dec = CNNAtari(model_dimension="nano"), ConvTransposeAtari(model_dimension="nano", gray_scaled=False)
+    else:
+        enc = MLP(model_dimension="nano")
+        dec = VectorDecoder(model_dimension="nano", observation_space=Box(-10, 10, (cfg.obs_dim,)))
+    wm = WorldModel(model_dimension="nano", action_space=space, batch_length_T=cfg.T, encoder=enc, decoder=dec,
+                    symlog_obs=cfg.symlog_obs)
+    dm = DreamerModel(model_dimension="nano", action_space=space, batch_size_B=cfg.B, batch_length_T=cfg.T,
+                      horizon_H=cfg.H, world_model=wm)
+    e = dm.engine
+    try:
+        e.load_params(group(z, "s2/param/"))
+        start = {k: v.repeat_interleave(cfg.B, 0) for k, v in dm.get_initial_state().items()}
+        # noise: posterior draws of the burn-in steps, then prior (and actor) draws of the rollout
+        u_dyn = np.full((cfg.H, cfg.N, cfg.Zc), 0.5, np.float32)
+        u_dyn[:, :cfg.B] = g["noise/u_dyn"]
+        act = np.full((cfg.H + 1, cfg.N) + (() if cfg.discrete else (cfg.A,)), 0.5, np.float32)
+        if mode == "actor":
+            act[1:, :cfg.B] = g["noise/act"]
+        wm.set_noise(u_dyn=u_dyn, act_noise=act)
+        steps = iter(range(burn))
+        orig = wm.forward_inference
+
+        def with_noise(states, obs, first):
+            wm.set_inference_noise(g["noise/u_burn"][next(steps)], np.full((cfg.B,) + (() if cfg.discrete else (cfg.A,)), 0.5, np.float32))
+            return orig(states, obs, first)
+        wm.forward_inference = with_noise
+        out = dm.dream_trajectory_with_burn_in(
+            start_states=start, timesteps_burn_in=burn, timesteps_H=cfg.H, observations=sample["obs"][:, :burn],
+            actions=acts, use_sampled_actions_in_dream=(mode == "given"))
+        akey = "actions_sampled_t0_to_H_B" if mode == "given" else "actions_dreamed_t0_to_H_B"
+        zi = out["z_states_prior_t0_to_H_B"][1:].argmax(-1).cpu().numpy()
+        assert (zi != g["z_indices_t1_to_H_B"]).sum() == 0
+        assert (out["continues_dreamed_t0_to_H_B"].cpu().numpy() != g["continues_dreamed_t0_to_H_B"]).sum() == 0
+        if cfg.discrete:
+            ik = akey.replace("actions_", "actions_ints_", 1)
+            assert (out[ik].cpu().numpy() != g[ik]).sum() == 0
+        for k in BURN_FLOAT_KEYS + (akey,):
+            assert rel(out[k].cpu().numpy(), g[k]) <= 1e-4, k
+    finally:
+        e.close()
