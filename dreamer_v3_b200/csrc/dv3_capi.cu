@@ -180,6 +180,17 @@ int dv3_train_update(dv3_engine* h, const dv3_hparams* hp, uint64_t noise_seed, 
 }
 int64_t dv3_kernel_launch_count(const dv3_engine*) { return dv3::g_launches; }
 
+// ---- replay sampler ----
+int dv3_replay_gather(const void* obs_store, int obs_is_u8, int normalize_u8, int64_t obs_elems, const float* act_store, int A,
+                      const float* rew_store, const int32_t* plan, int64_t n, float* obs_out, float* act_out, float* rew_out,
+                      float* is_first, float* is_last, float* is_terminated, void* stream) {
+  if (!obs_store || !act_store || !rew_store || !plan || !obs_out || !act_out || !rew_out || !is_first || !is_last || !is_terminated) return -1;
+  if (obs_elems < 1 || A < 1 || n < 0) return -1;
+  dv3::replay_gather(S(stream), obs_store, obs_is_u8, normalize_u8, obs_elems, act_store, A, rew_store, plan, n, obs_out, act_out, rew_out,
+                     is_first, is_last, is_terminated);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 // ---- isolated ops ---------------------------------------------------------------------------------------------
 static int op_done() { return cudaGetLastError() == cudaSuccess ? 0 : -1; }
 int dv3_op_symlog(const float* x, float* y, int64_t n, void* stream) { dv3::symlog_fwd(S(stream), x, y, n); return op_done(); }

@@ -228,4 +228,9 @@ void ema_update(cudaStream_t s, float* ema, const float* w, long long n, float d
 void philox_fill(cudaStream_t s, float* out, long long n, uint64_t seed, uint64_t salt, const unsigned long long* dev_step, int normal);
 void bump_counter(cudaStream_t s, unsigned long long* ctr);
 
+// ---- replay sampler (dv3_replay.cu) -------------------------------------------------------------------------
+int replay_gather(cudaStream_t s, const void* obs_store, int obs_is_u8, int normalize_u8, long long obs_elems, const float* act_store, int A,
+                  const float* rew_store, const int32_t* plan, long long n, float* obs_out, float* act_out, float* rew_out,
+                  float* is_first, float* is_last, float* is_term);
+
 }  // namespace dv3

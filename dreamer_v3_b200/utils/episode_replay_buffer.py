@@ -1,0 +1,217 @@
+"""EpisodeReplayBuffer with the reference's surface (utils/episode_replay_buffer.py:9-238: `add`, `sample`,
+`get_num_episodes`, `get_num_timesteps`, `get_sampled_timesteps`), re-designed for the GPU: the timesteps live in HBM in
+fixed-size *pages* owned by episodes, `sample()` builds a 16-byte-per-timestep gather plan on the host with the
+reference's index arithmetic and ONE CUDA kernel (`dv3_replay_gather`, csrc/dv3_replay.cu) packs the `[B, T, ...]`
+sample dict on the device - image frames stay uint8 in the store (1 B / pixel) and are normalised in the gather.
+
+Semantics kept from the reference (line numbers of utils/episode_replay_buffer.py):
+  * every stored timestep (episode, ts), ts < len(episode), is equally likely to start a row (:118-126); the order of that
+    index space is the arrival order of the added chunks (:44-56), so the same `np.random.randint` stream selects the
+    same timesteps;
+  * a row that runs past its episode's end continues with timestep 0 of the episode of the next drawn index (:139-141);
+  * the first reward of a row is the one that led to its first observation, 0.0 at an episode start (:134-138, :141);
+  * the action at an episode's final observation repeats the last action (:157-158);
+  * is_first at every segment start, is_last at every segment end, is_terminated only where a terminated episode's
+    final observation made it into the row (:128, :166-170);
+  * capacity counts timesteps; the oldest episodes are ejected first (:60-96).
+There is no CPU fallback: the store and the returned tensors are CUDA tensors.
+"""
+import ctypes as C
+from collections import deque
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .episode import Episode
+
+PAGE = 64  # timesteps per page
+
+
+class _Stored:
+    __slots__ = ("id_", "pages", "length", "is_terminated")
+
+    def __init__(self, id_):
+        self.id_, self.pages, self.length, self.is_terminated = id_, [], 0, False
+
+
+class EpisodeReplayBuffer:
+    def __init__(self, capacity: int = 10000, device=None, normalize_uint8=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("EpisodeReplayBuffer keeps its store in HBM; no CUDA device found (there is no CPU fallback)")
+        self.lib = _lib.load()
+        self.capacity = int(capacity)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.normalize_uint8 = bool(normalize_uint8)
+        self.episodes = deque()                # _Stored, oldest first
+        self.episode_id_to_index = {}          # id_ -> absolute episode index (ejected ones counted)
+        self._num_episodes_ejected = 0
+        self._chunks = []                      # arrival-ordered (abs episode index, ts0, count): the reference's `_indices`
+        self._chunk_cum = np.zeros(1, np.int64)
+        self.size = 0
+        self.sampled_timesteps = 0
+        self._obs_store = self._act_store = self._rew_store = None
+        self._free_pages = []
+        self._num_pages = 0
+
+    # ------------------------------------------------------------------ device store
+    def _alloc(self, obs0, act0):
+        obs0, act0 = np.asarray(obs0), np.asarray(act0, dtype=np.float32)
+        self._obs_shape = tuple(obs0.shape)
+        self._obs_u8 = obs0.dtype == np.uint8
+        self._act_shape = tuple(act0.shape)
+        self._obs_elems = int(np.prod(self._obs_shape)) if self._obs_shape else 1
+        self._A = int(np.prod(self._act_shape)) if self._act_shape else 1
+        # every episode wastes < 1 page (+1 slot for its final observation); short episodes are the worst case
+        # grown on demand (x1.5) up to what the capacity can need
+        self._num_pages = min(2 * ((self.capacity + PAGE - 1) // PAGE) + 64, 1024)
+        slots = self._num_pages * PAGE
+        self._obs_store = torch.empty((slots, self._obs_elems), dtype=torch.uint8 if self._obs_u8 else torch.float32, device=self.device)
+        self._act_store = torch.zeros((slots, self._A), dtype=torch.float32, device=self.device)
+        self._rew_store = torch.zeros((slots,), dtype=torch.float32, device=self.device)
+        self._free_pages = list(range(self._num_pages - 1, -1, -1))
+
+    def _slots(self, st, ts0, count):
+        """Store slots of timesteps ts0 .. ts0+count-1 of a stored episode (allocating pages as needed)."""
+        ts = np.arange(ts0, ts0 + count)
+        need = (ts0 + count + PAGE - 1) // PAGE
+        while len(st.pages) < need:
+            if not self._free_pages:
+                self._grow()
+            st.pages.append(self._free_pages.pop())
+        return torch.from_numpy(np.asarray(st.pages, np.int64)[ts // PAGE] * PAGE + ts % PAGE).to(self.device)
+
+    def _grow(self):
+        more = max(64, self._num_pages // 2)
+        for name in ("_obs_store", "_act_store", "_rew_store"):
+            old = getattr(self, name)
+            new = torch.empty((old.shape[0] + more * PAGE,) + tuple(old.shape[1:]), dtype=old.dtype, device=self.device)
+            new[:old.shape[0]] = old
+            setattr(self, name, new)
+        self._free_pages = list(range(self._num_pages + more - 1, self._num_pages - 1, -1)) + self._free_pages
+        self._num_pages += more
+
+    def _upload(self, st, obs, actions, rewards, obs_ts0, ts0):
+        """obs -> observation indices obs_ts0.., actions / rewards -> timestep indices ts0.. of the stored episode."""
+        if len(obs):
+            o = torch.from_numpy(np.ascontiguousarray(np.asarray(obs)).reshape(len(obs), self._obs_elems))
+            self._obs_store[self._slots(st, obs_ts0, len(obs))] = o.to(self.device, self._obs_store.dtype, non_blocking=True)
+        if len(actions):
+            idx = self._slots(st, ts0, len(actions))
+            a = torch.from_numpy(np.asarray(actions, dtype=np.float32).reshape(len(actions), self._A))
+            self._act_store[idx] = a.to(self.device, non_blocking=True)
+            self._rew_store[idx] = torch.from_numpy(np.asarray(rewards, dtype=np.float32)).to(self.device, non_blocking=True)
+
+    # ------------------------------------------------------------------ reference API
+    def add(self, episodes):
+        """:27-96. Episodes (or chunks of ongoing ones, same `id_`) are copied into the device store."""
+        if isinstance(episodes, Episode) or not isinstance(episodes, (list, tuple)):
+            episodes = [episodes]
+        for eps in episodes:
+            n = len(eps)
+            if self._obs_store is None:
+                self._alloc(eps.observations[0], eps.actions[0] if n else 0.0)
+            self.size += n
+            if eps.id_ in self.episode_id_to_index:
+                abs_idx = self.episode_id_to_index[eps.id_]
+                st = self.episodes[abs_idx - self._num_episodes_ejected]
+                if st.is_terminated:
+                    raise AssertionError("chunk added to a terminated episode")
+                old = st.length
+                # the chunk's first observation repeats the stored last one (:Episode.concat_episode)
+                self._upload(st, eps.observations[1:], eps.actions, eps.rewards, old + 1, old)
+                self._chunks.append((abs_idx, old, n))
+            else:
+                st = _Stored(eps.id_)
+                self.episodes.append(st)
+                abs_idx = len(self.episodes) - 1 + self._num_episodes_ejected
+                self.episode_id_to_index[eps.id_] = abs_idx
+                self._upload(st, eps.observations, eps.actions, eps.rewards, 0, 0)
+                self._chunks.append((abs_idx, 0, n))
+            st.length += n
+            st.is_terminated = st.is_terminated or bool(eps.is_terminated)
+            while self.size > self.capacity:
+                ej = self.episodes.popleft()
+                self.size -= ej.length
+                ej_idx = self.episode_id_to_index.pop(ej.id_)
+                self._free_pages.extend(ej.pages)
+                self._chunks = [c for c in self._chunks if c[0] != ej_idx]
+                self._num_episodes_ejected += 1
+        self._chunk_cum = np.concatenate([[0], np.cumsum([c[2] for c in self._chunks], dtype=np.int64)])
+
+    def _locate(self, flat_index):
+        """`self._indices[flat_index]` of the reference -> (stored episode, ts)."""
+        c = int(np.searchsorted(self._chunk_cum, flat_index, side="right")) - 1
+        abs_idx, ts0, _ = self._chunks[c]
+        return self.episodes[abs_idx - self._num_episodes_ejected], ts0 + int(flat_index - self._chunk_cum[c])
+
+    def plan(self, batch_size_B, batch_length_T):
+        """The reference's sampling loop (:98-189) as index arithmetic: int32 [B*T, 4] = obs slot, action slot,
+        reward slot (-1: 0.0), flags (1 is_first | 2 is_last | 4 is_terminated). Draws from `np.random` exactly as the
+        reference does (`randint(0, n, size=B*10)` blocks, one index consumed per segment)."""
+        B, T = int(batch_size_B), int(batch_length_T)
+        n_idx = int(self._chunk_cum[-1])
+        if n_idx == 0:
+            raise ValueError("cannot sample from an empty buffer")
+        plan = np.zeros((B, T, 4), np.int32)
+        draws, cursor = [], 0
+        for b in range(B):
+            fill = 0
+            while fill < T:
+                if len(draws) <= cursor:
+                    draws.extend(np.random.randint(0, n_idx, size=B * 10).tolist())
+                st, ts = self._locate(draws[cursor])
+                cursor += 1
+                if fill > 0:
+                    ts = 0  # continuation segments start at the episode's reset observation (:139-141)
+                pages = np.asarray(st.pages, np.int64)
+                slot = lambda t: pages[t // PAGE] * PAGE + t % PAGE  # noqa: E731
+                seg = min(st.length - ts + 1, T - fill)              # observations ts .. len(episode)
+                t_obs = np.arange(ts, ts + seg)
+                rows = plan[b, fill:fill + seg]
+                rows[:, 0] = slot(t_obs)
+                rows[:, 1] = slot(np.minimum(t_obs, st.length - 1))  # last action repeated (:157-158)
+                rows[:, 2] = np.where(t_obs > 0, slot(np.maximum(t_obs - 1, 0)), -1)  # reward that led to the observation
+                if fill > 0:
+                    rows[0, 2] = -1
+                rows[0, 3] |= 1
+                rows[seg - 1, 3] |= 2
+                if st.is_terminated and ts + seg == st.length + 1:
+                    rows[seg - 1, 3] |= 4
+                fill += seg
+        return plan.reshape(B * T, 4)
+
+    def sample(self, batch_size_B: int = 16, batch_length_T: int = 64, out=None):
+        """:98-211 -> dict of float32 CUDA tensors obs [B,T,...], actions [B,T(,A...)], rewards, is_first, is_last,
+        is_terminated [B,T]. `out` may hold preallocated tensors (e.g. the engine's in.obs / in.actions / in.rewards /
+        in.is_first / in.is_terminated) to gather straight into."""
+        B, T = int(batch_size_B), int(batch_length_T)
+        plan = torch.from_numpy(self.plan(B, T)).to(self.device, non_blocking=True)
+        out = dict(out or {})
+        shapes = {"obs": (B, T) + self._obs_shape, "actions": (B, T) + self._act_shape, "rewards": (B, T),
+                  "is_first": (B, T), "is_last": (B, T), "is_terminated": (B, T)}
+        for k, shp in shapes.items():
+            t = out.get(k)
+            if t is None:
+                out[k] = torch.empty(shp, dtype=torch.float32, device=self.device)
+            elif not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == int(np.prod(shp))):
+                raise ValueError(f"out[{k!r}] must be a contiguous float32 CUDA tensor of {int(np.prod(shp))} elements")
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        rc = self.lib.dv3_replay_gather(
+            p(self._obs_store), int(self._obs_u8), int(self.normalize_uint8), self._obs_elems, p(self._act_store), self._A,
+            p(self._rew_store), p(plan), B * T, p(out["obs"]), p(out["actions"]), p(out["rewards"]), p(out["is_first"]),
+            p(out["is_last"]), p(out["is_terminated"]), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"dv3_replay_gather failed ({rc})")
+        self._last_plan = plan  # keeps the plan alive until the kernel has run
+        self.sampled_timesteps += B * T
+        return out
+
+    def get_num_episodes(self):
+        return len(self.episodes)
+
+    def get_num_timesteps(self):
+        return int(self._chunk_cum[-1])
+
+    def get_sampled_timesteps(self):
+        return self.sampled_timesteps

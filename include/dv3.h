@@ -154,6 +154,17 @@ int dv3_train_update(dv3_engine* e, const dv3_hparams* hp, uint64_t noise_seed, 
  * piece 0: observe + WM losses/BPTT [all-reduce WM grads] 1: WM clip+Adam 2: dream + value targets [all-gather targets]
  * 3: critic/actor losses + gradients [all-reduce critic, actor grads] 4: actor/critic clip+Adam (+EMA). */
 int dv3_dp_piece(dv3_engine* e, const dv3_hparams* hp, int piece, uint64_t noise_seed, int use_graph, void* stream);
+/* ---- replay sampler: the producer of the [B,T,...] sample dict ------------------------- */
+/* Row packing of EpisodeReplayBuffer.sample (utils/episode_replay_buffer.py:98-211) over an HBM-resident paged episode
+ * store. obs_store [slots, obs_elems] uint8 (obs_is_u8; normalize_u8: x/128-1 as env_runner_v2.py:53-54) or float32;
+ * act_store [slots, A]; rew_store [slots]; plan int32 [n,4] = {obs_slot, act_slot, rew_slot (-1 => 0.0), flags
+ * (1 is_first | 2 is_last | 4 is_terminated)} for the n = B*T output timesteps, built on the host from the reference's
+ * index arithmetic (:121-158: reward shift, last-action repeat, episode-boundary packing). All pointers are device
+ * pointers; outputs are float32 [n, ...] (typically the engine's in.obs / in.actions / in.rewards / in.is_first /
+ * in.is_terminated tensors). */
+int dv3_replay_gather(const void* obs_store, int obs_is_u8, int normalize_u8, int64_t obs_elems, const float* act_store, int A,
+                      const float* rew_store, const int32_t* plan, int64_t n, float* obs_out, float* act_out, float* rew_out,
+                      float* is_first, float* is_last, float* is_terminated, void* stream);
 int64_t dv3_kernel_launch_count(const dv3_engine* e); /* kernels of this library launched (or replayed) so far */
 
 /* ---- isolated ops (parity tests call the same kernels the fused path uses) ---------------------- */
