@@ -310,7 +310,9 @@ def run_ours(args):
         "config": {"workload": w["name"], "id": wid, "B_per_gpu": B, "T": T, "H": H, "global_batch": B * world,
                    "parallelism": f"dp{world}" if world > 1 else "single",
                    "l2": "256 MiB buffer written between timed steps (L2 flush)",
-                   "cuda_graph": bool(use_graph), "compute_mode": args.mode},
+                   "cuda_graph": ("whole update = one graph replay" if use_graph else
+                                  "five graph-replayed pieces cut at the NCCL collectives (dv3_dp_piece)" if world > 1 and not args.no_graph
+                                  else False), "compute_mode": args.mode},
         "clocks": clk,
         "e2e": {"value": world * 1e3 / ms_e2e, "unit": "updates/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
