@@ -18,3 +18,12 @@ class ActorNetwork:
     @property
     def ema_value_target_pct95(self):
         return self._e().tensor("ac.pct_ema")[1]
+
+    def get_weights(self):
+        """`model.get_weights()` as saved by run_experiment.py:705 (order: utils/checkpoint.py)."""
+        from ..utils import checkpoint
+        return checkpoint.get_weights(self._e(), "actor")
+
+    def set_weights(self, weights):
+        from ..utils import checkpoint
+        checkpoint.set_weights(self._e(), "actor", weights)

@@ -18,3 +18,12 @@ class CriticNetwork:
 
     def update_ema(self):  # critic_network.py:93-100
         self._e().critic_update_ema(self.ema_decay)
+
+    def get_weights(self):
+        """`model.get_weights()` as saved by run_experiment.py:705 (order: utils/checkpoint.py)."""
+        from ..utils import checkpoint
+        return checkpoint.get_weights(self._e(), "critic")
+
+    def set_weights(self, weights):
+        from ..utils import checkpoint
+        checkpoint.set_weights(self._e(), "critic", weights)

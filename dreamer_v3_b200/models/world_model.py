@@ -34,6 +34,15 @@ class _OptimizerInfo:
     def iterations(self):
         return int(self._e().tensor(f"opt.{self.group}.step").item())
 
+    def get_weights(self):
+        """Keras-2 `optimizer.get_weights()` (run_experiment.py:706): [iterations, m..., v...]."""
+        from ..utils import checkpoint
+        return checkpoint.get_optimizer_weights(self._e(), self.group)
+
+    def set_weights(self, weights):
+        from ..utils import checkpoint
+        checkpoint.set_optimizer_weights(self._e(), self.group, weights)
+
 
 class _Variables:
     """Named zero-copy views of one optimizer group's parameters."""
@@ -112,6 +121,15 @@ class WorldModel:
             self._engine = Engine(cfg, compute_mode=self.compute_mode, world_size=a["world_size"], rank=a["rank"])
             self._engine.load_params(init_params(cfg, seed=self.seed, mode="keras"))
         return self._engine
+
+    def get_weights(self):
+        """`model.get_weights()` as saved by run_experiment.py:705 (order: utils/checkpoint.py)."""
+        from ..utils import checkpoint
+        return checkpoint.get_weights(self.engine, "world_model")
+
+    def set_weights(self, weights):
+        from ..utils import checkpoint
+        checkpoint.set_weights(self.engine, "world_model", weights)
 
     @property
     def num_gru_units(self):

@@ -136,3 +136,57 @@ def test_forward_inference_matches_oracle(kind):
     wz = wm.forward_inference(states, obs, is_first)
     assert set(wz) == {"h", "z"}
     e.close()
+
+
+@pytest.mark.gpu
+def test_checkpoint_round_trip_in_the_reference_layout(tmp_path):
+    """run_experiment.py:692-714 / :489-509 file layout (`weights=model.get_weights()` object arrays +
+    optimizer lists + counters) and the exact name-keyed state; two updates, save, two more, restore, two more -> the
+    same parameters."""
+    import os
+    from dreamer_v3_b200.models.components import MLP, VectorDecoder
+    from dreamer_v3_b200.models.dreamer_model import DreamerModel
+    from dreamer_v3_b200.models.world_model import WorldModel
+    from dreamer_v3_b200.spec import Box
+    from dreamer_v3_b200.training.train_one_step import train_actor_and_critic_one_step, train_world_model_one_step
+    from dreamer_v3_b200.utils.checkpoint import load_checkpoint, save_checkpoint
+    from oracle.dreamer_oracle import make_synthetic_sample
+    B, T, H = 4, 8, 5
+    space = Box(-1, 1, (2,))
+    wm = WorldModel(model_dimension="XXS", action_space=space, batch_length_T=T, encoder=MLP(model_dimension="XXS"),
+                    decoder=VectorDecoder(model_dimension="XXS", observation_space=Box(-1, 1, (5,))), symlog_obs=True, seed=5)
+    dm = DreamerModel(model_dimension="XXS", action_space=space, batch_size_B=B, batch_length_T=T, horizon_H=H, world_model=wm)
+    e = dm.engine
+    sample = make_synthetic_sample(e.cfg, seed=9)
+    hp = dict(horizon_H=H, gamma=0.997, lambda_=0.95, actor_grad_clip=100.0, critic_grad_clip=100.0, disagree_grad_clip=100.0,
+              entropy_scale=3e-4, return_normalization_decay=0.99)
+
+    def updates(n):
+        for _ in range(n):
+            r = train_world_model_one_step(sample=sample, batch_size_B=B, batch_length_T=T, grad_clip=1000.0, world_model=wm)
+            train_actor_and_critic_one_step(world_model_forward_train_outs=r["WORLD_MODEL_forward_train_outs"],
+                                            is_terminated=sample["is_terminated"].reshape(-1), dreamer_model=dm, **hp)
+    rng = np.random.default_rng(4)
+    cfg = e.cfg
+    wm.set_noise(u_post=rng.random((T, B, cfg.Zc), dtype=np.float32), u_dyn=rng.random((H, cfg.N, cfg.Zc), dtype=np.float32),
+                 act_noise=rng.standard_normal((H + 1, cfg.N, cfg.A)).astype(np.float32))  # same noise every update
+    try:
+        updates(2)
+        save_checkpoint(str(tmp_path), dm, total_env_steps=123, total_replayed_steps=456, total_train_steps=2, iteration=1)
+        assert len(wm.get_weights()) == len(list(wm.trainable_variables)) and wm.optimizer.get_weights()[0] == 2
+        updates(2)
+        want = e.get_params()
+        for route in ("exact", "reference layout"):
+            if route == "reference layout":
+                os.remove(os.path.join(str(tmp_path), "dv3_state.npz"))
+            for n in e.tensor_names():  # scramble everything a checkpoint has to restore
+                if n.startswith(("adam_m.", "adam_v.")) or n in want:
+                    e.tensor(n).normal_()
+            counters = load_checkpoint(str(tmp_path), dm)
+            assert counters == dict(total_env_steps=123, total_replayed_steps=456, total_train_steps=2, iteration=1)
+            updates(2)
+            got = e.get_params()
+            for k in want:  # (gradient accumulation uses fp32 atomics: equal up to summation order, not bit for bit)
+                np.testing.assert_allclose(got[k], want[k], rtol=1e-4, atol=1e-6, err_msg=f"{route}: {k}")
+    finally:
+        e.close()
