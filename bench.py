@@ -289,6 +289,39 @@ def run_ours(args):
     barrier()
     final = {"wm_total": float(host_scalars[6]), "critic_total": float(host_scalars[8]), "actor_total": float(host_scalars[11])}
 
+    # ---- the reference's inner loop with the device replay sampler: buffer.sample() -> WM step -> AC step,
+    # run_experiment.py:410-472; the sample is gathered from the HBM-resident episode store straight into in.* ----
+    replay_leg = None
+    if world == 1:
+        from dreamer_v3_b200.utils.episode import Episode
+        from dreamer_v3_b200.utils.episode_replay_buffer import EpisodeReplayBuffer
+        rng = np.random.default_rng(3)
+        buf = EpisodeReplayBuffer(capacity=20000)
+        for i in range(40):
+            n = int(rng.integers(50, 500))
+            if cfg.image_obs:
+                obs = rng.integers(0, 256, size=(n + 1, cfg.img_hw, cfg.img_hw, cfg.img_c), dtype=np.uint8)
+            else:
+                obs = rng.standard_normal((n + 1, cfg.obs_dim)).astype(np.float32)
+            act = (np.eye(cfg.A, dtype=np.float32)[rng.integers(0, cfg.A, size=n)] if cfg.discrete
+                   else rng.uniform(-1, 1, size=(n, cfg.A)).astype(np.float32))
+            buf.add(Episode(f"e{i}", observations=list(obs), actions=list(act), rewards=list(rng.standard_normal(n).astype(np.float32)),
+                            is_terminated=bool(rng.random() < 0.7)))
+        outs = {"obs": e.tensor("in.obs"), "actions": e.tensor("in.actions"), "rewards": e.tensor("in.rewards"),
+                "is_first": e.tensor("in.is_first"), "is_terminated": e.tensor("in.is_terminated")}
+        np.random.seed(0)
+
+        def replay_step():
+            buf.sample(B, T, out=outs)
+            api_step(False)
+            host_scalars[:8].copy_(e.tensor("wm.scalars"), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        for _ in range(3):
+            replay_step()
+        ms_rp = timed(replay_step, args.steps)
+        replay_leg = {"value": 1e3 / ms_rp, "unit": "updates/s", "ms_per_step": ms_rp,
+                      "what": "EpisodeReplayBuffer.sample (device store, dv3_replay_gather) + both update steps + D2H of the losses"}
+
     # ---- RSSM scan step latency (observe scan forward / T) ----
     def obs_fwd():
         e.observe_forward()
@@ -322,6 +355,8 @@ def run_ours(args):
         "final_losses": final,
         "wall_s_timed_region": wall,
     }
+    if replay_leg is not None:
+        line["e2e_device_replay"] = replay_leg
     line["roofline"] = measure_roofline(e, cfg, pk, args)
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(wid)

@@ -270,8 +270,16 @@ __global__ void __launch_bounds__(256) gemm_skinny_k_kernel(GemmArgs g) {
   }
 }
 
+// The single-pass kernels are for the latency-bound launches over the B*T or (H+1)*B*T rows of the heads. The conv
+// contractions over ~10^6 pixel rows have the same "few outputs / short K" shapes but are throughput problems: they stay
+// on the tiled / tensor-core kernels (4 ms instead of 0.2 ms per launch otherwise).
+constexpr long long kSkinnyMaxRows = 32768;
+bool skinny_shape(const GemmArgs& g) {
+  return !g.ta && g.M >= 64 && g.M <= kSkinnyMaxRows && ((g.N <= 32 && g.K >= 32) || (g.K <= 32 && g.N >= 32));
+}
+
 bool gemm_skinny(cudaStream_t s, const GemmArgs& g) {
-  if (g.ta || g.M < 64) return false;
+  if (!skinny_shape(g)) return false;
   if (g.N <= 32 && g.K >= 32) {
     const int grid = (int)min((long long)148 * 8, ((long long)g.M + 15) / 16);
     const int vec = ((uintptr_t)g.A % 16 == 0) && (g.lda % 4 == 0) && (g.K % 4 == 0);
@@ -319,7 +327,7 @@ bool pdl_enabled() {
 }
 
 void gemm_dispatch(cudaStream_t s, const GemmArgs& g, int mode) {
-  if (g.M > 0 && g.N > 0 && g.K > 0 && !g.ta && g.M >= 64 && ((g.N <= 32 && g.K >= 32) || (g.K <= 32 && g.N >= 32)) && mode != 2) {
+  if (g.M > 0 && g.N > 0 && g.K > 0 && skinny_shape(g) && mode != 2) {
     gemm_f32(s, g);   // degenerate shapes: skinny kernels, exact fp32 in every mode
     return;
   }
