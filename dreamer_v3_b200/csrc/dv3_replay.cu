@@ -74,41 +74,43 @@ replay_gather_kernel(const void* __restrict__ obs_store, const float* __restrict
 // contiguous bytes per instruction - and every thread keeps UNROLL independent loads in flight before it converts and
 // stores, which is what a copy needs to approach the HBM roofline.
 template <bool U8, bool NORM, int UNROLL>
-__global__ void __launch_bounds__(RP_THREADS)
+__global__ void __launch_bounds__(RP_THREADS, 8)   // 8 CTAs per SM resident: <= 32 registers, 32-bit index arithmetic
 replay_gather_wide_kernel(const void* __restrict__ obs_store, const float* __restrict__ act_store, const float* __restrict__ rew_store,
                           const int4* __restrict__ plan, long long n, long long obs_elems, int A,
                           float* __restrict__ obs_out, float* __restrict__ act_out, float* __restrict__ rew_out,
                           float* __restrict__ is_first, float* __restrict__ is_last, float* __restrict__ is_term) {
   const long long tid = (long long)blockIdx.x * RP_THREADS + threadIdx.x;
   const long long nthreads = (long long)gridDim.x * RP_THREADS;
-  const long long upr = obs_elems >> 2;  // units per row
-  const long long total = n * upr;
-  for (long long base = (long long)blockIdx.x * RP_THREADS * UNROLL + threadIdx.x; base < total; base += nthreads * UNROLL) {
-    uint4 v[UNROLL];
-    unsigned w[UNROLL];
-    long long off[UNROLL];
+  const unsigned upr = (unsigned)(obs_elems >> 2);   // units per row; the host guarantees n * obs_elems < 2^32
+  const unsigned total = (unsigned)n * upr;
+  const unsigned stride = gridDim.x * RP_THREADS * UNROLL;
+  for (unsigned base = blockIdx.x * RP_THREADS * UNROLL + threadIdx.x; base < total; base += stride) {
+    uint4 v[U8 ? 1 : UNROLL];
+    unsigned w[U8 ? UNROLL : 1];
+    unsigned off[UNROLL];   // unit index in the output
 #pragma unroll
     for (int j = 0; j < UNROLL; ++j) {
-      const long long u = base + (long long)j * RP_THREADS;
+      const unsigned u = base + j * RP_THREADS;
+      off[j] = u;
       if (u < total) {
-        const long long row = u / upr, col = u - row * upr;
+        const unsigned row = u / upr, col = u - row * upr;
         const long long slot = plan[row].x;
-        off[j] = row * obs_elems + col * 4;
-        if (U8) w[j] = __ldcs(reinterpret_cast<const unsigned*>((const unsigned char*)obs_store + slot * obs_elems) + col);
-        else v[j] = __ldcs(reinterpret_cast<const uint4*>((const float*)obs_store + slot * obs_elems) + col);
+        if (U8) w[U8 ? j : 0] = __ldcs(reinterpret_cast<const unsigned*>((const unsigned char*)obs_store + slot * obs_elems) + col);
+        else v[U8 ? 0 : j] = __ldcs(reinterpret_cast<const uint4*>((const float*)obs_store + slot * obs_elems) + col);
       }
     }
 #pragma unroll
     for (int j = 0; j < UNROLL; ++j) {
-      const long long u = base + (long long)j * RP_THREADS;
-      if (u >= total) continue;
+      if (off[j] >= total) continue;
+      float4* dst = reinterpret_cast<float4*>(obs_out) + off[j];   // rows are contiguous in the output: unit u -> float4 u
       if (U8) {
+        const unsigned x = w[U8 ? j : 0];
         float4 o;
-        o.x = (float)(w[j] & 0xff); o.y = (float)((w[j] >> 8) & 0xff); o.z = (float)((w[j] >> 16) & 0xff); o.w = (float)(w[j] >> 24);
+        o.x = (float)(x & 0xff); o.y = (float)((x >> 8) & 0xff); o.z = (float)((x >> 16) & 0xff); o.w = (float)(x >> 24);
         if (NORM) { o.x = o.x * 0.0078125f - 1.0f; o.y = o.y * 0.0078125f - 1.0f; o.z = o.z * 0.0078125f - 1.0f; o.w = o.w * 0.0078125f - 1.0f; }
-        __stcs(reinterpret_cast<float4*>(obs_out + off[j]), o);
+        __stcs(dst, o);
       } else {
-        __stcs(reinterpret_cast<uint4*>(obs_out + off[j]), v[j]);
+        __stcs(reinterpret_cast<uint4*>(dst), v[U8 ? 0 : j]);
       }
     }
   }
@@ -126,7 +128,7 @@ int replay_gather(cudaStream_t s, const void* obs_store, int obs_is_u8, int norm
                   const float* rew_store, const int32_t* plan, long long n, float* obs_out, float* act_out, float* rew_out,
                   float* is_first, float* is_last, float* is_term) {
   if (n <= 0) return 0;
-  if (obs_elems % 4 == 0 && obs_elems >= 1024) {
+  if (obs_elems % 4 == 0 && obs_elems >= 1024 && n * obs_elems < (1LL << 32)) {
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     const int unroll = obs_is_u8 ? 8 : 4;
