@@ -11,6 +11,7 @@
 // The LayerNorm backward needs whole-row statistics; instead of a separate row-owner stage (one more barrier) every
 // consumer CTA redoes it for the 16 rows from data it has to stage anyway. The contractions read TRANSPOSED weight
 // copies (refreshed once per update) so that weight reads stay coalesced.
+#include <algorithm>
 #include <cstdlib>
 
 #include "dv3_scan_common.cuh"
@@ -376,6 +377,267 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd_kernel(ScanBwdPa
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Two-stage version: every contraction whose K runs over what the previous stage has just produced is done SPLIT-K by
+// the producer itself - the task that owns 32 dlogit columns (or cwx GRU units) multiplies its own K-slice with the
+// matching weight rows and adds the [B x all-columns] partial product to the consumer's input with fp32 atomics (RED
+// to L2). That removes the S1 and S3 stages of the kernel above together with their grid barriers: two barriers and two
+// latency chains per step instead of four.
+//   X(t)  dp_pre = LN'SiLU'(dp_act[t]); dh_tot = d_hz[t].h (+ recurrent part of step t+1) + dp_pre . W_post_h^T; GRU gate
+//         gradients of the task's units; then dh_in[t] += dgh_task . Ut[task rows, :],  du[t] += dgx_task . Kt[task rows, :]
+//   Y(t)  dx_pre = LN'SiLU'(du[t]); dz_in = dx_pre . W_pre[:Z]^T for the task's 32 columns -> d_hz[t-1].z, categorical
+//         backward of step t-1 -> dlogits[t-1]; then dp_act[t-1] += dlogits_task . Wt_zq[task rows, :]
+// dp_act, du and dh_in are accumulators: the launcher zeroes them. Summation order inside them is not fixed (atomics);
+// the values agree with the four-stage kernel to fp32 rounding.
+
+// out[b*ldo + c] += sum_{k < K} in_s[k][b] * wrow(k)[c], c < ncols: thread = output column (coalesced weight rows),
+// the 16 rows of a k are one broadcast LDS.128 quad
+template <class RowFn>
+__device__ __forceinline__ void partial_accumulate(const float* in_s, int K, RowFn wrow, int ncols, float* out, size_t ldo, int B) {
+  for (int c = threadIdx.x; c < ncols; c += kThreads) {
+    float acc[kRows];
+#pragma unroll
+    for (int b = 0; b < kRows; ++b) acc[b] = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      const float w_ = wrow(k)[c];
+      const float4* iv = reinterpret_cast<const float4*>(in_s + (size_t)k * kInLd);
+      const float4 a0 = iv[0], a1 = iv[1], a2 = iv[2], a3 = iv[3];
+      acc[0] = fmaf(a0.x, w_, acc[0]); acc[1] = fmaf(a0.y, w_, acc[1]); acc[2] = fmaf(a0.z, w_, acc[2]); acc[3] = fmaf(a0.w, w_, acc[3]);
+      acc[4] = fmaf(a1.x, w_, acc[4]); acc[5] = fmaf(a1.y, w_, acc[5]); acc[6] = fmaf(a1.z, w_, acc[6]); acc[7] = fmaf(a1.w, w_, acc[7]);
+      acc[8] = fmaf(a2.x, w_, acc[8]); acc[9] = fmaf(a2.y, w_, acc[9]); acc[10] = fmaf(a2.z, w_, acc[10]); acc[11] = fmaf(a2.w, w_, acc[11]);
+      acc[12] = fmaf(a3.x, w_, acc[12]); acc[13] = fmaf(a3.y, w_, acc[13]); acc[14] = fmaf(a3.z, w_, acc[14]); acc[15] = fmaf(a3.w, w_, acc[15]);
+    }
+#pragma unroll
+    for (int b = 0; b < kRows; ++b)
+      if (b < B) atomicAdd(out + (size_t)b * ldo + c, acc[b]);
+  }
+}
+
+// Categorical backward of the (row, categorical) pairs of the 32-column block c0 at step tt, gradient w.r.t. z taken from
+// dz(b, col) ; dlogits -> global and, transposed, into dl_s[col - c0][b] for the split-K contraction that follows.
+template <class DzFn>
+__device__ __forceinline__ void repr_bwd_block(const ScanBwdParams& p, int tt, int c0, float* dl_s, DzFn dz) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Zk = p.Zk, Z = p.Z, cats = 32 / Zk;
+  for (int pr = warp; pr < kRows * cats; pr += kWarps) {
+    const int b = pr / cats, cl_ = pr % cats, cat = c0 / Zk + cl_;
+    const bool rok = b < p.B && cat < p.Zc;
+    const bool act = rok && lane < Zk;
+    const int col = cat * Zk + lane;
+    const size_t bt = (size_t)(rok ? b : 0) * p.T + tt;
+    const float l = act ? p.post_logits[bt * Z + col] : -INFINITY;
+    const float mx = warp_max(l);
+    const float ex = act ? expf(l - mx) : 0.f;
+    const float sden = warp_sum(ex);
+    const float prb = rok ? ex / sden : 0.f;
+    const float g = act ? 0.99f * (dz(b, col) + p.dpost[bt * Z + col]) : 0.f;
+    const float dot = warp_sum(g * prb);
+    const float dl = act ? prb * (g - dot) : 0.f;
+    if (act) p.dlogits[bt * Z + col] = dl;
+    if (lane < Zk && cl_ * Zk + lane < 32) dl_s[(size_t)(cl_ * Zk + lane) * kInLd + b] = dl;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd2_kernel(ScanBwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  unsigned int bar_target = 0;
+  const int B = p.B, T = p.T, G = p.G, D = p.D, Z = p.Z;
+  const int W = G + Z;
+  const int nblk = gridDim.x, blk = blockIdx.x;
+  const int tasks_Z = (Z + 31) / 32;
+  const int cwx = pick_cw(G, nblk), ntx = (G + cwx - 1) / cwx;   // X: GRU units per task
+  float* in_s = &sm.in_chunk[0][0][0];
+
+  // ---- weight slices resident in shared memory for all T steps (launcher: one task per CTA per stage and they fit) ----
+  const bool cached = p.cache_weights != 0;
+  float* wcP = reinterpret_cast<float*>(smem_raw + sizeof(Smem));   // Wt_post_h[:, my cwx units]   [D][cwx]
+  float* wcU = wcP + (size_t)D * cwx;                               // Ut rows of my units           [3 cwx][G]
+  float* wcK = wcU + (size_t)3 * cwx * G;                           // Kt rows of my units           [3 cwx][D]
+  float* wcX = wcK + (size_t)3 * cwx * D;                           // Wt_pre_z[:, my 32 columns]    [D][32]
+  float* wcQ = wcX + (size_t)D * 32;                                // Wt_zq rows of my 32 columns   [32][D]
+  if (cached) {
+    if (blk < ntx) {
+      cache_slice(wcP, p.Wt_post_h, G, blk * cwx, cwx, G, D);
+      for (int e = threadIdx.x; e < 3 * cwx * G; e += kThreads) {
+        const int k = e / G, c = e % G, u = blk * cwx + k % cwx;
+        wcU[e] = u < G ? p.Ut[(size_t)((k / cwx) * G + u) * G + c] : 0.f;
+      }
+      for (int e = threadIdx.x; e < 3 * cwx * D; e += kThreads) {
+        const int k = e / D, c = e % D, u = blk * cwx + k % cwx;
+        wcK[e] = u < G ? p.Kt[(size_t)((k / cwx) * G + u) * D + c] : 0.f;
+      }
+    }
+    if (blk < tasks_Z) {
+      cache_slice(wcX, p.Wt_pre_z, Z, blk * 32, 32, Z, D);
+      for (int e = threadIdx.x; e < 32 * D; e += kThreads) {
+        const int k = e / D, c = e % D;
+        wcQ[e] = blk * 32 + k < Z ? p.Wt_zq[(size_t)(blk * 32 + k) * D + c] : 0.f;
+      }
+    }
+    __syncthreads();
+  }
+  auto stamp = [&](int i) {
+    if (p.stamps != nullptr && blk == 0 && threadIdx.x == 0) {
+      unsigned long long v;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
+      p.stamps[i] = v;
+    }
+  };
+  // dlogits[tt] of a 32-column block are in in_s rows [0, 32): add their share of dp_act[tt]
+  auto dp_act_partial = [&](int tt, int c0) {
+    const int kq = min(32, Z - c0);
+    if (cached) partial_accumulate(in_s, kq, [&](int k) { return wcQ + (size_t)k * D; }, D, p.dp_act + (size_t)tt * D, (size_t)T * D, B);
+    else partial_accumulate(in_s, kq, [&](int k) { return p.Wt_zq + (size_t)(c0 + k) * D; }, D, p.dp_act + (size_t)tt * D, (size_t)T * D, B);
+    __syncthreads();
+  };
+
+  // prologue: dlogits of the last step (no recurrent contribution yet) and their dp_act
+  for (int task = blk; task < tasks_Z; task += nblk) {
+    const int c0 = task * 32;
+    repr_bwd_block(p, T - 1, c0, in_s, [&](int b, int col) { return __ldcg(p.d_hz + ((size_t)b * T + (T - 1)) * W + G + col); });
+    dp_act_partial(T - 1, c0);
+  }
+  grid_bar(p.bar, bar_target);
+  stamp(0);
+
+  for (int t = T - 1; t >= 0; --t) {
+    const int si = (T - 1 - t) * 8;
+    // ===== X(t) =====
+    for (int task = blk; task < ntx; task += nblk) {
+      const int c0 = task * cwx;
+      // epilogue operands (independent of the contraction): loads issued up front. thread -> (row b, unit jj), 2 passes
+      float e_d[2], e_z[2], e_r[2], e_c[2], e_h[2], e_g[2];
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int e = threadIdx.x + it * kThreads, b = e / cwx, j = c0 + e % cwx;
+        const bool ok = e < kRows * cwx && b < B && j < G;
+        const size_t bt = (size_t)(ok ? b : 0) * T + t;
+        const int jj = ok ? j : 0;
+        float d = ok ? __ldcg(p.d_hz + bt * W + jj) : 0.f;
+        if (ok && t + 1 < T) d += (1.f - p.is_first[bt + 1]) * __ldcg(p.dh_in + (bt + 1) * G + jj);   // recurrent part (X(t+1), complete)
+        e_d[it] = d;
+        e_z[it] = ok ? p.gates[bt * 3 * G + jj] : 0.f;
+        e_r[it] = ok ? p.gates[bt * 3 * G + G + jj] : 0.f;
+        e_c[it] = ok ? p.gates[bt * 3 * G + 2 * G + jj] : 0.f;
+        e_h[it] = ok ? p.h_in[bt * G + jj] : 0.f;
+        e_g[it] = ok ? p.gh[bt * 3 * G + 2 * G + jj] : 0.f;
+      }
+      cta_lnbwd_stage(in_s, p.dp_act + (size_t)t * D, p.p_pre + (size_t)t * D, (size_t)T * D, p.p_mean + t, p.p_rstd + t, (size_t)T,
+                      p.post_g, p.post_b, B, D, task == 0 ? p.dp_pre + (size_t)t * D : nullptr);
+      float acc[kRows];
+#pragma unroll
+      for (int b = 0; b < kRows; ++b) acc[b] = 0.f;
+      const int lane = threadIdx.x & 31;
+      if (cwx == 32) {
+        if (cached) gemv_acc<32>(acc, in_s, wcP, 32, (c0 + lane) < G ? lane : -1, D);
+        else gemv_acc<32>(acc, in_s, p.Wt_post_h, G, (c0 + lane) < G ? c0 + lane : -1, D);
+        gemv_finish<32>(sm, acc);
+      } else if (cwx == 16) {
+        if (cached) gemv_acc<16>(acc, in_s, wcP, 16, (c0 + lane % 16) < G ? lane % 16 : -1, D);
+        else gemv_acc<16>(acc, in_s, p.Wt_post_h, G, (c0 + lane % 16) < G ? c0 + lane % 16 : -1, D);
+        gemv_finish<16>(sm, acc);
+      } else {
+        if (cached) gemv_acc<8>(acc, in_s, wcP, 8, (c0 + lane % 8) < G ? lane % 8 : -1, D);
+        else gemv_acc<8>(acc, in_s, p.Wt_post_h, G, (c0 + lane % 8) < G ? c0 + lane % 8 : -1, D);
+        gemv_finish<8>(sm, acc);
+      }
+      // gate gradients -> global (weight gradients after the kernel) and, as [k][row], into the staging buffer:
+      // rows [0, 3 cwx) = dgh (z, r, c blocks of cwx), rows [3 cwx, 6 cwx) = dgx   (dp_pre in in_s is dead now)
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int e = threadIdx.x + it * kThreads;
+        if (e < kRows * cwx) {
+          const int b = e / cwx, jj = e % cwx, j = c0 + jj;
+          float dz = 0.f, dr = 0.f, dc = 0.f, dcr = 0.f;
+          if (b < B && j < G) {
+            const size_t bt = (size_t)b * T + t;
+            const float d = sm.tile[b][jj] + e_d[it];
+            const float z = e_z[it], r = e_r[it], c = e_c[it];
+            dz = d * (e_h[it] - c) * z * (1.f - z);
+            dc = d * (1.f - z) * (1.f - c * c);
+            dr = dc * e_g[it] * r * (1.f - r);
+            dcr = dc * r;
+            p.d_hz[bt * W + j] = e_d[it];
+            float* gxo = p.dgx + bt * 3 * G;
+            float* gho = p.dgh + bt * 3 * G;
+            gxo[j] = dz; gxo[G + j] = dr; gxo[2 * G + j] = dc;
+            gho[j] = dz; gho[G + j] = dr; gho[2 * G + j] = dcr;
+            atomicAdd(p.dh_in + bt * G + j, d * z);   // the direct path h_in -> h of the GRU cell
+          }
+          in_s[(size_t)(0 * cwx + jj) * kInLd + b] = dz;
+          in_s[(size_t)(1 * cwx + jj) * kInLd + b] = dr;
+          in_s[(size_t)(2 * cwx + jj) * kInLd + b] = dcr;
+          in_s[(size_t)(3 * cwx + jj) * kInLd + b] = dz;
+          in_s[(size_t)(4 * cwx + jj) * kInLd + b] = dr;
+          in_s[(size_t)(5 * cwx + jj) * kInLd + b] = dc;
+        }
+      }
+      __syncthreads();
+      // split-K: this task's 3 cwx gate rows of U^T / K^T
+      auto urow = [&](int k) { return p.Ut + (size_t)((k / cwx) * G + min(c0 + k % cwx, G - 1)) * G; };
+      auto krow = [&](int k) { return p.Kt + (size_t)((k / cwx) * G + min(c0 + k % cwx, G - 1)) * D; };
+      if (cached) {
+        partial_accumulate(in_s, 3 * cwx, [&](int k) { return wcU + (size_t)k * G; }, G, p.dh_in + (size_t)t * G, (size_t)T * G, B);
+        partial_accumulate(in_s + (size_t)3 * cwx * kInLd, 3 * cwx, [&](int k) { return wcK + (size_t)k * D; }, D, p.du + (size_t)t * D, (size_t)T * D, B);
+      } else {
+        partial_accumulate(in_s, 3 * cwx, urow, G, p.dh_in + (size_t)t * G, (size_t)T * G, B);
+        partial_accumulate(in_s + (size_t)3 * cwx * kInLd, 3 * cwx, krow, D, p.du + (size_t)t * D, (size_t)T * D, B);
+      }
+      __syncthreads();
+    }
+    stamp(si + 1); stamp(si + 2);
+    stamp(si + 3);
+    grid_bar(p.bar, bar_target);
+    stamp(si + 4);
+
+    // ===== Y(t) (at t = 0 only dx_pre is needed, for the weight gradients) =====
+    for (int task = blk; task < (t > 0 ? tasks_Z : 1); task += nblk) {
+      const int c0 = task * 32;
+      float e_old[2], e_keep[2];
+      if (t > 0) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int e = threadIdx.x + it * kThreads, b = e >> 5, j = e & 31;
+          const bool ok = b < B && c0 + j < Z;
+          const size_t bt = (size_t)(ok ? b : 0) * T + t;
+          e_old[it] = ok ? __ldcg(p.d_hz + (bt - 1) * W + G + c0 + (ok ? j : 0)) : 0.f;
+          e_keep[it] = ok ? 1.f - p.is_first[bt] : 0.f;
+        }
+      }
+      cta_lnbwd_stage(in_s, p.du + (size_t)t * D, p.x_pre + (size_t)t * D, (size_t)T * D, p.x_mean + t, p.x_rstd + t, (size_t)T,
+                      p.pre_g, p.pre_b, B, D, task == 0 ? p.dx_pre + (size_t)t * D : nullptr);
+      if (t == 0) break;
+      float acc[kRows];
+#pragma unroll
+      for (int b = 0; b < kRows; ++b) acc[b] = 0.f;
+      const int lane = threadIdx.x & 31;
+      if (cached) gemv_acc<32>(acc, in_s, wcX, 32, (c0 + lane) < Z ? lane : -1, D);
+      else gemv_acc<32>(acc, in_s, p.Wt_pre_z, Z, (c0 + lane) < Z ? c0 + lane : -1, D);
+      gemv_finish<32>(sm, acc);
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int e = threadIdx.x + it * kThreads;
+        const int b = e >> 5, j = e & 31;
+        if (b < B && c0 + j < Z) {
+          const float v = e_old[it] + e_keep[it] * sm.tile[b][j];
+          p.d_hz[((size_t)b * T + t - 1) * W + G + c0 + j] = v;
+          sm.tile[b][j] = v;      // the categorical backward below takes the updated gradient from here, not from L2
+        }
+      }
+      __syncthreads();
+      repr_bwd_block(p, t - 1, c0, in_s, [&](int b, int col) { return sm.tile[b][col - c0]; });
+      dp_act_partial(t - 1, c0);
+    }
+    stamp(si + 5); stamp(si + 6);
+    stamp(si + 7);
+    if (t > 0) grid_bar(p.bar, bar_target);
+    stamp(si + 8);
+  }
+}
+
 // out[c, r] = in[r, c]
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
   __shared__ float tile[32][33];
@@ -411,8 +673,37 @@ int scan_bwd_max_ctas(int device) {
 cudaError_t launch_observe_scan_bwd(cudaStream_t s, const ScanBwdParams& p, int ctas) {
   ScanBwdParams pp = p;
   if (const char* f = std::getenv("DV3_SCAN_BWD_CTAS")) { const int n = std::atoi(f); if (n > 0 && n < ctas) ctas = n; }
-  // same task-width choice as the kernel (pick_cw), to size the shared-memory weight cache
+  // Two-stage split-K kernel for the small layer sizes (XS: 19.5 vs 27.3 us per step). Its atomics grow with
+  // tasks x 16 x (G + D): at S (1 M per step) it ties with the four-stage kernel, at M (3.4 M) it loses (C4: 34.1 vs 31.9 ms
+  // per update), so the larger sizes stay on the four-stage kernel. DV3_SCAN_BWD_V1 / _V2 force one of them (tests, A / B).
+  const bool v1 = std::getenv("DV3_SCAN_BWD_V1") != nullptr || ((p.G > 256 || p.D > 256) && std::getenv("DV3_SCAN_BWD_V2") == nullptr);
   auto cw_of = [&](int ncols) { return ((ncols + 31) / 32 * 2 > ctas) ? 32 : (((ncols + 15) / 16 * 2 > ctas) ? 16 : 8); };
+  void* args[] = {&pp};
+  cudaMemsetAsync(pp.bar, 0, sizeof(unsigned int), s);
+  if (!v1) {
+    // accumulators of the split-K contractions
+    const size_t n = (size_t)p.B * p.T;
+    cudaMemsetAsync(pp.dp_act, 0, n * p.D * sizeof(float), s);
+    cudaMemsetAsync(pp.du, 0, n * p.D * sizeof(float), s);
+    cudaMemsetAsync(pp.dh_in, 0, n * p.G * sizeof(float), s);
+    const int tz = (p.Z + 31) / 32;
+    // CTAs beyond the widest stage only lengthen the grid barrier: shrink the grid when that keeps the task width
+    {
+      const int cw0 = cw_of(p.G), need = std::max((p.G + cw0 - 1) / cw0, tz);
+      const int ctas0 = ctas;
+      if (need < ctas) { ctas = need; if (cw_of(p.G) != cw0) ctas = ctas0; }
+    }
+    const int cwx = cw_of(p.G), ntx = (p.G + cwx - 1) / cwx;
+    const size_t cache = ((size_t)p.D * cwx + (size_t)3 * cwx * p.G + (size_t)3 * cwx * p.D + (size_t)p.D * 32 + (size_t)32 * p.D) * sizeof(float);
+    const bool fits = sizeof(Smem) + cache <= 227 * 1024 && ntx <= ctas && tz <= ctas && std::getenv("DV3_SCAN_NO_CACHE") == nullptr;
+    pp.cache_weights = fits ? 1 : 0;
+    const size_t smem = sizeof(Smem) + (fits ? cache : 0);
+    cudaFuncSetAttribute(observe_scan_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)observe_scan_bwd2_kernel, dim3(ctas), dim3(kThreads), args, smem, s);
+    if (e == cudaSuccess) count_launch();
+    return e;
+  }
+  // same task-width choice as the kernel (pick_cw), to size the shared-memory weight cache
   const int cw1 = cw_of(p.D), cw3 = cw_of(p.G + p.D);
   const int nt1 = (p.D + cw1 - 1) / cw1, nt3 = (p.G + cw3 - 1) / cw3 + (p.D + cw3 - 1) / cw3;
   const size_t cache = ((size_t)p.Z * cw1 + (size_t)p.D * 32 * 2 + (size_t)3 * p.G * cw3) * sizeof(float);
@@ -421,8 +712,6 @@ cudaError_t launch_observe_scan_bwd(cudaStream_t s, const ScanBwdParams& p, int 
   pp.cache_weights = fits ? 1 : 0;
   const size_t smem = sizeof(Smem) + (fits ? cache : 0);
   cudaFuncSetAttribute(observe_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaMemsetAsync(pp.bar, 0, sizeof(unsigned int), s);
-  void* args[] = {&pp};
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)observe_scan_bwd_kernel, dim3(ctas), dim3(kThreads), args, smem, s);
   if (e == cudaSuccess) count_launch();
   return e;

@@ -38,5 +38,11 @@ st = e.tensor("debug.scan_stamps").cpu().numpy().astype(np.int64)
 st = (st[0::2] & 0xFFFFFFFF) | (st[1::2] << 32)
 d = np.diff(st[: T * 8 + 1].astype(np.float64)) / 1e3
 d = d.reshape(T, 8)
-names = ["S1 work", "S1 sync", "S2 work", "S2 sync", "S3 work", "S3 sync", "S4 work", "S4 sync"]
-print("backward per-step mean us:", {n: round(float(d[2:-1, i].mean()), 2) for i, n in enumerate(names)}, "step total", round(float(d[2:-1].sum(1).mean()), 2))
+if os.environ.get("DV3_SCAN_BWD_V1"):
+    names = ["S1 work", "S1 sync", "S2 work", "S2 sync", "S3 work", "S3 sync", "S4 work", "S4 sync"]
+    print("backward (four-stage) per-step mean us:", {n: round(float(d[2:-1, i].mean()), 2) for i, n in enumerate(names)}, "step total", round(float(d[2:-1].sum(1).mean()), 2))
+else:   # two-stage kernel: stamps 1-3 close X(t), 4 follows its barrier, 5-7 close Y(t), 8 follows its barrier
+    m = d[2:-1].mean(0)
+    print("backward (two-stage) per-step mean us:", {"X work": round(float(m[0] + m[1] + m[2]), 2), "X sync": round(float(m[3]), 2),
+                                                     "Y work": round(float(m[4] + m[5] + m[6]), 2), "Y sync": round(float(m[7]), 2)},
+          "step total", round(float(d[2:-1].sum(1).mean()), 2))
