@@ -61,6 +61,7 @@ struct ScanBwdParams {
   float* dx_pre;     // [B, T, D]
   unsigned int* bar; // grid-barrier counter (zeroed by the launcher)
   int cache_weights; // set by the launcher: every CTA keeps its weight slice of each stage in shared memory
+  int cwx;           // set by the launcher (two-stage kernel): GRU units per X task (8, 16 or 32)
   unsigned long long* stamps;  // optional [T*8+1] globaltimer stamps of CTA 0 (profiling), may be null
 };
 

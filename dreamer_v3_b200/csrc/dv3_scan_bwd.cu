@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd2_kernel(ScanBwdP
   const int W = G + Z;
   const int nblk = gridDim.x, blk = blockIdx.x;
   const int tasks_Z = (Z + 31) / 32;
-  const int cwx = pick_cw(G, nblk), ntx = (G + cwx - 1) / cwx;   // X: GRU units per task
+  const int cwx = p.cwx, ntx = (G + cwx - 1) / cwx;   // X: GRU units per task
   float* in_s = &sm.in_chunk[0][0][0];
 
   // ---- weight slices resident in shared memory for all T steps (launcher: one task per CTA per stage and they fit) ----
@@ -687,13 +687,13 @@ cudaError_t launch_observe_scan_bwd(cudaStream_t s, const ScanBwdParams& p, int 
     cudaMemsetAsync(pp.du, 0, n * p.D * sizeof(float), s);
     cudaMemsetAsync(pp.dh_in, 0, n * p.G * sizeof(float), s);
     const int tz = (p.Z + 31) / 32;
-    // CTAs beyond the widest stage only lengthen the grid barrier: shrink the grid when that keeps the task width
-    {
-      const int cw0 = cw_of(p.G), need = std::max((p.G + cw0 - 1) / cw0, tz);
-      const int ctas0 = ctas;
-      if (need < ctas) { ctas = need; if (cw_of(p.G) != cw0) ctas = ctas0; }
-    }
-    const int cwx = cw_of(p.G), ntx = (p.G + cwx - 1) / cwx;
+    // X task width: the narrowest of 32 / 16 / 8 units that still gives every CTA work (DV3_SCAN_BWD_CW overrides: probing aid)
+    int cwx = cw_of(p.G);
+    if (const char* f = std::getenv("DV3_SCAN_BWD_CW")) { const int c = std::atoi(f); if (c == 8 || c == 16 || c == 32) cwx = c; }
+    const int ntx = (p.G + cwx - 1) / cwx;
+    pp.cwx = cwx;
+    // CTAs beyond the widest stage only lengthen the grid barrier
+    if (std::max(ntx, tz) < ctas) ctas = std::max(ntx, tz);
     const size_t cache = ((size_t)p.D * cwx + (size_t)3 * cwx * p.G + (size_t)3 * cwx * p.D + (size_t)p.D * 32 + (size_t)32 * p.D) * sizeof(float);
     const bool fits = sizeof(Smem) + cache <= 227 * 1024 && ntx <= ctas && tz <= ctas && std::getenv("DV3_SCAN_NO_CACHE") == nullptr;
     pp.cache_weights = fits ? 1 : 0;
