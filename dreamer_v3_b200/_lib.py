@@ -51,6 +51,7 @@ SIGNATURES = {
     "dv3_forward_inference": (_I, [_P, _I, _U64, _P]),
     "dv3_dream_forward": (_I, [_P, _F, _I, _P]),
     "dv3_dream_forward_actions": (_I, [_P, _F, _I, _I, _P]),
+    "dv3_replay_plan": (_I64, [_I, _I, _I, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P]),
     "dv3_replay_gather": (_I, [_P, _I, _I, _I64, _P, _I, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P]),
     "dv3_ac_loss_backward": (_I, [_P, C.POINTER(Dv3Hparams), _I, _P]),
     "dv3_critic_init_ema": (_I, [_P, _P]),

@@ -191,6 +191,15 @@ int dv3_replay_gather(const void* obs_store, int obs_is_u8, int normalize_u8, in
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+int64_t dv3_replay_plan(int B, int T, int page, const int64_t* chunk_cum, const int32_t* chunk_ep, const int32_t* chunk_ts0, int64_t n_chunks,
+                        const int32_t* ep_len, const uint8_t* ep_term, const int64_t* ep_page_off, const int32_t* pages,
+                        const int64_t* draws, int64_t n_draws, int32_t* plan) {
+  if (B < 1 || T < 1 || page < 1 || n_chunks < 1 || !chunk_cum || !chunk_ep || !chunk_ts0 || !ep_len || !ep_term || !ep_page_off || !pages ||
+      !draws || !plan) return INT64_MIN;
+  return dv3::replay_plan(B, T, page, (const long long*)chunk_cum, chunk_ep, chunk_ts0, n_chunks, ep_len, ep_term, (const long long*)ep_page_off,
+                          pages, (const long long*)draws, n_draws, plan);
+}
+
 // ---- isolated ops ---------------------------------------------------------------------------------------------
 static int op_done() { return cudaGetLastError() == cudaSuccess ? 0 : -1; }
 int dv3_op_symlog(const float* x, float* y, int64_t n, void* stream) { dv3::symlog_fwd(S(stream), x, y, n); return op_done(); }

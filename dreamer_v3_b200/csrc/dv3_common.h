@@ -232,5 +232,8 @@ void bump_counter(cudaStream_t s, unsigned long long* ctr);
 int replay_gather(cudaStream_t s, const void* obs_store, int obs_is_u8, int normalize_u8, long long obs_elems, const float* act_store, int A,
                   const float* rew_store, const int32_t* plan, long long n, float* obs_out, float* act_out, float* rew_out,
                   float* is_first, float* is_last, float* is_term);
+long long replay_plan(int B, int T, int page, const long long* chunk_cum, const int* chunk_ep, const int* chunk_ts0, long long n_chunks,
+                      const int* ep_len, const unsigned char* ep_term, const long long* ep_page_off, const int* pages,
+                      const long long* draws, long long n_draws, int32_t* plan);
 
 }  // namespace dv3

@@ -158,4 +158,46 @@ int replay_gather(cudaStream_t s, const void* obs_store, int obs_is_u8, int norm
   return 0;
 }
 
+// Host side of EpisodeReplayBuffer.sample (utils/episode_replay_buffer.py:98-189): the reference's sampling loop as index
+// arithmetic over the episode tables. Consumes `draws` (the caller's np.random.randint(0, n_indices, size = B*10) blocks,
+// concatenated) exactly as the reference consumes them: one per segment, in order.
+// Returns the number of draws consumed, or -(needed) when `draws` ran out (the caller appends a block and calls again).
+long long replay_plan(int B, int T, int page, const long long* chunk_cum, const int* chunk_ep, const int* chunk_ts0, long long n_chunks,
+                      const int* ep_len, const unsigned char* ep_term, const long long* ep_page_off, const int* pages,
+                      const long long* draws, long long n_draws, int32_t* plan) {
+  long long cursor = 0;
+  auto slot = [&](int ep, int t) -> int32_t { return (int32_t)((long long)pages[ep_page_off[ep] + t / page] * page + t % page); };
+  for (int b = 0; b < B; ++b) {
+    int fill = 0;
+    while (fill < T) {
+      if (cursor >= n_draws) return -(cursor + 1);
+      const long long flat = draws[cursor++];
+      // chunk that holds index `flat`: last c with chunk_cum[c] <= flat
+      long long lo = 0, hi = n_chunks;
+      while (hi - lo > 1) { const long long mid = (lo + hi) / 2; if (chunk_cum[mid] <= flat) lo = mid; else hi = mid; }
+      const int ep = chunk_ep[lo];
+      int ts = chunk_ts0[lo] + (int)(flat - chunk_cum[lo]);
+      if (fill > 0) ts = 0;                              // continuation segments start at the reset observation (:139-141)
+      const int len = ep_len[ep];
+      const int seg = std::min(len - ts + 1, T - fill);  // observations ts .. len
+      for (int i = 0; i < seg; ++i) {
+        const int t = ts + i;
+        int32_t* row = plan + ((size_t)b * T + fill + i) * 4;
+        row[0] = slot(ep, t);
+        row[1] = slot(ep, std::min(t, len - 1));        // last action repeated (:157-158)
+        row[2] = t > 0 ? slot(ep, t - 1) : -1;           // reward that led to the observation; 0.0 at a reset
+        row[3] = 0;
+      }
+      int32_t* first = plan + ((size_t)b * T + fill) * 4;
+      if (fill > 0) first[2] = -1;
+      first[3] |= 1;
+      int32_t* last = plan + ((size_t)b * T + fill + seg - 1) * 4;
+      last[3] |= 2;
+      if (ep_term[ep] && ts + seg == len + 1) last[3] |= 4;
+      fill += seg;
+    }
+  }
+  return cursor;
+}
+
 }  // namespace dv3

@@ -36,12 +36,18 @@ class _Stored:
 
 
 class EpisodeReplayBuffer:
-    def __init__(self, capacity: int = 10000, device=None, normalize_uint8=True):
-        if not torch.cuda.is_available():
+    def __init__(self, capacity: int = 10000, device=None, normalize_uint8=True, _host_index_only=False):
+        # _host_index_only (tests of the host logic on a machine without a GPU): bookkeeping and `plan()` work, the store is
+        # a host tensor nobody gathers from - `sample()` raises
+        self._host_only = bool(_host_index_only)
+        if not self._host_only and not torch.cuda.is_available():
             raise RuntimeError("EpisodeReplayBuffer keeps its store in HBM; no CUDA device found (there is no CPU fallback)")
         self.lib = _lib.load()
         self.capacity = int(capacity)
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self._host_only:
+            self.device = torch.device("cpu")
+        else:
+            self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.normalize_uint8 = bool(normalize_uint8)
         self.episodes = deque()                # _Stored, oldest first
         self.episode_id_to_index = {}          # id_ -> absolute episode index (ejected ones counted)
@@ -53,6 +59,7 @@ class EpisodeReplayBuffer:
         self._obs_store = self._act_store = self._rew_store = None
         self._free_pages = []
         self._num_pages = 0
+        self._tab = None
 
     # ------------------------------------------------------------------ device store
     def _alloc(self, obs0, act0):
@@ -137,54 +144,54 @@ class EpisodeReplayBuffer:
                 self._free_pages.extend(ej.pages)
                 self._chunks = [c for c in self._chunks if c[0] != ej_idx]
                 self._num_episodes_ejected += 1
-        self._chunk_cum = np.concatenate([[0], np.cumsum([c[2] for c in self._chunks], dtype=np.int64)])
+        self._chunk_cum = np.concatenate([[0], np.cumsum([c[2] for c in self._chunks], dtype=np.int64)]).astype(np.int64)
+        self._tab = None
 
-    def _locate(self, flat_index):
-        """`self._indices[flat_index]` of the reference -> (stored episode, ts)."""
-        c = int(np.searchsorted(self._chunk_cum, flat_index, side="right")) - 1
-        abs_idx, ts0, _ = self._chunks[c]
-        return self.episodes[abs_idx - self._num_episodes_ejected], ts0 + int(flat_index - self._chunk_cum[c])
+    def _tables(self):
+        """Episode / chunk tables for `dv3_replay_plan` (rebuilt after `add`)."""
+        if self._tab is None:
+            eps = list(self.episodes)
+            off = np.zeros(len(eps) + 1, np.int64)
+            np.cumsum([len(e.pages) for e in eps], out=off[1:])
+            self._tab = dict(
+                ep_len=np.asarray([e.length for e in eps], np.int32),
+                ep_term=np.asarray([e.is_terminated for e in eps], np.uint8),
+                ep_page_off=off[:-1].copy(),
+                pages=np.asarray([p for e in eps for p in e.pages], np.int32),
+                chunk_ep=np.asarray([c[0] - self._num_episodes_ejected for c in self._chunks], np.int32),
+                chunk_ts0=np.asarray([c[1] for c in self._chunks], np.int32),
+                chunk_cum=np.ascontiguousarray(self._chunk_cum[:-1]),
+            )
+        return self._tab
 
     def plan(self, batch_size_B, batch_length_T):
-        """The reference's sampling loop (:98-189) as index arithmetic: int32 [B*T, 4] = obs slot, action slot,
-        reward slot (-1: 0.0), flags (1 is_first | 2 is_last | 4 is_terminated). Draws from `np.random` exactly as the
-        reference does (`randint(0, n, size=B*10)` blocks, one index consumed per segment)."""
+        """The reference's sampling loop (:98-189) as index arithmetic (native: `dv3_replay_plan`): int32 [B*T, 4] = obs
+        slot, action slot, reward slot (-1: 0.0), flags (1 is_first | 2 is_last | 4 is_terminated). Draws from `np.random`
+        exactly as the reference does (`randint(0, n, size=B*10)` blocks, one index consumed per segment)."""
         B, T = int(batch_size_B), int(batch_length_T)
         n_idx = int(self._chunk_cum[-1])
         if n_idx == 0:
             raise ValueError("cannot sample from an empty buffer")
-        plan = np.zeros((B, T, 4), np.int32)
-        draws, cursor = [], 0
-        for b in range(B):
-            fill = 0
-            while fill < T:
-                if len(draws) <= cursor:
-                    draws.extend(np.random.randint(0, n_idx, size=B * 10).tolist())
-                st, ts = self._locate(draws[cursor])
-                cursor += 1
-                if fill > 0:
-                    ts = 0  # continuation segments start at the episode's reset observation (:139-141)
-                pages = np.asarray(st.pages, np.int64)
-                slot = lambda t: pages[t // PAGE] * PAGE + t % PAGE  # noqa: E731
-                seg = min(st.length - ts + 1, T - fill)              # observations ts .. len(episode)
-                t_obs = np.arange(ts, ts + seg)
-                rows = plan[b, fill:fill + seg]
-                rows[:, 0] = slot(t_obs)
-                rows[:, 1] = slot(np.minimum(t_obs, st.length - 1))  # last action repeated (:157-158)
-                rows[:, 2] = np.where(t_obs > 0, slot(np.maximum(t_obs - 1, 0)), -1)  # reward that led to the observation
-                if fill > 0:
-                    rows[0, 2] = -1
-                rows[0, 3] |= 1
-                rows[seg - 1, 3] |= 2
-                if st.is_terminated and ts + seg == st.length + 1:
-                    rows[seg - 1, 3] |= 4
-                fill += seg
-        return plan.reshape(B * T, 4)
+        t = self._tables()
+        plan = np.empty((B * T, 4), np.int32)
+        draws = np.random.randint(0, n_idx, size=B * 10).astype(np.int64)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        while True:
+            rc = self.lib.dv3_replay_plan(B, T, PAGE, ptr(t["chunk_cum"]), ptr(t["chunk_ep"]), ptr(t["chunk_ts0"]), len(t["chunk_ep"]),
+                                          ptr(t["ep_len"]), ptr(t["ep_term"]), ptr(t["ep_page_off"]), ptr(t["pages"]),
+                                          ptr(draws), len(draws), ptr(plan))
+            if rc >= 0:
+                return plan
+            if rc < -(1 << 40):
+                raise RuntimeError("dv3_replay_plan rejected its arguments")
+            draws = np.concatenate([draws, np.random.randint(0, n_idx, size=B * 10).astype(np.int64)])
 
     def sample(self, batch_size_B: int = 16, batch_length_T: int = 64, out=None):
         """:98-211 -> dict of float32 CUDA tensors obs [B,T,...], actions [B,T(,A...)], rewards, is_first, is_last,
         is_terminated [B,T]. `out` may hold preallocated tensors (e.g. the engine's in.obs / in.actions / in.rewards /
         in.is_first / in.is_terminated) to gather straight into."""
+        if self._host_only:
+            raise RuntimeError("the sample is gathered by a CUDA kernel; there is no CPU fallback")
         B, T = int(batch_size_B), int(batch_length_T)
         plan = torch.from_numpy(self.plan(B, T)).to(self.device, non_blocking=True)
         out = dict(out or {})

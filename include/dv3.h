@@ -165,6 +165,15 @@ int dv3_dp_piece(dv3_engine* e, const dv3_hparams* hp, int piece, uint64_t noise
 int dv3_replay_gather(const void* obs_store, int obs_is_u8, int normalize_u8, int64_t obs_elems, const float* act_store, int A,
                       const float* rew_store, const int32_t* plan, int64_t n, float* obs_out, float* act_out, float* rew_out,
                       float* is_first, float* is_last, float* is_terminated, void* stream);
+/* Host side of the same call: builds `plan` [B*T, 4] from the episode tables with the reference's sampling loop
+ * (:113-189). chunk_* [n_chunks]: the arrival-ordered index space (`_indices` of the reference, run-length encoded:
+ * chunk_cum[c] = first flat index of chunk c, chunk_ep / chunk_ts0 = its episode (row of the ep_* tables) and first
+ * timestep); ep_len / ep_term / ep_page_off [episodes], pages: the page lists, `page` timesteps per page. `draws`: the
+ * caller's np.random.randint(0, n_indices, size=B*10) blocks, consumed one per segment as the reference does. Returns
+ * the number of draws consumed, or -(k) when more than the k-1 given draws are needed (append a block and call again). */
+int64_t dv3_replay_plan(int B, int T, int page, const int64_t* chunk_cum, const int32_t* chunk_ep, const int32_t* chunk_ts0, int64_t n_chunks,
+                        const int32_t* ep_len, const uint8_t* ep_term, const int64_t* ep_page_off, const int32_t* pages,
+                        const int64_t* draws, int64_t n_draws, int32_t* plan);
 int64_t dv3_kernel_launch_count(const dv3_engine* e); /* kernels of this library launched (or replayed) so far */
 
 /* ---- isolated ops (parity tests call the same kernels the fused path uses) ---------------------- */

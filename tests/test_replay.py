@@ -33,10 +33,31 @@ def test_oracle_matches_reference_buffer(kind):
             assert s[k].shape == want.shape and np.array_equal(s[k], want), (kind, i, k)
 
 
+@pytest.mark.parametrize("kind", ("vec", "img"))
+def test_native_plan_matches_reference_buffer(kind):
+    """Host logic without a GPU: the bookkeeping of `add` (pages, chunk index space, ejection) and the native plan builder
+    `dv3_replay_plan`; the plan is applied with NumPy to a host copy of the store and compared with the reference's output."""
+    buf = device_buffer(kind == "img", _host_index_only=True)
+    assert buf.get_num_episodes() == int(GOLD[f"{kind}/num_episodes"])
+    assert buf.get_num_timesteps() == int(GOLD[f"{kind}/num_timesteps"])
+    obs_s, act_s, rew_s = buf._obs_store.numpy(), buf._act_store.numpy(), buf._rew_store.numpy()
+    for i, (B, T, seed) in enumerate(SAMPLES):
+        np.random.seed(seed)
+        plan = buf.plan(B, T)
+        want = {k: GOLD[f"{kind}/s{i}/{k}"] for k in KEYS}
+        assert np.array_equal(obs_s[plan[:, 0]].reshape(want["obs"].shape), want["obs"])
+        assert np.array_equal(act_s[plan[:, 1]].reshape(want["actions"].shape), want["actions"])
+        assert np.array_equal(np.where(plan[:, 2] >= 0, rew_s[np.maximum(plan[:, 2], 0)], 0.0).reshape(B, T), want["rewards"])
+        for bit, k in ((1, "is_first"), (2, "is_last"), (4, "is_terminated")):
+            assert np.array_equal((plan[:, 3] & bit).reshape(B, T) != 0, want[k]), k
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        buf.sample(4, 8)
+
+
 def device_buffer(image, capacity=CAPACITY, normalize_uint8=False, **kw):
     from dreamer_v3_b200.utils.episode import Episode
     from dreamer_v3_b200.utils.episode_replay_buffer import EpisodeReplayBuffer
-    buf = EpisodeReplayBuffer(capacity=capacity, normalize_uint8=normalize_uint8)
+    buf = EpisodeReplayBuffer(capacity=capacity, normalize_uint8=normalize_uint8, _host_index_only=kw.pop("_host_index_only", False))
     for id_, obs, actions, rewards, term in make_adds(image=image, **kw):
         buf.add(Episode(id_, observations=list(obs), actions=list(actions), rewards=list(rewards), is_terminated=term))
     return buf
