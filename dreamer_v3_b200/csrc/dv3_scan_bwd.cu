@@ -416,22 +416,42 @@ __device__ __forceinline__ void partial_accumulate(const float* in_s, int K, Row
 
 // Categorical backward of the (row, categorical) pairs of the 32-column block c0 at step tt, gradient w.r.t. z taken from
 // dz(b, col) ; dlogits -> global and, transposed, into dl_s[col - c0][b] for the split-K contraction that follows.
-template <class DzFn>
-__device__ __forceinline__ void repr_bwd_block(const ScanBwdParams& p, int tt, int c0, float* dl_s, DzFn dz) {
+// The first two pairs of every warp (all of them when a categorical has 32 classes) take their logits / KL gradient from
+// `pre` (repr_prefetch, issued before the contraction: one L2 round trip off the critical path).
+struct ReprPre { float l[2], dp[2]; };
+__device__ __forceinline__ ReprPre repr_prefetch(const ScanBwdParams& p, int tt, int c0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Zk = p.Zk, Z = p.Z, cats = 32 / Zk;
-  for (int pr = warp; pr < kRows * cats; pr += kWarps) {
+  ReprPre r;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int pr = warp + it * kWarps, b = pr / cats, cat = c0 / Zk + pr % cats;
+    const bool act = pr < kRows * cats && b < p.B && cat < p.Zc && lane < Zk;
+    const size_t bt = (size_t)(act ? b : 0) * p.T + tt;
+    const int col = act ? cat * Zk + lane : 0;
+    r.l[it] = act ? p.post_logits[bt * Z + col] : -INFINITY;
+    r.dp[it] = act ? p.dpost[bt * Z + col] : 0.f;
+  }
+  return r;
+}
+template <class DzFn>
+__device__ __forceinline__ void repr_bwd_block(const ScanBwdParams& p, int tt, int c0, float* dl_s, const ReprPre& pre, DzFn dz) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Zk = p.Zk, Z = p.Z, cats = 32 / Zk;
+  int it = 0;
+  for (int pr = warp; pr < kRows * cats; pr += kWarps, ++it) {
     const int b = pr / cats, cl_ = pr % cats, cat = c0 / Zk + cl_;
     const bool rok = b < p.B && cat < p.Zc;
     const bool act = rok && lane < Zk;
     const int col = cat * Zk + lane;
     const size_t bt = (size_t)(rok ? b : 0) * p.T + tt;
-    const float l = act ? p.post_logits[bt * Z + col] : -INFINITY;
+    const float l = it < 2 ? (it == 0 ? pre.l[0] : pre.l[1]) : (act ? p.post_logits[bt * Z + col] : -INFINITY);
+    const float dpv = it < 2 ? (it == 0 ? pre.dp[0] : pre.dp[1]) : (act ? p.dpost[bt * Z + col] : 0.f);
     const float mx = warp_max(l);
     const float ex = act ? expf(l - mx) : 0.f;
     const float sden = warp_sum(ex);
     const float prb = rok ? ex / sden : 0.f;
-    const float g = act ? 0.99f * (dz(b, col) + p.dpost[bt * Z + col]) : 0.f;
+    const float g = act ? 0.99f * (dz(b, col) + dpv) : 0.f;
     const float dot = warp_sum(g * prb);
     const float dl = act ? prb * (g - dot) : 0.f;
     if (act) p.dlogits[bt * Z + col] = dl;
@@ -497,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd2_kernel(ScanBwdP
   // prologue: dlogits of the last step (no recurrent contribution yet) and their dp_act
   for (int task = blk; task < tasks_Z; task += nblk) {
     const int c0 = task * 32;
-    repr_bwd_block(p, T - 1, c0, in_s, [&](int b, int col) { return __ldcg(p.d_hz + ((size_t)b * T + (T - 1)) * W + G + col); });
+    repr_bwd_block(p, T - 1, c0, in_s, repr_prefetch(p, T - 1, c0), [&](int b, int col) { return __ldcg(p.d_hz + ((size_t)b * T + (T - 1)) * W + G + col); });
     dp_act_partial(T - 1, c0);
   }
   grid_bar(p.bar, bar_target);
@@ -607,6 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd2_kernel(ScanBwdP
           e_keep[it] = ok ? 1.f - p.is_first[bt] : 0.f;
         }
       }
+      const ReprPre rpre = repr_prefetch(p, t > 0 ? t - 1 : 0, c0);
       cta_lnbwd_stage(in_s, p.du + (size_t)t * D, p.x_pre + (size_t)t * D, (size_t)T * D, p.x_mean + t, p.x_rstd + t, (size_t)T,
                       p.pre_g, p.pre_b, B, D, task == 0 ? p.dx_pre + (size_t)t * D : nullptr);
       if (t == 0) break;
@@ -628,7 +649,7 @@ __global__ void __launch_bounds__(kThreads, 1) observe_scan_bwd2_kernel(ScanBwdP
         }
       }
       __syncthreads();
-      repr_bwd_block(p, t - 1, c0, in_s, [&](int b, int col) { return sm.tile[b][col - c0]; });
+      repr_bwd_block(p, t - 1, c0, in_s, rpre, [&](int b, int col) { return sm.tile[b][col - c0]; });
       dp_act_partial(t - 1, c0);
     }
     stamp(si + 5); stamp(si + 6);
@@ -673,7 +694,7 @@ int scan_bwd_max_ctas(int device) {
 cudaError_t launch_observe_scan_bwd(cudaStream_t s, const ScanBwdParams& p, int ctas) {
   ScanBwdParams pp = p;
   if (const char* f = std::getenv("DV3_SCAN_BWD_CTAS")) { const int n = std::atoi(f); if (n > 0 && n < ctas) ctas = n; }
-  // Two-stage split-K kernel for the small layer sizes (XS: 19.5 vs 27.3 us per step). Its atomics grow with
+  // Two-stage split-K kernel for the small layer sizes (XS: 17.9 vs 27.3 us per step). Its atomics grow with
   // tasks x 16 x (G + D): at S (1 M per step) it ties with the four-stage kernel, at M (3.4 M) it loses (C4: 34.1 vs 31.9 ms
   // per update), so the larger sizes stay on the four-stage kernel. DV3_SCAN_BWD_V1 / _V2 force one of them (tests, A / B).
   const bool v1 = std::getenv("DV3_SCAN_BWD_V1") != nullptr || ((p.G > 256 || p.D > 256) && std::getenv("DV3_SCAN_BWD_V2") == nullptr);
