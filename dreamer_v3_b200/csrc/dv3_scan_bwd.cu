@@ -1,6 +1,8 @@
 // Reverse-time BPTT through the RSSM observe scan as ONE cooperative launch (replaces the ~700 per-op launches of
 // the reverse loop in Engine::wm_loss_backward). Only input gradients are on the recurrence; every weight gradient
-// is a single N-row contraction after the kernel. Per step t (T-1 .. 0), 4 stages separated by grid barriers:
+// is a single N-row contraction after the kernel. Two kernels (launch_observe_scan_bwd picks one by layer width):
+// observe_scan_bwd_kernel, described here, and the two-stage split-K observe_scan_bwd2_kernel further down (small
+// layer sizes). Per step t (T-1 .. 0), 4 stages separated by grid barriers:
 //   S1  dp_act = dlogits[t] . W_zq^T                                 (narrow column tasks: the K = Z contraction is the
 //                                                                      longest of the step, so it is spread over many CTAs)
 //   S2  dp_pre = LN'SiLU'(dp_act) recomputed by every task CTA (one warp per row, staged in shared memory);
