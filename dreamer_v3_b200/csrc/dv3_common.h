@@ -62,6 +62,9 @@ void gemm_f32(cudaStream_t s, const GemmArgs& g);
 // mode 0: always fp32 SIMT; mode 1: bf16 tcgen05 tensor cores for large contractions (dv3_gemm_tc.cu)
 void gemm_dispatch(cudaStream_t s, const GemmArgs& g, int mode);
 bool gemm_tc_eligible(const GemmArgs& g);
+// weight-streaming kernels for <= 16 rows against a large weight matrix (dv3_gemv.cu), fp32 in every mode
+bool gemv16_eligible(const GemmArgs& g);
+void gemv16(cudaStream_t s, const GemmArgs& g);
 void gemm_tc(cudaStream_t s, const GemmArgs& g);  // bf16 tcgen05 / TMEM path
 bool gemm_tma_eligible(const GemmArgs& g);
 bool gemm_tma(cudaStream_t s, const GemmArgs& g);  // both operands bf16 K-major in global memory: TMA + tcgen05

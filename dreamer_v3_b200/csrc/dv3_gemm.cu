@@ -327,6 +327,10 @@ bool pdl_enabled() {
 }
 
 void gemm_dispatch(cudaStream_t s, const GemmArgs& g, int mode) {
+  if (g.M > 0 && g.N > 0 && g.K > 0 && mode != 2 && gemv16_eligible(g)) {   // the 16 scan rows against a large weight matrix
+    gemv16(s, g);
+    return;
+  }
   if (g.M > 0 && g.N > 0 && g.K > 0 && skinny_shape(g) && mode != 2) {
     gemm_f32(s, g);   // degenerate shapes: skinny kernels, exact fp32 in every mode
     return;

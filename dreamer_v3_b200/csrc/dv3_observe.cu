@@ -136,7 +136,9 @@ int Engine::wm_loss_backward(cudaStream_t s) {
 
   phase_mark("wmb.heads_bwd");
   // reverse-time scan: only input gradients on the recurrence
-  if (use_persistent && scan_bwd_ctas > 0) {
+  // (as in the forward pass: at XL the weights no longer fit L2 and the per-op path on the weight-streaming kernels of
+  //  dv3_gemv.cu is faster - C5 62.0 vs 72.7 ms per update; at L the persistent kernel still wins, 40.6 vs 42.8 ms)
+  if (use_persistent && scan_bwd_ctas > 0 && G <= 2048) {
     transpose_f32(s, post_repr.w, Wt_zq, D, Z);
     transpose_f32(s, Wp.w + (size_t)E * D, Wt_post_h, G, D);
     transpose_f32(s, gru_U, Ut, G, 3 * G);

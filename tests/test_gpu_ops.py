@@ -116,3 +116,23 @@ def test_ln_silu():
             torch.from_numpy(x).double(), (D,), torch.from_numpy(g).double(), torch.from_numpy(b).double(), 1e-3)).numpy()
         got = ops.ln_silu(dev(x), dev(g), dev(b)).cpu().numpy()
         np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("tb", (False, True))
+@pytest.mark.parametrize("M,N,K", ((16, 12288, 1024), (16, 1030, 1302), (5, 1024, 4099), (1, 4096, 517), (16, 96, 12288)))
+@pytest.mark.parametrize("beta,with_bias", ((0.0, True), (1.0, False)))
+@pytest.mark.parametrize("mode", (0, 1))
+def test_weight_streaming_contraction_of_the_scan_rows(M, N, K, tb, beta, with_bias, mode):
+    """dv3_gemv.cu: <= 16 rows against a large weight matrix (the per-op observe scan at the large sizes), both weight
+    layouts, ragged N / K, unaligned leading dimensions, split-K accumulation; fp32 in every mode."""
+    import torch
+    from dreamer_v3_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    A = torch.randn((M, K), device="cuda", generator=g)
+    B = torch.randn((N, K) if tb else (K, N), device="cuda", generator=g)
+    bias = torch.randn((N,), device="cuda", generator=g) if with_bias else None
+    C0 = torch.randn((M, N), device="cuda", generator=g)
+    want = A.double() @ (B.double().t() if tb else B.double()) + (bias.double() if with_bias else 0.0) + beta * C0.double()
+    got = ops.gemm(A, B, tb=tb, bias=bias, C_=C0.clone(), beta=beta, mode=mode)
+    err = float((got.double() - want).abs().max() / want.abs().max())
+    assert err < 2e-6, err
