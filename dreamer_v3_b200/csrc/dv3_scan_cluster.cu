@@ -255,17 +255,14 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
       float x = 0.f;
       if (row_ok) {
         x = actw;
-        float w8[8];
+        float w32[32];   // all 32 row gathers in flight at once: one L2 round trip instead of four
 #pragma unroll
-        for (int c0 = 0; c0 < 32; c0 += 8) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int cls = first ? sm.idx0[c0 + c] : sm.idx[b][c0 + c];
-            w8[c] = p.W_pre[(size_t)((c0 + c) * Zk + cls) * D + u0 + j];
-          }
-#pragma unroll
-          for (int c = 0; c < 8; ++c) x += w8[c];
+        for (int c = 0; c < 32; ++c) {
+          const int cls = first ? sm.idx0[c] : sm.idx[b][c];
+          w32[c] = p.W_pre[(size_t)(c * Zk + cls) * D + u0 + j];
         }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) x += w32[c];
         p.x_pre[bt * D + u0 + j] = x;
         // masked recurrent inputs kept for the backward pass (world_model.py:246-250): my units / my 2 categoricals
         p.h_in[bt * G + u0 + j] = first ? sm.h0[u0 + j] : sm.hown[b][j];
@@ -370,21 +367,46 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
         lg[q4] = v;
         if (r < B) p.post_logits[((size_t)r * T + t) * Z + z0c + cl_ * 32 + lane] = v;
       }
-      // 2 categoricals x 16 rows = 32 (row, categorical) pairs, one warp each (4 per warp)
+      // 2 categoricals x 16 rows = 32 (row, categorical) pairs, one warp each (4 per warp). The four pairs of a warp go
+      // through the shuffle reductions together (their chains interleave instead of running back to back).
+      float mx[4], ex[4], sden[4], pu[4];
+      double cdf[4];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) mx[q4] = lg[q4];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) mx[q4] = fmaxf(mx[q4], __shfl_xor_sync(0xffffffffu, mx[q4], o));
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) { ex[q4] = expf(lg[q4] - mx[q4]); sden[q4] = ex[q4]; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) sden[q4] += __shfl_xor_sync(0xffffffffu, sden[q4], o);
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) { pu[q4] = 0.99f * (ex[q4] / sden[q4]) + 0.01f * (1.0f / 32.f); cdf[q4] = (double)pu[q4]; }
+      // fp64 inclusive scan of the fp32 probabilities (exact, as categorical_pick in dv3_device.cuh), four at a time
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const double tq = __shfl_up_sync(0xffffffffu, cdf[q4], o);
+          if (lane >= o) cdf[q4] += tq;
+        }
+      }
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         const int pr = warp + q4 * kWarps;
         const int r = pr >> 1, cl_ = pr & 1;
         const int cat = z0c / Zk + cl_;
+        const double tot = __shfl_sync(0xffffffffu, cdf[q4], 31);
+        const unsigned below = __ballot_sync(0xffffffffu, cdf[q4] <= (double)up[q4] * tot);
+        const int pick = min(__popc(below), 31);
         if (r >= B) continue;
-        const float l = lg[q4];
-        const float mx = warp_max(l);
-        const float ex = expf(l - mx);
-        const float s = warp_sum(ex);
-        const float pu = 0.99f * (ex / s) + 0.01f * (1.0f / 32.f);
         const size_t rt = (size_t)r * T + t;
-        p.post_probs[rt * Z + cat * 32 + lane] = pu;
-        const int pick = categorical_pick(pu, true, 32, up[q4], lane);
+        p.post_probs[rt * Z + cat * 32 + lane] = pu[q4];
         if (lane == 0) p.z_idx[rt * Zc + cat] = pick;
         p.hz[rt * W + G + cat * 32 + lane] = (lane == pick) ? 1.f : 0.f;
         if (lane < kC) cl.map_shared_rank(&sm.idx[0][0], lane)[r * 32 + cat] = pick;
