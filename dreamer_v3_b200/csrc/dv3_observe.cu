@@ -158,29 +158,48 @@ int Engine::wm_loss_backward(cudaStream_t s) {
     // LayerNorm gain / offset gradients of the two in-loop layers, one N-row pass each
     ln_silu_bwd(s, dp_act_all, D, p_pre, D, p_mean, p_rstd, Wp.g, Wp.b, nullptr, 0, Wp.dg, Wp.db, 1, N, D);
     ln_silu_bwd(s, du_all, D, x_pre, D, x_mean, x_rstd, Wx.g, Wx.b, nullptr, 0, Wx.dg, Wx.db, 1, N, D);
-  } else
+  } else {
+  // per-op path. At the sizes where it is the default (XL) the contractions stream their weights (dv3_gemv.cu) and the
+  // [K, N] layout streams 1.7x faster than the [N, K] one: use the transposed copies (one transposition per update).
+  const bool tp = G > 2048 || std::getenv("DV3_SCAN_BWD_TP") != nullptr;   // (env: lets the small test sizes cover this branch)
+  if (tp) {
+    transpose_f32(s, post_repr.w, Wt_zq, D, Z);
+    transpose_f32(s, Wp.w + (size_t)E * D, Wt_post_h, G, D);
+    transpose_f32(s, gru_U, Ut, G, 3 * G);
+    transpose_f32(s, gru_K, Kt, D, 3 * G);
+    transpose_f32(s, Wx.w, Wt_pre_z, Z, D);
+  }
   for (int t = T - 1; t >= 0; --t) {
     float* dhz_t = d_hz + (size_t)t * (G + Z);
     // posterior representation layer: straight-through dz + KL dprobs -> dlogits
     repr_bwd(s, post_logits + (size_t)t * Z, T * Z, dhz_t + G, ldhz, dpost + (size_t)t * Z, T * Z,
              dpost_logits + (size_t)t * Z, T * Z, B, Zc, Zk);
-    mm(dpost_logits + (size_t)t * Z, T * Z, false, post_repr.w, Z, true, sB_D0, D, B, D, Z);
+    if (tp) mm(dpost_logits + (size_t)t * Z, T * Z, false, Wt_zq, D, false, sB_D0, D, B, D, Z);
+    else mm(dpost_logits + (size_t)t * Z, T * Z, false, post_repr.w, Z, true, sB_D0, D, B, D, Z);
     ln_silu_bwd(s, sB_D0, D, p_pre + (size_t)t * D, T * D, p_mean + t, p_rstd + t, Wp.g, Wp.b, dp_pre + (size_t)t * D,
                 T * D, Wp.dg, Wp.db, T, B, D);
-    mm(dp_pre + (size_t)t * D, T * D, false, Wp.w + (size_t)E * D, D, true, dhz_t, ldhz, B, G, D, nullptr, 1.f);
+    if (tp) mm(dp_pre + (size_t)t * D, T * D, false, Wt_post_h, G, false, dhz_t, ldhz, B, G, D, nullptr, 1.f);
+    else mm(dp_pre + (size_t)t * D, T * D, false, Wp.w + (size_t)E * D, D, true, dhz_t, ldhz, B, G, D, nullptr, 1.f);
     // GRU
     gru_bwd(s, dhz_t, ldhz, gx + (size_t)t * 3 * G, T * 3 * G, gh + (size_t)t * 3 * G, T * 3 * G, h_in + (size_t)t * G,
             T * G, dgx + (size_t)t * 3 * G, T * 3 * G, dgh + (size_t)t * 3 * G, T * 3 * G, dh_in + (size_t)t * G, T * G, 0, B, G);
-    mm(dgh + (size_t)t * 3 * G, T * 3 * G, false, gru_U, 3 * G, true, dh_in + (size_t)t * G, T * G, B, G, 3 * G, nullptr, 1.f);
-    mm(dgx + (size_t)t * 3 * G, T * 3 * G, false, gru_K, 3 * G, true, sB_D0, D, B, D, 3 * G);
+    if (tp) {
+      mm(dgh + (size_t)t * 3 * G, T * 3 * G, false, Ut, G, false, dh_in + (size_t)t * G, T * G, B, G, 3 * G, nullptr, 1.f);
+      mm(dgx + (size_t)t * 3 * G, T * 3 * G, false, Kt, D, false, sB_D0, D, B, D, 3 * G);
+    } else {
+      mm(dgh + (size_t)t * 3 * G, T * 3 * G, false, gru_U, 3 * G, true, dh_in + (size_t)t * G, T * G, B, G, 3 * G, nullptr, 1.f);
+      mm(dgx + (size_t)t * 3 * G, T * 3 * G, false, gru_K, 3 * G, true, sB_D0, D, B, D, 3 * G);
+    }
     ln_silu_bwd(s, sB_D0, D, x_pre + (size_t)t * D, T * D, x_mean + t, x_rstd + t, Wx.g, Wx.b, dx_pre + (size_t)t * D,
                 T * D, Wx.dg, Wx.db, T, B, D);
     if (t > 0) {
-      mm(dx_pre + (size_t)t * D, T * D, false, Wx.w, D, true, sB_Z, Z, B, Z, D);
+      if (tp) mm(dx_pre + (size_t)t * D, T * D, false, Wt_pre_z, Z, false, sB_Z, Z, B, Z, D);
+      else mm(dx_pre + (size_t)t * D, T * D, false, Wx.w, D, true, sB_Z, Z, B, Z, D);
       float* dprev = d_hz + (size_t)(t - 1) * (G + Z);
       scan_mask_grads(s, in_is_first + t, T, dh_in + (size_t)t * G, T * G, dprev, ldhz, B, G);
       scan_mask_grads(s, in_is_first + t, T, sB_Z, Z, dprev + G, ldhz, B, Z);
     }
+  }
   }
   phase_mark("wmb.scan_bwd");
   // weight gradients, one N-row contraction each; they are independent of one another -> four concurrent chains.
