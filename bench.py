@@ -21,9 +21,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints it on stdout) off it
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly one JSON line: NCCL prints its version banner on stdout at the VERSION and WARN debug levels, so
+# the banner level is switched off and whatever NCCL still logs goes to stderr
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+    os.environ["NCCL_DEBUG"] = "NONE"
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
