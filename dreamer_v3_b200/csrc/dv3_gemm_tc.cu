@@ -482,7 +482,7 @@ void launch_tc(cudaStream_t s, const GemmArgs& g) {
   if (tiles <= 48 && g.K >= 16 * BK) {
     splits = (int)min((long long)(148 / tiles), (long long)(g.K / (8 * BK)));
     if (splits < 1) splits = 1;
-    if (splits > 32) splits = 32;
+    if (splits > 148) splits = 148;   // (conv weight gradients: a 48 x 32 output over 10^6 pixel rows is one tile - every SM takes a K slice)
   }
   const int kps = cdiv(cdiv(g.K, splits), BK) * BK;
   splits = cdiv(g.K, kps);
