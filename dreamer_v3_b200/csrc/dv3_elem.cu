@@ -72,7 +72,9 @@ __global__ void to_bf16_scalar_kernel(const float* __restrict__ src, int lds, __
 // ---- LayerNorm + SiLU: one warp per row ----------------------------------------------------------------
 // templated on the per-lane element count so that narrow rows (conv channels, D = 24..96) do not pay for 32 predicated
 // iterations: EPL = ceil(D / 32) rounded up to a power of two
-template <int kLnMaxPerLane>
+// RU rows per warp iteration: on narrow rows (conv channels over ~10^6 pixel rows) one 128-byte load in flight per warp
+// leaves the kernel latency-bound (1.6 TB/s); RU = 4 rows go through the loads and the shuffle reductions together.
+template <int kLnMaxPerLane, int RU>
 __global__ void ln_silu_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ y, int ldy,
                                    float* __restrict__ mean_out, float* __restrict__ rstd_out, int sstride, long long rows, int D,
@@ -82,45 +84,74 @@ __global__ void ln_silu_fwd_kernel(const float* __restrict__ x, int ldx, const f
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long r = warp0; r < rows; r += nwarps) {
-    const float* xr = x + (size_t)r * ldx;
-    float v[kLnMaxPerLane];
-    float s = 0.f;
+  float gm[kLnMaxPerLane], bt[kLnMaxPerLane];
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
-      const int c = lane + 32 * i;
-      v[i] = (c < D) ? xr[c] : 0.f;
-      s += v[i];
-    }
-    const float mean = warp_sum(s) / (float)D;
-    float q = 0.f;
+  for (int i = 0; i < kLnMaxPerLane; ++i) {
+    const int c = lane + 32 * i;
+    gm[i] = (c < D) ? gamma[c] : 0.f;
+    bt[i] = (c < D) ? beta[c] : 0.f;
+  }
+  for (long long r0 = warp0; r0 < rows; r0 += nwarps * RU) {
+    float v[RU][kLnMaxPerLane], s[RU], q[RU];
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
-      const int c = lane + 32 * i;
-      const float d = (c < D) ? (v[i] - mean) : 0.f;
-      q += d * d;
-    }
-    const float var = warp_sum(q) / (float)D;
-    const float rstd = rsqrtf(var + DV3_LN_EPS);
-    float* yr = y + (size_t)r * ldy;
+    for (int u = 0; u < RU; ++u) {
+      const long long r = r0 + u * nwarps;
+      const float* xr = x + (size_t)(r < rows ? r : r0) * ldx;
+      s[u] = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
-      const int c = lane + 32 * i;
-      if (c < D) {
-        const float n = (v[i] - mean) * rstd * gamma[c] + beta[c];
-        const float o = n * sigmoidf_(n);
-        yr[c] = o;
-        if (y16 != nullptr) y16[(size_t)r * ldy + c] = __float2bfloat16_rn(o);  // bf16 twin for the TMA-fed GEMM
+      for (int i = 0; i < kLnMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        v[u][i] = (c < D) ? xr[c] : 0.f;
+        s[u] += v[u][i];
       }
     }
-    if (lane == 0) {
-      if (mean_out) mean_out[r * sstride] = mean;
-      if (rstd_out) rstd_out[r * sstride] = rstd;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < RU; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      s[u] /= (float)D;   // mean
+      q[u] = 0.f;
+#pragma unroll
+      for (int i = 0; i < kLnMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        const float d = (c < D) ? (v[u][i] - s[u]) : 0.f;
+        q[u] += d * d;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < RU; ++u) q[u] += __shfl_xor_sync(0xffffffffu, q[u], o);
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const long long r = r0 + u * nwarps;
+      if (r >= rows) continue;
+      const float mean = s[u];
+      const float rstd = rsqrtf(q[u] / (float)D + DV3_LN_EPS);
+      float* yr = y + (size_t)r * ldy;
+#pragma unroll
+      for (int i = 0; i < kLnMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        if (c < D) {
+          const float n = (v[u][i] - mean) * rstd * gm[i] + bt[i];
+          const float o = n * sigmoidf_(n);
+          yr[c] = o;
+          if (y16 != nullptr) y16[(size_t)r * ldy + c] = __float2bfloat16_rn(o);  // bf16 twin for the TMA-fed GEMM
+        }
+      }
+      if (lane == 0) {
+        if (mean_out) mean_out[r * sstride] = mean;
+        if (rstd_out) rstd_out[r * sstride] = rstd;
+      }
     }
   }
 }
 
-template <int kLnMaxPerLane>
+template <int kLnMaxPerLane, int RU>
 __global__ void ln_silu_bwd_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
                                    const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -132,45 +163,80 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ dy, int lddy, const
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  float ag[kLnMaxPerLane], ab[kLnMaxPerLane];
+  float ag[kLnMaxPerLane], ab[kLnMaxPerLane], gm[kLnMaxPerLane], bt[kLnMaxPerLane];
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; ++i) ag[i] = ab[i] = 0.f;
-  for (long long r = warp0; r < rows; r += nwarps) {
-    const float* xr = x + (size_t)r * ldx;
-    const float* dyr = dy + (size_t)r * lddy;
-    const float mean = mean_in[r * sstride], rstd = rstd_in[r * sstride];
-    float xh[kLnMaxPerLane], dxh[kLnMaxPerLane];
-    float s1 = 0.f, s2 = 0.f;
+  for (int i = 0; i < kLnMaxPerLane; ++i) {
+    const int c = lane + 32 * i;
+    ag[i] = ab[i] = 0.f;
+    gm[i] = (c < D) ? gamma[c] : 0.f;
+    bt[i] = (c < D) ? beta[c] : 0.f;
+  }
+  for (long long r0 = warp0; r0 < rows; r0 += nwarps * RU) {
+    float xh[RU][kLnMaxPerLane], dxh[RU][kLnMaxPerLane], s1[RU], s2[RU], rs[RU];
+    // every load of the RU rows first
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
-      const int c = lane + 32 * i;
-      if (c < D) {
-        const float xhat = (xr[c] - mean) * rstd;
-        const float gm = gamma[c];
-        const float n = xhat * gm + beta[c];
-        const float sg = sigmoidf_(n);
-        const float dn = dyr[c] * (sg * (1.f + n * (1.f - sg)));
-        ag[i] += dn * xhat;
-        ab[i] += dn;
-        xh[i] = xhat;
-        dxh[i] = dn * gm;
-        s1 += dxh[i];
-        s2 += dxh[i] * xhat;
-      } else {
-        xh[i] = 0.f; dxh[i] = 0.f;
+    for (int u = 0; u < RU; ++u) {
+      const long long r = r0 + u * nwarps;
+      const bool rok = r < rows;
+      const long long rr = rok ? r : r0;
+      const float* xr = x + (size_t)rr * ldx;
+      const float* dyr = dy + (size_t)rr * lddy;
+      s1[u] = mean_in[rr * sstride];   // (mean, until the sums below)
+      rs[u] = rstd_in[rr * sstride];
+#pragma unroll
+      for (int i = 0; i < kLnMaxPerLane; ++i) {
+        const int c = lane + 32 * i;
+        xh[u][i] = (c < D) ? xr[c] : 0.f;
+        dxh[u][i] = (c < D && rok) ? dyr[c] : 0.f;
       }
     }
-    s1 = warp_sum(s1) / (float)D;
-    s2 = warp_sum(s2) / (float)D;
-    if (dx != nullptr) {
-      float* dxr = dx + (size_t)r * lddx;
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const float mean = s1[u];
+      float a1 = 0.f, a2 = 0.f;
 #pragma unroll
       for (int i = 0; i < kLnMaxPerLane; ++i) {
         const int c = lane + 32 * i;
         if (c < D) {
-          const float o = rstd * (dxh[i] - s1 - xh[i] * s2);
-          dxr[c] = o;
-          if (dx16 != nullptr) dx16[(size_t)r * lddx + c] = __float2bfloat16_rn(o);
+          const float xhat = (xh[u][i] - mean) * rs[u];
+          const float n = xhat * gm[i] + bt[i];
+          const float sg = sigmoidf_(n);
+          const float dn = dxh[u][i] * (sg * (1.f + n * (1.f - sg)));   // 0 for rows beyond the end (dy = 0)
+          ag[i] += dn * xhat;
+          ab[i] += dn;
+          xh[u][i] = xhat;
+          dxh[u][i] = dn * gm[i];
+          a1 += dxh[u][i];
+          a2 += dxh[u][i] * xhat;
+        } else {
+          xh[u][i] = 0.f; dxh[u][i] = 0.f;
+        }
+      }
+      s1[u] = a1; s2[u] = a2;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        s1[u] += __shfl_xor_sync(0xffffffffu, s1[u], o);
+        s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], o);
+      }
+    }
+    if (dx != nullptr) {
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const long long r = r0 + u * nwarps;
+        if (r >= rows) continue;
+        const float m1 = s1[u] / (float)D, m2 = s2[u] / (float)D;
+        float* dxr = dx + (size_t)r * lddx;
+#pragma unroll
+        for (int i = 0; i < kLnMaxPerLane; ++i) {
+          const int c = lane + 32 * i;
+          if (c < D) {
+            const float o = rs[u] * (dxh[u][i] - m1 - xh[u][i] * m2);
+            dxr[c] = o;
+            if (dx16 != nullptr) dx16[(size_t)r * lddx + c] = __float2bfloat16_rn(o);
+          }
         }
       }
     }
@@ -602,13 +668,13 @@ void ln_silu_fwd(cudaStream_t s, const float* x, int ldx, const float* gamma, co
     count_launch();
     return;
   }
-#define DV3_LN_FWD(E_) launch_pdl(ln_silu_fwd_kernel<E_>, dim3(grid), dim3(kThreads), 0, s, x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, D, y16)
-  if (D <= 32) DV3_LN_FWD(1);
-  else if (D <= 64) DV3_LN_FWD(2);
-  else if (D <= 128) DV3_LN_FWD(4);
-  else if (D <= 256) DV3_LN_FWD(8);
-  else if (D <= 512) DV3_LN_FWD(16);
-  else DV3_LN_FWD(32);
+#define DV3_LN_FWD(E_, RU_) launch_pdl(ln_silu_fwd_kernel<E_, RU_>, dim3(grid), dim3(kThreads), 0, s, x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, D, y16)
+  if (D <= 32) DV3_LN_FWD(1, 4);
+  else if (D <= 64) DV3_LN_FWD(2, 4);
+  else if (D <= 128) DV3_LN_FWD(4, 2);
+  else if (D <= 256) DV3_LN_FWD(8, 1);
+  else if (D <= 512) DV3_LN_FWD(16, 1);
+  else DV3_LN_FWD(32, 1);
 #undef DV3_LN_FWD
   count_launch();
 }
@@ -629,13 +695,13 @@ void ln_silu_bwd(cudaStream_t s, const float* dy, int lddy, const float* x, int 
     count_launch();
     return;
   }
-#define DV3_LN_BWD(E_) launch_pdl(ln_silu_bwd_kernel<E_>, dim3(grid), dim3(kThreads), 0, s, dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, D, dx16)
-  if (D <= 32) DV3_LN_BWD(1);
-  else if (D <= 64) DV3_LN_BWD(2);
-  else if (D <= 128) DV3_LN_BWD(4);
-  else if (D <= 256) DV3_LN_BWD(8);
-  else if (D <= 512) DV3_LN_BWD(16);
-  else DV3_LN_BWD(32);
+#define DV3_LN_BWD(E_, RU_) launch_pdl(ln_silu_bwd_kernel<E_, RU_>, dim3(grid), dim3(kThreads), 0, s, dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, D, dx16)
+  if (D <= 32) DV3_LN_BWD(1, 4);
+  else if (D <= 64) DV3_LN_BWD(2, 4);
+  else if (D <= 128) DV3_LN_BWD(4, 2);
+  else if (D <= 256) DV3_LN_BWD(8, 1);
+  else if (D <= 512) DV3_LN_BWD(16, 1);
+  else DV3_LN_BWD(32, 1);
 #undef DV3_LN_BWD
   count_launch();
 }
