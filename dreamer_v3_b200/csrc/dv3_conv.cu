@@ -14,34 +14,38 @@ namespace {
 
 __global__ void im2col_kernel(const float* __restrict__ img, float* __restrict__ cols, int n, int H, int W, int C,
                               __nv_bfloat16* __restrict__ cols16) {
+  // thread = one (pixel row, kernel tap): 32-bit index arithmetic (the host guarantees n*Ho*Wo*16 < 2^31), C contiguous
+  // channels copied per thread, so neighbouring threads write neighbouring runs of the patch row
   const int Ho = H / 2, Wo = W / 2;
-  const long long total = (long long)n * Ho * Wo * 16 * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    long long t = i / C;
-    const int kx = (int)(t % 4); t /= 4;
-    const int ky = (int)(t % 4); t /= 4;
-    const int ox = (int)(t % Wo); t /= Wo;
-    const int oy = (int)(t % Ho); t /= Ho;
-    const int b = (int)t;
-    const int y = 2 * oy - 1 + ky, x = 2 * ox - 1 + kx;
-    float v = 0.f;
-    if (y >= 0 && y < H && x >= 0 && x < W) v = img[(((size_t)b * H + y) * W + x) * C + c];
-    cols[i] = v;
-    if (cols16 != nullptr) cols16[i] = __float2bfloat16_rn(v);
+  const unsigned total = (unsigned)n * Ho * Wo * 16;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned kx = i & 3, ky = (i >> 2) & 3;
+    unsigned t = i >> 4;
+    const unsigned ox = t % Wo; t /= Wo;
+    const unsigned oy = t % Ho;
+    const unsigned b = t / Ho;
+    const int y = 2 * (int)oy - 1 + (int)ky, x = 2 * (int)ox - 1 + (int)kx;
+    const bool in = y >= 0 && y < H && x >= 0 && x < W;
+    const float* src = img + (((size_t)b * H + (in ? y : 0)) * W + (in ? x : 0)) * C;
+    float* dst = cols + (size_t)i * C;
+    for (int c = 0; c < C; ++c) {
+      const float v = in ? src[c] : 0.f;
+      dst[c] = v;
+      if (cols16 != nullptr) cols16[(size_t)i * C + c] = __float2bfloat16_rn(v);
+    }
   }
 }
 
 __global__ void col2im_kernel(const float* __restrict__ cols, float* __restrict__ img, int n, int H, int W, int C,
                               const float* __restrict__ bias, float add_const) {
   const int Ho = H / 2, Wo = W / 2;
-  const long long total = (long long)n * H * W * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    long long t = i / C;
-    const int x = (int)(t % W); t /= W;
-    const int y = (int)(t % H); t /= H;
-    const int b = (int)t;
+  const unsigned total = (unsigned)n * H * W * C;   // 32-bit index arithmetic (12.6 M elements at B16 x T64 x 64 x 64 x 3)
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = (int)(i % (unsigned)C);
+    unsigned t = i / (unsigned)C;
+    const int x = (int)(t % (unsigned)W); t /= (unsigned)W;
+    const int y = (int)(t % (unsigned)H);
+    const int b = (int)(t / (unsigned)H);
     float acc = add_const + (bias != nullptr ? bias[c] : 0.f);
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky) {
@@ -131,9 +135,9 @@ void im2col_k4s2(cudaStream_t s, const float* img, float* cols, int n, int H, in
   if (C % 4 == 0 && ((uintptr_t)img % 16 == 0) && ((uintptr_t)cols % 16 == 0) && ((uintptr_t)cols16 % 8 == 0))
     im2col_v4_kernel<<<grid_for((long long)n * (H / 2) * (W / 2) * 16 * (C / 4)), 256, 0, s>>>(
         reinterpret_cast<const float4*>(img), reinterpret_cast<float4*>(cols), n, H, W, C / 4, reinterpret_cast<uint2*>(cols16));
-  else
-    im2col_kernel<<<grid_for((long long)n * (H / 2) * (W / 2) * 16 * C), 256, 0, s>>>(img, cols, n, H, W, C,
-                                                                                       reinterpret_cast<__nv_bfloat16*>(cols16));
+  else   // (n * Ho * Wo * 16 < 2^31 for every configuration: 16 M at B16 x T64 x 64 x 64 inputs)
+    im2col_kernel<<<grid_for((long long)n * (H / 2) * (W / 2) * 16), 256, 0, s>>>(img, cols, n, H, W, C,
+                                                                                   reinterpret_cast<__nv_bfloat16*>(cols16));
   count_launch();
 }
 void col2im_k4s2(cudaStream_t s, const float* cols, float* img, int n, int H, int W, int C, const float* bias,
