@@ -660,10 +660,13 @@ void ln_silu_fwd(cudaStream_t s, const float* x, int ldx, const float* gamma, co
   if (rows <= 0) return;
   const int grid = grid_for(rows, kThreads / 32, 148 * 8);
   __nv_bfloat16* y16 = reinterpret_cast<__nv_bfloat16*>(y16_);
-  if ((D == 256 || D == 512 || D == 1024) && ldx % 4 == 0 && ldy % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0 &&
+  if (D % 128 == 0 && D <= 1024 && ldx % 4 == 0 && ldy % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0 &&
       (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0 && (uintptr_t)y16_ % 8 == 0) {
 #define DV3_LN_FWD4(V_) launch_pdl(ln_silu_fwd_v4_kernel<V_>, dim3(grid), dim3(kThreads), 0, s, x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, y16)
-    if (D == 256) DV3_LN_FWD4(2); else if (D == 512) DV3_LN_FWD4(4); else DV3_LN_FWD4(8);
+    switch (D / 128) {   // every width that is a multiple of 128 (dense 256 / 512 / 640 / 768 / 1024, wide conv channels)
+      case 1: DV3_LN_FWD4(1); break; case 2: DV3_LN_FWD4(2); break; case 3: DV3_LN_FWD4(3); break; case 4: DV3_LN_FWD4(4); break;
+      case 5: DV3_LN_FWD4(5); break; case 6: DV3_LN_FWD4(6); break; case 7: DV3_LN_FWD4(7); break; default: DV3_LN_FWD4(8); break;
+    }
 #undef DV3_LN_FWD4
     count_launch();
     return;
@@ -684,13 +687,16 @@ void ln_silu_bwd(cudaStream_t s, const float* dy, int lddy, const float* x, int 
   if (rows <= 0) return;
   const int grid = grid_for(rows, kThreads / 32, 148 * 4);
   __nv_bfloat16* dx16 = reinterpret_cast<__nv_bfloat16*>(dx16_);
-  if ((D == 256 || D == 512 || D == 1024) && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)dy % 16 == 0 &&
+  if (D % 128 == 0 && D <= 1024 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)dy % 16 == 0 &&
       (uintptr_t)dx % 16 == 0 && (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0 && (uintptr_t)dx16_ % 8 == 0) {
     // with gain / offset gradients every block ends with 2 D global atomics: fewer, longer blocks (measured at 16384 x 256:
     // 17.4 / 13.1 / 18.5 / 19.7 us for 1 / 2 / 4 / 8 blocks per SM)
     const int grid4 = grid_for(rows, kThreads / 32, dgamma != nullptr ? 148 * 2 : 148 * 8);
 #define DV3_LN_BWD4(V_) launch_pdl(ln_silu_bwd_v4_kernel<V_>, dim3(grid4), dim3(kThreads), 0, s, dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, dx16)
-    if (D == 256) DV3_LN_BWD4(2); else if (D == 512) DV3_LN_BWD4(4); else DV3_LN_BWD4(8);
+    switch (D / 128) {
+      case 1: DV3_LN_BWD4(1); break; case 2: DV3_LN_BWD4(2); break; case 3: DV3_LN_BWD4(3); break; case 4: DV3_LN_BWD4(4); break;
+      case 5: DV3_LN_BWD4(5); break; case 6: DV3_LN_BWD4(6); break; case 7: DV3_LN_BWD4(7); break; default: DV3_LN_BWD4(8); break;
+    }
 #undef DV3_LN_BWD4
     count_launch();
     return;
