@@ -271,6 +271,23 @@ def run_case(name, kw, seed, dtype):
             for k, v in bd.items():
                 out[pre + k] = v.numpy().astype(np.int32) if "ints" in k else npf(v)
             out[pre + "z_indices_t1_to_H_B"] = bd["z_states_prior_t0_to_H_B"].numpy()[1:].argmax(-1).astype(np.int32)
+        # ---- DreamerModel.forward_inference (dreamer_model.py:113-128), the acting step of env_runner_v2.py:274-282, on
+        # the same weights: previous states taken from the last observe pass, a mixed is_first vector ----
+        fwd = r_wm["WORLD_MODEL_forward_train_outs"]
+        rows = np.arange(cfg.B) * cfg.T + 1          # (b, t=1) of the folded B x T rows
+        prev = {"h": tf.convert_to_tensor(fwd["h_states_BxT"].numpy()[rows], dtype=dtype),
+                "z": tf.convert_to_tensor(fwd["z_states_BxT"].numpy()[rows], dtype=dtype),
+                "a": sample["actions"][:, 1]}
+        first = tf.convert_to_tensor(np.array([1.0] + [0.0] * (cfg.B - 1)), dtype=dtype)
+        tfp.DRAW_LOG.clear()
+        act, st = dm.forward_inference(prev, sample["obs"][:, 2], first)
+        log = list(tfp.DRAW_LOG)
+        assert len(log) == 3 and log[0][1].shape == (1, Zc)   # initial-state draw (discarded), posterior z, action
+        out["infer/noise/u_z"], out["infer/noise/act"] = log[1][1], log[2][1]
+        out["infer/prev_h"], out["infer/prev_z"], out["infer/prev_a"] = npf(prev["h"]), npf(prev["z"]), npf(prev["a"])
+        out["infer/obs"], out["infer/is_first"] = npf(sample["obs"][:, 2]), npf(first)
+        out["infer/h"], out["infer/a"] = npf(st["h"]), npf(act)
+        out["infer/z_indices"] = st["z"].numpy().argmax(-1).astype(np.int32)
     finally:
         tf.clip_by_global_norm = real_clip
     return out

@@ -238,3 +238,41 @@ def test_cuda_burn_in_dream_matches_reference_code(case, mode):
             assert rel(out[k].cpu().numpy(), g[k]) <= 1e-4, k
     finally:
         e.close()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_acting_step_matches_reference_code(case):
+    """DreamerModel.forward_inference (dreamer_model.py:113-128 -> world_model.py:141-180 + actor) on the fixture's
+    twice-updated weights, with a mixed is_first vector."""
+    z, cfg = load(case, "f64")
+    g = group(z, "infer/")
+    o = Oracle(cfg, group(z, "s2/param/"), dtype=torch.float64)
+    out = o.forward_inference(g["prev_h"], g["prev_z"], g["prev_a"], g["obs"], g["is_first"], u_z=g["noise/u_z"],
+                              act_noise=g["noise/act"])
+    assert (out["z_idx"] != g["z_indices"]).sum() == 0
+    assert rel(tnp(out["h"]), g["h"]) <= 1e-9
+    assert rel(tnp(out["a"]), g["a"]) <= 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_cuda_acting_step_matches_reference_code(case):
+    from dreamer_v3_b200.engine import Engine
+    z, cfg = load(case, "f32")
+    g = group(z, "infer/")
+    e = Engine(cfg)
+    try:
+        e.load_params(group(z, "s2/param/"))
+        rows = cfg.B
+        for name, key in (("inf.prev_h", "prev_h"), ("inf.prev_z", "prev_z"), ("inf.prev_a", "prev_a"), ("inf.obs", "obs"),
+                          ("inf.is_first", "is_first"), ("inf.u_z", "noise/u_z"), ("inf.act_noise", "noise/act")):
+            dst = e.tensor(name)
+            dst.copy_(torch.as_tensor(g[key], dtype=torch.float32).reshape(dst.shape))
+        e.forward_inference(rows, 0)
+        hz = e.tensor("inf.hz").cpu().numpy()
+        assert (e.tensor("inf.z_indices").cpu().numpy() != g["z_indices"]).sum() == 0
+        assert rel(hz[:, :cfg.G], g["h"]) <= 1e-4
+        assert rel(e.tensor("inf.a").cpu().numpy(), g["a"]) <= 1e-4
+        assert (hz[:, cfg.G:].reshape(rows, cfg.Zc, cfg.Zk).argmax(-1) != g["z_indices"]).sum() == 0
+    finally:
+        e.close()
