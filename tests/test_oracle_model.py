@@ -123,3 +123,69 @@ def test_oracle_reproduces_golden_fixture():
             want = g[k]
             got = res["grads"][k[len("grad/"):]].numpy()
             assert np.abs(got - want).max() <= 2e-4 * np.abs(want).max() + 1e-12, k
+
+
+def test_gru_step_against_torch_grucell():
+    """Independent check of the restated Keras GRU step (reset_after=True, gate order z, r, h): the same
+    weights permuted into torch.nn.GRUCell's (r, z, n) layout must give the same h'."""
+    import numpy as np
+    import torch
+    from dreamer_v3_b200.spec import EngineConfig, init_params
+    from oracle.dreamer_oracle import Oracle
+    cfg = EngineConfig.make("XXS", A=3, discrete=True, B=4, T=4, H=2)
+    o = Oracle(cfg, init_params(cfg, seed=5, mode="random"), dtype=torch.float64)
+    G, D = cfg.G, cfg.D
+    rng = np.random.default_rng(0)
+    z = torch.as_tensor(np.eye(cfg.Zk)[rng.integers(0, cfg.Zk, size=(5, cfg.Zc))])
+    a = torch.as_tensor(np.eye(cfg.A)[rng.integers(0, cfg.A, size=5)])
+    h = torch.as_tensor(rng.standard_normal((5, G)))
+    got = o.sequence_model(z, a, h)
+    u = o.mlp("seq.pre", torch.cat([z.reshape(5, -1), a], -1), 1)   # input of the GRU
+    K, U, b = (o.P[k].detach() for k in ("seq.gru.kernel", "seq.gru.recurrent", "seq.gru.bias"))
+    perm = lambda w: torch.cat([w[..., G:2 * G], w[..., :G], w[..., 2 * G:]], -1)   # (z, r, h) -> (r, z, n)  # noqa: E731
+    cell = torch.nn.GRUCell(D, G, dtype=torch.float64)
+    with torch.no_grad():
+        cell.weight_ih.copy_(perm(K).T)
+        cell.weight_hh.copy_(perm(U).T)
+        cell.bias_ih.copy_(perm(b[0]))
+        cell.bias_hh.copy_(perm(b[1]))
+    want = cell(u.detach(), h)
+    assert float((got - want).abs().max()) < 1e-12
+
+
+def test_conv_layouts_against_tf_documented_semantics():
+    """The oracle runs the Keras convolutions through torch ops on permuted kernels; this restates TensorFlow's documented
+    definitions directly (explicit loops) to pin the layout / padding / no-flip conventions:
+      Conv2D(k=4, s=2, 'same') on an even size: pad_total = (ceil(n/2) - 1) * 2 + 4 - n = 2, one pixel on each side;
+          y[oy, ox, co] = sum x[2 oy - 1 + ky, 2 ox - 1 + kx, ci] * w[ky, kx, ci, co]
+      Conv2DTranspose(k=4, s=2, 'same') = the gradient of that convolution w.r.t. its input, kernel [kh, kw, out, in]:
+          y[2 iy - 1 + ky, 2 ix - 1 + kx, co] += x[iy, ix, ci] * w[ky, kx, co, ci]"""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(1)
+    n, ci, co = 6, 3, 2
+    x = rng.standard_normal((1, n, n, ci))
+    w = rng.standard_normal((4, 4, ci, co))
+    want = np.zeros((1, n // 2, n // 2, co))
+    for oy in range(n // 2):
+        for ox in range(n // 2):
+            for ky in range(4):
+                for kx in range(4):
+                    y_, x_ = 2 * oy - 1 + ky, 2 * ox - 1 + kx
+                    if 0 <= y_ < n and 0 <= x_ < n:
+                        want[0, oy, ox] += x[0, y_, x_] @ w[ky, kx]
+    got = F.conv2d(torch.as_tensor(x).permute(0, 3, 1, 2), torch.as_tensor(w).permute(3, 2, 0, 1), stride=2, padding=1)
+    assert np.abs(got.permute(0, 2, 3, 1).numpy() - want).max() < 1e-12      # the call Oracle.encoder makes
+    wt = rng.standard_normal((4, 4, co, ci))    # Keras Conv2DTranspose kernel [kh, kw, out_ch, in_ch]
+    xin = rng.standard_normal((1, 3, 3, ci))
+    want_t = np.zeros((1, 6, 6, co))
+    for iy in range(3):
+        for ix in range(3):
+            for ky in range(4):
+                for kx in range(4):
+                    y_, x_ = 2 * iy - 1 + ky, 2 * ix - 1 + kx
+                    if 0 <= y_ < 6 and 0 <= x_ < 6:
+                        want_t[0, y_, x_] += wt[ky, kx] @ xin[0, iy, ix]
+    got_t = F.conv_transpose2d(torch.as_tensor(xin).permute(0, 3, 1, 2), torch.as_tensor(wt).permute(3, 2, 0, 1), stride=2, padding=1)
+    assert np.abs(got_t.permute(0, 2, 3, 1).numpy() - want_t).max() < 1e-12  # the call Oracle.decoder makes
