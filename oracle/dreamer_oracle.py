@@ -67,6 +67,11 @@ class Oracle:
         self.th_float = np.float32
 
     # ------------------------------------------------------------------ groups
+    def set_forced(self, forced):
+        """See `_draw`. forced: dict noise-key -> per-call index arrays (+ "continues": [(H+1)*N] flags), or None."""
+        self.forced = forced
+        self._forced_calls, self.forced_violation, self.forced_flips = {}, {}, {}
+
     def group_names(self, group):
         def grp(n):
             if n.startswith("actor."):
@@ -96,8 +101,29 @@ class Oracle:
         return x @ self.P[f"{prefix}.w"] + self.P[f"{prefix}.bias"]
 
     def _draw(self, probs, u, key, rng, margin):
-        """Categorical draw with explicit (or recorded, margin-safe) uniforms."""
+        """Categorical draw with explicit (or recorded, margin-safe) uniforms.
+
+        Forced mode (`self.forced[key]` = list of index arrays, one per call): the draw is *given* (the indices a
+        reduced-precision device run sampled from the same uniforms) and what is recorded instead is how far each
+        uniform lies outside the CDF bucket of its forced index under THIS oracle's probabilities
+        (`self.forced_violation[key]`, 0 when the oracle would have drawn the same index). Tests of the bf16 path bound
+        that distance, so a flipped draw is checked instead of waived and every downstream tensor stays comparable."""
         p_np = probs.detach().to(torch.float32).numpy()
+        forced = getattr(self, "forced", None)
+        if forced is not None and key in forced:
+            n_call = self._forced_calls.get(key, 0)
+            self._forced_calls[key] = n_call + 1
+            idx = np.asarray(forced[key][n_call]).astype(np.int64).reshape(p_np.shape[:-1])
+            cdf = np.cumsum(p_np.astype(np.float64), axis=-1)
+            cdf = cdf / cdf[..., -1:]
+            hi = np.take_along_axis(cdf, idx[..., None], -1)[..., 0]
+            lo = np.where(idx > 0, np.take_along_axis(cdf, np.maximum(idx - 1, 0)[..., None], -1)[..., 0], 0.0)
+            uu = np.asarray(u, dtype=np.float64).reshape(idx.shape)
+            viol = np.maximum(np.maximum(lo - uu, uu - hi), 0.0)
+            viol = np.where(idx == p_np.shape[-1] - 1, np.maximum(lo - uu, 0.0), viol)  # last bucket is open above
+            self.forced_violation[key] = max(self.forced_violation.get(key, 0.0), float(viol.max()) if viol.size else 0.0)
+            self.forced_flips[key] = self.forced_flips.get(key, 0) + int((nx.sample_categorical(p_np, np.asarray(u, dtype=np.float32)) != idx).sum())
+            return idx
         if u is None:
             assert rng is not None, f"noise {key!r} missing and no rng given"
             u = rng.random(p_np.shape[:-1], dtype=np.float32)
@@ -397,7 +423,14 @@ class Oracle:
         a_HB = torch.stack(acts, 0)
         r_sym, _ = self.reward_predictor(hz)
         r_HB = inverse_symlog(r_sym).reshape(H + 1, N)  # :219-224
-        c, _ = self.continue_predictor(hz)
+        c, c_logit = self.continue_predictor(hz)
+        forced = getattr(self, "forced", None)
+        if forced is not None and "continues" in forced:  # Bernoulli mode 1[logit > 0] given; record |logit| where it differs
+            cf = _t(np.asarray(forced["continues"]).reshape(-1), dt)
+            diff = (cf != c.reshape(-1))
+            self.forced_violation["continues"] = float(c_logit.detach().reshape(-1)[diff].abs().max()) if bool(diff.any()) else 0.0
+            self.forced_flips["continues"] = int(diff.sum())
+            c = cf
         c_HB = c.reshape(H + 1, N)
         c_HB = torch.cat([1.0 - _t(start_is_terminated, dt).reshape(1, N), c_HB[1:]], 0)  # :252-255
         w_HB = torch.cumprod(gamma * c_HB, dim=0) / gamma  # :261

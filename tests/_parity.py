@@ -98,7 +98,7 @@ class ParityRun:
     """One oracle-vs-engine comparison of a full train update (world model + actor/critic)."""
 
     def __init__(self, cfg: EngineConfig, seed=0, init_mode="random", oracle_dtype=torch.float64, compute_mode=0,
-                 margin=1e-3, steps=1, sync_grads=True, sample_fn=None, fixture=None):
+                 margin=1e-3, steps=1, sync_grads=True, sample_fn=None, fixture=None, forced=False):
         self.cfg = cfg
         self.report = {}      # name -> rel err (float tensors)
         self.exact = {}       # name -> number of mismatching integers
@@ -116,6 +116,11 @@ class ParityRun:
         self.engine.load_params(self.params0)
         self.margin = margin
         self.sync_grads = sync_grads
+        # forced = True (reduced-precision device modes): the device run goes first on plain uniforms, the oracle is then
+        # given the indices the device drew (Oracle._draw, forced mode) and records how far each uniform lies outside the
+        # oracle's own CDF bucket; every tensor stays comparable and the flips are bounded by the caller instead of waived
+        self.forced = forced
+        self.forced_violation, self.forced_flips = {}, {}
         for _ in range(steps):
             self.step()
 
@@ -142,8 +147,18 @@ class ParityRun:
         B, T, N, H, G = cfg.B, cfg.T, cfg.N, cfg.H, cfg.G
         self.prev_params = o.numpy_params()
         # ---------------- world model ----------------
-        res = o.train_world_model_one_step(self.sample, rng=self.rng, margin=self.margin)
-        u_post = o.last_noise["u_post"]
+        if self.forced:
+            u_post = self.rng.random((T, B, cfg.Zc), dtype=np.float32)
+            e.set_sample(self.sample)
+            e.set_noise(u_post=u_post)
+            e.observe_forward()
+            zi = e.tensor("wm.z_indices").cpu().numpy().reshape(B, T, cfg.Zc)
+            o.set_forced({"u_post": [zi[:, tt] for tt in range(T)]})
+            res = o.train_world_model_one_step(self.sample, u_post=u_post)
+            self._collect_forced()
+        else:
+            res = o.train_world_model_one_step(self.sample, rng=self.rng, margin=self.margin)
+            u_post = o.last_noise["u_post"]
         fwd = res["WORLD_MODEL_forward_train_outs"]
         e.set_sample(self.sample)
         e.set_noise(u_post=u_post)
@@ -181,10 +196,29 @@ class ParityRun:
             if self.sync_grads:
                 self.cmp_delta("adam_delta." + n, t(n), before[n], op[n], self.prev_params[n])
         # ---------------- actor / critic ----------------
-        ac = o.train_actor_and_critic_one_step(fwd["h_states_BxT"], fwd["z_states_BxT"], self.sample["is_terminated"],
-                                               H=H, rng=self.rng, margin=self.margin)
+        if self.forced:
+            u_dyn = self.rng.random((H, N, cfg.Zc), dtype=np.float32)
+            act_noise = (self.rng.random((H + 1, N), dtype=np.float32) if cfg.discrete
+                         else self.rng.standard_normal((H + 1, N, cfg.A)).astype(np.float32))
+            e.set_noise(u_dyn=u_dyn, act_noise=act_noise)
+            e.write("in.dream_h0", fwd["h_states_BxT"].to(torch.float32))
+            e.write("in.dream_z0", fwd["z_states_BxT"].reshape(N, -1).to(torch.float32))
+            e.dream_forward(start_from_observe=False)
+            zi = e.tensor("dream.z_indices").cpu().numpy().reshape(H, N, cfg.Zc)
+            forced = {"u_dyn": list(zi), "continues": e.tensor("dream.continues").cpu().numpy().reshape(-1)}
+            if cfg.discrete:
+                forced["u_act"] = list(e.tensor("dream.action_indices").cpu().numpy().reshape(H + 1, N))
+            o.set_forced(forced)
+            ac = o.train_actor_and_critic_one_step(fwd["h_states_BxT"], fwd["z_states_BxT"], self.sample["is_terminated"],
+                                                   H=H, u_dyn=u_dyn, act_noise=act_noise)
+            self._collect_forced()
+            o.set_forced(None)
+        else:
+            ac = o.train_actor_and_critic_one_step(fwd["h_states_BxT"], fwd["z_states_BxT"], self.sample["is_terminated"],
+                                                   H=H, rng=self.rng, margin=self.margin)
+            u_dyn, act_noise = o.last_noise["u_dyn"], o.last_noise["u_act" if cfg.discrete else "eps_act"]
         dream = ac["dream_data"]
-        e.set_noise(u_dyn=o.last_noise["u_dyn"], act_noise=o.last_noise["u_act" if cfg.discrete else "eps_act"])
+        e.set_noise(u_dyn=u_dyn, act_noise=act_noise)
         # the oracle dreams from its own (pre-update) h/z; feed exactly those to the engine
         e.write("in.dream_h0", fwd["h_states_BxT"].to(torch.float32))
         e.write("in.dream_z0", fwd["z_states_BxT"].reshape(N, -1).to(torch.float32))
@@ -229,6 +263,13 @@ class ParityRun:
                 if self.sync_grads and grp != "critic_ema":
                     self.cmp_delta("adam_delta." + n, t(n), before[n], op[n], self.prev_params[n])
         torch.cuda.synchronize()
+
+    def _collect_forced(self):
+        o = self.oracle
+        for k, v in o.forced_violation.items():
+            self.forced_violation[k] = max(self.forced_violation.get(k, 0.0), v)
+        for k, v in o.forced_flips.items():
+            self.forced_flips[k] = self.forced_flips.get(k, 0) + v
 
     def worst(self, k=12):
         return sorted(self.report.items(), key=lambda kv: -kv[1])[:k]

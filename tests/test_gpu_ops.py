@@ -136,3 +136,28 @@ def test_weight_streaming_contraction_of_the_scan_rows(M, N, K, tb, beta, with_b
     got = ops.gemm(A, B, tb=tb, bias=bias, C_=C0.clone(), beta=beta, mode=mode)
     err = float((got.double() - want).abs().max() / want.abs().max())
     assert err < 2e-6, err
+
+
+@pytest.mark.parametrize("D", (24, 32, 48, 96, 192, 256, 384, 512, 640, 768, 1024))
+@pytest.mark.parametrize("rows", (16, 300, 4099))
+def test_ln_silu_bwd_isolated(D, rows):
+    """Backward of Dense -> LayerNorm(eps 1e-3) -> SiLU (components/mlp.py:69-84) in isolation at every layer width of the
+    size table (dense 256...1024) and the conv channel counts (24...768): dx, dgamma, dbeta against torch autograd in fp64."""
+    from dreamer_v3_b200 import ops
+    rng = np.random.default_rng(D * 31 + rows)
+    x = (rng.standard_normal((rows, D)) * 2 + 0.5).astype(np.float32)
+    dy = rng.standard_normal((rows, D)).astype(np.float32)
+    g = (1 + 0.1 * rng.standard_normal(D)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(D)).astype(np.float32)
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    gt = torch.from_numpy(g).double().requires_grad_(True)
+    bt = torch.from_numpy(b).double().requires_grad_(True)
+    y = torch.nn.functional.silu(torch.nn.functional.layer_norm(xt, (D,), gt, bt, 1e-3))
+    y.backward(torch.from_numpy(dy).double())
+    dg = torch.zeros(D, device="cuda")
+    db = torch.zeros(D, device="cuda")
+    dx = ops.ln_silu_bwd(dev(dy), dev(x), dev(g), dev(b), dg, db)()
+    torch.cuda.synchronize()
+    for name, got, want in (("dx", dx, xt.grad), ("dgamma", dg, gt.grad), ("dbeta", db, bt.grad)):
+        err = float((got.cpu().double() - want).abs().max() / (want.abs().max() + 1e-30))
+        assert err < 1e-4, (name, err)

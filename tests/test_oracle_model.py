@@ -189,3 +189,42 @@ def test_conv_layouts_against_tf_documented_semantics():
                         want_t[0, y_, x_] += wt[ky, kx] @ xin[0, iy, ix]
     got_t = F.conv_transpose2d(torch.as_tensor(xin).permute(0, 3, 1, 2), torch.as_tensor(wt).permute(3, 2, 0, 1), stride=2, padding=1)
     assert np.abs(got_t.permute(0, 2, 3, 1).numpy() - want_t).max() < 1e-12  # the call Oracle.decoder makes
+
+
+def test_forced_draws_reproduce_free_draws():
+    """Oracle._draw forced mode (used by the bf16 GPU parity tests): forcing the indices the oracle itself drew from the same
+    uniforms reproduces the run bit for bit with zero CDF violation and zero flips; forcing a shifted index is reported."""
+    import numpy as np
+    import torch
+    from dreamer_v3_b200.spec import EngineConfig, init_params
+    from oracle.dreamer_oracle import Oracle, make_synthetic_sample
+    cfg = EngineConfig.make("nano", A=3, discrete=True, B=3, T=4, H=3)
+    p = init_params(cfg, seed=1, mode="random")
+    s = make_synthetic_sample(cfg, seed=2)
+    o1 = Oracle(cfg, p, dtype=torch.float64)
+    r1 = o1.train_world_model_one_step(s, rng=np.random.default_rng(0), apply=False)
+    u_post = o1.last_noise["u_post"]
+    f1 = r1["WORLD_MODEL_forward_train_outs"]
+    a1 = o1.train_actor_and_critic_one_step(f1["h_states_BxT"], f1["z_states_BxT"], s["is_terminated"], H=cfg.H,
+                                            rng=np.random.default_rng(1), apply=False)
+    u_dyn, u_act = o1.last_noise["u_dyn"], o1.last_noise["u_act"]
+    d1 = a1["dream_data"]
+    o2 = Oracle(cfg, p, dtype=torch.float64)
+    zi = f1["z_indices_BxT"].reshape(cfg.B, cfg.T, cfg.Zc)
+    o2.set_forced({"u_post": [zi[:, t] for t in range(cfg.T)]})
+    r2 = o2.train_world_model_one_step(s, u_post=u_post, apply=False)
+    assert o2.forced_violation == {"u_post": 0.0} and o2.forced_flips == {"u_post": 0}
+    assert float(r2["WORLD_MODEL_L_total"]) == float(r1["WORLD_MODEL_L_total"])
+    o2.set_forced({"u_dyn": list(d1["z_indices_t1_to_H_B"]), "u_act": list(d1["actions_ints_dreamed_t0_to_H_B"].numpy()),
+                   "continues": d1["continues_dreamed_t0_to_H_B"].numpy()[0:].reshape(-1) * 0 + (
+                       o1.continue_predictor(torch.cat([d1["h_states_t0_to_H_B"].reshape(-1, cfg.G), d1["z_states_prior_t0_to_H_B"].reshape(-1, cfg.Z)], -1))[0].numpy())})
+    a2 = o2.train_actor_and_critic_one_step(f1["h_states_BxT"], f1["z_states_BxT"], s["is_terminated"], H=cfg.H,
+                                            u_dyn=u_dyn, act_noise=u_act, apply=False)
+    assert all(v == 0.0 for v in o2.forced_violation.values()), o2.forced_violation
+    assert all(v == 0 for v in o2.forced_flips.values()), o2.forced_flips
+    assert float(a2["ACTOR_L_total"]) == float(a1["ACTOR_L_total"]) and float(a2["CRITIC_L_total"]) == float(a1["CRITIC_L_total"])
+    # a wrong forced index is measured, not hidden
+    o3 = Oracle(cfg, p, dtype=torch.float64)
+    o3.set_forced({"u_post": [(zi[:, t] + 1) % cfg.Zk for t in range(cfg.T)]})
+    o3.train_world_model_one_step(s, u_post=u_post, apply=False)
+    assert o3.forced_flips["u_post"] >= cfg.B * cfg.Zc and o3.forced_violation["u_post"] > 0.0  # at least the whole first step
