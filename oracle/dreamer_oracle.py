@@ -426,7 +426,8 @@ class Oracle:
         c, c_logit = self.continue_predictor(hz)
         forced = getattr(self, "forced", None)
         if forced is not None and "continues" in forced:  # Bernoulli mode 1[logit > 0] given; record |logit| where it differs
-            cf = _t(np.asarray(forced["continues"]).reshape(-1), dt)
+            cf = _t(np.asarray(forced["continues"]).reshape(-1), dt).clone()
+            cf[:N] = c.reshape(-1)[:N]  # step 0 is replaced by 1 - start_is_terminated below (:252-255), not a prediction
             diff = (cf != c.reshape(-1))
             self.forced_violation["continues"] = float(c_logit.detach().reshape(-1)[diff].abs().max()) if bool(diff.any()) else 0.0
             self.forced_flips["continues"] = int(diff.sum())

@@ -160,9 +160,10 @@ class ParityRun:
             res = o.train_world_model_one_step(self.sample, rng=self.rng, margin=self.margin)
             u_post = o.last_noise["u_post"]
         fwd = res["WORLD_MODEL_forward_train_outs"]
-        e.set_sample(self.sample)
-        e.set_noise(u_post=u_post)
-        e.observe_forward()
+        if not self.forced:  # (forced: the device pass above is the one compared - split-K atomics make a rerun differ in the last ulp)
+            e.set_sample(self.sample)
+            e.set_noise(u_post=u_post)
+            e.observe_forward()
         t = e.tensor
         if "encoder_out_TB" in fwd:  # not part of forward_train's result dict (absent from reference fixtures)
             self.cmp("wm.enc_out", t("wm.enc_out"), fwd["encoder_out_TB"].transpose(0, 1).reshape(N, -1))
@@ -218,11 +219,12 @@ class ParityRun:
                                                    H=H, rng=self.rng, margin=self.margin)
             u_dyn, act_noise = o.last_noise["u_dyn"], o.last_noise["u_act" if cfg.discrete else "eps_act"]
         dream = ac["dream_data"]
-        e.set_noise(u_dyn=u_dyn, act_noise=act_noise)
-        # the oracle dreams from its own (pre-update) h/z; feed exactly those to the engine
-        e.write("in.dream_h0", fwd["h_states_BxT"].to(torch.float32))
-        e.write("in.dream_z0", fwd["z_states_BxT"].reshape(N, -1).to(torch.float32))
-        e.dream_forward(start_from_observe=False)
+        if not self.forced:
+            e.set_noise(u_dyn=u_dyn, act_noise=act_noise)
+            # the oracle dreams from its own (pre-update) h/z; feed exactly those to the engine
+            e.write("in.dream_h0", fwd["h_states_BxT"].to(torch.float32))
+            e.write("in.dream_z0", fwd["z_states_BxT"].reshape(N, -1).to(torch.float32))
+            e.dream_forward(start_from_observe=False)
         dhz = t("dream.hz")
         self.cmp("dream.h_states", dhz[..., :G], dream["h_states_t0_to_H_B"])
         self.cmp_exact("dream.z_indices", t("dream.z_indices"), dream["z_indices_t1_to_H_B"])
