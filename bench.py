@@ -41,14 +41,51 @@ WORKLOADS = {
     "L": dict(name="size L / Discrete(18) / 64x64x3", size="L", A=18, discrete=True, image_obs=True),
     "c5": dict(name="size XL / Discrete(18) / 64x64x3", size="XL", A=18, discrete=True, image_obs=True),
 }
-# algorithmic GFLOP per update
-GFLOP_PER_UPDATE = {"c1": 150.0, "c2": 235.0, "c3": 827.0, "c4": 2319.0, "L": 3506.0, "c5": 8756.0}
+def algorithmic_gflop(cfg):
+    """Algorithmic GFLOP of one train update derived from the layer shapes of `cfg` (SURVEY.md 8d rules: FLOP = 2 MAC;
+    backward = 2x forward where a weight gradient is needed, 1x where only the input gradient is needed; the Discrete actor
+    has no BPTT through the dream, the Box actor has). Reproduces the SURVEY table (150 / 235 / 827 / 2319 / 3506 / 8756)."""
+    G, D, L, Z, A, E, m = cfg.G, cfg.D, cfg.L, cfg.Z, cfg.A, cfg.E, cfg.cnn_mult
+    N, H = cfg.N, cfg.H
+    R = (H + 1) * N
+    mlp = lambda k: k * D + (L - 1) * D * D          # noqa: E731  MACs per row of an L-layer MLP on k inputs
+    if cfg.image_obs:
+        enc, cin, side = 0, cfg.img_c, cfg.img_hw
+        for l in range(4):
+            cout, side = m << l, side // 2
+            enc += side * side * 16 * cin * cout
+            cin = cout
+        dec, cin, side = (G + Z) * E, 8 * m, 4
+        for l in range(3):
+            dec += side * side * 16 * cin * (cin // 2)
+            cin, side = cin // 2, side * 2
+        dec += side * side * 16 * cin * cfg.img_c
+    else:
+        enc = mlp(cfg.obs_dim)
+        dec = mlp(G + Z) + D * cfg.obs_dim
+    step = (Z + A) * D + D * 3 * G + G * 3 * G + (E + G) * D + 2 * D * Z + G * D   # one observe-scan step, per row
+    rew, cont = mlp(G + Z) + D * 255, mlp(G + Z) + D
+    wm = 3 * N * (enc + step + dec + rew + cont)
+    seq_dyn = (Z + A) * D + (D + G) * 3 * G + G * D + D * Z
+    actor = (mlp(G + Z) + D * A) * (1 if cfg.discrete else 2)
+    critic = mlp(G + Z) + D * 255
+    ac = H * N * seq_dyn + R * (actor + rew + cont + 2 * critic) + 2 * H * N * (critic + actor)
+    if not cfg.discrete:
+        ac += H * N * seq_dyn + R * (rew + critic)
+    return {"world_model": 2e-9 * wm, "actor_critic": 2e-9 * ac, "total": 2e-9 * (wm + ac), "observe_scan_fwd": 2e-9 * N * step}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel from the committed ncu --set full
-# capture (profiles/), keyed by (M, K, N, mode); None when no capture exists for the shape
-TRAFFIC_BYTES = {(16384, 1280, 256, 1): 42616320 + 142080,   # profiles/r01_gemm_tma_ncu.txt (the fp32 C tile stays in L2 past kernel end)
-                 (16384, 1280, 256, 0): None}
+def scan_step_weight_bytes(cfg, bytes_per_weight=4):
+    """Weights one observe-scan step has to read that are on the recurrence (the step's weights minus the
+    hoisted encoder / action parts): W_pre[:Z], GRU kernel + recurrent kernel, W_post[E:], posterior representation layer.
+    (The prior net is hoisted out of the loop entirely.)"""
+    G, D, Z = cfg.G, cfg.D, cfg.Z
+    return bytes_per_weight * (Z * D + D * 3 * G + G * 3 * G + G * D + D * Z)
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the head-contraction kernel from the committed ncu --set full
+# capture (profiles/r01_gemm_tma_ncu.txt; the fp32 C tile stays in L2 past kernel end), keyed by (M, K, N, mode)
+TRAFFIC_BYTES = {(16384, 1280, 256, 1): 42616320 + 142080}
 
 
 def make_cfg(wid, B=16, T=64, H=15):
@@ -161,90 +198,216 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------- our arm
-def run_ours(args):
-    import torch.distributed as dist
-    from dreamer_v3_b200.models.components import CNNAtari, ConvTransposeAtari, MLP, VectorDecoder
-    from dreamer_v3_b200.models.dreamer_model import DreamerModel
-    from dreamer_v3_b200.models.world_model import WorldModel
-    from dreamer_v3_b200.spec import Box, Discrete
-    from dreamer_v3_b200.training.train_one_step import train_actor_and_critic_one_step, train_world_model_one_step
+class Ctx:
+    """Process-wide state of the benchmarked arm: ranks, timing helpers."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    wid = args.workload
-    w = WORKLOADS[wid]
-    cfg = make_cfg(wid)
-    B, T, H = cfg.B, cfg.T, cfg.H
-    aspace = Discrete(w["A"]) if w["discrete"] else Box(-1.0, 1.0, (w["A"],))
-    size = w["size"]
-    if cfg.image_obs:
-        enc, dec = CNNAtari(model_dimension=size), ConvTransposeAtari(model_dimension=size, gray_scaled=False)
-    else:
-        enc, dec = MLP(model_dimension=size), VectorDecoder(model_dimension=size, observation_space=Box(-1, 1, (cfg.obs_dim,)))
-    wm = WorldModel(model_dimension=size, action_space=aspace, batch_length_T=T, encoder=enc, decoder=dec,
-                    symlog_obs=not cfg.image_obs, compute_mode=args.mode)
-    dm = DreamerModel(model_dimension=size, action_space=aspace, batch_size_B=B, batch_length_T=T, horizon_H=H,
-                      world_model=wm, world_size=world, rank=rank)
-    e = dm.engine
-    dm.critic.init_ema()
-    sample_np = synthetic_sample(cfg, seed=rank)
-    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in sample_np.items()}
-    h2d_bytes = sum(v.numel() * 4 for v in pinned.values())
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    host_scalars = torch.empty(24, dtype=torch.float32).pin_memory()
-    d2h_bytes = host_scalars.numel() * 4
-    hp = dict(horizon_H=H, gamma=0.997, lambda_=0.95, actor_grad_clip=100.0, critic_grad_clip=100.0,
-              disagree_grad_clip=100.0, entropy_scale=3e-4, return_normalization_decay=0.99)
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.args, self.dist = args, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-    def api_step(host_inputs):
-        sample = pinned if host_inputs else None
-        if sample is None:  # inputs already resident in the engine's in.* buffers
-            sample = {}
-        r = train_world_model_one_step(sample=sample, batch_size_B=B, batch_length_T=T, grad_clip=1000.0, world_model=wm)
-        a = train_actor_and_critic_one_step(world_model_forward_train_outs=r["WORLD_MODEL_forward_train_outs"],
-                                            is_terminated=e.tensor("in.is_terminated").reshape(-1), dreamer_model=dm, **hp)
-        if host_inputs:
-            host_scalars[:8].copy_(e.tensor("wm.scalars"), non_blocking=True)
-            host_scalars[8:24].copy_(e.tensor("ac.scalars"), non_blocking=True)
-        return r, a
-
-    use_graph = world == 1 and not args.no_graph
-
-    def device_step():
-        if use_graph:
-            e.train_update(noise_seed=1234, use_graph=True)
-        else:
-            api_step(False)
-
-    def barrier():
+    def barrier(self):
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        if self.world > 1:
+            self.dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(self, fn, steps):
         evs = []
         for _ in range(steps):
-            flush.zero_()  # L2 flush (256 MiB > 126 MB L2) between timed iterations, outside the timed events
+            self.flush.zero_()  # L2 flush (256 MiB > 126 MB L2) between timed iterations, outside the timed events
             s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record(); fn(); t.record()
             evs.append((s, t))
         torch.cuda.synchronize()
         return sum(a.elapsed_time(b) for a, b in evs) / steps
 
-    def max_over_ranks(ms):
-        if world == 1:
+    def max_over_ranks(self, ms):
+        if self.world == 1:
             return ms
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident leg ----
-    e.set_sample(pinned)
+
+class Job:
+    """One workload built through the reference-facing API (WorldModel / DreamerModel mirrors) on this rank."""
+
+    def __init__(self, ctx, wid, B_local, mode):
+        from dreamer_v3_b200.models.components import CNNAtari, ConvTransposeAtari, MLP, VectorDecoder
+        from dreamer_v3_b200.models.dreamer_model import DreamerModel
+        from dreamer_v3_b200.models.world_model import WorldModel
+        from dreamer_v3_b200.spec import Box, Discrete
+        self.ctx, self.wid, self.w = ctx, wid, WORKLOADS[wid]
+        w = self.w
+        self.cfg = cfg = make_cfg(wid, B=B_local)
+        aspace = Discrete(w["A"]) if w["discrete"] else Box(-1.0, 1.0, (w["A"],))
+        size = w["size"]
+        if cfg.image_obs:
+            enc, dec = CNNAtari(model_dimension=size), ConvTransposeAtari(model_dimension=size, gray_scaled=False)
+        else:
+            enc, dec = MLP(model_dimension=size), VectorDecoder(model_dimension=size, observation_space=Box(-1, 1, (cfg.obs_dim,)))
+        self.wm = WorldModel(model_dimension=size, action_space=aspace, batch_length_T=cfg.T, encoder=enc, decoder=dec,
+                             symlog_obs=not cfg.image_obs, compute_mode=mode)
+        self.dm = DreamerModel(model_dimension=size, action_space=aspace, batch_size_B=cfg.B, batch_length_T=cfg.T,
+                               horizon_H=cfg.H, world_model=self.wm, world_size=ctx.world, rank=ctx.rank)
+        self.e = self.dm.engine
+        self.dm.critic.init_ema()
+        sample_np = synthetic_sample(cfg, seed=ctx.rank)
+        self.pinned = {k: torch.from_numpy(v).pin_memory() for k, v in sample_np.items()}
+        self.h2d_bytes = sum(v.numel() * 4 for v in self.pinned.values())
+        self.host_scalars = torch.empty(24, dtype=torch.float32).pin_memory()
+        self.d2h_bytes = self.host_scalars.numel() * 4
+        self.hp = dict(horizon_H=cfg.H, gamma=0.997, lambda_=0.95, actor_grad_clip=100.0, critic_grad_clip=100.0,
+                       disagree_grad_clip=100.0, entropy_scale=3e-4, return_normalization_decay=0.99)
+        self.use_graph = ctx.world == 1 and not ctx.args.no_graph
+        self.e.set_sample(self.pinned)
+
+    def close(self):
+        self.e.close()
+        self.wm = self.dm = self.e = None
+        torch.cuda.empty_cache()
+
+    def api_step(self, host_inputs):
+        from dreamer_v3_b200.training.train_one_step import train_actor_and_critic_one_step, train_world_model_one_step
+        e, cfg = self.e, self.cfg
+        sample = self.pinned if host_inputs else {}   # {}: inputs already resident in the engine's in.* buffers
+        r = train_world_model_one_step(sample=sample, batch_size_B=cfg.B, batch_length_T=cfg.T, grad_clip=1000.0, world_model=self.wm)
+        a = train_actor_and_critic_one_step(world_model_forward_train_outs=r["WORLD_MODEL_forward_train_outs"],
+                                            is_terminated=e.tensor("in.is_terminated").reshape(-1), dreamer_model=self.dm, **self.hp)
+        if host_inputs:
+            self.host_scalars[:8].copy_(e.tensor("wm.scalars"), non_blocking=True)
+            self.host_scalars[8:24].copy_(e.tensor("ac.scalars"), non_blocking=True)
+        return r, a
+
+    def device_step(self):
+        if self.use_graph:
+            self.e.train_update(noise_seed=1234, use_graph=True)
+        else:
+            self.api_step(False)
+
+    def e2e_step(self):
+        self.api_step(True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the losses
+
+    def measure(self, steps, warmup, clocks=False, e2e=True, phases=True):
+        """device-resident leg (+ clocks), end-to-end leg, scan latency and the per-phase device times of one update."""
+        ctx, e, cfg = self.ctx, self.e, self.cfg
+        out = {}
+        for _ in range(max(warmup, 3)):
+            self.device_step()
+        ctx.barrier()
+        sampler = ClockSampler(ctx.local) if clocks and ctx.rank == 0 else None
+        if sampler:
+            sampler.start()
+        l0 = e.kernel_launch_count()
+        wall0 = time.perf_counter()
+        ms = ctx.timed(self.device_step, steps)
+        ctx.barrier()
+        out["wall_s_timed_region"] = time.perf_counter() - wall0
+        out["gpu_launches"] = int(e.kernel_launch_count() - l0)
+        if sampler:
+            out["clocks"] = sampler.stop()
+        out["ms_per_step"] = ms = ctx.max_over_ranks(ms)
+        if e2e:
+            for _ in range(3):
+                self.api_step(True)
+            ctx.barrier()
+            ms_e2e = ctx.max_over_ranks(ctx.timed(self.e2e_step, steps))
+            ctx.barrier()
+            out["e2e_ms_per_step"] = ms_e2e
+            hs = self.host_scalars
+            out["final_losses"] = {"wm_total": float(hs[6]), "critic_total": float(hs[8]), "actor_total": float(hs[11])}
+        if phases:
+            # per-phase device times of the non-graph path (CUDA events at the labelled phase boundaries, dv3_phase_report);
+            # "obs.scan" = the observe-scan kernel(s) alone, "wmb.scan_bwd" = the reverse-time BPTT scan alone
+            e.fill_noise(1, 0, 3)
+            reps = 3
+            for i in range(reps + 1):
+                if i == 1:
+                    e.phase_report(enable=1)      # discard the warm-up pass
+                e.observe_forward(); e.wm_loss_backward()
+                e.dream_forward(start_from_observe=True); e.ac_loss_backward(3)
+            ph = e.phase_report(enable=0)
+            out["phases_ms"] = {k: round(v[0] / reps, 4) for k, v in ph.items()}
+            T = cfg.T
+            out["scan_fwd_us_per_step"] = ctx.max_over_ranks(ph.get("obs.scan", (0.0, 1))[0] / reps) * 1e3 / T
+            out["scan_bwd_us_per_step"] = ctx.max_over_ranks(ph.get("wmb.scan_bwd", (0.0, 1))[0] / reps) * 1e3 / T
+        return out
+
+
+def scan_roofline(cfg, us_fwd, us_bwd, pk, mode):
+    """Roofline entry of the time-dominant latency / bandwidth kernel of an update: the observe scan. Algorithmic bytes per
+    step = the step's weights on the recurrence, read once (fp32 as the scan kernels hold them). At XS they are
+    resident in the cluster's shared memory for all T steps, so the kernel has no HBM roofline: it is a latency chain."""
+    wbytes = scan_step_weight_bytes(cfg, 4)
+    out = {"kernel": "observe scan forward (per timestep)", "weight_bytes_per_step": wbytes, "us_per_step": us_fwd,
+           "bwd_us_per_step": us_bwd, "peak": pk["hbm"], "unit": "GB/s", "peak_source": pk["src"]}
+    if cfg.G <= 256:
+        out.update({"bound": "latency", "note": "weights resident in the 16-CTA cluster's shared memory for all T steps (no weight "
+                    "bytes from HBM / L2 per step): 4 cluster barriers + 4 dependent 16-row contraction stages per step",
+                    "achieved": None, "frac": None})
+    else:
+        gbs = wbytes / (us_fwd * 1e-6) / 1e9 if us_fwd > 0 else None
+        gbs_b = wbytes / (us_bwd * 1e-6) / 1e9 if us_bwd > 0 else None
+        out.update({"bound": "hbm", "achieved": gbs, "frac": gbs / pk["hbm"] if gbs else None,
+                    "bwd_achieved": gbs_b, "bwd_frac": gbs_b / pk["hbm"] if gbs_b else None,
+                    "note": "weights re-read every step (from L2 while they fit its 126 MB, from HBM at XL)"})
+    return out
+
+
+def allreduce_ms(ctx, job):
+    """Device time of the gradient all-reduces of one update in isolation (NCCL over NVLink), max over ranks."""
+    e, dist = job.e, ctx.dist
+    bufs = [e.group_buffer(g, "grad") for g in ("world_model", "critic", "actor")]
+    for _ in range(2):
+        for b in bufs:
+            dist.all_reduce(b)
+    ctx.barrier()
+    s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    s.record()
+    for _ in range(reps):
+        for b in bufs:
+            dist.all_reduce(b)
+    t.record()
+    torch.cuda.synchronize()
+    return ctx.max_over_ranks(s.elapsed_time(t) / reps), sum(b.numel() * 4 for b in bufs)
+
+
+def config_entry(ctx, job, m, pk, mode):
+    cfg = job.cfg
+    gf = algorithmic_gflop(cfg)
+    ent = {"workload": job.w["name"], "B_per_gpu": cfg.B, "ms_per_step": m["ms_per_step"], "gpu_launches": m["gpu_launches"],
+           "algorithmic_gflop": round(gf["total"], 1), "step_tflops": gf["total"] / m["ms_per_step"],
+           "tensor_frac_of_sustained_peak": gf["total"] / m["ms_per_step"] / pk["tf_sustained"]}
+    if "e2e_ms_per_step" in m:
+        ent["e2e_ms_per_step"] = m["e2e_ms_per_step"]
+        ent["h2d_bytes_per_step"], ent["d2h_bytes_per_step"] = job.h2d_bytes, job.d2h_bytes
+    if "phases_ms" in m:
+        ent["scan_step_latency_us"] = m["scan_fwd_us_per_step"]
+        ent["scan_bwd_step_latency_us"] = m["scan_bwd_us_per_step"]
+        ent["phases_ms"] = m["phases_ms"]
+        ent["roofline"] = scan_roofline(cfg, m["scan_fwd_us_per_step"], m["scan_bwd_us_per_step"], pk, mode)
+    return ent
+
+
+def run_ours(args):
+    ctx = Ctx(args)
+    world, rank = ctx.world, ctx.rank
+    dist = ctx.dist
+    pk = peaks()
+    wid = args.workload
+    job = Job(ctx, wid, 16, args.mode)
+    e, cfg = job.e, job.cfg
+    B, T, H = cfg.B, cfg.T, cfg.H
+
     if args.breakdown:
         e.fill_noise(1, 0, 3)
         phases = [("observe_forward", e.observe_forward), ("wm_loss_backward", e.wm_loss_backward),
@@ -262,37 +425,16 @@ def run_ours(args):
                 out[name] = (round(s0.elapsed_time(s1), 3), e.kernel_launch_count() - l0)
         print(json.dumps({"breakdown_ms_launches": out, "total_ms": round(sum(v[0] for v in out.values()), 3)}), flush=True)
         return
-    for _ in range(args.warmup if args.quick else max(args.warmup, 3)):
-        device_step()
-    barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    l0 = e.kernel_launch_count()
-    wall0 = time.perf_counter()
-    ms = timed(device_step, args.steps)
-    barrier()
-    wall = time.perf_counter() - wall0
-    launches = e.kernel_launch_count() - l0
-    clk = clocks.stop() if rank == 0 else None
-    ms = max_over_ranks(ms)
-    value = world * 1e3 / ms
-
     if args.quick:
+        m = job.measure(args.steps, args.warmup, e2e=False, phases=False)
         if rank == 0:
-            print(json.dumps({"quick": True, "ms_per_step": ms, "value": value, "gpu_launches": int(launches)}), flush=True)
+            print(json.dumps({"quick": True, "ms_per_step": m["ms_per_step"], "value": world * 1e3 / m["ms_per_step"],
+                              "gpu_launches": m["gpu_launches"]}), flush=True)
         return
-    # ---- end-to-end leg (public API, pinned host inputs, D2H of the losses) ----
-    for _ in range(3):
-        api_step(True)
-    barrier()
 
-    def e2e_step():
-        api_step(True)
-        torch.cuda.current_stream().synchronize()  # the caller reads the losses
-    ms_e2e = max_over_ranks(timed(e2e_step, args.steps))
-    barrier()
-    final = {"wm_total": float(host_scalars[6]), "critic_total": float(host_scalars[8]), "actor_total": float(host_scalars[11])}
+    m = job.measure(args.steps, args.warmup, clocks=True)
+    ms, ms_e2e = m["ms_per_step"], m["e2e_ms_per_step"]
+    value = world * 1e3 / ms
 
     # ---- the reference's inner loop with the device replay sampler: buffer.sample() -> WM step -> AC step,
     # run_experiment.py:410-472; the sample is gathered from the HBM-resident episode store straight into in.* ----
@@ -318,54 +460,101 @@ def run_ours(args):
 
         def replay_step():
             buf.sample(B, T, out=outs)
-            api_step(False)
-            host_scalars[:8].copy_(e.tensor("wm.scalars"), non_blocking=True)
+            job.api_step(False)
+            job.host_scalars[:8].copy_(e.tensor("wm.scalars"), non_blocking=True)
             torch.cuda.current_stream().synchronize()
         for _ in range(3):
             replay_step()
-        ms_rp = timed(replay_step, args.steps)
+        ms_rp = ctx.timed(replay_step, args.steps)
         replay_leg = {"value": 1e3 / ms_rp, "unit": "updates/s", "ms_per_step": ms_rp,
                       "what": "EpisodeReplayBuffer.sample (device store, dv3_replay_gather) + both update steps + D2H of the losses"}
+        e.set_sample(job.pinned)
 
-    # ---- RSSM scan step latency (observe scan forward / T) ----
-    def obs_fwd():
-        e.observe_forward()
+    # ---- whole observe_forward / T (encoder and heads included), kept for continuity with round 1 ----
     for _ in range(3):
-        obs_fwd()
-    scan_us = max_over_ranks(timed(obs_fwd, max(5, args.steps // 2))) * 1e3 / T
+        e.observe_forward()
+    obs_us = ctx.max_over_ranks(ctx.timed(e.observe_forward, max(5, args.steps // 2))) * 1e3 / T
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    pk = peaks()
-    gflop = GFLOP_PER_UPDATE[wid]
+    ar = allreduce_ms(ctx, job) if world > 1 else None
+    gf = algorithmic_gflop(cfg)
     line = {
         "metric": METRIC, "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.mode == 0 else "bf16", "data": "synthetic",
-        "precision_note": ("fp32 everywhere" if args.mode == 0 else "bf16 operands / fp32 accumulate on tcgen05 for contractions with >= 128 rows; fp32 masters, fp32 B=16 observe scan, losses and optimizer"),
-        "config": {"workload": w["name"], "id": wid, "B_per_gpu": B, "T": T, "H": H, "global_batch": B * world,
+        "precision_note": ("fp32 everywhere" if args.mode == 0 else "bf16 operands / fp32 accumulate on tcgen05 for contractions with >= 128 rows; fp32 masters, losses and optimizer"),
+        "config": {"workload": job.w["name"], "id": wid, "B_per_gpu": B, "T": T, "H": H, "global_batch": B * world,
                    "parallelism": f"dp{world}" if world > 1 else "single",
                    "l2": "256 MiB buffer written between timed steps (L2 flush)",
-                   "cuda_graph": ("whole update = one graph replay" if use_graph else
+                   "cuda_graph": ("whole update = one graph replay" if job.use_graph else
                                   "five graph-replayed pieces cut at the NCCL collectives (dv3_dp_piece)" if world > 1 and not args.no_graph
                                   else False), "compute_mode": args.mode},
-        "clocks": clk,
+        "value_note": ("weak scaling: B=16 replay rows per GPU; value = B16xT64 batches consumed per second over all ranks "
+                       "(= optimizer updates/s x n_gpus); literal updates/s of the sharded global batch are in strong_xl"),
+        "clocks": m.get("clocks"),
         "e2e": {"value": world * 1e3 / ms_e2e, "unit": "updates/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
-        "gpu_launches": int(launches),
-        "scan_step_latency_us": scan_us,
-        "step_tflops": gflop / ms,  # algorithmic GFLOP per update / ms = TFLOP/s
-        "final_losses": final,
-        "wall_s_timed_region": wall,
+                "h2d_bytes_per_step": job.h2d_bytes, "d2h_bytes_per_step": job.d2h_bytes},
+        "gpu_launches": m["gpu_launches"],
+        "scan_step_latency_us": m["scan_fwd_us_per_step"],
+        "scan_bwd_step_latency_us": m["scan_bwd_us_per_step"],
+        "observe_forward_us_per_step": obs_us,
+        "phases_ms": m["phases_ms"],
+        "algorithmic_gflop": round(gf["total"], 1),
+        "step_tflops": gf["total"] / ms,  # algorithmic GFLOP per update / ms = TFLOP/s
+        "final_losses": m["final_losses"],
+        "wall_s_timed_region": m["wall_s_timed_region"],
     }
+    if ar is not None:
+        line["allreduce"] = {"ms_per_update_isolated": ar[0], "bytes": ar[1], "busbw_gbs": 2 * (world - 1) / world * ar[1] / (ar[0] * 1e-3) / 1e9}
     if replay_leg is not None:
         line["e2e_device_replay"] = replay_leg
-    line["roofline"] = measure_roofline(e, cfg, pk, args)
-    if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline(wid)
-    print(json.dumps(line), flush=True)
+    line["roofline"] = measure_roofline(e, cfg, pk, args) if rank == 0 else None
+    line["roofline_scan"] = scan_roofline(cfg, m["scan_fwd_us_per_step"], m["scan_bwd_us_per_step"], pk, args.mode)
+    if args.mode == 1 and not args.no_fp32_line and world == 1:
+        # the same update in the fp32 mode (compute_mode 0: the 1e-4 parity mode), device-resident leg only
+        job.close()
+        j0 = Job(ctx, wid, 16, 0)
+        m0 = j0.measure(max(3, args.steps // 2), 3, e2e=False, phases=False)
+        line["fp32_mode"] = {"value": 1e3 / m0["ms_per_step"], "ms_per_step": m0["ms_per_step"], "gpu_launches": m0["gpu_launches"]}
+        j0.close()
+    else:
+        job.close()
+
+    # ---- every other BASELINE configuration (the metric is "per model size") ----
+    if not args.no_per_config:
+        per = {}
+        if world == 1:
+            per[wid] = {"workload": job.w["name"], "value": value, "ms_per_step": ms, "e2e": line["e2e"]["value"],
+                        "scan_step_latency_us": line["scan_step_latency_us"], "see": "top-level keys of this line"}
+            for w2 in [k for k in WORKLOADS if k != wid]:
+                j = Job(ctx, w2, 16, args.mode)
+                k_steps = max(3, min(args.steps, 10 if w2 in ("c1", "c3") else 5))
+                mm = j.measure(k_steps, 3)
+                ent = config_entry(ctx, j, mm, pk, args.mode)
+                ent["value"] = 1e3 / mm["ms_per_step"]
+                ent["e2e"] = 1e3 / mm["e2e_ms_per_step"]
+                ent["steps"] = k_steps
+                per[w2] = ent
+                j.close()
+            line["per_config"] = per
+        # BASELINE configs[4]: XL with the B=16 replay batch SHARDED over the ranks (strong scaling, literal updates/s)
+        if world == 1 and "c5" in per and wid != "c5":
+            x = per["c5"]
+            line["strong_xl"] = {"n_gpus": 1, "B_global": 16, "B_per_gpu": 16, "value": x["value"], "unit": "updates/s",
+                                 "ms_per_step": x["ms_per_step"], "scaling": "strong", "allreduce": None}
+        elif world > 1 and 16 % world == 0:
+            j = Job(ctx, "c5", 16 // world, args.mode)
+            mm = j.measure(max(3, min(args.steps, 5)), 3, e2e=False)
+            arx = allreduce_ms(ctx, j)
+            line["strong_xl"] = {"n_gpus": world, "B_global": 16, "B_per_gpu": 16 // world, "value": 1e3 / mm["ms_per_step"],
+                                 "unit": "updates/s", "ms_per_step": mm["ms_per_step"], "scaling": "strong",
+                                 "phases_ms": mm.get("phases_ms"), "scan_step_latency_us": mm.get("scan_fwd_us_per_step"),
+                                 "allreduce": {"ms_per_update_isolated": arx[0], "bytes": arx[1],
+                                               "busbw_gbs": 2 * (world - 1) / world * arx[1] / (arx[0] * 1e-3) / 1e9}}
+            j.close()
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(wid)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -459,6 +648,8 @@ if __name__ == "__main__":
     ap.add_argument("--mode", type=int, default=1, help="1 = bf16 tcgen05 tensor cores for contractions with >= 128 rows (fp32 accumulate, fp32 scan / elementwise); 0 = fp32 everywhere")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-per-config", action="store_true", help="only the headline workload (skip per_config / strong_xl)")
+    ap.add_argument("--no-fp32-line", action="store_true", help="skip the fp32-mode value of the headline workload")
     ap.add_argument("--ref-rows", type=int, default=None)
     ap.add_argument("--breakdown", action="store_true", help="print per-phase device times (ms) and exit")
     ap.add_argument("--quick", action="store_true", help="profiling aid: only the device-resident leg, no minimum warm-up")

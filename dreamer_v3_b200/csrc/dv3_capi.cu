@@ -68,6 +68,16 @@ int dv3_sync(dv3_engine* h, void* stream) {
   return 0;
 }
 
+int dv3_phase_report(dv3_engine* h, int enable, char* out, size_t cap) {
+  const std::string rep = h->e.phase_collect();
+  if (enable >= 0) h->e.phase_times = enable != 0;
+  if (out == nullptr || cap == 0) return 0;
+  const size_t n = rep.size() < cap - 1 ? rep.size() : cap - 1;
+  std::memcpy(out, rep.data(), n);
+  out[n] = 0;
+  return (int)n;
+}
+
 int dv3_num_tensors(const dv3_engine* h) { return (int)h->e.tensors.size(); }
 
 static void fill_desc(const dv3::TensorEntry& t, dv3_tensor_desc* out) {

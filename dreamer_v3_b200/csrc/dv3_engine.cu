@@ -222,8 +222,9 @@ void Engine::phase_mark(const char* label) {
   cudaEventRecord(ev, cur);
   phase_marks.emplace_back(label, ev);
 }
-void Engine::phase_dump() {
-  if (phase_marks.empty()) return;
+std::string Engine::phase_collect() {
+  std::string out;
+  if (phase_marks.empty()) return out;
   cudaDeviceSynchronize();
   std::map<std::string, std::pair<double, int>> acc;
   std::vector<std::string> order;
@@ -234,9 +235,24 @@ void Engine::phase_dump() {
     if (a.second == 0) order.push_back(phase_marks[i].first);
     a.first += ms; a.second += 1;
   }
-  for (const auto& k : order) fprintf(stderr, "[dv3 phase] %-28s %8.3f ms  (n=%d)\n", k.c_str(), acc[k].first, acc[k].second);
+  char line[160];
+  for (const auto& k : order) {
+    snprintf(line, sizeof(line), "%s %.6f %d\n", k.c_str(), acc[k].first, acc[k].second);
+    out += line;
+  }
   for (auto& m : phase_marks) cudaEventDestroy(m.second);
   phase_marks.clear();
+  return out;
+}
+void Engine::phase_dump() {
+  if (!phase_env || phase_marks.empty()) { return; }
+  const std::string rep = phase_collect();
+  size_t pos = 0;
+  while (pos < rep.size()) {
+    const size_t nl = rep.find('\n', pos);
+    fprintf(stderr, "[dv3 phase] %s\n", rep.substr(pos, nl - pos).c_str());
+    pos = nl + 1;
+  }
 }
 
 void* Engine::twin_alloc(const float* base, size_t elems) {
@@ -473,7 +489,8 @@ void Engine::layout() {
 int Engine::init(const dv3_config* c) {
   cfg = *c;
   if (cfg.abi_version != DV3_ABI_VERSION) return fail("dv3_config.abi_version mismatch");
-  phase_times = std::getenv("DV3_PHASE_TIMES") != nullptr;
+  phase_env = std::getenv("DV3_PHASE_TIMES") != nullptr;  // env: dump at every dv3_sync; otherwise dv3_phase_report switches it
+  phase_times = phase_env;
   G = cfg.G; D = cfg.D; L = cfg.L; Zc = cfg.Zc; Zk = cfg.Zk; Z = Zc * Zk; A = cfg.A;
   B = cfg.B; T = cfg.T; H = cfg.H; N = B * T; R = (H + 1) * N;
   discrete = cfg.discrete != 0; image = cfg.image_obs != 0;

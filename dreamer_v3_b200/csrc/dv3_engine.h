@@ -159,10 +159,11 @@ struct Engine {
   void side_join();                                // cur waits for the side chain
   // ---- debug: DV3_PHASE_TIMES=1 records an event on `cur` at every labelled point of the non-graph path and prints
   // the device time between consecutive marks at the next dv3_sync ----
-  bool phase_times = false;
+  bool phase_times = false, phase_env = false;
   std::vector<std::pair<std::string, cudaEvent_t>> phase_marks;
   void phase_mark(const char* label);
   void phase_dump();
+  std::string phase_collect();  // accumulated per-label device times as text; clears the record
 
   // ---- graph ----
   struct GraphSlot { cudaGraphExec_t exec = nullptr; long long launches = 0; dv3_hparams hp{}; uint64_t seed = 0; };

@@ -149,6 +149,18 @@ class Engine:
         if act_noise is not None:
             self.write("in.act_noise", act_noise)
 
+    def phase_report(self, enable=-1):
+        """Device time per labelled phase of the non-graph path since the last report: {label: (ms, count)} (bench.py)."""
+        buf = C.create_string_buffer(1 << 14)
+        n = self.lib.dv3_phase_report(self.h, int(enable), buf, len(buf))
+        if n < 0:
+            raise Dv3Error("dv3_phase_report failed")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            k, ms, cnt = line.rsplit(" ", 2)
+            out[k] = (float(ms), int(cnt))
+        return out
+
     def fill_noise(self, seed, step=0, which=3):
         self._check(self.lib.dv3_fill_noise(self.h, int(seed), int(step), int(which), self._stream()), "dv3_fill_noise")
 

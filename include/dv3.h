@@ -175,6 +175,12 @@ int64_t dv3_replay_plan(int B, int T, int page, const int64_t* chunk_cum, const 
                         const int32_t* ep_len, const uint8_t* ep_term, const int64_t* ep_page_off, const int32_t* pages,
                         const int64_t* draws, int64_t n_draws, int32_t* plan);
 int64_t dv3_kernel_launch_count(const dv3_engine* e); /* kernels of this library launched (or replayed) so far */
+/* Measurement aid of bench.py (no reference counterpart): enable = 1 / 0 switches the recording of CUDA events at the
+ * labelled phase boundaries of the non-graph path (encoder | observe scan | heads | losses | head backward | backward
+ * scan | weight gradients | ...); enable = -1 leaves the switch alone. Synchronises the device and writes the device time
+ * accumulated per label since the last report as "label ms count" lines into out (capacity cap, NUL-terminated), then
+ * clears the record. Returns the number of bytes written, <0 on error. */
+int dv3_phase_report(dv3_engine* e, int enable, char* out, size_t cap);
 
 /* ---- isolated ops (parity tests call the same kernels the fused path uses) ---------------------- */
 int dv3_op_symlog(const float* x, float* y, int64_t n, void* stream);                 /* utils/symlog.py:9-12 */
