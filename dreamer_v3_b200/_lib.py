@@ -24,7 +24,7 @@ class Dv3Hparams(C.Structure):
     _fields_ = [(n, C.c_float) for n in (
         "gamma", "lambda_", "entropy_scale", "return_normalization_decay", "wm_grad_clip", "actor_grad_clip",
         "critic_grad_clip", "wm_lr", "wm_eps", "ac_lr", "ac_eps", "critic_ema_decay")]
-    _fields_ += [("train_actor", C.c_int32), ("reserved", C.c_int32 * 7)]
+    _fields_ += [("train_actor", C.c_int32), ("critic_lr", C.c_float), ("critic_eps", C.c_float), ("reserved", C.c_int32 * 5)]
 
 
 # name -> (restype, argtypes); mirrors include/dv3.h one to one (tests/test_capi_symbols.py checks it)

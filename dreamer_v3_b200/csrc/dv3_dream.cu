@@ -8,6 +8,10 @@
 
 namespace dv3 {
 
+// the critic has its own Adam in the reference (critic_network.py:58); 0 = same as the actor's
+static inline float critic_lr(const dv3_hparams* hp) { return hp->critic_lr > 0.f ? hp->critic_lr : hp->ac_lr; }
+static inline float critic_eps(const dv3_hparams* hp) { return hp->critic_eps > 0.f ? hp->critic_eps : hp->ac_eps; }
+
 void Engine::actor_fwd(long long row_off) {
   // models/actor_network.py:63-118 on rows [row_off, row_off + N) of the dream
   const float* x = dr_hz + (size_t)row_off * (G + Z);
@@ -110,7 +114,7 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
   phase_mark("dream.heads");
   // real-space rewards / continues / values, loss weights (dreamer_model.py:219-280) and lambda-returns
   AcArgs a{};
-  a.H = H; a.N = N; a.A = A; a.discrete = discrete; a.gamma = gamma; a.lambda_ = 0.95f;
+  a.H = H; a.N = N; a.A = A; a.discrete = discrete; a.gamma = gamma; a.lambda_ = last_lambda;
   a.rew_E = dr_rew_E; a.cont_logit = dr_cont_logit; a.v_E = v_E; a.ema_E = ema_E; a.is_terminated = in_is_term;
   a.r = ac_r; a.c = ac_c; a.w = ac_w; a.v = ac_v; a.targets = ac_targets;
   ac_value_targets(s, a);
@@ -125,6 +129,7 @@ int Engine::ac_loss_backward(const dv3_hparams* hp, int phase, cudaStream_t s) {
   AcArgs a{};
   a.H = H; a.N = N; a.A = A; a.discrete = discrete;
   a.gamma = hp->gamma; a.lambda_ = hp->lambda_; a.entropy_scale = hp->entropy_scale; a.decay = hp->return_normalization_decay;
+  last_lambda = hp->lambda_;
   a.inv_count = inv_world / (float)HN;
   a.rew_E = dr_rew_E; a.cont_logit = dr_cont_logit; a.v_E = v_E; a.ema_E = ema_E; a.is_terminated = in_is_term;
   a.r = ac_r; a.c = ac_c; a.w = ac_w; a.v = ac_v; a.targets = ac_targets;
@@ -134,8 +139,9 @@ int Engine::ac_loss_backward(const dv3_hparams* hp, int phase, cudaStream_t s) {
   }
   if (!(phase & 2)) return 0;
 
-  // percentile EMAs over the (all-gathered) value targets (actor_loss.py:110-129)
-  percentile_ema(s, ac_targets_all, HN * cfg.world_size, hp->return_normalization_decay, pct_ema, pct_raw, nullptr);
+  // percentile EMAs over the (all-gathered) value targets (actor_loss.py:110-129): part of actor_loss, which the reference
+  // only calls when the actor is trained (train_one_step.py:176-189) - a critic-only update leaves them untouched
+  if (hp->train_actor) percentile_ema(s, ac_targets_all, HN * cfg.world_size, hp->return_normalization_decay, pct_ema, pct_raw, nullptr);
 
   AcLossArgs l{};
   l.base = a; l.ema = pct_ema; l.critic_logits = critic_logits; l.dcritic_logits = dcritic_logits;
@@ -239,10 +245,10 @@ int Engine::train_ac(const dv3_hparams* hp, cudaStream_t s) {
   rc = ac_loss_backward(hp, 3, s);
   if (rc) return rc;
   if (hp->train_actor) {
-    rc = optimizer_step(1, hp->actor_grad_clip, hp->ac_lr, hp->ac_eps, 0.f, s);
+    rc = optimizer_step(1, hp->actor_grad_clip, hp->ac_lr, hp->ac_eps, -1.f, s);
     if (rc) return rc;
   }
-  return optimizer_step(2, hp->critic_grad_clip, hp->ac_lr, hp->ac_eps, hp->critic_ema_decay, s);
+  return optimizer_step(2, hp->critic_grad_clip, critic_lr(hp), critic_eps(hp), hp->critic_ema_decay, s);
 }
 
 template <class F>
@@ -269,8 +275,11 @@ int Engine::run_graphed(GraphSlot& slot, const dv3_hparams* hp, uint64_t seed, c
     e = cudaStreamEndCapture(run, &graph);
     slot.launches = g_launches - before;
     g_launches = before;
-    if (rc) return rc;
-    if (e != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    if (rc || e != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      if (rc) return rc;
+      return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    }
     e = cudaGraphInstantiate(&slot.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
@@ -318,7 +327,7 @@ int Engine::dp_piece(const dv3_hparams* hp, int piece, uint64_t seed, int use_gr
         rc = observe_forward(st);
         if (!rc) rc = wm_loss_backward(st);
         break;
-      case 1: rc = optimizer_step(0, hp->wm_grad_clip, hp->wm_lr, hp->wm_eps, 0.f, st); break;
+      case 1: rc = optimizer_step(0, hp->wm_grad_clip, hp->wm_lr, hp->wm_eps, -1.f, st); break;
       case 2:
         if (seed != 0) fill_noise(seed, 0, 2, true, st);
         rc = dream_forward(hp->gamma, 1, st);
@@ -326,8 +335,8 @@ int Engine::dp_piece(const dv3_hparams* hp, int piece, uint64_t seed, int use_gr
         break;
       case 3: rc = ac_loss_backward(hp, 2, st); break;
       default:
-        if (hp->train_actor) rc = optimizer_step(1, hp->actor_grad_clip, hp->ac_lr, hp->ac_eps, 0.f, st);
-        if (!rc) rc = optimizer_step(2, hp->critic_grad_clip, hp->ac_lr, hp->ac_eps, hp->critic_ema_decay, st);
+        if (hp->train_actor) rc = optimizer_step(1, hp->actor_grad_clip, hp->ac_lr, hp->ac_eps, -1.f, st);
+        if (!rc) rc = optimizer_step(2, hp->critic_grad_clip, critic_lr(hp), critic_eps(hp), hp->critic_ema_decay, st);
     }
     return rc;
   };
@@ -370,8 +379,11 @@ int Engine::train_update(const dv3_hparams* hp, uint64_t seed, int use_graph, cu
     e = cudaStreamEndCapture(run, &graph);
     graph_launches = g_launches - before;
     g_launches = before;
-    if (rc) return rc;
-    if (e != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    if (rc || e != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      if (rc) return rc;
+      return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    }
     e = cudaGraphInstantiate(&graph_exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));

@@ -335,6 +335,7 @@ void Engine::layout() {
   u_act = af("wm.u", {Nl, D});
   gx = af("wm.gates", {Nl, 3 * G});
   gh = af("wm.gh", {Nl, 3 * G});
+  if (cfg.compute_mode == 1 && G >= 512) gx_acc = af("", {Nl, 3 * G});
   hz = af("wm.hz", {Nl, G + Z});
   if (Nl >= 128) hz16 = twin_alloc(hz, (size_t)Nl * (G + Z));
   p_pre = af("wm.p_pre", {Nl, D}); p_mean = af("", {Nl}); p_rstd = af("", {Nl});
@@ -581,6 +582,7 @@ int Engine::init(const dv3_config* c) {
     if (wb < 8) wb = 8;
     scan_bwd_ctas = wb < max_b ? wb : max_b;
   }
+  scan_tc_ctas = (cfg.compute_mode == 1 && gx_acc != nullptr && B <= 16 && !shadow_host.empty()) ? scan_tc_max_ctas(cfg.device) : 0;
   const float nanv[2] = {NAN, NAN};
   CK(cudaMemcpy(pct_ema, nanv, 8, cudaMemcpyHostToDevice));
   CK(cudaDeviceSynchronize());
@@ -633,6 +635,17 @@ void Engine::build_shadows() {
   if (cudaMalloc((void**)&shadow_dev, shadow_host.size() * sizeof(ShadowDesc)) != cudaSuccess) { shadow_host.clear(); return; }
   allocations.push_back(shadow_dev);
   cudaMemcpy(shadow_dev, shadow_host.data(), shadow_host.size() * sizeof(ShadowDesc), cudaMemcpyHostToDevice);
+}
+
+const void* Engine::shadow_t(const float* w, int* ld) const {
+  for (const ShadowDesc& d : shadow_host) {
+    if (w < d.in || w >= d.in + (size_t)d.rows * d.cols) continue;
+    const size_t off = (size_t)(w - d.in);
+    if (off % d.cols != 0) return nullptr;   // only row sub-blocks (K offsets) are addressable in the transposed copy
+    *ld = d.rows;
+    return reinterpret_cast<const unsigned short*>(d.out_t) + off / d.cols;
+  }
+  return nullptr;
 }
 
 void Engine::refresh_shadows(cudaStream_t s) {
@@ -867,7 +880,7 @@ int Engine::optimizer_step(int group, float clip, float lr, float eps, float ema
   if (group < 0 || group > 2) return fail("optimizer_step: group must be 0 (world_model), 1 (actor) or 2 (critic)");
   cur = s;
   grad_norm(s, grads[group], numel[group], adam[group]);
-  float* ema = (group == 2 && ema_decay > 0.f) ? params[3] : nullptr;
+  float* ema = (group == 2 && ema_decay >= 0.f) ? params[3] : nullptr;   // a decay of 0.0 is a legitimate EMA (ema = w)
   adam_step(s, params[group], grads[group], adam_m[group], adam_v[group], numel[group], clip, lr, eps, adam[group], ema, ema_decay);
   return 0;
 }

@@ -90,6 +90,9 @@ struct Engine {
   unsigned int* scan_bar = nullptr;   // [2] grid-barrier counters of the persistent scan kernels (fwd, bwd)
   int scan_bwd_ctas = 0;
   int scan_ctas = 0;          // > 0: persistent cooperative scan kernels are usable with this many CTAs
+  int scan_tc_ctas = 0;       // > 0: the weight-streaming tensor-core scan (dv3_scan_tc.cu) is usable with this many CTAs
+  float* gx_acc = nullptr;    // [N, 3G] accumulator of u . K in that kernel
+  const void* shadow_t(const float* w, int* ld) const;  // bf16 transposed shadow [cols, rows] of (a row sub-block of) a weight matrix
   bool use_persistent = true;
   MlpAct enc_act;
   float *h_in, *z_in, *x_pre, *x_mean, *x_rstd, *u_act, *gx, *gh, *hz;
@@ -124,7 +127,7 @@ struct Engine {
   float *sN_Z, *sN_3G0, *sN_3G1, *sN_A;  // dream-backward scratch [N, Z], [N, 3G], [N, A]
   float *dr_dx_pre = nullptr, *dr_dact = nullptr;  // Box BPTT: per-step grads w.r.t. the pre-GRU pre-activation [H*N, D] and the actions [H*N, A]
   unsigned long long* noise_step = nullptr;
-  float last_gamma = 0.997f;
+  float last_gamma = 0.997f, last_lambda = 0.95f;   // lambda of the value targets exposed after dream_forward alone: the last hparams seen
 
   // ---- bf16 weight shadows for the tensor-core path (compute_mode 1) ----
   std::vector<ShadowDesc> shadow_host;

@@ -42,7 +42,7 @@ int Engine::observe_forward(cudaStream_t s) {
 
   // measured on B200: the persistent kernel wins up to size L; at XL (GRU 4096) weight streaming dominates and the
   // per-op path with split-K GEMMs is faster
-  if (use_persistent && scan_ctas > 0 && G <= 2048) {
+  auto scan_persistent = [&]() -> int {
     ScanFwdParams sp{};
     sp.B = B; sp.T = T; sp.G = G; sp.D = D; sp.Z = Z; sp.Zc = Zc; sp.Zk = Zk; sp.E = E;
     sp.W_pre = Wx.w; sp.pre_g = Wx.g; sp.pre_b = Wx.b; sp.gru_K = gru_K; sp.gru_U = gru_U; sp.gru_b = gru_b;
@@ -55,6 +55,36 @@ int Engine::observe_forward(cudaStream_t s) {
     sp.bar = scan_bar;
     cudaError_t ce = scan_cluster_supported(sp) ? launch_observe_scan_cluster(s, sp) : launch_observe_scan_fwd(s, sp, scan_ctas);
     if (ce != cudaSuccess) return fail(std::string("observe scan launch: ") + cudaGetErrorString(ce));
+    return 0;
+  };
+  // tensor-core mode, S ... XL: one persistent kernel streams the bf16 weight shadows through tcgen05 (dv3_scan_tc.cu)
+  ScanTcWeights tw{};
+  bool use_tc = false;
+  if (use_persistent && scan_tc_ctas > 0) {
+    ScanFwdParams sp{};
+    sp.B = B; sp.T = T; sp.G = G; sp.D = D; sp.Z = Z; sp.Zc = Zc; sp.Zk = Zk; sp.E = E;
+    if (scan_tc_supported(sp)) {
+      tw.Kt = shadow_t(gru_K, &tw.ld_Kt);
+      tw.Ut = shadow_t(gru_U, &tw.ld_Ut);
+      tw.Wpost_h_t = shadow_t(Wp.w + (size_t)E * D, &tw.ld_Wpost_h_t);
+      tw.Wzq_t = shadow_t(post_repr.w, &tw.ld_Wzq_t);
+      use_tc = tw.Kt && tw.Ut && tw.Wpost_h_t && tw.Wzq_t;
+    }
+  }
+  if (use_tc) {
+    ScanFwdParams sp{};
+    sp.B = B; sp.T = T; sp.G = G; sp.D = D; sp.Z = Z; sp.Zc = Zc; sp.Zk = Zk; sp.E = E;
+    sp.W_pre = Wx.w; sp.pre_g = Wx.g; sp.pre_b = Wx.b; sp.gru_K = gru_K; sp.gru_U = gru_U; sp.gru_b = gru_b;
+    sp.W_post = Wp.w; sp.post_g = Wp.g; sp.post_b = Wp.b; sp.W_zq = post_repr.w; sp.b_zq = post_repr.bias;
+    sp.is_first = in_is_first; sp.actW = actW; sp.u_post = in_u_post; sp.h0 = h0; sp.z0_idx = z0_idx;
+    sp.h_in = h_in; sp.z_in = z_in; sp.x_pre = x_pre; sp.x_mean = x_mean; sp.x_rstd = x_rstd; sp.u_act = u_act;
+    sp.gates = gx; sp.gh = gh; sp.hz = hz; sp.p_pre = p_pre; sp.p_mean = p_mean; sp.p_rstd = p_rstd;
+    sp.p_act = p_act; sp.post_logits = post_logits; sp.post_probs = post_probs; sp.z_idx = z_idx;
+    sp.bar = scan_bar;
+    cudaError_t ce = launch_observe_scan_tc(s, sp, tw, gx_acc, scan_tc_ctas);
+    if (ce != cudaSuccess) return fail(std::string("observe scan (tensor-core) launch: ") + cudaGetErrorString(ce));
+  } else if (use_persistent && scan_ctas > 0 && G <= 2048) {
+    if (int rc = scan_persistent()) return rc;
   } else
   for (int t = 0; t < T; ++t) {
     const float* hz_prev = t > 0 ? hz + (size_t)(t - 1) * (G + Z) : nullptr;
@@ -313,7 +343,7 @@ int Engine::train_wm(const dv3_hparams* hp, cudaStream_t s) {
   if (rc) return rc;
   rc = wm_loss_backward(s);
   if (rc) return rc;
-  return optimizer_step(0, hp->wm_grad_clip, hp->wm_lr, hp->wm_eps, 0.f, s);
+  return optimizer_step(0, hp->wm_grad_clip, hp->wm_lr, hp->wm_eps, -1.f, s);
 }
 
 }  // namespace dv3

@@ -75,4 +75,15 @@ cudaError_t launch_observe_scan_fwd(cudaStream_t s, const ScanFwdParams& p, int 
 bool scan_cluster_supported(const ScanFwdParams& p);
 cudaError_t launch_observe_scan_cluster(cudaStream_t s, const ScanFwdParams& p);
 
+// weight-streaming tensor-core version (dv3_scan_tc.cu; S ... XL in compute_mode 1): bf16 K-major weight shadows [N_out, K]
+struct ScanTcWeights {
+  const void* Kt; int ld_Kt;                // gru kernel^T            [3G, D]
+  const void* Ut; int ld_Ut;                // gru recurrent kernel^T  [3G, G]
+  const void* Wpost_h_t; int ld_Wpost_h_t;  // h-part of W_post^T      [D, G] (row stride E + G)
+  const void* Wzq_t; int ld_Wzq_t;          // posterior representation layer^T [Z, D]
+};
+bool scan_tc_supported(const ScanFwdParams& p);
+int scan_tc_max_ctas(int device);
+cudaError_t launch_observe_scan_tc(cudaStream_t s, const ScanFwdParams& p, const ScanTcWeights& w, float* gx_acc, int ctas);
+
 }  // namespace dv3

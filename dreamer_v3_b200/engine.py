@@ -174,7 +174,7 @@ class Engine:
     def wm_loss_backward(self):
         self._check(self.lib.dv3_wm_loss_backward(self.h, self._stream()), "dv3_wm_loss_backward")
 
-    def optimizer_step(self, group, clip, lr, eps, ema_decay=0.0):
+    def optimizer_step(self, group, clip, lr, eps, ema_decay=-1.0):
         self._check(self.lib.dv3_optimizer_step(self.h, GROUP_IDS[group], clip, lr, eps, ema_decay, self._stream()),
                     "dv3_optimizer_step")
 

@@ -70,6 +70,7 @@ def train_actor_and_critic_one_step(*, world_model_forward_train_outs, is_termin
         e.write("in.is_terminated", torch.as_tensor(is_terminated).reshape(e.cfg.B, e.cfg.T))
         hp.actor_grad_clip, hp.critic_grad_clip = float(actor_grad_clip), float(critic_grad_clip)
         hp.ac_lr, hp.ac_eps, hp.critic_ema_decay = aopt.learning_rate, aopt.epsilon, dreamer_model.critic.ema_decay
+        hp.critic_lr, hp.critic_eps = copt.learning_rate, copt.epsilon
         seed = 0 if wm._explicit_noise else wm.noise_seed + 104729 * e.rank
         e.dp_piece(2, seed)
         dist.all_gather_into_tensor(t("ac.value_targets_all").reshape(-1), t("ac.value_targets").reshape(-1))
@@ -86,6 +87,7 @@ def train_actor_and_critic_one_step(*, world_model_forward_train_outs, is_termin
         e.write("in.is_terminated", torch.as_tensor(is_terminated).reshape(e.cfg.B, e.cfg.T))
         hp.actor_grad_clip, hp.critic_grad_clip = float(actor_grad_clip), float(critic_grad_clip)
         hp.ac_lr, hp.ac_eps, hp.critic_ema_decay = aopt.learning_rate, aopt.epsilon, dreamer_model.critic.ema_decay
+        hp.critic_lr, hp.critic_eps = copt.learning_rate, copt.epsilon
         e.train_actor_critic_step(noise_seed=0 if wm._explicit_noise else wm.noise_seed)
         return _ac_results(e, dreamer_model._dream_outs(), train_actor)
     dream_data = dreamer_model.dream_trajectory(

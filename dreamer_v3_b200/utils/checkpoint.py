@@ -121,10 +121,13 @@ def set_optimizer_weights(engine, model, weights):
 MODELS = ("world_model", "actor", "critic")
 
 
-def save_checkpoint(path, dreamer_model, **counters):
-    """run_experiment.py:692-714 (+ dv3_state.npz). counters: total_env_steps, total_replayed_steps, total_train_steps, iteration."""
+def save_checkpoint(path, dreamer_model, buffer=None, **counters):
+    """run_experiment.py:692-714 (+ dv3_state.npz). counters: total_env_steps, total_replayed_steps, total_train_steps, iteration.
+    buffer: the EpisodeReplayBuffer, written as buffer.npz with key `state` exactly like run_experiment.py:708."""
     e = dreamer_model.engine
     os.makedirs(path, exist_ok=True)
+    if buffer is not None:
+        np.savez(os.path.join(path, "buffer"), state=buffer.get_state())
     for m in MODELS:
         np.savez(os.path.join(path, m), weights=np.array(get_weights(e, m), dtype=object))
         np.savez(os.path.join(path, m + "_optimizer"), weights=np.array(get_optimizer_weights(e, m), dtype=object))
@@ -142,9 +145,13 @@ def save_checkpoint(path, dreamer_model, **counters):
     np.savez(os.path.join(path, "dv3_state"), **state)
 
 
-def load_checkpoint(path, dreamer_model):
-    """Restores from dv3_state.npz when present (exact), else from the reference-layout files. Returns the counters."""
+def load_checkpoint(path, dreamer_model, buffer=None):
+    """Restores from dv3_state.npz when present (exact), else from the reference-layout files (EXPERIMENTAL: the Keras
+    get_weights() / optimizer-slot order is restated from Keras' documented tracking order and has not been validated against a
+    file written by TensorFlow). buffer: restored from buffer.npz when given (run_experiment.py:226-228). Returns the counters."""
     e = dreamer_model.engine
+    if buffer is not None:
+        buffer.set_state(np.load(os.path.join(path, "buffer.npz"), allow_pickle=True)["state"])
     exact = os.path.join(path, "dv3_state.npz")
     if os.path.exists(exact):
         z = np.load(exact)

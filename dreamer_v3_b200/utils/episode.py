@@ -57,6 +57,28 @@ class Episode:
     def get_return(self):
         return sum(self.rewards)
 
+    def get_state(self):
+        """utils/episode.py:110-118: the same key order (`from_state` and the buffer's `set_state` index it positionally)."""
+        return list({
+            "id_": self.id_,
+            "observations": self.observations,
+            "actions": self.actions,
+            "rewards": self.rewards,
+            "states": self.states,
+            "is_terminated": self.is_terminated,
+        }.items())
+
+    @staticmethod
+    def from_state(state):
+        """utils/episode.py:120-128."""
+        eps = Episode(id_=state[0][1])
+        eps.observations = list(state[1][1])
+        eps.actions = list(state[2][1])
+        eps.rewards = list(state[3][1])
+        eps.states = state[4][1]
+        eps.is_terminated = bool(state[5][1])
+        return eps
+
     def __len__(self):
         if len(self.observations) == 0:
             raise AssertionError("episode has no initial observation yet")

@@ -214,6 +214,71 @@ class EpisodeReplayBuffer:
         self.sampled_timesteps += B * T
         return out
 
+    # ------------------------------------------------------------------ checkpointing (run_experiment.py:228, :708)
+    def _download(self, st):
+        """A stored episode's pages read back from the store as a host `Episode` (observations in their original dtype)."""
+        n = st.length
+        pg = np.asarray(st.pages, np.int64)
+        ts = np.arange(n + 1)
+        slots = torch.from_numpy(pg[ts // PAGE] * PAGE + ts % PAGE).to(self.device)
+        obs = self._obs_store[slots].cpu().numpy().reshape((n + 1,) + self._obs_shape)
+        act = self._act_store[slots[:n]].cpu().numpy().reshape((n,) + self._act_shape)
+        rew = self._rew_store[slots[:n]].cpu().numpy()
+        return Episode(st.id_, observations=list(obs), actions=list(act), rewards=list(rew), is_terminated=st.is_terminated)
+
+    def get_state(self):
+        """utils/episode_replay_buffer.py:240-248, same keys in the same order (`np.savez(.../buffer, state=...)` of
+        run_experiment.py:708 stores it as an object array): the episodes are read back from the HBM pages; `_indices` is the
+        reference's arrival-ordered list of (absolute episode index, timestep) pairs, expanded from the chunk table."""
+        eps = [self._download(st).get_state() for st in self.episodes]
+        indices = [(int(c[0]), int(c[1]) + i) for c in self._chunks for i in range(int(c[2]))]
+        state = list({
+            "episodes": eps,
+            "episode_id_to_index": list(self.episode_id_to_index.items()),
+            "_num_episodes_ejected": self._num_episodes_ejected,
+            "_indices": indices,
+            "size": self.size,
+            "sampled_timesteps": self.sampled_timesteps,
+        }.items())
+        out = np.empty((len(state), 2), dtype=object)   # np.array(list(...)) of the reference, without ragged broadcasting
+        for i, (k, v) in enumerate(state):
+            out[i, 0], out[i, 1] = k, v
+        return out
+
+    def set_state(self, state):
+        """utils/episode_replay_buffer.py:250-264: positional keys as written by `get_state` (also of the reference's own
+        buffer). The episodes are uploaded into fresh pages, `_indices` is run-length encoded back into the chunk table."""
+        names = ("episodes", "episode_id_to_index", "_num_episodes_ejected", "_indices", "size", "sampled_timesteps")
+        for i, k in enumerate(names):
+            assert state[i][0] == k, (i, state[i][0], k)
+        self.episodes = deque()
+        self._chunks = []
+        self._obs_store = self._act_store = self._rew_store = None
+        self._free_pages, self._num_pages = [], 0
+        self.episode_id_to_index = {k: int(v) for k, v in dict(state[1][1]).items()}
+        self._num_episodes_ejected = int(state[2][1])
+        for eps_state in state[0][1]:
+            eps = Episode.from_state(eps_state)
+            n = len(eps)
+            if self._obs_store is None:
+                self._alloc(eps.observations[0], eps.actions[0] if n else 0.0)
+            st = _Stored(eps.id_)
+            self._upload(st, eps.observations, eps.actions, eps.rewards, 0, 0)
+            st.length, st.is_terminated = n, bool(eps.is_terminated)
+            self.episodes.append(st)
+        chunks = []
+        for e_idx, ts in state[3][1]:
+            e_idx, ts = int(e_idx), int(ts)
+            if chunks and chunks[-1][0] == e_idx and chunks[-1][1] + chunks[-1][2] == ts:
+                chunks[-1][2] += 1
+            else:
+                chunks.append([e_idx, ts, 1])
+        self._chunks = [tuple(c) for c in chunks]
+        self._chunk_cum = np.concatenate([[0], np.cumsum([c[2] for c in self._chunks], dtype=np.int64)]).astype(np.int64)
+        self.size = int(state[4][1])
+        self.sampled_timesteps = int(state[5][1])
+        self._tab = None
+
     def get_num_episodes(self):
         return len(self.episodes)
 

@@ -74,7 +74,8 @@ typedef struct dv3_hparams {
   float wm_lr, wm_eps, ac_lr, ac_eps;
   float critic_ema_decay;
   int32_t train_actor;
-  int32_t reserved[7];
+  float critic_lr, critic_eps;  /* the critic's own Adam (critic_network.py:58); 0 = use ac_lr / ac_eps */
+  int32_t reserved[5];
 } dv3_hparams;
 
 /* ---- lifetime ----------------------------------------------------------------------------- */
@@ -112,7 +113,7 @@ int dv3_observe_forward(dv3_engine* e, void* stream);
 int dv3_wm_loss_backward(dv3_engine* e, void* stream);
 /* tf.clip_by_global_norm + Keras Adam (+ critic EMA for group 2) on a group's flat buffers
  * (train_one_step.py:80-86, 214-250). Call after the gradient all-reduce when world_size > 1. */
-int dv3_optimizer_step(dv3_engine* e, int group, float clip, float lr, float eps, float ema_decay, void* stream);
+int dv3_optimizer_step(dv3_engine* e, int group, float clip, float lr, float eps, float ema_decay, void* stream); /* ema_decay < 0: no EMA update (any value in [0, 1] is a decay, 0 included) */
 /* One call = train_world_model_one_step (train_one_step.py:17-126) for world_size == 1. noise_seed != 0: in.u_post is
  * drawn on the device first; use_graph: the call is captured once into a CUDA graph and replayed. */
 int dv3_train_world_model_step(dv3_engine* e, const dv3_hparams* hp, uint64_t noise_seed, int use_graph, void* stream);

@@ -143,3 +143,72 @@ def test_no_cpu_fallback_for_the_replay_buffer():
     from dreamer_v3_b200.utils.episode_replay_buffer import EpisodeReplayBuffer
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         EpisodeReplayBuffer(capacity=10)
+
+
+@pytest.mark.parametrize("kind", ("vec", "img"))
+def test_buffer_state_round_trip(kind, tmp_path):
+    """get_state / set_state in the reference's key layout (utils/episode_replay_buffer.py:240-264; written as buffer.npz by
+    run_experiment.py:708, read back at :228): a buffer restored from the saved file reproduces the reference's own sample
+    vectors bit for bit (host bookkeeping + native plan; the store is a host tensor here)."""
+    from dreamer_v3_b200.utils.episode_replay_buffer import EpisodeReplayBuffer
+    buf = device_buffer(kind == "img", _host_index_only=True)
+    np.random.seed(5)
+    buf.plan(4, 8)
+    buf.sampled_timesteps = 32
+    np.savez(tmp_path / "buffer", state=buf.get_state())
+    state = np.load(tmp_path / "buffer.npz", allow_pickle=True)["state"]
+    assert [state[i][0] for i in range(6)] == ["episodes", "episode_id_to_index", "_num_episodes_ejected", "_indices", "size",
+                                               "sampled_timesteps"]
+    new = EpisodeReplayBuffer(capacity=CAPACITY, normalize_uint8=False, _host_index_only=True)
+    new.set_state(state)
+    assert new.get_num_episodes() == buf.get_num_episodes() == int(GOLD[f"{kind}/num_episodes"])
+    assert new.get_num_timesteps() == buf.get_num_timesteps() == int(GOLD[f"{kind}/num_timesteps"])
+    assert new.size == buf.size and new.get_sampled_timesteps() == 32
+    assert new._num_episodes_ejected == buf._num_episodes_ejected and new.episode_id_to_index == buf.episode_id_to_index
+    obs_s, act_s, rew_s = new._obs_store.numpy(), new._act_store.numpy(), new._rew_store.numpy()
+    for i, (B, T, seed) in enumerate(SAMPLES):
+        np.random.seed(seed)
+        plan = new.plan(B, T)
+        want = {k: GOLD[f"{kind}/s{i}/{k}"] for k in KEYS}
+        assert np.array_equal(obs_s[plan[:, 0]].reshape(want["obs"].shape), want["obs"])
+        assert np.array_equal(act_s[plan[:, 1]].reshape(want["actions"].shape), want["actions"])
+        assert np.array_equal(np.where(plan[:, 2] >= 0, rew_s[np.maximum(plan[:, 2], 0)], 0.0).reshape(B, T), want["rewards"])
+    # a restored buffer keeps accepting chunks of its ongoing episodes and new episodes
+    from dreamer_v3_b200.utils.episode import Episode
+    n0 = new.get_num_timesteps()
+    new.add(Episode("fresh", observations=list(np.zeros((4,) + new._obs_shape, new._obs_store.numpy().dtype)),
+                    actions=list(np.zeros((3,) + new._act_shape, np.float32)), rewards=[0.0, 1.0, 2.0], is_terminated=True))
+    assert new.get_num_timesteps() == n0 + 3 or new.size <= new.capacity   # (an ejection may have made room)
+
+
+def test_reference_buffer_loads_our_state():
+    """Cross-check against the reference's own code where it is available (this container only): the state written by our
+    buffer is accepted by the reference's `EpisodeReplayBuffer.set_state` and both then draw identical samples."""
+    import importlib.util
+    import sys
+    ref = "/root/reference/utils/episode_replay_buffer.py"
+    if not os.path.exists(ref):
+        pytest.skip("reference sources not present on this machine")
+    sys.path.insert(0, "/root/reference")
+    try:
+        for m in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
+            del sys.modules[m]
+        spec = importlib.util.spec_from_file_location("ref_erb", ref)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove("/root/reference")
+        for m in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
+            del sys.modules[m]
+    buf = device_buffer(False, _host_index_only=True)
+    rb = mod.EpisodeReplayBuffer(capacity=CAPACITY)
+    rb.set_state(buf.get_state())
+    assert rb.get_num_episodes() == buf.get_num_episodes() and rb.get_num_timesteps() == buf.get_num_timesteps()
+    obs_s, act_s, rew_s = buf._obs_store.numpy(), buf._act_store.numpy(), buf._rew_store.numpy()
+    for B, T, seed in SAMPLES[:2]:
+        np.random.seed(seed)
+        want = rb.sample(batch_size_B=B, batch_length_T=T)
+        np.random.seed(seed)
+        plan = buf.plan(B, T)
+        assert np.array_equal(obs_s[plan[:, 0]].reshape(np.asarray(want["obs"]).shape), np.asarray(want["obs"]))
+        assert np.array_equal(np.where(plan[:, 2] >= 0, rew_s[np.maximum(plan[:, 2], 0)], 0.0).reshape(B, T), np.asarray(want["rewards"]))

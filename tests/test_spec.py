@@ -68,7 +68,7 @@ def test_capi_exports_every_declared_symbol():
     assert lib.dv3_abi_version() == 1
     # struct layouts agree with the header (field order / count)
     assert ctypes.sizeof(_lib.Dv3Config) == 4 * (21 + 8)
-    assert ctypes.sizeof(_lib.Dv3Hparams) == 4 * (12 + 1 + 7)
+    assert ctypes.sizeof(_lib.Dv3Hparams) == 4 * (12 + 1 + 2 + 5)
     hp = _lib.Dv3Hparams()
     lib.dv3_default_hparams(ctypes.byref(hp))
     assert abs(hp.gamma - 0.997) < 1e-7 and abs(hp.lambda_ - 0.95) < 1e-7 and abs(hp.wm_lr - 1e-4) < 1e-10
