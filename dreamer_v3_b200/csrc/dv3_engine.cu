@@ -648,6 +648,17 @@ const void* Engine::shadow_t(const float* w, int* ld) const {
   return nullptr;
 }
 
+const void* Engine::shadow_n(const float* w, int* ld) const {
+  for (const ShadowDesc& d : shadow_host) {
+    if (w < d.in || w >= d.in + (size_t)d.rows * d.cols) continue;
+    const size_t off = (size_t)(w - d.in);
+    if (off % d.cols != 0) return nullptr;
+    *ld = d.cols;
+    return reinterpret_cast<const unsigned short*>(d.out_n) + off;
+  }
+  return nullptr;
+}
+
 void Engine::refresh_shadows(cudaStream_t s) {
   if (cfg.compute_mode != 1 || shadow_host.empty()) return;
   weight_shadow_batched(s, shadow_dev, (int)shadow_host.size(), shadow_tiles);

@@ -93,6 +93,7 @@ struct Engine {
   int scan_tc_ctas = 0;       // > 0: the weight-streaming tensor-core scan (dv3_scan_tc.cu) is usable with this many CTAs
   float* gx_acc = nullptr;    // [N, 3G] accumulator of u . K in that kernel
   const void* shadow_t(const float* w, int* ld) const;  // bf16 transposed shadow [cols, rows] of (a row sub-block of) a weight matrix
+  const void* shadow_n(const float* w, int* ld) const;  // bf16 plain shadow [rows, cols] of (a row sub-block of) a weight matrix
   bool use_persistent = true;
   MlpAct enc_act;
   float *h_in, *z_in, *x_pre, *x_mean, *x_rstd, *u_act, *gx, *gh, *hz;

@@ -61,9 +61,7 @@ int Engine::observe_forward(cudaStream_t s) {
   ScanTcWeights tw{};
   bool use_tc = false;
   if (use_persistent && scan_tc_ctas > 0) {
-    ScanFwdParams sp{};
-    sp.B = B; sp.T = T; sp.G = G; sp.D = D; sp.Z = Z; sp.Zc = Zc; sp.Zk = Zk; sp.E = E;
-    if (scan_tc_supported(sp)) {
+    if (scan_tc_supported(B, G, D, Z, Zk)) {
       tw.Kt = shadow_t(gru_K, &tw.ld_Kt);
       tw.Ut = shadow_t(gru_U, &tw.ld_Ut);
       tw.Wpost_h_t = shadow_t(Wp.w + (size_t)E * D, &tw.ld_Wpost_h_t);
@@ -81,6 +79,7 @@ int Engine::observe_forward(cudaStream_t s) {
     sp.gates = gx; sp.gh = gh; sp.hz = hz; sp.p_pre = p_pre; sp.p_mean = p_mean; sp.p_rstd = p_rstd;
     sp.p_act = p_act; sp.post_logits = post_logits; sp.post_probs = post_probs; sp.z_idx = z_idx;
     sp.bar = scan_bar;
+    sp.stamps = std::getenv("DV3_SCAN_STAMPS") ? scan_stamps : nullptr;
     cudaError_t ce = launch_observe_scan_tc(s, sp, tw, gx_acc, scan_tc_ctas);
     if (ce != cudaSuccess) return fail(std::string("observe scan (tensor-core) launch: ") + cudaGetErrorString(ce));
   } else if (use_persistent && scan_ctas > 0 && G <= 2048) {
@@ -168,7 +167,34 @@ int Engine::wm_loss_backward(cudaStream_t s) {
   // reverse-time scan: only input gradients on the recurrence
   // (as in the forward pass: at XL the weights no longer fit L2 and the per-op path on the weight-streaming kernels of
   //  dv3_gemv.cu is faster - C5 62.0 vs 72.7 ms per update; at L the persistent kernel still wins, 40.6 vs 42.8 ms)
-  if (use_persistent && scan_bwd_ctas > 0 && G <= 2048) {
+  ScanTcWeightsBwd twb{};
+  bool use_tc_bwd = false;
+  if (use_persistent && scan_tc_ctas > 0 && scan_tc_supported(B, G, D, Z, Zk) && std::getenv("DV3_NO_SCAN_TC_BWD") == nullptr) {
+    twb.Wzq = shadow_n(post_repr.w, &twb.ld_Wzq);
+    twb.Wpost_h = shadow_n(Wp.w + (size_t)E * D, &twb.ld_Wpost_h);
+    twb.U = shadow_n(gru_U, &twb.ld_U);
+    twb.K = shadow_n(gru_K, &twb.ld_K);
+    twb.Wpre_z = shadow_n(Wx.w, &twb.ld_Wpre_z);
+    use_tc_bwd = twb.Wzq && twb.Wpost_h && twb.U && twb.K && twb.Wpre_z;
+  }
+  if (use_tc_bwd) {
+    // tensor-core mode, S ... XL: one persistent kernel streams the plain bf16 weight shadows through tcgen05 (dv3_scan_tc.cu)
+    cudaMemsetAsync(dp_act_all, 0, (size_t)N * D * 4, s);
+    cudaMemsetAsync(du_all, 0, (size_t)N * D * 4, s);
+    cudaMemsetAsync(dh_in, 0, (size_t)N * G * 4, s);
+    ScanBwdParams bp{};
+    bp.B = B; bp.T = T; bp.G = G; bp.D = D; bp.Z = Z; bp.Zc = Zc; bp.Zk = Zk;
+    bp.post_g = Wp.g; bp.post_b = Wp.b; bp.pre_g = Wx.g; bp.pre_b = Wx.b;
+    bp.is_first = in_is_first; bp.post_logits = post_logits; bp.dpost = dpost; bp.p_pre = p_pre; bp.p_mean = p_mean;
+    bp.p_rstd = p_rstd; bp.gates = gx; bp.gh = gh; bp.h_in = h_in; bp.x_pre = x_pre; bp.x_mean = x_mean; bp.x_rstd = x_rstd;
+    bp.d_hz = d_hz; bp.dlogits = dpost_logits; bp.dp_act = dp_act_all; bp.dp_pre = dp_pre; bp.dh_tot = dh_tot;
+    bp.dgx = dgx; bp.dgh = dgh; bp.dh_in = dh_in; bp.du = du_all; bp.dx_pre = dx_pre; bp.bar = scan_bar + 32;
+    bp.stamps = std::getenv("DV3_SCAN_STAMPS") ? scan_stamps : nullptr;
+    cudaError_t ce = launch_observe_scan_tc_bwd(s, bp, twb, scan_tc_ctas);
+    if (ce != cudaSuccess) return fail(std::string("observe scan bwd (tensor-core) launch: ") + cudaGetErrorString(ce));
+    ln_silu_bwd(s, dp_act_all, D, p_pre, D, p_mean, p_rstd, Wp.g, Wp.b, nullptr, 0, Wp.dg, Wp.db, 1, N, D);
+    ln_silu_bwd(s, du_all, D, x_pre, D, x_mean, x_rstd, Wx.g, Wx.b, nullptr, 0, Wx.dg, Wx.db, 1, N, D);
+  } else if (use_persistent && scan_bwd_ctas > 0 && G <= 2048) {
     transpose_f32(s, post_repr.w, Wt_zq, D, Z);
     transpose_f32(s, Wp.w + (size_t)E * D, Wt_post_h, G, D);
     transpose_f32(s, gru_U, Ut, G, 3 * G);

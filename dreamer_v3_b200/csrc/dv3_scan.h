@@ -82,8 +82,18 @@ struct ScanTcWeights {
   const void* Wpost_h_t; int ld_Wpost_h_t;  // h-part of W_post^T      [D, G] (row stride E + G)
   const void* Wzq_t; int ld_Wzq_t;          // posterior representation layer^T [Z, D]
 };
-bool scan_tc_supported(const ScanFwdParams& p);
+// plain bf16 shadows ([out, in] row-major) for the transposed contractions of the backward scan
+struct ScanTcWeightsBwd {
+  const void* Wzq; int ld_Wzq;          // [D, Z]
+  const void* Wpost_h; int ld_Wpost_h;  // rows E.. of W_post: [G, D]
+  const void* U; int ld_U;              // [G, 3G]
+  const void* K; int ld_K;              // [D, 3G]
+  const void* Wpre_z; int ld_Wpre_z;    // rows 0..Z of W_pre: [Z, D]
+};
+bool scan_tc_supported(int B, int G, int D, int Z, int Zk);
 int scan_tc_max_ctas(int device);
 cudaError_t launch_observe_scan_tc(cudaStream_t s, const ScanFwdParams& p, const ScanTcWeights& w, float* gx_acc, int ctas);
+// q.dp_act, q.du and q.dh_in must be zero on entry (accumulators); q.d_hz holds the head / prior gradients
+cudaError_t launch_observe_scan_tc_bwd(cudaStream_t s, const ScanBwdParams& q, const ScanTcWeightsBwd& w, int ctas);
 
 }  // namespace dv3

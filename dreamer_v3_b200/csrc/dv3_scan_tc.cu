@@ -48,19 +48,27 @@ constexpr int kWBytes = 128 * 128;   // one weight k-block
 
 struct TcProblem { int n_out, K, tiles, kblocks, kc, span, unit_begin, units; };
 
-struct TcMaps { CUtensorMap m[4]; };
+constexpr int kMaxProb = 5, kMaxStages = 4;
+struct TcMaps { CUtensorMap m[kMaxProb]; };
 
+// forward: problems 0 gx (K = D), 1 gh (K = G) | 2 posterior h-part (K = G) | 3 posterior logits (K = D)   + sampling stage
+// backward: 0 dp_act (K = Z) | 1 dh (K = D) | 2 dh_in (K = 3G), 3 du (K = 3G) | 4 dz_in (K = D)
 struct ScanTcParams {
-  ScanFwdParams p;
-  float* gx_acc;        // [B, T, 3G], pre-filled with b0; p.gh is pre-filled with b1, p.post_logits with b_zq, p.x_pre with actW
-  TcProblem prob[4];    // 0: gx (K = D), 1: gh (K = G), 2: posterior h-part (K = G), 3: posterior logits (K = D)
-  int stage_units[3];
+  ScanFwdParams p;      // forward tensors (unused by the backward kernel)
+  ScanBwdParams q;      // backward tensors (unused by the forward kernel)
+  float* gx_acc;        // forward: [B, T, 3G], pre-filled with b0; p.gh is pre-filled with b1, p.post_logits with b_zq, p.x_pre with actW
+  TcProblem prob[kMaxProb];
+  int stage_units[kMaxStages], stage_p0[kMaxStages], stage_np[kMaxStages];
+  int B, T;
+  unsigned int* bar;
+  unsigned long long* stamps;   // optional globaltimer stamps of CTA 0 after every grid barrier (profiling), may be null
 };
 
 struct TcSmem {
   unsigned char ring[kRing][kWBytes];
   unsigned char bbuf[kSlots][kMaxKc][kKbBytes];
-  float stats[kRows][2];
+  float stats[kRows][2];    // forward: LayerNorm mean / rstd of the row; backward: m1, m2 of the LayerNorm backward
+  float stats2[kRows][2];   // backward: saved mean / rstd of the row
   uint64_t full[kRing], empty[kRing], acc_full[2], acc_empty[2], b_ready;
   uint32_t tmem_base;
 };
@@ -150,8 +158,8 @@ struct SegIter {
   }
   __device__ bool next(const ScanTcParams& P, Seg& s) {
     if (u >= u_end) return false;
-    int pr = stage == 0 ? 0 : stage + 1;
-    if (stage == 0 && u >= P.prob[1].unit_begin) pr = 1;
+    int pr = P.stage_p0[stage];
+    if (P.stage_np[stage] > 1 && u >= P.prob[pr + 1].unit_begin) ++pr;
     const TcProblem& q = P.prob[pr];
     const int local = u - q.unit_begin;
     const int chunk = local / q.span, r = local - chunk * q.span;
@@ -245,108 +253,350 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
-
-// Stages activation k-block `kb` (absolute, 64 k) of problem `prob` at step t as the bf16 K-major SWIZZLE_128B B operand.
-// Worker thread wt: row = wt / 8, 16-byte chunk (8 k) = wt % 8. `writer`: this CTA owns tile 0 of the k-block and stores the
-// fp32 values for the backward pass.
-__device__ __forceinline__ void stage_kb(const ScanTcParams& P, TcSmem& sm, unsigned char* dst, int prob, int kb, int t, bool writer, int wt) {
-  const ScanFwdParams& p = P.p;
-  const int b = wt >> 3, c8 = wt & 7, k = kb * 64 + c8 * 8;
-  const int T = p.T, G = p.G, D = p.D;
-  float v[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = 0.f;
-  if (b < p.B) {
-    const size_t bt = (size_t)b * T + t;
-    if (prob == 0 || prob == 3) {   // SiLU(LayerNorm(x)) of the pre-GRU (0) / posterior (3) layer
-      const float* x = (prob == 0 ? p.x_pre : p.p_pre) + bt * D + k;
-      float g[8], be[8];
-      load8(v, x);
-      load8_ro(g, (prob == 0 ? p.pre_g : p.post_g) + k);
-      load8_ro(be, (prob == 0 ? p.pre_b : p.post_b) + k);
-      const float mean = sm.stats[b][0], rstd = sm.stats[b][1];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * g[i] + be[i];
-      silu8(v);
-      if (writer) {
-        store8((prob == 0 ? p.u_act : p.p_act) + bt * D + k, v);
-        if (kb == 0 && c8 == 0) {
-          (prob == 0 ? p.x_mean : p.p_mean)[bt] = mean;
-          (prob == 0 ? p.x_rstd : p.p_rstd)[bt] = rstd;
-        }
-      }
-    } else if (prob == 1) {          // masked recurrent input h_in (world_model.py:246-247)
-      const bool first = (t == 0) || (p.is_first[bt] != 0.f);
-      if (first) load8_ro(v, p.h0 + k);
-      else load8(v, p.hz + (bt - 1) * (G + p.Z) + k);
-      if (writer) store8(p.h_in + bt * G + k, v);
-    } else {                         // h_t = GRU cell (Keras reset_after; gx / gh already hold their biases)
-      const float* gx = P.gx_acc + bt * 3 * G + k;
-      const float* gh = p.gh + bt * 3 * G + k;
-      float xz[8], xr[8], xc[8], hz_[8], hr[8], hc[8], hin[8];
-      load8(xz, gx); load8(xr, gx + G); load8(xc, gx + 2 * G);
-      load8(hz_, gh); load8(hr, gh + G); load8(hc, gh + 2 * G);
-      const bool first = (t == 0) || (p.is_first[bt] != 0.f);
-      if (first) load8_ro(hin, p.h0 + k);
-      else load8(hin, p.hz + (bt - 1) * (G + p.Z) + k);
-      float z[8], r[8], c[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        z[i] = sigmoid_fast(xz[i] + hz_[i]);
-        r[i] = sigmoid_fast(xr[i] + hr[i]);
-        c[i] = tanh_fast(xc[i] + r[i] * hc[i]);
-        v[i] = z[i] * hin[i] + (1.f - z[i]) * c[i];
-      }
-      if (writer) {
-        float* gt = p.gates + bt * 3 * G + k;
-        store8(gt, z); store8(gt + G, r); store8(gt + 2 * G, c);
-        store8(p.hz + bt * (G + p.Z) + k, v);
-      }
-    }
-  }
+// writes 8 staged values (row b, 16-byte chunk c8 of a 64-k block) as bf16 into the K-major SWIZZLE_128B B-operand block
+__device__ __forceinline__ void put_b(unsigned char* dst, int b, int c8, const float (&v)[8]) {
   const uint32_t a = smem_u32(dst) + (uint32_t)((b >> 3) * 1024 + (b & 7) * 128 + ((c8 ^ (b & 7)) << 4));
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16(v[0], v[1])), "r"(pack_bf16(v[2], v[3])),
                "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7])) : "memory");
 }
 
-// one (row, categorical) of stage S4 per warp; also used for the prologue (t = -1: only the gather of step 0)
-__device__ __forceinline__ void sample_and_gather(const ScanTcParams& P, int b, int cat, int t, int lane) {
-  const ScanFwdParams& p = P.p;
-  const int T = p.T, G = p.G, D = p.D, Z = p.Z, Zc = p.Zc, Zk = p.Zk, W = G + Z;
-  int pick = 0;
-  if (t >= 0) {
-    const size_t bt = (size_t)b * T + t;
-    const bool act = lane < Zk;
-    const float l = act ? __ldcg(p.post_logits + bt * Z + cat * Zk + lane) : -INFINITY;
-    const float mx = warp_max(l);
-    const float ex = act ? expf(l - mx) : 0.f;
-    const float s = warp_sum(ex);
-    const float pu = 0.99f * (ex / s) + 0.01f * (1.0f / (float)Zk);
-    if (act) p.post_probs[bt * Z + cat * Zk + lane] = pu;
-    pick = categorical_pick(pu, act, Zk, p.u_post[((size_t)t * p.B + b) * Zc + cat], lane);
-    if (lane == 0) p.z_idx[bt * Zc + cat] = pick;
-    if (act) p.hz[bt * W + G + cat * Zk + lane] = (lane == pick) ? 1.f : 0.f;
+// =====================================================================================================================
+// Forward policy (world_model.py:244-273)
+// =====================================================================================================================
+struct FwdPolicy {
+  static constexpr int kGemmStages = 3;
+  static constexpr bool kExtraStage = true;
+  __device__ static int time_of(const ScanTcParams& P, int i) { return i; }
+  __device__ static bool needs_stats(int prob) { return prob == 0 || prob == 3; }
+  __device__ static void stats(const ScanTcParams& P, TcSmem& sm, int prob, int t, int ww, int lane) {
+    row_stats(sm, prob == 0 ? P.p.x_pre : P.p.p_pre, P.T, t, P.B, P.p.D, ww, lane);
   }
-  if (t + 1 < T) {   // masked z input of the next step (world_model.py:249-250) and its row of the pre-GRU layer
-    const size_t bn = (size_t)b * T + t + 1;
-    const bool first = (t + 1 == 0) || (p.is_first[bn] != 0.f);
-    const int idx = first ? p.z0_idx[cat] : pick;
-    if (lane < Zk) p.z_in[bn * Z + cat * Zk + lane] = (lane == idx) ? 1.f : 0.f;
-    const float* wrow = p.W_pre + (size_t)(cat * Zk + idx) * D;
-    float* xrow = p.x_pre + bn * D;
-    for (int j = lane * 4; j < D; j += 128) red_add_v4(xrow + j, __ldg(reinterpret_cast<const float4*>(wrow + j)));
-  }
-}
 
-__global__ void __launch_bounds__(kThreadsTc, 1) observe_scan_tc_kernel(const __grid_constant__ TcMaps maps, const ScanTcParams P) {
+  // Stages activation k-block `kb` (absolute, 64 k) of problem `prob` at step t as the bf16 K-major SWIZZLE_128B B operand.
+  // Worker thread wt: row = wt / 8, 16-byte chunk (8 k) = wt % 8. `writer`: this CTA owns tile 0 of the k-block and stores the
+  // fp32 values for the backward pass.
+  __device__ static void stage_kb(const ScanTcParams& P, TcSmem& sm, unsigned char* dst, int prob, int kb, int t, bool writer, int wt) {
+    const ScanFwdParams& p = P.p;
+    const int b = wt >> 3, c8 = wt & 7, k = kb * 64 + c8 * 8;
+    const int T = p.T, G = p.G, D = p.D;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (b < p.B) {
+      const size_t bt = (size_t)b * T + t;
+      if (prob == 0 || prob == 3) {   // SiLU(LayerNorm(x)) of the pre-GRU (0) / posterior (3) layer
+        const float* x = (prob == 0 ? p.x_pre : p.p_pre) + bt * D + k;
+        float g[8], be[8];
+        load8(v, x);
+        load8_ro(g, (prob == 0 ? p.pre_g : p.post_g) + k);
+        load8_ro(be, (prob == 0 ? p.pre_b : p.post_b) + k);
+        const float mean = sm.stats[b][0], rstd = sm.stats[b][1];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * g[i] + be[i];
+        silu8(v);
+        if (writer) {
+          store8((prob == 0 ? p.u_act : p.p_act) + bt * D + k, v);
+          if (kb == 0 && c8 == 0) {
+            (prob == 0 ? p.x_mean : p.p_mean)[bt] = mean;
+            (prob == 0 ? p.x_rstd : p.p_rstd)[bt] = rstd;
+          }
+        }
+      } else if (prob == 1) {          // masked recurrent input h_in (world_model.py:246-247)
+        const bool first = (t == 0) || (p.is_first[bt] != 0.f);
+        if (first) load8_ro(v, p.h0 + k);
+        else load8(v, p.hz + (bt - 1) * (G + p.Z) + k);
+        if (writer) store8(p.h_in + bt * G + k, v);
+      } else {                         // h_t = GRU cell (Keras reset_after; gx / gh already hold their biases)
+        const float* gx = P.gx_acc + bt * 3 * G + k;
+        const float* gh = p.gh + bt * 3 * G + k;
+        float xz[8], xr[8], xc[8], hz_[8], hr[8], hc[8], hin[8];
+        load8(xz, gx); load8(xr, gx + G); load8(xc, gx + 2 * G);
+        load8(hz_, gh); load8(hr, gh + G); load8(hc, gh + 2 * G);
+        const bool first = (t == 0) || (p.is_first[bt] != 0.f);
+        if (first) load8_ro(hin, p.h0 + k);
+        else load8(hin, p.hz + (bt - 1) * (G + p.Z) + k);
+        float z[8], r[8], c[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          z[i] = sigmoid_fast(xz[i] + hz_[i]);
+          r[i] = sigmoid_fast(xr[i] + hr[i]);
+          c[i] = tanh_fast(xc[i] + r[i] * hc[i]);
+          v[i] = z[i] * hin[i] + (1.f - z[i]) * c[i];
+        }
+        if (writer) {
+          float* gt = p.gates + bt * 3 * G + k;
+          store8(gt, z); store8(gt + G, r); store8(gt + 2 * G, c);
+          store8(p.hz + bt * (G + p.Z) + k, v);
+        }
+      }
+    }
+    put_b(dst, b, c8, v);
+  }
+
+  // accumulator column n (= weight row) of problem `prob`: r[b] for the 16 batch rows -> out[b, t, n]
+  __device__ static void epilogue(const ScanTcParams& P, int prob, int t, int n, const uint32_t (&r)[16]) {
+    const ScanFwdParams& p = P.p;
+    const TcProblem& q = P.prob[prob];
+    float* out = prob == 0 ? P.gx_acc : prob == 1 ? p.gh : prob == 2 ? p.p_pre : p.post_logits;
+    float* o = out + (size_t)t * q.n_out + n;
+    const size_t ldo = (size_t)p.T * q.n_out;
+#pragma unroll
+    for (int b = 0; b < kRows; ++b)
+      if (b < p.B) red_add(o + (size_t)b * ldo, __uint_as_float(r[b]));
+  }
+
+  // one (row, categorical) of stage S4 per warp; t = -1: the prologue (only the gather of step 0)
+  __device__ static void sample_and_gather(const ScanTcParams& P, int b, int cat, int t, int lane) {
+    const ScanFwdParams& p = P.p;
+    const int T = p.T, G = p.G, D = p.D, Z = p.Z, Zc = p.Zc, Zk = p.Zk, W = G + Z;
+    int pick = 0;
+    if (t >= 0) {
+      const size_t bt = (size_t)b * T + t;
+      const bool act = lane < Zk;
+      const float l = act ? __ldcg(p.post_logits + bt * Z + cat * Zk + lane) : -INFINITY;
+      const float mx = warp_max(l);
+      const float ex = act ? expf(l - mx) : 0.f;
+      const float s = warp_sum(ex);
+      const float pu = 0.99f * (ex / s) + 0.01f * (1.0f / (float)Zk);
+      if (act) p.post_probs[bt * Z + cat * Zk + lane] = pu;
+      pick = categorical_pick(pu, act, Zk, p.u_post[((size_t)t * p.B + b) * Zc + cat], lane);
+      if (lane == 0) p.z_idx[bt * Zc + cat] = pick;
+      if (act) p.hz[bt * W + G + cat * Zk + lane] = (lane == pick) ? 1.f : 0.f;
+    }
+    if (t + 1 < T) {   // masked z input of the next step (world_model.py:249-250) and its row of the pre-GRU layer
+      const size_t bn = (size_t)b * T + t + 1;
+      const bool first = (t + 1 == 0) || (p.is_first[bn] != 0.f);
+      const int idx = first ? p.z0_idx[cat] : pick;
+      if (lane < Zk) p.z_in[bn * Z + cat * Zk + lane] = (lane == idx) ? 1.f : 0.f;
+      const float* wrow = p.W_pre + (size_t)(cat * Zk + idx) * D;
+      float* xrow = p.x_pre + bn * D;
+      for (int j = lane * 4; j < D; j += 128) red_add_v4(xrow + j, __ldg(reinterpret_cast<const float4*>(wrow + j)));
+    }
+  }
+  __device__ static void extra(const ScanTcParams& P, int t, int gwarp, int nwarps, int lane) {
+    const int ntask = P.B * P.p.Zc;
+    for (int task = gwarp; task < ntask; task += nwarps) sample_and_gather(P, task / P.p.Zc, task % P.p.Zc, t, lane);
+  }
+  __device__ static void prologue(const ScanTcParams& P, int gwarp, int nwarps, int lane) { extra(P, -1, gwarp, nwarps, lane); }
+};
+
+// =====================================================================================================================
+// Backward policy: reverse-time BPTT of the same scan (input gradients only; every weight gradient is one N-row contraction
+// after the kernel). Per step t = T-1 ... 0, 4 stages:
+//   B1  dp_act += dlogits . W_zq^T        dlogits = softmax-backward(0.99 (dz_t + dKL/dpost)), formed by the consumer
+//   B2  dh_t   += dp_pre . W_post[E:]^T   dp_pre = LayerNorm+SiLU backward of dp_act (row sums recomputed per CTA)
+//   B3  dh_in  += dgh . U^T,  du += dgx . K^T      (dgx, dgh) = GRU-cell backward of dh_t; dh_in also gets dh_t * z
+//   B4  dz_in  = dx_pre . W_pre[:Z]^T     dx_pre = LayerNorm+SiLU backward of du
+// dh_in and dz_in are passed to step t-1 in the epilogues: d_hz[t-1] += (1 - is_first[t]) * (dh_in | dz_in).
+// Weight operands: the plain bf16 shadows ([out, in] row-major = K-major for these transposed contractions).
+// =====================================================================================================================
+struct BwdPolicy {
+  static constexpr int kGemmStages = 4;
+  static constexpr bool kExtraStage = false;
+  __device__ static int time_of(const ScanTcParams& P, int i) { return P.T - 1 - i; }
+  __device__ static bool needs_stats(int prob) { return prob == 1 || prob == 4; }
+
+  // row sums of the LayerNorm backward: m1 = mean_k(dn g), m2 = mean_k(dn g xhat), dn = dy * silu'(n); two rows per round
+  template <int EPL>
+  __device__ static void ln_bwd_stats_t(const ScanTcParams& P, TcSmem& sm, const float* dy, const float* x, const float* mean_in,
+                                        const float* rstd_in, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        int t, int ww, int lane) {
+    const int T = P.T, B = P.B, D = P.q.D;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      float4 xv[2][EPL], dv[2][EPL];
+      float mean[2], rstd[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int b = ww * 4 + half * 2 + r;
+        const size_t bt = (size_t)(b < B ? b : 0) * T + t;
+        mean[r] = mean_in[bt]; rstd[r] = rstd_in[bt];
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+          const size_t off = bt * D + (size_t)(lane + 32 * i) * 4;
+          xv[r][i] = ldcg4(x + off);
+          dv[r][i] = b < B ? ldcg4(dy + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float xs[4] = {xv[r][i].x, xv[r][i].y, xv[r][i].z, xv[r][i].w};
+          const float ds[4] = {dv[r][i].x, dv[r][i].y, dv[r][i].z, dv[r][i].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float xhat = (xs[j] - mean[r]) * rstd[r];
+            const float n = xhat * g[j] + be[j];
+            const float sg = sigmoid_fast(n);
+            const float dng = ds[j] * (sg * (1.f + n * (1.f - sg))) * g[j];
+            s1[r] += dng; s2[r] += dng * xhat;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) { s1[r] += __shfl_xor_sync(0xffffffffu, s1[r], o); s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o); }
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int b = ww * 4 + half * 2 + r;
+          sm.stats[b][0] = s1[r] / (float)D; sm.stats[b][1] = s2[r] / (float)D;
+          sm.stats2[b][0] = mean[r]; sm.stats2[b][1] = rstd[r];
+        }
+      }
+    }
+  }
+  __device__ static void stats(const ScanTcParams& P, TcSmem& sm, int prob, int t, int ww, int lane) {
+    const ScanBwdParams& q = P.q;
+    const float* dy = prob == 1 ? q.dp_act : q.du;
+    const float* x = prob == 1 ? q.p_pre : q.x_pre;
+    const float* mi = prob == 1 ? q.p_mean : q.x_mean;
+    const float* ri = prob == 1 ? q.p_rstd : q.x_rstd;
+    const float* g = prob == 1 ? q.post_g : q.pre_g;
+    const float* be = prob == 1 ? q.post_b : q.pre_b;
+    switch (q.D / 128) {
+      case 4: ln_bwd_stats_t<4>(P, sm, dy, x, mi, ri, g, be, t, ww, lane); break;
+      case 5: ln_bwd_stats_t<5>(P, sm, dy, x, mi, ri, g, be, t, ww, lane); break;
+      case 6: ln_bwd_stats_t<6>(P, sm, dy, x, mi, ri, g, be, t, ww, lane); break;
+      default: ln_bwd_stats_t<8>(P, sm, dy, x, mi, ri, g, be, t, ww, lane); break;
+    }
+  }
+
+  __device__ static void stage_kb(const ScanTcParams& P, TcSmem& sm, unsigned char* dst, int prob, int kb, int t, bool writer, int wt) {
+    const ScanBwdParams& q = P.q;
+    const int b = wt >> 3, c8 = wt & 7, k = kb * 64 + c8 * 8;
+    const int T = P.T, G = q.G, D = q.D, Z = q.Z, W = G + Z;
+    const bool row_ok = b < P.B;
+    const size_t bt = (size_t)(row_ok ? b : 0) * T + t;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (prob == 0) {
+      // dlogits of the posterior categorical (representation_layer.py:73-113 backward): 4 neighbouring threads hold the 32
+      // classes of one categorical (Zk = 32); straight-through dz + KL dprobs, through the 1 % unimix and the softmax
+      float l[8], g[8];
+      load8(l, q.post_logits + bt * Z + k);
+      {
+        float dz[8], dk[8];
+        load8(dz, q.d_hz + bt * W + G + k);
+        load8(dk, q.dpost + bt * Z + k);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = 0.99f * (dz[i] + dk[i]);
+      }
+      float mx = l[0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) mx = fmaxf(mx, l[i]);
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float e[8], s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { e[i] = expf(l[i] - mx); s += e[i]; }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      const float inv = 1.f / s;
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { e[i] *= inv; dot += g[i] * e[i]; }
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = row_ok ? e[i] * (g[i] - dot) : 0.f;
+      if (writer && row_ok) store8(q.dlogits + bt * Z + k, v);
+    } else if (prob == 1 || prob == 4) {
+      // LayerNorm + SiLU backward of the posterior (1) / pre-GRU (4) layer
+      const float* dy = (prob == 1 ? q.dp_act : q.du) + bt * D + k;
+      const float* x = (prob == 1 ? q.p_pre : q.x_pre) + bt * D + k;
+      float d[8], xv[8], g[8], be[8];
+      load8(d, dy); load8(xv, x);
+      load8_ro(g, (prob == 1 ? q.post_g : q.pre_g) + k);
+      load8_ro(be, (prob == 1 ? q.post_b : q.pre_b) + k);
+      const float m1 = sm.stats[b][0], m2 = sm.stats[b][1], mean = sm.stats2[b][0], rstd = sm.stats2[b][1];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xhat = (xv[i] - mean) * rstd;
+        const float n = xhat * g[i] + be[i];
+        const float sg = sigmoid_fast(n);
+        const float dng = d[i] * (sg * (1.f + n * (1.f - sg))) * g[i];
+        v[i] = row_ok ? rstd * (dng - m1 - xhat * m2) : 0.f;
+      }
+      if (writer && row_ok) store8((prob == 1 ? q.dp_pre : q.dx_pre) + bt * D + k, v);
+    } else {
+      // GRU-cell backward (Keras reset_after); k runs over the 3G gate columns (z | r | c)
+      const int gate = k / G, u = k - gate * G;
+      float d[8], z[8], r[8], c[8], hh[8], hp[8];
+      load8(d, q.d_hz + bt * W + u);
+      const float* gt = q.gates + bt * 3 * G + u;
+      load8(z, gt); load8(r, gt + G); load8(c, gt + 2 * G);
+      load8(hh, q.gh + bt * 3 * G + 2 * G + u);
+      load8(hp, q.h_in + bt * G + u);
+      float dzg[8], drg[8], dcg[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        dzg[i] = d[i] * (hp[i] - c[i]) * z[i] * (1.f - z[i]);
+        dcg[i] = d[i] * (1.f - z[i]) * (1.f - c[i] * c[i]);
+        drg[i] = dcg[i] * hh[i] * r[i] * (1.f - r[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float val = gate == 0 ? dzg[i] : gate == 1 ? drg[i] : (prob == 2 ? dcg[i] * r[i] : dcg[i]);
+        v[i] = row_ok ? val : 0.f;
+      }
+      if (writer && row_ok) {
+        store8((prob == 2 ? q.dgh : q.dgx) + bt * 3 * G + k, v);
+        if (prob == 2 && gate == 0) {   // the direct path dh_in += dh * z (and on to step t-1 unless the row restarts at t)
+          const float keep = (t > 0 && q.is_first[bt] == 0.f) ? 1.f : 0.f;
+          float4 a = make_float4(d[0] * z[0], d[1] * z[1], d[2] * z[2], d[3] * z[3]);
+          float4 c4 = make_float4(d[4] * z[4], d[5] * z[5], d[6] * z[6], d[7] * z[7]);
+          red_add_v4(q.dh_in + bt * G + u, a); red_add_v4(q.dh_in + bt * G + u + 4, c4);
+          if (keep != 0.f) { red_add_v4(q.d_hz + (bt - 1) * W + u, a); red_add_v4(q.d_hz + (bt - 1) * W + u + 4, c4); }
+        }
+      }
+    }
+    put_b(dst, b, c8, v);
+  }
+
+  __device__ static void epilogue(const ScanTcParams& P, int prob, int t, int n, const uint32_t (&r)[16]) {
+    const ScanBwdParams& q = P.q;
+    const int T = P.T, G = q.G, D = q.D, Z = q.Z, W = G + Z;
+#pragma unroll
+    for (int b = 0; b < kRows; ++b) {
+      if (b >= P.B) continue;
+      const size_t bt = (size_t)b * T + t;
+      const float val = __uint_as_float(r[b]);
+      if (prob == 0) red_add(q.dp_act + bt * D + n, val);
+      else if (prob == 1) red_add(q.d_hz + bt * W + n, val);
+      else if (prob == 3) red_add(q.du + bt * D + n, val);
+      else {
+        const bool keep = t > 0 && q.is_first[bt] == 0.f;
+        if (prob == 2) {
+          red_add(q.dh_in + bt * G + n, val);
+          if (keep) red_add(q.d_hz + (bt - 1) * W + n, val);
+        } else if (keep) {
+          red_add(q.d_hz + (bt - 1) * W + G + n, val);
+        }
+      }
+    }
+  }
+  __device__ static void extra(const ScanTcParams&, int, int, int, int) {}
+  __device__ static void prologue(const ScanTcParams&, int, int, int) {}
+};
+
+template <class Pol>
+__global__ void __launch_bounds__(kThreadsTc, 1) scan_tc_kernel(const __grid_constant__ TcMaps maps, const ScanTcParams P) {
   extern __shared__ unsigned char smem_raw[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const ScanFwdParams& p = P.p;
-  const int T = p.T;
+  const int T = P.T;
 
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i]) : "memory");
+    for (int i = 0; i < kMaxProb; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i]) : "memory");
     for (int s = 0; s < kRing; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&sm.acc_full[s], 1); mbar_init(&sm.acc_empty[s], kWorkers); }
     mbar_init(&sm.b_ready, 1);
@@ -365,8 +615,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) observe_scan_tc_kernel(const __
     // ---------------- TMA producer: the whole weight stream of all T steps, throttled only by the ring ----------------
     if (lane == 0) {
       uint32_t it = 0;
-      for (int t = 0; t < T; ++t)
-        for (int st = 0; st < 3; ++st) {
+      for (int i = 0; i < T; ++i)
+        for (int st = 0; st < Pol::kGemmStages; ++st) {
           SegIter si(P, st);
           Seg s;
           while (si.next(P, s)) {
@@ -385,8 +635,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) observe_scan_tc_kernel(const __
     if (lane == 0) {
       const uint32_t idesc = make_idesc16();
       uint32_t it = 0, acc_it = 0, bphase = 0;
-      for (int t = 0; t < T; ++t)
-        for (int st = 0; st < 3; ++st) {
+      for (int i = 0; i < T; ++i)
+        for (int st = 0; st < Pol::kGemmStages; ++st) {
           SegIter si(P, st);
           SlotMap slots;
           Seg s;
@@ -432,26 +682,36 @@ __global__ void __launch_bounds__(kThreadsTc, 1) observe_scan_tc_kernel(const __
     unsigned int bar_target = 0;
     uint32_t acc_it = 0;
     const int gwarp = blockIdx.x * 4 + ww, nwarps = gridDim.x * 4;
-    const int ntask = p.B * p.Zc;
-    // prologue: every row starts from the learned initial state: x_pre[0] += gather of z0, z_in[0] = z0
-    for (int task = gwarp; task < ntask; task += nwarps) sample_and_gather(P, task / p.Zc, task % p.Zc, -1, lane);
-    grid_bar_workers(p.bar, bar_target, wt);
+    int n_stamp = 0;
+    auto stamp = [&]() {
+      if (P.stamps != nullptr && blockIdx.x == 0 && wt == 0) {
+        unsigned long long v;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
+        P.stamps[n_stamp] = v;
+      }
+      ++n_stamp;
+    };
+    Pol::prologue(P, gwarp, nwarps, lane);
+    grid_bar_workers(P.bar, bar_target, wt);
+    stamp();
 
-    for (int t = 0; t < T; ++t) {
-      for (int st = 0; st < 3; ++st) {
+    for (int i = 0; i < T; ++i) {
+      const int t = Pol::time_of(P, i);
+      for (int st = 0; st < Pol::kGemmStages; ++st) {
         // ---- stage the B operand of every segment of this CTA ----
         {
           SegIter si(P, st);
           SlotMap slots;
           Seg s;
           unsigned int staged[kSlots] = {0u, 0u};
-          bool any = false, have_stats = false;
+          bool any = false;
+          int stats_of = -1;
           while (si.next(P, s)) {
             any = true;
-            if ((s.prob == 0 || s.prob == 3) && !have_stats) {
-              row_stats(sm, s.prob == 0 ? p.x_pre : p.p_pre, T, t, p.B, p.D, ww, lane);
+            if (Pol::needs_stats(s.prob) && stats_of != s.prob) {
+              Pol::stats(P, sm, s.prob, t, ww, lane);
               worker_sync();
-              have_stats = true;
+              stats_of = s.prob;
             }
             bool fresh;
             const int sl = slots.get(s, fresh);
@@ -460,7 +720,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) observe_scan_tc_kernel(const __
             for (int kb = s.kb0; kb < s.kb1; ++kb) {
               if (staged[sl] & (1u << kb)) continue;
               staged[sl] |= 1u << kb;
-              stage_kb(P, sm, sm.bbuf[sl][kb], s.prob, s.chunk * q.kc + kb, t, s.tile == 0, wt);
+              Pol::stage_kb(P, sm, sm.bbuf[sl][kb], s.prob, s.chunk * q.kc + kb, t, s.tile == 0, wt);
             }
           }
           if (any) {
@@ -469,7 +729,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) observe_scan_tc_kernel(const __
             if (wt == 0) mbar_arrive(&sm.b_ready);
           }
         }
-        // ---- epilogue of every segment: TMEM [128 weight rows x 16 batch rows] -> red.global into out[b, t, n] ----
+        // ---- epilogue of every segment: TMEM [128 weight rows x 16 batch rows] -> red.global ----
         {
           SegIter si(P, st);
           Seg s;
@@ -489,23 +749,18 @@ __global__ void __launch_bounds__(kThreadsTc, 1) observe_scan_tc_kernel(const __
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&sm.acc_empty[as]);
             ++acc_it;
-            const TcProblem& q = P.prob[s.prob];
-            float* out = s.prob == 0 ? P.gx_acc : s.prob == 1 ? p.gh : s.prob == 2 ? p.p_pre : p.post_logits;
             const int n = s.tile * 128 + q4 * 32 + lane;
-            if (n < q.n_out) {
-              float* o = out + (size_t)t * q.n_out + n;
-              const size_t ldo = (size_t)T * q.n_out;
-#pragma unroll
-              for (int b = 0; b < kRows; ++b)
-                if (b < p.B) red_add(o + (size_t)b * ldo, __uint_as_float(r[b]));
-            }
+            if (n < P.prob[s.prob].n_out) Pol::epilogue(P, s.prob, t, n, r);
           }
         }
-        grid_bar_workers(p.bar, bar_target, wt);
+        grid_bar_workers(P.bar, bar_target, wt);
+        stamp();
       }
-      // ---- S4: sample z_t, feed the pre-GRU layer of step t+1 ----
-      for (int task = gwarp; task < ntask; task += nwarps) sample_and_gather(P, task / p.Zc, task % p.Zc, t, lane);
-      grid_bar_workers(p.bar, bar_target, wt);
+      if (Pol::kExtraStage) {
+        Pol::extra(P, t, gwarp, nwarps, lane);
+        grid_bar_workers(P.bar, bar_target, wt);
+        stamp();
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -560,61 +815,97 @@ int pick_kc(int kblocks) {
   return 1;
 }
 
+// problem table + stage table + tensor maps; false when a CTA's range of some stage could touch more than kSlots chunks
+bool build_schedule(ScanTcParams& P, TcMaps& maps, int nprob, const int* n_out, const int* K, const void* const* ptr, const int* ld,
+                    int nstage, const int* stage_p0, const int* stage_np, int ctas) {
+  for (int i = 0; i < kMaxProb; ++i) maps.m[i] = maps.m[0];
+  for (int i = 0; i < nprob; ++i) {
+    TcProblem& q = P.prob[i];
+    q.n_out = n_out[i]; q.K = K[i]; q.tiles = n_out[i] / 128; q.kblocks = K[i] / 64; q.kc = pick_kc(q.kblocks);
+    q.span = q.tiles * q.kc; q.units = q.tiles * q.kblocks; q.unit_begin = 0;
+    if (!make_wmap(&maps.m[i], ptr[i], n_out[i], K[i], ld[i])) return false;
+  }
+  for (int i = nprob; i < kMaxProb; ++i) maps.m[i] = maps.m[0];
+  for (int st = 0; st < nstage; ++st) {
+    P.stage_p0[st] = stage_p0[st]; P.stage_np[st] = stage_np[st];
+    int units = 0, span = 1 << 30;
+    for (int j = 0; j < stage_np[st]; ++j) {
+      TcProblem& q = P.prob[stage_p0[st] + j];
+      q.unit_begin = units;
+      units += q.units;
+      if (q.span < span) span = q.span;
+    }
+    P.stage_units[st] = units;
+    if ((units + ctas - 1) / ctas > span) return false;
+  }
+  return true;
+}
+
+template <class Pol>
+int max_ctas(int device) {
+  int sms = 0, per_sm = 0;
+  const size_t smem = sizeof(TcSmem) + 1024;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (cudaFuncSetAttribute(scan_tc_kernel<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_tc_kernel<Pol>, kThreadsTc, smem);
+  return per_sm > 0 ? sms : 0;
+}
+
+template <class Pol>
+cudaError_t launch(cudaStream_t s, TcMaps& maps, ScanTcParams& P, int ctas) {
+  static_assert(sizeof(TcSmem) + 1024 <= 227 * 1024, "TcSmem exceeds the dynamic shared memory limit");
+  cudaMemsetAsync(P.bar, 0, sizeof(unsigned int), s);
+  const size_t smem = sizeof(TcSmem) + 1024;
+  cudaFuncSetAttribute(scan_tc_kernel<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  void* args[] = {&maps, &P};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)scan_tc_kernel<Pol>, dim3(ctas), dim3(kThreadsTc), args, smem, s);
+  if (e == cudaSuccess) count_launch();
+  return e;
+}
+
 }  // namespace
 
-bool scan_tc_supported(const ScanFwdParams& p) {
-  return p.D % 128 == 0 && p.G % 128 == 0 && p.Z % 128 == 0 && p.Zk == 32 && p.D >= 512 && p.D <= 1024 && p.G >= 512 && p.B <= kRows &&
+bool scan_tc_supported(int B, int G, int D, int Z, int Zk) {
+  return D % 128 == 0 && G % 128 == 0 && Z % 128 == 0 && Zk == 32 && D >= 512 && D <= 1024 && G >= 512 && B <= kRows &&
          std::getenv("DV3_NO_SCAN_TC") == nullptr;
 }
 
 int scan_tc_max_ctas(int device) {
-  int sms = 0, per_sm = 0;
-  const size_t smem = sizeof(TcSmem) + 1024;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  if (cudaFuncSetAttribute(observe_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, observe_scan_tc_kernel, kThreadsTc, smem);
-  return per_sm > 0 ? sms : 0;
+  const int a = max_ctas<FwdPolicy>(device), b = max_ctas<BwdPolicy>(device);
+  return a < b ? a : b;
 }
 
 cudaError_t launch_observe_scan_tc(cudaStream_t s, const ScanFwdParams& p, const ScanTcWeights& w, float* gx_acc, int ctas) {
-  static_assert(sizeof(TcSmem) + 1024 <= 227 * 1024, "TcSmem exceeds the dynamic shared memory limit");
   ScanTcParams P{};
-  P.p = p;
-  P.gx_acc = gx_acc;
+  P.p = p; P.gx_acc = gx_acc; P.B = p.B; P.T = p.T; P.bar = p.bar; P.stamps = p.stamps;
   const int G = p.G, D = p.D, Z = p.Z;
   const int n_out[4] = {3 * G, 3 * G, D, Z}, K[4] = {D, G, G, D};
   const void* ptr[4] = {w.Kt, w.Ut, w.Wpost_h_t, w.Wzq_t};
   const int ld[4] = {w.ld_Kt, w.ld_Ut, w.ld_Wpost_h_t, w.ld_Wzq_t};
+  const int sp0[3] = {0, 2, 3}, snp[3] = {2, 1, 1};
   TcMaps maps;
-  for (int i = 0; i < 4; ++i) {
-    TcProblem& q = P.prob[i];
-    q.n_out = n_out[i]; q.K = K[i]; q.tiles = n_out[i] / 128; q.kblocks = K[i] / 64; q.kc = pick_kc(q.kblocks);
-    q.span = q.tiles * q.kc; q.units = q.tiles * q.kblocks; q.unit_begin = 0;
-    if (!make_wmap(&maps.m[i], ptr[i], n_out[i], K[i], ld[i])) return cudaErrorInvalidValue;
-  }
-  P.prob[1].unit_begin = P.prob[0].units;
-  P.stage_units[0] = P.prob[0].units + P.prob[1].units;
-  P.stage_units[1] = P.prob[2].units;
-  P.stage_units[2] = P.prob[3].units;
-  // a CTA's range of a stage may touch at most kSlots activation chunks
-  for (int st = 0; st < 3; ++st) {
-    const int per = (P.stage_units[st] + ctas - 1) / ctas;
-    const int span = st == 0 ? (P.prob[0].span < P.prob[1].span ? P.prob[0].span : P.prob[1].span) : P.prob[st + 1].span;
-    if (per > span) return cudaErrorInvalidConfiguration;
-  }
+  if (!build_schedule(P, maps, 4, n_out, K, ptr, ld, 3, sp0, snp, ctas)) return cudaErrorInvalidConfiguration;
   {
     const long long n4 = (long long)p.B * p.T * (6 * G + Z + D) / 4;
     const int blocks = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
     scan_tc_init_kernel<<<blocks, 256, 0, s>>>(p, gx_acc);
     count_launch();
   }
-  cudaMemsetAsync(p.bar, 0, sizeof(unsigned int), s);
-  const size_t smem = sizeof(TcSmem) + 1024;
-  cudaFuncSetAttribute(observe_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  void* args[] = {&maps, &P};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)observe_scan_tc_kernel, dim3(ctas), dim3(kThreadsTc), args, smem, s);
-  if (e == cudaSuccess) count_launch();
-  return e;
+  return launch<FwdPolicy>(s, maps, P, ctas);
+}
+
+// q.dp_act, q.du and q.dh_in must be zero on entry (accumulators); q.d_hz holds the head / prior gradients
+cudaError_t launch_observe_scan_tc_bwd(cudaStream_t s, const ScanBwdParams& q, const ScanTcWeightsBwd& w, int ctas) {
+  ScanTcParams P{};
+  P.q = q; P.B = q.B; P.T = q.T; P.bar = q.bar; P.stamps = q.stamps;
+  const int G = q.G, D = q.D, Z = q.Z;
+  const int n_out[5] = {D, G, G, D, Z}, K[5] = {Z, D, 3 * G, 3 * G, D};
+  const void* ptr[5] = {w.Wzq, w.Wpost_h, w.U, w.K, w.Wpre_z};
+  const int ld[5] = {w.ld_Wzq, w.ld_Wpost_h, w.ld_U, w.ld_K, w.ld_Wpre_z};
+  const int sp0[4] = {0, 1, 2, 4}, snp[4] = {1, 1, 2, 1};
+  TcMaps maps;
+  if (!build_schedule(P, maps, 5, n_out, K, ptr, ld, 4, sp0, snp, ctas)) return cudaErrorInvalidConfiguration;
+  return launch<BwdPolicy>(s, maps, P, ctas);
 }
 
 }  // namespace dv3

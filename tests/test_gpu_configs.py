@@ -32,6 +32,9 @@ TOL_BF16_GRAD = 6e-2  # gradients, updated parameters and the actor / critic los
 #                       advantages, bias gradients) over up to 16 384 rows behind up to 5 bf16 layers
 #                       (measured: <= 2.5e-2 at XS, <= 5.3e-2 at L / XL)
 FORWARD_CLASS = ("wm.", "dream.")
+# real-space dreamed rewards / values are inverse_symlog(predicted symlog expectation): exp() multiplies the relative error of
+# the prediction (compared at 2e-2 as dream.value_logits / dream.values_symlog_ema / wm.reward_logits) by up to |y| ~ 3-5
+LOOSE_FORWARD = ("wm.grad_global_norm", "dream.values", "dream.rewards", "wm.rewards")
 CDF_TOL = 2e-2      # forced draws: distance of the uniform to the oracle's bucket of the device-drawn index
 CONT_TOL = 0.25     # forced continue flags: |logit| of a flag that differs (bf16 error of a 255-free scalar head)
 
@@ -106,7 +109,7 @@ def test_config_parity_bf16(wid):
         cls = {"forward": {}, "gradient": {}}
         for k, v in run.report.items():
             if not k.startswith("adam_delta."):
-                cls["forward" if k.startswith(FORWARD_CLASS) and k != "wm.grad_global_norm" else "gradient"][k] = v
+                cls["forward" if k.startswith(FORWARD_CLASS) and k not in LOOSE_FORWARD else "gradient"][k] = v
         _REPORT[f"{wid}-bf16"]["max_forward"] = max(cls["forward"].values())
         _REPORT[f"{wid}-bf16"]["max_gradient"] = max(cls["gradient"].values())
         _record(f"{wid}-bf16", run, _REPORT[f"{wid}-bf16"])
