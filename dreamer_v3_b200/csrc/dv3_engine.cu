@@ -327,7 +327,7 @@ void Engine::layout() {
   z0_idx = ai("wm.z0_indices", {Zc});
   Wt_zq = af("", {Z, D}); Wt_post_h = af("", {D, G}); Ut = af("", {3 * G, G}); Kt = af("", {3 * G, D}); Wt_pre_z = af("", {D, Z});
   scan_bar = (unsigned int*)alloc_bytes("", 256, 1, {}, 6, -1);
-  scan_stamps = (unsigned long long*)alloc_bytes("debug.scan_stamps", (size_t)(T * 8 + 16) * 8, 1, {(long long)(T * 8 + 16) * 2}, 6, -1);
+  scan_stamps = (unsigned long long*)alloc_bytes("debug.scan_stamps", (size_t)(T * 16 + 16 + 4096) * 8, 1, {(long long)(T * 16 + 16 + 4096) * 2}, 6, -1);
   dp_act_all = af("", {Nl, D}); du_all = af("", {Nl, D}); dh_tot = af("", {B, G});
   h_in = af("wm.h_in", {Nl, G});
   z_in = af("wm.z_in", {Nl, Z});

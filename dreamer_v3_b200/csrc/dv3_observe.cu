@@ -181,7 +181,6 @@ int Engine::wm_loss_backward(cudaStream_t s) {
     // tensor-core mode, S ... XL: one persistent kernel streams the plain bf16 weight shadows through tcgen05 (dv3_scan_tc.cu)
     cudaMemsetAsync(dp_act_all, 0, (size_t)N * D * 4, s);
     cudaMemsetAsync(du_all, 0, (size_t)N * D * 4, s);
-    cudaMemsetAsync(dh_in, 0, (size_t)N * G * 4, s);
     ScanBwdParams bp{};
     bp.B = B; bp.T = T; bp.G = G; bp.D = D; bp.Z = Z; bp.Zc = Zc; bp.Zk = Zk;
     bp.post_g = Wp.g; bp.post_b = Wp.b; bp.pre_g = Wx.g; bp.pre_b = Wx.b;

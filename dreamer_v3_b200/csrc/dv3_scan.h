@@ -93,7 +93,7 @@ struct ScanTcWeightsBwd {
 bool scan_tc_supported(int B, int G, int D, int Z, int Zk);
 int scan_tc_max_ctas(int device);
 cudaError_t launch_observe_scan_tc(cudaStream_t s, const ScanFwdParams& p, const ScanTcWeights& w, float* gx_acc, int ctas);
-// q.dp_act, q.du and q.dh_in must be zero on entry (accumulators); q.d_hz holds the head / prior gradients
+// q.dp_act and q.du must be zero on entry (accumulators); q.d_hz holds the head / prior gradients
 cudaError_t launch_observe_scan_tc_bwd(cudaStream_t s, const ScanBwdParams& q, const ScanTcWeightsBwd& w, int ctas);
 
 }  // namespace dv3

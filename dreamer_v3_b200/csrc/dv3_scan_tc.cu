@@ -62,15 +62,35 @@ struct ScanTcParams {
   int B, T;
   unsigned int* bar;
   unsigned long long* stamps;   // optional globaltimer stamps of CTA 0 after every grid barrier (profiling), may be null
+  int evict_first;              // weights exceed the L2: stream them with the evict_first policy
 };
+
+constexpr int kMaxSeg = 12;              // segments of one CTA in one stage (checked by the launcher)
+constexpr int kMaxItems = 2 * kMaxKc + 2;  // staging events of one CTA in one stage
+constexpr int kMaxFlags = 4096;          // B * T is_first flags kept in shared memory
+
+// The work of a CTA is the same at every timestep: its schedule is built once at kernel start (one thread) and read from
+// shared memory by the three roles afterwards.
+struct SegRec {                // one output tile x consecutive k-blocks of one k-chunk
+  unsigned char prob, slot, kb0, kb1;
+  unsigned short tile, kb_abs0;          // first absolute k-block (chunk * kc + kb0)
+  unsigned char need[kMaxKc];            // need[kb - kb0]: staging events of this stage that must have completed before k-block kb
+};
+struct ItemRec {               // one staging event, in the order the MMA warp first touches the staged k-blocks
+  unsigned char rows, prob, slot, kb;    // rows = 1: the whole K = D activation (kc k-blocks) from full rows; else one k-block
+  unsigned short kb_abs, writer;         // writer: this CTA stores the fp32 values (rows: bit mask over the k-blocks)
+};
+struct StageSched { int nseg, nitem, count; SegRec seg[kMaxSeg]; ItemRec item[kMaxItems]; };
 
 struct TcSmem {
   unsigned char ring[kRing][kWBytes];
   unsigned char bbuf[kSlots][kMaxKc][kKbBytes];
-  float stats[kRows][2];    // forward: LayerNorm mean / rstd of the row; backward: m1, m2 of the LayerNorm backward
-  float stats2[kRows][2];   // backward: saved mean / rstd of the row
-  uint64_t full[kRing], empty[kRing], acc_full[2], acc_empty[2], b_ready;
+  float ln[4][1024];                 // pre_g, pre_b, post_g, post_b (the grid barrier invalidates L1: keep them on chip)
+  unsigned char first[kMaxFlags];    // is_first[b * T + t] != 0
+  StageSched sched[kMaxStages];
+  uint64_t full[kRing], empty[kRing], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
+  uint32_t staged_seq;      // running count of staging events completed by the worker warps (read by the MMA warp)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,6 +135,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -185,62 +211,6 @@ struct SlotMap {
   }
 };
 
-// LayerNorm statistics of the 16 rows x[b, t, 0:D] (fp32, read through L2) into sm.stats; worker warp w owns rows 4w .. 4w+3.
-template <int EPL>   // float4 per lane per row = D / 128
-__device__ __forceinline__ void row_stats_t(TcSmem& sm, const float* x, int T, int t, int B, int D, int ww, int lane) {
-  float4 v[4][EPL];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int b = ww * 4 + r;
-#pragma unroll
-    for (int i = 0; i < EPL; ++i)
-      v[r][i] = b < B ? ldcg4(x + ((size_t)b * T + t) * D + (size_t)(lane + 32 * i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  float s[4], q[4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    s[r] = 0.f;
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) s[r] += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
-  }
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    s[r] /= (float)D;
-    q[r] = 0.f;
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-      const float a = v[r][i].x - s[r], b_ = v[r][i].y - s[r], c = v[r][i].z - s[r], d = v[r][i].w - s[r];
-      q[r] += (a * a + b_ * b_) + (c * c + d * d);
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) { sm.stats[ww * 4 + r][0] = s[r]; sm.stats[ww * 4 + r][1] = rsqrtf(q[r] / (float)D + DV3_LN_EPS); }
-  }
-}
-__device__ __forceinline__ void row_stats(TcSmem& sm, const float* x, int T, int t, int B, int D, int ww, int lane) {
-  switch (D / 128) {
-    case 4: row_stats_t<4>(sm, x, T, t, B, D, ww, lane); break;
-    case 5: row_stats_t<5>(sm, x, T, t, B, D, ww, lane); break;
-    case 6: row_stats_t<6>(sm, x, T, t, B, D, ww, lane); break;
-    default: row_stats_t<8>(sm, x, T, t, B, D, ww, lane); break;
-  }
-}
-
-__device__ __forceinline__ void silu8(float (&v)[8]) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = v[i] * sigmoid_fast(v[i]);
-}
 __device__ __forceinline__ void load8(float (&v)[8], const float* p) {
   const float4 a = ldcg4(p), b = ldcg4(p + 4);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -257,8 +227,16 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
 __device__ __forceinline__ void put_b(unsigned char* dst, int b, int c8, const float (&v)[8]) {
   const uint32_t a = smem_u32(dst) + (uint32_t)((b >> 3) * 1024 + (b & 7) * 128 + ((c8 ^ (b & 7)) << 4));
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16(v[0], v[1])), "r"(pack_bf16(v[2], v[3])),
-               "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7])) : "memory");
+               "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7])));
 }
+// row-resident staging: 4 values of row b at columns c .. c+3 (c % 4 == 0) of a K = D activation whose k-blocks lie back to
+// back from `chunk` (bbuf[slot][0])
+__device__ __forceinline__ void put_b4(unsigned char* chunk, int b, int c, float v0, float v1, float v2, float v3) {
+  const int kb = c >> 6, c8 = (c & 63) >> 3, half = (c >> 2) & 1;
+  const uint32_t a = smem_u32(chunk) + (uint32_t)(kb * kKbBytes + (b >> 3) * 1024 + (b & 7) * 128 + ((c8 ^ (b & 7)) << 4) + half * 8);
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(pack_bf16(v0, v1)), "r"(pack_bf16(v2, v3)));
+}
+
 
 // =====================================================================================================================
 // Forward policy (world_model.py:244-273)
@@ -267,74 +245,177 @@ struct FwdPolicy {
   static constexpr int kGemmStages = 3;
   static constexpr bool kExtraStage = true;
   __device__ static int time_of(const ScanTcParams& P, int i) { return i; }
-  __device__ static bool needs_stats(int prob) { return prob == 0 || prob == 3; }
-  __device__ static void stats(const ScanTcParams& P, TcSmem& sm, int prob, int t, int ww, int lane) {
-    row_stats(sm, prob == 0 ? P.p.x_pre : P.p.p_pre, P.T, t, P.B, P.p.D, ww, lane);
-  }
+  __device__ static const float* ln_vec(const ScanTcParams& P, int i) { return i == 0 ? P.p.pre_g : i == 1 ? P.p.pre_b : i == 2 ? P.p.post_g : P.p.post_b; }
+  __device__ static const float* first_flags(const ScanTcParams& P) { return P.p.is_first; }
+  __device__ static int width_D(const ScanTcParams& P) { return P.p.D; }
+  // K = D problems: the CTA reads the 16 full rows once (LayerNorm statistics need them anyway) and stages every k-block of the
+  // activation straight from those registers
+  __device__ static bool row_resident(int prob) { return prob == 0 || prob == 3; }
+  __device__ static int batch_of(int prob) { return prob == 1 ? 4 : 2; }
+  __device__ static bool has_pre_stage(int) { return false; }
+  __device__ static void pre_stage(const ScanTcParams&, TcSmem&, int, int, int) {}
 
-  // Stages activation k-block `kb` (absolute, 64 k) of problem `prob` at step t as the bf16 K-major SWIZZLE_128B B operand.
-  // Worker thread wt: row = wt / 8, 16-byte chunk (8 k) = wt % 8. `writer`: this CTA owns tile 0 of the k-block and stores the
-  // fp32 values for the backward pass.
-  __device__ static void stage_kb(const ScanTcParams& P, TcSmem& sm, unsigned char* dst, int prob, int kb, int t, bool writer, int wt) {
+  // SiLU(LayerNorm(x[b, t, :])) of the pre-GRU (prob 0) / posterior (prob 3) layer for all 16 rows: worker warp ww owns rows
+  // 4ww .. 4ww+3, a lane holds D / 128 float4 per row. writer_mask: k-blocks whose fp32 values this CTA stores for the backward
+  // pass.
+  template <int EPL>
+  __device__ static void stage_rows_t(const ScanTcParams& P, TcSmem& sm, unsigned char* chunk, int prob, int t, unsigned int writer_mask, int ww, int lane) {
     const ScanFwdParams& p = P.p;
-    const int b = wt >> 3, c8 = wt & 7, k = kb * 64 + c8 * 8;
-    const int T = p.T, G = p.G, D = p.D;
-    float v[8];
+    const int T = p.T, B = p.B, D = p.D;
+    const float* x = prob == 0 ? p.x_pre : p.p_pre;
+    const float* gamma = sm.ln[prob == 0 ? 0 : 2];   // shared memory copies
+    const float* beta = sm.ln[prob == 0 ? 1 : 3];
+    float4 v[4][EPL];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
-    if (b < p.B) {
-      const size_t bt = (size_t)b * T + t;
-      if (prob == 0 || prob == 3) {   // SiLU(LayerNorm(x)) of the pre-GRU (0) / posterior (3) layer
-        const float* x = (prob == 0 ? p.x_pre : p.p_pre) + bt * D + k;
-        float g[8], be[8];
-        load8(v, x);
-        load8_ro(g, (prob == 0 ? p.pre_g : p.post_g) + k);
-        load8_ro(be, (prob == 0 ? p.pre_b : p.post_b) + k);
-        const float mean = sm.stats[b][0], rstd = sm.stats[b][1];
+    for (int r = 0; r < 4; ++r) {
+      const int b = ww * 4 + r;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = (v[i] - mean) * rstd * g[i] + be[i];
-        silu8(v);
-        if (writer) {
-          store8((prob == 0 ? p.u_act : p.p_act) + bt * D + k, v);
-          if (kb == 0 && c8 == 0) {
-            (prob == 0 ? p.x_mean : p.p_mean)[bt] = mean;
-            (prob == 0 ? p.x_rstd : p.p_rstd)[bt] = rstd;
-          }
-        }
-      } else if (prob == 1) {          // masked recurrent input h_in (world_model.py:246-247)
-        const bool first = (t == 0) || (p.is_first[bt] != 0.f);
-        if (first) load8_ro(v, p.h0 + k);
-        else load8(v, p.hz + (bt - 1) * (G + p.Z) + k);
-        if (writer) store8(p.h_in + bt * G + k, v);
-      } else {                         // h_t = GRU cell (Keras reset_after; gx / gh already hold their biases)
-        const float* gx = P.gx_acc + bt * 3 * G + k;
-        const float* gh = p.gh + bt * 3 * G + k;
-        float xz[8], xr[8], xc[8], hz_[8], hr[8], hc[8], hin[8];
-        load8(xz, gx); load8(xr, gx + G); load8(xc, gx + 2 * G);
-        load8(hz_, gh); load8(hr, gh + G); load8(hc, gh + 2 * G);
-        const bool first = (t == 0) || (p.is_first[bt] != 0.f);
-        if (first) load8_ro(hin, p.h0 + k);
-        else load8(hin, p.hz + (bt - 1) * (G + p.Z) + k);
-        float z[8], r[8], c[8];
+      for (int i = 0; i < EPL; ++i)
+        v[r][i] = b < B ? ldcg4(x + ((size_t)b * T + t) * D + (size_t)(lane + 32 * i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float s[4], q[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          z[i] = sigmoid_fast(xz[i] + hz_[i]);
-          r[i] = sigmoid_fast(xr[i] + hr[i]);
-          c[i] = tanh_fast(xc[i] + r[i] * hc[i]);
-          v[i] = z[i] * hin[i] + (1.f - z[i]) * c[i];
-        }
-        if (writer) {
-          float* gt = p.gates + bt * 3 * G + k;
-          store8(gt, z); store8(gt + G, r); store8(gt + 2 * G, c);
-          store8(p.hz + bt * (G + p.Z) + k, v);
+    for (int r = 0; r < 4; ++r) {
+      s[r] = 0.f;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) s[r] += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      s[r] /= (float)D;
+      q[r] = 0.f;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        const float a = v[r][i].x - s[r], b_ = v[r][i].y - s[r], c = v[r][i].z - s[r], d = v[r][i].w - s[r];
+        q[r] += (a * a + b_ * b_) + (c * c + d * d);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) q[r] = rsqrtf(q[r] / (float)D + DV3_LN_EPS);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      const float4 g4 = *reinterpret_cast<const float4*>(gamma + c), b4 = *reinterpret_cast<const float4*>(beta + c);
+      const bool wr = (writer_mask >> (c >> 6)) & 1u;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int b = ww * 4 + r;
+        float4 o;
+        o.x = (v[r][i].x - s[r]) * q[r] * g4.x + b4.x; o.y = (v[r][i].y - s[r]) * q[r] * g4.y + b4.y;
+        o.z = (v[r][i].z - s[r]) * q[r] * g4.z + b4.z; o.w = (v[r][i].w - s[r]) * q[r] * g4.w + b4.w;
+        o.x *= sigmoid_fast(o.x); o.y *= sigmoid_fast(o.y); o.z *= sigmoid_fast(o.z); o.w *= sigmoid_fast(o.w);
+        if (b >= B) o = make_float4(0.f, 0.f, 0.f, 0.f);
+        put_b4(chunk, b, c, o.x, o.y, o.z, o.w);
+        if (wr && b < B) *reinterpret_cast<float4*>((prob == 0 ? p.u_act : p.p_act) + ((size_t)b * T + t) * D + c) = o;
+      }
+    }
+    if ((writer_mask & 1u) && lane == 0) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int b = ww * 4 + r;
+        if (b < B) {
+          (prob == 0 ? p.x_mean : p.p_mean)[(size_t)b * T + t] = s[r];
+          (prob == 0 ? p.x_rstd : p.p_rstd)[(size_t)b * T + t] = q[r];
         }
       }
     }
-    put_b(dst, b, c8, v);
+  }
+  __device__ static void stage_rows(const ScanTcParams& P, TcSmem& sm, unsigned char* chunk, int prob, int t, unsigned int writer_mask, int ww, int lane) {
+    switch (P.p.D / 128) {
+      case 4: stage_rows_t<4>(P, sm, chunk, prob, t, writer_mask, ww, lane); break;
+      case 5: stage_rows_t<5>(P, sm, chunk, prob, t, writer_mask, ww, lane); break;
+      case 6: stage_rows_t<6>(P, sm, chunk, prob, t, writer_mask, ww, lane); break;
+      default: stage_rows_t<8>(P, sm, chunk, prob, t, writer_mask, ww, lane); break;
+    }
+  }
+
+  // Stages NB k-blocks (64 k each) of problem 1 (masked recurrent input h_in, world_model.py:246-247) or 2 (h_t = GRU cell,
+  // Keras reset_after; gx / gh already hold their biases) as the bf16 K-major SWIZZLE_128B B operand. Worker thread wt: row =
+  // wt / 8, 16-byte chunk (8 k) = wt % 8. Every load of the batch is issued before the first use (one L2 round trip per batch).
+  // `writer`: this CTA owns tile 0 of the k-block and stores the fp32 values for the backward pass.
+  template <int NB>
+  __device__ static void stage_batch(const ScanTcParams& P, TcSmem& sm, const ItemRec* it, int n, int t, int wt) {
+    const ScanFwdParams& p = P.p;
+    const int b = wt >> 3, c8 = wt & 7;
+    const int T = p.T, G = p.G, W = G + p.Z;
+    const bool row_ok = b < p.B;
+    const size_t bt = (size_t)(row_ok ? b : 0) * T + t;
+    const bool first = (t == 0) || (sm.first[bt] != 0);
+    const int prob = it[0].prob;
+    if (prob == 1) {
+      float v[NB][8];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        if (j < n) {
+          const int k = it[j].kb_abs * 64 + c8 * 8;
+          if (first) load8_ro(v[j], p.h0 + k);
+          else load8(v[j], p.hz + (bt - 1) * W + k);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        if (j < n) {
+          const int k = it[j].kb_abs * 64 + c8 * 8;
+          if (!row_ok) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
+          } else if (it[j].writer) store8(p.h_in + bt * G + k, v[j]);
+          put_b(sm.bbuf[it[j].slot][it[j].kb], b, c8, v[j]);
+        }
+      }
+    } else {
+      float xz[NB][8], xr[NB][8], xc[NB][8], hz_[NB][8], hr[NB][8], hc[NB][8], hin[NB][8];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        if (j < n) {
+          const int k = it[j].kb_abs * 64 + c8 * 8;
+          const float* gx = P.gx_acc + bt * 3 * G + k;
+          const float* gh = p.gh + bt * 3 * G + k;
+          load8(xz[j], gx); load8(xr[j], gx + G); load8(xc[j], gx + 2 * G);
+          load8(hz_[j], gh); load8(hr[j], gh + G); load8(hc[j], gh + 2 * G);
+          if (first) load8_ro(hin[j], p.h0 + k);
+          else load8(hin[j], p.hz + (bt - 1) * W + k);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        if (j < n) {
+          const int k = it[j].kb_abs * 64 + c8 * 8;
+          float z[8], r[8], c[8], v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            z[i] = sigmoid_fast(xz[j][i] + hz_[j][i]);
+            r[i] = sigmoid_fast(xr[j][i] + hr[j][i]);
+            c[i] = tanh_fast(xc[j][i] + r[i] * hc[j][i]);
+            v[i] = row_ok ? z[i] * hin[j][i] + (1.f - z[i]) * c[i] : 0.f;
+          }
+          if (it[j].writer && row_ok) {
+            float* gt = p.gates + bt * 3 * G + k;
+            store8(gt, z); store8(gt + G, r); store8(gt + 2 * G, c);
+            store8(p.hz + bt * W + k, v);
+          }
+          put_b(sm.bbuf[it[j].slot][it[j].kb], b, c8, v);
+        }
+      }
+    }
+  }
+  __device__ static void stage_items(const ScanTcParams& P, TcSmem& sm, const ItemRec* it, int n, int t, int wt) {
+    if (it[0].prob == 1) stage_batch<4>(P, sm, it, n, t, wt);
+    else stage_batch<2>(P, sm, it, n, t, wt);
   }
 
   // accumulator column n (= weight row) of problem `prob`: r[b] for the 16 batch rows -> out[b, t, n]
-  __device__ static void epilogue(const ScanTcParams& P, int prob, int t, int n, const uint32_t (&r)[16]) {
+  __device__ static void epilogue(const ScanTcParams& P, TcSmem&, int prob, int t, int n, const uint32_t (&r)[16]) {
     const ScanFwdParams& p = P.p;
     const TcProblem& q = P.prob[prob];
     float* out = prob == 0 ? P.gx_acc : prob == 1 ? p.gh : prob == 2 ? p.p_pre : p.post_logits;
@@ -346,7 +427,7 @@ struct FwdPolicy {
   }
 
   // one (row, categorical) of stage S4 per warp; t = -1: the prologue (only the gather of step 0)
-  __device__ static void sample_and_gather(const ScanTcParams& P, int b, int cat, int t, int lane) {
+  __device__ static void sample_and_gather(const ScanTcParams& P, TcSmem& sm, int b, int cat, int t, int lane) {
     const ScanFwdParams& p = P.p;
     const int T = p.T, G = p.G, D = p.D, Z = p.Z, Zc = p.Zc, Zk = p.Zk, W = G + Z;
     int pick = 0;
@@ -365,7 +446,7 @@ struct FwdPolicy {
     }
     if (t + 1 < T) {   // masked z input of the next step (world_model.py:249-250) and its row of the pre-GRU layer
       const size_t bn = (size_t)b * T + t + 1;
-      const bool first = (t + 1 == 0) || (p.is_first[bn] != 0.f);
+      const bool first = (t + 1 == 0) || (sm.first[bn] != 0);
       const int idx = first ? p.z0_idx[cat] : pick;
       if (lane < Zk) p.z_in[bn * Z + cat * Zk + lane] = (lane == idx) ? 1.f : 0.f;
       const float* wrow = p.W_pre + (size_t)(cat * Zk + idx) * D;
@@ -373,11 +454,11 @@ struct FwdPolicy {
       for (int j = lane * 4; j < D; j += 128) red_add_v4(xrow + j, __ldg(reinterpret_cast<const float4*>(wrow + j)));
     }
   }
-  __device__ static void extra(const ScanTcParams& P, int t, int gwarp, int nwarps, int lane) {
+  __device__ static void extra(const ScanTcParams& P, TcSmem& sm, int t, int gwarp, int nwarps, int lane) {
     const int ntask = P.B * P.p.Zc;
-    for (int task = gwarp; task < ntask; task += nwarps) sample_and_gather(P, task / P.p.Zc, task % P.p.Zc, t, lane);
+    for (int task = gwarp; task < ntask; task += nwarps) sample_and_gather(P, sm, task / P.p.Zc, task % P.p.Zc, t, lane);
   }
-  __device__ static void prologue(const ScanTcParams& P, int gwarp, int nwarps, int lane) { extra(P, -1, gwarp, nwarps, lane); }
+  __device__ static void prologue(const ScanTcParams& P, TcSmem& sm, int gwarp, int nwarps, int lane) { extra(P, sm, -1, gwarp, nwarps, lane); }
 };
 
 // =====================================================================================================================
@@ -385,23 +466,35 @@ struct FwdPolicy {
 // after the kernel). Per step t = T-1 ... 0, 4 stages:
 //   B1  dp_act += dlogits . W_zq^T        dlogits = softmax-backward(0.99 (dz_t + dKL/dpost)), formed by the consumer
 //   B2  dh_t   += dp_pre . W_post[E:]^T   dp_pre = LayerNorm+SiLU backward of dp_act (row sums recomputed per CTA)
-//   B3  dh_in  += dgh . U^T,  du += dgx . K^T      (dgx, dgh) = GRU-cell backward of dh_t; dh_in also gets dh_t * z
+//   B3a (dgx, dgh) = GRU-cell backward of dh_t, each element once over the grid (elementwise stage); dh_in = dh_t * z
+//   B3  dh_in  += dgh . U^T,  du += dgx . K^T
 //   B4  dz_in  = dx_pre . W_pre[:Z]^T     dx_pre = LayerNorm+SiLU backward of du
-// dh_in and dz_in are passed to step t-1 in the epilogues: d_hz[t-1] += (1 - is_first[t]) * (dh_in | dz_in).
+// dz_in is passed to step t-1 in the epilogue of B4 (d_hz[t-1, G:] += (1 - is_first[t]) dz_in), dh_in is picked up by B3a of
+// step t-1.
 // Weight operands: the plain bf16 shadows ([out, in] row-major = K-major for these transposed contractions).
 // =====================================================================================================================
 struct BwdPolicy {
   static constexpr int kGemmStages = 4;
   static constexpr bool kExtraStage = false;
   __device__ static int time_of(const ScanTcParams& P, int i) { return P.T - 1 - i; }
-  __device__ static bool needs_stats(int prob) { return prob == 1 || prob == 4; }
+  __device__ static const float* ln_vec(const ScanTcParams& P, int i) { return i == 0 ? P.q.pre_g : i == 1 ? P.q.pre_b : i == 2 ? P.q.post_g : P.q.post_b; }
+  __device__ static const float* first_flags(const ScanTcParams& P) { return P.q.is_first; }
+  __device__ static int width_D(const ScanTcParams& P) { return P.q.D; }
+  __device__ static bool row_resident(int prob) { return prob == 1 || prob == 4; }
 
-  // row sums of the LayerNorm backward: m1 = mean_k(dn g), m2 = mean_k(dn g xhat), dn = dy * silu'(n); two rows per round
+  // LayerNorm + SiLU backward of the posterior (prob 1: dp_act -> dp_pre) / pre-GRU (prob 4: du -> dx_pre) layer for all 16
+  // rows, two rows per warp and round: dn = dy silu'(n) g, dx = rstd (dn - mean(dn) - xhat mean(dn xhat))
   template <int EPL>
-  __device__ static void ln_bwd_stats_t(const ScanTcParams& P, TcSmem& sm, const float* dy, const float* x, const float* mean_in,
-                                        const float* rstd_in, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                        int t, int ww, int lane) {
-    const int T = P.T, B = P.B, D = P.q.D;
+  __device__ static void stage_rows_t(const ScanTcParams& P, TcSmem& sm, unsigned char* chunk, int prob, int t, unsigned int writer_mask, int ww, int lane) {
+    const ScanBwdParams& q = P.q;
+    const int T = P.T, B = P.B, D = q.D;
+    const float* dy = prob == 1 ? q.dp_act : q.du;
+    const float* x = prob == 1 ? q.p_pre : q.x_pre;
+    const float* mean_in = prob == 1 ? q.p_mean : q.x_mean;
+    const float* rstd_in = prob == 1 ? q.p_rstd : q.x_rstd;
+    const float* gamma = sm.ln[prob == 1 ? 2 : 0];   // shared memory copies
+    const float* beta = sm.ln[prob == 1 ? 3 : 1];
+    float* out = prob == 1 ? q.dp_pre : q.dx_pre;
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
       float4 xv[2][EPL], dv[2][EPL];
@@ -421,13 +514,13 @@ struct BwdPolicy {
       float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+        const float4 g4 = *(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+        const float4 b4 = *(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
         const float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          const float xs[4] = {xv[r][i].x, xv[r][i].y, xv[r][i].z, xv[r][i].w};
-          const float ds[4] = {dv[r][i].x, dv[r][i].y, dv[r][i].z, dv[r][i].w};
+          float xs[4] = {xv[r][i].x, xv[r][i].y, xv[r][i].z, xv[r][i].w};
+          float ds[4] = {dv[r][i].x, dv[r][i].y, dv[r][i].z, dv[r][i].w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float xhat = (xs[j] - mean[r]) * rstd[r];
@@ -435,7 +528,10 @@ struct BwdPolicy {
             const float sg = sigmoid_fast(n);
             const float dng = ds[j] * (sg * (1.f + n * (1.f - sg))) * g[j];
             s1[r] += dng; s2[r] += dng * xhat;
+            xs[j] = xhat; ds[j] = dng;   // kept for the second pass
           }
+          xv[r][i] = make_float4(xs[0], xs[1], xs[2], xs[3]);
+          dv[r][i] = make_float4(ds[0], ds[1], ds[2], ds[3]);
         }
       }
 #pragma unroll
@@ -443,126 +539,142 @@ struct BwdPolicy {
 #pragma unroll
         for (int r = 0; r < 2; ++r) { s1[r] += __shfl_xor_sync(0xffffffffu, s1[r], o); s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o); }
       }
-      if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        const bool wr = (writer_mask >> (c >> 6)) & 1u;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           const int b = ww * 4 + half * 2 + r;
-          sm.stats[b][0] = s1[r] / (float)D; sm.stats[b][1] = s2[r] / (float)D;
-          sm.stats2[b][0] = mean[r]; sm.stats2[b][1] = rstd[r];
+          const float m1 = s1[r] / (float)D, m2 = s2[r] / (float)D;
+          float4 o;
+          o.x = rstd[r] * (dv[r][i].x - m1 - xv[r][i].x * m2); o.y = rstd[r] * (dv[r][i].y - m1 - xv[r][i].y * m2);
+          o.z = rstd[r] * (dv[r][i].z - m1 - xv[r][i].z * m2); o.w = rstd[r] * (dv[r][i].w - m1 - xv[r][i].w * m2);
+          if (b >= B) o = make_float4(0.f, 0.f, 0.f, 0.f);
+          put_b4(chunk, b, c, o.x, o.y, o.z, o.w);
+          if (wr && b < B) *reinterpret_cast<float4*>(out + ((size_t)b * T + t) * D + c) = o;
         }
       }
     }
   }
-  __device__ static void stats(const ScanTcParams& P, TcSmem& sm, int prob, int t, int ww, int lane) {
-    const ScanBwdParams& q = P.q;
-    const float* dy = prob == 1 ? q.dp_act : q.du;
-    const float* x = prob == 1 ? q.p_pre : q.x_pre;
-    const float* mi = prob == 1 ? q.p_mean : q.x_mean;
-    const float* ri = prob == 1 ? q.p_rstd : q.x_rstd;
-    const float* g = prob == 1 ? q.post_g : q.pre_g;
-    const float* be = prob == 1 ? q.post_b : q.pre_b;
-    switch (q.D / 128) {
-      case 4: ln_bwd_stats_t<4>(P, sm, dy, x, mi, ri, g, be, t, ww, lane); break;
-      case 5: ln_bwd_stats_t<5>(P, sm, dy, x, mi, ri, g, be, t, ww, lane); break;
-      case 6: ln_bwd_stats_t<6>(P, sm, dy, x, mi, ri, g, be, t, ww, lane); break;
-      default: ln_bwd_stats_t<8>(P, sm, dy, x, mi, ri, g, be, t, ww, lane); break;
+  __device__ static void stage_rows(const ScanTcParams& P, TcSmem& sm, unsigned char* chunk, int prob, int t, unsigned int writer_mask, int ww, int lane) {
+    switch (P.q.D / 128) {
+      case 4: stage_rows_t<4>(P, sm, chunk, prob, t, writer_mask, ww, lane); break;
+      case 5: stage_rows_t<5>(P, sm, chunk, prob, t, writer_mask, ww, lane); break;
+      case 6: stage_rows_t<6>(P, sm, chunk, prob, t, writer_mask, ww, lane); break;
+      default: stage_rows_t<8>(P, sm, chunk, prob, t, writer_mask, ww, lane); break;
     }
   }
 
-  __device__ static void stage_kb(const ScanTcParams& P, TcSmem& sm, unsigned char* dst, int prob, int kb, int t, bool writer, int wt) {
+  template <int NB>
+  __device__ static void stage_batch(const ScanTcParams& P, TcSmem& sm, const ItemRec* it, int n, int t, int wt) {
     const ScanBwdParams& q = P.q;
-    const int b = wt >> 3, c8 = wt & 7, k = kb * 64 + c8 * 8;
-    const int T = P.T, G = q.G, D = q.D, Z = q.Z, W = G + Z;
+    const int b = wt >> 3, c8 = wt & 7;
+    const int T = P.T, G = q.G, Z = q.Z, W = G + Z;
     const bool row_ok = b < P.B;
     const size_t bt = (size_t)(row_ok ? b : 0) * T + t;
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    const int prob = it[0].prob;
     if (prob == 0) {
       // dlogits of the posterior categorical (representation_layer.py:73-113 backward): 4 neighbouring threads hold the 32
       // classes of one categorical (Zk = 32); straight-through dz + KL dprobs, through the 1 % unimix and the softmax
-      float l[8], g[8];
-      load8(l, q.post_logits + bt * Z + k);
-      {
-        float dz[8], dk[8];
-        load8(dz, q.d_hz + bt * W + G + k);
-        load8(dk, q.dpost + bt * Z + k);
+      float l[NB][8], dz[NB][8], dk[NB][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = 0.99f * (dz[i] + dk[i]);
+      for (int j = 0; j < NB; ++j) {
+        if (j < n) {
+          const int k = it[j].kb_abs * 64 + c8 * 8;
+          load8(l[j], q.post_logits + bt * Z + k);
+          load8(dz[j], q.d_hz + bt * W + G + k);
+          load8(dk[j], q.dpost + bt * Z + k);
+        }
       }
-      float mx = l[0];
 #pragma unroll
-      for (int i = 1; i < 8; ++i) mx = fmaxf(mx, l[i]);
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      float e[8], s = 0.f;
+      for (int j = 0; j < NB; ++j) {
+        if (j < n) {   // (n is uniform over the CTA: every lane takes part in the shuffles)
+          const int k = it[j].kb_abs * 64 + c8 * 8;
+          float g[8], e[8], v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { e[i] = expf(l[i] - mx); s += e[i]; }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      const float inv = 1.f / s;
-      float dot = 0.f;
+          for (int i = 0; i < 8; ++i) g[i] = 0.99f * (dz[j][i] + dk[j][i]);
+          float mx = l[j][0];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { e[i] *= inv; dot += g[i] * e[i]; }
-      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+          for (int i = 1; i < 8; ++i) mx = fmaxf(mx, l[j][i]);
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = row_ok ? e[i] * (g[i] - dot) : 0.f;
-      if (writer && row_ok) store8(q.dlogits + bt * Z + k, v);
-    } else if (prob == 1 || prob == 4) {
-      // LayerNorm + SiLU backward of the posterior (1) / pre-GRU (4) layer
-      const float* dy = (prob == 1 ? q.dp_act : q.du) + bt * D + k;
-      const float* x = (prob == 1 ? q.p_pre : q.x_pre) + bt * D + k;
-      float d[8], xv[8], g[8], be[8];
-      load8(d, dy); load8(xv, x);
-      load8_ro(g, (prob == 1 ? q.post_g : q.pre_g) + k);
-      load8_ro(be, (prob == 1 ? q.post_b : q.pre_b) + k);
-      const float m1 = sm.stats[b][0], m2 = sm.stats[b][1], mean = sm.stats2[b][0], rstd = sm.stats2[b][1];
+          for (int i = 0; i < 8; ++i) { e[i] = expf(l[j][i] - mx); s += e[i]; }
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          const float inv = 1.f / s;
+          float dot = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xhat = (xv[i] - mean) * rstd;
-        const float n = xhat * g[i] + be[i];
-        const float sg = sigmoid_fast(n);
-        const float dng = d[i] * (sg * (1.f + n * (1.f - sg))) * g[i];
-        v[i] = row_ok ? rstd * (dng - m1 - xhat * m2) : 0.f;
+          for (int i = 0; i < 8; ++i) { e[i] *= inv; dot += g[i] * e[i]; }
+          dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = row_ok ? e[i] * (g[i] - dot) : 0.f;
+          if (it[j].writer && row_ok) store8(q.dlogits + bt * Z + k, v);
+          put_b(sm.bbuf[it[j].slot][it[j].kb], b, c8, v);
+        }
       }
-      if (writer && row_ok) store8((prob == 1 ? q.dp_pre : q.dx_pre) + bt * D + k, v);
     } else {
-      // GRU-cell backward (Keras reset_after); k runs over the 3G gate columns (z | r | c)
-      const int gate = k / G, u = k - gate * G;
-      float d[8], z[8], r[8], c[8], hh[8], hp[8];
-      load8(d, q.d_hz + bt * W + u);
-      const float* gt = q.gates + bt * 3 * G + u;
-      load8(z, gt); load8(r, gt + G); load8(c, gt + 2 * G);
-      load8(hh, q.gh + bt * 3 * G + 2 * G + u);
-      load8(hp, q.h_in + bt * G + u);
-      float dzg[8], drg[8], dcg[8];
+      // dgh (prob 2) / dgx (prob 3), formed once per step by the elementwise stage B3a: plain fp32 -> bf16 staging
+      const float* src = (prob == 2 ? q.dgh : q.dgx) + bt * 3 * G + c8 * 8;
+      float v[NB][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        dzg[i] = d[i] * (hp[i] - c[i]) * z[i] * (1.f - z[i]);
-        dcg[i] = d[i] * (1.f - z[i]) * (1.f - c[i] * c[i]);
-        drg[i] = dcg[i] * hh[i] * r[i] * (1.f - r[i]);
-      }
+      for (int j = 0; j < NB; ++j)
+        if (j < n) load8(v[j], src + (size_t)it[j].kb_abs * 64);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float val = gate == 0 ? dzg[i] : gate == 1 ? drg[i] : (prob == 2 ? dcg[i] * r[i] : dcg[i]);
-        v[i] = row_ok ? val : 0.f;
-      }
-      if (writer && row_ok) {
-        store8((prob == 2 ? q.dgh : q.dgx) + bt * 3 * G + k, v);
-        if (prob == 2 && gate == 0) {   // the direct path dh_in += dh * z (and on to step t-1 unless the row restarts at t)
-          const float keep = (t > 0 && q.is_first[bt] == 0.f) ? 1.f : 0.f;
-          float4 a = make_float4(d[0] * z[0], d[1] * z[1], d[2] * z[2], d[3] * z[3]);
-          float4 c4 = make_float4(d[4] * z[4], d[5] * z[5], d[6] * z[6], d[7] * z[7]);
-          red_add_v4(q.dh_in + bt * G + u, a); red_add_v4(q.dh_in + bt * G + u + 4, c4);
-          if (keep != 0.f) { red_add_v4(q.d_hz + (bt - 1) * W + u, a); red_add_v4(q.d_hz + (bt - 1) * W + u + 4, c4); }
+      for (int j = 0; j < NB; ++j) {
+        if (j < n) {
+          if (!row_ok) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
+          }
+          put_b(sm.bbuf[it[j].slot][it[j].kb], b, c8, v[j]);
         }
       }
     }
-    put_b(dst, b, c8, v);
+  }
+  // B3a: GRU-cell backward (Keras reset_after) of step t for all rows, each (row, unit) exactly once over the grid:
+  //   dh = d_hz[t] (heads + posterior) + (1 - is_first[t+1]) dh_in[t+1];   dgx = (dz, dr, dc), dgh = (dz, dr, dc r), dh_in[t] = dh z
+  // (the contraction dgh . U^T of stage B3 is then added to dh_in[t] with red.global)
+  __device__ static bool has_pre_stage(int st) { return st == 2; }
+  __device__ static void pre_stage(const ScanTcParams& P, TcSmem& sm, int t, int gthread, int nthreads) {
+    const ScanBwdParams& q = P.q;
+    const int T = P.T, G = q.G, W = G + q.Z, G4 = G / 4;
+    for (int e = gthread; e < P.B * G4; e += nthreads) {
+      const int b = e / G4, u = (e - b * G4) * 4;
+      const size_t bt = (size_t)b * T + t;
+      float4 d = ldcg4(q.d_hz + bt * W + u);
+      const bool carry = t + 1 < T && sm.first[bt + 1] == 0;
+      const float* gt = q.gates + bt * 3 * G + u;
+      const float4 z = ldcg4(gt), r = ldcg4(gt + G), c = ldcg4(gt + 2 * G);
+      const float4 hh = ldcg4(q.gh + bt * 3 * G + 2 * G + u), hp = ldcg4(q.h_in + bt * G + u);
+      if (carry) {
+        const float4 nx = ldcg4(q.dh_in + (bt + 1) * G + u);
+        d.x += nx.x; d.y += nx.y; d.z += nx.z; d.w += nx.w;
+      }
+      float4 dz, dr, dc, dcr, dhz;
+#define DV3_GRU_BWD(f) \
+      dz.f = d.f * (hp.f - c.f) * z.f * (1.f - z.f); dc.f = d.f * (1.f - z.f) * (1.f - c.f * c.f); \
+      dr.f = dc.f * hh.f * r.f * (1.f - r.f); dcr.f = dc.f * r.f; dhz.f = d.f * z.f;
+      DV3_GRU_BWD(x) DV3_GRU_BWD(y) DV3_GRU_BWD(z) DV3_GRU_BWD(w)
+#undef DV3_GRU_BWD
+      float* gx = q.dgx + bt * 3 * G + u;
+      float* gh = q.dgh + bt * 3 * G + u;
+      *reinterpret_cast<float4*>(gx) = dz; *reinterpret_cast<float4*>(gx + G) = dr; *reinterpret_cast<float4*>(gx + 2 * G) = dc;
+      *reinterpret_cast<float4*>(gh) = dz; *reinterpret_cast<float4*>(gh + G) = dr; *reinterpret_cast<float4*>(gh + 2 * G) = dcr;
+      *reinterpret_cast<float4*>(q.dh_in + bt * G + u) = dhz;
+      *reinterpret_cast<float4*>(q.d_hz + bt * W + u) = d;   // total gradient w.r.t. h_t
+    }
+  }
+  __device__ static int batch_of(int prob) { return prob == 0 ? 2 : 8; }
+  __device__ static void stage_items(const ScanTcParams& P, TcSmem& sm, const ItemRec* it, int n, int t, int wt) {
+    if (it[0].prob == 0) stage_batch<2>(P, sm, it, n, t, wt);
+    else stage_batch<8>(P, sm, it, n, t, wt);
   }
 
-  __device__ static void epilogue(const ScanTcParams& P, int prob, int t, int n, const uint32_t (&r)[16]) {
+  __device__ static void epilogue(const ScanTcParams& P, TcSmem& sm, int prob, int t, int n, const uint32_t (&r)[16]) {
     const ScanBwdParams& q = P.q;
     const int T = P.T, G = q.G, D = q.D, Z = q.Z, W = G + Z;
 #pragma unroll
@@ -573,20 +685,57 @@ struct BwdPolicy {
       if (prob == 0) red_add(q.dp_act + bt * D + n, val);
       else if (prob == 1) red_add(q.d_hz + bt * W + n, val);
       else if (prob == 3) red_add(q.du + bt * D + n, val);
-      else {
-        const bool keep = t > 0 && q.is_first[bt] == 0.f;
-        if (prob == 2) {
-          red_add(q.dh_in + bt * G + n, val);
-          if (keep) red_add(q.d_hz + (bt - 1) * W + n, val);
-        } else if (keep) {
-          red_add(q.d_hz + (bt - 1) * W + G + n, val);
-        }
-      }
+      else if (prob == 2) red_add(q.dh_in + bt * G + n, val);
+      else if (t > 0 && sm.first[bt] == 0) red_add(q.d_hz + (bt - 1) * W + G + n, val);
     }
   }
-  __device__ static void extra(const ScanTcParams&, int, int, int, int) {}
-  __device__ static void prologue(const ScanTcParams&, int, int, int) {}
+  __device__ static void extra(const ScanTcParams&, TcSmem&, int, int, int, int) {}
+  __device__ static void prologue(const ScanTcParams&, TcSmem&, int, int, int) {}
 };
+
+
+// Builds the CTA's schedule of one stage (run once, by one thread): segments in unit order, the activation-chunk slot of each,
+// the staging events in the order the MMA warp first touches what they stage, and per k-block the number of events it needs.
+template <class Pol>
+__device__ void build_stage_sched(const ScanTcParams& P, int st, StageSched& sc) {
+  SegIter si(P, st);
+  SlotMap slots;
+  Seg s;
+  unsigned int staged[kSlots] = {0u, 0u};
+  int rows_item[kSlots] = {-1, -1};
+  sc.nseg = 0; sc.nitem = 0; sc.count = 0;
+  while (si.next(P, s)) {
+    bool fresh;
+    const int sl = slots.get(s, fresh);
+    if (fresh) { staged[sl] = 0u; rows_item[sl] = -1; }
+    const TcProblem& q = P.prob[s.prob];
+    if (sc.nseg >= kMaxSeg) { printf("dv3 scan_tc: segment table overflow (block %d stage %d)\n", blockIdx.x, st); __trap(); }
+    SegRec& r = sc.seg[sc.nseg++];
+    r.prob = (unsigned char)s.prob; r.slot = (unsigned char)sl; r.kb0 = (unsigned char)s.kb0; r.kb1 = (unsigned char)s.kb1;
+    r.tile = (unsigned short)s.tile; r.kb_abs0 = (unsigned short)(s.chunk * q.kc + s.kb0);
+    for (int kb = s.kb0; kb < s.kb1; ++kb) {
+      if (!((staged[sl] >> kb) & 1u)) {
+        if (sc.nitem >= kMaxItems) { printf("dv3 scan_tc: staging table overflow (block %d stage %d)\n", blockIdx.x, st); __trap(); }
+        ItemRec& it = sc.item[sc.nitem];
+        if (Pol::row_resident(s.prob)) {
+          it.rows = 1; it.prob = (unsigned char)s.prob; it.slot = (unsigned char)sl; it.kb = 0; it.kb_abs = 0; it.writer = 0;
+          rows_item[sl] = sc.nitem;
+          staged[sl] = 0xFFFFFFFFu;
+        } else {
+          it.rows = 0; it.prob = (unsigned char)s.prob; it.slot = (unsigned char)sl; it.kb = (unsigned char)kb;
+          it.kb_abs = (unsigned short)(s.chunk * q.kc + kb); it.writer = s.tile == 0 ? 1 : 0;
+          staged[sl] |= 1u << kb;
+        }
+        ++sc.nitem;
+        sc.count = sc.nitem;
+      }
+      r.need[kb - s.kb0] = (unsigned char)sc.nitem;   // every event up to the one that staged this k-block
+    }
+    if (Pol::row_resident(s.prob) && s.tile == 0 && rows_item[sl] >= 0)
+      sc.item[rows_item[sl]].writer |= (unsigned short)(((1u << (s.kb1 - s.kb0)) - 1u) << s.kb0);
+  }
+  // need[] is exact only for the first touch; later touches may carry a larger count, which is harmless (already completed)
+}
 
 template <class Pol>
 __global__ void __launch_bounds__(kThreadsTc, 1) scan_tc_kernel(const __grid_constant__ TcMaps maps, const ScanTcParams P) {
@@ -599,12 +748,19 @@ __global__ void __launch_bounds__(kThreadsTc, 1) scan_tc_kernel(const __grid_con
     for (int i = 0; i < kMaxProb; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i]) : "memory");
     for (int s = 0; s < kRing; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&sm.acc_full[s], 1); mbar_init(&sm.acc_empty[s], kWorkers); }
-    mbar_init(&sm.b_ready, 1);
+    sm.staged_seq = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(32));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid >= 64 && tid < 64 + Pol::kGemmStages) build_stage_sched<Pol>(P, tid - 64, sm.sched[tid - 64]);
+  {   // LayerNorm gains / offsets and the is_first flags: read thousands of times, and the grid barrier invalidates L1
+    const int D = Pol::width_D(P);
+    for (int i = tid; i < 4 * D; i += kThreadsTc) sm.ln[i / D][i % D] = Pol::ln_vec(P, i / D)[i % D];
+    const float* f = Pol::first_flags(P);
+    for (int i = tid; i < P.B * T; i += kThreadsTc) sm.first[i] = f[i] != 0.f ? 1 : 0;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -614,18 +770,23 @@ __global__ void __launch_bounds__(kThreadsTc, 1) scan_tc_kernel(const __grid_con
   if (warp == 0) {
     // ---------------- TMA producer: the whole weight stream of all T steps, throttled only by the ring ----------------
     if (lane == 0) {
+      uint64_t policy = 0;
+      if (P.evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
       uint32_t it = 0;
       for (int i = 0; i < T; ++i)
         for (int st = 0; st < Pol::kGemmStages; ++st) {
-          SegIter si(P, st);
-          Seg s;
-          while (si.next(P, s)) {
-            const TcProblem& q = P.prob[s.prob];
-            for (int kb = s.kb0; kb < s.kb1; ++kb, ++it) {
+          const StageSched& sc = sm.sched[st];
+          for (int g = 0; g < sc.nseg; ++g) {
+            const SegRec& r = sc.seg[g];
+            const int n = r.kb1 - r.kb0;
+            for (int j = 0; j < n; ++j, ++it) {
               const int slot = it % kRing;
               mbar_wait(&sm.empty[slot], ((it / kRing) & 1) ^ 1);
               mbar_expect_tx(&sm.full[slot], kWBytes);
-              tma_load_2d(smem_u32(sm.ring[slot]), &maps.m[s.prob], (s.chunk * q.kc + kb) * 64, s.tile * 128, &sm.full[slot]);
+              // weights larger than the L2 are streamed with evict_first so that they do not push the step's activations
+              // (a few hundred KB, re-read by every CTA) out of the L2
+              if (P.evict_first) tma_load_2d_hint(smem_u32(sm.ring[slot]), &maps.m[r.prob], (r.kb_abs0 + j) * 64, r.tile * 128, &sm.full[slot], policy);
+              else tma_load_2d(smem_u32(sm.ring[slot]), &maps.m[r.prob], (r.kb_abs0 + j) * 64, r.tile * 128, &sm.full[slot]);
             }
           }
         }
@@ -634,34 +795,35 @@ __global__ void __launch_bounds__(kThreadsTc, 1) scan_tc_kernel(const __grid_con
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       const uint32_t idesc = make_idesc16();
-      uint32_t it = 0, acc_it = 0, bphase = 0;
+      uint32_t it = 0, acc_it = 0, base_seq = 0, have = 0;
       for (int i = 0; i < T; ++i)
         for (int st = 0; st < Pol::kGemmStages; ++st) {
-          SegIter si(P, st);
-          SlotMap slots;
-          Seg s;
-          bool any = false;
-          while (si.next(P, s)) {
-            if (!any) {   // the stage's activation chunks have been staged by the worker warps
-              mbar_wait(&sm.b_ready, bphase & 1);
-              ++bphase;
-              any = true;
-            }
-            bool fresh;
-            const int sl = slots.get(s, fresh);
+          const StageSched& sc = sm.sched[st];
+          for (int g = 0; g < sc.nseg; ++g) {
+            const SegRec& r = sc.seg[g];
             const uint32_t as = acc_it & 1;
             mbar_wait(&sm.acc_empty[as], ((acc_it >> 1) & 1) ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d_tmem = tmem + as * 16;
-            for (int kb = s.kb0; kb < s.kb1; ++kb, ++it) {
+            for (int kb = r.kb0; kb < r.kb1; ++kb, ++it) {
+              // the activation k-block must have been staged: the worker warps publish a running count of staging events
+              const uint32_t need = base_seq + r.need[kb - r.kb0];
+              if ((int32_t)(have - need) < 0) {
+                uint32_t spins = 0;
+                do {
+                  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(have) : "r"(smem_u32(&sm.staged_seq)) : "memory");
+                  if (++spins > (1u << 26)) { printf("dv3 scan_tc: staging wait timed out (block %d)\n", blockIdx.x); __trap(); }
+                } while ((int32_t)(have - need) < 0);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              }
               const int slot = it % kRing;
               mbar_wait(&sm.full[slot], (it / kRing) & 1);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              const uint32_t a_addr = smem_u32(sm.ring[slot]), b_addr = smem_u32(sm.bbuf[sl][kb]);
+              const uint32_t a_addr = smem_u32(sm.ring[slot]), b_addr = smem_u32(sm.bbuf[r.slot][kb]);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const uint64_t da = make_desc(a_addr + j * 32), db = make_desc(b_addr + j * 32);
-                const uint32_t accum = (kb == s.kb0 && j == 0) ? 0u : 1u;
+                const uint32_t accum = (kb == r.kb0 && j == 0) ? 0u : 1u;
                 asm volatile(
                     "{\n\t.reg .pred p;\n\t"
                     "setp.ne.b32 p, %4, 0;\n\t"
@@ -674,13 +836,14 @@ __global__ void __launch_bounds__(kThreadsTc, 1) scan_tc_kernel(const __grid_con
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sm.acc_full[as])) : "memory");
             ++acc_it;
           }
+          base_seq += (uint32_t)sc.count;
         }
     }
   } else {
     // ---------------- workers: stage activations, drain accumulators, sample ----------------
     const int wt = tid - 64, ww = warp - 2, q4 = warp & 3;
     unsigned int bar_target = 0;
-    uint32_t acc_it = 0;
+    uint32_t acc_it = 0, seq = 0;
     const int gwarp = blockIdx.x * 4 + ww, nwarps = gridDim.x * 4;
     int n_stamp = 0;
     auto stamp = [&]() {
@@ -691,76 +854,97 @@ __global__ void __launch_bounds__(kThreadsTc, 1) scan_tc_kernel(const __grid_con
       }
       ++n_stamp;
     };
-    Pol::prologue(P, gwarp, nwarps, lane);
+    // optional per-CTA cycle totals (P.stamps + 2048 + 8 * blockIdx.x): 1 row-resident staging, 2 batched staging, 3 publish,
+    // 4 accumulator wait, 5 epilogue reds, 6 grid barrier, 7 extra stage
+    long long prof1 = 0, prof2 = 0, prof3 = 0, prof4 = 0, prof5 = 0, prof6 = 0, prof7 = 0;
+    long long tc0 = clock64();
+    const bool profiling = P.stamps != nullptr;
+    auto lap = [&](long long& acc) { if (profiling) { const long long c = clock64(); acc += c - tc0; tc0 = c; } };
+    // staged k-blocks become visible to the tensor core (generic -> async proxy), then their running count to the MMA warp
+    auto publish = [&](uint32_t count) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      worker_sync();
+      seq += count;
+      if (wt == 0) asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(&sm.staged_seq)), "r"(seq) : "memory");
+    };
+    Pol::prologue(P, sm, gwarp, nwarps, lane);
     grid_bar_workers(P.bar, bar_target, wt);
     stamp();
+    tc0 = clock64();
 
     for (int i = 0; i < T; ++i) {
       const int t = Pol::time_of(P, i);
       for (int st = 0; st < Pol::kGemmStages; ++st) {
-        // ---- stage the B operand of every segment of this CTA ----
-        {
-          SegIter si(P, st);
-          SlotMap slots;
-          Seg s;
-          unsigned int staged[kSlots] = {0u, 0u};
-          bool any = false;
-          int stats_of = -1;
-          while (si.next(P, s)) {
-            any = true;
-            if (Pol::needs_stats(s.prob) && stats_of != s.prob) {
-              Pol::stats(P, sm, s.prob, t, ww, lane);
-              worker_sync();
-              stats_of = s.prob;
-            }
-            bool fresh;
-            const int sl = slots.get(s, fresh);
-            if (fresh) staged[sl] = 0u;
-            const TcProblem& q = P.prob[s.prob];
-            for (int kb = s.kb0; kb < s.kb1; ++kb) {
-              if (staged[sl] & (1u << kb)) continue;
-              staged[sl] |= 1u << kb;
-              Pol::stage_kb(P, sm, sm.bbuf[sl][kb], s.prob, s.chunk * q.kc + kb, t, s.tile == 0, wt);
-            }
-          }
-          if (any) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-            worker_sync();
-            if (wt == 0) mbar_arrive(&sm.b_ready);
+        const StageSched& sc = sm.sched[st];
+        if (Pol::has_pre_stage(st)) {   // an elementwise stage of its own (every element once over the grid), then a barrier
+          Pol::pre_stage(P, sm, t, blockIdx.x * kWorkers + wt, gridDim.x * kWorkers);
+          lap(prof7);
+          stamp();
+          grid_bar_workers(P.bar, bar_target, wt);
+          lap(prof6);
+          stamp();
+        }
+        // ---- stage the B operand of every segment of this CTA, in the order the MMA warp consumes it ----
+        for (int done = 0; done < sc.nitem;) {
+          const ItemRec& it0 = sc.item[done];
+          if (it0.rows) {
+            Pol::stage_rows(P, sm, sm.bbuf[it0.slot][0], it0.prob, t, it0.writer, ww, lane);
+            lap(prof1);
+            publish(1u);
+            lap(prof3);
+            ++done;
+          } else {
+            const int nb = Pol::batch_of(it0.prob);
+            int n = 1;
+            while (n < nb && done + n < sc.nitem && !sc.item[done + n].rows && sc.item[done + n].prob == it0.prob) ++n;
+            Pol::stage_items(P, sm, &sc.item[done], n, t, wt);
+            lap(prof2);
+            publish((uint32_t)n);
+            lap(prof3);
+            done += n;
           }
         }
+        stamp();   // operands staged
         // ---- epilogue of every segment: TMEM [128 weight rows x 16 batch rows] -> red.global ----
-        {
-          SegIter si(P, st);
-          Seg s;
-          while (si.next(P, s)) {
-            const uint32_t as = acc_it & 1;
-            mbar_wait(&sm.acc_full[as], (acc_it >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t r[16];
-            const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * 16);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&sm.acc_empty[as]);
-            ++acc_it;
-            const int n = s.tile * 128 + q4 * 32 + lane;
-            if (n < P.prob[s.prob].n_out) Pol::epilogue(P, s.prob, t, n, r);
-          }
+        for (int g = 0; g < sc.nseg; ++g) {
+          const SegRec& r_ = sc.seg[g];
+          const uint32_t as = acc_it & 1;
+          mbar_wait(&sm.acc_full[as], (acc_it >> 1) & 1);
+          lap(prof4);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint32_t r[16];
+          const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * 16);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(&sm.acc_empty[as]);
+          ++acc_it;
+          const int n = (int)r_.tile * 128 + q4 * 32 + lane;
+          if (n < P.prob[r_.prob].n_out) Pol::epilogue(P, sm, r_.prob, t, n, r);
+          lap(prof5);
         }
+        stamp();   // accumulators drained
         grid_bar_workers(P.bar, bar_target, wt);
-        stamp();
+        lap(prof6);
+        stamp();   // stage complete on every CTA
       }
       if (Pol::kExtraStage) {
-        Pol::extra(P, t, gwarp, nwarps, lane);
+        Pol::extra(P, sm, t, gwarp, nwarps, lane);
+        lap(prof7);
+        stamp();
         grid_bar_workers(P.bar, bar_target, wt);
+        lap(prof6);
         stamp();
       }
+    }
+    if (profiling && wt == 0) {
+      unsigned long long* o = P.stamps + 2048 + 8 * blockIdx.x;
+      o[0] = 0; o[1] = prof1; o[2] = prof2; o[3] = prof3; o[4] = prof4; o[5] = prof5; o[6] = prof6; o[7] = prof7;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -836,9 +1020,16 @@ bool build_schedule(ScanTcParams& P, TcMaps& maps, int nprob, const int* n_out, 
       if (q.span < span) span = q.span;
     }
     P.stage_units[st] = units;
-    if ((units + ctas - 1) / ctas > span) return false;
+    const int per = (units + ctas - 1) / ctas;
+    if (per > span) return false;
+    int kc_min = kMaxKc;
+    for (int j = 0; j < stage_np[st]; ++j) if (P.prob[stage_p0[st] + j].kc < kc_min) kc_min = P.prob[stage_p0[st] + j].kc;
+    if (per / kc_min + 4 > kMaxSeg) return false;   // segment table of a CTA (kMaxSeg per stage)
   }
-  return true;
+  long long wbytes = 0;
+  for (int i = 0; i < nprob; ++i) wbytes += 2LL * n_out[i] * K[i];
+  P.evict_first = wbytes > (90LL << 20) ? 1 : 0;   // the bf16 weights of one step do not fit the 126 MB L2 next to everything else
+  return P.B * P.T <= kMaxFlags;
 }
 
 template <class Pol>
@@ -894,7 +1085,7 @@ cudaError_t launch_observe_scan_tc(cudaStream_t s, const ScanFwdParams& p, const
   return launch<FwdPolicy>(s, maps, P, ctas);
 }
 
-// q.dp_act, q.du and q.dh_in must be zero on entry (accumulators); q.d_hz holds the head / prior gradients
+// q.dp_act and q.du must be zero on entry (accumulators); q.d_hz holds the head / prior gradients
 cudaError_t launch_observe_scan_tc_bwd(cudaStream_t s, const ScanBwdParams& q, const ScanTcWeightsBwd& w, int ctas) {
   ScanTcParams P{};
   P.q = q; P.B = q.B; P.T = q.T; P.bar = q.bar; P.stamps = q.stamps;
