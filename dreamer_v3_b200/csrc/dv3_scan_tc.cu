@@ -37,8 +37,10 @@
 namespace dv3 {
 namespace {
 
-constexpr int kThreadsTc = 192;
-constexpr int kWorkers = 128;        // warps 2..5
+constexpr int kWorkers = 256;        // warps 2..9
+constexpr int kWorkerWarps = kWorkers / 32;
+constexpr int kThreadsTc = 64 + kWorkers;
+constexpr int kRowsPerWarp = 16 / kWorkerWarps;      // rows of the row-resident staging owned by one worker warp
 constexpr int kRing = 7;             // weight k-blocks (128 rows x 64 k bf16 = 16 KB) in flight per CTA
 constexpr int kMaxKc = 16;           // k-blocks per activation chunk (<= 1024 k)
 constexpr int kSlots = 2;            // activation chunks resident per stage
@@ -143,7 +145,7 @@ __device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
-__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory"); }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -251,7 +253,7 @@ struct FwdPolicy {
   // K = D problems: the CTA reads the 16 full rows once (LayerNorm statistics need them anyway) and stages every k-block of the
   // activation straight from those registers
   __device__ static bool row_resident(int prob) { return prob == 0 || prob == 3; }
-  __device__ static int batch_of(int prob) { return prob == 1 ? 4 : 2; }
+  __device__ static int batch_of(int prob) { return prob == 1 ? 8 : 4; }   // k-blocks per staging event (two thread groups)
   __device__ static bool has_pre_stage(int) { return false; }
   __device__ static void pre_stage(const ScanTcParams&, TcSmem&, int, int, int) {}
 
@@ -265,17 +267,17 @@ struct FwdPolicy {
     const float* x = prob == 0 ? p.x_pre : p.p_pre;
     const float* gamma = sm.ln[prob == 0 ? 0 : 2];   // shared memory copies
     const float* beta = sm.ln[prob == 0 ? 1 : 3];
-    float4 v[4][EPL];
+    float4 v[kRowsPerWarp][EPL];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int b = ww * 4 + r;
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+      const int b = ww * kRowsPerWarp + r;
 #pragma unroll
       for (int i = 0; i < EPL; ++i)
         v[r][i] = b < B ? ldcg4(x + ((size_t)b * T + t) * D + (size_t)(lane + 32 * i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    float s[4], q[4];
+    float s[kRowsPerWarp], q[kRowsPerWarp];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < kRowsPerWarp; ++r) {
       s[r] = 0.f;
 #pragma unroll
       for (int i = 0; i < EPL; ++i) s[r] += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
@@ -283,10 +285,10 @@ struct FwdPolicy {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+      for (int r = 0; r < kRowsPerWarp; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < kRowsPerWarp; ++r) {
       s[r] /= (float)D;
       q[r] = 0.f;
 #pragma unroll
@@ -298,18 +300,18 @@ struct FwdPolicy {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
+      for (int r = 0; r < kRowsPerWarp; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) q[r] = rsqrtf(q[r] / (float)D + DV3_LN_EPS);
+    for (int r = 0; r < kRowsPerWarp; ++r) q[r] = rsqrtf(q[r] / (float)D + DV3_LN_EPS);
 #pragma unroll
     for (int i = 0; i < EPL; ++i) {
       const int c = (lane + 32 * i) * 4;
       const float4 g4 = *reinterpret_cast<const float4*>(gamma + c), b4 = *reinterpret_cast<const float4*>(beta + c);
       const bool wr = (writer_mask >> (c >> 6)) & 1u;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int b = ww * 4 + r;
+      for (int r = 0; r < kRowsPerWarp; ++r) {
+        const int b = ww * kRowsPerWarp + r;
         float4 o;
         o.x = (v[r][i].x - s[r]) * q[r] * g4.x + b4.x; o.y = (v[r][i].y - s[r]) * q[r] * g4.y + b4.y;
         o.z = (v[r][i].z - s[r]) * q[r] * g4.z + b4.z; o.w = (v[r][i].w - s[r]) * q[r] * g4.w + b4.w;
@@ -321,8 +323,8 @@ struct FwdPolicy {
     }
     if ((writer_mask & 1u) && lane == 0) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int b = ww * 4 + r;
+      for (int r = 0; r < kRowsPerWarp; ++r) {
+        const int b = ww * kRowsPerWarp + r;
         if (b < B) {
           (prob == 0 ? p.x_mean : p.p_mean)[(size_t)b * T + t] = s[r];
           (prob == 0 ? p.x_rstd : p.p_rstd)[(size_t)b * T + t] = q[r];
@@ -346,18 +348,19 @@ struct FwdPolicy {
   template <int NB>
   __device__ static void stage_batch(const ScanTcParams& P, TcSmem& sm, const ItemRec* it, int n, int t, int wt) {
     const ScanFwdParams& p = P.p;
-    const int b = wt >> 3, c8 = wt & 7;
+    const int grp = wt >> 7, b = (wt & 127) >> 3, c8 = wt & 7;   // two groups of 128 threads take alternate k-blocks of a batch
     const int T = p.T, G = p.G, W = G + p.Z;
     const bool row_ok = b < p.B;
     const size_t bt = (size_t)(row_ok ? b : 0) * T + t;
     const bool first = (t == 0) || (sm.first[bt] != 0);
     const int prob = it[0].prob;
+    it += grp; n = (n - grp + 1) / 2;   // this group's items: grp, grp + 2, ...
     if (prob == 1) {
       float v[NB][8];
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         if (j < n) {
-          const int k = it[j].kb_abs * 64 + c8 * 8;
+          const int k = it[2 * j].kb_abs * 64 + c8 * 8;
           if (first) load8_ro(v[j], p.h0 + k);
           else load8(v[j], p.hz + (bt - 1) * W + k);
         }
@@ -365,12 +368,12 @@ struct FwdPolicy {
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         if (j < n) {
-          const int k = it[j].kb_abs * 64 + c8 * 8;
+          const int k = it[2 * j].kb_abs * 64 + c8 * 8;
           if (!row_ok) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
-          } else if (it[j].writer) store8(p.h_in + bt * G + k, v[j]);
-          put_b(sm.bbuf[it[j].slot][it[j].kb], b, c8, v[j]);
+          } else if (it[2 * j].writer) store8(p.h_in + bt * G + k, v[j]);
+          put_b(sm.bbuf[it[2 * j].slot][it[2 * j].kb], b, c8, v[j]);
         }
       }
     } else {
@@ -378,7 +381,7 @@ struct FwdPolicy {
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         if (j < n) {
-          const int k = it[j].kb_abs * 64 + c8 * 8;
+          const int k = it[2 * j].kb_abs * 64 + c8 * 8;
           const float* gx = P.gx_acc + bt * 3 * G + k;
           const float* gh = p.gh + bt * 3 * G + k;
           load8(xz[j], gx); load8(xr[j], gx + G); load8(xc[j], gx + 2 * G);
@@ -390,7 +393,7 @@ struct FwdPolicy {
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         if (j < n) {
-          const int k = it[j].kb_abs * 64 + c8 * 8;
+          const int k = it[2 * j].kb_abs * 64 + c8 * 8;
           float z[8], r[8], c[8], v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -399,12 +402,12 @@ struct FwdPolicy {
             c[i] = tanh_fast(xc[j][i] + r[i] * hc[j][i]);
             v[i] = row_ok ? z[i] * hin[j][i] + (1.f - z[i]) * c[i] : 0.f;
           }
-          if (it[j].writer && row_ok) {
+          if (it[2 * j].writer && row_ok) {
             float* gt = p.gates + bt * 3 * G + k;
             store8(gt, z); store8(gt + G, r); store8(gt + 2 * G, c);
             store8(p.hz + bt * W + k, v);
           }
-          put_b(sm.bbuf[it[j].slot][it[j].kb], b, c8, v);
+          put_b(sm.bbuf[it[2 * j].slot][it[2 * j].kb], b, c8, v);
         }
       }
     }
@@ -414,16 +417,16 @@ struct FwdPolicy {
     else stage_batch<2>(P, sm, it, n, t, wt);
   }
 
-  // accumulator column n (= weight row) of problem `prob`: r[b] for the 16 batch rows -> out[b, t, n]
-  __device__ static void epilogue(const ScanTcParams& P, TcSmem&, int prob, int t, int n, const uint32_t (&r)[16]) {
+  // accumulator column n (= weight row) of problem `prob`: r[j] for batch rows b0 + j -> out[b, t, n]
+  __device__ static void epilogue(const ScanTcParams& P, TcSmem&, int prob, int t, int n, int b0, const uint32_t (&r)[8]) {
     const ScanFwdParams& p = P.p;
     const TcProblem& q = P.prob[prob];
     float* out = prob == 0 ? P.gx_acc : prob == 1 ? p.gh : prob == 2 ? p.p_pre : p.post_logits;
     float* o = out + (size_t)t * q.n_out + n;
     const size_t ldo = (size_t)p.T * q.n_out;
 #pragma unroll
-    for (int b = 0; b < kRows; ++b)
-      if (b < p.B) red_add(o + (size_t)b * ldo, __uint_as_float(r[b]));
+    for (int j = 0; j < 8; ++j)
+      if (b0 + j < p.B) red_add(o + (size_t)(b0 + j) * ldo, __uint_as_float(r[j]));
   }
 
   // one (row, categorical) of stage S4 per warp; t = -1: the prologue (only the gather of step 0)
@@ -495,13 +498,12 @@ struct BwdPolicy {
     const float* gamma = sm.ln[prob == 1 ? 2 : 0];   // shared memory copies
     const float* beta = sm.ln[prob == 1 ? 3 : 1];
     float* out = prob == 1 ? q.dp_pre : q.dx_pre;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      float4 xv[2][EPL], dv[2][EPL];
-      float mean[2], rstd[2];
+    {
+      float4 xv[kRowsPerWarp][EPL], dv[kRowsPerWarp][EPL];
+      float mean[kRowsPerWarp], rstd[kRowsPerWarp];
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int b = ww * 4 + half * 2 + r;
+      for (int r = 0; r < kRowsPerWarp; ++r) {
+        const int b = ww * kRowsPerWarp + r;
         const size_t bt = (size_t)(b < B ? b : 0) * T + t;
         mean[r] = mean_in[bt]; rstd[r] = rstd_in[bt];
 #pragma unroll
@@ -511,14 +513,16 @@ struct BwdPolicy {
           dv[r][i] = b < B ? ldcg4(dy + off) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+      float s1[kRowsPerWarp], s2[kRowsPerWarp];
+#pragma unroll
+      for (int r = 0; r < kRowsPerWarp; ++r) { s1[r] = 0.f; s2[r] = 0.f; }
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {
         const float4 g4 = *(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
         const float4 b4 = *(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
         const float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < kRowsPerWarp; ++r) {
           float xs[4] = {xv[r][i].x, xv[r][i].y, xv[r][i].z, xv[r][i].w};
           float ds[4] = {dv[r][i].x, dv[r][i].y, dv[r][i].z, dv[r][i].w};
 #pragma unroll
@@ -537,15 +541,15 @@ struct BwdPolicy {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int r = 0; r < 2; ++r) { s1[r] += __shfl_xor_sync(0xffffffffu, s1[r], o); s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o); }
+        for (int r = 0; r < kRowsPerWarp; ++r) { s1[r] += __shfl_xor_sync(0xffffffffu, s1[r], o); s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o); }
       }
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {
         const int c = (lane + 32 * i) * 4;
         const bool wr = (writer_mask >> (c >> 6)) & 1u;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int b = ww * 4 + half * 2 + r;
+        for (int r = 0; r < kRowsPerWarp; ++r) {
+          const int b = ww * kRowsPerWarp + r;
           const float m1 = s1[r] / (float)D, m2 = s2[r] / (float)D;
           float4 o;
           o.x = rstd[r] * (dv[r][i].x - m1 - xv[r][i].x * m2); o.y = rstd[r] * (dv[r][i].y - m1 - xv[r][i].y * m2);
@@ -569,11 +573,12 @@ struct BwdPolicy {
   template <int NB>
   __device__ static void stage_batch(const ScanTcParams& P, TcSmem& sm, const ItemRec* it, int n, int t, int wt) {
     const ScanBwdParams& q = P.q;
-    const int b = wt >> 3, c8 = wt & 7;
+    const int grp = wt >> 7, b = (wt & 127) >> 3, c8 = wt & 7;   // two groups of 128 threads take alternate k-blocks of a batch
     const int T = P.T, G = q.G, Z = q.Z, W = G + Z;
     const bool row_ok = b < P.B;
     const size_t bt = (size_t)(row_ok ? b : 0) * T + t;
     const int prob = it[0].prob;
+    it += grp; n = (n - grp + 1) / 2;   // this group's items: grp, grp + 2, ...
     if (prob == 0) {
       // dlogits of the posterior categorical (representation_layer.py:73-113 backward): 4 neighbouring threads hold the 32
       // classes of one categorical (Zk = 32); straight-through dz + KL dprobs, through the 1 % unimix and the softmax
@@ -581,7 +586,7 @@ struct BwdPolicy {
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         if (j < n) {
-          const int k = it[j].kb_abs * 64 + c8 * 8;
+          const int k = it[2 * j].kb_abs * 64 + c8 * 8;
           load8(l[j], q.post_logits + bt * Z + k);
           load8(dz[j], q.d_hz + bt * W + G + k);
           load8(dk[j], q.dpost + bt * Z + k);
@@ -590,7 +595,7 @@ struct BwdPolicy {
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         if (j < n) {   // (n is uniform over the CTA: every lane takes part in the shuffles)
-          const int k = it[j].kb_abs * 64 + c8 * 8;
+          const int k = it[2 * j].kb_abs * 64 + c8 * 8;
           float g[8], e[8], v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) g[i] = 0.99f * (dz[j][i] + dk[j][i]);
@@ -612,8 +617,8 @@ struct BwdPolicy {
           dot += __shfl_xor_sync(0xffffffffu, dot, 2);
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = row_ok ? e[i] * (g[i] - dot) : 0.f;
-          if (it[j].writer && row_ok) store8(q.dlogits + bt * Z + k, v);
-          put_b(sm.bbuf[it[j].slot][it[j].kb], b, c8, v);
+          if (it[2 * j].writer && row_ok) store8(q.dlogits + bt * Z + k, v);
+          put_b(sm.bbuf[it[2 * j].slot][it[2 * j].kb], b, c8, v);
         }
       }
     } else {
@@ -622,7 +627,7 @@ struct BwdPolicy {
       float v[NB][8];
 #pragma unroll
       for (int j = 0; j < NB; ++j)
-        if (j < n) load8(v[j], src + (size_t)it[j].kb_abs * 64);
+        if (j < n) load8(v[j], src + (size_t)it[2 * j].kb_abs * 64);
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         if (j < n) {
@@ -630,7 +635,7 @@ struct BwdPolicy {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
           }
-          put_b(sm.bbuf[it[j].slot][it[j].kb], b, c8, v[j]);
+          put_b(sm.bbuf[it[2 * j].slot][it[2 * j].kb], b, c8, v[j]);
         }
       }
     }
@@ -668,20 +673,21 @@ struct BwdPolicy {
       *reinterpret_cast<float4*>(q.d_hz + bt * W + u) = d;   // total gradient w.r.t. h_t
     }
   }
-  __device__ static int batch_of(int prob) { return prob == 0 ? 2 : 8; }
+  __device__ static int batch_of(int prob) { return prob == 0 ? 4 : 16; }   // k-blocks per staging event (two thread groups)
   __device__ static void stage_items(const ScanTcParams& P, TcSmem& sm, const ItemRec* it, int n, int t, int wt) {
     if (it[0].prob == 0) stage_batch<2>(P, sm, it, n, t, wt);
     else stage_batch<8>(P, sm, it, n, t, wt);
   }
 
-  __device__ static void epilogue(const ScanTcParams& P, TcSmem& sm, int prob, int t, int n, const uint32_t (&r)[16]) {
+  __device__ static void epilogue(const ScanTcParams& P, TcSmem& sm, int prob, int t, int n, int b0, const uint32_t (&r)[8]) {
     const ScanBwdParams& q = P.q;
     const int T = P.T, G = q.G, D = q.D, Z = q.Z, W = G + Z;
 #pragma unroll
-    for (int b = 0; b < kRows; ++b) {
+    for (int j = 0; j < 8; ++j) {
+      const int b = b0 + j;
       if (b >= P.B) continue;
       const size_t bt = (size_t)b * T + t;
-      const float val = __uint_as_float(r[b]);
+      const float val = __uint_as_float(r[j]);
       if (prob == 0) red_add(q.dp_act + bt * D + n, val);
       else if (prob == 1) red_add(q.d_hz + bt * W + n, val);
       else if (prob == 3) red_add(q.du + bt * D + n, val);
@@ -844,7 +850,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) scan_tc_kernel(const __grid_con
     const int wt = tid - 64, ww = warp - 2, q4 = warp & 3;
     unsigned int bar_target = 0;
     uint32_t acc_it = 0, seq = 0;
-    const int gwarp = blockIdx.x * 4 + ww, nwarps = gridDim.x * 4;
+    const int gwarp = blockIdx.x * kWorkerWarps + ww, nwarps = gridDim.x * kWorkerWarps;
     int n_stamp = 0;
     auto stamp = [&]() {
       if (P.stamps != nullptr && blockIdx.x == 0 && wt == 0) {
@@ -912,20 +918,19 @@ __global__ void __launch_bounds__(kThreadsTc, 1) scan_tc_kernel(const __grid_con
           mbar_wait(&sm.acc_full[as], (acc_it >> 1) & 1);
           lap(prof4);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          uint32_t r[16];
-          const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * 16);
+          uint32_t r[8];
+          const int b0 = (ww >> 2) * 8;   // two warps per TMEM lane quarter: accumulator columns (batch rows) b0 .. b0 + 7
+          const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(as * 16 + b0);
           asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
               : "r"(taddr));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           mbar_arrive(&sm.acc_empty[as]);
           ++acc_it;
           const int n = (int)r_.tile * 128 + q4 * 32 + lane;
-          if (n < P.prob[r_.prob].n_out) Pol::epilogue(P, sm, r_.prob, t, n, r);
+          if (n < P.prob[r_.prob].n_out) Pol::epilogue(P, sm, r_.prob, t, n, b0, r);
           lap(prof5);
         }
         stamp();   // accumulators drained
