@@ -61,6 +61,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 void gemm_f32(cudaStream_t s, const GemmArgs& g);
 // mode 0: always fp32 SIMT; mode 1: bf16 tcgen05 tensor cores for large contractions (dv3_gemm_tc.cu)
 void gemm_dispatch(cudaStream_t s, const GemmArgs& g, int mode);
+bool gemm_uses_tma(const GemmArgs& g, int mode);   // would gemm_dispatch take the TMA-fed kernel (bf16 operand copies only)?
 bool gemm_tc_eligible(const GemmArgs& g);
 // weight-streaming kernels for <= 16 rows against a large weight matrix (dv3_gemv.cu), fp32 in every mode
 bool gemv16_eligible(const GemmArgs& g);
@@ -127,7 +128,8 @@ void infer_mask(cudaStream_t s, const float* f, const float* ph, const float* pz
 
 // ---- conv helpers (dv3_conv.cu): 4x4 stride-2 "same" ------------------------------------------------
 // cols[(n,oy,ox), (ky,kx,c)] = img[n, 2oy-1+ky, 2ox-1+kx, c] (0 outside); img NHWC [n,H,W,C], out H/2 x W/2
-void im2col_k4s2(cudaStream_t s, const float* img, float* cols, int n, int H, int W, int C, void* cols16 = nullptr);  // cols16: bf16 twin
+// cols16: bf16 twin of the patch matrix; cols may be null when only the twin is wanted
+void im2col_k4s2(cudaStream_t s, const float* img, float* cols, int n, int H, int W, int C, void* cols16 = nullptr);
 // img[n,y,x,c] (+)= sum over the (<=4) patches covering (y,x) of cols[(n,oy,ox),(ky,kx,c)] + bias[c] + add_const
 void col2im_k4s2(cudaStream_t s, const float* cols, float* img, int n, int H, int W, int C, const float* bias,
                  float add_const);

@@ -30,7 +30,7 @@ __global__ void im2col_kernel(const float* __restrict__ img, float* __restrict__
     float* dst = cols + (size_t)i * C;
     for (int c = 0; c < C; ++c) {
       const float v = in ? src[c] : 0.f;
-      dst[c] = v;
+      if (cols != nullptr) dst[c] = v;
       if (cols16 != nullptr) cols16[(size_t)i * C + c] = __float2bfloat16_rn(v);
     }
   }
@@ -81,7 +81,7 @@ __global__ void im2col_v4_kernel(const float4* __restrict__ img, float4* __restr
     const int y = 2 * oy - 1 + ky, x = 2 * ox - 1 + kx;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (y >= 0 && y < H && x >= 0 && x < W) v = img[(((size_t)b * H + y) * W + x) * C4 + c];
-    cols[i] = v;
+    if (cols != nullptr) cols[i] = v;   // (null: every consumer reads the bf16 patch matrix)
     if (cols16 != nullptr) {   // bf16 twin of the patch matrix for the TMA-fed contraction
       __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
       uint2 o; o.x = *reinterpret_cast<uint32_t*>(&lo); o.y = *reinterpret_cast<uint32_t*>(&hi);

@@ -722,6 +722,16 @@ void Engine::side_join() {
 // ------------------------------------------------------------------------------------------ building blocks
 void Engine::mm(const float* A_, int lda, bool ta, const float* B_, int ldb, bool tb, float* C, int ldc, int M, int N_,
                 int K, const float* bias, float beta, const void* A16, const void* B16) {
+  gemm_dispatch(cur, mm_args(A_, lda, ta, B_, ldb, tb, C, ldc, M, N_, K, bias, beta, A16, B16), cfg.compute_mode);
+}
+
+bool Engine::mm_tma(const float* A_, int lda, bool ta, const float* B_, int ldb, bool tb, float* C, int ldc, int M, int N_, int K,
+                    const void* A16, const void* B16) const {
+  return gemm_uses_tma(mm_args(A_, lda, ta, B_, ldb, tb, C, ldc, M, N_, K, nullptr, 0.f, A16, B16), cfg.compute_mode);
+}
+
+GemmArgs Engine::mm_args(const float* A_, int lda, bool ta, const float* B_, int ldb, bool tb, float* C, int ldc, int M, int N_,
+                         int K, const float* bias, float beta, const void* A16, const void* B16) const {
   GemmArgs g{A_, lda, ta ? 1 : 0, B_, ldb, tb ? 1 : 0, C, ldc, M, N_, K, bias, beta};
   if (A16 != nullptr && cfg.compute_mode == 1 && (!ta || (B16 != nullptr && !tb))) { g.Ah = A16; g.ldah = lda; }
   if (B16 != nullptr && ta && !tb && cfg.compute_mode == 1) { g.Bmn = B16; g.ldbmn = ldb; }
@@ -741,7 +751,7 @@ void Engine::mm(const float* A_, int lda, bool ta, const float* B_, int ldb, boo
       break;
     }
   }
-  gemm_dispatch(cur, g, cfg.compute_mode);
+  return g;
 }
 
 void Engine::mlp_fwd(const Mlp& mdl, MlpAct& a, const float* x, int ldx, long long rows, long long row_off,
@@ -801,7 +811,9 @@ void Engine::encoder_fwd() {
     ConvLayer& c = enc_conv[l];
     const int ho = c.hin / 2;
     const long long rows = (long long)N * ho * ho;
-    im2col_k4s2(cur, x, cols, N, c.hin, c.hin, c.cin, cols16);
+    // (the fp32 patch matrix is only written when the contraction cannot take the TMA path, which reads the bf16 one)
+    const bool tma = cols16 != nullptr && mm_tma(cols, 16 * c.cin, false, c.w, c.cout, false, c.pre, c.cout, (int)rows, c.cout, 16 * c.cin, cols16, nullptr);
+    im2col_k4s2(cur, x, tma ? nullptr : cols, N, c.hin, c.hin, c.cin, cols16);
     mm(cols, 16 * c.cin, false, c.w, c.cout, false, c.pre, c.cout, (int)rows, c.cout, 16 * c.cin, nullptr, 0.f, cols16);
     ln_silu_fwd(cur, c.pre, c.cout, c.g, c.b, c.act, c.cout, c.mean, c.rstd, 1, rows, c.cout, c.act16);
     x = c.act;
@@ -822,7 +834,9 @@ void Engine::encoder_bwd(float* d_enc) {
     const long long rows = (long long)N * ho * ho;
     ln_silu_bwd(cur, dcur, c.cout, c.pre, c.cout, c.mean, c.rstd, c.g, c.b, conv_dpre, c.cout, c.dg, c.db, 1, rows, c.cout, conv_dpre16);
     const float* xin = (l == 0) ? obs_sym : enc_conv[l - 1].act;
-    im2col_k4s2(cur, xin, cols, N, c.hin, c.hin, c.cin, cols16);
+    const bool tma = cols16 != nullptr &&
+                     mm_tma(cols, 16 * c.cin, true, conv_dpre, c.cout, false, c.dw, c.cout, 16 * c.cin, c.cout, (int)rows, cols16, conv_dpre16);
+    im2col_k4s2(cur, xin, tma ? nullptr : cols, N, c.hin, c.hin, c.cin, cols16);
     mm(cols, 16 * c.cin, true, conv_dpre, c.cout, false, c.dw, c.cout, 16 * c.cin, c.cout, (int)rows, nullptr, 1.f, cols16, conv_dpre16);
     if (l > 0) {
       mm(conv_dpre, c.cout, false, c.w, c.cout, true, cols, 16 * c.cin, (int)rows, 16 * c.cin, c.cout, nullptr, 0.f, conv_dpre16);
@@ -876,9 +890,13 @@ void Engine::decoder_bwd() {
     ConvLayer& c = dec_convT[l];
     const long long rows_in = (long long)N * c.hin * c.hin, rows_out = rows_in * 4;
     ln_silu_bwd(cur, dcur, c.cout, c.pre, c.cout, c.mean, c.rstd, c.g, c.b, conv_dpre, c.cout, c.dg, c.db, 1, rows_out, c.cout);
-    im2col_k4s2(cur, conv_dpre, cols, N, 2 * c.hin, 2 * c.hin, c.cout, cols16);
     const float* xin = (l == 0) ? dec_dense_out : dec_convT[l - 1].act;
     const void* xin16 = (l == 0) ? dec_dense_out16 : dec_convT[l - 1].act16;
+    float* dnext_q = bufs[flip];
+    const bool tma = cols16 != nullptr &&
+                     mm_tma(cols, 16 * c.cout, true, xin, c.cin, false, c.dw, c.cin, 16 * c.cout, c.cin, (int)rows_in, cols16, xin16) &&
+                     mm_tma(cols, 16 * c.cout, false, c.w, c.cin, false, dnext_q, c.cin, (int)rows_in, c.cin, 16 * c.cout, cols16, nullptr);
+    im2col_k4s2(cur, conv_dpre, tma ? nullptr : cols, N, 2 * c.hin, 2 * c.hin, c.cout, cols16);
     mm(cols, 16 * c.cout, true, xin, c.cin, false, c.dw, c.cin, 16 * c.cout, c.cin, (int)rows_in, nullptr, 1.f, cols16, xin16);
     float* dnext = bufs[flip]; flip ^= 1;
     mm(cols, 16 * c.cout, false, c.w, c.cin, false, dnext, c.cin, (int)rows_in, c.cin, 16 * c.cout, nullptr, 0.f, cols16);

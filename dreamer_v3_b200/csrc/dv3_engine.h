@@ -201,6 +201,11 @@ struct Engine {
   // A16: bf16 twin of A (same element layout), valid only when the kernel that produced A wrote it in the same launch
   void mm(const float* A_, int lda, bool ta, const float* B_, int ldb, bool tb, float* C, int ldc, int M, int N_, int K,
           const float* bias = nullptr, float beta = 0.f, const void* A16 = nullptr, const void* B16 = nullptr);
+  GemmArgs mm_args(const float* A_, int lda, bool ta, const float* B_, int ldb, bool tb, float* C, int ldc, int M, int N_, int K,
+                   const float* bias, float beta, const void* A16, const void* B16) const;
+  // would this mm() run on the TMA-fed kernel, i.e. read only the bf16 copies of its operands?
+  bool mm_tma(const float* A_, int lda, bool ta, const float* B_, int ldb, bool tb, float* C, int ldc, int M, int N_, int K,
+              const void* A16, const void* B16) const;
   void mlp_fwd(const Mlp& m, MlpAct& a, const float* x, int ldx, long long rows, long long row_off = 0,
                const void* x16 = nullptr);
   // ---- bf16 twins of activation buffers that feed large contractions (tensor-core mode only) ----

@@ -326,6 +326,14 @@ bool pdl_enabled() {
   return on;
 }
 
+// true when gemm_dispatch would run this contraction on the TMA-fed tcgen05 kernel, which reads only the bf16 operand copies
+// (so a producer may skip writing the fp32 original of an operand whose every consumer says yes)
+bool gemm_uses_tma(const GemmArgs& g, int mode) {
+  if (!(g.M > 0 && g.N > 0 && g.K > 0) || mode != 1) return false;
+  if (gemv16_eligible(g) || skinny_shape(g)) return false;
+  return gemm_tma_eligible(g) && gemm_tc_eligible(g);
+}
+
 void gemm_dispatch(cudaStream_t s, const GemmArgs& g, int mode) {
   if (g.M > 0 && g.N > 0 && g.K > 0 && mode != 2 && gemv16_eligible(g)) {   // the 16 scan rows against a large weight matrix
     gemv16(s, g);
