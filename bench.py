@@ -342,23 +342,41 @@ class Job:
         return out
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per timestep of the scan kernels from the committed ncu --set full captures
+# (profiles/r02_scan_tc_xl_ncu.txt: XL forward 8798.9 + 197.7 MB, backward 8977.4 + 173.1 MB over T = 64 steps;
+#  profiles/r02_c3_kernels_ncu_table.txt: S backward 46.8 + 5.6 MB - the bf16 weights stay in the L2)
+SCAN_TRAFFIC_PER_STEP = {("XL", "fwd"): (8798.88e6 + 197.66e6) / 64, ("XL", "bwd"): (8977.40e6 + 173.10e6) / 64,
+                         ("S", "bwd"): (46.80e6 + 5.60e6) / 64}
+
+
 def scan_roofline(cfg, us_fwd, us_bwd, pk, mode):
     """Roofline entry of the time-dominant latency / bandwidth kernel of an update: the observe scan. Algorithmic bytes per
-    step = the step's weights on the recurrence, read once (fp32 as the scan kernels hold them). At XS they are
-    resident in the cluster's shared memory for all T steps, so the kernel has no HBM roofline: it is a latency chain."""
-    wbytes = scan_step_weight_bytes(cfg, 4)
-    out = {"kernel": "observe scan forward (per timestep)", "weight_bytes_per_step": wbytes, "us_per_step": us_fwd,
-           "bwd_us_per_step": us_bwd, "peak": pk["hbm"], "unit": "GB/s", "peak_source": pk["src"]}
+    step = the step's weights on the recurrence, read once: bf16 in the tensor-core mode at S ... XL (the
+    weight-streaming tcgen05 kernels of dv3_scan_tc.cu; the backward kernel also streams W_pre[:Z]), fp32 otherwise. At XS the
+    weights are resident in the cluster's shared memory for all T steps, so the kernel has no HBM roofline: a latency chain."""
+    G, D, Z = cfg.G, cfg.D, cfg.Z
+    tc = mode == 1 and G >= 512 and D % 128 == 0 and G % 128 == 0 and cfg.B <= 16
+    bpw = 2 if tc else 4
+    fwd_bytes = bpw * (D * 3 * G + G * 3 * G + G * D + D * Z) + (0 if tc else bpw * Z * D)
+    bwd_bytes = bpw * (D * 3 * G + G * 3 * G + G * D + D * Z + Z * D)
+    size = cfg.model_dimension
+    out = {"kernel": ("scan_tc_kernel<FwdPolicy> / <BwdPolicy> (bf16 weight stream, swap-AB tcgen05)" if tc else
+                      "observe scan forward / backward"),
+           "weight_bytes_per_step": fwd_bytes, "bwd_weight_bytes_per_step": bwd_bytes, "weight_dtype": "bf16" if tc else "f32",
+           "us_per_step": us_fwd, "bwd_us_per_step": us_bwd, "peak": pk["hbm"], "unit": "GB/s", "peak_source": pk["src"],
+           "traffic": SCAN_TRAFFIC_PER_STEP.get((size, "fwd")), "bwd_traffic": SCAN_TRAFFIC_PER_STEP.get((size, "bwd"))}
     if cfg.G <= 256:
         out.update({"bound": "latency", "note": "weights resident in the 16-CTA cluster's shared memory for all T steps (no weight "
                     "bytes from HBM / L2 per step): 4 cluster barriers + 4 dependent 16-row contraction stages per step",
                     "achieved": None, "frac": None})
     else:
-        gbs = wbytes / (us_fwd * 1e-6) / 1e9 if us_fwd > 0 else None
-        gbs_b = wbytes / (us_bwd * 1e-6) / 1e9 if us_bwd > 0 else None
+        gbs = fwd_bytes / (us_fwd * 1e-6) / 1e9 if us_fwd > 0 else None
+        gbs_b = bwd_bytes / (us_bwd * 1e-6) / 1e9 if us_bwd > 0 else None
         out.update({"bound": "hbm", "achieved": gbs, "frac": gbs / pk["hbm"] if gbs else None,
                     "bwd_achieved": gbs_b, "bwd_frac": gbs_b / pk["hbm"] if gbs_b else None,
-                    "note": "weights re-read every step (from L2 while they fit its 126 MB, from HBM at XL)"})
+                    "note": ("the step's weights are re-read every step: from HBM at XL (136 MB bf16 > what the 126 MB L2 keeps), from the "
+                             "L2 at S ... L, where the step is a chain of 4 - 5 grid-wide stages (barrier + staging latency), not a "
+                             "bandwidth limit")})
     return out
 
 

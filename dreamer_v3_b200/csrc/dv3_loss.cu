@@ -126,10 +126,39 @@ __global__ void __launch_bounds__(256) wm_losses_kernel(WmLossArgs a) {
     const float* l = a.loc + (size_t)n * a.obs_flat;
     float* d = a.dloc + (size_t)n * a.obs_flat;
     const float sc = 2.f * a.inv_count;
-    for (int i = tid; i < a.obs_flat; i += 256) {
-      const float df = l[i] - o[i];
-      sse += df * df;
-      d[i] = sc * df;
+    if ((a.obs_flat & 3) == 0 && (((uintptr_t)o | (uintptr_t)l | (uintptr_t)d) & 15) == 0) {
+      // image observations (12 288 values per row, 150 MB per update over the three tensors): 128-bit accesses, four
+      // independent load pairs in flight per thread
+      const float4* o4 = reinterpret_cast<const float4*>(o);
+      const float4* l4 = reinterpret_cast<const float4*>(l);
+      float4* d4 = reinterpret_cast<float4*>(d);
+      const int n4 = a.obs_flat >> 2;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int i = tid;
+      for (; i + 3 * 256 < n4; i += 4 * 256) {
+        float4 lv[4], ov[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { lv[j] = __ldg(l4 + i + j * 256); ov[j] = __ldg(o4 + i + j * 256); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 df = make_float4(lv[j].x - ov[j].x, lv[j].y - ov[j].y, lv[j].z - ov[j].z, lv[j].w - ov[j].w);
+          s0 += df.x * df.x; s1 += df.y * df.y; s2 += df.z * df.z; s3 += df.w * df.w;
+          d4[i + j * 256] = make_float4(sc * df.x, sc * df.y, sc * df.z, sc * df.w);   // (stays in the L2 for the decoder backward)
+        }
+      }
+      for (; i < n4; i += 256) {
+        const float4 lv = l4[i], ov = o4[i];
+        const float4 df = make_float4(lv.x - ov.x, lv.y - ov.y, lv.z - ov.z, lv.w - ov.w);
+        s0 += df.x * df.x; s1 += df.y * df.y; s2 += df.z * df.z; s3 += df.w * df.w;
+        d4[i] = make_float4(sc * df.x, sc * df.y, sc * df.z, sc * df.w);
+      }
+      sse = (s0 + s1) + (s2 + s3);
+    } else {
+      for (int i = tid; i < a.obs_flat; i += 256) {
+        const float df = l[i] - o[i];
+        sse += df * df;
+        d[i] = sc * df;
+      }
     }
   }
   sse = warp_sum(sse);
