@@ -383,7 +383,7 @@ def scan_roofline(cfg, us_fwd, us_bwd, pk, mode):
 def allreduce_ms(ctx, job):
     """Device time of the gradient all-reduces of one update in isolation (NCCL over NVLink), max over ranks."""
     e, dist = job.e, ctx.dist
-    bufs = [e.group_buffer(g, "grad") for g in ("world_model", "critic", "actor")]
+    bufs = [e.group_buffer(g, "grad") for g in ("world_model", "actor_critic")]   # the two collectives an update issues
     for _ in range(2):
         for b in bufs:
             dist.all_reduce(b)

@@ -117,8 +117,9 @@ int dv3_read_tensor(dv3_engine* h, const char* name, void* dst, size_t nbytes, i
   return 0;
 }
 int dv3_group_buffer(const dv3_engine* h, int group, int kind, void** ptr, int64_t* numel) {
-  if (group < 0 || group > 3 || kind < 0 || kind > 3 || (group == 3 && kind != 0)) return -1;
   const Engine& e = h->e;
+  if (group == 4 && kind == 1) { *ptr = e.grads[1]; *numel = e.grads_ac_numel; return 0; }   // actor + critic gradients, one span
+  if (group < 0 || group > 3 || kind < 0 || kind > 3 || (group == 3 && kind != 0)) return -1;
   float* p = kind == 0 ? e.params[group] : kind == 1 ? e.grads[group] : kind == 2 ? e.adam_m[group] : e.adam_v[group];
   *ptr = p; *numel = e.numel[group];
   return 0;

@@ -514,15 +514,25 @@ int Engine::init(const dv3_config* c) {
   if (cfg.compute_mode != 0 && cfg.compute_mode != 1) return fail("compute_mode must be 0 (fp32) or 1 (bf16 tensor cores)");
   CK(cudaSetDevice(cfg.device));
   build_param_table();
+  {
+    // the three gradient buffers share one allocation, so that the actor and the critic gradients (adjacent, 256-byte aligned,
+    // zero padding between them) can be all-reduced with ONE collective under data parallelism (dv3_group_buffer group 4)
+    size_t off[4] = {0, 0, 0, 0};
+    for (int g = 0; g < 3; ++g) off[g + 1] = off[g] + (((size_t)numel[g] * 4 + 255) / 256) * 256;
+    char* gb = nullptr;
+    CK(cudaMalloc((void**)&gb, off[3])); allocations.push_back(gb);
+    CK(cudaMemset(gb, 0, off[3]));
+    for (int g = 0; g < 3; ++g) grads[g] = reinterpret_cast<float*>(gb + off[g]);
+    grads_ac_numel = (long long)((off[3] - off[1]) / 4);
+  }
   for (int g = 0; g < 4; ++g) {
     const size_t bytes = (size_t)numel[g] * 4;
     CK(cudaMalloc((void**)&params[g], bytes)); allocations.push_back(params[g]);
     CK(cudaMemset(params[g], 0, bytes));
     if (g < 3) {
-      CK(cudaMalloc((void**)&grads[g], bytes)); allocations.push_back(grads[g]);
       CK(cudaMalloc((void**)&adam_m[g], bytes)); allocations.push_back(adam_m[g]);
       CK(cudaMalloc((void**)&adam_v[g], bytes)); allocations.push_back(adam_v[g]);
-      CK(cudaMemset(grads[g], 0, bytes)); CK(cudaMemset(adam_m[g], 0, bytes)); CK(cudaMemset(adam_v[g], 0, bytes));
+      CK(cudaMemset(adam_m[g], 0, bytes)); CK(cudaMemset(adam_v[g], 0, bytes));
       char* st = nullptr;
       CK(cudaMalloc((void**)&st, 64)); allocations.push_back(st);
       CK(cudaMemset(st, 0, 64));

@@ -66,6 +66,7 @@ struct Engine {
   float* adam_m[3] = {nullptr, nullptr, nullptr};
   float* adam_v[3] = {nullptr, nullptr, nullptr};
   long long numel[4] = {0, 0, 0, 0};
+  long long grads_ac_numel = 0;   // floats from grads[1] to the end of grads[2] (one allocation, padding included)
   AdamState adam[3];
   struct PInfo { std::string name; int group; std::vector<int64_t> shape; long long off; };
   std::vector<PInfo> pinfo;

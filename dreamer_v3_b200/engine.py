@@ -11,7 +11,7 @@ import torch
 from . import _lib
 from .spec import EngineConfig, param_spec
 
-GROUP_IDS = {"world_model": 0, "actor": 1, "critic": 2, "critic_ema": 3}
+GROUP_IDS = {"world_model": 0, "actor": 1, "critic": 2, "critic_ema": 3, "actor_critic": 4}   # 4: gradient span of actor + critic
 
 
 class _CudaView:

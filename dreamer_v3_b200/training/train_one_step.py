@@ -75,9 +75,8 @@ def train_actor_and_critic_one_step(*, world_model_forward_train_outs, is_termin
         e.dp_piece(2, seed)
         dist.all_gather_into_tensor(t("ac.value_targets_all").reshape(-1), t("ac.value_targets").reshape(-1))
         e.dp_piece(3)
-        dist.all_reduce(e.group_buffer("critic", "grad"))
-        if train_actor:
-            dist.all_reduce(e.group_buffer("actor", "grad"))
+        # actor and critic gradients are adjacent in memory: one collective for both
+        dist.all_reduce(e.group_buffer("actor_critic" if train_actor else "critic", "grad"))
         e.dp_piece(4)
         return _ac_results(e, dreamer_model._dream_outs(), train_actor)
     if not _dp(e) and own_states and horizon_H == e.cfg.H:
@@ -98,9 +97,7 @@ def train_actor_and_critic_one_step(*, world_model_forward_train_outs, is_termin
         e.ac_loss_backward(1)
         dist.all_gather_into_tensor(t("ac.value_targets_all").reshape(-1), t("ac.value_targets").reshape(-1))
         e.ac_loss_backward(2)
-        dist.all_reduce(e.group_buffer("critic", "grad"))
-        if train_actor:
-            dist.all_reduce(e.group_buffer("actor", "grad"))
+        dist.all_reduce(e.group_buffer("actor_critic" if train_actor else "critic", "grad"))
     else:
         e.ac_loss_backward(3)
     if train_actor:

@@ -93,7 +93,8 @@ int dv3_find_tensor(const dv3_engine* e, const char* name, dv3_tensor_desc* out)
 /* copy nbytes between a host (or device) buffer and a named engine tensor; host_is_device=1 for D2D */
 int dv3_write_tensor(dv3_engine* e, const char* name, const void* src, size_t nbytes, int src_is_device, void* stream, int sync);
 int dv3_read_tensor(dv3_engine* e, const char* name, void* dst, size_t nbytes, int dst_is_device, void* stream, int sync);
-/* flat per-group views for the data-parallel all-reduce: kind in {0 param,1 grad,2 m,3 v} */
+/* flat per-group views for the data-parallel all-reduce: kind in {0 param,1 grad,2 m,3 v}; group 4 with kind 1 = the actor and
+ * critic gradient buffers as ONE span (adjacent in memory, zero padding between them): one collective for both */
 int dv3_group_buffer(const dv3_engine* e, int group, int kind, void** ptr, int64_t* numel);
 
 /* ---- noise ------------------------------------------------------------------------------- */
