@@ -72,7 +72,9 @@ bool gemm_tma(cudaStream_t s, const GemmArgs& g);  // both operands bf16 K-major
 void to_bf16(cudaStream_t s, const float* src, int lds, void* dst, int ldd, long long rows, int cols);
 // bf16 shadows of weight matrices: out_t[c*rows + r] = bf16(in[r*cols + c]) (transposed), out_n = bf16(in) (plain)
 void weight_shadow_bf16(cudaStream_t s, const float* in, void* out_t, void* out_n, int rows, int cols);
-struct ShadowDesc { const float* in; void* out_t; void* out_n; int rows, cols, tile_begin, pad; };
+// ld_t: row stride of the transposed copy (rows rounded up to 8 elements = 16 bytes, so that every row is a legal TMA row
+// even for K = Z + A input widths such as 1025)
+struct ShadowDesc { const float* in; void* out_t; void* out_n; int rows, cols, tile_begin, ld_t; };
 void weight_shadow_batched(cudaStream_t s, const ShadowDesc* descs_dev, int n, int total_tiles);
 
 // ---- elementwise / normalisation / recurrent cells (dv3_elem.cu) ---------------------------------

@@ -623,11 +623,12 @@ void Engine::build_shadows() {
     if (p.shape.size() < 2) continue;
     const long long cols = p.shape.back(), rows = prod(p.shape) / cols;
     if (rows * cols < 4096) continue;  // too small to ever reach the tensor-core path
-    bytes += (size_t)((rows * cols * 2 + 255) / 256 * 256) * 2;
+    bytes += (size_t)((rows * cols * 2 + 255) / 256 * 256) + (size_t)((((rows + 7) / 8 * 8) * cols * 2 + 255) / 256 * 256);
   }
   char* base = nullptr;
   if (bytes == 0 || cudaMalloc((void**)&base, bytes) != cudaSuccess) return;
   allocations.push_back(base);
+  cudaMemset(base, 0, bytes);   // (the padding columns of the transposed copies are never written)
   size_t off = 0;
   for (const auto& p : pinfo) {
     if (p.shape.size() < 2) continue;
@@ -636,7 +637,8 @@ void Engine::build_shadows() {
     const size_t sz = (size_t)(rows * cols * 2 + 255) / 256 * 256;
     ShadowDesc d{};
     d.in = params[p.group] + p.off; d.rows = (int)rows; d.cols = (int)cols;
-    d.out_t = base + off; off += sz;
+    d.ld_t = (int)((rows + 7) / 8 * 8);
+    d.out_t = base + off; off += (size_t)((size_t)d.ld_t * cols * 2 + 255) / 256 * 256;
     d.out_n = base + off; off += sz;
     d.tile_begin = shadow_tiles;
     shadow_tiles += ((int)cols + 31) / 32 * (((int)rows + 31) / 32);
@@ -652,7 +654,7 @@ const void* Engine::shadow_t(const float* w, int* ld) const {
     if (w < d.in || w >= d.in + (size_t)d.rows * d.cols) continue;
     const size_t off = (size_t)(w - d.in);
     if (off % d.cols != 0) return nullptr;   // only row sub-blocks (K offsets) are addressable in the transposed copy
-    *ld = d.rows;
+    *ld = d.ld_t;
     return reinterpret_cast<const unsigned short*>(d.out_t) + off / d.cols;
   }
   return nullptr;
@@ -752,8 +754,8 @@ GemmArgs Engine::mm_args(const float* A_, int lda, bool ta, const float* B_, int
       const size_t off = (size_t)(B_ - d.in);
       const int r0 = (int)(off / d.cols), c0 = (int)(off % d.cols);
       if (!tb) {  // op(B)(k, n) = W[r0 + k][c0 + n] -> transposed shadow T[c0 + n][r0 + k]
-        g.Bh = reinterpret_cast<const unsigned short*>(d.out_t) + (size_t)c0 * d.rows + r0;
-        g.ldbh = d.rows;
+        g.Bh = reinterpret_cast<const unsigned short*>(d.out_t) + (size_t)c0 * d.ld_t + r0;
+        g.ldbh = d.ld_t;
       } else {    // op(B)(k, n) = W[r0 + n][c0 + k] -> plain shadow
         g.Bh = reinterpret_cast<const unsigned short*>(d.out_n) + off;
         g.ldbh = d.cols;

@@ -572,7 +572,7 @@ __global__ void weight_shadow_batched_kernel(const ShadowDesc* __restrict__ desc
   const int r2 = by * 32 + threadIdx.x;
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int c2 = bx * 32 + i;
-    if (r2 < d.rows && c2 < d.cols) out_t[(size_t)c2 * d.rows + r2] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    if (r2 < d.rows && c2 < d.cols) out_t[(size_t)c2 * d.ld_t + r2] = __float2bfloat16_rn(tile[threadIdx.x][i]);
   }
 }
 }  // namespace
