@@ -3,7 +3,9 @@
 // (row = i*N + n) as in the reference. Heads (reward / continue / critic / EMA critic) run once over all
 // (H+1)*N rows after the rollout; the actor has to run inside it because a_i feeds h_{i+1}.
 #include "dv3_engine.h"
+#include "dv3_dream_tc.h"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace dv3 {
@@ -45,6 +47,51 @@ void Engine::dream_action(int i) {
     actor_fwd(off);
 }
 
+// The H dreamed steps as ONE persistent kernel (dv3_dream_tc.cu): tensor-core mode, XS / S layer sizes, actor-sampled actions.
+bool Engine::dream_rollout_tc(cudaStream_t s) {
+  // opt-in (DV3_DREAM_TC=1): measured on B200 it runs a dreamed step in 65 us at XS - the same as the per-kernel path inside the
+  // replayed CUDA graph (7 - 8 grid-wide stages of 6 - 9 us vs ~17 kernel nodes): correct (parity-tested), not faster
+  const bool opt_in = std::getenv("DV3_DREAM_TC") != nullptr;
+  if (!opt_in || dream_tc_ctas <= 0 || dream_action_mode != 0 || !use_persistent || dr_hz16 == nullptr) return false;
+  const LnLayer& Wx = pre_mlp.layers[0];
+  const LnLayer& Wd = dyn_mlp.layers[0];
+  DreamTcArgs a{};
+  a.N = N; a.H = H; a.G = G; a.D = D; a.Z = Z; a.Zc = Zc; a.Zk = Zk; a.A = A; a.L = L; a.discrete = discrete ? 1 : 0;
+  auto fill = [&](DreamTcMlp& m, const Mlp& w, MlpAct& act) -> bool {
+    for (int l = 0; l < L; ++l) {
+      m.pre[l] = act.pre[l]; m.act[l] = act.act[l]; m.mean[l] = act.mean[l]; m.rstd[l] = act.rstd[l];
+      m.act16[l] = act.act16.empty() ? nullptr : act.act16[l];
+      m.g[l] = w.layers[l].g; m.b[l] = w.layers[l].b;
+      m.wt[l] = shadow_t(w.layers[l].w, &m.ld_wt[l]);
+      if (m.wt[l] == nullptr) return false;
+    }
+    return true;
+  };
+  if (!fill(a.actor, actor_mlp, actor_act)) return false;
+  if (!discrete && !fill(a.actor_std, actor_std_mlp, actor_std_act)) return false;
+  a.actor_out_w = actor_out.w; a.actor_out_b = actor_out.bias; a.std_out_w = actor_std_out.w; a.std_out_b = actor_std_out.bias;
+  a.W_pre_a = Wx.w + (size_t)Z * D;
+  a.pre_g = Wx.g; a.pre_b = Wx.b; a.gru_b = gru_b; a.dyn_g = Wd.g; a.dyn_b = Wd.b; a.zp_bias = dyn_repr.bias;
+  a.Wt_pre_z = shadow_t(Wx.w, &a.ld_pre_z); a.Wt_U = shadow_t(gru_U, &a.ld_U); a.Wt_K = shadow_t(gru_K, &a.ld_K);
+  a.Wt_dyn = shadow_t(Wd.w, &a.ld_dyn); a.Wt_zp = shadow_t(dyn_repr.w, &a.ld_zp);
+  if (!a.Wt_pre_z || !a.Wt_U || !a.Wt_K || !a.Wt_dyn || !a.Wt_zp) return false;
+  if (dr_u16 == nullptr || dr_q_act16 == nullptr) return false;   // the kernel's contractions read the bf16 twins through TMA
+  for (int l = 0; l + 1 < L; ++l)
+    if (a.actor.act16[l] == nullptr || (!discrete && a.actor_std.act16[l] == nullptr)) return false;
+  a.act_noise = in_act_noise; a.u_dyn = in_u_dyn;
+  a.hz = dr_hz; a.hz16 = dr_hz16;
+  a.actor_logits = actor_logits; a.actor_s = actor_s; a.actor_probs = actor_probs; a.a_idx = dr_a_idx; a.dr_act = dr_act;
+  a.x_pre = dr_x_pre; a.x_mean = dr_x_mean; a.x_rstd = dr_x_rstd; a.u = dr_u; a.u16 = dr_u16;
+  a.gx = dr_gx; a.gh = dr_gh; a.zpart = sN_D0; a.gx_raw = sN_3G0;
+  a.q_pre = dr_q_pre; a.q_mean = dr_q_mean; a.q_rstd = dr_q_rstd; a.q_act = dr_q_act; a.q_act16 = dr_q_act16;
+  a.prior_logits = dr_prior_logits; a.prior_probs = dr_prior_probs; a.z_idx = dr_z_idx;
+  a.bar = scan_bar + 48;
+  a.prof = std::getenv("DV3_SCAN_STAMPS") ? scan_stamps + 2048 : nullptr;
+  const cudaError_t ce = launch_dream_tc(s, a, dream_tc_ctas);
+  if (ce != cudaSuccess) { err = std::string("dream rollout (tensor-core) launch: ") + cudaGetErrorString(ce); return false; }
+  return true;
+}
+
 int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
   cur = s;
   last_gamma = gamma;
@@ -64,6 +111,9 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
   auto t16 = [&](void* base, size_t off) -> void* { return base ? (void*)((unsigned short*)base + off) : nullptr; };
   if (hz16p) to_bf16(s, dr_hz, W, hz16p, W, N, W);
   phase_mark("dream.begin");
+  if (dream_rollout_tc(s)) {
+    phase_mark("dream.rollout_tc");
+  } else
   for (int i = 1; i <= H; ++i) {
     const size_t prev = (size_t)(i - 1) * N, curr = (size_t)i * N, st = (size_t)(i - 1) * N;  // st: per-step buffers
     const float* hz_p = dr_hz + prev * W;

@@ -1,6 +1,7 @@
 // Engine construction: parameter table (mirrors dreamer_v3_b200/spec.py), memory layout, weight binding,
 // MLP / dense / conv building blocks. The hot-path orchestration lives in dv3_observe.cu and dv3_dream.cu.
 #include "dv3_engine.h"
+#include "dv3_dream_tc.h"
 
 #include <map>
 
@@ -592,6 +593,7 @@ int Engine::init(const dv3_config* c) {
     if (wb < 8) wb = 8;
     scan_bwd_ctas = wb < max_b ? wb : max_b;
   }
+  dream_tc_ctas = (cfg.compute_mode == 1 && !shadow_host.empty() && dream_tc_supported(N, G, D, Z, Zk, A, L)) ? dream_tc_max_ctas(cfg.device) : 0;
   scan_tc_ctas = (cfg.compute_mode == 1 && gx_acc != nullptr && B <= 16 && !shadow_host.empty()) ? scan_tc_max_ctas(cfg.device) : 0;
   const float nanv[2] = {NAN, NAN};
   CK(cudaMemcpy(pct_ema, nanv, 8, cudaMemcpyHostToDevice));

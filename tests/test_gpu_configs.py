@@ -123,3 +123,29 @@ def test_config_parity_bf16(wid):
         assert max(run.report.values()) > 1e-5  # the tensor-core path really ran (fp32 would sit at ~1e-6)
     finally:
         run.close()
+
+
+@pytest.mark.parametrize("wid", ("c1", "c2", "c3"))
+def test_persistent_dream_kernel_opt_in(wid, monkeypatch):
+    """dv3_dream_tc.cu (DV3_DREAM_TC=1): the H dreamed steps as one persistent tcgen05 kernel (XS / S layer sizes). Not the default
+    path (measured: same speed as the per-kernel path inside the replayed graph), kept under the same parity bar."""
+    from _parity import ParityRun
+    monkeypatch.setenv("DV3_DREAM_TC", "1")
+    cfg = _cfg(wid, SHAPES_BF16[wid])
+    run = ParityRun(cfg, steps=1, compute_mode=1, forced=True)
+    try:
+        launches_tc = run.engine.kernel_launch_count()
+        for k, v in run.forced_violation.items():
+            assert v <= (CONT_TOL if k == "continues" else CDF_TOL), (k, v)
+        bad = {k: v for k, v in run.report.items() if not k.startswith("adam_delta.") and not v <= TOL_BF16_TERMS}
+        assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:20]
+        bad = {k: v for k, v in run.report.items() if k.startswith(FORWARD_CLASS) and k not in LOOSE_FORWARD and not v <= TOL_BF16}
+        assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:20]
+    finally:
+        run.close()
+    monkeypatch.delenv("DV3_DREAM_TC")
+    run2 = ParityRun(cfg, steps=1, compute_mode=1, forced=True)
+    try:
+        assert run2.engine.kernel_launch_count() > launches_tc   # the persistent kernel really replaced the per-step launches
+    finally:
+        run2.close()
