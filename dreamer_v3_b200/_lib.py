@@ -61,6 +61,7 @@ SIGNATURES = {
     "dv3_dp_piece": (_I, [_P, C.POINTER(Dv3Hparams), _I, _U64, _I, _P]),
     "dv3_kernel_launch_count": (_I64, [_P]),
     "dv3_phase_report": (_I, [_P, _I, C.c_char_p, _SZ]),
+    "dv3_scan_tc_schedule_check": (_I, [_I, _I, _I, _I, _I, _I]),
     "dv3_op_symlog": (_I, [_P, _P, _I64, _P]),
     "dv3_op_inverse_symlog": (_I, [_P, _P, _I64, _P]),
     "dv3_op_two_hot": (_I, [_P, _I64, _P, _P, _P, _P, _P, _P]),

@@ -3,6 +3,7 @@
 #include <new>
 
 #include "dv3_engine.h"
+#include "dv3_scan.h"
 
 using dv3::Engine;
 
@@ -77,6 +78,8 @@ int dv3_phase_report(dv3_engine* h, int enable, char* out, size_t cap) {
   out[n] = 0;
   return (int)n;
 }
+
+int dv3_scan_tc_schedule_check(int B, int T, int G, int D, int Z, int ctas) { return dv3::scan_tc_schedule_check(B, T, G, D, Z, ctas); }
 
 int dv3_num_tensors(const dv3_engine* h) { return (int)h->e.tensors.size(); }
 

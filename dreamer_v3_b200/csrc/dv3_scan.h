@@ -92,6 +92,7 @@ struct ScanTcWeightsBwd {
 };
 bool scan_tc_supported(int B, int G, int D, int Z, int Zk);
 int scan_tc_max_ctas(int device);
+int scan_tc_schedule_check(int B, int T, int G, int D, int Z, int ctas);   // host-only walk of the kernels' stream-K schedules
 cudaError_t launch_observe_scan_tc(cudaStream_t s, const ScanFwdParams& p, const ScanTcWeights& w, float* gx_acc, int ctas);
 // q.dp_act and q.du must be zero on entry (accumulators); q.d_hz holds the head / prior gradients
 cudaError_t launch_observe_scan_tc_bwd(cudaStream_t s, const ScanBwdParams& q, const ScanTcWeightsBwd& w, int ctas);

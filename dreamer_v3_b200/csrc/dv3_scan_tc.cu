@@ -30,6 +30,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "dv3_device.cuh"
 #include "dv3_scan.h"
@@ -179,12 +180,12 @@ struct Seg { int prob, tile, chunk, kb0, kb1; };
 // the CTA's contiguous unit range of a stage, cut into segments (one output tile, consecutive k-blocks of one k-chunk)
 struct SegIter {
   int u, u_end, stage;
-  __device__ SegIter(const ScanTcParams& P, int st) : stage(st) {
+  __host__ __device__ SegIter(const ScanTcParams& P, int st, int blk, int nblk) : stage(st) {
     const long long U = P.stage_units[st];
-    u = (int)(U * blockIdx.x / gridDim.x);
-    u_end = (int)(U * (blockIdx.x + 1) / gridDim.x);
+    u = (int)(U * blk / nblk);
+    u_end = (int)(U * (blk + 1) / nblk);
   }
-  __device__ bool next(const ScanTcParams& P, Seg& s) {
+  __host__ __device__ bool next(const ScanTcParams& P, Seg& s) {
     if (u >= u_end) return false;
     int pr = P.stage_p0[stage];
     if (P.stage_np[stage] > 1 && u >= P.prob[pr + 1].unit_begin) ++pr;
@@ -192,7 +193,9 @@ struct SegIter {
     const int local = u - q.unit_begin;
     const int chunk = local / q.span, r = local - chunk * q.span;
     const int tile = r / q.kc, kbi = r - tile * q.kc;
-    const int n = min(q.kc - kbi, min(u_end, q.unit_begin + q.units) - u);
+    int n = q.kc - kbi;
+    const int lim = (u_end < q.unit_begin + q.units ? u_end : q.unit_begin + q.units) - u;
+    if (lim < n) n = lim;
     s.prob = pr; s.tile = tile; s.chunk = chunk; s.kb0 = kbi; s.kb1 = kbi + n;
     u += n;
     return true;
@@ -202,8 +205,8 @@ struct SegIter {
 // by the launcher); identical in the MMA and the worker warps
 struct SlotMap {
   int key[kSlots], n;
-  __device__ SlotMap() : n(0) { key[0] = key[1] = -1; }
-  __device__ int get(const Seg& s, bool& fresh) {
+  __host__ __device__ SlotMap() : n(0) { key[0] = key[1] = -1; }
+  __host__ __device__ int get(const Seg& s, bool& fresh) {
     const int k = s.prob * 4096 + s.chunk;
     fresh = false;
     for (int i = 0; i < n; ++i) if (key[i] == k) return i;
@@ -252,7 +255,7 @@ struct FwdPolicy {
   __device__ static int width_D(const ScanTcParams& P) { return P.p.D; }
   // K = D problems: the CTA reads the 16 full rows once (LayerNorm statistics need them anyway) and stages every k-block of the
   // activation straight from those registers
-  __device__ static bool row_resident(int prob) { return prob == 0 || prob == 3; }
+  __host__ __device__ static bool row_resident(int prob) { return prob == 0 || prob == 3; }
   __device__ static int batch_of(int prob) { return prob == 1 ? 8 : 4; }   // k-blocks per staging event (two thread groups)
   __device__ static bool has_pre_stage(int) { return false; }
   __device__ static void pre_stage(const ScanTcParams&, TcSmem&, int, int, int) {}
@@ -483,7 +486,7 @@ struct BwdPolicy {
   __device__ static const float* ln_vec(const ScanTcParams& P, int i) { return i == 0 ? P.q.pre_g : i == 1 ? P.q.pre_b : i == 2 ? P.q.post_g : P.q.post_b; }
   __device__ static const float* first_flags(const ScanTcParams& P) { return P.q.is_first; }
   __device__ static int width_D(const ScanTcParams& P) { return P.q.D; }
-  __device__ static bool row_resident(int prob) { return prob == 1 || prob == 4; }
+  __host__ __device__ static bool row_resident(int prob) { return prob == 1 || prob == 4; }
 
   // LayerNorm + SiLU backward of the posterior (prob 1: dp_act -> dp_pre) / pre-GRU (prob 4: du -> dx_pre) layer for all 16
   // rows, two rows per warp and round: dn = dy silu'(n) g, dx = rstd (dn - mean(dn) - xhat mean(dn xhat))
@@ -702,9 +705,11 @@ struct BwdPolicy {
 
 // Builds the CTA's schedule of one stage (run once, by one thread): segments in unit order, the activation-chunk slot of each,
 // the staging events in the order the MMA warp first touches what they stage, and per k-block the number of events it needs.
+// Returns 0, or -1 / -2 when the segment / staging table would overflow (the launcher's bounds make that impossible; the host-side
+// check dv3_scan_tc_schedule_check walks every CTA of every size through this very function).
 template <class Pol>
-__device__ void build_stage_sched(const ScanTcParams& P, int st, StageSched& sc) {
-  SegIter si(P, st);
+__host__ __device__ int build_stage_sched(const ScanTcParams& P, int st, StageSched& sc, int blk, int nblk) {
+  SegIter si(P, st, blk, nblk);
   SlotMap slots;
   Seg s;
   unsigned int staged[kSlots] = {0u, 0u};
@@ -715,13 +720,13 @@ __device__ void build_stage_sched(const ScanTcParams& P, int st, StageSched& sc)
     const int sl = slots.get(s, fresh);
     if (fresh) { staged[sl] = 0u; rows_item[sl] = -1; }
     const TcProblem& q = P.prob[s.prob];
-    if (sc.nseg >= kMaxSeg) { printf("dv3 scan_tc: segment table overflow (block %d stage %d)\n", blockIdx.x, st); __trap(); }
+    if (sc.nseg >= kMaxSeg) return -1;
     SegRec& r = sc.seg[sc.nseg++];
     r.prob = (unsigned char)s.prob; r.slot = (unsigned char)sl; r.kb0 = (unsigned char)s.kb0; r.kb1 = (unsigned char)s.kb1;
     r.tile = (unsigned short)s.tile; r.kb_abs0 = (unsigned short)(s.chunk * q.kc + s.kb0);
     for (int kb = s.kb0; kb < s.kb1; ++kb) {
       if (!((staged[sl] >> kb) & 1u)) {
-        if (sc.nitem >= kMaxItems) { printf("dv3 scan_tc: staging table overflow (block %d stage %d)\n", blockIdx.x, st); __trap(); }
+        if (sc.nitem >= kMaxItems) return -2;
         ItemRec& it = sc.item[sc.nitem];
         if (Pol::row_resident(s.prob)) {
           it.rows = 1; it.prob = (unsigned char)s.prob; it.slot = (unsigned char)sl; it.kb = 0; it.kb_abs = 0; it.writer = 0;
@@ -740,7 +745,7 @@ __device__ void build_stage_sched(const ScanTcParams& P, int st, StageSched& sc)
     if (Pol::row_resident(s.prob) && s.tile == 0 && rows_item[sl] >= 0)
       sc.item[rows_item[sl]].writer |= (unsigned short)(((1u << (s.kb1 - s.kb0)) - 1u) << s.kb0);
   }
-  // need[] is exact only for the first touch; later touches may carry a larger count, which is harmless (already completed)
+  return slots.n > kSlots ? -3 : 0;   // (-3: a CTA's range of this stage touched more activation chunks than there are slots)
 }
 
 template <class Pol>
@@ -761,7 +766,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) scan_tc_kernel(const __grid_con
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(32));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (tid >= 64 && tid < 64 + Pol::kGemmStages) build_stage_sched<Pol>(P, tid - 64, sm.sched[tid - 64]);
+  if (tid >= 64 && tid < 64 + Pol::kGemmStages && build_stage_sched<Pol>(P, tid - 64, sm.sched[tid - 64], blockIdx.x, gridDim.x) != 0) {
+    printf("dv3 scan_tc: schedule table overflow (block %d stage %d)\n", blockIdx.x, tid - 64);
+    __trap();
+  }
   {   // LayerNorm gains / offsets and the is_first flags: read thousands of times, and the grid barrier invalidates L1
     const int D = Pol::width_D(P);
     for (int i = tid; i < 4 * D; i += kThreadsTc) sm.ln[i / D][i % D] = Pol::ln_vec(P, i / D)[i % D];
@@ -1005,16 +1013,13 @@ int pick_kc(int kblocks) {
 }
 
 // problem table + stage table + tensor maps; false when a CTA's range of some stage could touch more than kSlots chunks
-bool build_schedule(ScanTcParams& P, TcMaps& maps, int nprob, const int* n_out, const int* K, const void* const* ptr, const int* ld,
-                    int nstage, const int* stage_p0, const int* stage_np, int ctas) {
-  for (int i = 0; i < kMaxProb; ++i) maps.m[i] = maps.m[0];
+bool build_tables(ScanTcParams& P, int nprob, const int* n_out, const int* K, int nstage, const int* stage_p0, const int* stage_np, int ctas) {
   for (int i = 0; i < nprob; ++i) {
     TcProblem& q = P.prob[i];
+    if (n_out[i] % 128 != 0 || K[i] % 64 != 0) return false;
     q.n_out = n_out[i]; q.K = K[i]; q.tiles = n_out[i] / 128; q.kblocks = K[i] / 64; q.kc = pick_kc(q.kblocks);
     q.span = q.tiles * q.kc; q.units = q.tiles * q.kblocks; q.unit_begin = 0;
-    if (!make_wmap(&maps.m[i], ptr[i], n_out[i], K[i], ld[i])) return false;
   }
-  for (int i = nprob; i < kMaxProb; ++i) maps.m[i] = maps.m[0];
   for (int st = 0; st < nstage; ++st) {
     P.stage_p0[st] = stage_p0[st]; P.stage_np[st] = stage_np[st];
     int units = 0, span = 1 << 30;
@@ -1035,6 +1040,66 @@ bool build_schedule(ScanTcParams& P, TcMaps& maps, int nprob, const int* n_out, 
   for (int i = 0; i < nprob; ++i) wbytes += 2LL * n_out[i] * K[i];
   P.evict_first = wbytes > (90LL << 20) ? 1 : 0;   // the bf16 weights of one step do not fit the 126 MB L2 next to everything else
   return P.B * P.T <= kMaxFlags;
+}
+
+// problem table + stage table + tensor maps; false when a CTA's range of some stage could touch more than kSlots chunks
+bool build_schedule(ScanTcParams& P, TcMaps& maps, int nprob, const int* n_out, const int* K, const void* const* ptr, const int* ld,
+                    int nstage, const int* stage_p0, const int* stage_np, int ctas) {
+  if (!build_tables(P, nprob, n_out, K, nstage, stage_p0, stage_np, ctas)) return false;
+  for (int i = 0; i < nprob; ++i)
+    if (!make_wmap(&maps.m[i], ptr[i], n_out[i], K[i], ld[i])) return false;
+  for (int i = nprob; i < kMaxProb; ++i) maps.m[i] = maps.m[0];
+  return true;
+}
+
+void fwd_shapes(int G, int D, int Z, int* n_out, int* K) {
+  const int n[4] = {3 * G, 3 * G, D, Z}, k[4] = {D, G, G, D};
+  for (int i = 0; i < 4; ++i) { n_out[i] = n[i]; K[i] = k[i]; }
+}
+void bwd_shapes(int G, int D, int Z, int* n_out, int* K) {
+  const int n[5] = {D, G, G, D, Z}, k[5] = {Z, D, 3 * G, 3 * G, D};
+  for (int i = 0; i < 5; ++i) { n_out[i] = n[i]; K[i] = k[i]; }
+}
+
+// Host-side walk of the device schedule: every CTA's tables are built with the code the kernel runs and every (contraction,
+// tile, k-block) unit of every stage must be covered exactly once, within the table bounds, with at most kSlots activation chunks
+// per CTA and stage, and with staging counts that never decrease along a CTA's consumption order.
+template <class Pol>
+int check_schedule(ScanTcParams& P, int nprob, int nstage, int ctas) {
+  for (int st = 0; st < nstage; ++st) {
+    std::vector<int> seen;
+    std::vector<int> base(nprob + 1, 0);
+    for (int i = 0; i < nprob; ++i) base[i + 1] = base[i] + P.prob[i].tiles * P.prob[i].kblocks;
+    seen.assign(base[nprob], 0);
+    for (int blk = 0; blk < ctas; ++blk) {
+      StageSched sc;
+      const int rc = build_stage_sched<Pol>(P, st, sc, blk, ctas);
+      if (rc != 0) return -10 + rc;
+      int last_need = 0;
+      for (int g = 0; g < sc.nseg; ++g) {
+        const SegRec& r = sc.seg[g];
+        const TcProblem& q = P.prob[r.prob];
+        if (r.prob < P.stage_p0[st] || r.prob >= P.stage_p0[st] + P.stage_np[st] || r.tile >= q.tiles || r.kb1 > q.kc || r.slot >= kSlots) return -20;
+        for (int kb = r.kb0; kb < r.kb1; ++kb) {
+          const int kb_abs = r.kb_abs0 + (kb - r.kb0);
+          if (kb_abs >= q.kblocks) return -21;
+          ++seen[base[r.prob] + r.tile * q.kblocks + kb_abs];
+          const int need = r.need[kb - r.kb0];
+          if (need < 1 || need > sc.count) return -22;
+          if (need > last_need) last_need = need;
+        }
+      }
+      if (last_need != sc.count) return -23;
+    }
+    for (int i = P.stage_p0[st]; i < P.stage_p0[st] + P.stage_np[st]; ++i)
+      for (int u = base[i]; u < base[i + 1]; ++u)
+        if (seen[u] != 1) return -30;
+    for (int i = 0; i < nprob; ++i)
+      if (i < P.stage_p0[st] || i >= P.stage_p0[st] + P.stage_np[st])
+        for (int u = base[i]; u < base[i + 1]; ++u)
+          if (seen[u] != 0) return -31;
+  }
+  return 0;
 }
 
 template <class Pol>
@@ -1066,6 +1131,31 @@ bool scan_tc_supported(int B, int G, int D, int Z, int Zk) {
          std::getenv("DV3_NO_SCAN_TC") == nullptr;
 }
 
+// 0 = the stream-K schedules of both scan kernels are valid for these sizes on `ctas` CTAs; 1 = sizes not handled by the kernels
+// (the engine then uses the other scan paths); < 0 = a defect of the schedule (see check_schedule)
+int scan_tc_schedule_check(int B, int T, int G, int D, int Z, int ctas) {
+  if (!(D % 128 == 0 && G % 128 == 0 && Z % 128 == 0 && D >= 512 && D <= 1024 && G >= 512 && B <= kRows) || ctas < 1) return 1;
+  const int sp0f[3] = {0, 2, 3}, snpf[3] = {2, 1, 1}, sp0b[4] = {0, 1, 2, 4}, snpb[4] = {1, 1, 2, 1};
+  int n_out[5], K[5];
+  {
+    ScanTcParams P{};
+    P.B = B; P.T = T;
+    fwd_shapes(G, D, Z, n_out, K);
+    if (!build_tables(P, 4, n_out, K, 3, sp0f, snpf, ctas)) return 1;
+    const int rc = check_schedule<FwdPolicy>(P, 4, 3, ctas);
+    if (rc != 0) return rc;
+  }
+  {
+    ScanTcParams P{};
+    P.B = B; P.T = T;
+    bwd_shapes(G, D, Z, n_out, K);
+    if (!build_tables(P, 5, n_out, K, 4, sp0b, snpb, ctas)) return 1;
+    const int rc = check_schedule<BwdPolicy>(P, 5, 4, ctas);
+    if (rc != 0) return rc - 100;
+  }
+  return 0;
+}
+
 int scan_tc_max_ctas(int device) {
   const int a = max_ctas<FwdPolicy>(device), b = max_ctas<BwdPolicy>(device);
   return a < b ? a : b;
@@ -1075,7 +1165,8 @@ cudaError_t launch_observe_scan_tc(cudaStream_t s, const ScanFwdParams& p, const
   ScanTcParams P{};
   P.p = p; P.gx_acc = gx_acc; P.B = p.B; P.T = p.T; P.bar = p.bar; P.stamps = p.stamps;
   const int G = p.G, D = p.D, Z = p.Z;
-  const int n_out[4] = {3 * G, 3 * G, D, Z}, K[4] = {D, G, G, D};
+  int n_out[4], K[4];
+  fwd_shapes(G, D, Z, n_out, K);
   const void* ptr[4] = {w.Kt, w.Ut, w.Wpost_h_t, w.Wzq_t};
   const int ld[4] = {w.ld_Kt, w.ld_Ut, w.ld_Wpost_h_t, w.ld_Wzq_t};
   const int sp0[3] = {0, 2, 3}, snp[3] = {2, 1, 1};
@@ -1095,7 +1186,8 @@ cudaError_t launch_observe_scan_tc_bwd(cudaStream_t s, const ScanBwdParams& q, c
   ScanTcParams P{};
   P.q = q; P.B = q.B; P.T = q.T; P.bar = q.bar; P.stamps = q.stamps;
   const int G = q.G, D = q.D, Z = q.Z;
-  const int n_out[5] = {D, G, G, D, Z}, K[5] = {Z, D, 3 * G, 3 * G, D};
+  int n_out[5], K[5];
+  bwd_shapes(G, D, Z, n_out, K);
   const void* ptr[5] = {w.Wzq, w.Wpost_h, w.U, w.K, w.Wpre_z};
   const int ld[5] = {w.ld_Wzq, w.ld_Wpost_h, w.ld_U, w.ld_K, w.ld_Wpre_z};
   const int sp0[4] = {0, 1, 2, 4}, snp[4] = {1, 1, 2, 1};

@@ -183,6 +183,10 @@ int64_t dv3_kernel_launch_count(const dv3_engine* e); /* kernels of this library
  * accumulated per label since the last report as "label ms count" lines into out (capacity cap, NUL-terminated), then
  * clears the record. Returns the number of bytes written, <0 on error. */
 int dv3_phase_report(dv3_engine* e, int enable, char* out, size_t cap);
+/* Host-only self-check of the stream-K schedules of the tensor-core observe-scan kernels (world_model.py:244-273 on S ... XL):
+ * walks every CTA's segment / staging tables with the code the kernels run. 0 = valid, 1 = these sizes are not handled by those
+ * kernels (other scan paths are used), < 0 = defect. Needs no GPU. */
+int dv3_scan_tc_schedule_check(int B, int T, int G, int D, int Z, int ctas);
 
 /* ---- isolated ops (parity tests call the same kernels the fused path uses) ---------------------- */
 int dv3_op_symlog(const float* x, float* y, int64_t n, void* stream);                 /* utils/symlog.py:9-12 */

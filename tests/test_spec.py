@@ -100,3 +100,24 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".h", ".cuh")):
                 src = open(os.path.join(d, f)).read()
                 assert "oracle" not in src.lower() or f.endswith((".cu", ".cuh", ".h")) and "import" not in src, f
+
+
+@pytest.mark.parametrize("size", ("S", "M", "L", "XL"))
+@pytest.mark.parametrize("ctas", (148, 132, 96, 37))
+def test_scan_tc_stream_k_schedule(size, ctas):
+    """Host-only walk of the stream-K schedules of the tensor-core observe-scan kernels (csrc/dv3_scan_tc.cu; the work of
+    world_model.py:244-273 and its BPTT cut into per-CTA segment / staging tables): built with the very code the kernels run, every
+    (contraction, tile, k-block) unit must be covered exactly once on any grid size, within the table bounds."""
+    cfg = EngineConfig.make(size, action_space=Discrete(6), image_obs=True)
+    lib = _lib.load()
+    rc = lib.dv3_scan_tc_schedule_check(16, 64, cfg.G, cfg.D, cfg.Z, ctas)
+    assert rc in (0, 1), rc      # 1: this size / grid is routed to the other scan kernels (launcher bounds), never a defect
+    if ctas == 148:
+        assert rc == 0, (size, rc)   # the B200 grid must be schedulable at every size
+
+
+def test_scan_tc_schedule_check_rejects_other_sizes():
+    lib = _lib.load()
+    assert lib.dv3_scan_tc_schedule_check(16, 64, 256, 256, 1024, 148) == 1     # XS: cluster kernel
+    assert lib.dv3_scan_tc_schedule_check(17, 64, 512, 512, 1024, 148) == 1     # more than 16 rows
+    assert lib.dv3_scan_tc_schedule_check(16, 1024, 512, 512, 1024, 148) == 1   # is_first flags do not fit shared memory
