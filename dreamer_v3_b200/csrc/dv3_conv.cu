@@ -66,21 +66,23 @@ __global__ void col2im_kernel(const float* __restrict__ cols, float* __restrict_
   }
 }
 
-__global__ void im2col_v4_kernel(const float4* __restrict__ img, float4* __restrict__ cols, int n, int H, int W, int C4,
-                                 uint2* __restrict__ cols16) {
+// grid.y = one row of output pixels (b, oy); grid.x x 256 threads cover its (ox, tap, 4-channel group) elements: a single
+// 32-bit division per thread (the flat 64-bit index decode of the first version cost more than the memory traffic)
+__global__ void __launch_bounds__(256) im2col_v4_kernel(const float4* __restrict__ img, float4* __restrict__ cols, int n, int H, int W, int C4,
+                                                        uint2* __restrict__ cols16) {
   const int Ho = H / 2, Wo = W / 2;
-  const long long total = (long long)n * Ho * Wo * 16 * C4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4);
-    long long t = i / C4;
-    const int kx = (int)(t & 3); t >>= 2;
-    const int ky = (int)(t & 3); t >>= 2;
-    const int ox = (int)(t % Wo); t /= Wo;
-    const int oy = (int)(t % Ho); t /= Ho;
-    const int b = (int)t;
-    const int y = 2 * oy - 1 + ky, x = 2 * ox - 1 + kx;
+  const unsigned per_row = (unsigned)Wo * 16u * (unsigned)C4;
+  const unsigned j = blockIdx.x * 256u + threadIdx.x;
+  if (j >= per_row) return;
+  const unsigned t = j / (unsigned)C4, c = j - t * (unsigned)C4;
+  const int kx = (int)(t & 3u), ky = (int)((t >> 2) & 3u), ox = (int)(t >> 4);
+  const int x = 2 * ox - 1 + kx;
+  for (unsigned row = blockIdx.y; row < (unsigned)n * (unsigned)Ho; row += gridDim.y) {
+    const unsigned b = row / (unsigned)Ho, oy = row - b * (unsigned)Ho;
+    const int y = 2 * (int)oy - 1 + ky;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (y >= 0 && y < H && x >= 0 && x < W) v = img[(((size_t)b * H + y) * W + x) * C4 + c];
+    const size_t i = (size_t)row * per_row + j;
     if (cols != nullptr) cols[i] = v;   // (null: every consumer reads the bf16 patch matrix)
     if (cols16 != nullptr) {   // bf16 twin of the patch matrix for the TMA-fed contraction
       __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
@@ -133,7 +135,7 @@ inline int grid_for(long long n) {
 
 void im2col_k4s2(cudaStream_t s, const float* img, float* cols, int n, int H, int W, int C, void* cols16) {
   if (C % 4 == 0 && ((uintptr_t)img % 16 == 0) && ((uintptr_t)cols % 16 == 0) && ((uintptr_t)cols16 % 8 == 0))
-    im2col_v4_kernel<<<grid_for((long long)n * (H / 2) * (W / 2) * 16 * (C / 4)), 256, 0, s>>>(
+    im2col_v4_kernel<<<dim3((unsigned)(((W / 2) * 16 * (C / 4) + 255) / 256), (unsigned)(n * (H / 2) < 65535 ? n * (H / 2) : 65535)), 256, 0, s>>>(
         reinterpret_cast<const float4*>(img), reinterpret_cast<float4*>(cols), n, H, W, C / 4, reinterpret_cast<uint2*>(cols16));
   else   // (n * Ho * Wo * 16 < 2^31 for every configuration: 16 M at B16 x T64 x 64 x 64 inputs)
     im2col_kernel<<<grid_for((long long)n * (H / 2) * (W / 2) * 16), 256, 0, s>>>(img, cols, n, H, W, C,
