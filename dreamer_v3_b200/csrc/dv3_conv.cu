@@ -92,18 +92,19 @@ __global__ void __launch_bounds__(256) im2col_v4_kernel(const float4* __restrict
   }
 }
 
-__global__ void col2im_v4_kernel(const float4* __restrict__ cols, float4* __restrict__ img, int n, int H, int W, int C4,
-                                 const float* __restrict__ bias, float add_const) {
+// grid.y = one row of image pixels (b, y); grid.x x 256 threads cover its (x, 4-channel group) elements
+__global__ void __launch_bounds__(256) col2im_v4_kernel(const float4* __restrict__ cols, float4* __restrict__ img, int n, int H, int W, int C4,
+                                                        const float* __restrict__ bias, float add_const) {
   const int Ho = H / 2, Wo = W / 2;
-  const long long total = (long long)n * H * W * C4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4);
-    long long t = i / C4;
-    const int x = (int)(t % W); t /= W;
-    const int y = (int)(t % H); t /= H;
-    const int b = (int)t;
-    float4 acc = make_float4(add_const, add_const, add_const, add_const);
-    if (bias != nullptr) { acc.x += bias[4 * c]; acc.y += bias[4 * c + 1]; acc.z += bias[4 * c + 2]; acc.w += bias[4 * c + 3]; }
+  const unsigned per_row = (unsigned)W * (unsigned)C4;
+  const unsigned j = blockIdx.x * 256u + threadIdx.x;
+  if (j >= per_row) return;
+  const int x = (int)(j / (unsigned)C4), c = (int)(j - (unsigned)x * (unsigned)C4);
+  float4 acc0 = make_float4(add_const, add_const, add_const, add_const);
+  if (bias != nullptr) { acc0.x += bias[4 * c]; acc0.y += bias[4 * c + 1]; acc0.z += bias[4 * c + 2]; acc0.w += bias[4 * c + 3]; }
+  for (unsigned row = blockIdx.y; row < (unsigned)n * (unsigned)H; row += gridDim.y) {
+    const int b = (int)(row / (unsigned)H), y = (int)(row - (unsigned)b * (unsigned)H);
+    float4 acc = acc0;
 #pragma unroll
     for (int ky = 0; ky < 4; ++ky) {
       const int ty = y + 1 - ky;
@@ -120,7 +121,7 @@ __global__ void col2im_v4_kernel(const float4* __restrict__ cols, float4* __rest
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
     }
-    img[i] = acc;
+    img[(size_t)row * per_row + j] = acc;
   }
 }
 
@@ -145,7 +146,7 @@ void im2col_k4s2(cudaStream_t s, const float* img, float* cols, int n, int H, in
 void col2im_k4s2(cudaStream_t s, const float* cols, float* img, int n, int H, int W, int C, const float* bias,
                  float add_const) {
   if (C % 4 == 0 && ((uintptr_t)img % 16 == 0) && ((uintptr_t)cols % 16 == 0))
-    col2im_v4_kernel<<<grid_for((long long)n * H * W * (C / 4)), 256, 0, s>>>(
+    col2im_v4_kernel<<<dim3((unsigned)((W * (C / 4) + 255) / 256), (unsigned)(n * H < 65535 ? n * H : 65535)), 256, 0, s>>>(
         reinterpret_cast<const float4*>(cols), reinterpret_cast<float4*>(img), n, H, W, C / 4, bias, add_const);
   else
     col2im_kernel<<<grid_for((long long)n * H * W * C), 256, 0, s>>>(cols, img, n, H, W, C, bias, add_const);
