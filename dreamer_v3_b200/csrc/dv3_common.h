@@ -218,6 +218,25 @@ void box_actor_bwd(cudaStream_t s, const float* mu, const float* sraw, const flo
 void disc_actor_fwd(cudaStream_t s, const float* logits, const float* u, float* probs, int32_t* idx, float* a,
                     int lda, long long rows, int A);
 
+// Fused actor tail + sequence-model input layer of one dreamed step (dv3_actor_step.cu): LN+SiLU of the actor's last hidden layer,
+// its D x A output layer, the action sample, x_pre += a . W_pre[Z:], u = SiLU(LN(x_pre)). All pointers address the first row.
+constexpr int kActorStepMaxA = 8;
+struct ActorStepNet {   // last hidden layer of the actor (net 0) / of its std net (net 1, Box spaces)
+  const float* pre; float* act; void* act16; float* mean; float* rstd;
+  const float* g; const float* b;           // LayerNorm gain / offset
+  const float* out_w; const float* out_b;   // [D, A], [A]
+};
+struct ActorStepArgs {
+  long long rows; int D, A, discrete, do_pre;
+  ActorStepNet net[2];
+  const float* noise;                        // uniforms [rows] (discrete) or standard normals [rows, A] (Box)
+  float* logits; float* s_raw; float* probs; int32_t* a_idx; float* act;   // [rows, A] ([rows] for a_idx)
+  const float* W_pre_a; const float* pre_g; const float* pre_b;            // rows Z.. of the pre-GRU layer [A, D], its LayerNorm
+  float* x_pre; float* x_mean; float* x_rstd; float* u; void* u16;         // x_pre holds z . W_pre[:Z] on entry
+};
+bool actor_step_supported(int D, int A);
+cudaError_t actor_step(cudaStream_t s, const ActorStepArgs& a);
+
 // ---- optimizer (dv3_optim.cu) ---------------------------------------------------------------------------
 // stats[0] = sum of squares (as double bits in 2 floats? no: separate double*), see implementation.
 struct AdamState {

@@ -37,6 +37,51 @@ void Engine::actor_fwd(long long row_off) {
   }
 }
 
+// The fused path: the actor's contractions (everything up to the last hidden layer's pre-activation) ...
+bool Engine::actor_step_applicable(int i) const {
+  static const bool off = std::getenv("DV3_NO_ACTOR_STEP") != nullptr;
+  const bool given = dream_action_mode == 2 || (dream_action_mode == 1 && i == 0);
+  return !off && !given && actor_step_supported(D, A);
+}
+void Engine::actor_step_mlps(long long row_off) {
+  const float* x = dr_hz + (size_t)row_off * (G + Z);
+  const void* x16 = dr_hz16 ? (const void*)((const unsigned short*)dr_hz16 + (size_t)row_off * (G + Z)) : nullptr;
+  if (discrete) {
+    mlp_fwd(actor_mlp, actor_act, x, G + Z, N, row_off, x16, true);
+  } else {
+    run_branches({[&] { mlp_fwd(actor_mlp, actor_act, x, G + Z, N, row_off, x16, true); },
+                  [&] { mlp_fwd(actor_std_mlp, actor_std_act, x, G + Z, N, row_off, x16, true); }});
+  }
+}
+// ... and its tail: LN+SiLU of that layer, the output layer, the sample and (with_pre) the pre-GRU layer of step i + 1
+int Engine::actor_step_tail(int i, bool with_pre) {
+  const size_t off = (size_t)i * N;
+  const LnLayer& Wx = pre_mlp.layers[0];
+  ActorStepArgs a{};
+  a.rows = N; a.D = D; a.A = A; a.discrete = discrete ? 1 : 0; a.do_pre = with_pre ? 1 : 0;
+  auto fill = [&](ActorStepNet& n, const Mlp& w, MlpAct& act, const DenseLayer& head) {
+    const size_t l = w.layers.size() - 1;
+    n.pre = act.pre[l] + off * D; n.act = act.act[l] + off * D;
+    n.act16 = N >= 128 && !act.act16.empty() && act.act16[l] ? (void*)((unsigned short*)act.act16[l] + off * D) : nullptr;
+    n.mean = act.mean[l] + off; n.rstd = act.rstd[l] + off; n.g = w.layers[l].g; n.b = w.layers[l].b;
+    n.out_w = head.w; n.out_b = head.bias;
+  };
+  fill(a.net[0], actor_mlp, actor_act, actor_out);
+  if (!discrete) fill(a.net[1], actor_std_mlp, actor_std_act, actor_std_out);
+  a.noise = in_act_noise + off * (discrete ? 1 : A);
+  a.logits = actor_logits + off * A; a.s_raw = actor_s ? actor_s + off * A : nullptr;
+  a.probs = actor_probs ? actor_probs + off * A : nullptr; a.a_idx = dr_a_idx ? dr_a_idx + off : nullptr;
+  a.act = dr_act + off * A;
+  if (with_pre) {
+    a.W_pre_a = Wx.w + (size_t)Z * D; a.pre_g = Wx.g; a.pre_b = Wx.b;
+    a.x_pre = dr_x_pre + off * D; a.x_mean = dr_x_mean + off; a.x_rstd = dr_x_rstd + off; a.u = dr_u + off * D;
+    a.u16 = dr_u16 ? (void*)((unsigned short*)dr_u16 + off * D) : nullptr;
+  }
+  const cudaError_t ce = actor_step(cur, a);
+  if (ce != cudaSuccess) return fail(std::string("actor step launch: ") + cudaGetErrorString(ce));
+  return 0;
+}
+
 // Action of dream step i: the actor's sample, or the caller's (dream_trajectory_with_burn_in, dreamer_model.py:306-413:
 // a_0 = the last burn-in action; with use_sampled_actions / use_random_actions every action is given).
 void Engine::dream_action(int i) {
@@ -120,12 +165,18 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
     float* hz_c = dr_hz + curr * W;
     // Everything that only needs [h, z]_{i-1} runs concurrently: the actor (its action a_{i-1} enters the sequence model
     // through the small a-part of the pre-GRU layer only), the z-part of that layer, and h_{i-1} . U.
-    run_branches({[&] { dream_action(i - 1); },
+    const bool fused = actor_step_applicable(i - 1);
+    run_branches({[&] { if (fused) actor_step_mlps((long long)prev); else dream_action(i - 1); },
                   [&] { mm(hz_p + G, W, false, Wx.w, D, false, dr_x_pre + st * D, D, N, D, Z, nullptr, 0.f, h16(prev, G)); },
                   [&] { mm(hz_p, W, false, gru_U, 3 * G, false, dr_gh + st * 3 * G, 3 * G, N, 3 * G, G, gru_b + 3 * G, 0.f, h16(prev, 0)); }});
     phase_mark("dream.actor|z|gh");
-    mm(dr_act + prev * A, A, false, Wx.w + (size_t)Z * D, D, false, dr_x_pre + st * D, D, N, D, A, nullptr, 1.f);
-    ln_silu_fwd(s, dr_x_pre + st * D, D, Wx.g, Wx.b, dr_u + st * D, D, dr_x_mean + st, dr_x_rstd + st, 1, N, D, t16(dr_u16, st * D));
+    if (fused) {
+      // actor tail, a . W_pre[Z:] and the pre-GRU LayerNorm in one launch
+      if (int rc = actor_step_tail(i - 1, true)) return rc;
+    } else {
+      mm(dr_act + prev * A, A, false, Wx.w + (size_t)Z * D, D, false, dr_x_pre + st * D, D, N, D, A, nullptr, 1.f);
+      ln_silu_fwd(s, dr_x_pre + st * D, D, Wx.g, Wx.b, dr_u + st * D, D, dr_x_mean + st, dr_x_rstd + st, 1, N, D, t16(dr_u16, st * D));
+    }
     mm(dr_u + st * D, D, false, gru_K, 3 * G, false, dr_gx + st * 3 * G, 3 * G, N, 3 * G, D, gru_b, 0.f, t16(dr_u16, st * D));
     phase_mark("dream.pre+gx");
     gru_fwd(s, dr_gx + st * 3 * G, 3 * G, dr_gh + st * 3 * G, 3 * G, hz_p, W, hz_c, W, N, G, h16(curr, 0));
@@ -160,7 +211,10 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
         mm(ema_act.act.back(), D, false, ema_head.w, DV3_NB, false, ema_logits, DV3_NB, R, DV3_NB, D, ema_head.bias, 0.f, ema_act.act16.back());
         bucket_expectation(cur, ema_logits, DV3_NB, ema_E, R);
       },
-      [&] { dream_action(H); }});
+      [&] {
+        if (actor_step_applicable(H)) { actor_step_mlps((long long)H * N); actor_step_tail(H, false); }
+        else dream_action(H);
+      }});
   phase_mark("dream.heads");
   // real-space rewards / continues / values, loss weights (dreamer_model.py:219-280) and lambda-returns
   AcArgs a{};

@@ -209,8 +209,9 @@ struct Engine {
   // would this mm() run on the TMA-fed kernel, i.e. read only the bf16 copies of its operands?
   bool mm_tma(const float* A_, int lda, bool ta, const float* B_, int ldb, bool tb, float* C, int ldc, int M, int N_, int K,
               const void* A16, const void* B16) const;
+  // skip_last_ln: leave the last layer at its pre-activation (the caller's fused kernel applies LN+SiLU)
   void mlp_fwd(const Mlp& m, MlpAct& a, const float* x, int ldx, long long rows, long long row_off = 0,
-               const void* x16 = nullptr);
+               const void* x16 = nullptr, bool skip_last_ln = false);
   // ---- bf16 twins of activation buffers that feed large contractions (tensor-core mode only) ----
   std::unordered_map<const float*, void*> twins;
   void* twin_alloc(const float* base, size_t elems);
@@ -232,6 +233,11 @@ struct Engine {
   int optimizer_step(int group, float clip, float lr, float eps, float ema_decay, cudaStream_t s);
   int dream_forward(float gamma, int start_from_observe, cudaStream_t s);
   void actor_fwd(long long row_off);
+  // actor of dream step i fused with the sequence model's input layer of step i + 1 (dv3_actor_step.cu); with_pre = false for the
+  // last dreamed state, whose action is not fed back. false: not applicable (caller takes the per-op path)
+  bool actor_step_applicable(int i) const;
+  void actor_step_mlps(long long row_off);
+  int actor_step_tail(int i, bool with_pre);
   int ac_loss_backward(const dv3_hparams* hp, int phase, cudaStream_t s);
   void actor_backward(const dv3_hparams* hp, const AcArgs& a);
   int fill_noise(uint64_t seed, uint64_t step, int which, bool device_step, cudaStream_t s);

@@ -53,7 +53,7 @@ int Engine::observe_forward(cudaStream_t s) {
     sp.p_act = p_act; sp.post_logits = post_logits; sp.post_probs = post_probs; sp.z_idx = z_idx;
     sp.stamps = std::getenv("DV3_SCAN_STAMPS") ? scan_stamps : nullptr;
     sp.bar = scan_bar;
-    cudaError_t ce = scan_cluster_supported(sp) ? launch_observe_scan_cluster(s, sp) : launch_observe_scan_fwd(s, sp, scan_ctas);
+    cudaError_t ce = scan_cluster_supported(sp) ? launch_observe_scan_cluster(s, sp, cfg.compute_mode == 1) : launch_observe_scan_fwd(s, sp, scan_ctas);
     if (ce != cudaSuccess) return fail(std::string("observe scan launch: ") + cudaGetErrorString(ce));
     return 0;
   };

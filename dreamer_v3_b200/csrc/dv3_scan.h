@@ -73,7 +73,8 @@ int scan_fwd_max_ctas(int device);  // 0 when the kernel cannot be made co-resid
 cudaError_t launch_observe_scan_fwd(cudaStream_t s, const ScanFwdParams& p, int ctas);
 // single 16-CTA cluster version (dv3_scan_cluster.cu): weights resident in the cluster's shared memory, DSMEM exchange
 bool scan_cluster_supported(const ScanFwdParams& p);
-cudaError_t launch_observe_scan_cluster(cudaStream_t s, const ScanFwdParams& p);
+// bf16: tensor-core variant (bf16 weights resident on chip incl. the gathered W_pre rows, mma.sync contractions)
+cudaError_t launch_observe_scan_cluster(cudaStream_t s, const ScanFwdParams& p, bool bf16);
 
 // weight-streaming tensor-core version (dv3_scan_tc.cu; S ... XL in compute_mode 1): bf16 K-major weight shadows [N_out, K]
 struct ScanTcWeights {

@@ -18,8 +18,10 @@
 //   D  p_act = SiLU(LN(p_pre)) in place; logits[:, my 64 cols] = p_act . W_zq + b; softmax, 1% unimix, fp64 inverse-CDF
 //      sample of my 2 categoricals                                                          -> idx to all peers
 #include <cooperative_groups.h>
+#include <cuda_bf16.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "dv3_scan_common.cuh"
 
@@ -36,10 +38,9 @@ constexpr int kZC = 64;       // posterior logit columns owned per CTA (2 catego
 constexpr int kG = kC * kU;   // 256
 constexpr int kLd = kInLd;    // 20: row stride of the [k][row] staging buffers
 
-struct CSmem {
-  float wK[kG][3 * kU];       // K[:, gate*G + my units]            48 KB
-  float wU[kG][3 * kU];       // U[:, gate*G + my units]            48 KB
-  float wZ[kG][kZC];          // W_zq[:, my 64 columns]             64 KB
+constexpr int kWLd = kG + 8; // k stride of a resident bf16 weight column (tensor-core variant): conflict-free fragment loads
+
+struct CCommon {
   float buf0[kG][kLd];        // x_pre -> u, then p_pre -> p_act    20 KB   [k][row]
   float buf1[kG][kLd];        // h; cross-warp scratch in stage D   20 KB
   float red[4 * kRows * (3 * kU + 1)];   // k-slice partial sums of a 48-column pass ([4][16][49]); also the 16-column p_pre pass
@@ -52,7 +53,19 @@ struct CSmem {
   float h0[kG];               // learned initial state
   float lnp[4][kG];           // LayerNorm gain / offset of the pre-GRU and the posterior layer
 };
-static_assert(sizeof(CSmem) <= 227 * 1024, "cluster scan shared memory");
+struct CSmem : CCommon {      // fp32 variant: weights [k][column]
+  float wK[kG][3 * kU];       // K[:, gate*G + my units]            48 KB
+  float wU[kG][3 * kU];       // U[:, gate*G + my units]            48 KB
+  float wZ[kG][kZC];          // W_zq[:, my 64 columns]             64 KB
+};
+struct CSmemTc : CCommon {    // tensor-core variant: bf16 weights [column][k] (the col-major B operand of mma.m16n8k16)
+  __nv_bfloat16 wK[3 * kU][kWLd];   // 25 KB
+  __nv_bfloat16 wU[3 * kU][kWLd];   // 25 KB
+  __nv_bfloat16 wZ[kZC][kWLd];      // 33 KB
+  __nv_bfloat16 wP[kU][kWLd];       // W_post[E:][:, my 16 columns]    8 KB
+  __nv_bfloat16 wX[kC * kZC][kU];   // W_pre[:Z][:, my 16 columns]    32 KB: the one-hot row gather of stage A stays on chip
+};
+static_assert(sizeof(CSmem) <= 227 * 1024 && sizeof(CSmemTc) <= 227 * 1024, "cluster scan shared memory");
 
 // Register-tiled contraction of the 16 staged rows with NC = 16 * CPL resident weight columns, K = 256:
 // warp -> (k-slice of 64, column half), lane -> (4 rows, CPL columns): one LDS.128 of activations and CPL weights feed
@@ -100,9 +113,85 @@ __device__ __forceinline__ float red_sum(const float* red, int b, int col) {
          red[(3 * kRows + b) * (NC + 1) + col];
 }
 
+// Tensor-core variant of the contractions. The batch is 16 rows, so the shape is mma.sync m16n8k16 (tcgen05 starts at M = 64
+// and takes a TMEM round trip per result; here the whole pass is a dozen warp-level MMAs per warp). A fragments come straight
+// from the fp32 [k][row] staging buffer (rounded to bf16 here), B fragments from the resident bf16 columns W16[n][k].
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// A fragment of rows 0..15, k in [kb, kb + 16) (lane: g = lane / 4 -> rows g, g + 8; tq = lane % 4 -> k pairs 2 tq, 2 tq + 8)
+__device__ __forceinline__ void load_a_frag(const float* in_s, int kb, int g, int tq, uint32_t (&a)[4]) {
+  const float* ap = in_s + (size_t)(kb + 2 * tq) * kLd + g;
+  a[0] = pack2_bf16(ap[0], ap[kLd]);
+  a[1] = pack2_bf16(ap[8], ap[kLd + 8]);
+  a[2] = pack2_bf16(ap[8 * kLd], ap[9 * kLd]);
+  a[3] = pack2_bf16(ap[8 * kLd + 8], ap[9 * kLd + 8]);
+}
+// NC = 48 / 64 columns: warp -> (k-slice of 64, column half); leaves the four k-slice partial sums in red[ks][row][col] like tile_pass
+template <int NC>
+__device__ __forceinline__ void mma_pass(const float* in_s, const __nv_bfloat16* W16, float* red) {
+  constexpr int NT = NC / 16;   // n-tiles (8 columns) per warp
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ks = warp & 3, half = warp >> 2, g = lane >> 2, tq = lane & 3;
+  float c[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) { c[nt][0] = 0.f; c[nt][1] = 0.f; c[nt][2] = 0.f; c[nt][3] = 0.f; }
+#pragma unroll
+  for (int st = 0; st < 4; ++st) {
+    const int kb = 64 * ks + 16 * st;
+    uint32_t a[4];
+    load_a_frag(in_s, kb, g, tq, a);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const uint32_t* bp = reinterpret_cast<const uint32_t*>(W16 + (size_t)((half * NT + nt) * 8 + g) * kWLd + kb + 2 * tq);
+      mma_bf16_16816(c[nt], a[0], a[1], a[2], a[3], bp[0], bp[4]);
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int col = (half * NT + nt) * 8 + 2 * tq;
+    float* r0 = red + (size_t)(ks * kRows + g) * (NC + 1) + col;
+    float* r1 = red + (size_t)(ks * kRows + g + 8) * (NC + 1) + col;
+    r0[0] = c[nt][0]; r0[1] = c[nt][1]; r1[0] = c[nt][2]; r1[1] = c[nt][3];
+  }
+  __syncthreads();
+}
+// the 16-column p_pre pass: warp -> k-slice of 32, both n-tiles; partial sums in red[warp][row][17]
+__device__ __forceinline__ void mma_pass16(const float* in_s, const __nv_bfloat16* W16, float* red) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+  float c[2][4];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) { c[nt][0] = 0.f; c[nt][1] = 0.f; c[nt][2] = 0.f; c[nt][3] = 0.f; }
+#pragma unroll
+  for (int st = 0; st < 2; ++st) {
+    const int kb = 32 * warp + 16 * st;
+    uint32_t a[4];
+    load_a_frag(in_s, kb, g, tq, a);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const uint32_t* bp = reinterpret_cast<const uint32_t*>(W16 + (size_t)(nt * 8 + g) * kWLd + kb + 2 * tq);
+      mma_bf16_16816(c[nt], a[0], a[1], a[2], a[3], bp[0], bp[4]);
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt) {
+    const int col = nt * 8 + 2 * tq;
+    float* r0 = red + (size_t)(warp * kRows + g) * 17 + col;
+    float* r1 = red + (size_t)(warp * kRows + g + 8) * 17 + col;
+    r0[0] = c[nt][0]; r0[1] = c[nt][1]; r1[0] = c[nt][2]; r1[1] = c[nt][3];
+  }
+  __syncthreads();
+}
+
 // Broadcasts this CTA's block (value `v` of thread (row b, column j)) into rows [u0, u0 + 16) of every peer's [k][row] buffer:
 // staged through shared memory so that each remote store carries 4 rows (16 bytes) instead of 4 bytes.
-__device__ __forceinline__ void broadcast_block(cg::cluster_group& cl, CSmem& sm, float* buf_local, int u0, float v) {
+__device__ __forceinline__ void broadcast_block(cg::cluster_group& cl, CCommon& sm, float* buf_local, int u0, float v) {
   const int b = threadIdx.x >> 4, j = threadIdx.x & 15;
   sm.xch[j][b] = v;
   __syncthreads();
@@ -175,9 +264,11 @@ __device__ __forceinline__ void ln_silu_inplace(float* buf, const float* gamma, 
   __syncthreads();
 }
 
+template <bool kTc>
 __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observe_scan_cluster_kernel(ScanFwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  CSmem& sm = *reinterpret_cast<CSmem*>(smem_raw);
+  using SmemT = typename std::conditional<kTc, CSmemTc, CSmem>::type;
+  SmemT& sm = *reinterpret_cast<SmemT*>(smem_raw);
   cg::cluster_group cl = cg::this_cluster();
   const unsigned rank = cl.block_rank();
   const int B = p.B, T = p.T, G = kG, D = kG, Z = p.Z, Zc = p.Zc, Zk = p.Zk, E = p.E;
@@ -190,13 +281,27 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
   // ---- resident weights ----
   for (int e = tid; e < kG * 3 * kU; e += kThreads) {
     const int k = e / (3 * kU), j = e % (3 * kU), col = (j / kU) * G + u0 + (j % kU);
-    sm.wK[k][j] = p.gru_K[(size_t)k * 3 * G + col];
-    sm.wU[k][j] = p.gru_U[(size_t)k * 3 * G + col];
+    if constexpr (kTc) {
+      sm.wK[j][k] = __float2bfloat16_rn(p.gru_K[(size_t)k * 3 * G + col]);
+      sm.wU[j][k] = __float2bfloat16_rn(p.gru_U[(size_t)k * 3 * G + col]);
+    } else {
+      sm.wK[k][j] = p.gru_K[(size_t)k * 3 * G + col];
+      sm.wU[k][j] = p.gru_U[(size_t)k * 3 * G + col];
+    }
   }
-  for (int e = tid; e < kG * kZC; e += kThreads) { const int k = e / kZC, j = e % kZC; sm.wZ[k][j] = p.W_zq[(size_t)k * Z + z0c + j]; }
-  // W_post[E:][:, my 16 columns] in registers: thread (warp, lane) owns column lane % 16 and the k's of its gemv_acc<16> slice
-  float wP[16];
-  {
+  for (int e = tid; e < kG * kZC; e += kThreads) {
+    const int k = e / kZC, j = e % kZC;
+    if constexpr (kTc) sm.wZ[j][k] = __float2bfloat16_rn(p.W_zq[(size_t)k * Z + z0c + j]);
+    else sm.wZ[k][j] = p.W_zq[(size_t)k * Z + z0c + j];
+  }
+  // W_post[E:][:, my 16 columns]: fp32 variant in registers (thread (warp, lane) owns column lane % 16 and the k's of its slice),
+  // tensor-core variant in shared memory next to W_pre[:Z][:, my 16 columns]
+  float wP[kTc ? 1 : 16];
+  if constexpr (kTc) {
+    wP[0] = 0.f;
+    for (int e = tid; e < kG * kU; e += kThreads) { const int k = e / kU, j = e % kU; sm.wP[j][k] = __float2bfloat16_rn(W_post_h[(size_t)k * D + u0 + j]); }
+    for (int e = tid; e < Z * kU; e += kThreads) { const int k = e / kU, j = e % kU; sm.wX[k][j] = __float2bfloat16_rn(p.W_pre[(size_t)k * D + u0 + j]); }
+  } else {
     const int k0 = warp * (kG / kWarps) + lane / 16;
 #pragma unroll
     for (int i = 0; i < 16; ++i) wP[i] = W_post_h[(size_t)(k0 + 2 * i) * D + u0 + (lane & 15)];
@@ -211,7 +316,8 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
   // every row starts from the learned initial state: buf1 <- h0 for all rows, gh(0) = gh0 = h0 . U + b1
   for (int e = tid; e < kG * kRows; e += kThreads) sm.buf1[e / kRows][e % kRows] = p.h0[e / kRows];
   __syncthreads();
-  tile_pass<3>(&sm.buf1[0][0], &sm.wU[0][0], sm.red);
+  if constexpr (kTc) mma_pass<48>(&sm.buf1[0][0], &sm.wU[0][0], sm.red);
+  else tile_pass<3>(&sm.buf1[0][0], &sm.wU[0][0], sm.red);
   if (tid < 3 * kU) sm.gh0[tid] = red_sum<48>(sm.red, 0, tid) + p.gru_b[3 * G + (tid / kU) * G + u0 + (tid % kU)];
   __syncthreads();
   for (int e = tid; e < kRows * 3 * kU; e += kThreads) sm.gh[e / (3 * kU)][e % (3 * kU)] = sm.gh0[e % (3 * kU)];
@@ -255,11 +361,12 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
       float x = 0.f;
       if (row_ok) {
         x = actw;
-        float w32[32];   // all 32 row gathers in flight at once: one L2 round trip instead of four
+        float w32[32];   // all 32 row gathers in flight at once: one L2 round trip instead of four (tensor-core variant: on chip)
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const int cls = first ? sm.idx0[c] : sm.idx[b][c];
-          w32[c] = p.W_pre[(size_t)(c * Zk + cls) * D + u0 + j];
+          if constexpr (kTc) w32[c] = __bfloat162float(sm.wX[c * Zk + cls][j]);
+          else w32[c] = p.W_pre[(size_t)(c * Zk + cls) * D + u0 + j];
         }
 #pragma unroll
         for (int c = 0; c < 32; ++c) x += w32[c];
@@ -282,7 +389,8 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
 
     // ===== stage B: u = SiLU(LN(x_pre)); gx for my units; GRU cell =====
     ln_silu_inplace(&sm.buf0[0][0], sm.lnp[0], sm.lnp[1], B, rank, p.u_act + (size_t)t * D, p.x_mean + t, p.x_rstd + t, (size_t)T * D, (size_t)T);
-    tile_pass<3>(&sm.buf0[0][0], &sm.wK[0][0], sm.red);
+    if constexpr (kTc) mma_pass<48>(&sm.buf0[0][0], &sm.wK[0][0], sm.red);
+    else tile_pass<3>(&sm.buf0[0][0], &sm.wK[0][0], sm.red);
     {
       const int u = u0 + j;
       float hn = 0.f;
@@ -309,28 +417,32 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
 
     // ===== stage C: p_pre (my 16 columns, weights in registers); gh(t+1) for my units =====
     {
-      float acc[kRows];
+      if constexpr (kTc) {
+        mma_pass16(&sm.buf1[0][0], &sm.wP[0][0], sm.red);
+      } else {
+        float acc[kRows];
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
-      const float* in_s = &sm.buf1[0][0];
-      const int k0 = warp * (kG / kWarps) + lane / 16;
+        for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
+        const float* in_s = &sm.buf1[0][0];
+        const int k0 = warp * (kG / kWarps) + lane / 16;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float4* iv = reinterpret_cast<const float4*>(in_s + (size_t)(k0 + 2 * i) * kLd);
-        const float4 a0 = iv[0], a1 = iv[1], a2 = iv[2], a3 = iv[3];
-        const float w_ = wP[i];
-        acc[0] = fmaf(a0.x, w_, acc[0]); acc[1] = fmaf(a0.y, w_, acc[1]); acc[2] = fmaf(a0.z, w_, acc[2]); acc[3] = fmaf(a0.w, w_, acc[3]);
-        acc[4] = fmaf(a1.x, w_, acc[4]); acc[5] = fmaf(a1.y, w_, acc[5]); acc[6] = fmaf(a1.z, w_, acc[6]); acc[7] = fmaf(a1.w, w_, acc[7]);
-        acc[8] = fmaf(a2.x, w_, acc[8]); acc[9] = fmaf(a2.y, w_, acc[9]); acc[10] = fmaf(a2.z, w_, acc[10]); acc[11] = fmaf(a2.w, w_, acc[11]);
-        acc[12] = fmaf(a3.x, w_, acc[12]); acc[13] = fmaf(a3.y, w_, acc[13]); acc[14] = fmaf(a3.z, w_, acc[14]); acc[15] = fmaf(a3.w, w_, acc[15]);
+        for (int i = 0; i < 16; ++i) {
+          const float4* iv = reinterpret_cast<const float4*>(in_s + (size_t)(k0 + 2 * i) * kLd);
+          const float4 a0 = iv[0], a1 = iv[1], a2 = iv[2], a3 = iv[3];
+          const float w_ = wP[i];
+          acc[0] = fmaf(a0.x, w_, acc[0]); acc[1] = fmaf(a0.y, w_, acc[1]); acc[2] = fmaf(a0.z, w_, acc[2]); acc[3] = fmaf(a0.w, w_, acc[3]);
+          acc[4] = fmaf(a1.x, w_, acc[4]); acc[5] = fmaf(a1.y, w_, acc[5]); acc[6] = fmaf(a1.z, w_, acc[6]); acc[7] = fmaf(a1.w, w_, acc[7]);
+          acc[8] = fmaf(a2.x, w_, acc[8]); acc[9] = fmaf(a2.y, w_, acc[9]); acc[10] = fmaf(a2.z, w_, acc[10]); acc[11] = fmaf(a2.w, w_, acc[11]);
+          acc[12] = fmaf(a3.x, w_, acc[12]); acc[13] = fmaf(a3.y, w_, acc[13]); acc[14] = fmaf(a3.z, w_, acc[14]); acc[15] = fmaf(a3.w, w_, acc[15]);
+        }
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 16);
+        if (lane < 16) {
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) sm.red[(warp * kRows + r) * 17 + lane] = acc[r];
+        }
+        __syncthreads();
       }
-#pragma unroll
-      for (int r = 0; r < kRows; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 16);
-      if (lane < 16) {
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) sm.red[(warp * kRows + r) * 17 + lane] = acc[r];
-      }
-      __syncthreads();
       float s = 0.f;
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) s += sm.red[(w * kRows + b) * 17 + j];
@@ -342,8 +454,12 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
       broadcast_block(cl, sm, &sm.buf0[0][0], u0, pv);
       __syncthreads();
     }
+    // everything the peers wait for (my p_pre columns) is on its way: arrive now and compute gh(t+1), which only this CTA reads,
+    // while the barrier completes
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     if (t + 1 < T) {
-      tile_pass<3>(&sm.buf1[0][0], &sm.wU[0][0], sm.red);
+      if constexpr (kTc) mma_pass<48>(&sm.buf1[0][0], &sm.wU[0][0], sm.red);
+      else tile_pass<3>(&sm.buf1[0][0], &sm.wU[0][0], sm.red);
 #pragma unroll
       for (int gate = 0; gate < 3; ++gate) {
         const int q = gate * kU + j;
@@ -351,14 +467,15 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
       }
     }
     stamp(t * 8 + 5);
-    cl.sync();
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     stamp(t * 8 + 6);
 
     // ===== stage D: p_act = SiLU(LN(p_pre)); logits for my 64 columns; sample my 2 categoricals =====
     ln_silu_inplace(&sm.buf0[0][0], sm.lnp[2], sm.lnp[3], B, rank, p.p_act + (size_t)t * D, p.p_mean + t, p.p_rstd + t, (size_t)T * D, (size_t)T);
     {
       float* red64 = &sm.buf1[0][0];   // h is dead until stage B of the next step: [4][16][65] k-slice partial sums
-      tile_pass<4>(&sm.buf0[0][0], &sm.wZ[0][0], red64);
+      if constexpr (kTc) mma_pass<64>(&sm.buf0[0][0], &sm.wZ[0][0], red64);
+      else tile_pass<4>(&sm.buf0[0][0], &sm.wZ[0][0], red64);
       float lg[4];   // logits of this thread: rows (tid >> 5) + 8 i' ... laid out so that a warp owns one (row, categorical) pair
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
@@ -427,19 +544,28 @@ bool scan_cluster_supported(const ScanFwdParams& p) {
   return p.G == kG && p.D == kG && p.Z == kC * kZC && p.Zk == 32 && p.Zc == 32 && p.B <= kRows && std::getenv("DV3_NO_CLUSTER_SCAN") == nullptr;
 }
 
-cudaError_t launch_observe_scan_cluster(cudaStream_t s, const ScanFwdParams& p) {
+template <bool kTc>
+static cudaError_t launch_cluster_variant(cudaStream_t s, const ScanFwdParams& p) {
+  using SmemT = typename std::conditional<kTc, CSmemTc, CSmem>::type;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(observe_scan_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaError_t e = cudaFuncSetAttribute(observe_scan_cluster_kernel<kTc>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(observe_scan_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CSmem));
+    e = cudaFuncSetAttribute(observe_scan_cluster_kernel<kTc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT));
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  observe_scan_cluster_kernel<<<dim3(kC), dim3(kThreads), sizeof(CSmem), s>>>(p);
+  observe_scan_cluster_kernel<kTc><<<dim3(kC), dim3(kThreads), sizeof(SmemT), s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) count_launch();
   return e;
+}
+
+// bf16: the tensor-core variant (compute mode 1): bf16 weights resident on chip (the one-hot gather of W_pre included), mma.sync
+// contractions with fp32 accumulation; everything else (LayerNorm, gates, softmax, the fp64 inverse-CDF draw) as in the fp32 variant
+cudaError_t launch_observe_scan_cluster(cudaStream_t s, const ScanFwdParams& p, bool bf16) {
+  static const bool no_tc = std::getenv("DV3_NO_CLUSTER_TC") != nullptr;
+  return (bf16 && !no_tc) ? launch_cluster_variant<true>(s, p) : launch_cluster_variant<false>(s, p);
 }
 
 }  // namespace dv3

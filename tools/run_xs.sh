@@ -1,0 +1,5 @@
+# config parity tests + the engine tests, then the two XS bench lines (C1 CartPole, C2 Pendulum) with their phase breakdown
+timeout 1200 python -m pytest tests/test_gpu_configs.py tests/test_gpu_engine.py -q -m gpu --timeout 300 2>&1 | tail -25 > gpurun_out/r2_xs_tests.log; tail -4 gpurun_out/r2_xs_tests.log
+for w in c1 c2; do timeout 300 python bench.py --workload $w --no-per-config --no-cpu --no-fp32-line --steps 20 2>gpurun_out/r2_xs_$w.err > gpurun_out/r2_xs_$w.json; python -c "
+import json,sys
+d=json.loads(open('gpurun_out/r2_xs_$w.json').read().strip().splitlines()[-1]); print(d['config']['id'], round(d['value'],2), round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value'],1), 'scan fwd/bwd us', round(d['scan_step_latency_us'],1), round(d['scan_bwd_step_latency_us'],1), {k: v for k, v in d['phases_ms'].items() if v > 0.1})"; tail -2 gpurun_out/r2_xs_$w.err; done

@@ -13,6 +13,8 @@ from dreamer_v3_b200.spec import init_params  # noqa: E402
 
 wid = sys.argv[1] if len(sys.argv) > 1 else "c2"
 cfg = make_cfg(wid)
+if len(sys.argv) > 2:
+    cfg.compute_mode = int(sys.argv[2])   # 0 fp32, 1 bf16 tensor-core mode
 e = Engine(cfg)
 e.load_params(init_params(cfg, seed=0))
 e.set_sample(synthetic_sample(cfg, 0))
