@@ -46,11 +46,12 @@ bool Engine::actor_step_applicable(int i) const {
 void Engine::actor_step_mlps(long long row_off) {
   const float* x = dr_hz + (size_t)row_off * (G + Z);
   const void* x16 = dr_hz16 ? (const void*)((const unsigned short*)dr_hz16 + (size_t)row_off * (G + Z)) : nullptr;
+  // (the first layer's pre-activations were zeroed for all dream rows at the start of the rollout: see dream_forward)
   if (discrete) {
-    mlp_fwd(actor_mlp, actor_act, x, G + Z, N, row_off, x16, true);
+    mlp_fwd(actor_mlp, actor_act, x, G + Z, N, row_off, x16, true, true);
   } else {
-    run_branches({[&] { mlp_fwd(actor_mlp, actor_act, x, G + Z, N, row_off, x16, true); },
-                  [&] { mlp_fwd(actor_std_mlp, actor_std_act, x, G + Z, N, row_off, x16, true); }});
+    run_branches({[&] { mlp_fwd(actor_mlp, actor_act, x, G + Z, N, row_off, x16, true, true); },
+                  [&] { mlp_fwd(actor_std_mlp, actor_std_act, x, G + Z, N, row_off, x16, true, true); }});
   }
 }
 // ... and its tail: LN+SiLU of that layer, the output layer, the sample and (with_pre) the pre-GRU layer of step i + 1
@@ -155,6 +156,14 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
   auto h16 = [&](size_t row, int col) -> void* { return hz16p ? (void*)(hz16p + row * W + col) : nullptr; };
   auto t16 = [&](void* base, size_t off) -> void* { return base ? (void*)((unsigned short*)base + off) : nullptr; };
   if (hz16p) to_bf16(s, dr_hz, W, hz16p, W, N, W);
+  // Accumulating contractions of the rollout add into rows zeroed here, once for all steps: at the XS sizes the K = Z and
+  // K = G + Z contractions are split-K, and a zero-fill node in front of each would sit on the step's dependency chain
+  const bool fused_any = actor_step_applicable(1);
+  cudaMemsetAsync(dr_x_pre, 0, (size_t)H * N * D * 4, s);
+  if (fused_any) {
+    cudaMemsetAsync(actor_act.pre[0], 0, (size_t)R * actor_mlp.layers[0].out * 4, s);
+    if (!discrete) cudaMemsetAsync(actor_std_act.pre[0], 0, (size_t)R * actor_std_mlp.layers[0].out * 4, s);
+  }
   phase_mark("dream.begin");
   if (dream_rollout_tc(s)) {
     phase_mark("dream.rollout_tc");
@@ -167,7 +176,7 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
     // through the small a-part of the pre-GRU layer only), the z-part of that layer, and h_{i-1} . U.
     const bool fused = actor_step_applicable(i - 1);
     run_branches({[&] { if (fused) actor_step_mlps((long long)prev); else dream_action(i - 1); },
-                  [&] { mm(hz_p + G, W, false, Wx.w, D, false, dr_x_pre + st * D, D, N, D, Z, nullptr, 0.f, h16(prev, G)); },
+                  [&] { mm(hz_p + G, W, false, Wx.w, D, false, dr_x_pre + st * D, D, N, D, Z, nullptr, 1.f, h16(prev, G)); },
                   [&] { mm(hz_p, W, false, gru_U, 3 * G, false, dr_gh + st * 3 * G, 3 * G, N, 3 * G, G, gru_b + 3 * G, 0.f, h16(prev, 0)); }});
     phase_mark("dream.actor|z|gh");
     if (fused) {
@@ -297,15 +306,19 @@ void Engine::actor_backward(const dv3_hparams* hp, const AcArgs& a) {
     dense_bwd(critic_head, nullptr, 0, dr_dlogits255, DV3_NB, sN_D0, D, 0.f, false, R);
     mlp_bwd(critic_mlp, critic_act, dr_hz, W, sN_D0, sN_D1, d_dr_hz, W, false, R);
     phase_mark("ac.heads_dx");
+    // per-step slices (rows N .. of the (H+1) N-row scratch; rows 0 .. N stay the per-step du scratch below), zeroed once: the
+    // split-K contraction of each step accumulates into its slice instead of waiting for a zero-fill node of its own
+    cudaMemsetAsync(sN_D0 + (size_t)N * D, 0, (size_t)H * N * D * 4, s);
     for (int i = H; i >= 1; --i) {
       const size_t prev = (size_t)(i - 1) * N, curr = (size_t)i * N, st = (size_t)(i - 1) * N;
+      float* dq = sN_D0 + (st + N) * D;   // d q_act of this step
       float* d_c = d_dr_hz + curr * W;
       float* d_p = d_dr_hz + prev * W;
       const float* hz_p = dr_hz + prev * W;
       // z_i = straight-through sample of prior(h_i)
       repr_bwd(s, dr_prior_logits + st * Z, Z, d_c + G, W, nullptr, 0, sN_Z, Z, N, Zc, Zk, twin_of(sN_Z));
-      mm(sN_Z, Z, false, dyn_repr.w, Z, true, sN_D0, D, N, D, Z, nullptr, 0.f, twin_of(sN_Z));
-      ln_silu_bwd(s, sN_D0, D, dr_q_pre + st * D, D, dr_q_mean + st, dr_q_rstd + st, Wd.g, Wd.b, sN_D1, D, nullptr, nullptr, 1, N, D, twin_of(sN_D1));
+      mm(sN_Z, Z, false, dyn_repr.w, Z, true, dq, D, N, D, Z, nullptr, 1.f, twin_of(sN_Z));
+      ln_silu_bwd(s, dq, D, dr_q_pre + st * D, D, dr_q_mean + st, dr_q_rstd + st, Wd.g, Wd.b, sN_D1, D, nullptr, nullptr, 1, N, D, twin_of(sN_D1));
       mm(sN_D1, D, false, Wd.w, D, true, d_c, W, N, G, D, nullptr, 1.f, twin_of(sN_D1));
       // h_i = GRU(pre([z_{i-1}, a_{i-1}]), h_{i-1})
       gru_bwd(s, d_c, W, dr_gx + st * 3 * G, 3 * G, dr_gh + st * 3 * G, 3 * G, hz_p, W, sN_3G0, 3 * G, sN_3G1, 3 * G, d_p, W, 1, N, G,

@@ -491,6 +491,84 @@ __global__ void repr_fwd_kernel(const float* __restrict__ logits, int ldl, float
   }
 }
 
+// Same, 32-class categoricals, four per warp at a time: their loads are issued together and their shuffle chains (max, sum,
+// fp64 scan) interleave instead of running back to back - the kernel is a latency chain per warp, not a bandwidth problem
+__global__ void __launch_bounds__(256) repr_fwd4_kernel(const float* __restrict__ logits, int ldl, float* __restrict__ probs, int ldp,
+                                                        const float* __restrict__ u, int ldu, int32_t* __restrict__ idx, int ldi,
+                                                        float* __restrict__ z, int ldz, int M, int Zc, int mode,
+                                                        __nv_bfloat16* __restrict__ z16) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int groups = Zc / 4;
+  const long long total = (long long)M * groups;
+  for (long long w = warp0; w < total; w += nwarps) {
+    const int r = (int)(w / groups), c0 = (int)(w % groups) * 4;
+    float l[4], uu[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      l[q] = logits[(size_t)r * ldl + (c0 + q) * 32 + lane];
+      uu[q] = mode == 1 ? u[(size_t)r * ldu + c0 + q] : 0.f;
+    }
+    float mx[4], e[4], sden[4], p[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) mx[q] = l[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], o));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { e[q] = expf(l[q] - mx[q]); sden[q] = e[q]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sden[q] += __shfl_xor_sync(0xffffffffu, sden[q], o);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      p[q] = 0.99f * (e[q] / sden[q]) + 0.01f * (1.0f / 32.0f);
+      if (probs != nullptr) probs[(size_t)r * ldp + (c0 + q) * 32 + lane] = p[q];
+    }
+    if (mode == 0) continue;
+    int pick[4];
+    if (mode == 1) {
+      double cdf[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cdf[q] = (double)p[q];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double t = __shfl_up_sync(0xffffffffu, cdf[q], o);
+          if (lane >= o) cdf[q] += t;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {   // as categorical_pick (dv3_device.cuh): index = #(cdf <= u * total), clamped
+        const double tot = __shfl_sync(0xffffffffu, cdf[q], 31);
+        const unsigned below = __ballot_sync(0xffffffffu, cdf[q] <= (double)uu[q] * tot);
+        pick[q] = min(__popc(below), 31);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {   // argmax, first index on ties
+        const float pm = warp_max(p[q]);
+        pick[q] = __ffs(__ballot_sync(0xffffffffu, p[q] == pm)) - 1;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (idx != nullptr && lane == 0) idx[(size_t)r * ldi + c0 + q] = pick[q];
+      const float hot = (lane == pick[q]) ? 1.f : 0.f;
+      if (z != nullptr) z[(size_t)r * ldz + (c0 + q) * 32 + lane] = hot;
+      if (z16 != nullptr) z16[(size_t)r * ldz + (c0 + q) * 32 + lane] = __float2bfloat16_rn(hot);
+    }
+  }
+}
+
 __global__ void repr_bwd_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ dz, int lddz,
                                 const float* __restrict__ dprobs, int lddp, float* __restrict__ dlogits, int lddl,
                                 int M, int Zc, int Zk, __nv_bfloat16* __restrict__ dl16) {
@@ -729,6 +807,12 @@ void gru_bwd(cudaStream_t s, const float* dh, int lddh, const float* gates, int 
 void repr_fwd(cudaStream_t s, const float* logits, int ldl, float* probs, int ldp, const float* u, int ldu,
               int32_t* idx, int ldi, float* z, int ldz, int M, int Zc, int Zk, int mode, void* z16) {
   if (M <= 0) return;
+  if (Zk == 32 && Zc % 4 == 0) {
+    launch_pdl(repr_fwd4_kernel, dim3(grid_for((long long)M * (Zc / 4), kThreads / 32)), dim3(kThreads), 0, s, logits, ldl, probs, ldp, u, ldu, idx, ldi, z, ldz, M, Zc,
+               mode, reinterpret_cast<__nv_bfloat16*>(z16));
+    count_launch();
+    return;
+  }
   launch_pdl(repr_fwd_kernel, dim3(grid_for((long long)M * Zc, kThreads / 32)), dim3(kThreads), 0, s, logits, ldl, probs, ldp, u, ldu, idx, ldi, z, ldz, M, Zc, Zk, mode,
                                                                                   reinterpret_cast<__nv_bfloat16*>(z16));
   count_launch();

@@ -769,7 +769,7 @@ GemmArgs Engine::mm_args(const float* A_, int lda, bool ta, const float* B_, int
 }
 
 void Engine::mlp_fwd(const Mlp& mdl, MlpAct& a, const float* x, int ldx, long long rows, long long row_off,
-                     const void* x16, bool skip_last_ln) {
+                     const void* x16, bool skip_last_ln, bool acc_first) {
   const float* in = x;
   const void* in16 = x16;
   int ldin = ldx;
@@ -778,7 +778,7 @@ void Engine::mlp_fwd(const Mlp& mdl, MlpAct& a, const float* x, int ldx, long lo
     float* pre = a.pre[l] + row_off * ly.out;
     float* act = a.act[l] + row_off * ly.out;
     void* act16 = rows >= 128 ? bf16_off(a.act16[l], (size_t)row_off * ly.out) : nullptr;
-    mm(in, ldin, false, ly.w, ly.out, false, pre, ly.out, (int)rows, ly.out, ly.in, nullptr, 0.f, in16);
+    mm(in, ldin, false, ly.w, ly.out, false, pre, ly.out, (int)rows, ly.out, ly.in, nullptr, (acc_first && l == 0) ? 1.f : 0.f, in16);
     if (skip_last_ln && l + 1 == mdl.layers.size()) break;
     ln_silu_fwd(cur, pre, ly.out, ly.g, ly.b, act, ly.out, a.mean[l] + row_off, a.rstd[l] + row_off, 1, rows, ly.out, act16);
     in = act; in16 = act16; ldin = ly.out;

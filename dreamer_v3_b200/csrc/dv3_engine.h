@@ -210,8 +210,10 @@ struct Engine {
   bool mm_tma(const float* A_, int lda, bool ta, const float* B_, int ldb, bool tb, float* C, int ldc, int M, int N_, int K,
               const void* A16, const void* B16) const;
   // skip_last_ln: leave the last layer at its pre-activation (the caller's fused kernel applies LN+SiLU)
+  // acc_first: the first layer's pre-activation rows are known to be zero and its contraction adds to them (a split-K
+  // contraction then needs no zero-fill node in front of it)
   void mlp_fwd(const Mlp& m, MlpAct& a, const float* x, int ldx, long long rows, long long row_off = 0,
-               const void* x16 = nullptr, bool skip_last_ln = false);
+               const void* x16 = nullptr, bool skip_last_ln = false, bool acc_first = false);
   // ---- bf16 twins of activation buffers that feed large contractions (tensor-core mode only) ----
   std::unordered_map<const float*, void*> twins;
   void* twin_alloc(const float* base, size_t elems);

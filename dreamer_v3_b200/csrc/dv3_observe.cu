@@ -193,6 +193,24 @@ int Engine::wm_loss_backward(cudaStream_t s) {
     if (ce != cudaSuccess) return fail(std::string("observe scan bwd (tensor-core) launch: ") + cudaGetErrorString(ce));
     ln_silu_bwd(s, dp_act_all, D, p_pre, D, p_mean, p_rstd, Wp.g, Wp.b, nullptr, 0, Wp.dg, Wp.db, 1, N, D);
     ln_silu_bwd(s, du_all, D, x_pre, D, x_mean, x_rstd, Wx.g, Wx.b, nullptr, 0, Wx.dg, Wx.db, 1, N, D);
+  } else if (use_persistent && cfg.compute_mode == 1 && [&] {
+               // tensor-core mode, XS: the 16-CTA cluster kernel (dv3_scan_cluster.cu) with bf16 weight rows resident on chip
+               ScanBwdParams bp{};
+               bp.B = B; bp.T = T; bp.G = G; bp.D = D; bp.Z = Z; bp.Zc = Zc; bp.Zk = Zk;
+               bp.W_zq = post_repr.w; bp.W_post_h = Wp.w + (size_t)E * D; bp.gru_U = gru_U; bp.gru_K = gru_K; bp.W_pre = Wx.w;
+               if (!scan_bwd_cluster_supported(bp)) return false;
+               bp.post_g = Wp.g; bp.post_b = Wp.b; bp.pre_g = Wx.g; bp.pre_b = Wx.b;
+               bp.is_first = in_is_first; bp.post_logits = post_logits; bp.dpost = dpost; bp.p_pre = p_pre; bp.p_mean = p_mean;
+               bp.p_rstd = p_rstd; bp.gates = gx; bp.gh = gh; bp.h_in = h_in; bp.x_pre = x_pre; bp.x_mean = x_mean; bp.x_rstd = x_rstd;
+               bp.d_hz = d_hz; bp.dlogits = dpost_logits; bp.dp_act = dp_act_all; bp.dp_pre = dp_pre; bp.dh_tot = dh_tot;
+               bp.dgx = dgx; bp.dgh = dgh; bp.dh_in = dh_in; bp.du = du_all; bp.dx_pre = dx_pre;
+               bp.stamps = std::getenv("DV3_SCAN_STAMPS") ? scan_stamps : nullptr;
+               const cudaError_t ce = launch_observe_scan_bwd_cluster(s, bp);
+               if (ce != cudaSuccess) { fail(std::string("observe scan bwd (cluster) launch: ") + cudaGetErrorString(ce)); return false; }
+               return true;
+             }()) {
+    ln_silu_bwd(s, dp_act_all, D, p_pre, D, p_mean, p_rstd, Wp.g, Wp.b, nullptr, 0, Wp.dg, Wp.db, 1, N, D);
+    ln_silu_bwd(s, du_all, D, x_pre, D, x_mean, x_rstd, Wx.g, Wx.b, nullptr, 0, Wx.dg, Wx.db, 1, N, D);
   } else if (use_persistent && scan_bwd_ctas > 0 && G <= 2048) {
     transpose_f32(s, post_repr.w, Wt_zq, D, Z);
     transpose_f32(s, Wp.w + (size_t)E * D, Wt_post_h, G, D);

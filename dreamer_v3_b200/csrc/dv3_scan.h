@@ -43,6 +43,12 @@ struct ScanBwdParams {
   const float* Ut;         // [3G, G]
   const float* Kt;         // [3G, D]
   const float* Wt_pre_z;   // [D, Z]
+  // untransposed fp32 weights (cluster kernel: converts the rows it owns to bf16 itself)
+  const float* W_zq;       // [D, Z]
+  const float* W_post_h;   // rows E.. of W_post: [G, D]
+  const float* gru_U;      // [G, 3G]
+  const float* gru_K;      // [D, 3G]
+  const float* W_pre;      // [Z + A, D]
   const float* post_g; const float* post_b; const float* pre_g; const float* pre_b;
   // saved by the forward pass (B-major [B, T, ...])
   const float* is_first; const float* post_logits; const float* dpost;
@@ -73,6 +79,9 @@ int scan_fwd_max_ctas(int device);  // 0 when the kernel cannot be made co-resid
 cudaError_t launch_observe_scan_fwd(cudaStream_t s, const ScanFwdParams& p, int ctas);
 // single 16-CTA cluster version (dv3_scan_cluster.cu): weights resident in the cluster's shared memory, DSMEM exchange
 bool scan_cluster_supported(const ScanFwdParams& p);
+// reverse-time BPTT on the same cluster (tensor-core mode only): bf16 weight rows resident, operands exchanged through DSMEM
+bool scan_bwd_cluster_supported(const ScanBwdParams& p);
+cudaError_t launch_observe_scan_bwd_cluster(cudaStream_t s, const ScanBwdParams& p);
 // bf16: tensor-core variant (bf16 weights resident on chip incl. the gathered W_pre rows, mma.sync contractions)
 cudaError_t launch_observe_scan_cluster(cudaStream_t s, const ScanFwdParams& p, bool bf16);
 

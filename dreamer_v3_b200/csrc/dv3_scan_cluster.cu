@@ -537,6 +537,368 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Reverse-time BPTT through the scan on the same 16-CTA cluster (tensor-core mode; replaces tape.gradient over
+// world_model.py:244-273, train_one_step.py:80). CTA r owns dense columns / GRU units [16 r, 16 r + 16) and posterior logit
+// columns [64 r, 64 r + 64). Every contraction keeps its WEIGHTS stationary: the rows of the (untransposed) fp32 weight
+// matrices that produce this CTA's output columns are converted to bf16 once and stay in shared memory for all T steps
+// (125 KB per CTA), the 16-row operands travel between the CTAs through distributed shared memory in bf16 ([row][k], the A
+// fragment layout of mma.m16n8k16) or fp32 ([k][row], where a LayerNorm backward over whole rows follows). Per step t
+// (T-1 .. 0), 5 stages and 4 cluster barriers:
+//   S1  dlogits[t] (my 2 categoricals) = softmax-Jacobian^T 0.99 (d_hz[t].z + carried dz_in + dKL/dprobs)   -> all peers (bf16)
+//   S2  dp_act[:, my cols] = dlogits . W_zq^T                                                                 -> all peers (fp32)
+//   S3  dp_pre = LN'SiLU'(dp_act) (every CTA, whole rows); dh = d_hz[t].h + carried dh_in + dp_pre . W_post[E:]^T for my units;
+//       GRU gate gradients dz, dr, dc, dc r of my units                                                       -> all peers (bf16)
+//   S4  dh_in[:, my units] = dh z + [dz dr dc r] . U^T;  du[:, my cols] = [dz dr dc] . K^T                    -> du to all peers (fp32)
+//   S5  dx_pre = LN'SiLU'(du); dz_in[:, my 64 cols] = dx_pre . W_pre[:Z]^T: stays in this CTA (it is the z-gradient of the
+//       categoricals S1 of step t-1 handles here); nothing of the recurrence goes through global memory.
+// Everything a stage reads from the forward pass is loaded at the top of the step, before S1 (no dependent L2 round trip inside).
+constexpr int kLdL = kC * kZC + 8;   // bf16 row stride of the staged dlogits   [row][1024 + 8]
+constexpr int kLdG = 3 * kG + 8;     // bf16 k stride of the resident U / K rows [unit][768 + 8]
+
+struct BSmem {
+  __nv_bfloat16 wA[kU][kLdL];      // W_zq[my 16 rows][Z]             33 KB
+  __nv_bfloat16 wB[kU][kWLd];      // W_post[E + my 16 units][D]       8 KB
+  __nv_bfloat16 wC[kU][kLdG];      // U[my 16 units][3G]              24 KB
+  __nv_bfloat16 wD[kU][kLdG];      // K[my 16 columns][3G]            24 KB
+  __nv_bfloat16 wE[kZC][kWLd];     // W_pre[my 64 rows][D]            33 KB
+  union {                          // operands every peer writes into (never live at the same time, see the barriers)
+    __nv_bfloat16 dl[kRows][kLdL];       // dlogits[t], all 1024 columns
+    __nv_bfloat16 dg[4][kRows][kWLd];    // dz, dr, dc, dc r of all 256 units
+  } x;
+  float buf[kG][kLd];              // dp_act -> dp_pre, then du -> dx_pre: fp32 [k][row]   20 KB
+  float red[2 * kWarps * kRows * 17];   // per-warp partial sums (two products in S4); [4][16][65] in S5
+  float dzc[kRows][kZC + 1];       // carried z-gradient of my 64 columns: (1 - is_first[t+1]) dz_in[t+1]
+  float xch[kU][kRows];            // my [16 columns][16 rows] fp32 block, staged for the broadcast
+  __nv_bfloat16 xl[kRows][kZC];    // my dlogits block, staged for the broadcast
+  __nv_bfloat16 xg[4][kRows][kU];  // my gate-gradient blocks, staged for the broadcast
+  float lnp[4][kG];                // post_g, post_b, pre_g, pre_b
+};
+static_assert(sizeof(BSmem) <= 227 * 1024, "cluster scan backward shared memory");
+static_assert(2 * kWarps * kRows * 17 >= 4 * kRows * (kZC + 1), "red holds the S5 partial sums");
+
+__device__ __forceinline__ float silu_grad_fast(float n) {
+  const float sg = sigmoid_fast(n);
+  return sg * (1.f + n * (1.f - sg));
+}
+// A fragment (rows g, g + 8; k pairs 2 tq, 2 tq + 8 of [kb, kb + 16)) from a bf16 [row][k] operand with row stride ld
+__device__ __forceinline__ void load_a_frag16(const __nv_bfloat16* a16, int ld, int kb, int g, int tq, uint32_t (&a)[4]) {
+  const uint32_t* r0 = reinterpret_cast<const uint32_t*>(a16 + (size_t)g * ld + kb + 2 * tq);
+  const uint32_t* r1 = reinterpret_cast<const uint32_t*>(a16 + (size_t)(g + 8) * ld + kb + 2 * tq);
+  a[0] = r0[0]; a[1] = r1[0]; a[2] = r0[4]; a[3] = r1[4];
+}
+__device__ __forceinline__ void store_c_frag17(float* red, int slot, int nt, int g, int tq, const float (&c)[4]) {
+  const int col = nt * 8 + 2 * tq;
+  float* r0 = red + (size_t)(slot * kRows + g) * 17 + col;
+  float* r1 = red + (size_t)(slot * kRows + g + 8) * 17 + col;
+  r0[0] = c[0]; r0[1] = c[1]; r1[0] = c[2]; r1[1] = c[3];
+}
+// In-place LayerNorm+SiLU backward of the 16 rows staged as buf[k][row]: warp w handles rows w and w + 8, lane the columns
+// lane + 32 i. xr / mu / rs: the forward pre-activations and statistics of those two rows (loaded by the caller at the top
+// of the step). Row b of the result also goes to out (global, [B, T, D] at step t) from CTA `rank == b`.
+__device__ __forceinline__ void ln_bwd_inplace(float* buf, const float (&xr)[2][kG / 32], const float (&mu)[2], const float (&rs)[2],
+                                               const float* gamma, const float* beta, int B, unsigned rank, float* out, size_t row_stride) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int EPL = kG / 32;
+  float xh[2][EPL], d[2][EPL], s1[2], s2[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int b = warp + r * kWarps;
+    float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int c = lane + 32 * i;
+      const float gm = gamma[c];
+      const float xhat = (xr[r][i] - mu[r]) * rs[r];
+      const float dv = buf[c * kLd + b] * silu_grad_fast(xhat * gm + beta[c]) * gm;
+      xh[r][i] = xhat; d[r][i] = dv;
+      a1 += dv; a2 += dv * xhat;
+    }
+    s1[r] = a1; s2[r] = a2;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      s1[r] += __shfl_xor_sync(0xffffffffu, s1[r], o);
+      s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int b = warp + r * kWarps;
+    const float m1 = s1[r] / (float)kG, m2 = s2[r] / (float)kG;
+    const bool row_ok = b < B, wr = row_ok && (unsigned)b == rank;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int c = lane + 32 * i;
+      const float o = row_ok ? rs[r] * (d[r][i] - m1 - xh[r][i] * m2) : 0.f;
+      buf[c * kLd + b] = o;
+      if (wr) out[(size_t)b * row_stride + c] = o;
+    }
+  }
+  __syncthreads();
+}
+// my [16 columns][16 rows] fp32 block (value v of thread (row b, column j)) into rows [u0, u0 + 16) of every peer's buf[k][row]
+__device__ __forceinline__ void broadcast_block_b(cg::cluster_group& cl, BSmem& sm, int u0, float v) {
+  const int b = threadIdx.x >> 4, j = threadIdx.x & 15;
+  sm.xch[j][b] = v;
+  __syncthreads();
+  float* dst = cl.map_shared_rank(&sm.buf[0][0], threadIdx.x >> 4);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int chunk = (threadIdx.x & 15) + 16 * i, col = chunk >> 2, rg = chunk & 3;
+    const float4 q = *reinterpret_cast<const float4*>(&sm.xch[col][4 * rg]);
+    *reinterpret_cast<float4*>(dst + (size_t)(u0 + col) * kLd + 4 * rg) = q;
+  }
+}
+
+__global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observe_scan_bwd_cluster_kernel(ScanBwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BSmem& sm = *reinterpret_cast<BSmem*>(smem_raw);
+  cg::cluster_group cl = cg::this_cluster();
+  const unsigned rank = cl.block_rank();
+  const int B = p.B, T = p.T, G = kG, D = kG, Z = p.Z, W = kG + p.Z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g8 = lane >> 2, tq = lane & 3;
+  const int u0 = rank * kU, z0c = rank * kZC;
+  constexpr int EPL = kG / 32;
+
+  // ---- resident weights: rows of the untransposed matrices, fp32 -> bf16 ----
+  for (int e = tid; e < kU * Z; e += kThreads) { const int n = e / Z, k = e - n * Z; sm.wA[n][k] = __float2bfloat16_rn(p.W_zq[(size_t)(u0 + n) * Z + k]); }
+  for (int e = tid; e < kU * D; e += kThreads) { const int n = e / D, k = e - n * D; sm.wB[n][k] = __float2bfloat16_rn(p.W_post_h[(size_t)(u0 + n) * D + k]); }
+  for (int e = tid; e < kU * 3 * G; e += kThreads) {
+    const int n = e / (3 * G), k = e - n * 3 * G;
+    sm.wC[n][k] = __float2bfloat16_rn(p.gru_U[(size_t)(u0 + n) * 3 * G + k]);
+    sm.wD[n][k] = __float2bfloat16_rn(p.gru_K[(size_t)(u0 + n) * 3 * G + k]);
+  }
+  for (int e = tid; e < kZC * D; e += kThreads) { const int n = e / D, k = e - n * D; sm.wE[n][k] = __float2bfloat16_rn(p.W_pre[(size_t)(z0c + n) * D + k]); }
+  for (int e = tid; e < kG; e += kThreads) { sm.lnp[0][e] = p.post_g[e]; sm.lnp[1][e] = p.post_b[e]; sm.lnp[2][e] = p.pre_g[e]; sm.lnp[3][e] = p.pre_b[e]; }
+  for (int e = tid; e < kRows * (kZC + 1); e += kThreads) (&sm.dzc[0][0])[e] = 0.f;
+  __syncthreads();
+  cl.sync();
+
+  const int b = tid >> 4, j = tid & 15;   // (row, owned column / unit) of this thread in the 16 x 16 epilogues
+  const bool row_ok = b < B;
+  float dh_carry = 0.f;                    // (1 - is_first[t+1]) dh_in[t+1] of (row b, unit u0 + j)
+  auto stamp = [&](int i) {
+    if (p.stamps != nullptr && rank == 0 && tid == 0) {
+      unsigned long long v;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
+      p.stamps[i] = v;
+    }
+  };
+  stamp(0);
+
+  for (int t = T - 1; t >= 0; --t) {
+    const int si = (T - 1 - t) * 8;
+    const size_t bt = (size_t)(row_ok ? b : 0) * T + t;
+    // ---- everything this step reads from the forward pass / the head gradients, issued before the first stage ----
+    float q_l[4], q_dp[4], q_dz[4];          // S1: logits, dKL/dprobs, d_hz.z of my (row, categorical) pairs
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const int pr = warp + q4 * kWarps, r = pr >> 1, cl_ = pr & 1;
+      const bool ok = r < B;
+      const size_t rt = (size_t)(ok ? r : 0) * T + t;
+      const int col = z0c + cl_ * 32 + lane;
+      q_l[q4] = ok ? p.post_logits[rt * Z + col] : 0.f;
+      q_dp[q4] = ok ? p.dpost[rt * Z + col] : 0.f;
+      q_dz[q4] = ok ? p.d_hz[rt * W + G + col] : 0.f;
+    }
+    float xp[2][EPL], xx[2][EPL], mp[2], rp[2], mx_[2], rx[2];   // S3 / S5: LayerNorm inputs of rows warp, warp + 8
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int rb = warp + r * kWarps;
+      const bool ok = rb < B;
+      const size_t rt = (size_t)(ok ? rb : 0) * T + t;
+      mp[r] = ok ? p.p_mean[rt] : 0.f; rp[r] = ok ? p.p_rstd[rt] : 0.f;
+      mx_[r] = ok ? p.x_mean[rt] : 0.f; rx[r] = ok ? p.x_rstd[rt] : 0.f;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        xp[r][i] = ok ? p.p_pre[rt * D + lane + 32 * i] : 0.f;
+        xx[r][i] = ok ? p.x_pre[rt * D + lane + 32 * i] : 0.f;
+      }
+    }
+    const int u = u0 + j;                      // S3 / S4: GRU operands of (row b, unit u)
+    const float e_d = row_ok ? p.d_hz[bt * W + u] : 0.f;
+    const float e_z = row_ok ? p.gates[bt * 3 * G + u] : 0.f;
+    const float e_r = row_ok ? p.gates[bt * 3 * G + G + u] : 0.f;
+    const float e_c = row_ok ? p.gates[bt * 3 * G + 2 * G + u] : 0.f;
+    const float e_h = row_ok ? p.h_in[bt * G + u] : 0.f;
+    const float e_g = row_ok ? p.gh[bt * 3 * G + 2 * G + u] : 0.f;
+    const float keep = row_ok ? 1.f - p.is_first[bt] : 0.f;
+    float keep4[4];                            // S5: rows of the 4 dz_in columns this thread finishes (same row b)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) keep4[m] = keep;
+
+    // ===== S1: categorical backward (representation_layer.py:73-113) of my 2 categoricals x 16 rows, one warp per pair =====
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const int pr = warp + q4 * kWarps, r = pr >> 1, cl_ = pr & 1;
+      const bool ok = r < B;
+      const float l = q_l[q4];
+      float mx = l;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float ex = expf(l - mx);
+      const float sden = warp_sum(ex);
+      const float prb = ex / sden;
+      const float gz = 0.99f * (q_dz[q4] + sm.dzc[r][cl_ * 32 + lane] + q_dp[q4]);
+      const float dot = warp_sum(gz * prb);
+      const float dl = ok ? prb * (gz - dot) : 0.f;
+      if (ok) p.dlogits[((size_t)r * T + t) * Z + z0c + cl_ * 32 + lane] = dl;
+      sm.xl[r][cl_ * 32 + lane] = __float2bfloat16_rn(dl);
+    }
+    __syncthreads();
+    {   // my [16 rows][64 columns] bf16 block -> columns [64 rank, +64) of every peer's dl: thread -> (peer, row), 8 x 16 bytes
+      const unsigned peer = tid >> 4;
+      const int row = tid & 15;
+      __nv_bfloat16* dst = cl.map_shared_rank(&sm.x.dl[0][0], peer) + (size_t)row * kLdL + z0c;
+      const uint4* src = reinterpret_cast<const uint4*>(&sm.xl[row][0]);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) reinterpret_cast<uint4*>(dst)[c] = src[c];
+    }
+    stamp(si + 1);
+    cl.sync();
+    stamp(si + 2);
+
+    // ===== S2: dp_act[:, my 16 columns] = dlogits . W_zq^T (K = 1024: 8 k-steps per warp) =====
+    {
+      float c[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) { c[nt][0] = 0.f; c[nt][1] = 0.f; c[nt][2] = 0.f; c[nt][3] = 0.f; }
+#pragma unroll
+      for (int st = 0; st < 8; ++st) {
+        const int kb = 128 * warp + 16 * st;
+        uint32_t a[4];
+        load_a_frag16(&sm.x.dl[0][0], kLdL, kb, g8, tq, a);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const uint32_t* bp = reinterpret_cast<const uint32_t*>(&sm.wA[nt * 8 + g8][kb + 2 * tq]);
+          mma_bf16_16816(c[nt], a[0], a[1], a[2], a[3], bp[0], bp[4]);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) store_c_frag17(sm.red, warp, nt, g8, tq, c[nt]);
+      __syncthreads();
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s += sm.red[(w * kRows + b) * 17 + j];
+      if (row_ok) p.dp_act[bt * D + u0 + j] = s; else s = 0.f;
+      broadcast_block_b(cl, sm, u0, s);
+    }
+    stamp(si + 3);
+    cl.sync();
+    stamp(si + 4);
+
+    // ===== S3: dp_pre (whole rows, every CTA); dh of my units; GRU gate gradients =====
+    ln_bwd_inplace(&sm.buf[0][0], xp, mp, rp, sm.lnp[0], sm.lnp[1], B, rank, p.dp_pre + (size_t)t * D, (size_t)T * D);
+    float dhz = 0.f;   // dh z of (row b, unit u): the direct path into dh_in
+    {
+      float c[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) { c[nt][0] = 0.f; c[nt][1] = 0.f; c[nt][2] = 0.f; c[nt][3] = 0.f; }
+#pragma unroll
+      for (int st = 0; st < 2; ++st) {
+        const int kb = 32 * warp + 16 * st;
+        uint32_t a[4];
+        load_a_frag(&sm.buf[0][0], kb, g8, tq, a);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const uint32_t* bp = reinterpret_cast<const uint32_t*>(&sm.wB[nt * 8 + g8][kb + 2 * tq]);
+          mma_bf16_16816(c[nt], a[0], a[1], a[2], a[3], bp[0], bp[4]);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) store_c_frag17(sm.red, warp, nt, g8, tq, c[nt]);
+      __syncthreads();
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s += sm.red[(w * kRows + b) * 17 + j];
+      float dz = 0.f, dr = 0.f, dc = 0.f, dcr = 0.f;
+      if (row_ok) {
+        const float d = s + e_d + dh_carry;
+        dz = d * (e_h - e_c) * e_z * (1.f - e_z);
+        dc = d * (1.f - e_z) * (1.f - e_c * e_c);
+        dr = dc * e_g * e_r * (1.f - e_r);
+        dcr = dc * e_r;
+        dhz = d * e_z;
+        float* gxo = p.dgx + bt * 3 * G;
+        float* gho = p.dgh + bt * 3 * G;
+        gxo[u] = dz; gxo[G + u] = dr; gxo[2 * G + u] = dc;
+        gho[u] = dz; gho[G + u] = dr; gho[2 * G + u] = dcr;
+      }
+      sm.xg[0][b][j] = __float2bfloat16_rn(dz); sm.xg[1][b][j] = __float2bfloat16_rn(dr);
+      sm.xg[2][b][j] = __float2bfloat16_rn(dc); sm.xg[3][b][j] = __float2bfloat16_rn(dcr);
+      __syncthreads();
+      // my 4 x [16 rows][16 units] bf16 blocks -> units [16 rank, +16) of every peer's dg: thread -> (peer, 8 chunks of 16 bytes)
+      const unsigned peer = tid >> 4;
+      __nv_bfloat16* dst = cl.map_shared_rank(&sm.x.dg[0][0][0], peer);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int q = (tid & 15) + 16 * m, blk = q >> 5, row = (q >> 1) & 15, half = q & 1;
+        const uint4 v = *reinterpret_cast<const uint4*>(&sm.xg[blk][row][8 * half]);
+        *reinterpret_cast<uint4*>(dst + ((size_t)blk * kRows + row) * kWLd + u0 + 8 * half) = v;
+      }
+    }
+    stamp(si + 5);
+    cl.sync();
+    stamp(si + 6);
+
+    // ===== S4: dh_in[:, my units] = dh z + [dz dr dc r] . U^T;  du[:, my columns] = [dz dr dc] . K^T (K = 768: 6 k-steps per warp) =====
+    {
+      float ch[2][4], cu[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        ch[nt][0] = 0.f; ch[nt][1] = 0.f; ch[nt][2] = 0.f; ch[nt][3] = 0.f;
+        cu[nt][0] = 0.f; cu[nt][1] = 0.f; cu[nt][2] = 0.f; cu[nt][3] = 0.f;
+      }
+#pragma unroll
+      for (int st = 0; st < 6; ++st) {
+        const int ks = 6 * warp + st, gate = ks >> 4, kk = (ks & 15) * 16, kw = gate * kG + kk;
+        uint32_t ax[4], ah[4];
+        load_a_frag16(&sm.x.dg[gate][0][0], kWLd, kk, g8, tq, ax);
+        if (gate == 2) load_a_frag16(&sm.x.dg[3][0][0], kWLd, kk, g8, tq, ah);
+        else { ah[0] = ax[0]; ah[1] = ax[1]; ah[2] = ax[2]; ah[3] = ax[3]; }
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const uint32_t* bu = reinterpret_cast<const uint32_t*>(&sm.wC[nt * 8 + g8][kw + 2 * tq]);
+          const uint32_t* bk = reinterpret_cast<const uint32_t*>(&sm.wD[nt * 8 + g8][kw + 2 * tq]);
+          mma_bf16_16816(ch[nt], ah[0], ah[1], ah[2], ah[3], bu[0], bu[4]);
+          mma_bf16_16816(cu[nt], ax[0], ax[1], ax[2], ax[3], bk[0], bk[4]);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) { store_c_frag17(sm.red, warp, nt, g8, tq, ch[nt]); store_c_frag17(sm.red, kWarps + warp, nt, g8, tq, cu[nt]); }
+      __syncthreads();
+      float sh = 0.f, su = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) { sh += sm.red[(w * kRows + b) * 17 + j]; su += sm.red[((kWarps + w) * kRows + b) * 17 + j]; }
+      if (row_ok) {
+        const float v = sh + dhz;
+        p.dh_in[bt * G + u] = v;
+        dh_carry = keep * v;
+        p.du[bt * D + u0 + j] = su;
+      } else {
+        su = 0.f;
+      }
+      broadcast_block_b(cl, sm, u0, su);
+    }
+    stamp(si + 7);
+    cl.sync();
+    stamp(si + 8);
+
+    // ===== S5: dx_pre (whole rows, every CTA); dz_in of my 64 columns stays here for S1 of step t-1 =====
+    ln_bwd_inplace(&sm.buf[0][0], xx, mx_, rx, sm.lnp[2], sm.lnp[3], B, rank, p.dx_pre + (size_t)t * D, (size_t)T * D);
+    if (t > 0) {
+      mma_pass<64>(&sm.buf[0][0], &sm.wE[0][0], sm.red);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) sm.dzc[b][j + 16 * m] = keep4[m] * red_sum<64>(sm.red, b, j + 16 * m);
+      __syncthreads();
+    }
+  }
+}
+
 }  // namespace
 
 // The cluster version needs the XS layer sizes (everything resident in 16 SMs' shared memory).
@@ -564,8 +926,30 @@ static cudaError_t launch_cluster_variant(cudaStream_t s, const ScanFwdParams& p
 // bf16: the tensor-core variant (compute mode 1): bf16 weights resident on chip (the one-hot gather of W_pre included), mma.sync
 // contractions with fp32 accumulation; everything else (LayerNorm, gates, softmax, the fp64 inverse-CDF draw) as in the fp32 variant
 cudaError_t launch_observe_scan_cluster(cudaStream_t s, const ScanFwdParams& p, bool bf16) {
-  static const bool no_tc = std::getenv("DV3_NO_CLUSTER_TC") != nullptr;
+  const bool no_tc = std::getenv("DV3_NO_CLUSTER_TC") != nullptr;
   return (bf16 && !no_tc) ? launch_cluster_variant<true>(s, p) : launch_cluster_variant<false>(s, p);
 }
+
+// The backward cluster kernel: same size limits as the forward one; tensor-core mode only (its contractions are bf16)
+bool scan_bwd_cluster_supported(const ScanBwdParams& p) {
+  return p.G == kG && p.D == kG && p.Z == kC * kZC && p.Zk == 32 && p.Zc == 32 && p.B <= kRows && p.W_zq != nullptr &&
+         std::getenv("DV3_NO_CLUSTER_SCAN") == nullptr && std::getenv("DV3_NO_CLUSTER_BWD") == nullptr;
+}
+
+cudaError_t launch_observe_scan_bwd_cluster(cudaStream_t s, const ScanBwdParams& p) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(observe_scan_bwd_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(observe_scan_bwd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BSmem));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  observe_scan_bwd_cluster_kernel<<<dim3(kC), dim3(kThreads), sizeof(BSmem), s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) count_launch();
+  return e;
+}
+
 
 }  // namespace dv3

@@ -13,9 +13,8 @@ from dreamer_v3_b200.spec import init_params  # noqa: E402
 
 wid = sys.argv[1] if len(sys.argv) > 1 else "c2"
 cfg = make_cfg(wid)
-if len(sys.argv) > 2:
-    cfg.compute_mode = int(sys.argv[2])   # 0 fp32, 1 bf16 tensor-core mode
-e = Engine(cfg)
+mode = int(sys.argv[2]) if len(sys.argv) > 2 else 0   # 0 fp32, 1 bf16 tensor-core mode
+e = Engine(cfg, compute_mode=mode)
 e.load_params(init_params(cfg, seed=0))
 e.set_sample(synthetic_sample(cfg, 0))
 e.fill_noise(1, 0, 3)
@@ -40,7 +39,11 @@ st = e.tensor("debug.scan_stamps").cpu().numpy().astype(np.int64)
 st = (st[0::2] & 0xFFFFFFFF) | (st[1::2] << 32)
 d = np.diff(st[: T * 8 + 1].astype(np.float64)) / 1e3
 d = d.reshape(T, 8)
-if os.environ.get("DV3_SCAN_BWD_V1"):
+if mode == 1 and not os.environ.get("DV3_NO_CLUSTER_BWD"):
+    # cluster kernel: stamps close S1, S2, S3, S4 and follow each barrier; S5 of step t is counted with S1 of step t-1
+    names = ["S5+S1 work", "sync1", "S2 work", "sync2", "S3 work", "sync3", "S4 work", "sync4"]
+    print("backward (cluster) per-step mean us:", {n: round(float(d[2:-1, i].mean()), 2) for i, n in enumerate(names)}, "step total", round(float(d[2:-1].sum(1).mean()), 2))
+elif os.environ.get("DV3_SCAN_BWD_V1"):
     names = ["S1 work", "S1 sync", "S2 work", "S2 sync", "S3 work", "S3 sync", "S4 work", "S4 sync"]
     print("backward (four-stage) per-step mean us:", {n: round(float(d[2:-1, i].mean()), 2) for i, n in enumerate(names)}, "step total", round(float(d[2:-1].sum(1).mean()), 2))
 else:   # two-stage kernel: stamps 1-3 close X(t), 4 follows its barrier, 5-7 close Y(t), 8 follows its barrier
