@@ -602,6 +602,61 @@ __global__ void repr_bwd_kernel(const float* __restrict__ logits, int ldl, const
   }
 }
 
+// Same, 32-class categoricals, four per warp at a time (loads issued together, shuffle chains interleaved; see repr_fwd4_kernel)
+__global__ void __launch_bounds__(256) repr_bwd4_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ dz, int lddz,
+                                                        const float* __restrict__ dprobs, int lddp, float* __restrict__ dlogits, int lddl,
+                                                        int M, int Zc, __nv_bfloat16* __restrict__ dl16) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int groups = Zc / 4;
+  const long long total = (long long)M * groups;
+  for (long long w = warp0; w < total; w += nwarps) {
+    const int r = (int)(w / groups), c0 = (int)(w % groups) * 4;
+    float l[4], g[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int col = (c0 + q) * 32 + lane;
+      l[q] = logits[(size_t)r * ldl + col];
+      float gg = 0.f;
+      if (dz != nullptr) gg += dz[(size_t)r * lddz + col];
+      if (dprobs != nullptr) gg += dprobs[(size_t)r * lddp + col];
+      g[q] = gg * 0.99f;
+    }
+    float mx[4], e[4], sden[4], p[4], dot[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) mx[q] = l[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], o));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { e[q] = expf(l[q] - mx[q]); sden[q] = e[q]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sden[q] += __shfl_xor_sync(0xffffffffu, sden[q], o);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { p[q] = e[q] / sden[q]; dot[q] = g[q] * p[q]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dot[q] += __shfl_xor_sync(0xffffffffu, dot[q], o);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int col = (c0 + q) * 32 + lane;
+      const float o = p[q] * (g[q] - dot[q]);
+      dlogits[(size_t)r * lddl + col] = o;
+      if (dl16 != nullptr) dl16[(size_t)r * lddl + col] = __float2bfloat16_rn(o);
+    }
+  }
+}
+
 // ---- observe-scan masking (world_model.py:246-253) -----------------------------------------------------------
 __global__ void scan_mask_inputs_kernel(const float* __restrict__ is_first, int ldf, const float* __restrict__ h_prev,
                                         int ldhp, const float* __restrict__ z_prev, int ldzp,
@@ -820,6 +875,12 @@ void repr_fwd(cudaStream_t s, const float* logits, int ldl, float* probs, int ld
 void repr_bwd(cudaStream_t s, const float* logits, int ldl, const float* dz, int lddz, const float* dprobs, int lddp,
               float* dlogits, int lddl, int M, int Zc, int Zk, void* dl16) {
   if (M <= 0) return;
+  if (Zk == 32 && Zc % 4 == 0) {
+    launch_pdl(repr_bwd4_kernel, dim3(grid_for((long long)M * (Zc / 4), kThreads / 32)), dim3(kThreads), 0, s, logits, ldl, dz, lddz, dprobs, lddp, dlogits, lddl, M, Zc,
+               reinterpret_cast<__nv_bfloat16*>(dl16));
+    count_launch();
+    return;
+  }
   launch_pdl(repr_bwd_kernel, dim3(grid_for((long long)M * Zc, kThreads / 32)), dim3(kThreads), 0, s, logits, ldl, dz, lddz, dprobs, lddp, dlogits, lddl, M, Zc, Zk, reinterpret_cast<__nv_bfloat16*>(dl16));
   count_launch();
 }

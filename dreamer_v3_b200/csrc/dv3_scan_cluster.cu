@@ -689,22 +689,59 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
     }
   };
   stamp(0);
-
-  for (int t = T - 1; t >= 0; --t) {
-    const int si = (T - 1 - t) * 8;
-    const size_t bt = (size_t)(row_ok ? b : 0) * T + t;
-    // ---- everything this step reads from the forward pass / the head gradients, issued before the first stage ----
-    float q_l[4], q_dp[4], q_dz[4];          // S1: logits, dKL/dprobs, d_hz.z of my (row, categorical) pairs
+  // S1 is the first thing a step does with data from global memory: its operands are fetched one step ahead (before S5 of
+  // the step before), so that no L2 round trip sits between the LayerNorm backward of S5 and the categorical backward of S1
+  float q_l[4], q_dp[4], q_dz[4];
+  auto load_s1 = [&](int tt) {
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4) {
       const int pr = warp + q4 * kWarps, r = pr >> 1, cl_ = pr & 1;
       const bool ok = r < B;
-      const size_t rt = (size_t)(ok ? r : 0) * T + t;
+      const size_t rt = (size_t)(ok ? r : 0) * T + tt;
       const int col = z0c + cl_ * 32 + lane;
       q_l[q4] = ok ? p.post_logits[rt * Z + col] : 0.f;
       q_dp[q4] = ok ? p.dpost[rt * Z + col] : 0.f;
       q_dz[q4] = ok ? p.d_hz[rt * W + G + col] : 0.f;
     }
+  };
+  load_s1(T - 1);
+
+  for (int t = T - 1; t >= 0; --t) {
+    const int si = (T - 1 - t) * 8;
+    const size_t bt = (size_t)(row_ok ? b : 0) * T + t;
+    // ===== S1: categorical backward (representation_layer.py:73-113) of my 2 categoricals x 16 rows, one warp per pair =====
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const int pr = warp + q4 * kWarps, r = pr >> 1, cl_ = pr & 1;
+      const bool ok = r < B;
+      const float l = q_l[q4];
+      float mx = l;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float ex = expf(l - mx);
+      const float sden = warp_sum(ex);
+      const float prb = ex / sden;
+      const float gz = 0.99f * (q_dz[q4] + sm.dzc[r][cl_ * 32 + lane] + q_dp[q4]);
+      const float dot = warp_sum(gz * prb);
+      const float dl = ok ? prb * (gz - dot) : 0.f;
+      if (ok) p.dlogits[((size_t)r * T + t) * Z + z0c + cl_ * 32 + lane] = dl;
+      sm.xl[r][cl_ * 32 + lane] = __float2bfloat16_rn(dl);
+    }
+    __syncthreads();
+    stamp(T * 8 + 16 + (T - 1 - t) * 4 + 2);
+    {   // my [16 rows][64 columns] bf16 block -> columns [64 rank, +64) of every peer's dl: thread -> (peer, row), 8 x 16 bytes
+      const unsigned peer = tid >> 4;
+      const int row = tid & 15;
+      __nv_bfloat16* dst = cl.map_shared_rank(&sm.x.dl[0][0], peer) + (size_t)row * kLdL + z0c;
+      const uint4* src = reinterpret_cast<const uint4*>(&sm.xl[row][0]);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) reinterpret_cast<uint4*>(dst)[c] = src[c];
+    }
+    stamp(T * 8 + 16 + (T - 1 - t) * 4 + 3);
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // the loads below are issued while the barrier completes
+    // ---- everything else this step reads from the forward pass / the head gradients: issued here, behind the broadcast the peers
+    // wait for, and in flight across the barrier (first use in S3) ----
+    // (the S1 operands - logits, dKL/dprobs, d_hz.z of my (row, categorical) pairs - were loaded one step ahead: q_l, q_dp, q_dz)
     float xp[2][EPL], xx[2][EPL], mp[2], rp[2], mx_[2], rx[2];   // S3 / S5: LayerNorm inputs of rows warp, warp + 8
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -731,35 +768,8 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
 #pragma unroll
     for (int m = 0; m < 4; ++m) keep4[m] = keep;
 
-    // ===== S1: categorical backward (representation_layer.py:73-113) of my 2 categoricals x 16 rows, one warp per pair =====
-#pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {
-      const int pr = warp + q4 * kWarps, r = pr >> 1, cl_ = pr & 1;
-      const bool ok = r < B;
-      const float l = q_l[q4];
-      float mx = l;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const float ex = expf(l - mx);
-      const float sden = warp_sum(ex);
-      const float prb = ex / sden;
-      const float gz = 0.99f * (q_dz[q4] + sm.dzc[r][cl_ * 32 + lane] + q_dp[q4]);
-      const float dot = warp_sum(gz * prb);
-      const float dl = ok ? prb * (gz - dot) : 0.f;
-      if (ok) p.dlogits[((size_t)r * T + t) * Z + z0c + cl_ * 32 + lane] = dl;
-      sm.xl[r][cl_ * 32 + lane] = __float2bfloat16_rn(dl);
-    }
-    __syncthreads();
-    {   // my [16 rows][64 columns] bf16 block -> columns [64 rank, +64) of every peer's dl: thread -> (peer, row), 8 x 16 bytes
-      const unsigned peer = tid >> 4;
-      const int row = tid & 15;
-      __nv_bfloat16* dst = cl.map_shared_rank(&sm.x.dl[0][0], peer) + (size_t)row * kLdL + z0c;
-      const uint4* src = reinterpret_cast<const uint4*>(&sm.xl[row][0]);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) reinterpret_cast<uint4*>(dst)[c] = src[c];
-    }
     stamp(si + 1);
-    cl.sync();
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     stamp(si + 2);
 
     // ===== S2: dp_act[:, my 16 columns] = dlogits . W_zq^T (K = 1024: 8 k-steps per warp) =====
@@ -889,13 +899,16 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
     stamp(si + 8);
 
     // ===== S5: dx_pre (whole rows, every CTA); dz_in of my 64 columns stays here for S1 of step t-1 =====
+    if (t > 0) load_s1(t - 1);
     ln_bwd_inplace(&sm.buf[0][0], xx, mx_, rx, sm.lnp[2], sm.lnp[3], B, rank, p.dx_pre + (size_t)t * D, (size_t)T * D);
+    stamp(T * 8 + 16 + (T - 1 - t) * 4 + 0);
     if (t > 0) {
       mma_pass<64>(&sm.buf[0][0], &sm.wE[0][0], sm.red);
 #pragma unroll
       for (int m = 0; m < 4; ++m) sm.dzc[b][j + 16 * m] = keep4[m] * red_sum<64>(sm.red, b, j + 16 * m);
       __syncthreads();
     }
+    stamp(T * 8 + 16 + (T - 1 - t) * 4 + 1);
   }
 }
 

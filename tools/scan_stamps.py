@@ -43,6 +43,15 @@ if mode == 1 and not os.environ.get("DV3_NO_CLUSTER_BWD"):
     # cluster kernel: stamps close S1, S2, S3, S4 and follow each barrier; S5 of step t is counted with S1 of step t-1
     names = ["S5+S1 work", "sync1", "S2 work", "sync2", "S3 work", "sync3", "S4 work", "sync4"]
     print("backward (cluster) per-step mean us:", {n: round(float(d[2:-1, i].mean()), 2) for i, n in enumerate(names)}, "step total", round(float(d[2:-1].sum(1).mean()), 2))
+    # sub-stamps inside "S5+S1": after the LayerNorm backward of S5, after dz_in, after the categorical backward of S1, after its broadcast
+    sub = st[T * 8 + 16: T * 8 + 16 + T * 4].astype(np.float64).reshape(T, 4)
+    s8 = st[: T * 8 + 1].astype(np.float64)
+    rows = []
+    for k in range(2, T - 1):   # step index k (t = T-1-k): S5 of step k starts at stamp 8k+8, S1 of step k+1 ends at stamp 8(k+1)+1
+        t0 = s8[8 * k + 8]
+        rows.append([(sub[k, 0] - t0), (sub[k, 1] - sub[k, 0]), (sub[k + 1, 2] - sub[k, 1]), (sub[k + 1, 3] - sub[k + 1, 2]), (s8[8 * (k + 1) + 1] - sub[k + 1, 3])])
+    m = np.array(rows).mean(0) / 1e3
+    print("  S5 LN bwd %.2f, S5 dz_in %.2f, S1 categorical bwd %.2f, S1 broadcast %.2f, step loads %.2f us" % tuple(m))
 elif os.environ.get("DV3_SCAN_BWD_V1"):
     names = ["S1 work", "S1 sync", "S2 work", "S2 sync", "S3 work", "S3 sync", "S4 work", "S4 sync"]
     print("backward (four-stage) per-step mean us:", {n: round(float(d[2:-1, i].mean()), 2) for i, n in enumerate(names)}, "step total", round(float(d[2:-1].sum(1).mean()), 2))
