@@ -20,6 +20,8 @@
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
+#include <cstddef>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -47,10 +49,13 @@ struct CCommon {
   float gh[kRows][3 * kU];    // gh(t) of my units (z, r, c gate blocks of 16)
   float gh0[3 * kU];          // h0 . U + b for my units
   float hown[kRows][kU];      // h_{t-1} of my units
-  float xch[kU][kRows];       // this CTA's [16 columns][16 rows] block, staged for the vectorised DSMEM broadcast
-  int idx[kRows][32];         // z_{t-1} class indices of every row (all 32 categoricals)
+  float xch[3][kU][kLd];      // this CTA's [16 columns][16 rows (+ pad)] blocks of exchanges A, B, C, staged in the layout of its slice
+                              // of buf0 / buf1 (one staging block per exchange: a block is rewritten one whole step later, when every
+                              // peer is known to have received it)
+  int idx[kC][kRows][2];      // z_{t-1} class indices: [owner CTA][row][its 2 categoricals] (categorical c -> idx[c / 2][row][c % 2])
+  int xidx[kRows][2];         // this CTA's picks, staged
+  unsigned long long xbar[4]; // mbarriers: arrival of all 16 blocks of exchange A (x_pre), B (h), C (p_pre), D (indices)
   int idx0[32];               // mode of the prior at the initial state (rows that restart)
-  float h0[kG];               // learned initial state
   float lnp[4][kG];           // LayerNorm gain / offset of the pre-GRU and the posterior layer
 };
 struct CSmem : CCommon {      // fp32 variant: weights [k][column]
@@ -189,20 +194,57 @@ __device__ __forceinline__ void mma_pass16(const float* in_s, const __nv_bfloat1
   __syncthreads();
 }
 
-// Broadcasts this CTA's block (value `v` of thread (row b, column j)) into rows [u0, u0 + 16) of every peer's [k][row] buffer:
-// staged through shared memory so that each remote store carries 4 rows (16 bytes) instead of 4 bytes.
-__device__ __forceinline__ void broadcast_block(cg::cluster_group& cl, CCommon& sm, float* buf_local, int u0, float v) {
-  const int b = threadIdx.x >> 4, j = threadIdx.x & 15;
-  sm.xch[j][b] = v;
+// ---- exchange between the CTAs of the cluster -------------------------------------------------------------------------------
+// A producer stages its block in its own shared memory in exactly the layout of its slice of the peers' receive buffer and
+// hands it to the bulk-copy engine once per peer (cp.async.bulk shared::cta -> shared::cluster, one elected thread per peer):
+// the 16 copies run at DSMEM bandwidth without occupying the LSU, and each signals the DESTINATION's mbarrier with its byte
+// count. A consumer waits on its own mbarrier for the bytes of all 16 producers - the arrival of the data is the signal, so a
+// step has no cluster-wide barrier at all. Write-after-read safety follows from the data flow: a CTA can only produce the block
+// of exchange n + 1 after it has received every block of exchange n, i.e. after every peer has finished the stage that read the
+// buffers of exchange n - 1 ... (each buffer is rewritten two exchanges later at the earliest; see the stage order).
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void xbar_init(unsigned long long* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
+}
+// one thread: this phase completes after `bytes` have landed in my receive buffer
+__device__ __forceinline__ void xbar_arm(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void xbar_wait(unsigned long long* bar, uint32_t parity) {
+  const uint32_t a = smem_addr(bar);
+  uint32_t done, spins = 0;
+  do {
+    if (++spins > (1u << 26)) { printf("dv3 cluster scan: exchange wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// all threads call it after writing `staging` (bytes, multiple of 16): block -> offset rank * bytes of every peer's `recv`
+__device__ __forceinline__ void xchg_send(void* recv, const void* staging, uint32_t bytes, unsigned long long* bar, unsigned rank) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // my generic-proxy writes of the staging block -> async proxy
   __syncthreads();
-  const unsigned peer = threadIdx.x >> 4;
-  float* dst = cl.map_shared_rank(buf_local, peer);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int chunk = (threadIdx.x & 15) + 16 * i, col = chunk >> 2, rg = chunk & 3;
-    const float4 q = *reinterpret_cast<const float4*>(&sm.xch[col][4 * rg]);
-    *reinterpret_cast<float4*>(dst + (size_t)(u0 + col) * kLd + 4 * rg) = q;
+  if (threadIdx.x < kC) {
+    const uint32_t dst = map_to_rank(smem_addr(recv) + rank * bytes, threadIdx.x);
+    const uint32_t mb = map_to_rank(smem_addr(bar), threadIdx.x);
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "r"(smem_addr(staging)), "r"(bytes), "r"(mb) : "memory");
   }
+}
+constexpr uint32_t kBlkBytes = kU * kLd * 4;   // a CTA's [16 columns][20] fp32 slice of buf0 / buf1
+// this thread's value of (row b = tid / 16, column j = tid % 16) -> my slice of every peer's buf[k][row]
+__device__ __forceinline__ void send_block(float (*xch)[kLd], float* buf, unsigned long long* bar, unsigned rank, float v) {
+  xch[threadIdx.x & 15][threadIdx.x >> 4] = v;
+  xchg_send(buf, &xch[0][0], kBlkBytes, bar, rank);
 }
 
 // In-place LayerNorm + SiLU of the 16 rows staged as buf[k][row]; one warp per row (2 rows per warp, both in flight).
@@ -306,10 +348,13 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
 #pragma unroll
     for (int i = 0; i < 16; ++i) wP[i] = W_post_h[(size_t)(k0 + 2 * i) * D + u0 + (lane & 15)];
   }
-  for (int e = tid; e < kRows * 32; e += kThreads) sm.idx[e / 32][e % 32] = p.z0_idx[e % 32];
+  for (int e = tid; e < kC * kRows * 2; e += kThreads) (&sm.idx[0][0][0])[e] = p.z0_idx[(e / (2 * kRows)) * 2 + (e & 1)];
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) xbar_init(&sm.xbar[i]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   if (tid < 32) sm.idx0[tid] = p.z0_idx[tid];
   for (int e = tid; e < kG; e += kThreads) {
-    sm.h0[e] = p.h0[e];
     sm.lnp[0][e] = p.pre_g[e]; sm.lnp[1][e] = p.pre_b[e]; sm.lnp[2][e] = p.post_g[e]; sm.lnp[3][e] = p.post_b[e];
   }
   for (int e = tid; e < kRows * kU; e += kThreads) sm.hown[e / kU][e % kU] = p.h0[u0 + (e % kU)];
@@ -325,6 +370,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
 
   const int b = tid >> 4, j = tid & 15;   // (row, owned column) of this thread in the 16 x 16 epilogues
   const bool row_ok = b < B;
+  const float h0_own = p.h0[u0 + j];      // learned initial state of this thread's unit (rows that restart)
   // per-thread constants and the first step's streamed inputs (later steps are prefetched one step ahead, so that the
   // only global load a stage ever waits for is the row gather of stage A)
   float gb[6];
@@ -344,6 +390,11 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
 
   for (int t = 0; t < T; ++t) {
     const size_t bt = (size_t)b * T + t;
+    const uint32_t par = (uint32_t)t & 1u;   // phase parity of this step's four exchanges
+    if (tid == 0) {   // (each barrier's previous phase was waited for in the previous step)
+      xbar_arm(&sm.xbar[0], kC * kBlkBytes); xbar_arm(&sm.xbar[1], kC * kBlkBytes); xbar_arm(&sm.xbar[2], kC * kBlkBytes);
+      xbar_arm(&sm.xbar[3], kC * (uint32_t)sizeof(sm.xidx));
+    }
     // streamed inputs of this step, consumed in stages C / D
     const float pp_in = row_ok ? p.p_pre[bt * D + u0 + j] : 0.f;
     float up[4];
@@ -364,7 +415,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
         float w32[32];   // all 32 row gathers in flight at once: one L2 round trip instead of four (tensor-core variant: on chip)
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const int cls = first ? sm.idx0[c] : sm.idx[b][c];
+          const int cls = first ? sm.idx0[c] : sm.idx[c >> 1][b][c & 1];
           if constexpr (kTc) w32[c] = __bfloat162float(sm.wX[c * Zk + cls][j]);
           else w32[c] = p.W_pre[(size_t)(c * Zk + cls) * D + u0 + j];
         }
@@ -372,19 +423,19 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
         for (int c = 0; c < 32; ++c) x += w32[c];
         p.x_pre[bt * D + u0 + j] = x;
         // masked recurrent inputs kept for the backward pass (world_model.py:246-250): my units / my 2 categoricals
-        p.h_in[bt * G + u0 + j] = first ? sm.h0[u0 + j] : sm.hown[b][j];
+        p.h_in[bt * G + u0 + j] = first ? h0_own : sm.hown[b][j];
       }
-      broadcast_block(cl, sm, &sm.buf0[0][0], u0, x);
+      send_block(sm.xch[0], &sm.buf0[0][0], &sm.xbar[0], rank, x);
       if (row_ok) {
         for (int q = j; q < kZC; q += 16) {
           const int cat = (z0c + q) / Zk, cls = (z0c + q) % Zk;
-          const int pick = first ? sm.idx0[cat] : sm.idx[b][cat];
+          const int pick = first ? sm.idx0[cat] : sm.idx[cat >> 1][b][cat & 1];
           p.z_in[bt * Z + z0c + q] = (pick == cls) ? 1.f : 0.f;
         }
       }
     }
     stamp(t * 8 + 1);
-    cl.sync();
+    xbar_wait(&sm.xbar[0], par);
     stamp(t * 8 + 2);
 
     // ===== stage B: u = SiLU(LN(x_pre)); gx for my units; GRU cell =====
@@ -395,7 +446,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
       const int u = u0 + j;
       float hn = 0.f;
       if (row_ok) {
-        const float hp = first ? sm.h0[u] : sm.hown[b][j];
+        const float hp = first ? h0_own : sm.hown[b][j];
         const float ghz = sm.gh[b][j], ghr = sm.gh[b][kU + j], ghc = sm.gh[b][2 * kU + j];
         const float z = sigmoid_fast(red_sum<48>(sm.red, b, j) + gb[0] + ghz);
         const float r = sigmoid_fast(red_sum<48>(sm.red, b, kU + j) + gb[1] + ghr);
@@ -408,11 +459,11 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
         gho[u] = ghz; gho[G + u] = ghr; gho[2 * G + u] = ghc;
       }
       __syncthreads();   // every thread has read hown / gh of this step
-        sm.hown[b][j] = hn;
-      broadcast_block(cl, sm, &sm.buf1[0][0], u0, hn);
+      sm.hown[b][j] = hn;
+      send_block(sm.xch[1], &sm.buf1[0][0], &sm.xbar[1], rank, hn);
     }
     stamp(t * 8 + 3);
-    cl.sync();
+    xbar_wait(&sm.xbar[1], par);
     stamp(t * 8 + 4);
 
     // ===== stage C: p_pre (my 16 columns, weights in registers); gh(t+1) for my units =====
@@ -451,12 +502,10 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
         pv = pp_in + s;     // p_pre was pre-loaded with enc . W_post[:E]
         p.p_pre[bt * D + u0 + j] = pv;
       }
-      broadcast_block(cl, sm, &sm.buf0[0][0], u0, pv);
-      __syncthreads();
+      send_block(sm.xch[2], &sm.buf0[0][0], &sm.xbar[2], rank, pv);
     }
-    // everything the peers wait for (my p_pre columns) is on its way: arrive now and compute gh(t+1), which only this CTA reads,
-    // while the barrier completes
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    // everything the peers wait for (my p_pre columns) is on its way: gh(t+1), which only this CTA reads, is computed while the
+    // blocks travel
     if (t + 1 < T) {
       if constexpr (kTc) mma_pass<48>(&sm.buf1[0][0], &sm.wU[0][0], sm.red);
       else tile_pass<3>(&sm.buf1[0][0], &sm.wU[0][0], sm.red);
@@ -467,7 +516,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
       }
     }
     stamp(t * 8 + 5);
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    xbar_wait(&sm.xbar[2], par);
     stamp(t * 8 + 6);
 
     // ===== stage D: p_act = SiLU(LN(p_pre)); logits for my 64 columns; sample my 2 categoricals =====
@@ -526,15 +575,18 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
         p.post_probs[rt * Z + cat * 32 + lane] = pu[q4];
         if (lane == 0) p.z_idx[rt * Zc + cat] = pick;
         p.hz[rt * W + G + cat * 32 + lane] = (lane == pick) ? 1.f : 0.f;
-        if (lane < kC) cl.map_shared_rank(&sm.idx[0][0], lane)[r * 32 + cat] = pick;
+        if (lane == 0) sm.xidx[r][cl_] = pick;
       }
+      for (int pr = warp; pr < 2 * kRows; pr += kWarps) if ((pr >> 1) >= B && lane == 0) sm.xidx[pr >> 1][pr & 1] = 0;
+      xchg_send(&sm.idx[0][0][0], &sm.xidx[0][0], (uint32_t)sizeof(sm.xidx), &sm.xbar[3], rank);
     }
     first = first_n;
     actw = actw_n;
     stamp(t * 8 + 7);
-    cl.sync();
+    xbar_wait(&sm.xbar[3], par);
     stamp(t * 8 + 8);
   }
+  cl.sync();   // no CTA leaves while a peer may still be reading its staging blocks
 }
 
 
@@ -554,8 +606,10 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
 //   S5  dx_pre = LN'SiLU'(du); dz_in[:, my 64 cols] = dx_pre . W_pre[:Z]^T: stays in this CTA (it is the z-gradient of the
 //       categoricals S1 of step t-1 handles here); nothing of the recurrence goes through global memory.
 // Everything a stage reads from the forward pass is loaded at the top of the step, before S1 (no dependent L2 round trip inside).
-constexpr int kLdL = kC * kZC + 8;   // bf16 row stride of the staged dlogits   [row][1024 + 8]
-constexpr int kLdG = 3 * kG + 8;     // bf16 k stride of the resident U / K rows [unit][768 + 8]
+constexpr int kLdL = kC * kZC + 8;   // bf16 k stride of the resident W_zq rows   [column][1024 + 8]
+constexpr int kLdG = 3 * kG + 8;     // bf16 k stride of the resident U / K rows  [unit][768 + 8]
+constexpr int kLdXl = kZC + 8;       // row stride of a CTA's dlogits block       [row][64 + 8]   (fragment loads: 32 distinct banks)
+constexpr int kLdXg = kU + 8;        // row stride of a CTA's gate-gradient block [row][16 + 8]   (same)
 
 struct BSmem {
   __nv_bfloat16 wA[kU][kLdL];      // W_zq[my 16 rows][Z]             33 KB
@@ -563,19 +617,24 @@ struct BSmem {
   __nv_bfloat16 wC[kU][kLdG];      // U[my 16 units][3G]              24 KB
   __nv_bfloat16 wD[kU][kLdG];      // K[my 16 columns][3G]            24 KB
   __nv_bfloat16 wE[kZC][kWLd];     // W_pre[my 64 rows][D]            33 KB
-  union {                          // operands every peer writes into (never live at the same time, see the barriers)
-    __nv_bfloat16 dl[kRows][kLdL];       // dlogits[t], all 1024 columns
-    __nv_bfloat16 dg[4][kRows][kWLd];    // dz, dr, dc, dc r of all 256 units
+  union {                          // receive buffers, one block per producing CTA (never live at the same time)
+    __nv_bfloat16 dl[kC][kRows][kLdXl];      // dlogits[t]: [owner CTA][row][its 64 columns]                    36 KB
+    __nv_bfloat16 dg[kC][4][kRows][kLdXg];   // dz, dr, dc, dc r: [owner CTA][gate block][row][its 16 units]     48 KB
   } x;
   float buf[kG][kLd];              // dp_act -> dp_pre, then du -> dx_pre: fp32 [k][row]   20 KB
   float red[2 * kWarps * kRows * 17];   // per-warp partial sums (two products in S4); [4][16][65] in S5
   float dzc[kRows][kZC + 1];       // carried z-gradient of my 64 columns: (1 - is_first[t+1]) dz_in[t+1]
-  float xch[kU][kRows];            // my [16 columns][16 rows] fp32 block, staged for the broadcast
-  __nv_bfloat16 xl[kRows][kZC];    // my dlogits block, staged for the broadcast
-  __nv_bfloat16 xg[4][kRows][kU];  // my gate-gradient blocks, staged for the broadcast
+  float xch[2][kU][kLd];           // my [16 columns][16 rows (+ pad)] fp32 blocks of dp_act / du, staged in the layout of my slice of buf
+  __nv_bfloat16 xl[kRows][kLdXl];  // my dlogits block, staged
+  __nv_bfloat16 xg[4][kRows][kLdXg];   // my gate-gradient blocks, staged
   float lnp[4][kG];                // post_g, post_b, pre_g, pre_b
+  unsigned long long xbar[4];      // mbarriers: all 16 blocks of dlogits / dp_act / gate gradients / du have landed
 };
 static_assert(sizeof(BSmem) <= 227 * 1024, "cluster scan backward shared memory");
+static_assert(offsetof(BSmem, x) % 16 == 0 && offsetof(BSmem, buf) % 16 == 0 && offsetof(BSmem, xch) % 16 == 0 && offsetof(BSmem, xl) % 16 == 0 &&
+              offsetof(BSmem, xg) % 16 == 0 && offsetof(BSmem, xbar) % 8 == 0, "bulk copies need 16-byte aligned blocks");
+static_assert(offsetof(CCommon, buf1) % 16 == 0 && offsetof(CCommon, xch) % 16 == 0 && offsetof(CCommon, idx) % 16 == 0 &&
+              offsetof(CCommon, xidx) % 16 == 0 && offsetof(CCommon, xbar) % 8 == 0, "bulk copies need 16-byte aligned blocks");
 static_assert(2 * kWarps * kRows * 17 >= 4 * kRows * (kZC + 1), "red holds the S5 partial sums");
 
 __device__ __forceinline__ float silu_grad_fast(float n) {
@@ -640,20 +699,6 @@ __device__ __forceinline__ void ln_bwd_inplace(float* buf, const float (&xr)[2][
   }
   __syncthreads();
 }
-// my [16 columns][16 rows] fp32 block (value v of thread (row b, column j)) into rows [u0, u0 + 16) of every peer's buf[k][row]
-__device__ __forceinline__ void broadcast_block_b(cg::cluster_group& cl, BSmem& sm, int u0, float v) {
-  const int b = threadIdx.x >> 4, j = threadIdx.x & 15;
-  sm.xch[j][b] = v;
-  __syncthreads();
-  float* dst = cl.map_shared_rank(&sm.buf[0][0], threadIdx.x >> 4);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int chunk = (threadIdx.x & 15) + 16 * i, col = chunk >> 2, rg = chunk & 3;
-    const float4 q = *reinterpret_cast<const float4*>(&sm.xch[col][4 * rg]);
-    *reinterpret_cast<float4*>(dst + (size_t)(u0 + col) * kLd + 4 * rg) = q;
-  }
-}
-
 __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observe_scan_bwd_cluster_kernel(ScanBwdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BSmem& sm = *reinterpret_cast<BSmem*>(smem_raw);
@@ -675,6 +720,13 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
   for (int e = tid; e < kZC * D; e += kThreads) { const int n = e / D, k = e - n * D; sm.wE[n][k] = __float2bfloat16_rn(p.W_pre[(size_t)(z0c + n) * D + k]); }
   for (int e = tid; e < kG; e += kThreads) { sm.lnp[0][e] = p.post_g[e]; sm.lnp[1][e] = p.post_b[e]; sm.lnp[2][e] = p.pre_g[e]; sm.lnp[3][e] = p.pre_b[e]; }
   for (int e = tid; e < kRows * (kZC + 1); e += kThreads) (&sm.dzc[0][0])[e] = 0.f;
+  for (int e = tid; e < kRows * kLdXl; e += kThreads) (&sm.xl[0][0])[e] = __float2bfloat16_rn(0.f);
+  for (int e = tid; e < 4 * kRows * kLdXg; e += kThreads) (&sm.xg[0][0][0])[e] = __float2bfloat16_rn(0.f);
+  for (int e = tid; e < 2 * kU * kLd; e += kThreads) (&sm.xch[0][0][0])[e] = 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) xbar_init(&sm.xbar[i]);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   cl.sync();
 
@@ -709,36 +761,53 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
   for (int t = T - 1; t >= 0; --t) {
     const int si = (T - 1 - t) * 8;
     const size_t bt = (size_t)(row_ok ? b : 0) * T + t;
-    // ===== S1: categorical backward (representation_layer.py:73-113) of my 2 categoricals x 16 rows, one warp per pair =====
-#pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {
-      const int pr = warp + q4 * kWarps, r = pr >> 1, cl_ = pr & 1;
-      const bool ok = r < B;
-      const float l = q_l[q4];
-      float mx = l;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const float ex = expf(l - mx);
-      const float sden = warp_sum(ex);
-      const float prb = ex / sden;
-      const float gz = 0.99f * (q_dz[q4] + sm.dzc[r][cl_ * 32 + lane] + q_dp[q4]);
-      const float dot = warp_sum(gz * prb);
-      const float dl = ok ? prb * (gz - dot) : 0.f;
-      if (ok) p.dlogits[((size_t)r * T + t) * Z + z0c + cl_ * 32 + lane] = dl;
-      sm.xl[r][cl_ * 32 + lane] = __float2bfloat16_rn(dl);
+    const uint32_t par = (uint32_t)(T - 1 - t) & 1u;   // phase parity of this step's four exchanges
+    if (tid == 0) {   // (each barrier's previous phase was waited for in the previous step)
+      xbar_arm(&sm.xbar[0], kC * (uint32_t)sizeof(sm.xl)); xbar_arm(&sm.xbar[1], kC * kBlkBytes);
+      xbar_arm(&sm.xbar[2], kC * (uint32_t)sizeof(sm.xg)); xbar_arm(&sm.xbar[3], kC * kBlkBytes);
     }
-    __syncthreads();
+    // ===== S1: categorical backward (representation_layer.py:73-113) of my 2 categoricals x 16 rows, one warp per pair; the four
+    // pairs of a warp go through the shuffle reductions together =====
+    {
+      float mx[4], ex[4], sden[4], prb[4], gz[4], dot[4];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) mx[q4] = q_l[q4];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) mx[q4] = fmaxf(mx[q4], __shfl_xor_sync(0xffffffffu, mx[q4], o));
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) { ex[q4] = __expf(q_l[q4] - mx[q4]); sden[q4] = ex[q4]; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) sden[q4] += __shfl_xor_sync(0xffffffffu, sden[q4], o);
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int pr = warp + q4 * kWarps, r = pr >> 1, cl_ = pr & 1;
+        prb[q4] = __fdividef(ex[q4], sden[q4]);
+        gz[q4] = 0.99f * (q_dz[q4] + sm.dzc[r][cl_ * 32 + lane] + q_dp[q4]);
+        dot[q4] = gz[q4] * prb[q4];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) dot[q4] += __shfl_xor_sync(0xffffffffu, dot[q4], o);
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int pr = warp + q4 * kWarps, r = pr >> 1, cl_ = pr & 1;
+        const bool ok = r < B;
+        const float dl = ok ? prb[q4] * (gz[q4] - dot[q4]) : 0.f;
+        if (ok) p.dlogits[((size_t)r * T + t) * Z + z0c + cl_ * 32 + lane] = dl;
+        sm.xl[r][cl_ * 32 + lane] = __float2bfloat16_rn(dl);
+      }
+    }
     stamp(T * 8 + 16 + (T - 1 - t) * 4 + 2);
-    {   // my [16 rows][64 columns] bf16 block -> columns [64 rank, +64) of every peer's dl: thread -> (peer, row), 8 x 16 bytes
-      const unsigned peer = tid >> 4;
-      const int row = tid & 15;
-      __nv_bfloat16* dst = cl.map_shared_rank(&sm.x.dl[0][0], peer) + (size_t)row * kLdL + z0c;
-      const uint4* src = reinterpret_cast<const uint4*>(&sm.xl[row][0]);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) reinterpret_cast<uint4*>(dst)[c] = src[c];
-    }
+    xchg_send(&sm.x.dl[0][0][0], &sm.xl[0][0], (uint32_t)sizeof(sm.xl), &sm.xbar[0], rank);   // my block -> dl[rank] of every peer
     stamp(T * 8 + 16 + (T - 1 - t) * 4 + 3);
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // the loads below are issued while the barrier completes
     // ---- everything else this step reads from the forward pass / the head gradients: issued here, behind the broadcast the peers
     // wait for, and in flight across the barrier (first use in S3) ----
     // (the S1 operands - logits, dKL/dprobs, d_hz.z of my (row, categorical) pairs - were loaded one step ahead: q_l, q_dp, q_dz)
@@ -769,7 +838,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
     for (int m = 0; m < 4; ++m) keep4[m] = keep;
 
     stamp(si + 1);
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    xbar_wait(&sm.xbar[0], par);
     stamp(si + 2);
 
     // ===== S2: dp_act[:, my 16 columns] = dlogits . W_zq^T (K = 1024: 8 k-steps per warp) =====
@@ -781,7 +850,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
       for (int st = 0; st < 8; ++st) {
         const int kb = 128 * warp + 16 * st;
         uint32_t a[4];
-        load_a_frag16(&sm.x.dl[0][0], kLdL, kb, g8, tq, a);
+        load_a_frag16(&sm.x.dl[kb >> 6][0][0], kLdXl, kb & 63, g8, tq, a);
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
           const uint32_t* bp = reinterpret_cast<const uint32_t*>(&sm.wA[nt * 8 + g8][kb + 2 * tq]);
@@ -795,10 +864,10 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) s += sm.red[(w * kRows + b) * 17 + j];
       if (row_ok) p.dp_act[bt * D + u0 + j] = s; else s = 0.f;
-      broadcast_block_b(cl, sm, u0, s);
+      send_block(sm.xch[0], &sm.buf[0][0], &sm.xbar[1], rank, s);
     }
     stamp(si + 3);
-    cl.sync();
+    xbar_wait(&sm.xbar[1], par);
     stamp(si + 4);
 
     // ===== S3: dp_pre (whole rows, every CTA); dh of my units; GRU gate gradients =====
@@ -840,19 +909,10 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
       }
       sm.xg[0][b][j] = __float2bfloat16_rn(dz); sm.xg[1][b][j] = __float2bfloat16_rn(dr);
       sm.xg[2][b][j] = __float2bfloat16_rn(dc); sm.xg[3][b][j] = __float2bfloat16_rn(dcr);
-      __syncthreads();
-      // my 4 x [16 rows][16 units] bf16 blocks -> units [16 rank, +16) of every peer's dg: thread -> (peer, 8 chunks of 16 bytes)
-      const unsigned peer = tid >> 4;
-      __nv_bfloat16* dst = cl.map_shared_rank(&sm.x.dg[0][0][0], peer);
-#pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const int q = (tid & 15) + 16 * m, blk = q >> 5, row = (q >> 1) & 15, half = q & 1;
-        const uint4 v = *reinterpret_cast<const uint4*>(&sm.xg[blk][row][8 * half]);
-        *reinterpret_cast<uint4*>(dst + ((size_t)blk * kRows + row) * kWLd + u0 + 8 * half) = v;
-      }
+      xchg_send(&sm.x.dg[0][0][0][0], &sm.xg[0][0][0], (uint32_t)sizeof(sm.xg), &sm.xbar[2], rank);   // my 4 blocks -> dg[rank] of every peer
     }
     stamp(si + 5);
-    cl.sync();
+    xbar_wait(&sm.xbar[2], par);
     stamp(si + 6);
 
     // ===== S4: dh_in[:, my units] = dh z + [dz dr dc r] . U^T;  du[:, my columns] = [dz dr dc] . K^T (K = 768: 6 k-steps per warp) =====
@@ -867,8 +927,8 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
       for (int st = 0; st < 6; ++st) {
         const int ks = 6 * warp + st, gate = ks >> 4, kk = (ks & 15) * 16, kw = gate * kG + kk;
         uint32_t ax[4], ah[4];
-        load_a_frag16(&sm.x.dg[gate][0][0], kWLd, kk, g8, tq, ax);
-        if (gate == 2) load_a_frag16(&sm.x.dg[3][0][0], kWLd, kk, g8, tq, ah);
+        load_a_frag16(&sm.x.dg[kk >> 4][gate][0][0], kLdXg, 0, g8, tq, ax);
+        if (gate == 2) load_a_frag16(&sm.x.dg[kk >> 4][3][0][0], kLdXg, 0, g8, tq, ah);
         else { ah[0] = ax[0]; ah[1] = ax[1]; ah[2] = ax[2]; ah[3] = ax[3]; }
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
@@ -892,10 +952,10 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
       } else {
         su = 0.f;
       }
-      broadcast_block_b(cl, sm, u0, su);
+      send_block(sm.xch[1], &sm.buf[0][0], &sm.xbar[3], rank, su);
     }
     stamp(si + 7);
-    cl.sync();
+    xbar_wait(&sm.xbar[3], par);
     stamp(si + 8);
 
     // ===== S5: dx_pre (whole rows, every CTA); dz_in of my 64 columns stays here for S1 of step t-1 =====
@@ -910,6 +970,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
     }
     stamp(T * 8 + 16 + (T - 1 - t) * 4 + 1);
   }
+  cl.sync();   // no CTA leaves while a peer may still be reading its staging blocks
 }
 
 }  // namespace
