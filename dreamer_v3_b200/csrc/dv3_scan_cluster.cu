@@ -811,19 +811,15 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
     // ---- everything else this step reads from the forward pass / the head gradients: issued here, behind the broadcast the peers
     // wait for, and in flight across the barrier (first use in S3) ----
     // (the S1 operands - logits, dKL/dprobs, d_hz.z of my (row, categorical) pairs - were loaded one step ahead: q_l, q_dp, q_dz)
-    float xp[2][EPL], xx[2][EPL], mp[2], rp[2], mx_[2], rx[2];   // S3 / S5: LayerNorm inputs of rows warp, warp + 8
+    float xp[2][EPL], mp[2], rp[2];   // S3: LayerNorm inputs of rows warp, warp + 8 (those of S5 are loaded behind the S3 send)
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int rb = warp + r * kWarps;
       const bool ok = rb < B;
       const size_t rt = (size_t)(ok ? rb : 0) * T + t;
       mp[r] = ok ? p.p_mean[rt] : 0.f; rp[r] = ok ? p.p_rstd[rt] : 0.f;
-      mx_[r] = ok ? p.x_mean[rt] : 0.f; rx[r] = ok ? p.x_rstd[rt] : 0.f;
 #pragma unroll
-      for (int i = 0; i < EPL; ++i) {
-        xp[r][i] = ok ? p.p_pre[rt * D + lane + 32 * i] : 0.f;
-        xx[r][i] = ok ? p.x_pre[rt * D + lane + 32 * i] : 0.f;
-      }
+      for (int i = 0; i < EPL; ++i) xp[r][i] = ok ? p.p_pre[rt * D + lane + 32 * i] : 0.f;
     }
     const int u = u0 + j;                      // S3 / S4: GRU operands of (row b, unit u)
     const float e_d = row_ok ? p.d_hz[bt * W + u] : 0.f;
@@ -910,6 +906,16 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) observ
       sm.xg[0][b][j] = __float2bfloat16_rn(dz); sm.xg[1][b][j] = __float2bfloat16_rn(dr);
       sm.xg[2][b][j] = __float2bfloat16_rn(dc); sm.xg[3][b][j] = __float2bfloat16_rn(dcr);
       xchg_send(&sm.x.dg[0][0][0][0], &sm.xg[0][0][0], (uint32_t)sizeof(sm.xg), &sm.xbar[2], rank);   // my 4 blocks -> dg[rank] of every peer
+    }
+    float xx[2][EPL], mx_[2], rx[2];   // S5: LayerNorm inputs of rows warp, warp + 8, in flight while the gate gradients travel
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int rb = warp + r * kWarps;
+      const bool ok = rb < B;
+      const size_t rt = (size_t)(ok ? rb : 0) * T + t;
+      mx_[r] = ok ? p.x_mean[rt] : 0.f; rx[r] = ok ? p.x_rstd[rt] : 0.f;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) xx[r][i] = ok ? p.x_pre[rt * D + lane + 32 * i] : 0.f;
     }
     stamp(si + 5);
     xbar_wait(&sm.xbar[2], par);
