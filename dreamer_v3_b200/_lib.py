@@ -73,6 +73,7 @@ SIGNATURES = {
     "dv3_op_ln_silu_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I, _P]),
     "dv3_op_to_bf16": (_I, [_P, _I, _P, _I, _I64, _I, _P]),
     "dv3_op_gemm_bf16": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _F, _P]),
+    "dv3_op_gemm_bf16_small": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _F, _P]),
     "dv3_op_gemm_bf16_wgrad": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _F, _P]),
     "dv3_op_ln_silu": (_I, [_P, _P, _P, _P, _I64, _I, _P]),
 }

@@ -273,6 +273,14 @@ int dv3_op_gemm_bf16(const void* Ah, int ldah, const void* Bh, int ldbh, float* 
   if (!dv3::gemm_tma(S(stream), g)) return -2;
   return op_done();
 }
+int dv3_op_gemm_bf16_small(const void* Ah, int ldah, const void* Bh, int ldbh, float* C, int ldc, int M, int N, int K,
+                           const float* bias, float beta, void* stream) {
+  dv3::GemmArgs g{nullptr, 0, 0, nullptr, 0, 1, C, ldc, M, N, K, bias, beta};
+  g.Bh = Bh; g.ldbh = ldbh; g.Ah = Ah; g.ldah = ldah;
+  if (!dv3::gemm_small_eligible(g)) return -1;
+  if (!dv3::gemm_small(S(stream), g)) return -2;
+  return op_done();
+}
 int dv3_op_gemm_bf16_wgrad(const void* Xh, int ldx, const void* dYh, int ldy, float* C, int ldc, int M, int N, int K, float beta,
                            void* stream) {
   dv3::GemmArgs g{nullptr, 0, 1, nullptr, 0, 0, C, ldc, M, N, K, nullptr, beta};

@@ -68,6 +68,10 @@ bool gemv16_eligible(const GemmArgs& g);
 void gemv16(cudaStream_t s, const GemmArgs& g);
 void gemm_tc(cudaStream_t s, const GemmArgs& g);  // bf16 tcgen05 / TMEM path
 bool gemm_tma_eligible(const GemmArgs& g);
+// small-shape bf16 contraction on mma.sync (dv3_gemm_small.cu): both bf16 operand copies present, <= 1.4 GFLOP
+bool gemm_small_eligible(const GemmArgs& g);
+bool gemm_small_preferred(const GemmArgs& g);   // eligible and measured faster than the TMA kernel as a graph node
+bool gemm_small(cudaStream_t s, const GemmArgs& g);
 bool gemm_tma(cudaStream_t s, const GemmArgs& g);  // both operands bf16 K-major in global memory: TMA + tcgen05
 void to_bf16(cudaStream_t s, const float* src, int lds, void* dst, int ldd, long long rows, int cols);
 // bf16 shadows of weight matrices: out_t[c*rows + r] = bf16(in[r*cols + c]) (transposed), out_n = bf16(in) (plain)

@@ -331,6 +331,7 @@ bool pdl_enabled() {
 bool gemm_uses_tma(const GemmArgs& g, int mode) {
   if (!(g.M > 0 && g.N > 0 && g.K > 0) || mode != 1) return false;
   if (gemv16_eligible(g) || skinny_shape(g)) return false;
+  if (gemm_tc_eligible(g) && gemm_small_preferred(g)) return true;   // (reads the bf16 copies only, like the TMA kernel)
   return gemm_tma_eligible(g) && gemm_tc_eligible(g);
 }
 
@@ -343,6 +344,8 @@ void gemm_dispatch(cudaStream_t s, const GemmArgs& g, int mode) {
     gemm_f32(s, g);   // degenerate shapes: skinny kernels, exact fp32 in every mode
     return;
   }
+  // small contractions on a dependency chain (the per-step products of the XS dream): the fixed cost of the TMA kernel is their cost
+  if (mode == 1 && g.M > 0 && g.N > 0 && g.K > 0 && gemm_tc_eligible(g) && gemm_small_preferred(g) && gemm_small(s, g)) return;
   if (mode >= 1 && g.M > 0 && g.N > 0 && g.K > 0 && gemm_tma_eligible(g) && (mode == 2 || gemm_tc_eligible(g)) && gemm_tma(s, g)) return;
   if (mode == 1 && g.M > 0 && g.N > 0 && g.K > 0 && gemm_tc_eligible(g)) gemm_tc(s, g);
   else if (mode == 2 && g.M > 0 && g.N > 0 && g.K > 0) gemm_tc(s, g);  // forced (tests)

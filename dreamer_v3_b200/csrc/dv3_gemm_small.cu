@@ -152,15 +152,22 @@ cudaError_t launch_small(cudaStream_t s, const SmallArgs& a) {
 
 }  // namespace
 
-// Both operands exist in bf16 (K-major) and the whole contraction is small enough that the fixed cost of the TMA kernel would
-// dominate it (<= 1.4 GFLOP: the per-step contractions of the XS dream; the 16384-row head contractions stay on the TMA kernel)
+// What the kernel can run: both operands in bf16 (K-major), M in [64, 4096], <= 1.4 GFLOP
 bool gemm_small_eligible(const GemmArgs& g) {
-  static const bool off = std::getenv("DV3_NO_GEMM_SMALL") != nullptr;
-  if (off || g.ta || g.Ah == nullptr || g.Bh == nullptr) return false;
+  if (g.ta || g.Ah == nullptr || g.Bh == nullptr) return false;
   if (g.M < 64 || g.M > 4096 || g.N < 16 || g.K < 32) return false;
   if ((long long)g.M * g.N * g.K > 1024LL * 1024 * 1280) return false;
   return g.K % 8 == 0 && g.ldah % 8 == 0 && g.ldbh % 8 == 0 && (uintptr_t)g.Ah % 16 == 0 && (uintptr_t)g.Bh % 16 == 0 && g.ldc % 2 == 0 &&
          (uintptr_t)g.C % 8 == 0;
+}
+
+// Where it is the faster of the two bf16 kernels as a node of a replayed graph (tools/gemm_small_probe.py, us per dependent
+// launch, TMA kernel vs this one): [1024 x 256] x [256 x 256] 4.7 vs 3.2, [2048 x 256] x [256 x 256] 4.9 vs 4.2, 512^3 6.1 vs 4.8 -
+// but 5.0 vs 5.4 at N = 768, 6.4 vs 7.7 at K = 1024 (the TMA kernel splits K over the idle SMs), and accumulating into C costs this
+// kernel a dependent read (4.7 vs 5.0): narrow outputs, short K, plain stores only.
+bool gemm_small_preferred(const GemmArgs& g) {
+  static const bool off = std::getenv("DV3_NO_GEMM_SMALL") != nullptr;
+  return !off && gemm_small_eligible(g) && g.beta == 0.f && g.N <= 512 && g.K <= 512 && (long long)g.M * g.N <= 1024LL * 512;
 }
 
 bool gemm_small(cudaStream_t s, const GemmArgs& g) {

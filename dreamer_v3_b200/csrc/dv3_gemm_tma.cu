@@ -346,7 +346,7 @@ bool launch_tma(cudaStream_t s, const GemmArgs& g) {
   a.tiles_n = cdiv(g.N, BN);
   a.tiles = a.tiles_n * cdiv(g.M, BM);
   int splits = 1;
-  if (a.tiles <= 48 && g.K >= 16 * BK) {
+  if (a.tiles <= 48 && g.K >= 12 * BK) {   // (K = 768, the GRU backward products of the XS dream: 7.3 us unsplit as a graph node, ~5 split)
     splits = min(148 / a.tiles, g.K / (4 * BK));
     splits = max(1, min(splits, 32));
   }

@@ -134,9 +134,10 @@ def to_bf16(x):
     return out
 
 
-def gemm_bf16(A16, W, bias=None, C_=None, beta=0.0):
+def gemm_bf16(A16, W, bias=None, C_=None, beta=0.0, small=False):
     """C = A16 W with A16 [M, K] bf16 (as written by the producer kernels in tensor-core mode) and W [K, N] fp32 whose
-    bf16 K-major shadow is built here; `run` launches the TMA-fed tcgen05 kernel only."""
+    bf16 K-major shadow is built here; `run` launches the TMA-fed tcgen05 kernel only (small=True: the small-shape
+    mma.sync kernel of the dream rollout's per-step contractions)."""
     assert A16.dtype == torch.bfloat16 and A16.dim() == 2 and A16.stride(1) == 1
     Wh = W.t().contiguous().to(torch.bfloat16)  # [N, K]
     M, K = A16.shape
@@ -146,8 +147,9 @@ def gemm_bf16(A16, W, bias=None, C_=None, beta=0.0):
         C_ = torch.zeros((M, N), dtype=torch.float32, device=A16.device)
 
     def run():
-        _ok(_lib.load().dv3_op_gemm_bf16(_p(A16), A16.stride(0), _p(Wh), K, _p(C_), C_.stride(0), M, N, K, _p(bias), beta,
-                                         _s()), "dv3_op_gemm_bf16")
+        fn = _lib.load().dv3_op_gemm_bf16_small if small else _lib.load().dv3_op_gemm_bf16
+        _ok(fn(_p(A16), A16.stride(0), _p(Wh), K, _p(C_), C_.stride(0), M, N, K, _p(bias), beta, _s()),
+            "dv3_op_gemm_bf16_small" if small else "dv3_op_gemm_bf16")
         return C_
     run.keepalive = Wh
     return run

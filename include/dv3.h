@@ -210,6 +210,11 @@ int dv3_op_ln_silu_bwd(const float* dy, const float* x, const float* mean, const
 int dv3_op_to_bf16(const float* src, int lds, void* dst, int ldd, int64_t rows, int cols, void* stream);
 int dv3_op_gemm_bf16(const void* Ah, int ldah, const void* Bh, int ldbh, float* C, int ldc, int M, int N, int K,
                      const float* bias, float beta, void* stream);
+/* the same contraction on the small-shape kernel (mma.sync tiles, no TMA / TMEM set-up) the engine uses for the per-step products
+ * of the XS dream rollout (models/dreamer_model.py:189-208), where the launch-to-result latency is the cost; -1: not eligible
+ * (M in [64, 4096], M N K <= 1024 x 1024 x 1280, K % 8 == 0) */
+int dv3_op_gemm_bf16_small(const void* Ah, int ldah, const void* Bh, int ldbh, float* C, int ldc, int M, int N, int K,
+                           const float* bias, float beta, void* stream);
 /* weight-gradient contraction C[M,N] (+)= Xh[K,M]^T * dYh[K,N] on bf16 copies as stored (both operands MN-major) */
 int dv3_op_gemm_bf16_wgrad(const void* Xh, int ldx, const void* dYh, int ldy, float* C, int ldc, int M, int N, int K, float beta,
                            void* stream);

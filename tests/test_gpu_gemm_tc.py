@@ -96,6 +96,28 @@ def test_gemm_tma_variant(M, N, K):
     assert float((got - (want + C0.double())).abs().max()) <= tol, (M, N, K, "beta")
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 256, 256), (1024, 768, 256), (1024, 256, 1280), (1024, 1024, 256), (1024, 256, 1024),
+                                   (1024, 256, 768), (1000, 250, 264), (64, 16, 32), (130, 24, 72), (4096, 320, 1000)])
+def test_gemm_small_variant(M, N, K):
+    """Small-shape mma.sync kernel (csrc/dv3_gemm_small.cu): the per-step contractions of the XS dream rollout and its BPTT.
+    Ragged M / N / K (K % 8 == 0), bias, accumulate (also into a strided view, as the BPTT does into the [h, z] gradient)."""
+    from dreamer_v3_b200 import ops
+    g = torch.Generator().manual_seed(M * 3 + N * 5 + K)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(K, N, generator=g)
+    bias = torch.randn(N, generator=g)
+    A16 = ops.to_bf16(A.cuda())
+    want = A.bfloat16().double() @ W.bfloat16().double()
+    tol = 2e-5 * np.sqrt(K) * 8
+    got = ops.gemm_bf16(A16, W.cuda(), bias=bias.cuda(), small=True)().cpu().double()
+    assert float((got - (want + bias.double())).abs().max()) <= tol, (M, N, K)
+    wide = torch.randn(M, N + 6, generator=g).cuda()      # accumulate into columns [2, 2 + N) of a wider matrix
+    before = wide.clone()
+    ops.gemm_bf16(A16, W.cuda(), C_=wide[:, 2:2 + N], beta=1.0, small=True)()
+    assert float((wide[:, 2:2 + N].cpu().double() - (want + before[:, 2:2 + N].cpu().double())).abs().max()) <= tol, (M, N, K, "beta")
+    assert torch.equal(wide[:, :2], before[:, :2]) and torch.equal(wide[:, 2 + N:], before[:, 2 + N:])
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 64, 512), (1280, 256, 15360), (256, 256, 16384), (1000, 248, 1000), (64, 768, 1024),
                                    (1280, 256, 1024), (520, 72, 4104)])
 def test_gemm_tma_wgrad_variant(M, N, K):

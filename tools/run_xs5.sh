@@ -1,0 +1,7 @@
+timeout 600 python -m pytest tests/test_gpu_gemm_tc.py -q -m gpu --timeout 300 -k "small or tma" 2>&1 | tail -8
+timeout 900 python -m pytest tests/test_gpu_configs.py tests/test_gpu_engine.py -q -m gpu --timeout 300 -k "c1 or c2 or cluster or bf16" 2>&1 | tail -15 > gpurun_out/r2_xs5_tests.log; tail -3 gpurun_out/r2_xs5_tests.log
+timeout 300 python tools/graph_split.py c2 15 5 2>&1 | tail -2
+timeout 300 python tools/graph_split.py c1 15 5 2>&1 | tail -2
+for w in c1 c2; do timeout 300 python bench.py --workload $w --no-per-config --no-cpu --no-fp32-line --steps 20 2>gpurun_out/r2_xs_$w.err > gpurun_out/r2_xs_$w.json; python -c "
+import json,sys
+d=json.loads(open('gpurun_out/r2_xs_$w.json').read().strip().splitlines()[-1]); print(d['config']['id'], round(d['value'],2), round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value'],1), 'scan fwd/bwd us', round(d['scan_step_latency_us'],1), round(d['scan_bwd_step_latency_us'],1))"; tail -2 gpurun_out/r2_xs_$w.err; done
