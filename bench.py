@@ -366,9 +366,16 @@ def scan_roofline(cfg, us_fwd, us_bwd, pk, mode):
            "us_per_step": us_fwd, "bwd_us_per_step": us_bwd, "peak": pk["hbm"], "unit": "GB/s", "peak_source": pk["src"],
            "traffic": SCAN_TRAFFIC_PER_STEP.get((size, "fwd")), "bwd_traffic": SCAN_TRAFFIC_PER_STEP.get((size, "bwd"))}
     if cfg.G <= 256:
-        out.update({"bound": "latency", "note": "weights resident in the 16-CTA cluster's shared memory for all T steps (no weight "
-                    "bytes from HBM / L2 per step): 4 cluster barriers + 4 dependent 16-row contraction stages per step",
-                    "achieved": None, "frac": None})
+        if mode == 1:
+            out["kernel"] = "observe_scan_cluster_kernel<true> / observe_scan_bwd_cluster_kernel (bf16 weights resident, mma.sync)"
+            out["weight_dtype"] = "bf16 (resident in shared memory)"
+            note = ("weights resident in the 16-CTA cluster's shared memory in bf16 for all T steps (no weight bytes from HBM / L2 per "
+                    "step; the one-hot row gather of W_pre included): per step 4 dependent 16-row mma.sync stages, each followed by a "
+                    "bulk-copy exchange through distributed shared memory signalled on the receiver's mbarrier (no cluster barrier)")
+        else:
+            note = ("weights resident in the 16-CTA cluster's shared memory for all T steps (no weight bytes from HBM / L2 per step): "
+                    "4 dependent 16-row contraction stages + exchanges per step (backward: two-stage grid-wide kernel)")
+        out.update({"bound": "latency", "note": note, "achieved": None, "frac": None})
     else:
         gbs = fwd_bytes / (us_fwd * 1e-6) / 1e9 if us_fwd > 0 else None
         gbs_b = bwd_bytes / (us_bwd * 1e-6) / 1e9 if us_bwd > 0 else None

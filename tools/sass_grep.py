@@ -25,12 +25,13 @@ for line in sass.splitlines():
     for k in MN:
         if re.search(r"\b" + re.escape(k), line):
             counts[cur][k.rstrip(".")] += 1
-cols = ["UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UCGABAR", "HMMA", "REDG"]
+cols = ["UTCHMMA", "LDTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UBLKCP", "UCGABAR", "HMMA", "REDG"]
 print("# cuobjdump -sass dreamer_v3_b200/libdv3.so: occurrences per kernel (tcgen05.mma = UTCHMMA, tcgen05.ld = LDTM, TMA = UTMALDG /")
-print("# UTMASTG / UTMAREDG, cluster barrier = UCGABAR, legacy mma.sync = HMMA, red.global = REDG); kernels without any of them omitted")
+print("# UTMASTG / UTMAREDG, bulk copy (shared::cta -> shared::cluster exchange) = UBLKCP, cluster barrier = UCGABAR, mma.sync = HMMA,")
+print("# red.global = REDG); kernels without any of them omitted")
 print(f"{'kernel':90s} " + " ".join(f"{c:>8s}" for c in cols))
 for k, c in counts.items():
-    if not any(c[x] for x in cols[:7]):
+    if not any(c[x] for x in cols[:8]):
         continue
     print(f"{k[:90]:90s} " + " ".join(f"{c[x]:8d}" for x in cols))
-print(f"# {len(counts)} kernels in the library; {sum(1 for c in counts.values() if c['UTCHMMA'])} issue tcgen05.mma; {sum(1 for c in counts.values() if c['HMMA'])} use legacy HMMA")
+print(f"# {len(counts)} kernels in the library; {sum(1 for c in counts.values() if c['UTCHMMA'])} issue tcgen05.mma; {sum(1 for c in counts.values() if c['HMMA'])} use mma.sync (HMMA)")
