@@ -94,11 +94,16 @@ void Engine::dream_action(int i) {
 }
 
 // The H dreamed steps as ONE persistent kernel (dv3_dream_tc.cu): tensor-core mode, XS / S layer sizes, actor-sampled actions.
-bool Engine::dream_rollout_tc(cudaStream_t s) {
-  // opt-in (DV3_DREAM_TC=1): measured on B200 it runs a dreamed step in 65 us at XS - the same as the per-kernel path inside the
-  // replayed CUDA graph (7 - 8 grid-wide stages of 6 - 9 us vs ~17 kernel nodes): correct (parity-tested), not faster
+bool Engine::dream_rollout_tc(cudaStream_t s, int start_from_observe) {
+  // Two persistent rollout kernels, both opt-in: measured on B200 neither beats the per-kernel path inside the replayed CUDA graph
+  // (XS, us per dreamed step: per-kernel path ~64; DV3_DREAM_TC=1, grid-wide stage kernel of dv3_dream_tc.cu: 65 - 7 - 8 grid-wide
+  // stages of 6 - 9 us each; DV3_DREAM_RR=1, row-resident kernel of dv3_dream_rr.cu: 52 (Discrete) - 61 (Box) - 64 CTAs x 1.6 MB of
+  // weight tiles + 0.8 MB of gathered rows per step is 150 MB per step out of L2, and with 8 warps per SM the epilogues are latency
+  // chains). Both are parity-tested against the oracle.
   const bool opt_in = std::getenv("DV3_DREAM_TC") != nullptr;
-  if (!opt_in || dream_tc_ctas <= 0 || dream_action_mode != 0 || !use_persistent || dr_hz16 == nullptr) return false;
+  const bool rr = !opt_in && start_from_observe && std::getenv("DV3_DREAM_RR") != nullptr && dream_rr_supported(N, G, D, Z, Zc, Zk, A, L);
+  if (!(opt_in || rr) || dream_action_mode != 0 || !use_persistent || dr_hz16 == nullptr) return false;
+  if (opt_in && dream_tc_ctas <= 0) return false;
   const LnLayer& Wx = pre_mlp.layers[0];
   const LnLayer& Wd = dyn_mlp.layers[0];
   DreamTcArgs a{};
@@ -133,6 +138,18 @@ bool Engine::dream_rollout_tc(cudaStream_t s) {
   a.prior_logits = dr_prior_logits; a.prior_probs = dr_prior_probs; a.z_idx = dr_z_idx;
   a.bar = scan_bar + 48;
   a.prof = std::getenv("DV3_SCAN_STAMPS") ? scan_stamps + 2048 : nullptr;
+  if (rr) {
+    DreamRrExtra x{};
+    x.Wn_pre = shadow_n(Wx.w, &x.ld_n_pre);
+    x.Wn_act[0] = shadow_n(actor_mlp.layers[0].w, &x.ld_n_act[0]);
+    x.Wn_act[1] = discrete ? x.Wn_act[0] : shadow_n(actor_std_mlp.layers[0].w, &x.ld_n_act[1]);
+    if (discrete) x.ld_n_act[1] = x.ld_n_act[0];
+    x.z0_idx = z_idx;
+    if (!x.Wn_pre || !x.Wn_act[0] || !x.Wn_act[1] || x.ld_n_pre % 8 != 0 || x.ld_n_act[0] % 8 != 0 || x.ld_n_act[1] % 8 != 0) return false;
+    const cudaError_t ce = launch_dream_rr(s, a, x);
+    if (ce != cudaSuccess) { err = std::string("dream rollout (row-resident) launch: ") + cudaGetErrorString(ce); dream_rollout_failed = true; return false; }
+    return true;
+  }
   const cudaError_t ce = launch_dream_tc(s, a, dream_tc_ctas);
   if (ce != cudaSuccess) { err = std::string("dream rollout (tensor-core) launch: ") + cudaGetErrorString(ce); return false; }
   return true;
@@ -165,8 +182,11 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
     if (!discrete) cudaMemsetAsync(actor_std_act.pre[0], 0, (size_t)R * actor_std_mlp.layers[0].out * 4, s);
   }
   phase_mark("dream.begin");
-  if (dream_rollout_tc(s)) {
+  dream_rollout_failed = false;
+  if (dream_rollout_tc(s, start_from_observe)) {
     phase_mark("dream.rollout_tc");
+  } else if (dream_rollout_failed) {
+    return fail(err);   // a persistent rollout kernel that applies but cannot launch is an error, not a reason to fall back
   } else
   for (int i = 1; i <= H; ++i) {
     const size_t prev = (size_t)(i - 1) * N, curr = (size_t)i * N, st = (size_t)(i - 1) * N;  // st: per-step buffers

@@ -35,6 +35,16 @@ struct DreamTcArgs {
   unsigned long long* prof;   // optional per-CTA cycle totals [ctas][16] (profiling), may be null
 };
 
+// Row-resident rollout (dv3_dream_rr.cu): same arguments plus the plain bf16 shadows the one-hot row gathers read and the class
+// indices of the start states. XS layer sizes, one actor layer, dreams that start from the engine's own observe pass.
+struct DreamRrExtra {
+  const void* Wn_pre; int ld_n_pre;          // plain shadow of W_pre [Z + A, D]
+  const void* Wn_act[2]; int ld_n_act[2];    // plain shadows of the first layer of the actor / its std net [G + Z, D]
+  const int32_t* z0_idx;                     // [N, Zc]
+};
+bool dream_rr_supported(int N, int G, int D, int Z, int Zc, int Zk, int A, int L);
+cudaError_t launch_dream_rr(cudaStream_t s, const DreamTcArgs& a, const DreamRrExtra& x);
+
 bool dream_tc_supported(int N, int G, int D, int Z, int Zk, int A, int L);
 int dream_tc_max_ctas(int device);
 cudaError_t launch_dream_tc(cudaStream_t s, const DreamTcArgs& a, int ctas);

@@ -93,7 +93,8 @@ struct Engine {
   int scan_ctas = 0;          // > 0: persistent cooperative scan kernels are usable with this many CTAs
   int scan_tc_ctas = 0;       // > 0: the weight-streaming tensor-core scan (dv3_scan_tc.cu) is usable with this many CTAs
   int dream_tc_ctas = 0;      // > 0: the persistent imagination-rollout kernel (dv3_dream_tc.cu) is usable with this many CTAs
-  bool dream_rollout_tc(cudaStream_t s);   // runs the H dreamed steps on it; false: not applicable (caller takes the per-kernel path)
+  bool dream_rollout_tc(cudaStream_t s, int start_from_observe);
+  bool dream_rollout_failed = false;   // runs the H dreamed steps on it; false: not applicable (caller takes the per-kernel path)
   float* gx_acc = nullptr;    // [N, 3G] accumulator of u . K in that kernel
   const void* shadow_t(const float* w, int* ld) const;  // bf16 transposed shadow [cols, rows] of (a row sub-block of) a weight matrix
   const void* shadow_n(const float* w, int* ld) const;  // bf16 plain shadow [rows, cols] of (a row sub-block of) a weight matrix

@@ -207,9 +207,11 @@ class ParityRun:
             act_noise = (self.rng.random((H + 1, N), dtype=np.float32) if cfg.discrete
                          else self.rng.standard_normal((H + 1, N, cfg.A)).astype(np.float32))
             e.set_noise(u_dyn=u_dyn, act_noise=act_noise)
-            e.write("in.dream_h0", fwd["h_states_BxT"].to(torch.float32))
-            e.write("in.dream_z0", fwd["z_states_BxT"].reshape(N, -1).to(torch.float32))
-            e.dream_forward(start_from_observe=False)
+            # Dream from the engine's own observe buffers, the way a train update does (that is the entry the persistent rollout
+            # kernels take: they need the class indices of the start states, wm.z_indices), with the oracle's h written over the
+            # engine's so that both dream from identical start states (the z indices are already identical: forced draws).
+            e.write("wm.hz", torch.cat([fwd["h_states_BxT"].reshape(N, -1), fwd["z_states_BxT"].reshape(N, -1)], dim=1).to(torch.float32))
+            e.dream_forward(start_from_observe=True)
             zi = e.tensor("dream.z_indices").cpu().numpy().reshape(H, N, cfg.Zc)
             forced = {"u_dyn": list(zi), "continues": e.tensor("dream.continues").cpu().numpy().reshape(-1)}
             if cfg.discrete:

@@ -125,12 +125,14 @@ def test_config_parity_bf16(wid):
         run.close()
 
 
-@pytest.mark.parametrize("wid", ("c1", "c2", "c3"))
-def test_persistent_dream_kernel_opt_in(wid, monkeypatch):
-    """dv3_dream_tc.cu (DV3_DREAM_TC=1): the H dreamed steps as one persistent tcgen05 kernel (XS / S layer sizes). Not the default
-    path (measured: same speed as the per-kernel path inside the replayed graph), kept under the same parity bar."""
+@pytest.mark.parametrize("wid,switch", (("c1", "DV3_DREAM_TC"), ("c2", "DV3_DREAM_TC"), ("c3", "DV3_DREAM_TC"),
+                                        ("c1", "DV3_DREAM_RR"), ("c2", "DV3_DREAM_RR")))
+def test_persistent_dream_kernel_opt_in(wid, switch, monkeypatch):
+    """The H dreamed steps as one persistent kernel: dv3_dream_tc.cu (DV3_DREAM_TC=1; grid-wide tcgen05 stages, XS / S layer sizes)
+    and dv3_dream_rr.cu (DV3_DREAM_RR=1; row-resident, 16 dream rows per CTA from the start state to step H, XS). Not the default
+    path (measured: no faster than the per-kernel path inside the replayed graph), kept under the same parity bar."""
     from _parity import ParityRun
-    monkeypatch.setenv("DV3_DREAM_TC", "1")
+    monkeypatch.setenv(switch, "1")
     cfg = _cfg(wid, SHAPES_BF16[wid])
     run = ParityRun(cfg, steps=1, compute_mode=1, forced=True)
     try:
@@ -143,7 +145,7 @@ def test_persistent_dream_kernel_opt_in(wid, monkeypatch):
         assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:20]
     finally:
         run.close()
-    monkeypatch.delenv("DV3_DREAM_TC")
+    monkeypatch.delenv(switch)
     run2 = ParityRun(cfg, steps=1, compute_mode=1, forced=True)
     try:
         assert run2.engine.kernel_launch_count() > launches_tc   # the persistent kernel really replaced the per-step launches
