@@ -18,9 +18,12 @@
 // step and CTA out of L2): the producer runs ahead across layer and step boundaries, so the weight stream never waits for an
 // epilogue. Everything the heads, the losses and the BPTT read afterwards is written on the side in the layout of the per-op path.
 //
-// Measured (tools/dream_rr_prof.py, XS, us per dreamed step): gathers 6 - 9, weight-tile phases 25 - 28 (the same with 16 instead of 64
-// CTAs: bound by the mma.sync issue rate, 6144 HMMA per CTA and step, not by L2), epilogues 21 - 24 -> 52 (Discrete) / 61 (Box) in
-// total against ~64 on the per-kernel path inside the replayed graph: opt-in (DV3_DREAM_RR=1), parity-tested.
+// Measured (tools/dream_rr_prof.py, XS, us per dreamed step): gathers 6 - 9, weight-tile phases 25 - 28, epilogues 21 - 24 -> 52
+// (Discrete) / 61 (Box) in total against ~64 on the per-kernel path inside the replayed graph: opt-in (DV3_DREAM_RR=1), parity-tested.
+// The tile phases with the multiplications switched off: 21 us (the stream alone: 68 GB/s into one SM with 96 KB in flight; the same
+// with 16 instead of 64 CTAs, and the same with tile-major weights moved by one contiguous 32 KB bulk copy per tile); with the stream
+// switched off: 14.7 us (5632 HMMA). A CTA that owns its rows for a whole step ingests the step's 1.6 MB of weights whatever its row
+// count: ~30 us per step with the gathered rows is this design's floor.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
