@@ -101,7 +101,7 @@ bool Engine::dream_rollout_tc(cudaStream_t s, int start_from_observe) {
   // step's 1.6 MB of weights at 68 GB/s, 21 us, its 5632 HMMA take 14.7 us, and with 8 warps per SM the epilogues are latency
   // chains). Both are parity-tested against the oracle.
   const bool opt_in = std::getenv("DV3_DREAM_TC") != nullptr;
-  const bool rr = !opt_in && start_from_observe && std::getenv("DV3_DREAM_RR") != nullptr && dream_rr_supported(N, G, D, Z, Zc, Zk, A, L);
+  const bool rr = !opt_in && start_from_observe && std::getenv("DV3_DREAM_RR") != nullptr && std::getenv("DV3_DREAM_RR")[0] != 0 && dream_rr_supported(N, G, D, Z, Zc, Zk, A, L);
   if (!(opt_in || rr) || dream_action_mode != 0 || !use_persistent || dr_hz16 == nullptr) return false;
   if (opt_in && dream_tc_ctas <= 0) return false;
   const LnLayer& Wx = pre_mlp.layers[0];
