@@ -594,6 +594,13 @@ int Engine::init(const dv3_config* c) {
     scan_bwd_ctas = wb < max_b ? wb : max_b;
   }
   dream_tc_ctas = (cfg.compute_mode == 1 && !shadow_host.empty() && dream_tc_supported(N, G, D, Z, Zk, A, L)) ? dream_tc_max_ctas(cfg.device) : 0;
+  if (cfg.compute_mode == 1 && !shadow_host.empty() && std::getenv("DV3_NO_CONV_SCRATCH") == nullptr)
+    for (auto& p : conv_scratch) {   // (own allocations: the arena was sized by layout())
+      void* q = nullptr;
+      if (cudaMalloc(&q, kConvScratchElems * 2) != cudaSuccess) { cudaGetLastError(); break; }
+      allocations.push_back(q);
+      p = (unsigned short*)q;
+    }
   scan_tc_ctas = (cfg.compute_mode == 1 && gx_acc != nullptr && B <= 16 && !shadow_host.empty()) ? scan_tc_max_ctas(cfg.device) : 0;
   const float nanv[2] = {NAN, NAN};
   CK(cudaMemcpy(pct_ema, nanv, 8, cudaMemcpyHostToDevice));
@@ -734,9 +741,41 @@ void Engine::side_join() {
 }
 
 // ------------------------------------------------------------------------------------------ building blocks
+unsigned short* Engine::conv_scratch_for(cudaStream_t s) const {
+  for (int d = 0; d < kDepth; ++d)
+    for (int i = 0; i < kAux; ++i)
+      if (aux[d][i] != nullptr && s == aux[d][i]) return conv_scratch[1 + d * kAux + i];
+  if (side != nullptr && s == side) return conv_scratch[1 + kDepth * kAux];
+  return conv_scratch[0];
+}
+
 void Engine::mm(const float* A_, int lda, bool ta, const float* B_, int ldb, bool tb, float* C, int ldc, int M, int N_,
                 int K, const float* bias, float beta, const void* A16, const void* B16) {
-  gemm_dispatch(cur, mm_args(A_, lda, ta, B_, ldb, tb, C, ldc, M, N_, K, bias, beta, A16, B16), cfg.compute_mode);
+  GemmArgs g = mm_args(A_, lda, ta, B_, ldb, tb, C, ldc, M, N_, K, bias, beta, A16, B16);
+  // Large contraction that would miss the TMA-fed kernel only because an activation / gradient operand has no bf16 copy: make
+  // the copy in this stream's scratch (one extra pass over the operand) and take the TMA kernel.
+  unsigned short* sc = cfg.compute_mode == 1 ? conv_scratch_for(cur) : nullptr;
+  if (sc != nullptr && (long long)M * N_ * K >= (1LL << 28) && gemm_tc_eligible(g) && !gemv16_eligible(g) && !gemm_uses_tma(g, 1) &&
+      ldc % 4 == 0 && (uintptr_t)C % 16 == 0) {
+    const size_t half = kConvScratchElems / 2;
+    if (!ta && g.Ah == nullptr && g.Bh != nullptr && g.ldbh % 8 == 0 && (uintptr_t)g.Bh % 16 == 0 && M >= 128) {
+      const int ld = (K + 7) & ~7;
+      if ((size_t)M * ld <= kConvScratchElems) {
+        to_bf16(cur, A_, lda, sc, ld, M, K);
+        g.Ah = sc; g.ldah = ld;
+      }
+    } else if (ta && !tb && M >= 64 && K >= 512) {
+      const int lda16 = (M + 7) & ~7, ldb16 = (N_ + 7) & ~7;
+      const bool fits = (g.Ah != nullptr || (size_t)K * lda16 <= half) && (g.Bmn != nullptr || (size_t)K * ldb16 <= half);
+      const bool have_ok = (g.Ah == nullptr || (g.ldah % 8 == 0 && (uintptr_t)g.Ah % 16 == 0)) &&
+                           (g.Bmn == nullptr || (g.ldbmn % 8 == 0 && (uintptr_t)g.Bmn % 16 == 0));
+      if (fits && have_ok) {
+        if (g.Ah == nullptr) { to_bf16(cur, A_, lda, sc, lda16, K, M); g.Ah = sc; g.ldah = lda16; }
+        if (g.Bmn == nullptr) { to_bf16(cur, B_, ldb, sc + half, ldb16, K, N_); g.Bmn = sc + half; g.ldbmn = ldb16; }
+      }
+    }
+  }
+  gemm_dispatch(cur, g, cfg.compute_mode);
 }
 
 bool Engine::mm_tma(const float* A_, int lda, bool ta, const float* B_, int ldb, bool tb, float* C, int ldc, int M, int N_, int K,

@@ -94,7 +94,8 @@ struct Engine {
   int scan_tc_ctas = 0;       // > 0: the weight-streaming tensor-core scan (dv3_scan_tc.cu) is usable with this many CTAs
   int dream_tc_ctas = 0;      // > 0: the persistent imagination-rollout kernel (dv3_dream_tc.cu) is usable with this many CTAs
   bool dream_rollout_tc(cudaStream_t s, int start_from_observe);
-  bool dream_rollout_failed = false;   // runs the H dreamed steps on it; false: not applicable (caller takes the per-kernel path)
+  bool dream_rollout_failed = false;
+  // runs the H dreamed steps on it; false: not applicable (caller takes the per-kernel path)
   float* gx_acc = nullptr;    // [N, 3G] accumulator of u . K in that kernel
   const void* shadow_t(const float* w, int* ld) const;  // bf16 transposed shadow [cols, rows] of (a row sub-block of) a weight matrix
   const void* shadow_n(const float* w, int* ld) const;  // bf16 plain shadow [rows, cols] of (a row sub-block of) a weight matrix
@@ -156,7 +157,12 @@ struct Engine {
   static constexpr int kDepth = 2;   // run_branches may nest once (a branch that forks again uses its own stream set)
   cudaStream_t aux[kDepth][kAux] = {};
   cudaEvent_t ev_fork[kDepth] = {}, ev_join[kDepth][kAux] = {};
-  int branch_depth = 0;
+  // bf16 conversion scratch, one per stream the engine launches on (main, kDepth x kAux branch streams, side): a large contraction
+  // whose activation / gradient operand has no bf16 copy gets one made here first and then runs on the TMA-fed kernel instead of
+  // the kernel that converts fp32 tiles inside the CTA (2 - 4x slower at these sizes)
+  static constexpr size_t kConvScratchElems = 32u << 20;   // bf16 elements per stream (64 MB)
+  unsigned short* conv_scratch[2 + kDepth * kAux] = {};
+  unsigned short* conv_scratch_for(cudaStream_t s) const;   int branch_depth = 0;
   bool use_branches = true;
   // runs branches[0] on the current stream and the others concurrently on auxiliary streams, then joins them
   void run_branches(const std::vector<std::function<void()>>& branches);

@@ -3,6 +3,9 @@
 // the operand is 16-byte aligned, split-K with fp32 atomics when the tile grid is smaller than the GPU.
 #include <cstdlib>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "dv3_common.h"
 #include "dv3_device.cuh"
 
@@ -347,7 +350,14 @@ void gemm_dispatch(cudaStream_t s, const GemmArgs& g, int mode) {
   // small contractions on a dependency chain (the per-step products of the XS dream): the fixed cost of the TMA kernel is their cost
   if (mode == 1 && g.M > 0 && g.N > 0 && g.K > 0 && gemm_tc_eligible(g) && gemm_small_preferred(g) && gemm_small(s, g)) return;
   if (mode >= 1 && g.M > 0 && g.N > 0 && g.K > 0 && gemm_tma_eligible(g) && (mode == 2 || gemm_tc_eligible(g)) && gemm_tma(s, g)) return;
-  if (mode == 1 && g.M > 0 && g.N > 0 && g.K > 0 && gemm_tc_eligible(g)) gemm_tc(s, g);
+  if (mode == 1 && g.M > 0 && g.N > 0 && g.K > 0 && gemm_tc_eligible(g)) {
+    static const bool trace = std::getenv("DV3_TRACE_FALLBACK") != nullptr;   // which contractions miss the TMA kernel, and why
+    if (trace)
+      fprintf(stderr, "gemm_tc fallback: M %d N %d K %d ta %d tb %d lda %d ldb %d ldc %d beta %g Ah %d(ld %d) Bh %d(ld %d) Bmn %d(ld %d) C%%16 %d\n", g.M, g.N, g.K,
+              g.ta, g.tb, g.lda, g.ldb, g.ldc, (double)g.beta, g.Ah != nullptr, g.ldah, g.Bh != nullptr, g.ldbh, g.Bmn != nullptr, g.ldbmn,
+              (int)((uintptr_t)g.C % 16));
+    gemm_tc(s, g);
+  }
   else if (mode == 2 && g.M > 0 && g.N > 0 && g.K > 0) gemm_tc(s, g);  // forced (tests)
   else gemm_f32(s, g);
 }
