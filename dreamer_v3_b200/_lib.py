@@ -11,8 +11,9 @@ ABI_VERSION = 1
 class Dv3Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "abi_version", "G", "D", "L", "cnn_mult", "Zc", "Zk", "A", "discrete", "image_obs", "obs_dim",
-        "img_hw", "img_c", "B", "T", "H", "symlog_obs", "compute_mode", "world_size", "rank", "device")]
-    _fields_ += [("reserved", C.c_int32 * 8)]
+        "img_hw", "img_c", "B", "T", "H", "symlog_obs", "compute_mode", "world_size", "rank", "device",
+        "num_curiosity_nets")]
+    _fields_ += [("intrinsic_rewards_scale", C.c_float), ("reserved", C.c_int32 * 6)]
 
 
 class Dv3TensorDesc(C.Structure):
@@ -24,7 +25,9 @@ class Dv3Hparams(C.Structure):
     _fields_ = [(n, C.c_float) for n in (
         "gamma", "lambda_", "entropy_scale", "return_normalization_decay", "wm_grad_clip", "actor_grad_clip",
         "critic_grad_clip", "wm_lr", "wm_eps", "ac_lr", "ac_eps", "critic_ema_decay")]
-    _fields_ += [("train_actor", C.c_int32), ("critic_lr", C.c_float), ("critic_eps", C.c_float), ("reserved", C.c_int32 * 5)]
+    _fields_ += [("train_actor", C.c_int32), ("critic_lr", C.c_float), ("critic_eps", C.c_float)]
+    _fields_ += [(n, C.c_float) for n in ("disagree_grad_clip", "disagree_lr", "disagree_eps")]
+    _fields_ += [("reserved", C.c_int32 * 2)]
 
 
 # name -> (restype, argtypes); mirrors include/dv3.h one to one (tests/test_capi_symbols.py checks it)
@@ -54,6 +57,7 @@ SIGNATURES = {
     "dv3_replay_plan": (_I64, [_I, _I, _I, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P]),
     "dv3_replay_gather": (_I, [_P, _I, _I, _I64, _P, _I, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P]),
     "dv3_ac_loss_backward": (_I, [_P, C.POINTER(Dv3Hparams), _I, _P]),
+    "dv3_disagree_loss_backward": (_I, [_P, _P]),
     "dv3_critic_init_ema": (_I, [_P, _P]),
     "dv3_critic_update_ema": (_I, [_P, _F, _P]),
     "dv3_train_actor_critic_step": (_I, [_P, C.POINTER(Dv3Hparams), _U64, _I, _P]),

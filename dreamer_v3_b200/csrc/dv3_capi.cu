@@ -60,6 +60,7 @@ void dv3_default_hparams(dv3_hparams* hp) {
   hp->wm_grad_clip = 1000.f; hp->actor_grad_clip = 100.f; hp->critic_grad_clip = 100.f;
   hp->wm_lr = 1e-4f; hp->wm_eps = 1e-8f; hp->ac_lr = 3e-5f; hp->ac_eps = 1e-5f;
   hp->critic_ema_decay = 0.98f; hp->train_actor = 1;
+  hp->disagree_grad_clip = 100.f; hp->disagree_lr = 1e-4f; hp->disagree_eps = 1e-5f;   // run_experiment.py:252, disagree_networks.py:43
 }
 
 int dv3_sync(dv3_engine* h, void* stream) {
@@ -122,7 +123,8 @@ int dv3_read_tensor(dv3_engine* h, const char* name, void* dst, size_t nbytes, i
 int dv3_group_buffer(const dv3_engine* h, int group, int kind, void** ptr, int64_t* numel) {
   const Engine& e = h->e;
   if (group == 4 && kind == 1) { *ptr = e.grads[1]; *numel = e.grads_ac_numel; return 0; }   // actor + critic gradients, one span
-  if (group < 0 || group > 3 || kind < 0 || kind > 3 || (group == 3 && kind != 0)) return -1;
+  if (group == Engine::kDisagree && e.numel[group] == 0) return -1;   // curiosity is off
+  if (group < 0 || (group > 3 && group != Engine::kDisagree) || kind < 0 || kind > 3 || (group == 3 && kind != 0)) return -1;
   float* p = kind == 0 ? e.params[group] : kind == 1 ? e.grads[group] : kind == 2 ? e.adam_m[group] : e.adam_v[group];
   *ptr = p; *numel = e.numel[group];
   return 0;
@@ -165,6 +167,10 @@ int dv3_dream_forward_actions(dv3_engine* h, float gamma, int start_from_observe
 }
 int dv3_ac_loss_backward(dv3_engine* h, const dv3_hparams* hp, int phase, void* stream) {
   int rc = h->e.ac_loss_backward(hp, phase, S(stream));
+  return rc ? rc : check_async(h->e);
+}
+int dv3_disagree_loss_backward(dv3_engine* h, void* stream) {
+  int rc = h->e.disagree_loss_backward(S(stream));
   return rc ? rc : check_async(h->e);
 }
 int dv3_critic_init_ema(dv3_engine* h, void* stream) {

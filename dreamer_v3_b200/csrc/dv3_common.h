@@ -181,6 +181,7 @@ struct AcArgs {
   const float* is_terminated;  // [N]
   float* r; float* c; float* w; float* v;  // [(H+1)N] real-space outputs
   float* targets;          // [H*N]
+  const float* r_intr;     // nullable [(H+1)N]: intrinsic (curiosity) rewards, rows of t >= 1 added to r inside the lambda-returns only
 };
 void ac_value_targets(cudaStream_t s, const AcArgs& a);
 void value_targets_raw(cudaStream_t s, const float* r, const float* c, const float* v, int H, int N, float gamma,
@@ -240,6 +241,18 @@ struct ActorStepArgs {
 };
 bool actor_step_supported(int D, int A);
 cudaError_t actor_step(cudaStream_t s, const ActorStepArgs& a);
+
+// ---- curiosity (dv3_disagree.cu): models/disagree_networks.py:47-76, losses/disagree_loss.py:11-41 ------------------------
+// out[r] = mean over the Z probabilities of the population stddev over the nets; probs [nets][rows, Z] (net_stride elements apart)
+void disagree_std_rows(cudaStream_t s, const float* probs, size_t net_stride, int nets, long long rows, int Z, float* out);
+// ri = (std_rows - mean(std_rows)) * scale; scalars[1] = mean of ri[first_row:]
+void disagree_intrinsic(cudaStream_t s, const float* std_rows, long long rows, long long first_row, float scale, float* ri,
+                        float* scalars);
+// one net: mse[r] = |p[r] - z_next[r]|^2, dprobs = 2 (p - z_next) inv_count
+void disagree_loss_rows(cudaStream_t s, const float* probs, const float* z_next, int ldz, long long rows, int Z, float inv_count,
+                        float* dprobs, float* mse);
+// scalars[0] = sum(mse[0:n]) / rows
+void disagree_loss_total(cudaStream_t s, const float* mse, long long n, long long rows, float* scalars);
 
 // ---- optimizer (dv3_optim.cu) ---------------------------------------------------------------------------
 // stats[0] = sum of squares (as double bits in 2 floats? no: separate double*), see implementation.

@@ -245,9 +245,14 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
         else dream_action(H);
       }});
   phase_mark("dream.heads");
+  if (!dis.empty()) {   // dreamer_model.py:226-240: needs the actions of all H + 1 dreamed states
+    disagree_forward();
+    phase_mark("dream.disagree");
+  }
   // real-space rewards / continues / values, loss weights (dreamer_model.py:219-280) and lambda-returns
   AcArgs a{};
   a.H = H; a.N = N; a.A = A; a.discrete = discrete; a.gamma = gamma; a.lambda_ = last_lambda;
+  a.r_intr = dis.empty() ? nullptr : dis_ri;
   a.rew_E = dr_rew_E; a.cont_logit = dr_cont_logit; a.v_E = v_E; a.ema_E = ema_E; a.is_terminated = in_is_term;
   a.r = ac_r; a.c = ac_c; a.w = ac_w; a.v = ac_v; a.targets = ac_targets;
   ac_value_targets(s, a);
@@ -264,6 +269,7 @@ int Engine::ac_loss_backward(const dv3_hparams* hp, int phase, cudaStream_t s) {
   a.gamma = hp->gamma; a.lambda_ = hp->lambda_; a.entropy_scale = hp->entropy_scale; a.decay = hp->return_normalization_decay;
   last_lambda = hp->lambda_;
   a.inv_count = inv_world / (float)HN;
+  a.r_intr = dis.empty() ? nullptr : dis_ri;
   a.rew_E = dr_rew_E; a.cont_logit = dr_cont_logit; a.v_E = v_E; a.ema_E = ema_E; a.is_terminated = in_is_term;
   a.r = ac_r; a.c = ac_c; a.w = ac_w; a.v = ac_v; a.targets = ac_targets;
   if (phase & 1) {
@@ -376,11 +382,56 @@ void Engine::actor_backward(const dv3_hparams* hp, const AcArgs& a) {
   }
 }
 
+// Curiosity forward (models/disagree_networks.py:47-95): every net = MLP(L) -> RepresentationLayer probabilities on
+// stop_gradient([h, z, a]) of all (H+1) N dreamed rows; intrinsic reward = mean over the Zc Zk probabilities of their
+// population stddev over the nets, centred over all rows, times the scale (row block 0 is computed like the reference does
+// and dropped by the consumers: rewards_intrinsic_t1_to_H_B, dreamer_model.py:236-238).
+void Engine::disagree_forward() {
+  cudaStream_t s = cur;
+  const int W = G + Z, Nd = (int)dis.size();
+  copy_2d(s, dr_hz, W, dis_in, dis_ld, R, W);
+  copy_2d(s, dr_act, A, dis_in + W, dis_ld, R, A);
+  for (int n = 0; n < Nd; ++n) {
+    DisagreeNet& d = dis[n];
+    mlp_fwd(d.mlp, d.act, dis_in, dis_ld, R);
+    mm(d.act.act.back(), D, false, d.repr.w, Z, false, d.logits, Z, R, Z, D, d.repr.bias, 0.f, d.act.act16.empty() ? nullptr : d.act.act16.back());
+    repr_fwd(s, d.logits, Z, d.probs, Z, nullptr, 0, nullptr, 0, nullptr, 0, R, Zc, Zk, 0);
+  }
+  disagree_std_rows(s, dis_probs, (size_t)R * Z, Nd, R, Z, dis_std);
+  disagree_intrinsic(s, dis_std, R, N, cfg.intrinsic_rewards_scale, dis_ri, dis_scalars);
+}
+
+// disagree_loss (losses/disagree_loss.py:11-41) and its gradients (train_one_step.py:209-212): per net the squared error of
+// the probabilities predicted at t < H against the dreamed prior z of t + 1, mean over [H, N], summed over the nets; the
+// inputs are stop-gradient'ed, so only weight gradients. Time-major rows: t < H are the first H N rows, t + 1 is N rows on.
+int Engine::disagree_loss_backward(cudaStream_t s) {
+  if (dis.empty()) return fail("disagree_loss_backward: the engine was created without curiosity nets");
+  cur = s;
+  const int W = G + Z, Nd = (int)dis.size();
+  const long long HN = (long long)H * N;
+  cudaMemsetAsync(grads[kDisagree], 0, (size_t)numel[kDisagree] * 4, s);
+  for (int n = 0; n < Nd; ++n) {
+    DisagreeNet& d = dis[n];
+    disagree_loss_rows(s, d.probs, dr_hz + (size_t)N * W + G, W, HN, Z, 1.0f / (float)HN, dis_dprobs, dis_mse + (size_t)n * HN);
+    repr_bwd(s, d.logits, Z, nullptr, 0, dis_dprobs, Z, dis_dlogits, Z, (int)HN, Zc, Zk);
+    dense_bwd(d.repr, d.act.act.back(), D, dis_dlogits, Z, dis_s0, D, 0.f, true, HN);
+    mlp_bwd(d.mlp, d.act, dis_in, dis_ld, dis_s0, dis_s1, nullptr, 0, true, HN);
+  }
+  disagree_loss_total(s, dis_mse, (long long)Nd * HN, HN, dis_scalars);
+  phase_mark("ac.disagree_bwd");
+  return 0;
+}
+
 int Engine::train_ac(const dv3_hparams* hp, cudaStream_t s) {
   int rc = dream_forward(hp->gamma, 1, s);
   if (rc) return rc;
   rc = ac_loss_backward(hp, 3, s);
   if (rc) return rc;
+  if (!dis.empty()) {   // train_one_step.py:180-181, 209-212, 226-246
+    rc = disagree_loss_backward(s);
+    if (!rc) rc = optimizer_step(kDisagree, hp->disagree_grad_clip, hp->disagree_lr, hp->disagree_eps, -1.f, s);
+    if (rc) return rc;
+  }
   if (hp->train_actor) {
     rc = optimizer_step(1, hp->actor_grad_clip, hp->ac_lr, hp->ac_eps, -1.f, s);
     if (rc) return rc;

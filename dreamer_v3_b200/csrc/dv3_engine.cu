@@ -29,7 +29,7 @@ static long long prod(const std::vector<int64_t>& s) {
 // ------------------------------------------------------------------------------------------ param table
 void Engine::build_param_table() {
   pinfo.clear();
-  for (int g = 0; g < 4; ++g) numel[g] = 0;
+  for (int g = 0; g < kGroups; ++g) numel[g] = 0;
   auto add = [&](int group, const std::string& name, std::vector<int64_t> shape) {
     PInfo p{name, group, shape, numel[group]};
     long long n = prod(shape);
@@ -105,6 +105,12 @@ void Engine::build_param_table() {
   dense(2, "critic.head", D, DV3_NB);
   mlp(3, "critic_ema", G + Z, L);
   dense(3, "critic_ema.head", D, DV3_NB);
+  // curiosity: N x (MLP(L) -> RepresentationLayer) on [h, z, a] (models/disagree_networks.py:31-40)
+  for (int n = 0; n < cfg.num_curiosity_nets; ++n) {
+    const std::string b = "disagree.net" + std::to_string(n);
+    mlp(kDisagree, b, G + Z + A, L);
+    dense(kDisagree, b + ".repr", D, Z);
+  }
 }
 
 float* Engine::P(const std::string& name) const {
@@ -115,7 +121,7 @@ float* Engine::P(const std::string& name) const {
 }
 float* Engine::dP(const std::string& name) const {
   for (const auto& p : pinfo)
-    if (p.name == name) return p.group < 3 ? grads[p.group] + p.off : nullptr;
+    if (p.name == name) return has_grad(p.group) ? grads[p.group] + p.off : nullptr;
   fprintf(stderr, "dv3: unknown parameter %s\n", name.c_str());
   abort();
 }
@@ -193,6 +199,11 @@ void Engine::bind_params() {
   bind_dense(critic_head, "critic.head", D, DV3_NB);
   bind_mlp(ema_mlp, "critic_ema", G + Z, L, false);
   bind_dense(ema_head, "critic_ema.head", D, DV3_NB, false);
+  for (int n = 0; n < (int)dis.size(); ++n) {
+    const std::string b = "disagree.net" + std::to_string(n);
+    bind_mlp(dis[n].mlp, b, G + Z + A, L);
+    bind_dense(dis[n].repr, b + ".repr", D, Z);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ memory
@@ -485,6 +496,26 @@ void Engine::layout() {
     if (Nl >= 128) twin_alloc(dr_dx_pre, (size_t)HN * D);
   }
   if (Nl >= 128) { twin_alloc(sN_Z, (size_t)Nl * Z); twin_alloc(sN_3G0, (size_t)Nl * 3 * G); twin_alloc(sN_3G1, (size_t)Nl * 3 * G); }
+  // ---- curiosity (models/disagree_networks.py): inputs, per-net activations, statistics, loss / backward scratch ----
+  const int Nd = cfg.num_curiosity_nets;
+  dis.resize(Nd);
+  if (Nd > 0) {
+    dis_ld = (G + Z + A + 7) & ~7;
+    dis_in = af("", {Rl, dis_ld});
+    dis_probs = af("disagree.z_predicted_probs", {Nd, Rl, Zc, Zk});
+    for (int n = 0; n < Nd; ++n) {
+      dis[n].act = alloc_mlp_act("disagree.net" + std::to_string(n), Rl, L);
+      dis[n].logits = af("", {Rl, Z});
+      dis[n].probs = dry ? nullptr : dis_probs + (size_t)n * Rl * Z;
+    }
+    dis_std = af("", {Rl});
+    dis_ri = af("dream.rewards_intrinsic", {H + 1, Nl});
+    dis_mse = af("", {Nd, HN});
+    dis_scalars = af("disagree.scalars", {4});
+    dis_dprobs = af("", {HN, Z}); dis_dlogits = af("", {HN, Z});
+    dis_s0 = af("", {HN, D}); dis_s1 = af("", {HN, D});
+    twin_alloc(dis_s1, (size_t)HN * D);
+  }
   noise_step = (unsigned long long*)alloc_bytes("noise_step", 8, 1, {2}, 6, -1);
 }
 
@@ -503,6 +534,9 @@ int Engine::init(const dv3_config* c) {
   if (D > 1024) return fail("dense width D must be <= 1024");
   if (discrete && A > 32) return fail("Discrete action spaces with more than 32 actions are not supported");
   if (L > 8) return fail("at most 8 MLP layers");
+  if (cfg.num_curiosity_nets < 0 || cfg.num_curiosity_nets > 64) return fail("num_curiosity_nets must be in [0, 64]");
+  if (cfg.num_curiosity_nets > 0 && cfg.world_size > 1)
+    return fail("curiosity (disagree nets) is single-process: the intrinsic rewards are centred over the whole dream batch");
   if (image) {
     if (cfg.img_hw != 64) return fail("image observations must be 64x64");
     if (8 * cfg.cnn_mult > 1024) return fail("cnn multiplier too large");
@@ -526,11 +560,16 @@ int Engine::init(const dv3_config* c) {
     for (int g = 0; g < 3; ++g) grads[g] = reinterpret_cast<float*>(gb + off[g]);
     grads_ac_numel = (long long)((off[3] - off[1]) / 4);
   }
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < kGroups; ++g) {
+    if (numel[g] == 0) continue;
     const size_t bytes = (size_t)numel[g] * 4;
     CK(cudaMalloc((void**)&params[g], bytes)); allocations.push_back(params[g]);
     CK(cudaMemset(params[g], 0, bytes));
-    if (g < 3) {
+    if (g == kDisagree) {   // (groups 0 - 2 share the allocation above)
+      CK(cudaMalloc((void**)&grads[g], bytes)); allocations.push_back(grads[g]);
+      CK(cudaMemset(grads[g], 0, bytes));
+    }
+    if (has_grad(g)) {
       CK(cudaMalloc((void**)&adam_m[g], bytes)); allocations.push_back(adam_m[g]);
       CK(cudaMalloc((void**)&adam_v[g], bytes)); allocations.push_back(adam_v[g]);
       CK(cudaMemset(adam_m[g], 0, bytes)); CK(cudaMemset(adam_v[g], 0, bytes));
@@ -538,7 +577,7 @@ int Engine::init(const dv3_config* c) {
       CK(cudaMalloc((void**)&st, 64)); allocations.push_back(st);
       CK(cudaMemset(st, 0, 64));
       adam[g].sumsq = (double*)st; adam[g].stats = (float*)(st + 16); adam[g].step = (int*)(st + 32);
-      const char* gn[3] = {"world_model", "actor", "critic"};
+      const char* gn[kGroups] = {"world_model", "actor", "critic", "", "", "disagree"};
       index[std::string("opt.") + gn[g] + ".stats"] = (int)tensors.size();
       tensors.push_back(TensorEntry{std::string("opt.") + gn[g] + ".stats", adam[g].stats, 0, {4}, 6, g, 16});
       index[std::string("opt.") + gn[g] + ".step"] = (int)tensors.size();
@@ -549,7 +588,7 @@ int Engine::init(const dv3_config* c) {
     const size_t bytes = (size_t)prod(p.shape) * 4;
     index[p.name] = (int)tensors.size();
     tensors.push_back(TensorEntry{p.name, params[p.group] + p.off, 0, p.shape, 0, p.group, bytes});
-    if (p.group < 3) {
+    if (has_grad(p.group)) {
       index["grad." + p.name] = (int)tensors.size();
       tensors.push_back(TensorEntry{"grad." + p.name, grads[p.group] + p.off, 0, p.shape, 1, p.group, bytes});
       index["adam_m." + p.name] = (int)tensors.size();
@@ -960,7 +999,7 @@ void Engine::decoder_bwd() {
 }
 
 int Engine::optimizer_step(int group, float clip, float lr, float eps, float ema_decay, cudaStream_t s) {
-  if (group < 0 || group > 2) return fail("optimizer_step: group must be 0 (world_model), 1 (actor) or 2 (critic)");
+  if (!has_grad(group) || numel[group] == 0) return fail("optimizer_step: group must be 0 (world_model), 1 (actor), 2 (critic) or 5 (disagree nets, with curiosity on)");
   cur = s;
   grad_norm(s, grads[group], numel[group], adam[group]);
   float* ema = (group == 2 && ema_decay >= 0.f) ? params[3] : nullptr;   // a decay of 0.0 is a legitimate EMA (ema = w)

@@ -61,13 +61,18 @@ struct Engine {
   size_t arena_off = 0, arena_size = 0;
   bool dry = true;
 
-  float* params[4] = {nullptr, nullptr, nullptr, nullptr};
-  float* grads[3] = {nullptr, nullptr, nullptr};
-  float* adam_m[3] = {nullptr, nullptr, nullptr};
-  float* adam_v[3] = {nullptr, nullptr, nullptr};
-  long long numel[4] = {0, 0, 0, 0};
+  // optimizer groups: 0 world_model, 1 actor, 2 critic, 3 critic_ema (no gradients), 4 unused (the id of the actor + critic
+  // gradient span in dv3_group_buffer), 5 disagree nets (curiosity)
+  static constexpr int kGroups = 6;
+  static constexpr int kDisagree = 5;
+  static bool has_grad(int g) { return g == 0 || g == 1 || g == 2 || g == kDisagree; }
+  float* params[kGroups] = {};
+  float* grads[kGroups] = {};
+  float* adam_m[kGroups] = {};
+  float* adam_v[kGroups] = {};
+  long long numel[kGroups] = {};
   long long grads_ac_numel = 0;   // floats from grads[1] to the end of grads[2] (one allocation, padding included)
-  AdamState adam[3];
+  AdamState adam[kGroups];
   struct PInfo { std::string name; int group; std::vector<int64_t> shape; long long off; };
   std::vector<PInfo> pinfo;
 
@@ -134,6 +139,15 @@ struct Engine {
   float *dr_dx_pre = nullptr, *dr_dact = nullptr;  // Box BPTT: per-step grads w.r.t. the pre-GRU pre-activation [H*N, D] and the actions [H*N, A]
   unsigned long long* noise_step = nullptr;
   float last_gamma = 0.997f, last_lambda = 0.95f;   // lambda of the value targets exposed after dream_forward alone: the last hparams seen
+
+  // ---- curiosity: the Plan2Explore disagree nets (models/disagree_networks.py), cfg.num_curiosity_nets > 0 ----
+  struct DisagreeNet { Mlp mlp; DenseLayer repr; MlpAct act; float* logits = nullptr; float* probs = nullptr; };
+  std::vector<DisagreeNet> dis;
+  int dis_ld = 0;                  // row stride of dis_in ([h, z, a] rows, padded to 8 floats)
+  float *dis_in = nullptr, *dis_probs = nullptr, *dis_std = nullptr, *dis_ri = nullptr, *dis_mse = nullptr, *dis_scalars = nullptr;
+  float *dis_dprobs = nullptr, *dis_dlogits = nullptr, *dis_s0 = nullptr, *dis_s1 = nullptr;
+  void disagree_forward();   // every net on stop_gradient([h, z, a]) of all dreamed rows + the intrinsic rewards
+  int disagree_loss_backward(cudaStream_t s);   // disagree_loss + gradients into group 5
 
   // ---- bf16 weight shadows for the tensor-core path (compute_mode 1) ----
   std::vector<ShadowDesc> shadow_host;

@@ -274,7 +274,8 @@ __global__ void ac_value_targets_kernel(AcArgs a) {
     for (int t = H - 1; t >= 0; --t) {
       const size_t j = (size_t)(t + 1) * N + n;
       const float disc = a.c[j] * a.gamma;
-      const float inter = a.r[j] + disc * (1.f - a.lambda_) * a.v[j];
+      const float rj = a.r_intr ? a.r[j] + a.r_intr[j] : a.r[j];   // critic_loss.py:118-120
+      const float inter = rj + disc * (1.f - a.lambda_) * a.v[j];
       R = inter + disc * a.lambda_ * R;
       a.targets[(size_t)t * N + n] = R;
     }

@@ -11,7 +11,8 @@ import torch
 from . import _lib
 from .spec import EngineConfig, param_spec
 
-GROUP_IDS = {"world_model": 0, "actor": 1, "critic": 2, "critic_ema": 3, "actor_critic": 4}   # 4: gradient span of actor + critic
+# 4: gradient span of actor + critic; 5: the Plan2Explore disagree nets (curiosity)
+GROUP_IDS = {"world_model": 0, "actor": 1, "critic": 2, "critic_ema": 3, "actor_critic": 4, "disagree": 5}
 
 
 class _CudaView:
@@ -42,6 +43,7 @@ class Engine:
         c.img_hw, c.img_c, c.B, c.T, c.H = cfg.img_hw, cfg.img_c, cfg.B, cfg.T, cfg.H
         c.symlog_obs, c.compute_mode = int(cfg.symlog_obs), int(compute_mode)
         c.world_size, c.rank, c.device = int(world_size), int(rank), self.device_index
+        c.num_curiosity_nets, c.intrinsic_rewards_scale = int(cfg.num_curiosity_nets), float(cfg.intrinsic_rewards_scale)
         self.world_size, self.rank, self.compute_mode = int(world_size), int(rank), int(compute_mode)
         h = C.c_void_p()
         rc = self.lib.dv3_create(C.byref(c), C.byref(h))
@@ -194,6 +196,10 @@ class Engine:
     def ac_loss_backward(self, phase=3):
         self._check(self.lib.dv3_ac_loss_backward(self.h, C.byref(self.hp), int(phase), self._stream()),
                     "dv3_ac_loss_backward")
+
+    def disagree_loss_backward(self):
+        """disagree_loss + its gradients (losses/disagree_loss.py, train_one_step.py:180-181, 209-212); curiosity engines only."""
+        self._check(self.lib.dv3_disagree_loss_backward(self.h, self._stream()), "dv3_disagree_loss_backward")
 
     def critic_init_ema(self):
         self._check(self.lib.dv3_critic_init_ema(self.h, self._stream()), "dv3_critic_init_ema")

@@ -8,8 +8,9 @@ from .. import ops
 
 def compute_value_targets(*, rewards_t0_to_H_BxT, intrinsic_rewards_t1_to_H_BxT=None, continues_t0_to_H_BxT,
                           value_predictions_t0_to_H_BxT, gamma, lambda_):
-    if intrinsic_rewards_t1_to_H_BxT is not None:
-        raise NotImplementedError("curiosity is out of scope")
     dev = lambda x: torch.as_tensor(x, dtype=torch.float32).cuda()
-    return ops.value_targets(dev(rewards_t0_to_H_BxT), dev(continues_t0_to_H_BxT), dev(value_predictions_t0_to_H_BxT),
+    r = dev(rewards_t0_to_H_BxT)
+    if intrinsic_rewards_t1_to_H_BxT is not None:  # critic_loss.py:118-120 (the first reward is never used)
+        r = torch.cat([r[:1], r[1:] + dev(intrinsic_rewards_t1_to_H_BxT)], dim=0)
+    return ops.value_targets(r, dev(continues_t0_to_H_BxT), dev(value_predictions_t0_to_H_BxT),
                              float(gamma), float(lambda_))

@@ -3,6 +3,7 @@ import torch
 
 from .actor_network import ActorNetwork
 from .critic_network import CriticNetwork
+from .disagree_networks import DisagreeNetworks
 
 
 class _ActionDist:
@@ -32,18 +33,19 @@ class _ActionDist:
 class DreamerModel:
     def __init__(self, *, model_dimension="XS", action_space, batch_size_B, batch_length_T, horizon_H, world_model,
                  use_curiosity=False, intrinsic_rewards_scale=0.1, world_size=1, rank=0):
-        if use_curiosity:
-            raise NotImplementedError("Plan2Explore disagree networks are out of scope (SURVEY.md section 2, row 14)")
         self.model_dimension = model_dimension
         self.action_space = action_space
-        self.use_curiosity = False
+        self.use_curiosity = bool(use_curiosity)
         self.batch_size_B, self.batch_length_T, self.horizon_H = batch_size_B, batch_length_T, horizon_H
         self.world_model = world_model
-        world_model._configure(B=batch_size_B, H=horizon_H, world_size=world_size, rank=rank)
+        world_model._configure(B=batch_size_B, H=horizon_H, world_size=world_size, rank=rank,
+                               use_curiosity=self.use_curiosity, intrinsic_rewards_scale=float(intrinsic_rewards_scale))
         get = lambda: self.world_model.engine
         self.actor = ActorNetwork(action_space=action_space, model_dimension=model_dimension, engine_getter=get)
         self.critic = CriticNetwork(model_dimension=model_dimension, engine_getter=get)
-        self.disagree_nets = None
+        # dreamer_model.py:61-67
+        self.disagree_nets = DisagreeNetworks(
+            model_dimension=model_dimension, intrinsic_rewards_scale=intrinsic_rewards_scale, engine_getter=get) if self.use_curiosity else None
 
     @property
     def engine(self):
@@ -108,6 +110,9 @@ class DreamerModel:
             "v_symlog_dreamed_ema_t0_to_H_B": e.tensor("dream.values_symlog_ema"),
             "dream_loss_weights_t0_to_H_B": e.tensor("dream.loss_weights"),
         }
+        if self.use_curiosity:  # dreamer_model.py:296-298
+            ret["rewards_intrinsic_t1_to_H_B"] = e.tensor("dream.rewards_intrinsic")[1:]
+            ret["z_predicted_probs_N_HxB"] = list(e.tensor("disagree.z_predicted_probs"))
         if cfg.discrete:
             ret["actions_ints_dreamed_t0_to_H_B"] = e.tensor("dream.action_indices")
         return ret

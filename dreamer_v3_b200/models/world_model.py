@@ -79,7 +79,7 @@ class WorldModel:
         self.seed = seed
         self.compute_mode = compute_mode
         self._engine = None
-        self._engine_args = dict(B=None, H=15, world_size=1, rank=0)
+        self._engine_args = dict(B=None, H=15, world_size=1, rank=0, use_curiosity=False, intrinsic_rewards_scale=0.1)
         self._noise_step = 0
         self._explicit_noise = False
         self.noise_seed = 0x5EED + seed
@@ -100,11 +100,14 @@ class WorldModel:
         return EngineConfig.make(
             self.model_dimension, A=A, discrete=discrete, image_obs=image,
             obs_dim=getattr(self.decoder, "obs_dim", 4), img_c=getattr(self.decoder, "img_c", 3),
-            B=B, T=self.batch_length_T, H=H, symlog_obs=self.symlog_obs, num_gru_units=self.num_gru_units_override)
+            B=B, T=self.batch_length_T, H=H, symlog_obs=self.symlog_obs, num_gru_units=self.num_gru_units_override,
+            use_curiosity=self._engine_args["use_curiosity"],
+            intrinsic_rewards_scale=self._engine_args["intrinsic_rewards_scale"])
 
-    def _configure(self, B=None, H=None, world_size=None, rank=None):
+    def _configure(self, B=None, H=None, world_size=None, rank=None, use_curiosity=None, intrinsic_rewards_scale=None):
         a = self._engine_args
-        for k, v in (("B", B), ("H", H), ("world_size", world_size), ("rank", rank)):
+        for k, v in (("B", B), ("H", H), ("world_size", world_size), ("rank", rank), ("use_curiosity", use_curiosity),
+                     ("intrinsic_rewards_scale", intrinsic_rewards_scale)):
             if v is not None:
                 if self._engine is not None and a[k] != v:
                     raise RuntimeError(f"engine already built with {k}={a[k]}, cannot change to {v}")

@@ -25,13 +25,14 @@ from .utils.model_dimensions import (
     get_cnn_multiplier,
     get_dense_hidden_units,
     get_gru_units,
+    get_num_curiosity_nets,
     get_num_dense_layers,
     get_num_z_categoricals,
     get_num_z_classes,
 )
 
 NUM_BUCKETS = 255  # reward_predictor.py:20-22, critic_network.py:20-22
-GROUPS = ("world_model", "actor", "critic", "critic_ema")
+GROUPS = ("world_model", "actor", "critic", "critic_ema", "disagree")
 
 
 class Discrete:
@@ -76,6 +77,9 @@ class EngineConfig:
     T: int = 64
     H: int = 15
     symlog_obs: bool = True
+    # Plan2Explore curiosity (models/disagree_networks.py): 0 = off (use_curiosity=False), else the number of disagree nets
+    num_curiosity_nets: int = 0
+    intrinsic_rewards_scale: float = 0.1
 
     @property
     def Z(self):
@@ -95,7 +99,8 @@ class EngineConfig:
 
     @staticmethod
     def make(model_dimension="XS", *, action_space=None, A=None, discrete=None, image_obs=False,
-             obs_dim=4, img_c=3, B=16, T=64, H=15, symlog_obs=None, num_gru_units=None):
+             obs_dim=4, img_c=3, B=16, T=64, H=15, symlog_obs=None, num_gru_units=None, use_curiosity=False,
+             num_curiosity_nets=None, intrinsic_rewards_scale=0.1):
         if action_space is not None:
             discrete, A = action_space_info(action_space)
         assert A is not None and discrete is not None
@@ -111,6 +116,8 @@ class EngineConfig:
             Zk=get_num_z_classes(model_dimension),
             A=int(A), discrete=bool(discrete), image_obs=bool(image_obs), obs_dim=int(obs_dim),
             img_c=int(img_c), B=int(B), T=int(T), H=int(H), symlog_obs=bool(symlog_obs),
+            num_curiosity_nets=(get_num_curiosity_nets(model_dimension, override=num_curiosity_nets) if use_curiosity else 0),
+            intrinsic_rewards_scale=float(intrinsic_rewards_scale),
         )
 
     def asdict(self):
@@ -202,6 +209,10 @@ def param_spec(cfg: EngineConfig) -> List[ParamInfo]:
     for grp, pre in (("critic", "critic"), ("critic_ema", "critic_ema")):
         _mlp(p, grp, pre, G + Z, D, L)
         _dense(p, grp, f"{pre}.head", D, NUM_BUCKETS, init="zeros")
+    # --- curiosity: N x (MLP(L) -> RepresentationLayer) on [h, z, a] (models/disagree_networks.py:31-40) ----
+    for n in range(cfg.num_curiosity_nets):
+        _mlp(p, "disagree", f"disagree.net{n}", G + Z + A, D, L)
+        _dense(p, "disagree", f"disagree.net{n}.repr", D, Z)
     return p
 
 

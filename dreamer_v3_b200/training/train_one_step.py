@@ -53,10 +53,15 @@ def train_world_model_one_step(*, sample, batch_size_B, batch_length_T, grad_cli
 def train_actor_and_critic_one_step(*, world_model_forward_train_outs, is_terminated, horizon_H, gamma, lambda_,
                                     actor_grad_clip, critic_grad_clip, disagree_grad_clip, dreamer_model,
                                     entropy_scale, return_normalization_decay, train_actor=True, use_curiosity=False):
-    if use_curiosity:
-        raise NotImplementedError("curiosity is out of scope")
     e = dreamer_model.engine
+    if bool(use_curiosity) != (e.cfg.num_curiosity_nets > 0):
+        raise ValueError("use_curiosity must match the DreamerModel's (dreamer_model.py:62-67 builds the disagree nets)")
+    if use_curiosity and _dp(e):
+        raise ValueError("curiosity is single-process (the intrinsic rewards are centred over the whole dream batch)")
     hp = e.hp
+    if use_curiosity:
+        dopt = dreamer_model.disagree_nets.optimizer
+        hp.disagree_grad_clip, hp.disagree_lr, hp.disagree_eps = float(disagree_grad_clip), dopt.learning_rate, dopt.epsilon
     hp.gamma, hp.lambda_, hp.entropy_scale = float(gamma), float(lambda_), float(entropy_scale)
     hp.return_normalization_decay = float(return_normalization_decay)
     hp.train_actor = int(bool(train_actor))
@@ -88,7 +93,7 @@ def train_actor_and_critic_one_step(*, world_model_forward_train_outs, is_termin
         hp.ac_lr, hp.ac_eps, hp.critic_ema_decay = aopt.learning_rate, aopt.epsilon, dreamer_model.critic.ema_decay
         hp.critic_lr, hp.critic_eps = copt.learning_rate, copt.epsilon
         e.train_actor_critic_step(noise_seed=0 if wm._explicit_noise else wm.noise_seed)
-        return _ac_results(e, dreamer_model._dream_outs(), train_actor)
+        return _ac_results(e, dreamer_model._dream_outs(), train_actor, use_curiosity)
     dream_data = dreamer_model.dream_trajectory(
         start_states={"h": world_model_forward_train_outs["h_states_BxT"],
                       "z": world_model_forward_train_outs["z_states_BxT"]},
@@ -104,10 +109,13 @@ def train_actor_and_critic_one_step(*, world_model_forward_train_outs, is_termin
         e.optimizer_step("actor", float(actor_grad_clip), aopt.learning_rate, aopt.epsilon)
     # critic Adam + update_ema() fused (train_one_step.py:235-250)
     e.optimizer_step("critic", float(critic_grad_clip), copt.learning_rate, copt.epsilon, dreamer_model.critic.ema_decay)
-    return _ac_results(e, dream_data, train_actor)
+    if use_curiosity:  # train_one_step.py:180-181, 209-212, 226-246
+        e.disagree_loss_backward()
+        e.optimizer_step("disagree", hp.disagree_grad_clip, hp.disagree_lr, hp.disagree_eps)
+    return _ac_results(e, dream_data, train_actor, use_curiosity)
 
 
-def _ac_results(e, dream_data, train_actor):
+def _ac_results(e, dream_data, train_actor, use_curiosity=False):
     t = e.tensor
     s = t("ac.scalars")
     results = {
@@ -136,5 +144,13 @@ def _ac_results(e, dream_data, train_actor):
             "ACTOR_L_neglogp_reinforce_term": s[5],
             "ACTOR_L_neg_entropy_term_H_B": t("ac.ACTOR_L_neg_entropy_term_H_B"), "ACTOR_L_neg_entropy_term": s[6],
             "ACTOR_gradients_maxabs": ast[1], "ACTOR_gradients_clipped_by_glob_norm_maxabs": ast[2],
+        })
+    if use_curiosity:  # train_one_step.py:201-208, 230-231
+        ds, dst = t("disagree.scalars"), t("opt.disagree.stats")
+        results.update({
+            "DISAGREE_L_total": ds[0],
+            "DISAGREE_intrinsic_rewards_H_B": dream_data["rewards_intrinsic_t1_to_H_B"],
+            "DISAGREE_intrinsic_rewards": ds[1],
+            "DISAGREE_gradients_maxabs": dst[1], "DISAGREE_gradients_clipped_by_glob_norm_maxabs": dst[2],
         })
     return results

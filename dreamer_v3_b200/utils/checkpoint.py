@@ -33,7 +33,7 @@ def _mlp(prefix, L, out=None):
 
 
 def weight_order(cfg, model):
-    """spec names in `model.get_weights()` order, model in {"world_model", "actor", "critic"}."""
+    """spec names in `model.get_weights()` order, model in {"world_model", "actor", "critic", "disagree"}."""
     L = cfg.L
     if model == "world_model":
         n = ["initial_h"]  # the model's own tf.Variable (world_model.py:98-101) precedes its sub-layers
@@ -64,6 +64,14 @@ def weight_order(cfg, model):
     if model == "critic":  # trainable (mlp, return_layer) then non-trainable (mlp_ema, return_layer_ema)
         return (_mlp("critic", L) + ["critic.head.w", "critic.head.bias"]
                 + _mlp("critic_ema", L) + ["critic_ema.head.w", "critic_ema.head.bias"])
+    if model == "disagree":  # disagree_networks.py:28-40: the mlps list, then the representation_layers list
+        N = cfg.num_curiosity_nets
+        n = []
+        for i in range(N):
+            n += _mlp(f"disagree.net{i}", L)
+        for i in range(N):
+            n += [f"disagree.net{i}.repr.w", f"disagree.net{i}.repr.bias"]
+        return n
     raise KeyError(model)
 
 
@@ -121,6 +129,11 @@ def set_optimizer_weights(engine, model, weights):
 MODELS = ("world_model", "actor", "critic")
 
 
+def _models(cfg):
+    """(engine group, file stem) pairs; run_experiment.py:495,702 names the curiosity files `disagree_nets`."""
+    return [(m, m) for m in MODELS] + ([("disagree", "disagree_nets")] if cfg.num_curiosity_nets > 0 else [])
+
+
 def save_checkpoint(path, dreamer_model, buffer=None, **counters):
     """run_experiment.py:692-714 (+ dv3_state.npz). counters: total_env_steps, total_replayed_steps, total_train_steps, iteration.
     buffer: the EpisodeReplayBuffer, written as buffer.npz with key `state` exactly like run_experiment.py:708."""
@@ -128,9 +141,9 @@ def save_checkpoint(path, dreamer_model, buffer=None, **counters):
     os.makedirs(path, exist_ok=True)
     if buffer is not None:
         np.savez(os.path.join(path, "buffer"), state=buffer.get_state())
-    for m in MODELS:
-        np.savez(os.path.join(path, m), weights=np.array(get_weights(e, m), dtype=object))
-        np.savez(os.path.join(path, m + "_optimizer"), weights=np.array(get_optimizer_weights(e, m), dtype=object))
+    for m, stem in _models(e.cfg):
+        np.savez(os.path.join(path, stem), weights=np.array(get_weights(e, m), dtype=object))
+        np.savez(os.path.join(path, stem + "_optimizer"), weights=np.array(get_optimizer_weights(e, m), dtype=object))
     for k, v in counters.items():
         np.save(os.path.join(path, k), v)
     state = {}
@@ -139,7 +152,7 @@ def save_checkpoint(path, dreamer_model, buffer=None, **counters):
         if pi.group != "critic_ema":
             state["adam_m/" + pi.name] = e.tensor("adam_m." + pi.name).detach().cpu().numpy()
             state["adam_v/" + pi.name] = e.tensor("adam_v." + pi.name).detach().cpu().numpy()
-    for m in MODELS:
+    for m, _ in _models(e.cfg):
         state["step/" + m] = e.tensor(f"opt.{m}.step").detach().cpu().numpy()
     state["pct_ema"] = e.tensor("ac.pct_ema").detach().cpu().numpy()
     np.savez(os.path.join(path, "dv3_state"), **state)
@@ -165,9 +178,9 @@ def load_checkpoint(path, dreamer_model, buffer=None):
                 e.tensor(f"opt.{name}.step").copy_(torch.from_numpy(z[k]))
         e.tensor("ac.pct_ema").copy_(torch.from_numpy(z["pct_ema"]))
     else:
-        for m in MODELS:
-            set_weights(e, m, list(np.load(os.path.join(path, m + ".npz"), allow_pickle=True)["weights"]))
-            set_optimizer_weights(e, m, list(np.load(os.path.join(path, m + "_optimizer.npz"), allow_pickle=True)["weights"]))
+        for m, stem in _models(e.cfg):
+            set_weights(e, m, list(np.load(os.path.join(path, stem + ".npz"), allow_pickle=True)["weights"]))
+            set_optimizer_weights(e, m, list(np.load(os.path.join(path, stem + "_optimizer.npz"), allow_pickle=True)["weights"]))
     out = {}
     for k in ("total_env_steps", "total_replayed_steps", "total_train_steps", "iteration"):
         f = os.path.join(path, k + ".npy")

@@ -53,7 +53,10 @@ typedef struct dv3_config {
   int32_t world_size;    /* data-parallel ranks (losses are normalised by world_size*B) */
   int32_t rank;
   int32_t device;        /* CUDA device ordinal */
-  int32_t reserved[8];
+  int32_t num_curiosity_nets; /* 0 = use_curiosity False; else the N of DisagreeNetworks (models/disagree_networks.py:23-40,
+                                 utils/model_dimensions.py:69-78); single-process only (world_size == 1) */
+  float intrinsic_rewards_scale; /* DreamerModel(intrinsic_rewards_scale=0.1) (dreamer_model.py:33) */
+  int32_t reserved[6];
 } dv3_config;
 
 typedef struct dv3_tensor_desc {
@@ -63,7 +66,7 @@ typedef struct dv3_tensor_desc {
   int32_t ndim;
   int64_t shape[6];
   int32_t kind;      /* 0 param, 1 grad, 2 adam_m, 3 adam_v, 4 input, 5 output/activation, 6 scalar state */
-  int32_t group;     /* 0 world_model, 1 actor, 2 critic, 3 critic_ema, -1 n/a */
+  int32_t group;     /* 0 world_model, 1 actor, 2 critic, 3 critic_ema, 5 disagree nets, -1 n/a */
 } dv3_tensor_desc;
 
 /* Hyper-parameters of the two update steps (run_experiment.py:145-148, 245-252; world_model.py:124;
@@ -75,7 +78,10 @@ typedef struct dv3_hparams {
   float critic_ema_decay;
   int32_t train_actor;
   float critic_lr, critic_eps;  /* the critic's own Adam (critic_network.py:58); 0 = use ac_lr / ac_eps */
-  int32_t reserved[5];
+  /* curiosity (num_curiosity_nets > 0): disagree_grad_clip (run_experiment.py:252), the disagree nets' Adam
+   * (disagree_networks.py:43) */
+  float disagree_grad_clip, disagree_lr, disagree_eps;
+  int32_t reserved[2];
 } dv3_hparams;
 
 /* ---- lifetime ----------------------------------------------------------------------------- */
@@ -94,7 +100,8 @@ int dv3_find_tensor(const dv3_engine* e, const char* name, dv3_tensor_desc* out)
 int dv3_write_tensor(dv3_engine* e, const char* name, const void* src, size_t nbytes, int src_is_device, void* stream, int sync);
 int dv3_read_tensor(dv3_engine* e, const char* name, void* dst, size_t nbytes, int dst_is_device, void* stream, int sync);
 /* flat per-group views for the data-parallel all-reduce: kind in {0 param,1 grad,2 m,3 v}; group 4 with kind 1 = the actor and
- * critic gradient buffers as ONE span (adjacent in memory, zero padding between them): one collective for both */
+ * critic gradient buffers as ONE span (adjacent in memory, zero padding between them): one collective for both; group 5 = the
+ * disagree nets (curiosity) */
 int dv3_group_buffer(const dv3_engine* e, int group, int kind, void** ptr, int64_t* numel);
 
 /* ---- noise ------------------------------------------------------------------------------- */
@@ -113,7 +120,7 @@ int dv3_observe_forward(dv3_engine* e, void* stream);
  * Reads in.rewards [B,T], in.is_terminated [B,T]. */
 int dv3_wm_loss_backward(dv3_engine* e, void* stream);
 /* tf.clip_by_global_norm + Keras Adam (+ critic EMA for group 2) on a group's flat buffers
- * (train_one_step.py:80-86, 214-250). Call after the gradient all-reduce when world_size > 1. */
+ * (train_one_step.py:80-86, 214-250; group 5: the disagree nets, :226-246). Call after the gradient all-reduce when world_size > 1. */
 int dv3_optimizer_step(dv3_engine* e, int group, float clip, float lr, float eps, float ema_decay, void* stream); /* ema_decay < 0: no EMA update (any value in [0, 1] is a decay, 0 included) */
 /* One call = train_world_model_one_step (train_one_step.py:17-126) for world_size == 1. noise_seed != 0: in.u_post is
  * drawn on the device first; use_graph: the call is captured once into a CUDA graph and replayed. */
@@ -141,6 +148,14 @@ int dv3_dream_forward_actions(dv3_engine* e, float gamma, int start_from_observe
  * dream for Box). phase 1 = value targets only (so the caller can all-gather them across ranks for
  * the percentile), phase 2 = the rest, 3 = both. */
 int dv3_ac_loss_backward(dv3_engine* e, const dv3_hparams* hp, int phase, void* stream);
+/* Curiosity (use_curiosity=True; models/disagree_networks.py:47-95, losses/disagree_loss.py:11-41, train_one_step.py:180-246).
+ * With num_curiosity_nets > 0, dv3_dream_forward also runs every disagree net on stop_gradient([h, z, a]) of all (H+1)*N dreamed
+ * rows (disagree.z_predicted_probs [nets, (H+1)N, Zc*Zk]) and fills dream.rewards_intrinsic [H+1, N] (row 0 unused:
+ * rewards_intrinsic_t1_to_H_B is rows 1..H), which dv3_ac_loss_backward adds to the dreamed rewards inside the lambda-returns
+ * (critic_loss.py:118-120). dv3_disagree_loss_backward: disagree_loss (disagree.scalars[0] = DISAGREE_L_total, [1] = mean
+ * intrinsic reward) and its gradients into group 5; dv3_train_actor_critic_step / dv3_train_update do all of it and step group 5
+ * with hp->disagree_grad_clip / disagree_lr / disagree_eps. */
+int dv3_disagree_loss_backward(dv3_engine* e, void* stream);
 /* CriticNetwork.init_ema / update_ema (critic_network.py:84-100). */
 int dv3_critic_init_ema(dv3_engine* e, void* stream);
 int dv3_critic_update_ema(dv3_engine* e, float decay, void* stream);

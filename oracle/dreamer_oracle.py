@@ -57,7 +57,7 @@ class Oracle:
         self.dtype = dtype
         self.P = {k: _t(v, dtype).clone().requires_grad_(not k.startswith("critic_ema."))
                   for k, v in params.items()}
-        self.adam = {g: {"t": 0, "m": {}, "v": {}} for g in ("world_model", "actor", "critic")}
+        self.adam = {g: {"t": 0, "m": {}, "v": {}} for g in ("world_model", "actor", "critic", "disagree")}
         self.ema_pct5 = float("nan")  # actor_network.py:31-36
         self.ema_pct95 = float("nan")
         self.buckets = torch.linspace(-20.0, 20.0, NUM_BUCKETS, dtype=dtype)
@@ -80,6 +80,8 @@ class Oracle:
                 return "critic_ema"
             if n.startswith("critic."):
                 return "critic"
+            if n.startswith("disagree."):
+                return "disagree"
             return "world_model"
         return [n for n in self.P if grp(n) == group]
 
@@ -454,9 +456,44 @@ class Oracle:
             "dream_loss_weights_t0_to_H_B": w_HB,
             "z_indices_t1_to_H_B": np.stack(zidx, 0) if zidx else None,
         }
+        if getattr(cfg, "num_curiosity_nets", 0) > 0:  # dreamer_model.py:226-240, :296-298
+            cur = self.compute_intrinsic_rewards(hz, a_HB.reshape((H + 1) * N, -1))
+            out["rewards_intrinsic_t1_to_H_B"] = cur["rewards_intrinsic"].reshape(H + 1, N)[1:]
+            out["z_predicted_probs_N_HxB"] = cur["z_predicted_probs_N_HxB"]
         if cfg.discrete:
             out["actions_ints_dreamed_t0_to_H_B"] = torch.argmax(a_HB, -1)
         return out
+
+    # ------------------------------------------------------------------ curiosity (Plan2Explore disagreement)
+    def disagree_forward_train(self, hz, a):
+        """models/disagree_networks.py:78-95: every net = MLP(L layers) -> RepresentationLayer probs on
+        stop_gradient([h, z, a])."""
+        cfg = self.cfg
+        x = torch.cat([hz, a], -1).detach()
+        return [self.representation(f"disagree.net{n}.repr", self.mlp(f"disagree.net{n}", x, cfg.L), None, sample=False)[1]
+                for n in range(cfg.num_curiosity_nets)]
+
+    def compute_intrinsic_rewards(self, hz, a):
+        """models/disagree_networks.py:47-76: population stddev over the nets of every class probability, mean over the
+        Zc*Zk probabilities, minus the mean over all rows (the reference's `#TEST` lines), times the scale."""
+        cfg = self.cfg
+        probs = self.disagree_forward_train(hz, a)
+        p = torch.stack(probs, 0).reshape(len(probs), hz.shape[0], -1)
+        std = torch.sqrt(((p - p.mean(0, keepdim=True)) ** 2).mean(0))  # tf.math.reduce_std
+        s = std.mean(-1)
+        s = s - s.mean()
+        return {"rewards_intrinsic": s * cfg.intrinsic_rewards_scale, "z_predicted_probs_N_HxB": probs}
+
+    def disagree_loss(self, dream):
+        """losses/disagree_loss.py:11-41 (no loss weights, as in the reference)."""
+        z = dream["z_states_prior_t0_to_H_B"].detach()
+        Hp1, N = z.shape[0], z.shape[1]
+        target = z[1:].reshape(Hp1 - 1, N, -1)
+        loss = 0.0
+        for p in dream["z_predicted_probs_N_HxB"]:
+            pred = p.reshape(Hp1, N, -1)[:-1]
+            loss = loss + ((pred - target) ** 2).sum(-1).mean()
+        return loss
 
     def dream_trajectory_with_burn_in(self, start_states, timesteps_burn_in, timesteps_H, observations, actions,
                                       u_burn, u_dyn, act_noise=None, use_sampled_actions_in_dream=False):
@@ -499,10 +536,11 @@ class Oracle:
         return out
 
     @staticmethod
-    def compute_value_targets(r, c, v, gamma, lambda_):
+    def compute_value_targets(r, c, v, gamma, lambda_, intrinsic_t1_to_H=None):
         """losses/critic_loss.py:92-139 (differentiable restatement)."""
         discount = c[1:] * gamma
-        inter = r[1:] + discount * (1.0 - lambda_) * v[1:]
+        r1 = r[1:] if intrinsic_t1_to_H is None else r[1:] + intrinsic_t1_to_H  # :118-120
+        inter = r1 + discount * (1.0 - lambda_) * v[1:]
         Rs = [v[-1]]
         for t in reversed(range(discount.shape[0])):
             Rs.append(inter[t] + discount[t] * lambda_ * Rs[-1])
@@ -582,27 +620,41 @@ class Oracle:
     def train_actor_and_critic_one_step(self, h_BxT, z_BxT, is_terminated, H=15, gamma=0.997, lambda_=0.95,
                                         actor_grad_clip=100.0, critic_grad_clip=100.0, entropy_scale=3e-4,
                                         return_normalization_decay=0.99, u_dyn=None, act_noise=None, rng=None,
-                                        margin=0.0, apply=True):
-        """training/train_one_step.py:130-252."""
+                                        margin=0.0, apply=True, disagree_grad_clip=100.0):
+        """training/train_one_step.py:130-252 (use_curiosity = cfg.num_curiosity_nets > 0)."""
+        use_curiosity = getattr(self.cfg, "num_curiosity_nets", 0) > 0
         dream = self.dream_trajectory(h_BxT, z_BxT, np.asarray(is_terminated).reshape(-1), H, gamma,
                                       u_dyn, act_noise, rng, margin)
         vt = self.compute_value_targets(dream["rewards_dreamed_t0_to_H_B"], dream["continues_dreamed_t0_to_H_B"],
-                                        dream["values_dreamed_t0_to_H_B"], gamma, lambda_)
+                                        dream["values_dreamed_t0_to_H_B"], gamma, lambda_,
+                                        dream["rewards_intrinsic_t1_to_H_B"] if use_curiosity else None)
         res = self.critic_loss(dream, vt)
         res.update(self.actor_loss(dream, vt, entropy_scale, return_normalization_decay))
         res["VALUE_TARGETS_H_B"] = vt
         res["dream_data"] = dream
         an, cn = self.group_names("actor"), self.group_names("critic")
         ag = torch.autograd.grad(res["ACTOR_L_total"], [self.P[n] for n in an], retain_graph=True, allow_unused=True)
-        cg = torch.autograd.grad(res["CRITIC_L_total"], [self.P[n] for n in cn], allow_unused=True)
+        cg = torch.autograd.grad(res["CRITIC_L_total"], [self.P[n] for n in cn], retain_graph=use_curiosity, allow_unused=True)
         ag = [g if g is not None else torch.zeros_like(self.P[n]) for n, g in zip(an, ag)]
         cg = [g if g is not None else torch.zeros_like(self.P[n]) for n, g in zip(cn, cg)]
         res["grads"] = {n: g.detach().clone() for n, g in list(zip(an, ag)) + list(zip(cn, cg))}
+        if use_curiosity:  # train_one_step.py:180-181, 201-212
+            dn = self.group_names("disagree")
+            res["DISAGREE_L_total"] = self.disagree_loss(dream)
+            res["DISAGREE_intrinsic_rewards_H_B"] = dream["rewards_intrinsic_t1_to_H_B"]
+            res["DISAGREE_intrinsic_rewards"] = dream["rewards_intrinsic_t1_to_H_B"].mean()
+            dg = torch.autograd.grad(res["DISAGREE_L_total"], [self.P[n] for n in dn], allow_unused=True)
+            dg = [g if g is not None else torch.zeros_like(self.P[n]) for n, g in zip(dn, dg)]
+            res["grads"].update({n: g.detach().clone() for n, g in zip(dn, dg)})
+            res["DISAGREE_gradients_maxabs"] = max(float(g.abs().max()) for g in dg)
         res["ACTOR_gradients_maxabs"] = max(float(g.abs().max()) for g in ag)
         res["CRITIC_gradients_maxabs"] = max(float(g.abs().max()) for g in cg)
         if apply:
             res["actor_grad_global_norm"], _ = self._apply("actor", an, ag, actor_grad_clip, 3e-5, 1e-5)
             res["critic_grad_global_norm"], _ = self._apply("critic", cn, cg, critic_grad_clip, 3e-5, 1e-5)
+            if use_curiosity:  # disagree_networks.py:43: Adam(1e-4, eps 1e-5)
+                res["disagree_grad_global_norm"], cl = self._apply("disagree", dn, dg, disagree_grad_clip, 1e-4, 1e-5)
+                res["DISAGREE_gradients_clipped_by_glob_norm_maxabs"] = max(float(g.abs().max()) for g in cl)
             self.update_ema()
         return res
 

@@ -10,7 +10,7 @@ index, concatenation orders, stop-gradients, loss weighting, lambda-returns, per
 EMA calls).  What is NOT pinned: TensorFlow's own arithmetic of the primitives, which the shim restates (SURVEY.md
 Appendix A.1) - see DESIGN.md section 5.
 
-    python tests/golden/make_reference_golden.py        # needs /root/reference; writes tests/golden/ref_*.npz
+    python tests/golden/make_reference_golden.py [case ...]   # needs /root/reference; writes tests/golden/ref_*.npz
 
 Each fixture holds: parameters before the update (spec names), the replay sample, every random number the
 reference consumed (uniforms of the categorical draws, normals of the Box actor), and the reference's outputs:
@@ -41,6 +41,11 @@ CASES = {
     "vec_disc": (dict(model_dimension="nano", A=2, discrete=True, obs_dim=4, B=3, T=5, H=4), 101),
     "vec_box": (dict(model_dimension="nano", A=2, discrete=False, obs_dim=3, B=3, T=5, H=4), 202),
     "img_disc": (dict(model_dimension="nano", A=3, discrete=True, image_obs=True, B=2, T=3, H=2), 303),
+    # use_curiosity=True: the Plan2Explore disagree nets (models/disagree_networks.py, losses/disagree_loss.py), 8 nets at nano
+    "vec_disc_cur": (dict(model_dimension="nano", A=3, discrete=True, obs_dim=4, B=3, T=4, H=3, use_curiosity=True,
+                          intrinsic_rewards_scale=0.1), 404),
+    "vec_box_cur": (dict(model_dimension="nano", A=2, discrete=False, obs_dim=3, B=2, T=4, H=3, use_curiosity=True,
+                         intrinsic_rewards_scale=0.5), 505),
 }
 
 
@@ -64,7 +69,8 @@ def build_reference(cfg):
     world_model = WorldModel(model_dimension=md, action_space=action_space, batch_length_T=cfg.T, encoder=encoder,
                              decoder=decoder, symlog_obs=cfg.symlog_obs)
     return DreamerModel(model_dimension=md, action_space=action_space, world_model=world_model, batch_size_B=cfg.B,
-                        batch_length_T=cfg.T, horizon_H=cfg.H)
+                        batch_length_T=cfg.T, horizon_H=cfg.H, use_curiosity=cfg.num_curiosity_nets > 0,
+                        intrinsic_rewards_scale=cfg.intrinsic_rewards_scale)
 
 
 def variable_map(dm, cfg):
@@ -117,6 +123,9 @@ def variable_map(dm, cfg):
     dense("critic.head", dm.critic.return_layer.reward_buckets_layer)
     mlp("critic_ema", dm.critic.mlp_ema, cfg.L)
     dense("critic_ema.head", dm.critic.return_layer_ema.reward_buckets_layer)
+    for n in range(cfg.num_curiosity_nets):
+        mlp(f"disagree.net{n}", dm.disagree_nets.mlps[n], cfg.L)
+        dense(f"disagree.net{n}.repr", dm.disagree_nets.representation_layers[n].z_generating_layer)
     return m
 
 
@@ -152,6 +161,8 @@ def run_case(name, kw, seed, dtype):
     sample = {k: tf.convert_to_tensor(v, dtype=dtype) for k, v in sample_np.items()}
     dm = build_reference(cfg)
     wm = dm.world_model
+    cur = cfg.num_curiosity_nets > 0
+    models = [("world_model", wm), ("actor", dm.actor), ("critic", dm.critic)] + ([("disagree", dm.disagree_nets)] if cur else [])
     grads_seen = []
     real_clip = tf.clip_by_global_norm
 
@@ -173,7 +184,7 @@ def run_case(name, kw, seed, dtype):
             world_model_forward_train_outs=fwd, is_terminated=tf.reshape(sample["is_terminated"], [-1]),
             horizon_H=H, gamma=0.997, lambda_=0.95, actor_grad_clip=100.0, critic_grad_clip=100.0,
             disagree_grad_clip=100.0, dreamer_model=dm, entropy_scale=3e-4, return_normalization_decay=0.99,
-            train_actor=True, use_curiosity=False)
+            train_actor=True, use_curiosity=cur)
         return r_wm, r_ac, n_wm_draws
 
     # ---- build pass: creates the lazily-built Keras variables; its numbers are discarded ----
@@ -190,11 +201,11 @@ def run_case(name, kw, seed, dtype):
             var.assign(torch.as_tensor(params0[n], dtype=dtype))
         # every trainable variable of the reference is in the table, in the right optimizer group
         by_id = {id(v): n for n, v in vm.items()}
-        for grp, model in (("world_model", wm), ("actor", dm.actor), ("critic", dm.critic)):
+        for grp, model in models:
             got = sorted(by_id[id(v)] for v in model.trainable_variables)
             want = sorted(p.name for p in param_spec(cfg) if p.group == grp)
             assert got == want, (grp, sorted(set(got) ^ set(want)))
-        for opt in (wm.optimizer, dm.actor.optimizer, dm.critic.optimizer):  # forget the build pass
+        for opt in [m.optimizer for _, m in models]:  # forget the build pass
             opt.iterations, opt.m, opt.v = 0, {}, {}
         dm.actor.ema_value_target_pct5.assign(np.nan)
         dm.actor.ema_value_target_pct95.assign(np.nan)
@@ -215,7 +226,10 @@ def run_case(name, kw, seed, dtype):
             assert len(wm_log) == 1 + 2 * cfg.T + 1 and wm_log[0][1].shape == (1, Zc)
             out[pre + "noise/u_post"] = np.stack([wm_log[1 + 2 * t][1] for t in range(cfg.T)], 0)      # [T,B,Zc]
             # dream_trajectory: actor(t0), then per step (prior z, actor)
-            assert len(ac_log) == 1 + 2 * H
+            # (+ with curiosity one draw per disagree net after the rollout: their RepresentationLayers sample a z that
+            # compute_intrinsic_rewards discards, disagree_networks.py:88-91 - not part of the noise contract)
+            assert len(ac_log) == 1 + 2 * H + cfg.num_curiosity_nets
+            assert all(d[1].shape == ((H + 1) * N, Zc) for d in ac_log[1 + 2 * H:])
             out[pre + "noise/act"] = np.stack([ac_log[0][1]] + [ac_log[2 + 2 * i][1] for i in range(H)], 0)
             out[pre + "noise/u_dyn"] = np.stack([ac_log[1 + 2 * i][1] for i in range(H)], 0)          # [H,N,Zc]
             assert out[pre + "noise/u_dyn"].shape == (H, N, Zc)
@@ -240,12 +254,15 @@ def run_case(name, kw, seed, dtype):
             out[pre + "dream/z_indices_t1_to_H_B"] = dd["z_states_prior_t0_to_H_B"].numpy()[1:].argmax(-1).astype(np.int32)
             if cfg.discrete:
                 out[pre + "dream/actions_ints_dreamed_t0_to_H_B"] = dd["actions_ints_dreamed_t0_to_H_B"].numpy().astype(np.int32)
+            if cur:
+                out[pre + "dream/rewards_intrinsic_t1_to_H_B"] = npf(dd["rewards_intrinsic_t1_to_H_B"])
+                out[pre + "dream/z_predicted_probs_N_HxB"] = np.stack([npf(p) for p in dd["z_predicted_probs_N_HxB"]], 0)
             for k, v in r_ac.items():
                 if k != "dream_data" and isinstance(v, torch.Tensor):
                     out[pre + "ac/" + k] = npf(v)
             # ---- gradients (the lists handed to tf.clip_by_global_norm: WM, actor, critic) ----------
-            assert len(grads_seen) == 3
-            for grp, model, gl in zip(("world_model", "actor", "critic"), (wm, dm.actor, dm.critic), grads_seen):
+            assert len(grads_seen) == len(models)   # the lists handed to tf.clip_by_global_norm: WM, actor, critic (, disagree)
+            for (grp, model), gl in zip(models, grads_seen):
                 for var, g in zip(model.trainable_variables, gl):
                     out[pre + "grad/" + by_id[id(var)]] = npf(g)
             out.update({pre + "param/" + n: npf(v) for n, v in vm.items()})
@@ -294,7 +311,10 @@ def run_case(name, kw, seed, dtype):
 
 
 def main():
+    only = sys.argv[1:]   # optional case names; default: all
     for name, (kw, seed) in CASES.items():
+        if only and name not in only:
+            continue
         for dtype, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
             out = run_case(name, kw, seed, dtype)
             path = os.path.join(HERE, f"ref_{name}_{tag}.npz")

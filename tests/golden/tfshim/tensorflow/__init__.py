@@ -60,6 +60,20 @@ class Tensor(torch.Tensor):
     def __bool__(self):
         return builtins.bool(self.detach().as_subclass(torch.Tensor).item())
 
+    # tf.Tensor is immutable: `a += b` rebinds the name to a new tensor. torch's in-place versions would also change every
+    # view of `a` (critic_loss.py:117-120 adds the intrinsic rewards to a slice of dream_data["rewards_dreamed_t0_to_H_B"]).
+    def __iadd__(self, other):
+        return self + other
+
+    def __isub__(self, other):
+        return self - other
+
+    def __imul__(self, other):
+        return self * other
+
+    def __itruediv__(self, other):
+        return self / other
+
 
 def _wrap(t):
     return t.as_subclass(Tensor) if not isinstance(t, Tensor) else t

@@ -21,6 +21,8 @@ from oracle.dreamer_oracle import Oracle
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ("vec_disc", "vec_box", "img_disc")
+# use_curiosity=True (models/disagree_networks.py, losses/disagree_loss.py): 8 Plan2Explore disagree nets at nano
+CUR_CASES = ("vec_disc_cur", "vec_box_cur")
 
 
 def load(case, tag):
@@ -62,8 +64,12 @@ DREAM_KEYS = ("h_states_t0_to_H_B", "rewards_dreamed_t0_to_H_B", "continues_drea
               "v_symlog_dreamed_ema_t0_to_H_B", "dream_loss_weights_t0_to_H_B")
 
 
+CUR_AC_KEYS = ("DISAGREE_L_total", "DISAGREE_intrinsic_rewards_H_B", "DISAGREE_intrinsic_rewards", "DISAGREE_gradients_maxabs",
+               "DISAGREE_gradients_clipped_by_glob_norm_maxabs")
+
+
 @pytest.mark.parametrize("tag,tol", (("f64", 1e-9), ("f32", 1e-4)))
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + CUR_CASES)
 def test_oracle_matches_reference_code(case, tag, tol):
     z, cfg = load(case, tag)
     dtype = torch.float64 if tag == "f64" else torch.float32
@@ -97,7 +103,12 @@ def test_oracle_matches_reference_code(case, tag, tol):
             (tnp(dd["continues_dreamed_t0_to_H_B"]) != g["dream/continues_dreamed_t0_to_H_B"]).sum())
         for k in DREAM_KEYS:
             err[f"s{step}.dream.{k}"] = rel(tnp(dd[k]), g["dream/" + k])
-        for k in AC_KEYS:
+        if cfg.num_curiosity_nets > 0:
+            err[f"s{step}.dream.rewards_intrinsic"] = rel(tnp(dd["rewards_intrinsic_t1_to_H_B"]), g["dream/rewards_intrinsic_t1_to_H_B"])
+            err[f"s{step}.dream.z_predicted_probs"] = rel(np.stack([tnp(p) for p in dd["z_predicted_probs_N_HxB"]], 0),
+                                                          g["dream/z_predicted_probs_N_HxB"])
+            assert any(n.startswith("disagree.") for n in ac["grads"])
+        for k in AC_KEYS + (CUR_AC_KEYS if cfg.num_curiosity_nets > 0 else ()):
             err[f"s{step}.{k}"] = rel(tnp(ac[k]), g["ac/" + k])
         for n, gr in ac["grads"].items():
             err[f"s{step}.grad.{n}"] = rel(tnp(gr), g["grad/" + n])
