@@ -84,9 +84,10 @@ class FixtureOracle:
             dream["actions_ints_dreamed_t0_to_H_B"] = g["dream/actions_ints_dreamed_t0_to_H_B"]
         ac = {k[3:]: T(v) for k, v in g.items() if k.startswith("ac/")}
         ac["dream_data"] = dream
-        names = self.group_names("actor") + self.group_names("critic")
+        groups = ("actor", "critic") + (("disagree",) if cfg.num_curiosity_nets > 0 else ())
+        names = [n for grp in groups for n in self.group_names(grp)]
         ac["grads"] = {n: T(g["grad/" + n]) for n in names}
-        for grp in ("actor", "critic"):
+        for grp in groups:
             ac[grp + "_grad_global_norm"] = float(np.sqrt(sum(
                 (g["grad/" + n].astype(np.float64) ** 2).sum() for n in self.group_names(grp))))
         for n in names + self.group_names("critic_ema"):
@@ -245,6 +246,12 @@ class ParityRun:
         self.cmp("dream.value_logits", t("dream.value_logits"), dream["values_symlog_dreamed_logits_t0_to_HxB"])
         self.cmp("dream.values_symlog_ema", t("dream.values_symlog_ema"), dream["v_symlog_dreamed_ema_t0_to_H_B"])
         self.cmp("dream.loss_weights", t("dream.loss_weights"), dream["dream_loss_weights_t0_to_H_B"])
+        cur = cfg.num_curiosity_nets > 0
+        if cur:  # Plan2Explore disagree nets (models/disagree_networks.py:47-95)
+            zp = dream["z_predicted_probs_N_HxB"]
+            zp = np.stack([to_np(p) for p in zp], 0) if isinstance(zp, (list, tuple)) else to_np(zp)
+            self.cmp("dream.z_predicted_probs", t("disagree.z_predicted_probs"), zp.reshape(cfg.num_curiosity_nets, (H + 1) * N, cfg.Zc, cfg.Zk))
+            self.cmp("dream.rewards_intrinsic", t("dream.rewards_intrinsic")[1:], dream["rewards_intrinsic_t1_to_H_B"])
         e.ac_loss_backward(3)
         self.cmp("ac.value_targets", t("ac.value_targets"), ac["VALUE_TARGETS_H_B"])
         for k in ("CRITIC_L_total_H_B", "CRITIC_L_neg_logp_of_value_targets_H_B", "CRITIC_L_slow_critic_regularization_H_B",
@@ -257,9 +264,15 @@ class ParityRun:
         # of its terms, not against the cancelled sum
         self.cmp_scalar("ac.ACTOR_L_total", t("ac.scalars")[3], ac["ACTOR_L_total"], to_np(ac["ACTOR_L_total_H_B"]))
         self.cmp("ac.pct_ema", t("ac.pct_ema"), np.array([ac["ACTOR_value_targets_pct5_ema"], ac["ACTOR_value_targets_pct95_ema"]]))
+        if cur:  # losses/disagree_loss.py:11-41, train_one_step.py:201-212
+            e.disagree_loss_backward()
+            self.cmp("ac.DISAGREE_L_total", t("disagree.scalars")[0], ac["DISAGREE_L_total"])
+            self.cmp_scalar("ac.DISAGREE_intrinsic_rewards", t("disagree.scalars")[1], ac["DISAGREE_intrinsic_rewards"],
+                            to_np(dream["rewards_intrinsic_t1_to_H_B"]))
         for n, g in ac["grads"].items():
             self.cmp("grad." + n, t("grad." + n), g)
-        before = {n: t(n).detach().cpu().numpy().copy() for g_ in ("actor", "critic") for n in o.group_names(g_)}
+        before = {n: t(n).detach().cpu().numpy().copy()
+                  for g_ in ("actor", "critic") + (("disagree",) if cur else ()) for n in o.group_names(g_)}
         if self.sync_grads:
             for n, g in ac["grads"].items():
                 e.write("grad." + n, g.to(torch.float32))
@@ -267,8 +280,11 @@ class ParityRun:
         e.optimizer_step("critic", 100.0, 3e-5, 1e-5, 0.98)
         self.cmp("ac.actor_grad_global_norm", t("opt.actor.stats")[0], ac["actor_grad_global_norm"])
         self.cmp("ac.critic_grad_global_norm", t("opt.critic.stats")[0], ac["critic_grad_global_norm"])
+        if cur:
+            e.optimizer_step("disagree", 100.0, 1e-4, 1e-5)  # run_experiment.py:252, disagree_networks.py:43
+            self.cmp("ac.disagree_grad_global_norm", t("opt.disagree.stats")[0], ac["disagree_grad_global_norm"])
         op = o.numpy_params()
-        for grp in ("actor", "critic", "critic_ema"):
+        for grp in ("actor", "critic", "critic_ema") + (("disagree",) if cur else ()):
             for n in o.group_names(grp):
                 self.cmp("param." + n, t(n), op[n])
                 if self.sync_grads and grp != "critic_ema":

@@ -142,7 +142,7 @@ def test_reference_fixture_pins_the_wraparound_action():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + CUR_CASES)
 def test_cuda_engine_matches_reference_code(case):
     """The CUDA engine (fp32 mode) against the vectors the reference's own code produced in float32, fed the very
     noise the reference consumed: drawn category / action indices, continue flags and two-hot bucket indices
