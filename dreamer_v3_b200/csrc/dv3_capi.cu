@@ -123,6 +123,12 @@ int dv3_read_tensor(dv3_engine* h, const char* name, void* dst, size_t nbytes, i
 int dv3_group_buffer(const dv3_engine* h, int group, int kind, void** ptr, int64_t* numel) {
   const Engine& e = h->e;
   if (group == 4 && kind == 1) { *ptr = e.grads[1]; *numel = e.grads_ac_numel; return 0; }   // actor + critic gradients, one span
+  if (group >= 6 && group <= 8 && kind == 1) {   // the world-model gradient buffer in three buckets (see dv3.h)
+    const long long lo = group == 6 ? e.wm_heads_off : group == 7 ? e.wm_enc_end : 0;
+    const long long hi = group == 6 ? e.numel[0] : group == 7 ? e.wm_heads_off : e.wm_enc_end;
+    *ptr = e.grads[0] + lo; *numel = hi - lo;
+    return 0;
+  }
   if (group == Engine::kDisagree && e.numel[group] == 0) return -1;   // curiosity is off
   if (group < 0 || (group > 3 && group != Engine::kDisagree) || kind < 0 || kind > 3 || (group == 3 && kind != 0)) return -1;
   float* p = kind == 0 ? e.params[group] : kind == 1 ? e.grads[group] : kind == 2 ? e.adam_m[group] : e.adam_v[group];

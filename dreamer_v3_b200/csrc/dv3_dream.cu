@@ -505,8 +505,12 @@ int Engine::train_ac_graph(const dv3_hparams* hp, uint64_t seed, cudaStream_t s)
 //   2: noise + dream rollout + value targets                    -> all-gather(value targets)
 //   3: percentiles, critic / actor losses and gradients          -> all-reduce(critic grads), all-reduce(actor grads)
 //   4: actor and critic clip + Adam (+ critic EMA)
+// Overlapped variant of piece 0 (large models), three gradient buckets in finalisation order: 5 = noise + observe forward +
+// losses + head backward + reverse-time scan -> the caller starts all-reduce(head-network grads, dv3_group_buffer group 6)
+// asynchronously; 6 = recurrent weight gradients, running next to that collective -> async all-reduce(group 7); 7 = encoder
+// backward, next to both -> all-reduce(encoder grads, group 8).
 int Engine::dp_piece(const dv3_hparams* hp, int piece, uint64_t seed, int use_graph, cudaStream_t s) {
-  if (piece < 0 || piece > 4) return fail("dp_piece: piece must be in [0, 4]");
+  if (piece < 0 || piece > 7) return fail("dp_piece: piece must be in [0, 7]");
   auto body = [&](cudaStream_t st) -> int {
     int rc = 0;
     switch (piece) {
@@ -522,6 +526,13 @@ int Engine::dp_piece(const dv3_hparams* hp, int piece, uint64_t seed, int use_gr
         if (!rc) rc = ac_loss_backward(hp, 1, st);
         break;
       case 3: rc = ac_loss_backward(hp, 2, st); break;
+      case 5:   // piece 0 cut once more, so that the all-reduce of the head gradients runs under piece 6
+        if (seed != 0) { bump_counter(st, noise_step); fill_noise(seed, 0, 1, true, st); }
+        rc = observe_forward(st);
+        if (!rc) rc = wm_loss_backward(st, 1);
+        break;
+      case 6: rc = wm_loss_backward(st, 2); break;
+      case 7: rc = wm_loss_backward(st, 4); break;
       default:
         if (hp->train_actor) rc = optimizer_step(1, hp->actor_grad_clip, hp->ac_lr, hp->ac_eps, -1.f, st);
         if (!rc) rc = optimizer_step(2, hp->critic_grad_clip, critic_lr(hp), critic_eps(hp), hp->critic_ema_decay, st);

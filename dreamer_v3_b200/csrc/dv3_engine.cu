@@ -64,6 +64,7 @@ void Engine::build_param_table() {
   } else {
     mlp(0, "enc", cfg.obs_dim, L);
   }
+  wm_enc_end = numel[0];
   mlp(0, "post", E + G, 1);
   dense(0, "post.repr", D, Z);
   mlp(0, "dyn", G, 1);
@@ -73,6 +74,7 @@ void Engine::build_param_table() {
   add(0, "seq.gru.kernel", {D, 3 * G});
   add(0, "seq.gru.recurrent", {G, 3 * G});
   add(0, "seq.gru.bias", {2, 3 * G});
+  wm_heads_off = numel[0];   // everything from here to the end of group 0 belongs to the reward / continue / decoder heads
   mlp(0, "rew", G + Z, L);
   dense(0, "rew.head", D, DV3_NB);
   mlp(0, "cont", G + Z, L);

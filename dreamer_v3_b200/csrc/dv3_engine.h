@@ -195,7 +195,7 @@ struct Engine {
 
   // ---- graph ----
   struct GraphSlot { cudaGraphExec_t exec = nullptr; long long launches = 0; dv3_hparams hp{}; uint64_t seed = 0; };
-  GraphSlot slot_wm, slot_ac, slot_piece[5];
+  GraphSlot slot_wm, slot_ac, slot_piece[8];
   int dp_piece(const dv3_hparams* hp, int piece, uint64_t seed, int use_graph, cudaStream_t s);
   template <class F> int run_graphed(GraphSlot& slot, const dv3_hparams* hp, uint64_t seed, cudaStream_t s, F body);
   int train_wm_graph(const dv3_hparams* hp, uint64_t seed, cudaStream_t s);
@@ -252,7 +252,10 @@ struct Engine {
 
   int initial_state(cudaStream_t s);
   int observe_forward(cudaStream_t s);
-  int wm_loss_backward(cudaStream_t s);
+  int wm_loss_backward(cudaStream_t s, int phase = 7);
+  // cuts of the flat world-model gradient buffer: [0, wm_enc_end) encoder | [wm_enc_end, wm_heads_off) recurrent part |
+  // [wm_heads_off, numel) reward / continue / decoder heads
+  long long wm_enc_end = 0, wm_heads_off = 0;
   int optimizer_step(int group, float clip, float lr, float eps, float ema_decay, cudaStream_t s);
   int dream_forward(float gamma, int start_from_observe, cudaStream_t s);
   void actor_fwd(long long row_off);

@@ -129,12 +129,18 @@ int Engine::observe_forward(cudaStream_t s) {
   return 0;
 }
 
-int Engine::wm_loss_backward(cudaStream_t s) {
+// phase bits: 1 = losses, head backward, reverse-time scan: after it the gradients of the head networks (reward, continue,
+// decoder - the tail of the flat world-model gradient buffer, dv3_group_buffer group 6) are final; 2 = the weight gradients of
+// the recurrent part (posterior, GRU, pre-GRU layer, initial state: the middle of the buffer, group 7); 4 = the encoder
+// backward (the front, group 8). A data-parallel caller starts the all-reduce of each bucket as soon as it is final and runs
+// it under the next phase (train_one_step.py of the package). 7 = everything.
+int Engine::wm_loss_backward(cudaStream_t s, int phase) {
   cur = s;
   const LnLayer& Wp = post_mlp.layers[0];
   const LnLayer& Wx = pre_mlp.layers[0];
   const LnLayer& Wd = dyn_mlp.layers[0];
   const int ldhz = T * (G + Z);
+  if (phase & 1) {
   cudaMemsetAsync(grads[0], 0, (size_t)numel[0] * 4, s);
 
   WmLossArgs a{};
@@ -275,6 +281,8 @@ int Engine::wm_loss_backward(cudaStream_t s) {
   }
   }
   phase_mark("wmb.scan_bwd");
+  }   // phase & 1
+  if (phase & 2) {
   // weight gradients, one N-row contraction each; they are independent of one another -> four concurrent chains.
   // In tensor-core mode both operands of each get a bf16 copy first (the scan kernels write fp32 only), so the
   // contractions run on the TMA-fed MN-major path.
@@ -312,6 +320,8 @@ int Engine::wm_loss_backward(cudaStream_t s) {
         tanh_bwd_acc(cur, dh0, h0, d_initial_h, G);
       }});
   phase_mark("wmb.wgrads");
+  }   // phase & 2
+  if (!(phase & 4)) return 0;
   // encoder
   mm(dp_pre, D, false, Wp.w, D, true, d_enc_out, E, N, E, D);
   encoder_bwd(d_enc_out);

@@ -12,7 +12,10 @@ from . import _lib
 from .spec import EngineConfig, param_spec
 
 # 4: gradient span of actor + critic; 5: the Plan2Explore disagree nets (curiosity)
-GROUP_IDS = {"world_model": 0, "actor": 1, "critic": 2, "critic_ema": 3, "actor_critic": 4, "disagree": 5}
+# 6 / 7 / 8: the world-model gradient buffer as three buckets in the order the backward pass finalises them (tail = reward /
+# continue / decoder heads | recurrent part | encoder)
+GROUP_IDS = {"world_model": 0, "actor": 1, "critic": 2, "critic_ema": 3, "actor_critic": 4, "disagree": 5,
+             "world_model_heads": 6, "world_model_recurrent": 7, "world_model_encoder": 8}
 
 
 class _CudaView:

@@ -6,12 +6,27 @@ Data parallelism: when torch.distributed is initialised with world_size > 1 (and
 that world_size), the flat gradient buffers are all-reduced (sum; the engine already divides the losses by
 the global batch) between the backward pass and the optimizer step, and the value targets are all-gathered
 before the percentile (the only statistic that does not decompose over the batch)."""
+import os
+
 import torch
 import torch.distributed as dist
 
 
 def _dp(engine):
     return engine.world_size > 1 and dist.is_available() and dist.is_initialized()
+
+
+# Gradient all-reduce overlapped with the backward pass (SURVEY 8e): worth its extra graph launch once the collective is
+# bandwidth-bound; below this many bytes of head-network gradients (XS: 2 MB, XL: 390 MB) one collective after the backward
+# pass is faster. DV3_DP_OVERLAP=1 / 0 forces it on / off.
+_OVERLAP_MIN_BYTES = 32 << 20
+
+
+def _overlap(engine):
+    env = os.environ.get("DV3_DP_OVERLAP")
+    if env is not None:
+        return env not in ("", "0")
+    return engine.group_buffer("world_model_heads", "grad").numel() * 4 >= _OVERLAP_MIN_BYTES
 
 
 def train_world_model_one_step(*, sample, batch_size_B, batch_length_T, grad_clip, world_model):
@@ -24,8 +39,21 @@ def train_world_model_one_step(*, sample, batch_size_B, batch_length_T, grad_cli
         # data parallel: graph-replayed pieces with the NCCL collectives between them
         e.hp.wm_grad_clip, e.hp.wm_lr, e.hp.wm_eps = float(grad_clip), opt.learning_rate, opt.epsilon
         seed = 0 if world_model._explicit_noise else world_model.noise_seed + 104729 * e.rank
-        e.dp_piece(0, seed)
-        dist.all_reduce(e.group_buffer("world_model", "grad"))
+        if _overlap(e):
+            # three buckets in finalisation order: the head networks' gradients (the tail of the flat buffer) are final after
+            # piece 5, the recurrent part's after piece 6; their all-reduces run on NCCL's stream next to the pieces that
+            # follow (which only write the buckets in front), the small encoder bucket closes the pass
+            e.dp_piece(5, seed)
+            w1 = dist.all_reduce(e.group_buffer("world_model_heads", "grad"), async_op=True)
+            e.dp_piece(6)
+            w2 = dist.all_reduce(e.group_buffer("world_model_recurrent", "grad"), async_op=True)
+            e.dp_piece(7)
+            dist.all_reduce(e.group_buffer("world_model_encoder", "grad"))
+            w1.wait()
+            w2.wait()
+        else:
+            e.dp_piece(0, seed)
+            dist.all_reduce(e.group_buffer("world_model", "grad"))
         e.dp_piece(1)
     else:
         # single process: forward + losses + BPTT + clip/Adam replayed as ONE CUDA graph (noise drawn inside it)

@@ -101,7 +101,9 @@ int dv3_write_tensor(dv3_engine* e, const char* name, const void* src, size_t nb
 int dv3_read_tensor(dv3_engine* e, const char* name, void* dst, size_t nbytes, int dst_is_device, void* stream, int sync);
 /* flat per-group views for the data-parallel all-reduce: kind in {0 param,1 grad,2 m,3 v}; group 4 with kind 1 = the actor and
  * critic gradient buffers as ONE span (adjacent in memory, zero padding between them): one collective for both; group 5 = the
- * disagree nets (curiosity) */
+ * disagree nets (curiosity); groups 6 / 7 / 8 with kind 1 = the world-model gradient buffer as three buckets in the order the
+ * backward pass finalises them: 6 = the head networks (reward, continue, decoder: the tail of the buffer, final after
+ * dv3_dp_piece 5), 7 = the recurrent part (posterior, prior, sequence model; after piece 6), 8 = the encoder (after piece 7) */
 int dv3_group_buffer(const dv3_engine* e, int group, int kind, void** ptr, int64_t* numel);
 
 /* ---- noise ------------------------------------------------------------------------------- */
@@ -169,7 +171,11 @@ int dv3_train_actor_critic_step(dv3_engine* e, const dv3_hparams* hp, uint64_t n
 int dv3_train_update(dv3_engine* e, const dv3_hparams* hp, uint64_t noise_seed, int use_graph, void* stream);
 /* Data-parallel update (world_size > 1): the same work cut at the collectives into five graph-replayed pieces;
  * piece 0: observe + WM losses/BPTT [all-reduce WM grads] 1: WM clip+Adam 2: dream + value targets [all-gather targets]
- * 3: critic/actor losses + gradients [all-reduce critic, actor grads] 4: actor/critic clip+Adam (+EMA). */
+ * 3: critic/actor losses + gradients [all-reduce critic, actor grads] 4: actor/critic clip+Adam (+EMA).
+ * Pieces 5 + 6 + 7 = piece 0 cut at the points where a gradient bucket becomes final, so that its all-reduce runs under the
+ * rest of the backward pass (SURVEY 8e "bucketed + overlapped"):
+ * 5: observe + WM losses + head backward + reverse-time scan [start all-reduce of group 6 asynchronously]
+ * 6: recurrent weight gradients [start all-reduce of group 7 asynchronously] 7: encoder backward [all-reduce group 8, wait]. */
 int dv3_dp_piece(dv3_engine* e, const dv3_hparams* hp, int piece, uint64_t noise_seed, int use_graph, void* stream);
 /* ---- replay sampler: the producer of the [B,T,...] sample dict ------------------------- */
 /* Row packing of EpisodeReplayBuffer.sample (utils/episode_replay_buffer.py:98-211) over an HBM-resident paged episode
