@@ -63,6 +63,8 @@ SIGNATURES = {
     "dv3_train_actor_critic_step": (_I, [_P, C.POINTER(Dv3Hparams), _U64, _I, _P]),
     "dv3_train_update": (_I, [_P, C.POINTER(Dv3Hparams), _U64, _I, _P]),
     "dv3_dp_piece": (_I, [_P, C.POINTER(Dv3Hparams), _I, _U64, _I, _P]),
+    "dv3_get_inference_calls": (_I64, [_P]),
+    "dv3_set_inference_calls": (_I, [_P, _I64]),
     "dv3_kernel_launch_count": (_I64, [_P]),
     "dv3_phase_report": (_I, [_P, _I, C.c_char_p, _SZ]),
     "dv3_scan_tc_schedule_check": (_I, [_I, _I, _I, _I, _I, _I]),

@@ -175,6 +175,12 @@ int dv3_ac_loss_backward(dv3_engine* h, const dv3_hparams* hp, int phase, void* 
   int rc = h->e.ac_loss_backward(hp, phase, S(stream));
   return rc ? rc : check_async(h->e);
 }
+int64_t dv3_get_inference_calls(const dv3_engine* h) { return (int64_t)h->e.inf_calls; }
+int dv3_set_inference_calls(dv3_engine* h, int64_t calls) {
+  if (calls < 0) return h->e.fail("dv3_set_inference_calls: negative count");
+  h->e.inf_calls = (unsigned long long)calls;
+  return 0;
+}
 int dv3_disagree_loss_backward(dv3_engine* h, void* stream) {
   int rc = h->e.disagree_loss_backward(S(stream));
   return rc ? rc : check_async(h->e);

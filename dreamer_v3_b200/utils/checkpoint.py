@@ -155,6 +155,13 @@ def save_checkpoint(path, dreamer_model, buffer=None, **counters):
     for m, _ in _models(e.cfg):
         state["step/" + m] = e.tensor(f"opt.{m}.step").detach().cpu().numpy()
     state["pct_ema"] = e.tensor("ac.pct_ema").detach().cpu().numpy()
+    # position of the device noise stream (counter-based Philox: seed + step), so that a resumed run draws what the
+    # uninterrupted one would have drawn
+    state["noise_step"] = e.tensor("noise_step").detach().cpu().numpy()
+    wm = dreamer_model.world_model
+    state["py_noise_step"] = np.int64(getattr(wm, "_noise_step", 0))
+    state["noise_seed"] = np.int64(getattr(wm, "noise_seed", 0))
+    state["inference_calls"] = np.int64(e.lib.dv3_get_inference_calls(e.h))
     np.savez(os.path.join(path, "dv3_state"), **state)
 
 
@@ -177,6 +184,12 @@ def load_checkpoint(path, dreamer_model, buffer=None):
             elif kind == "step":
                 e.tensor(f"opt.{name}.step").copy_(torch.from_numpy(z[k]))
         e.tensor("ac.pct_ema").copy_(torch.from_numpy(z["pct_ema"]))
+        if "noise_step" in z.files:
+            e.tensor("noise_step").copy_(torch.from_numpy(z["noise_step"]))
+            dreamer_model.world_model._noise_step = int(z["py_noise_step"])
+        if "noise_seed" in z.files:
+            dreamer_model.world_model.noise_seed = int(z["noise_seed"])
+            e._check(e.lib.dv3_set_inference_calls(e.h, int(z["inference_calls"])), "dv3_set_inference_calls")
     else:
         for m, stem in _models(e.cfg):
             set_weights(e, m, list(np.load(os.path.join(path, stem + ".npz"), allow_pickle=True)["weights"]))

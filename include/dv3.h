@@ -197,6 +197,10 @@ int dv3_replay_gather(const void* obs_store, int obs_is_u8, int normalize_u8, in
 int64_t dv3_replay_plan(int B, int T, int page, const int64_t* chunk_cum, const int32_t* chunk_ep, const int32_t* chunk_ts0, int64_t n_chunks,
                         const int32_t* ep_len, const uint8_t* ep_term, const int64_t* ep_page_off, const int32_t* pages,
                         const int64_t* draws, int64_t n_draws, int32_t* plan);
+/* Host-side position of the acting step's device noise stream (the number of dv3_forward_inference calls that drew noise), so
+ * that a checkpoint can carry it and a resumed run (run_experiment.py:224-233) draws what the uninterrupted one would have. */
+int64_t dv3_get_inference_calls(const dv3_engine* e);
+int dv3_set_inference_calls(dv3_engine* e, int64_t calls);
 int64_t dv3_kernel_launch_count(const dv3_engine* e); /* kernels of this library launched (or replayed) so far */
 /* Measurement aid of bench.py (no reference counterpart): enable = 1 / 0 switches the recording of CUDA events at the
  * labelled phase boundaries of the non-graph path (encoder | observe scan | heads | losses | head backward | backward
