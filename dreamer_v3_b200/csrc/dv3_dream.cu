@@ -391,12 +391,19 @@ void Engine::disagree_forward() {
   const int W = G + Z, Nd = (int)dis.size();
   copy_2d(s, dr_hz, W, dis_in, dis_ld, R, W);
   copy_2d(s, dr_act, A, dis_in + W, dis_ld, R, A);
-  for (int n = 0; n < Nd; ++n) {
+  void* in16 = R >= 128 ? twin_of(dis_in) : nullptr;   // one bf16 copy of the shared input for the first layer of every net
+  if (in16) to_bf16(s, dis_in, dis_ld, in16, dis_ld, R, dis_ld);
+  // the nets are independent chains: four of them in flight (main stream + the auxiliary ones)
+  auto net_fwd = [&](int n) {
     DisagreeNet& d = dis[n];
-    mlp_fwd(d.mlp, d.act, dis_in, dis_ld, R);
+    mlp_fwd(d.mlp, d.act, dis_in, dis_ld, R, 0, in16);
     mm(d.act.act.back(), D, false, d.repr.w, Z, false, d.logits, Z, R, Z, D, d.repr.bias, 0.f, d.act.act16.empty() ? nullptr : d.act.act16.back());
-    repr_fwd(s, d.logits, Z, d.probs, Z, nullptr, 0, nullptr, 0, nullptr, 0, R, Zc, Zk, 0);
-  }
+    repr_fwd(cur, d.logits, Z, d.probs, Z, nullptr, 0, nullptr, 0, nullptr, 0, R, Zc, Zk, 0);
+  };
+  std::vector<std::function<void()>> groups;
+  for (int g = 0; g < 4 && g < Nd; ++g)
+    groups.push_back([&, g] { for (int n = g; n < Nd; n += 4) net_fwd(n); });
+  run_branches(groups);
   disagree_std_rows(s, dis_probs, (size_t)R * Z, Nd, R, Z, dis_std);
   disagree_intrinsic(s, dis_std, R, N, cfg.intrinsic_rewards_scale, dis_ri, dis_scalars);
 }
@@ -415,7 +422,7 @@ int Engine::disagree_loss_backward(cudaStream_t s) {
     disagree_loss_rows(s, d.probs, dr_hz + (size_t)N * W + G, W, HN, Z, 1.0f / (float)HN, dis_dprobs, dis_mse + (size_t)n * HN);
     repr_bwd(s, d.logits, Z, nullptr, 0, dis_dprobs, Z, dis_dlogits, Z, (int)HN, Zc, Zk);
     dense_bwd(d.repr, d.act.act.back(), D, dis_dlogits, Z, dis_s0, D, 0.f, true, HN);
-    mlp_bwd(d.mlp, d.act, dis_in, dis_ld, dis_s0, dis_s1, nullptr, 0, true, HN);
+    mlp_bwd(d.mlp, d.act, dis_in, dis_ld, dis_s0, dis_s1, nullptr, 0, true, HN, 0, HN >= 128 ? twin_of(dis_in) : nullptr);
   }
   disagree_loss_total(s, dis_mse, (long long)Nd * HN, HN, dis_scalars);
   phase_mark("ac.disagree_bwd");

@@ -504,6 +504,7 @@ void Engine::layout() {
   if (Nd > 0) {
     dis_ld = (G + Z + A + 7) & ~7;
     dis_in = af("", {Rl, dis_ld});
+    if (Rl >= 128) twin_alloc(dis_in, (size_t)Rl * dis_ld);
     dis_probs = af("disagree.z_predicted_probs", {Nd, Rl, Zc, Zk});
     for (int n = 0; n < Nd; ++n) {
       dis[n].act = alloc_mlp_act("disagree.net" + std::to_string(n), Rl, L);

@@ -49,10 +49,13 @@ def test_curiosity_changes_the_value_targets():
     off = ParityRun(EngineConfig.make("XXS", **kw), steps=1)
     try:
         t_on, t_off = on.engine.tensor, off.engine.tensor
-        assert torch.allclose(t_on("dream.rewards"), t_off("dream.rewards"), rtol=0, atol=1e-6)   # same weights, same noise: same dream
+        # same weights, same noise: the same dream (up to the summation order of split-K atomics)
+        assert torch.allclose(t_on("dream.rewards"), t_off("dream.rewards"), rtol=1e-4, atol=1e-5), \
+            float((t_on("dream.rewards") - t_off("dream.rewards")).abs().max())
         ri = t_on("dream.rewards_intrinsic")
-        assert float(ri.abs().max()) > 0 and abs(float(ri.mean())) < 1e-6 * float(ri.abs().max()) + 1e-7   # centred over all rows
-        assert float((t_on("ac.value_targets") - t_off("ac.value_targets")).abs().max()) > 1e-4
+        assert float(ri.abs().max()) > 0 and abs(float(ri.mean())) < 1e-4 * float(ri.abs().max()) + 1e-6, \
+            (float(ri.mean()), float(ri.abs().max()))   # centred over all rows
+        assert float((t_on("ac.value_targets") - t_off("ac.value_targets")).abs().max()) > 1e-3 * float(ri.abs().max())
     finally:
         on.close(); off.close()
 
