@@ -70,6 +70,8 @@ __global__ void to_bf16_scalar_kernel(const float* __restrict__ src, int lds, __
 }
 
 // ---- LayerNorm + SiLU: one warp per row ----------------------------------------------------------------
+// (SiLU's sigmoid is the ex2.approx one of dv3_device.cuh in every LayerNorm kernel of this file, rel. error ~1e-6: the exact
+//  expf + IEEE division cost as much as the memory traffic - 10^6 x 32 rows forward 165 -> 64 us with it)
 // templated on the per-lane element count so that narrow rows (conv channels, D = 24..96) do not pay for 32 predicated
 // iterations: EPL = ceil(D / 32) rounded up to a power of two
 // RU rows per warp iteration: on narrow rows (conv channels over ~10^6 pixel rows) one 128-byte load in flight per warp
@@ -138,7 +140,7 @@ __global__ void ln_silu_fwd_kernel(const float* __restrict__ x, int ldx, const f
         const int c = lane + 32 * i;
         if (c < D) {
           const float n = (v[u][i] - mean) * rstd * gm[i] + bt[i];
-          const float o = n * sigmoidf_(n);
+          const float o = n * sigmoid_fast(n);
           yr[c] = o;
           if (y16 != nullptr) y16[(size_t)r * ldy + c] = __float2bfloat16_rn(o);  // bf16 twin for the TMA-fed GEMM
         }
@@ -200,7 +202,7 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ dy, int lddy, const
         if (c < D) {
           const float xhat = (xh[u][i] - mean) * rs[u];
           const float n = xhat * gm[i] + bt[i];
-          const float sg = sigmoidf_(n);
+          const float sg = sigmoid_fast(n);
           const float dn = dxh[u][i] * (sg * (1.f + n * (1.f - sg)));   // 0 for rows beyond the end (dy = 0)
           ag[i] += dn * xhat;
           ab[i] += dn;
@@ -262,6 +264,226 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ dy, int lddy, const
   }
 }
 
+// ---- narrow rows (conv channels over ~10^6 pixel rows: D = 24 ... 192, D % 4 == 0, 16-byte aligned rows) -------------------
+// A warp-per-row layout moves 128 bytes per warp-load at D = 32 and spends 10 shuffles per row: latency-bound at ~1.6 - 2 TB/s.
+// Here LPR = 8 / 16 / 32 lanes share a row (32 / LPR rows per warp-load, each lane one float4 per chunk, VPL chunks per lane), so
+// every load instruction of a warp moves up to 512 contiguous bytes and a row reduction is log2(LPR) shuffles; RU such steps are
+// in flight together. The rows of one warp iteration are consecutive in memory. The sigmoid is the ex2.approx one of the scan
+// kernels (rel. error ~1e-6): at 8 bytes per element the exact expf + division was half of the kernel's time.
+template <int LPR, int VPL, int RU>
+__global__ void __launch_bounds__(256) ln_silu_fwd_narrow_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, float* __restrict__ y, int ldy,
+                                                                  float* __restrict__ mean_out, float* __restrict__ rstd_out, int sstride,
+                                                                  long long rows, int D, __nv_bfloat16* __restrict__ y16) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane / LPR, cl = lane % LPR;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float invD = 1.f / (float)D;
+  float4 gm[VPL], bt[VPL];
+  bool act[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = 4 * (cl + LPR * i);
+    act[i] = c < D;
+    gm[i] = act[i] ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    bt[i] = act[i] ? __ldg(reinterpret_cast<const float4*>(beta + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long base = warp0 * (RPW * RU); base < rows; base += nwarps * (RPW * RU)) {
+    float4 v[RU][VPL];
+    float s[RU], q[RU];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const long long r = base + u * RPW + sub;
+      s[u] = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        v[u][i] = (r < rows && act[i]) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)r * ldx + 4 * (cl + LPR * i)))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        s[u] += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < RU; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      s[u] *= invD;   // mean
+      q[u] = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        if (act[i]) {
+          const float dx = v[u][i].x - s[u], dy = v[u][i].y - s[u], dz = v[u][i].z - s[u], dw = v[u][i].w - s[u];
+          q[u] += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < RU; ++u) q[u] += __shfl_xor_sync(0xffffffffu, q[u], o);
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const long long r = base + u * RPW + sub;
+      if (r >= rows) continue;
+      const float mean = s[u];
+      const float rstd = rsqrtf(q[u] * invD + DV3_LN_EPS);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        if (!act[i]) continue;
+        const int c = 4 * (cl + LPR * i);
+        float4 o;
+        { const float n = (v[u][i].x - mean) * rstd * gm[i].x + bt[i].x; o.x = n * sigmoid_fast(n); }
+        { const float n = (v[u][i].y - mean) * rstd * gm[i].y + bt[i].y; o.y = n * sigmoid_fast(n); }
+        { const float n = (v[u][i].z - mean) * rstd * gm[i].z + bt[i].z; o.z = n * sigmoid_fast(n); }
+        { const float n = (v[u][i].w - mean) * rstd * gm[i].w + bt[i].w; o.w = n * sigmoid_fast(n); }
+        *reinterpret_cast<float4*>(y + (size_t)r * ldy + c) = o;
+        if (y16 != nullptr) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+          uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(y16 + (size_t)r * ldy + c) = pk;
+        }
+      }
+      if (cl == 0) {
+        if (mean_out) mean_out[r * sstride] = mean;
+        if (rstd_out) rstd_out[r * sstride] = rstd;
+      }
+    }
+  }
+}
+
+template <int LPR, int VPL, int RU>
+__global__ void __launch_bounds__(256) ln_silu_bwd_narrow_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ x, int ldx,
+                                                                  const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  float* __restrict__ dx, int lddx, float* __restrict__ dgamma,
+                                                                  float* __restrict__ dbeta, int sstride, long long rows, int D,
+                                                                  __nv_bfloat16* __restrict__ dx16) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane / LPR, cl = lane % LPR;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float invD = 1.f / (float)D;
+  float4 gm[VPL], bt[VPL], ag[VPL], ab[VPL];
+  bool act[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = 4 * (cl + LPR * i);
+    act[i] = c < D;
+    gm[i] = act[i] ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    bt[i] = act[i] ? __ldg(reinterpret_cast<const float4*>(beta + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long base = warp0 * (RPW * RU); base < rows; base += nwarps * (RPW * RU)) {
+    float4 xh[RU][VPL], dh[RU][VPL];
+    float s1[RU], s2[RU], rs[RU], mu[RU];
+    // every load of the RU x RPW rows first
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const long long r = base + u * RPW + sub;
+      const bool rok = r < rows;
+      mu[u] = rok ? mean_in[r * sstride] : 0.f;
+      rs[u] = rok ? rstd_in[r * sstride] : 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const bool ok = rok && act[i];
+        const int c = 4 * (cl + LPR * i);
+        xh[u][i] = ok ? __ldg(reinterpret_cast<const float4*>(x + (size_t)r * ldx + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dh[u][i] = ok ? __ldg(reinterpret_cast<const float4*>(dy + (size_t)r * lddy + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        if (!act[i]) continue;
+        // per component: xhat, n = xhat g + b, dn = dy silu'(n); accumulates dgamma / dbeta, leaves (xhat, dn g) in place
+#define DV3_LN_COMP(F_)                                                                  \
+        {                                                                                \
+          const float xhat = (xh[u][i].F_ - mu[u]) * rs[u];                              \
+          const float n = xhat * gm[i].F_ + bt[i].F_;                                    \
+          const float sg = sigmoid_fast(n);                                                 \
+          const float dn = dh[u][i].F_ * (sg * (1.f + n * (1.f - sg)));                  \
+          ag[i].F_ += dn * xhat; ab[i].F_ += dn;                                         \
+          xh[u][i].F_ = xhat; dh[u][i].F_ = dn * gm[i].F_;                               \
+          a1 += dh[u][i].F_; a2 += dh[u][i].F_ * xhat;                                   \
+        }
+        DV3_LN_COMP(x) DV3_LN_COMP(y) DV3_LN_COMP(z) DV3_LN_COMP(w)
+#undef DV3_LN_COMP
+      }
+      s1[u] = a1; s2[u] = a2;
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        s1[u] += __shfl_xor_sync(0xffffffffu, s1[u], o);
+        s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], o);
+      }
+    }
+    if (dx != nullptr) {
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const long long r = base + u * RPW + sub;
+        if (r >= rows) continue;
+        const float m1 = s1[u] * invD, m2 = s2[u] * invD;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          if (!act[i]) continue;
+          const int c = 4 * (cl + LPR * i);
+          float4 o;
+          o.x = rs[u] * (dh[u][i].x - m1 - xh[u][i].x * m2);
+          o.y = rs[u] * (dh[u][i].y - m1 - xh[u][i].y * m2);
+          o.z = rs[u] * (dh[u][i].z - m1 - xh[u][i].z * m2);
+          o.w = rs[u] * (dh[u][i].w - m1 - xh[u][i].w * m2);
+          *reinterpret_cast<float4*>(dx + (size_t)r * lddx + c) = o;
+          if (dx16 != nullptr) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+            uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(dx16 + (size_t)r * lddx + c) = pk;
+          }
+        }
+      }
+    }
+  }
+  if (dgamma != nullptr) {
+    // the row groups of a warp hold partial sums of the same columns: fold them with shuffles, then one shared-memory atomic
+    // per column and warp, one global atomic per column and block
+    __shared__ float sdg[4 * LPR * VPL], sdb[4 * LPR * VPL];
+    for (int c = threadIdx.x; c < 4 * LPR * VPL; c += blockDim.x) { sdg[c] = 0.f; sdb[c] = 0.f; }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) {
+        ag[i].x += __shfl_xor_sync(0xffffffffu, ag[i].x, o); ag[i].y += __shfl_xor_sync(0xffffffffu, ag[i].y, o);
+        ag[i].z += __shfl_xor_sync(0xffffffffu, ag[i].z, o); ag[i].w += __shfl_xor_sync(0xffffffffu, ag[i].w, o);
+        ab[i].x += __shfl_xor_sync(0xffffffffu, ab[i].x, o); ab[i].y += __shfl_xor_sync(0xffffffffu, ab[i].y, o);
+        ab[i].z += __shfl_xor_sync(0xffffffffu, ab[i].z, o); ab[i].w += __shfl_xor_sync(0xffffffffu, ab[i].w, o);
+      }
+      if (sub == 0 && act[i]) {
+        const int c = 4 * (cl + LPR * i);
+        atomicAdd(&sdg[c], ag[i].x); atomicAdd(&sdg[c + 1], ag[i].y); atomicAdd(&sdg[c + 2], ag[i].z); atomicAdd(&sdg[c + 3], ag[i].w);
+        atomicAdd(&sdb[c], ab[i].x); atomicAdd(&sdb[c + 1], ab[i].y); atomicAdd(&sdb[c + 2], ab[i].z); atomicAdd(&sdb[c + 3], ab[i].w);
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      atomicAdd(&dgamma[c], sdg[c]);
+      atomicAdd(&dbeta[c], sdb[c]);
+    }
+  }
+}
+
 // ---- vectorised LayerNorm + SiLU (D a multiple of 128, 16-byte aligned rows): lane owns V chunks of 4 consecutive columns,
 // chunk i at column 4 * (lane + 32 i); all loads of a row are 128-bit and issued together ----
 __device__ __forceinline__ void store_bf16x4(__nv_bfloat16* p, float a, float b, float c, float d) {
@@ -309,10 +531,10 @@ __global__ void __launch_bounds__(256) ln_silu_fwd_v4_kernel(const float* __rest
       const int c0 = 4 * (lane + 32 * i);
       float4 o;
       float n;
-      n = (v[i].x - mean) * rstd * g[i].x + be[i].x; o.x = n * sigmoidf_(n);
-      n = (v[i].y - mean) * rstd * g[i].y + be[i].y; o.y = n * sigmoidf_(n);
-      n = (v[i].z - mean) * rstd * g[i].z + be[i].z; o.z = n * sigmoidf_(n);
-      n = (v[i].w - mean) * rstd * g[i].w + be[i].w; o.w = n * sigmoidf_(n);
+      n = (v[i].x - mean) * rstd * g[i].x + be[i].x; o.x = n * sigmoid_fast(n);
+      n = (v[i].y - mean) * rstd * g[i].y + be[i].y; o.y = n * sigmoid_fast(n);
+      n = (v[i].z - mean) * rstd * g[i].z + be[i].z; o.z = n * sigmoid_fast(n);
+      n = (v[i].w - mean) * rstd * g[i].w + be[i].w; o.w = n * sigmoid_fast(n);
       *reinterpret_cast<float4*>(y + (size_t)r * ldy + c0) = o;
       if (y16 != nullptr) store_bf16x4(y16 + (size_t)r * ldy + c0, o.x, o.y, o.z, o.w);
     }
@@ -358,7 +580,7 @@ __global__ void __launch_bounds__(256) ln_silu_bwd_v4_kernel(const float* __rest
       {                                                                          \
         const float xhat = (xh[i].c_ - mean) * rstd;                             \
         const float n = xhat * g[i].c_ + be[i].c_;                               \
-        const float sg = sigmoidf_(n);                                           \
+        const float sg = sigmoid_fast(n);                                           \
         const float dn = dh[i].c_ * (sg * (1.f + n * (1.f - sg)));               \
         ag[i].c_ += dn * xhat; ab[i].c_ += dn;                                   \
         xh[i].c_ = xhat; dh[i].c_ = dn * g[i].c_;                                \
@@ -804,6 +1026,21 @@ void ln_silu_fwd(cudaStream_t s, const float* x, int ldx, const float* gamma, co
     count_launch();
     return;
   }
+  static const bool no_narrow = std::getenv("DV3_NO_LN_NARROW") != nullptr;   // (A/B switch: the warp-per-row kernels below)
+  if (!no_narrow && D % 4 == 0 && D <= 256 && ldx % 4 == 0 && ldy % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0 &&
+      (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0 && (uintptr_t)y16_ % 8 == 0) {
+    // conv channel counts 24 ... 192 (and the small test sizes): several rows per warp, 128-bit accesses
+#define DV3_LN_FWDN(L_, V_, RU_)                                                                                                   \
+    launch_pdl(ln_silu_fwd_narrow_kernel<L_, V_, RU_>, dim3(grid_for(cdiv(rows, (32 / L_) * RU_), kThreads / 32, 148 * 8)), dim3(kThreads), \
+               0, s, x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, D, y16)
+    if (D <= 32) DV3_LN_FWDN(8, 1, 4);
+    else if (D <= 64) DV3_LN_FWDN(16, 1, 4);
+    else if (D <= 128) DV3_LN_FWDN(32, 1, 4);
+    else DV3_LN_FWDN(32, 2, 2);
+#undef DV3_LN_FWDN
+    count_launch();
+    return;
+  }
 #define DV3_LN_FWD(E_, RU_) launch_pdl(ln_silu_fwd_kernel<E_, RU_>, dim3(grid), dim3(kThreads), 0, s, x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, D, y16)
   if (D <= 32) DV3_LN_FWD(1, 4);
   else if (D <= 64) DV3_LN_FWD(2, 4);
@@ -831,6 +1068,20 @@ void ln_silu_bwd(cudaStream_t s, const float* dy, int lddy, const float* x, int 
       case 5: DV3_LN_BWD4(5); break; case 6: DV3_LN_BWD4(6); break; case 7: DV3_LN_BWD4(7); break; default: DV3_LN_BWD4(8); break;
     }
 #undef DV3_LN_BWD4
+    count_launch();
+    return;
+  }
+  static const bool no_narrow = std::getenv("DV3_NO_LN_NARROW") != nullptr;
+  if (!no_narrow && D % 4 == 0 && D <= 256 && ldx % 4 == 0 && lddy % 4 == 0 && (dx == nullptr || lddx % 4 == 0) && (uintptr_t)x % 16 == 0 &&
+      (uintptr_t)dy % 16 == 0 && (uintptr_t)dx % 16 == 0 && (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0 && (uintptr_t)dx16_ % 8 == 0) {
+#define DV3_LN_BWDN(L_, V_, RU_)                                                                                                   \
+    launch_pdl(ln_silu_bwd_narrow_kernel<L_, V_, RU_>, dim3(grid_for(cdiv(rows, (32 / L_) * RU_), kThreads / 32, 148 * 4)), dim3(kThreads), \
+               0, s, dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, D, dx16)
+    if (D <= 32) DV3_LN_BWDN(8, 1, 4);
+    else if (D <= 64) DV3_LN_BWDN(16, 1, 4);
+    else if (D <= 128) DV3_LN_BWDN(32, 1, 2);
+    else DV3_LN_BWDN(32, 2, 1);
+#undef DV3_LN_BWDN
     count_launch();
     return;
   }

@@ -108,8 +108,11 @@ def test_gemm_strided_views():
 def test_ln_silu():
     from dreamer_v3_b200 import ops
     rng = np.random.default_rng(4)
-    for D in (16, 24, 255, 256, 640, 1024):
-        x = (rng.standard_normal((300, D)) * 3 + 1).astype(np.float32)
+    # 255: scalar warp-per-row kernel; 4 ... 192 (D % 4 == 0): the several-rows-per-warp kernels of the conv channel counts;
+    # multiples of 128: the vectorised warp-per-row kernel
+    for D, rows in ((4, 7), (16, 300), (24, 300), (32, 4099), (48, 1001), (64, 300), (96, 4099), (192, 301), (255, 300), (256, 300),
+                    (640, 300), (1024, 300)):
+        x = (rng.standard_normal((rows, D)) * 3 + 1).astype(np.float32)
         g = (1 + 0.1 * rng.standard_normal(D)).astype(np.float32)
         b = (0.1 * rng.standard_normal(D)).astype(np.float32)
         want = torch.nn.functional.silu(torch.nn.functional.layer_norm(
