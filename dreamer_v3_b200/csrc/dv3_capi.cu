@@ -276,6 +276,7 @@ int dv3_op_gemm_shadow(const float* A, int lda, int ta, const void* Bh, int ldbh
 int dv3_op_ln_silu_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
                        float* dx, float* dgamma, float* dbeta, int64_t rows, int D, void* stream) {
   if (D > 1024) return -1;
+  dv3::set_ln_fast(true);
   dv3::ln_silu_bwd(S(stream), dy, D, x, D, mean, rstd, gamma, beta, dx, D, dgamma, dbeta, 1, rows, D);
   return op_done();
 }
@@ -309,6 +310,7 @@ int dv3_op_gemm_bf16_wgrad(const void* Xh, int ldx, const void* dYh, int ldy, fl
 }
 int dv3_op_ln_silu(const float* x, const float* gamma, const float* beta, float* y, int64_t rows, int D, void* stream) {
   if (D > 1024) return -1;
+  dv3::set_ln_fast(true);
   dv3::ln_silu_fwd(S(stream), x, D, gamma, beta, y, D, nullptr, nullptr, 1, rows, D);
   return op_done();
 }

@@ -90,6 +90,9 @@ void copy_2d(cudaStream_t s, const float* src, int lds, float* dst, int ldd, int
 void add_2d(cudaStream_t s, const float* src, int lds, float* dst, int ldd, int rows, int cols);  // dst += src
 void tanh_fwd(cudaStream_t s, const float* x, float* y, int n);
 
+// which LayerNorm + SiLU kernels the two calls below launch: false = the exact-sigmoid warp-per-row kernels (fp32 parity mode),
+// true = ex2.approx sigmoid + the rows-per-warp kernels for narrow rows (tensor-core mode; the default of the isolated ops)
+void set_ln_fast(bool on);
 // y = silu(LayerNorm(x)); saves mean/rstd per row. Rows addressed as x + r*ldx.
 void ln_silu_fwd(cudaStream_t s, const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy,
                  float* mean, float* rstd, int sstride, long long rows, int D, void* y16 = nullptr);  // y16: bf16 twin of y, same ld

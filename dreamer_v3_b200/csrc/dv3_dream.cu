@@ -157,6 +157,7 @@ bool Engine::dream_rollout_tc(cudaStream_t s, int start_from_observe) {
 
 int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
   cur = s;
+  set_ln_fast(cfg.compute_mode == 1);
   last_gamma = gamma;
   const LnLayer& Wx = pre_mlp.layers[0];
   const LnLayer& Wd = dyn_mlp.layers[0];
@@ -262,6 +263,7 @@ int Engine::dream_forward(float gamma, int start_from_observe, cudaStream_t s) {
 
 int Engine::ac_loss_backward(const dv3_hparams* hp, int phase, cudaStream_t s) {
   cur = s;
+  set_ln_fast(cfg.compute_mode == 1);
   const int W = G + Z;
   const long long HN = (long long)H * N;
   AcArgs a{};
@@ -414,6 +416,7 @@ void Engine::disagree_forward() {
 int Engine::disagree_loss_backward(cudaStream_t s) {
   if (dis.empty()) return fail("disagree_loss_backward: the engine was created without curiosity nets");
   cur = s;
+  set_ln_fast(cfg.compute_mode == 1);
   const int W = G + Z, Nd = (int)dis.size();
   const long long HN = (long long)H * N;
   cudaMemsetAsync(grads[kDisagree], 0, (size_t)numel[kDisagree] * 4, s);

@@ -16,6 +16,12 @@ inline int grid_for(long long n, int per_block = kThreads, int cap = 148 * 16) {
   return (int)b;
 }
 
+// SiLU's sigmoid in the LayerNorm kernels: exact (expf + IEEE division) in the fp32 parity mode, ex2.approx based (rel. error
+// ~1e-6) in the tensor-core mode, where it halves the time of these 8 - 16 byte / element passes. The engine sets the switch at
+// every entry point from its compute mode (set_ln_fast); the isolated ops run the fast kernels.
+static bool g_ln_fast = true;
+__device__ __forceinline__ float silu_sigmoid(float n, int fast) { return fast ? sigmoid_fast(n) : sigmoidf_(n); }
+
 __global__ void symlog_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = symlog_dev(x[i]);
@@ -80,7 +86,7 @@ template <int kLnMaxPerLane, int RU>
 __global__ void ln_silu_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ y, int ldy,
                                    float* __restrict__ mean_out, float* __restrict__ rstd_out, int sstride, long long rows, int D,
-                                   __nv_bfloat16* __restrict__ y16) {
+                                   __nv_bfloat16* __restrict__ y16, int fast) {
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -140,7 +146,7 @@ __global__ void ln_silu_fwd_kernel(const float* __restrict__ x, int ldx, const f
         const int c = lane + 32 * i;
         if (c < D) {
           const float n = (v[u][i] - mean) * rstd * gm[i] + bt[i];
-          const float o = n * sigmoid_fast(n);
+          const float o = n * silu_sigmoid(n, fast);
           yr[c] = o;
           if (y16 != nullptr) y16[(size_t)r * ldy + c] = __float2bfloat16_rn(o);  // bf16 twin for the TMA-fed GEMM
         }
@@ -159,7 +165,7 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ dy, int lddy, const
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ dx, int lddx, float* __restrict__ dgamma,
                                    float* __restrict__ dbeta, int sstride, long long rows, int D,
-                                   __nv_bfloat16* __restrict__ dx16) {
+                                   __nv_bfloat16* __restrict__ dx16, int fast) {
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -202,7 +208,7 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ dy, int lddy, const
         if (c < D) {
           const float xhat = (xh[u][i] - mean) * rs[u];
           const float n = xhat * gm[i] + bt[i];
-          const float sg = sigmoid_fast(n);
+          const float sg = silu_sigmoid(n, fast);
           const float dn = dxh[u][i] * (sg * (1.f + n * (1.f - sg)));   // 0 for rows beyond the end (dy = 0)
           ag[i] += dn * xhat;
           ab[i] += dn;
@@ -274,7 +280,7 @@ template <int LPR, int VPL, int RU>
 __global__ void __launch_bounds__(256) ln_silu_fwd_narrow_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, float* __restrict__ y, int ldy,
                                                                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int sstride,
-                                                                  long long rows, int D, __nv_bfloat16* __restrict__ y16) {
+                                                                  long long rows, int D, __nv_bfloat16* __restrict__ y16, int fast) {
   pdl_trigger();
   pdl_wait();
   constexpr int RPW = 32 / LPR;
@@ -338,10 +344,10 @@ __global__ void __launch_bounds__(256) ln_silu_fwd_narrow_kernel(const float* __
         if (!act[i]) continue;
         const int c = 4 * (cl + LPR * i);
         float4 o;
-        { const float n = (v[u][i].x - mean) * rstd * gm[i].x + bt[i].x; o.x = n * sigmoid_fast(n); }
-        { const float n = (v[u][i].y - mean) * rstd * gm[i].y + bt[i].y; o.y = n * sigmoid_fast(n); }
-        { const float n = (v[u][i].z - mean) * rstd * gm[i].z + bt[i].z; o.z = n * sigmoid_fast(n); }
-        { const float n = (v[u][i].w - mean) * rstd * gm[i].w + bt[i].w; o.w = n * sigmoid_fast(n); }
+        { const float n = (v[u][i].x - mean) * rstd * gm[i].x + bt[i].x; o.x = n * silu_sigmoid(n, fast); }
+        { const float n = (v[u][i].y - mean) * rstd * gm[i].y + bt[i].y; o.y = n * silu_sigmoid(n, fast); }
+        { const float n = (v[u][i].z - mean) * rstd * gm[i].z + bt[i].z; o.z = n * silu_sigmoid(n, fast); }
+        { const float n = (v[u][i].w - mean) * rstd * gm[i].w + bt[i].w; o.w = n * silu_sigmoid(n, fast); }
         *reinterpret_cast<float4*>(y + (size_t)r * ldy + c) = o;
         if (y16 != nullptr) {
           __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
@@ -363,7 +369,7 @@ __global__ void __launch_bounds__(256) ln_silu_bwd_narrow_kernel(const float* __
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   float* __restrict__ dx, int lddx, float* __restrict__ dgamma,
                                                                   float* __restrict__ dbeta, int sstride, long long rows, int D,
-                                                                  __nv_bfloat16* __restrict__ dx16) {
+                                                                  __nv_bfloat16* __restrict__ dx16, int fast) {
   pdl_trigger();
   pdl_wait();
   constexpr int RPW = 32 / LPR;
@@ -411,7 +417,7 @@ __global__ void __launch_bounds__(256) ln_silu_bwd_narrow_kernel(const float* __
         {                                                                                \
           const float xhat = (xh[u][i].F_ - mu[u]) * rs[u];                              \
           const float n = xhat * gm[i].F_ + bt[i].F_;                                    \
-          const float sg = sigmoid_fast(n);                                                 \
+          const float sg = silu_sigmoid(n, fast);                                                 \
           const float dn = dh[u][i].F_ * (sg * (1.f + n * (1.f - sg)));                  \
           ag[i].F_ += dn * xhat; ab[i].F_ += dn;                                         \
           xh[u][i].F_ = xhat; dh[u][i].F_ = dn * gm[i].F_;                               \
@@ -496,7 +502,7 @@ template <int V>
 __global__ void __launch_bounds__(256) ln_silu_fwd_v4_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float* __restrict__ y, int ldy,
                                                              float* __restrict__ mean_out, float* __restrict__ rstd_out, int sstride,
-                                                             long long rows, __nv_bfloat16* __restrict__ y16) {
+                                                             long long rows, __nv_bfloat16* __restrict__ y16, int fast) {
   pdl_trigger();
   pdl_wait();
   constexpr int D = V * 128;
@@ -531,10 +537,10 @@ __global__ void __launch_bounds__(256) ln_silu_fwd_v4_kernel(const float* __rest
       const int c0 = 4 * (lane + 32 * i);
       float4 o;
       float n;
-      n = (v[i].x - mean) * rstd * g[i].x + be[i].x; o.x = n * sigmoid_fast(n);
-      n = (v[i].y - mean) * rstd * g[i].y + be[i].y; o.y = n * sigmoid_fast(n);
-      n = (v[i].z - mean) * rstd * g[i].z + be[i].z; o.z = n * sigmoid_fast(n);
-      n = (v[i].w - mean) * rstd * g[i].w + be[i].w; o.w = n * sigmoid_fast(n);
+      n = (v[i].x - mean) * rstd * g[i].x + be[i].x; o.x = n * silu_sigmoid(n, fast);
+      n = (v[i].y - mean) * rstd * g[i].y + be[i].y; o.y = n * silu_sigmoid(n, fast);
+      n = (v[i].z - mean) * rstd * g[i].z + be[i].z; o.z = n * silu_sigmoid(n, fast);
+      n = (v[i].w - mean) * rstd * g[i].w + be[i].w; o.w = n * silu_sigmoid(n, fast);
       *reinterpret_cast<float4*>(y + (size_t)r * ldy + c0) = o;
       if (y16 != nullptr) store_bf16x4(y16 + (size_t)r * ldy + c0, o.x, o.y, o.z, o.w);
     }
@@ -551,7 +557,7 @@ __global__ void __launch_bounds__(256) ln_silu_bwd_v4_kernel(const float* __rest
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              float* __restrict__ dx, int lddx, float* __restrict__ dgamma,
                                                              float* __restrict__ dbeta, int sstride, long long rows,
-                                                             __nv_bfloat16* __restrict__ dx16) {
+                                                             __nv_bfloat16* __restrict__ dx16, int fast) {
   pdl_trigger();
   pdl_wait();
   constexpr int D = V * 128;
@@ -580,7 +586,7 @@ __global__ void __launch_bounds__(256) ln_silu_bwd_v4_kernel(const float* __rest
       {                                                                          \
         const float xhat = (xh[i].c_ - mean) * rstd;                             \
         const float n = xhat * g[i].c_ + be[i].c_;                               \
-        const float sg = sigmoid_fast(n);                                           \
+        const float sg = silu_sigmoid(n, fast);                                           \
         const float dn = dh[i].c_ * (sg * (1.f + n * (1.f - sg)));               \
         ag[i].c_ += dn * xhat; ab[i].c_ += dn;                                   \
         xh[i].c_ = xhat; dh[i].c_ = dn * g[i].c_;                                \
@@ -1010,14 +1016,17 @@ void add_2d(cudaStream_t s, const float* src, int lds, float* dst, int ldd, int 
   launch_pdl(op_2d_kernel<2>, dim3(grid_for((long long)rows * cols)), dim3(kThreads), 0, s, src, lds, dst, ldd, rows, cols); count_launch();
 }
 
+void set_ln_fast(bool on) { g_ln_fast = on; }
+
 void ln_silu_fwd(cudaStream_t s, const float* x, int ldx, const float* gamma, const float* beta, float* y, int ldy,
                  float* mean, float* rstd, int sstride, long long rows, int D, void* y16_) {
   if (rows <= 0) return;
+  const int fast = g_ln_fast ? 1 : 0;
   const int grid = grid_for(rows, kThreads / 32, 148 * 8);
   __nv_bfloat16* y16 = reinterpret_cast<__nv_bfloat16*>(y16_);
   if (D % 128 == 0 && D <= 1024 && ldx % 4 == 0 && ldy % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0 &&
       (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0 && (uintptr_t)y16_ % 8 == 0) {
-#define DV3_LN_FWD4(V_) launch_pdl(ln_silu_fwd_v4_kernel<V_>, dim3(grid), dim3(kThreads), 0, s, x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, y16)
+#define DV3_LN_FWD4(V_) launch_pdl(ln_silu_fwd_v4_kernel<V_>, dim3(grid), dim3(kThreads), 0, s, x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, y16, fast)
     switch (D / 128) {   // every width that is a multiple of 128 (dense 256 / 512 / 640 / 768 / 1024, wide conv channels)
       case 1: DV3_LN_FWD4(1); break; case 2: DV3_LN_FWD4(2); break; case 3: DV3_LN_FWD4(3); break; case 4: DV3_LN_FWD4(4); break;
       case 5: DV3_LN_FWD4(5); break; case 6: DV3_LN_FWD4(6); break; case 7: DV3_LN_FWD4(7); break; default: DV3_LN_FWD4(8); break;
@@ -1027,12 +1036,12 @@ void ln_silu_fwd(cudaStream_t s, const float* x, int ldx, const float* gamma, co
     return;
   }
   static const bool no_narrow = std::getenv("DV3_NO_LN_NARROW") != nullptr;   // (A/B switch: the warp-per-row kernels below)
-  if (!no_narrow && D % 4 == 0 && D <= 256 && ldx % 4 == 0 && ldy % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0 &&
+  if (fast && !no_narrow && D % 4 == 0 && D <= 256 && ldx % 4 == 0 && ldy % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0 &&
       (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0 && (uintptr_t)y16_ % 8 == 0) {
     // conv channel counts 24 ... 192 (and the small test sizes): several rows per warp, 128-bit accesses
 #define DV3_LN_FWDN(L_, V_, RU_)                                                                                                   \
     launch_pdl(ln_silu_fwd_narrow_kernel<L_, V_, RU_>, dim3(grid_for(cdiv(rows, (32 / L_) * RU_), kThreads / 32, 148 * 8)), dim3(kThreads), \
-               0, s, x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, D, y16)
+               0, s, x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, D, y16, fast)
     if (D <= 32) DV3_LN_FWDN(8, 1, 4);
     else if (D <= 64) DV3_LN_FWDN(16, 1, 4);
     else if (D <= 128) DV3_LN_FWDN(32, 1, 4);
@@ -1041,7 +1050,7 @@ void ln_silu_fwd(cudaStream_t s, const float* x, int ldx, const float* gamma, co
     count_launch();
     return;
   }
-#define DV3_LN_FWD(E_, RU_) launch_pdl(ln_silu_fwd_kernel<E_, RU_>, dim3(grid), dim3(kThreads), 0, s, x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, D, y16)
+#define DV3_LN_FWD(E_, RU_) launch_pdl(ln_silu_fwd_kernel<E_, RU_>, dim3(grid), dim3(kThreads), 0, s, x, ldx, gamma, beta, y, ldy, mean, rstd, sstride, rows, D, y16, fast)
   if (D <= 32) DV3_LN_FWD(1, 4);
   else if (D <= 64) DV3_LN_FWD(2, 4);
   else if (D <= 128) DV3_LN_FWD(4, 2);
@@ -1055,6 +1064,7 @@ void ln_silu_bwd(cudaStream_t s, const float* dy, int lddy, const float* x, int 
                  const float* rstd, const float* gamma, const float* beta, float* dx, int lddx, float* dgamma,
                  float* dbeta, int sstride, long long rows, int D, void* dx16_) {
   if (rows <= 0) return;
+  const int fast = g_ln_fast ? 1 : 0;
   const int grid = grid_for(rows, kThreads / 32, 148 * 4);
   __nv_bfloat16* dx16 = reinterpret_cast<__nv_bfloat16*>(dx16_);
   if (D % 128 == 0 && D <= 1024 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)dy % 16 == 0 &&
@@ -1062,7 +1072,7 @@ void ln_silu_bwd(cudaStream_t s, const float* dy, int lddy, const float* x, int 
     // with gain / offset gradients every block ends with 2 D global atomics: fewer, longer blocks (measured at 16384 x 256:
     // 17.4 / 13.1 / 18.5 / 19.7 us for 1 / 2 / 4 / 8 blocks per SM)
     const int grid4 = grid_for(rows, kThreads / 32, dgamma != nullptr ? 148 * 2 : 148 * 8);
-#define DV3_LN_BWD4(V_) launch_pdl(ln_silu_bwd_v4_kernel<V_>, dim3(grid4), dim3(kThreads), 0, s, dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, dx16)
+#define DV3_LN_BWD4(V_) launch_pdl(ln_silu_bwd_v4_kernel<V_>, dim3(grid4), dim3(kThreads), 0, s, dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, dx16, fast)
     switch (D / 128) {
       case 1: DV3_LN_BWD4(1); break; case 2: DV3_LN_BWD4(2); break; case 3: DV3_LN_BWD4(3); break; case 4: DV3_LN_BWD4(4); break;
       case 5: DV3_LN_BWD4(5); break; case 6: DV3_LN_BWD4(6); break; case 7: DV3_LN_BWD4(7); break; default: DV3_LN_BWD4(8); break;
@@ -1072,11 +1082,11 @@ void ln_silu_bwd(cudaStream_t s, const float* dy, int lddy, const float* x, int 
     return;
   }
   static const bool no_narrow = std::getenv("DV3_NO_LN_NARROW") != nullptr;
-  if (!no_narrow && D % 4 == 0 && D <= 256 && ldx % 4 == 0 && lddy % 4 == 0 && (dx == nullptr || lddx % 4 == 0) && (uintptr_t)x % 16 == 0 &&
+  if (fast && !no_narrow && D % 4 == 0 && D <= 256 && ldx % 4 == 0 && lddy % 4 == 0 && (dx == nullptr || lddx % 4 == 0) && (uintptr_t)x % 16 == 0 &&
       (uintptr_t)dy % 16 == 0 && (uintptr_t)dx % 16 == 0 && (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0 && (uintptr_t)dx16_ % 8 == 0) {
 #define DV3_LN_BWDN(L_, V_, RU_)                                                                                                   \
     launch_pdl(ln_silu_bwd_narrow_kernel<L_, V_, RU_>, dim3(grid_for(cdiv(rows, (32 / L_) * RU_), kThreads / 32, 148 * 4)), dim3(kThreads), \
-               0, s, dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, D, dx16)
+               0, s, dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, D, dx16, fast)
     if (D <= 32) DV3_LN_BWDN(8, 1, 4);
     else if (D <= 64) DV3_LN_BWDN(16, 1, 4);
     else if (D <= 128) DV3_LN_BWDN(32, 1, 2);
@@ -1085,7 +1095,7 @@ void ln_silu_bwd(cudaStream_t s, const float* dy, int lddy, const float* x, int 
     count_launch();
     return;
   }
-#define DV3_LN_BWD(E_, RU_) launch_pdl(ln_silu_bwd_kernel<E_, RU_>, dim3(grid), dim3(kThreads), 0, s, dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, D, dx16)
+#define DV3_LN_BWD(E_, RU_) launch_pdl(ln_silu_bwd_kernel<E_, RU_>, dim3(grid), dim3(kThreads), 0, s, dy, lddy, x, ldx, mean, rstd, gamma, beta, dx, lddx, dgamma, dbeta, sstride, rows, D, dx16, fast)
   if (D <= 32) DV3_LN_BWD(1, 4);
   else if (D <= 64) DV3_LN_BWD(2, 4);
   else if (D <= 128) DV3_LN_BWD(4, 2);

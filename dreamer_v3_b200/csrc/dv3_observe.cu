@@ -15,6 +15,7 @@ namespace dv3 {
 
 int Engine::initial_state(cudaStream_t s) {
   cur = s;
+  set_ln_fast(cfg.compute_mode == 1);
   const LnLayer& Wd = dyn_mlp.layers[0];
   tanh_fwd(s, initial_h, h0, G);  // world_model.py:128
   mm(h0, G, false, Wd.w, D, false, q0_pre, D, 1, D, G);
@@ -26,6 +27,7 @@ int Engine::initial_state(cudaStream_t s) {
 
 int Engine::observe_forward(cudaStream_t s) {
   cur = s;
+  set_ln_fast(cfg.compute_mode == 1);
   const LnLayer& Wp = post_mlp.layers[0];
   const LnLayer& Wx = pre_mlp.layers[0];
   const LnLayer& Wd = dyn_mlp.layers[0];
@@ -136,6 +138,7 @@ int Engine::observe_forward(cudaStream_t s) {
 // it under the next phase (train_one_step.py of the package). 7 = everything.
 int Engine::wm_loss_backward(cudaStream_t s, int phase) {
   cur = s;
+  set_ln_fast(cfg.compute_mode == 1);
   const LnLayer& Wp = post_mlp.layers[0];
   const LnLayer& Wx = pre_mlp.layers[0];
   const LnLayer& Wd = dyn_mlp.layers[0];
@@ -334,6 +337,7 @@ int Engine::wm_loss_backward(cudaStream_t s, int phase) {
 int Engine::forward_inference(int rows, uint64_t noise_seed, cudaStream_t s) {
   if (rows < 1 || rows > B) return fail("forward_inference: rows must be in [1, B]");
   cur = s;
+  set_ln_fast(cfg.compute_mode == 1);
   const LnLayer& Wp = post_mlp.layers[0];
   const LnLayer& Wx = pre_mlp.layers[0];
   const int W = G + Z;
