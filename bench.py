@@ -151,6 +151,15 @@ def synthetic_sample(cfg, seed):
     return make_synthetic_sample(cfg, seed=seed)
 
 
+def workload_config(wid, world):
+    """The `config` block of the JSON line: the workload both arms are measured on (the reference arm runs "on your arm's
+    config", so the two lines carry the same dict; what describes an implementation - graph replay, compute mode - is in the
+    top-level `engine` block of the GPU arm)."""
+    return {"workload": WORKLOADS[wid]["name"], "id": wid, "B_per_gpu": 16, "T": 64, "H": 15, "global_batch": 16 * world,
+            "parallelism": f"dp{world}" if world > 1 else "single",
+            "l2": "GPU arm: 256 MiB buffer written between timed steps (L2 flush); not applicable to the CPU reference arm"}
+
+
 # ------------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     """The reference algorithm on the box's host cores: the oracle restatement (TensorFlow is not installable in
@@ -189,7 +198,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "updates/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt16 * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[wid]["name"], "id": wid, "B_per_gpu": 16, "T": 64, "H": 15},
+        "config": workload_config(wid, max(1, args.gpus)),
         "cpu_baseline": {"value": val, "unit": "updates/s", "cores": cores, "kind": "port", "sample": samp},
         "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference algorithm, PyTorch-CPU restatement (TensorFlow unavailable in this image)",
@@ -507,11 +516,9 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.mode == 0 else "bf16", "data": "synthetic",
         "precision_note": ("fp32 everywhere" if args.mode == 0 else "bf16 operands / fp32 accumulate on tcgen05 for contractions with >= 128 rows; fp32 masters, losses and optimizer"),
-        "config": {"workload": job.w["name"], "id": wid, "B_per_gpu": B, "T": T, "H": H, "global_batch": B * world,
-                   "parallelism": f"dp{world}" if world > 1 else "single",
-                   "l2": "256 MiB buffer written between timed steps (L2 flush)",
-                   "cuda_graph": ("whole update = one graph replay" if job.use_graph else
-                                  "five graph-replayed pieces cut at the NCCL collectives (dv3_dp_piece)" if world > 1 and not args.no_graph
+        "config": workload_config(wid, world),
+        "engine": {"cuda_graph": ("whole update = one graph replay" if job.use_graph else
+                                  "graph-replayed pieces cut at the NCCL collectives (dv3_dp_piece)" if world > 1 and not args.no_graph
                                   else False), "compute_mode": args.mode},
         "value_note": ("weak scaling: B=16 replay rows per GPU; value = B16xT64 batches consumed per second over all ranks "
                        "(= optimizer updates/s x n_gpus); literal updates/s of the sharded global batch are in strong_xl"),
