@@ -121,3 +121,33 @@ def test_scan_tc_schedule_check_rejects_other_sizes():
     assert lib.dv3_scan_tc_schedule_check(16, 64, 256, 256, 1024, 148) == 1     # XS: cluster kernel
     assert lib.dv3_scan_tc_schedule_check(17, 64, 512, 512, 1024, 148) == 1     # more than 16 rows
     assert lib.dv3_scan_tc_schedule_check(16, 1024, 512, 512, 1024, 148) == 1   # is_first flags do not fit shared memory
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """dv3_config / dv3_hparams / dv3_tensor_desc are mirrored by hand in _lib.py: compile a probe against include/dv3.h (gcc, no
+    CUDA needed) and compare sizes and the offsets of the fields added last (curiosity, the critic's / disagree nets' Adam)."""
+    import ctypes
+    import shutil
+    import subprocess
+    from dreamer_v3_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "probe.c"
+    src.write_text(
+        '#include <stddef.h>\n#include <stdio.h>\n#include "dv3.h"\n'
+        'int main(void) {\n'
+        '  printf("%zu %zu %zu\\n", sizeof(dv3_config), sizeof(dv3_hparams), sizeof(dv3_tensor_desc));\n'
+        '  printf("%zu %zu %zu\\n", offsetof(dv3_config, device), offsetof(dv3_config, num_curiosity_nets), offsetof(dv3_config, intrinsic_rewards_scale));\n'
+        '  printf("%zu %zu %zu %zu\\n", offsetof(dv3_hparams, train_actor), offsetof(dv3_hparams, critic_lr), offsetof(dv3_hparams, disagree_grad_clip), offsetof(dv3_hparams, disagree_eps));\n'
+        '  printf("%zu %zu %zu\\n", offsetof(dv3_tensor_desc, shape), offsetof(dv3_tensor_desc, kind), offsetof(dv3_tensor_desc, group));\n'
+        '  return 0;\n}\n')
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    got = [int(x) for x in out]
+    C, H, D = _lib.Dv3Config, _lib.Dv3Hparams, _lib.Dv3TensorDesc
+    want = [ctypes.sizeof(C), ctypes.sizeof(H), ctypes.sizeof(D),
+            C.device.offset, C.num_curiosity_nets.offset, C.intrinsic_rewards_scale.offset,
+            H.train_actor.offset, H.critic_lr.offset, H.disagree_grad_clip.offset, H.disagree_eps.offset,
+            D.shape.offset, D.kind.offset, D.group.offset]
+    assert got == want, (got, want)
