@@ -61,7 +61,7 @@ def test_curiosity_changes_the_value_targets():
 
 
 @pytest.mark.parametrize("discrete", (True, False))
-def test_curiosity_api_graph_and_stepwise_paths_agree_with_oracle(discrete):
+def test_curiosity_api_matches_oracle_over_three_updates(discrete):
     """train_actor_and_critic_one_step(use_curiosity=True) through the reference-facing API: the one-graph path (dreaming
     from the engine's own observe pass) against the oracle over three updates, result keys of train_one_step.py:201-231."""
     from dreamer_v3_b200.models.components import MLP, VectorDecoder
